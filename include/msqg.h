@@ -1,0 +1,184 @@
+/*
+ * msqg.h -- C ABI of the B200-native msqg multilayer-QG timestep.
+ *
+ * Two layers, both plain C (no C++/torch types cross this boundary):
+ *
+ *  (1) handle-based device layer `msqg_*`: what a host program binds to replace
+ *      the reference's function-pointer plugin
+ *          advance = advance_qg; update = update_qg;        (msqg/qg.h:922-923)
+ *      and the solver/diagnostic calls around it.  All field buffers are HOST
+ *      pointers to C-contiguous double [layer][y][x] (x fastest), the layout of
+ *      pyset_field/pyget_field (msqg/qg.h:1164-1189); device memory is owned by
+ *      the handle; calls are synchronous unless stated.
+ *
+ *  (2) the reference's own global-state surface (same names, same argument
+ *      meaning as the SWIG module `qg`, msqg/qg.i:29-36, msqg/qg_bfn.i:10-46,
+ *      and the driver msqg/qg.c): read_params, init_grid, set_vars, set_const,
+ *      create_outdir, backup_config, trash_vars, set_vars_bfn, trash_vars_bfn,
+ *      pystep_bfn, pyq2p, pyp2q, run.  Implemented in C on top of layer (1).
+ *
+ * Error behaviour: the reference calls exit(0) on fatal input errors
+ * (msqg/qg.h:735-738,991-995,1009-1012); layer (1) returns a negative code
+ * instead and layer (2) prints the reference's message and returns the code.
+ * There is NO CPU fallback: every compute entry point fails with
+ * MSQG_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MSQG_H
+#define MSQG_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSQG_MAXL 32
+
+enum {
+  MSQG_OK = 0,
+  MSQG_ERR_ARG = -1,     /* bad argument / unsupported configuration */
+  MSQG_ERR_CUDA = -2,    /* CUDA failure or no device */
+  MSQG_ERR_FILE = -3,    /* file missing (read_params, msqg/qg.h:735-738) */
+  MSQG_ERR_CONFIG = -4,  /* thickness == 0 or Rom <= 0 (msqg/qg.h:990-1012) */
+  MSQG_ERR_NOCONV = -5   /* informational: multigrid hit NITERMAX */
+};
+
+/* keys of params.in (msqg/qg.h:698-731) + derived values (:739-746) */
+typedef struct msqg_params {
+  int N, nl, ediag, varRo, nptr, flsrv;
+  double L0, Rom, Ekb, Eks, tau0, Re, Re4, sbc, beta, afilt, Lfmax;
+  double DT, tend, dtout, dtflt, CFL;
+  double Fr[MSQG_MAXL], dh[MSQG_MAXL], upg[MSQG_MAXL], vpg[MSQG_MAXL];
+  double iRe, iRe4;
+  int stochastic;            /* the -D_STOCHASTIC build (msqg/qg.c:25) */
+  double tr_stoch, itr_stoch, amp_stoch;
+  int mode_pv_invert;        /* MODE_PV_INVERT (msqg/qg.h:4) as a runtime knob */
+} msqg_params;
+
+/* mgstats (Basilisk poisson.h; in-tree copy mspg/elliptic.h:118-123) */
+typedef struct msqg_mgstats {
+  int i;
+  double resb, resa, sum;
+  int nrelax;
+} msqg_mgstats;
+
+/* field-list ids for msqg_set_field / msqg_get_field */
+enum {
+  MSQG_PSI = 0,   /* pol      msqg/qg.h:24  */
+  MSQG_Q,         /* qol      msqg/qg.h:23  */
+  MSQG_PSIPG,     /* ppl      msqg/qg.h:36  */
+  MSQG_FR,        /* Frl      msqg/qg.h:43  (nl scalars, nl-1 meaningful) */
+  MSQG_QFORC,     /* q_forcl  msqg/qg.h:30  */
+  MSQG_TOPO,      /* topo     msqg/qg.h:50  (1 scalar) */
+  MSQG_RD,        /* Rd       msqg/qg.h:47  (1 scalar) */
+  MSQG_SSTOCH,    /* s_stochl msqg/qg_stochastic.h:14 */
+  MSQG_ZETA,      /* zetal    msqg/qg.h:25  */
+  MSQG_DQ,        /* "updates" list of the predictor-corrector */
+  MSQG_STR,       /* strl     msqg/qg.h:37  */
+  MSQG_NSTOCH,    /* n_stochl msqg/qg_stochastic.h:13 */
+  MSQG_IBU,       /* iBul     msqg/qg.h:42  */
+  MSQG_CL2M,      /* cl2m     msqg/qg.h:40  (nl*nl scalars) */
+  MSQG_CM2L,      /* cm2l     msqg/qg.h:41  */
+  MSQG_PM,        /* pom      msqg/qg.h:33  */
+  MSQG_QM,        /* qom      msqg/qg.h:32  */
+  MSQG_TMP,       /* tmpl     msqg/qg.h:57  */
+  MSQG_ZETAP,     /* zetapl   msqg/qg.h:26  */
+  MSQG_QPRED,     /* "predictor" list of the predictor-corrector */
+  MSQG_NFIELDS
+};
+
+typedef struct msqg_model msqg_model;
+
+/* ---- (1) handle-based device layer ------------------------------------ */
+
+void msqg_default_params(msqg_params *p);
+/* read_params (msqg/qg.h:689-761) into *p (which must hold defaults). */
+int msqg_read_params(const char *path, msqg_params *p);
+
+/* init_grid(N) + set_vars() (msqg/qg.h:837-925): allocates every layer list on
+ * `device`, zero fields, ppl = vpg*x - upg*y, Frl = Fr.  N must be a power of
+ * two >= 32, 2 <= nl <= 12, sbc == 0. */
+int msqg_create(const msqg_params *p, int device, msqg_model **out);
+void msqg_destroy(msqg_model *m);                 /* trash_vars, qg.h:1130-1154 */
+/* run on this CUDA stream (a cudaStream_t passed as void*); default: own stream */
+int msqg_set_stream(msqg_model *m, void *cuda_stream);
+int msqg_nfields(msqg_model *m, int id);          /* scalars in list `id` (0 if absent) */
+/* pyset_field (qg.h:1164-1175): host [nf][N][N] -> cells, then boundary() */
+int msqg_set_field(msqg_model *m, int id, const double *host);
+/* pyget_field (qg.h:1177-1189) */
+int msqg_get_field(msqg_model *m, int id, double *host);
+int msqg_set_flag_topo(msqg_model *m, int flag);  /* flag_topo, qg.h:971-977 */
+/* set_const (qg.h:931-1116) minus the file reads (done by the C host, which
+ * pushes file contents through msqg_set_field first) */
+int msqg_set_const(msqg_model *m);
+
+/* invertq(pol, q) (qg.h:113-163); q_id = MSQG_Q or MSQG_QPRED */
+int msqg_invertq(msqg_model *m, int q_id);
+int msqg_comp_q(msqg_model *m);                   /* comp_q(pol,qol), qg.h:396-403 */
+/* mgstats of the last invertq; mode < 0: mgpsi (last solve), else modal solve */
+int msqg_last_mgstats(msqg_model *m, int mode, msqg_mgstats *out);
+long msqg_total_cycles(msqg_model *m);
+
+/* update_qg(evolving=q_id, updates=DQ, dtmax) (qg.h:609-650); returns the new
+ * dtmax through *dtmax_out (timestep() chain, qg.h:383-391). */
+int msqg_update(msqg_model *m, int q_id, double dtmax, double *dtmax_out);
+/* advance_qg(output, input, updates=DQ, dt) (qg.h:594-606) */
+int msqg_advance(msqg_model *m, int out_id, int in_id, double dt);
+/* one iteration of Basilisk run() (predictor-corrector.h), fused on device:
+ *   dt = dtnext(update(q, DT)); qpred = q + dt/2*F(q); q += dt*F(qpred)
+ * tnext < 0: no event rounding (dt = update's dtmax).  returns dt in *dt_out. */
+int msqg_step(msqg_model *m, double t, double tnext, double *dt_out, double *tnext_out);
+int msqg_ke1(msqg_model *m, double *ke);          /* writestdout, qg.c:101-106 */
+/* the tendency of pystep_bfn (qg_bfn.h:21-80, vartype==1): q already set */
+int msqg_tendency_bfn(msqg_model *m, double direction);
+/* timestep()'s static `previous` (Basilisk timestep.h): get / reset */
+double msqg_get_ts_previous(msqg_model *m);
+void msqg_set_ts_previous(msqg_model *m, double v);
+/* seed of the host libc rand() stream used by the stochastic forcing
+ * (qg_stochastic.h:9); noise is generated on the host in reference order */
+void msqg_seed_noise(msqg_model *m, unsigned seed);
+/* number of CUDA kernels launched by this handle since creation */
+long msqg_launch_count(msqg_model *m);
+const char *msqg_last_error(void);
+
+/* kernel-level hooks for parity tests (level = multigrid level, n = 2^level):
+ * fields are host [nf][n][n]; they exercise exactly the production kernels. */
+int msqg_test_relax(msqg_model *m, int level, const double *s /*[nl-1][n][n] or NULL=model's*/,
+                    double *a, const double *b, int nsweeps);
+int msqg_test_residual(msqg_model *m, const double *a, const double *b, double *res, double *maxres);
+int msqg_test_restrict(msqg_model *m, int level, const double *fine, double *coarse);
+int msqg_test_prolong(msqg_model *m, int level, const double *coarse, double *fine);
+/* one mg_cycle + residual at the model's shape, timed with CUDA events (ms) */
+int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_out);
+
+/* ---- (2) reference surface (global state, like the SWIG module `qg`) --- */
+
+int read_params(char *path2file);                 /* qg.h:689 */
+int init_grid(int n);                             /* Basilisk init_grid (qg.c:45) */
+int set_vars(void);                               /* qg.h:837 */
+int set_const(void);                              /* qg.h:931 (reads CWD input files) */
+int create_outdir(void);                          /* qg.h:766 */
+int backup_config(void);                          /* qg.h:782 */
+int trash_vars(void);                             /* qg.h:1130 */
+int set_vars_bfn(void);                           /* qg_bfn.h:7 */
+int trash_vars_bfn(void);                         /* qg_bfn.h:12 */
+int pystep_bfn(double *varin_py, int len1, int len2, int len3,
+               double *tend_py, int len4, int len5, int len6,
+               double direction, int vartype);    /* qg_bfn.h:21 */
+int pyq2p(double *po_py, int len7, int len8, int len9,
+          double *qo_py, int len10, int len11, int len12);   /* qg_bfn.h:85 */
+int pyp2q(double *po_py, int len13, int len14, int len15,
+          double *qo_py, int len16, int len17, int len18);   /* qg_bfn.h:95 */
+int run(void);                                    /* Basilisk run() + qg.c events */
+/* access to the global handle/params behind the reference surface */
+msqg_model *qg_model(void);
+msqg_params *qg_params(void);
+int qg_set_device(int device);
+int qg_set_mode_pv_invert(int mode);              /* MODE_PV_INVERT, qg.h:4 */
+int qg_set_stochastic(int on);                    /* -D_STOCHASTIC, qg.c:25 */
+/* .bas files (auxiliar_input.h:24-59,101-149) on host arrays [nf][N][N] */
+int qg_write_bas(const char *name, int nf, int N, double L0, const double *v);
+int qg_read_bas(const char *name, int nf, int N, double L0, double *v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,118 @@
+/*
+ * msqg_oracle.h -- CPU oracle for the msqg multilayer QG timestep.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C99 restatement of the reference
+ * algorithm (bderembl/msom, msqg/qg.h + poisson_layer.h + eigmode.h + layer.h +
+ * qg.c, and the Basilisk runtime pieces they call).  Only tests/, the
+ * __graft_entry__.smoke() check and bench.py's cpu_baseline / --impl reference
+ * legs may load it.  The product (msqg_b200/) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference ships no golden vectors or tests and cannot
+ * be built here (qcc/Basilisk absent), so this oracle is pinned only by
+ * known-answer identities (tests/test_oracle_*.py), not by reference outputs.
+ *
+ * Field API layout: C-contiguous double [layer][y][x] (x fastest), the layout
+ * of pyset_field/pyget_field (msqg/qg.h:1164-1189).
+ */
+#ifndef MSQG_ORACLE_H
+#define MSQG_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAXL 32
+
+typedef struct {
+  /* keys of params.in, msqg/qg.h:698-731 */
+  int N, nl, ediag, varRo, nptr, flsrv;
+  double L0, Rom, Ekb, Eks, tau0, Re, Re4, sbc, beta, afilt, Lfmax;
+  double DT, tend, dtout, dtflt, CFL;
+  double Fr[ORC_MAXL], dh[ORC_MAXL], upg[ORC_MAXL], vpg[ORC_MAXL];
+  /* derived, msqg/qg.h:739-746 */
+  double iRe, iRe4;
+  /* -D_STOCHASTIC build, msqg/qg_stochastic.h:3-6 */
+  int stochastic;
+  double tr_stoch, itr_stoch, amp_stoch;
+  /* compile-time switch MODE_PV_INVERT (msqg/qg.h:4) made a runtime knob */
+  int mode_pv_invert;
+  /* emulate Basilisk's MPI px*py block decomposition of the GS sweep
+     (1,1 = serial reference order) */
+  int px, py;
+} orc_params;
+
+typedef struct {
+  int i;             /* cycles */
+  double resb, resa; /* max residual before / after */
+  double sum;        /* sum of rhs */
+  int nrelax;        /* final nrelax */
+} orc_mgstats;
+
+typedef struct orc_model orc_model;
+
+enum {
+  ORC_PSI = 0, ORC_Q, ORC_PSIPG, ORC_FR, ORC_QFORC, ORC_TOPO, ORC_RD, ORC_SSTOCH,
+  ORC_ZETA, ORC_DQ, ORC_STR, ORC_NSTOCH, ORC_IBU, ORC_CL2M, ORC_CM2L, ORC_PM, ORC_QM,
+  ORC_TMP, ORC_ZETAP
+};
+
+void orc_default_params(orc_params *p);
+/* read_params, msqg/qg.h:689-761.  returns 0 ok, -1 file missing */
+int orc_read_params(const char *path, orc_params *p);
+
+orc_model *orc_create(const orc_params *p);      /* init_grid + set_vars */
+void orc_destroy(orc_model *m);                  /* trash_vars */
+int  orc_nfields(orc_model *m, int id);          /* number of scalars in list id */
+void orc_set_field(orc_model *m, int id, const double *v); /* pyset_field */
+void orc_get_field(orc_model *m, int id, double *v);       /* pyget_field */
+int  orc_set_const(orc_model *m);                /* set_const; -1 on the exit(0) paths */
+void orc_set_flag_topo(orc_model *m, int flag);
+/* MPI-style block Gauss-Seidel emulation: px*py blocks on levels with n >= agg_n */
+void orc_set_decomp(orc_model *m, int px, int py, int agg_n);
+void orc_init_noise(orc_model *m, unsigned seed);/* qg.c:60-70 with srand(seed) */
+void orc_remove_mean_psi(orc_model *m);          /* qg.c:66-70 */
+
+void orc_invertq(orc_model *m);                  /* invertq(pol,qol) */
+void orc_comp_q(orc_model *m);                   /* comp_q(pol,qol) */
+orc_mgstats orc_last_mgstats(orc_model *m, int mode);
+int  orc_total_cycles(orc_model *m);
+
+/* update_qg on the model's q (evolving) -> DQ; returns dtmax */
+double orc_update(orc_model *m, double dtmax);
+/* one predictor-corrector step of Basilisk run() without the event machinery:
+   dt = update(q, DT) (no dtnext rounding); returns dt used */
+double orc_step(orc_model *m);
+/* run() with events: output every dtout (invertq side effect), writestdout ke.
+   write_files: 0 none, 1 write .bas into outdir.  returns number of steps. */
+int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, int verbose);
+double orc_time(orc_model *m);
+double orc_ke1(orc_model *m);                    /* qg.c:101-106 */
+
+/* python entry points, msqg/qg_bfn.h */
+void orc_pystep_bfn(orc_model *m, const double *q_in, double *tend, double direction, int vartype);
+void orc_pyq2p(orc_model *m, double *po, const double *qo);
+void orc_pyp2q(orc_model *m, const double *po, double *qo);
+
+/* unit-level hooks for kernel parity tests (operate on scratch lists) */
+/* one relax_layer sweep x nsweeps (each followed by boundary_level) on level l.
+   a,b: [nl][n][n] arrays at that level; s: [nl-1][n][n] stretching at that level */
+void orc_test_relax(int nl, int level, double L0, const double *dh, const double *s,
+                    double *a, const double *b, int nsweeps, int px, int py);
+double orc_test_residual(int nl, int level, double L0, const double *dh, const double *s,
+                         const double *a, const double *b, double *res);
+void orc_test_restrict(int nf, int level, const double *fine, double *coarse);
+void orc_test_prolong(int nf, int level, const double *coarse, double *fine); /* level = fine level */
+void orc_test_relax_scalar(int level, double L0, const double *lam, double *a, const double *b, int nsweeps);
+double orc_test_residual_scalar(int level, double L0, const double *lam, const double *a, const double *b, double *res);
+/* eigmod for one column: amat inputs -> cl2m[nl*nl], cm2l[nl*nl], iBu[nl]; returns 0 ok */
+int orc_eigmod_column(int nl, const double *dhf, const double *Fr, double Ro,
+                      double *cl2m, double *cm2l, double *iBu);
+
+/* .bas I/O, msqg/auxiliar_input.h */
+int orc_write_bas(const char *name, int nf, int N, double L0, const double *v /*[nf][y][x]*/);
+int orc_read_bas(const char *name, int nf, int N, double L0, double *v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
