@@ -95,7 +95,7 @@ int msqg_read_params(const char *path, msqg_params *p);
 
 /* init_grid(N) + set_vars() (msqg/qg.h:837-925): allocates every layer list on
  * `device`, zero fields, ppl = vpg*x - upg*y, Frl = Fr.  N must be a power of
- * two >= 32, 2 <= nl <= 12, sbc == 0. */
+ * two >= 8, 2 <= nl <= 12, sbc == 0. */
 int msqg_create(const msqg_params *p, int device, msqg_model **out);
 void msqg_destroy(msqg_model *m);                 /* trash_vars, qg.h:1130-1154 */
 /* run on this CUDA stream (a cudaStream_t passed as void*); default: own stream */
@@ -139,13 +139,24 @@ void msqg_seed_noise(msqg_model *m, unsigned seed);
 long msqg_launch_count(msqg_model *m);
 const char *msqg_last_error(void);
 
+/* keep the tendency list DQ when stepping with the fused msqg_step (default 0:
+ * the RHS is consumed by the fused stage update and never stored) */
+int msqg_set_keep_dq(msqg_model *m, int keep);
+/* signed dissipation coefficients (pystep_bfn flips them, qg_bfn.h:34-44) */
+int msqg_set_dissipation(msqg_model *m, double iRe, double iRe4, double Eks, double Ekb);
+/* derived values of read_params (qg.h:739-746,757) for a hand-filled struct */
+void msqg_derive_params(msqg_params *p);
+
 /* kernel-level hooks for parity tests (level = multigrid level, n = 2^level):
- * fields are host [nf][n][n]; they exercise exactly the production kernels. */
-int msqg_test_relax(msqg_model *m, int level, const double *s /*[nl-1][n][n] or NULL=model's*/,
-                    double *a, const double *b, int nsweeps);
+ * fields are host [nf][n][n]; they exercise exactly the production kernels
+ * with the model's stretching and layer metrics (set_const must have run). */
+int msqg_test_relax(msqg_model *m, int level, double *a, const double *b, int nsweeps);
+int msqg_test_relax_scalar(msqg_model *m, int level, double lambda, double *a, const double *b, int nsweeps);
 int msqg_test_residual(msqg_model *m, const double *a, const double *b, double *res, double *maxres);
 int msqg_test_restrict(msqg_model *m, int level, const double *fine, double *coarse);
 int msqg_test_prolong(msqg_model *m, int level, const double *coarse, double *fine);
+/* div_by() (exact division by a pivot with known reciprocal) next to IEEE x/d */
+int msqg_test_div(int device, const double *x, const double *d, double *q_fast, double *q_ieee, int n);
 /* one mg_cycle + residual at the model's shape, timed with CUDA events (ms) */
 int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_out);
 

@@ -1,0 +1,229 @@
+"""ctypes binding of the handle-based C ABI (include/msqg.h, layer 1).
+
+Thin marshaling only: numpy float64 C-contiguous arrays [layer][y][x] in, the
+same out.  All compute happens in libmsqg_cuda.so (hand-written sm_100a
+kernels); there is no CPU path and loading fails loudly if the library is
+missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_CUDA = os.path.join(_HERE, "lib", "libmsqg_cuda.so")
+MAXL = 32
+
+(PSI, Q, PSIPG, FR, QFORC, TOPO, RD, SSTOCH, ZETA, DQ, STR, NSTOCH, IBU, CL2M, CM2L, PM, QM, TMP, ZETAP,
+ QPRED) = range(20)
+
+OK, ERR_ARG, ERR_CUDA, ERR_FILE, ERR_CONFIG, ERR_NOCONV = 0, -1, -2, -3, -4, -5
+
+
+class Params(C.Structure):
+    """msqg_params (keys of params.in, msqg/qg.h:698-731, + derived values)."""
+    _fields_ = (
+        [(k, C.c_int) for k in ("N", "nl", "ediag", "varRo", "nptr", "flsrv")]
+        + [(k, C.c_double) for k in ("L0", "Rom", "Ekb", "Eks", "tau0", "Re", "Re4", "sbc", "beta",
+                                     "afilt", "Lfmax", "DT", "tend", "dtout", "dtflt", "CFL")]
+        + [(k, C.c_double * MAXL) for k in ("Fr", "dh", "upg", "vpg")]
+        + [("iRe", C.c_double), ("iRe4", C.c_double), ("stochastic", C.c_int),
+           ("tr_stoch", C.c_double), ("itr_stoch", C.c_double), ("amp_stoch", C.c_double),
+           ("mode_pv_invert", C.c_int)]
+    )
+
+
+class MgStats(C.Structure):
+    _fields_ = [("i", C.c_int), ("resb", C.c_double), ("resa", C.c_double), ("sum", C.c_double),
+                ("nrelax", C.c_int)]
+
+
+class MsqgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("msqg error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def _find_lapack():
+    """eigmod (msqg/eigmode.h:153) needs LAPACK dgeev; point the library at one."""
+    if "MSQG_LAPACK" in os.environ:
+        return
+    import glob
+    try:
+        import scipy
+        c = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so"))
+        if c:
+            os.environ["MSQG_LAPACK"] = os.path.abspath(c[0])
+    except Exception:
+        pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_CUDA):
+        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the msqg timestep has no CPU fallback)" % LIB_CUDA)
+    _find_lapack()
+    L = C.CDLL(LIB_CUDA, mode=C.RTLD_GLOBAL)
+    dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    vp = C.c_void_p
+    pd = C.POINTER(C.c_double)
+    L.msqg_last_error.restype = C.c_char_p
+    L.msqg_default_params.argtypes = [C.POINTER(Params)]
+    L.msqg_derive_params.argtypes = [C.POINTER(Params)]
+    L.msqg_read_params.argtypes = [C.c_char_p, C.POINTER(Params)]
+    L.msqg_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(vp)]
+    L.msqg_destroy.argtypes = [vp]
+    L.msqg_set_stream.argtypes = [vp, vp]
+    L.msqg_nfields.argtypes = [vp, C.c_int]
+    L.msqg_set_field.argtypes = [vp, C.c_int, dp]
+    L.msqg_get_field.argtypes = [vp, C.c_int, dp]
+    L.msqg_set_flag_topo.argtypes = [vp, C.c_int]
+    L.msqg_set_keep_dq.argtypes = [vp, C.c_int]
+    L.msqg_set_dissipation.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.msqg_set_const.argtypes = [vp]
+    L.msqg_invertq.argtypes = [vp, C.c_int]
+    L.msqg_comp_q.argtypes = [vp]
+    L.msqg_last_mgstats.argtypes = [vp, C.c_int, C.POINTER(MgStats)]
+    L.msqg_total_cycles.argtypes = [vp]
+    L.msqg_total_cycles.restype = C.c_long
+    L.msqg_update.argtypes = [vp, C.c_int, C.c_double, pd]
+    L.msqg_advance.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+    L.msqg_step.argtypes = [vp, C.c_double, C.c_double, pd, pd]
+    L.msqg_ke1.argtypes = [vp, pd]
+    L.msqg_tendency_bfn.argtypes = [vp, C.c_double]
+    L.msqg_get_ts_previous.argtypes = [vp]
+    L.msqg_get_ts_previous.restype = C.c_double
+    L.msqg_set_ts_previous.argtypes = [vp, C.c_double]
+    L.msqg_seed_noise.argtypes = [vp, C.c_uint]
+    L.msqg_launch_count.argtypes = [vp]
+    L.msqg_launch_count.restype = C.c_long
+    L.msqg_test_relax.argtypes = [vp, C.c_int, dp, dp, C.c_int]
+    L.msqg_test_relax_scalar.argtypes = [vp, C.c_int, C.c_double, dp, dp, C.c_int]
+    L.msqg_test_residual.argtypes = [vp, dp, dp, dp, pd]
+    L.msqg_test_restrict.argtypes = [vp, C.c_int, dp, dp]
+    L.msqg_test_prolong.argtypes = [vp, C.c_int, dp, dp]
+    L.msqg_test_div.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int]
+    L.msqg_time_vcycle.argtypes = [vp, C.c_int, C.c_int, pd]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise MsqgError(rc, lib().msqg_last_error().decode(errors="replace"))
+
+
+def make_params(**kw):
+    """msqg_params with the reference defaults, overridden by kw, then the
+    derived values of read_params (msqg/qg.h:739-746)."""
+    p = Params()
+    lib().msqg_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k in ("Fr", "dh", "upg", "vpg"):
+            arr = getattr(p, k)
+            for i, x in enumerate(v):
+                arr[i] = float(x)
+        else:
+            setattr(p, k, v)
+    lib().msqg_derive_params(C.byref(p))
+    return p
+
+
+def read_params(path, stochastic=0, mode_pv_invert=0):
+    p = Params()
+    lib().msqg_default_params(C.byref(p))
+    p.stochastic = stochastic
+    p.mode_pv_invert = mode_pv_invert
+    check(lib().msqg_read_params(str(path).encode(), C.byref(p)))
+    return p
+
+
+class Model:
+    """One msqg model resident on one GPU (msqg_create .. msqg_destroy)."""
+
+    def __init__(self, params, device=0):
+        self.L = lib()
+        self.p = params
+        self.N, self.nl = params.N, params.nl
+        h = C.c_void_p()
+        check(self.L.msqg_create(C.byref(params), device, C.byref(h)))
+        self.h = h
+        self.t = 0.0
+        self.i = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.msqg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nfields(self, fid):
+        return self.L.msqg_nfields(self.h, fid)
+
+    def set(self, fid, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.shape == (self.nfields(fid), self.N, self.N), (arr.shape, self.nfields(fid))
+        check(self.L.msqg_set_field(self.h, fid, arr))
+
+    def get(self, fid):
+        out = np.zeros((self.nfields(fid), self.N, self.N))
+        check(self.L.msqg_get_field(self.h, fid, out))
+        return out
+
+    def set_const(self):
+        check(self.L.msqg_set_const(self.h))
+
+    def invertq(self, q_id=Q):
+        check(self.L.msqg_invertq(self.h, q_id))
+
+    def comp_q(self):
+        check(self.L.msqg_comp_q(self.h))
+
+    def mgstats(self, mode=-1):
+        s = MgStats()
+        check(self.L.msqg_last_mgstats(self.h, mode, C.byref(s)))
+        return s
+
+    def update(self, dtmax, q_id=Q):
+        out = C.c_double()
+        check(self.L.msqg_update(self.h, q_id, dtmax, C.byref(out)))
+        return out.value
+
+    def advance(self, out_id, in_id, dt):
+        check(self.L.msqg_advance(self.h, out_id, in_id, dt))
+
+    def step(self, tnext_event=-1.0):
+        dt, tn = C.c_double(), C.c_double()
+        check(self.L.msqg_step(self.h, self.t, tnext_event, C.byref(dt), C.byref(tn)))
+        self.t = tn.value
+        self.i += 1
+        return dt.value
+
+    def ke1(self):
+        ke = C.c_double()
+        check(self.L.msqg_ke1(self.h, C.byref(ke)))
+        return ke.value
+
+    def time_vcycle(self, nrelax=4, reps=5):
+        ms = C.c_double()
+        check(self.L.msqg_time_vcycle(self.h, nrelax, reps, C.byref(ms)))
+        return ms.value
+
+    @property
+    def total_cycles(self):
+        return self.L.msqg_total_cycles(self.h)
+
+    @property
+    def launches(self):
+        return self.L.msqg_launch_count(self.h)

@@ -1,0 +1,30 @@
+/*
+ * layout.cuh -- HBM data layout of the msqg layer fields.
+ *
+ * A "list" (the reference's `scalar *`, msqg/qg.h:23-59) on multigrid level L is
+ *     double [nf][n+2][pitch]          n = 2^L, x fastest
+ * with one ghost ring ([BASILISK] allocates two, msqg only ever reads one).
+ * Interior cell (x=0,y=0) of a plane sits at element  pitch + OX, OX = 16, so
+ * every interior row starts 128-byte aligned; pitch is a multiple of 16 doubles.
+ * This is the numpy (nl,N,N) = [layer][y][x] layout of pyset_field/pyget_field
+ * (msqg/qg.h:1164-1189) plus padding; the reference's own AoS/y-fastest storage
+ * is not observable through any interface.
+ */
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#define MSQG_OX 16
+#define MSQG_MAXLEV 16
+#define MSQG_NLMAX 12 /* device kernels are instantiated for 1..12 layers */
+
+struct Geom {
+  int n;        /* cells per side */
+  int pitch;    /* doubles per row */
+  size_t plane; /* doubles per scalar = (n+2)*pitch */
+  double Delta; /* L0/n */
+};
+
+static inline int msqg_pitch(int n) { return ((n + MSQG_OX + 1 + 15) / 16) * 16; }
+
+#define GIDX(P, y, x) ((size_t)((y) + 1) * (size_t)(P) + (size_t)(MSQG_OX + (x)))

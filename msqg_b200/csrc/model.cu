@@ -1,0 +1,1266 @@
+/*
+ * model.cu -- handle-based C ABI of the B200 msqg timestep (include/msqg.h, layer 1).
+ *
+ * Host logic here is the part of the reference that drives the hot kernels:
+ *   mg_solve / mg_cycle      [BASILISK] poisson.h; in-tree copy mspg/elliptic.h:43-99,145-229
+ *   poisson_layer            msqg/poisson_layer.h:263-306
+ *   invertq                  msqg/qg.h:113-163
+ *   update_qg / advance_qg   msqg/qg.h:594-650 (+ msqg/qg_stochastic.h)
+ *   timestep()               [BASILISK] timestep.h; in-tree copy newqg/qg.h:202-219
+ *   set_vars / set_const     msqg/qg.h:837-1116
+ * No CPU fallback exists: every compute entry point needs a CUDA device.
+ */
+#include "../../include/msqg.h"
+#include "layout.cuh"
+#include "mg_kernels.cuh"
+#include "rhs_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+extern "C" const char *msqg_last_error(void) { return g_err; }
+#define FAIL(code, ...)                        \
+  do {                                         \
+    snprintf(g_err, sizeof(g_err), __VA_ARGS__); \
+    return (code);                             \
+  } while (0)
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) FAIL(MSQG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static inline double sq(double x) { return x * x; }
+
+struct List {
+  int nf = 0;
+  double sg = -1.;               /* -1 dirichlet(0), +1 symmetry (layer.h:5-35) */
+  double *lev[MSQG_MAXLEV + 1];  /* device pointers per level (only allocated levels non-NULL) */
+  List() { for (auto &p : lev) p = nullptr; }
+};
+
+struct msqg_model {
+  msqg_params p;
+  int N, nl, depth, device;
+  cudaStream_t stream;
+  bool own_stream;
+  Geom g[MSQG_MAXLEV + 1];
+  /* layer lists (finest level only unless noted) */
+  List psi, q, qpred, dq, zeta, tmp, psipg, zetap, qforc, fr, str /*all levels*/, topo, rd, ro, sigfilt;
+  List sstoch, nstoch;
+  List da, res; /* all levels; nf = nl */
+  List pm, qm, ibu /*all levels*/, cl2m, cm2l;
+  double dhf[MSQG_MAXL], dhc[MSQG_MAXL], idh0[MSQG_MAXL], idh1[MSQG_MAXL];
+  double iRe, iRe4, Eks, Ekb;
+  int flag_topo, has_pg, has_zp, has_qforc;
+  int const_set;
+  /* uniform-stretching tables: s per level/layer and Thomas coefficients */
+  bool s_uniform;
+  std::vector<double> s_lev;   /* [(depth+1)][nl] */
+  std::vector<double> h_fr;    /* host copy of Frl finest [nl][N][N] */
+  /* modal */
+  bool modes_uniform;
+  double h_cl2m[MSQG_NLMAX * MSQG_NLMAX], h_cm2l[MSQG_NLMAX * MSQG_NLMAX], h_ibu[MSQG_NLMAX];
+  std::vector<double> lam_lev; /* [(depth+1)][nl] lambda per level (restricted) */
+  /* scratch */
+  double *d_stage;   /* staging [max nf][N][N] */
+  size_t stage_doubles;
+  double *d_scal;    /* device scalars: [0] maxres, [1..] umax[nl] */
+  double *h_scal;    /* pinned mirror */
+  double *d_wind;    /* [N] */
+  double *d_kepart;
+  unsigned long long *mailbox;
+  size_t mailbox_words;
+  int *d_err;
+  int *h_err;
+  int num_sms;
+  /* state */
+  double ts_previous;
+  int corrector_step;
+  unsigned noise_seeded;
+  std::vector<double> h_noise, h_sstoch;
+  double umax_pg[MSQG_MAXL];
+  msqg_mgstats mgpsi, mgmode[MSQG_MAXL];
+  long total_cycles, launches;
+  int keep_dq;
+};
+
+/* ------------------------------------------------------------------ params */
+extern "C" void msqg_default_params(msqg_params *p) {
+  memset(p, 0, sizeof(*p));
+  /* [BASILISK] N=64, L0=1, DT=1e10, CFL=0.5; msqg/qg.h:53-98 */
+  p->N = 64; p->nl = 1; p->ediag = -1; p->L0 = 1.; p->beta = 0.5;
+  p->afilt = 10.; p->Lfmax = 1.e10; p->DT = 1e10; p->tend = 1; p->dtout = 1;
+  p->dtflt = -1; p->CFL = 0.5; p->amp_stoch = 1;
+}
+
+/* trim_whitespace, msqg/qg.h:668-675 (blanks only) */
+static void trim_ws(char *s) {
+  const char *d = s;
+  do { while (*d == ' ') ++d; } while ((*s++ = *d++));
+}
+/* str2array, msqg/qg.h:678-687 */
+static void str2array(char *s, double *arr) {
+  int n = 0;
+  char *p = strtok(s, "[,]");
+  while (p != NULL && n < MSQG_MAXL) { arr[n++] = atof(p); p = strtok(NULL, ","); }
+}
+extern "C" void msqg_derive_params(msqg_params *p) {
+  /* msqg/qg.h:739-746,757 */
+  if (p->Re == 0) p->iRe = 0.; else p->iRe = 1 / p->Re;
+  if (p->Re4 == 0) p->iRe4 = 0.; else p->iRe4 = -1 / p->Re4;
+  if (p->Re != 0) p->DT = 0.5 * fmin(p->DT, sq(p->L0 / p->N) * p->Re / 4.);
+  if (p->Re4 != 0) p->DT = 0.5 * fmin(p->DT, sq(sq(p->L0 / p->N)) * p->Re4 / 32.);
+  if (p->tr_stoch != 0) p->itr_stoch = 1 / p->tr_stoch;
+}
+extern "C" int msqg_read_params(const char *path, msqg_params *p) {
+  FILE *fp = fopen(path, "rt");
+  if (!fp) FAIL(MSQG_ERR_FILE, "file %s not found", path);
+  char buf[300];
+  while (fgets(buf, 300, fp)) {
+    trim_ws(buf);
+    char *k = strtok(buf, "=");
+    char *v = strtok(NULL, "=");
+    if (!k || !v) continue;
+    if      (!strcmp(k, "N"))     p->N = atoi(v);
+    else if (!strcmp(k, "nl"))    p->nl = atoi(v);
+    else if (!strcmp(k, "ediag")) p->ediag = atoi(v);
+    else if (!strcmp(k, "varRo")) p->varRo = atoi(v);
+    else if (!strcmp(k, "nptr"))  p->nptr = atoi(v);
+    else if (!strcmp(k, "flsrv")) p->flsrv = atoi(v);
+    else if (!strcmp(k, "L0"))    p->L0 = atof(v);
+    else if (!strcmp(k, "Rom"))   p->Rom = atof(v);
+    else if (!strcmp(k, "Ekb"))   p->Ekb = atof(v);
+    else if (!strcmp(k, "Eks"))   p->Eks = atof(v);
+    else if (!strcmp(k, "tau0"))  p->tau0 = atof(v);
+    else if (!strcmp(k, "Re"))    p->Re = atof(v);
+    else if (!strcmp(k, "Re4"))   p->Re4 = atof(v);
+    else if (!strcmp(k, "sbc"))   p->sbc = atof(v);
+    else if (!strcmp(k, "beta"))  p->beta = atof(v);
+    else if (!strcmp(k, "afilt")) p->afilt = atof(v);
+    else if (!strcmp(k, "Lfmax")) p->Lfmax = atof(v);
+    else if (!strcmp(k, "DT"))    p->DT = atof(v);
+    else if (!strcmp(k, "tend"))  p->tend = atof(v);
+    else if (!strcmp(k, "dtout")) p->dtout = atof(v);
+    else if (!strcmp(k, "dtflt")) p->dtflt = atof(v);
+    else if (!strcmp(k, "CFL"))   p->CFL = atof(v);
+    else if (!strcmp(k, "Fr"))    str2array(v, p->Fr);
+    else if (!strcmp(k, "dh"))    str2array(v, p->dh);
+    else if (!strcmp(k, "upg"))   str2array(v, p->upg);
+    else if (!strcmp(k, "vpg"))   str2array(v, p->vpg);
+    else if (p->stochastic && !strcmp(k, "tr_stoch"))  p->tr_stoch = atof(v);
+    else if (p->stochastic && !strcmp(k, "amp_stoch")) p->amp_stoch = atof(v);
+  }
+  fclose(fp);
+  msqg_derive_params(p);
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ allocation */
+static int alloc_list(msqg_model *m, List &L, int nf, double sg, int lev_lo, int lev_hi) {
+  L.nf = nf; L.sg = sg;
+  for (int l = lev_lo; l <= lev_hi; l++) {
+    size_t bytes = (size_t)nf * m->g[l].plane * sizeof(double);
+    CK(cudaMalloc(&L.lev[l], bytes));
+    CK(cudaMemsetAsync(L.lev[l], 0, bytes, m->stream));
+  }
+  return MSQG_OK;
+}
+static void free_list(List &L) {
+  for (auto &p : L.lev) { if (p) cudaFree(p); p = nullptr; }
+  L.nf = 0;
+}
+
+static List *list_by_id(msqg_model *m, int id) {
+  switch (id) {
+    case MSQG_PSI: return &m->psi;     case MSQG_Q: return &m->q;
+    case MSQG_PSIPG: return &m->psipg; case MSQG_FR: return &m->fr;
+    case MSQG_QFORC: return &m->qforc; case MSQG_TOPO: return &m->topo;
+    case MSQG_RD: return &m->rd;       case MSQG_SSTOCH: return &m->sstoch;
+    case MSQG_ZETA: return &m->zeta;   case MSQG_DQ: return &m->dq;
+    case MSQG_STR: return &m->str;     case MSQG_NSTOCH: return &m->nstoch;
+    case MSQG_IBU: return &m->ibu;     case MSQG_CL2M: return &m->cl2m;
+    case MSQG_CM2L: return &m->cm2l;   case MSQG_PM: return &m->pm;
+    case MSQG_QM: return &m->qm;       case MSQG_TMP: return &m->tmp;
+    case MSQG_ZETAP: return &m->zetap; case MSQG_QPRED: return &m->qpred;
+  }
+  return nullptr;
+}
+
+static dim3 grid2(int nx, int ny, dim3 b, int nz = 1) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, nz); }
+
+static int pack_to(msqg_model *m, List &L, const double *host) {
+  const Geom &g = m->g[m->depth];
+  size_t cnt = (size_t)L.nf * g.n * g.n;
+  if (cnt > m->stage_doubles) FAIL(MSQG_ERR_ARG, "staging buffer too small");
+  CK(cudaMemcpyAsync(m->d_stage, host, cnt * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  dim3 b(32, 8);
+  k_pack<<<grid2(g.n + 2, g.n + 2, b, L.nf), b, 0, m->stream>>>(L.lev[m->depth], m->d_stage, L.nf, g, L.sg);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->stream)); /* host buffer is borrowed for the call only */
+  return MSQG_OK;
+}
+static int unpack_from(msqg_model *m, List &L, double *host) {
+  const Geom &g = m->g[m->depth];
+  size_t cnt = (size_t)L.nf * g.n * g.n;
+  if (cnt > m->stage_doubles) FAIL(MSQG_ERR_ARG, "staging buffer too small");
+  dim3 b(32, 8);
+  k_unpack<<<grid2(g.n, g.n, b, L.nf), b, 0, m->stream>>>(m->d_stage, L.lev[m->depth], L.nf, g);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host, m->d_stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ create / destroy */
+extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    FAIL(MSQG_ERR_CUDA, "no CUDA device: the msqg timestep has no CPU path");
+  if (device < 0 || device >= ndev) FAIL(MSQG_ERR_ARG, "bad device %d", device);
+  if (p->nl < 2 || p->nl > MSQG_NLMAX) FAIL(MSQG_ERR_ARG, "nl must be in [2,%d] (nl==1 is not functional in the reference)", MSQG_NLMAX);
+  if (p->N < 8 || (p->N & (p->N - 1))) FAIL(MSQG_ERR_ARG, "N must be a power of two >= 8");
+  if (p->sbc != 0) FAIL(MSQG_ERR_ARG, "only sbc == 0 (free slip) is supported");
+  if (p->nptr != 0) FAIL(MSQG_ERR_ARG, "passive tracers (nptr > 0) are out of scope");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) FAIL(MSQG_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a", device, prop.major, prop.minor);
+  msqg_model *m = new msqg_model();
+  m->p = *p; m->N = p->N; m->nl = p->nl; m->device = device;
+  m->num_sms = prop.multiProcessorCount;
+  int depth = 0;
+  while ((1 << depth) < p->N) depth++;
+  m->depth = depth;
+  for (int l = 0; l <= depth; l++) {
+    Geom &g = m->g[l];
+    g.n = 1 << l; g.pitch = msqg_pitch(g.n); g.plane = (size_t)(g.n + 2) * g.pitch;
+    g.Delta = p->L0 / g.n; /* == L0*(1./(1 << level)) [BASILISK], exact power-of-two scaling */
+  }
+  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  m->own_stream = true;
+  const int nl = p->nl, D = depth;
+  int rc;
+#define AL(L, nf, sg, lo, hi) if ((rc = alloc_list(m, L, nf, sg, lo, hi))) { msqg_destroy(m); return rc; }
+  /* set_vars, msqg/qg.h:849-883: bc_type 0 -> dirichlet(0); +1 -> symmetry */
+  AL(m->psi, nl, -1., D, D) AL(m->q, nl, -1., D, D) AL(m->qpred, nl, -1., D, D) AL(m->dq, nl, -1., D, D)
+  AL(m->zeta, nl, -1., D, D) AL(m->tmp, nl, -1., D, D) AL(m->psipg, nl, -1., D, D) AL(m->zetap, nl, -1., D, D)
+  AL(m->qforc, nl, -1., D, D) AL(m->fr, nl, 1., D, D) AL(m->str, nl, 1., 1, D)
+  AL(m->topo, 1, 1., D, D) AL(m->rd, 1, 1., D, D) AL(m->ro, 1, 1., D, D) AL(m->sigfilt, 1, 1., D, D)
+  AL(m->da, nl, -1., 1, D) AL(m->res, nl, -1., 1, D)
+  if (p->mode_pv_invert) {
+    AL(m->pm, nl, -1., D, D) AL(m->qm, nl, -1., D, D) AL(m->ibu, nl, 1., 1, D)
+    AL(m->cl2m, nl * nl, 1., D, D) AL(m->cm2l, nl * nl, 1., D, D)
+  }
+  if (p->stochastic) { AL(m->sstoch, nl, -1., D, D) AL(m->nstoch, nl, -1., D, D) }
+#undef AL
+  const int maxnf = p->mode_pv_invert ? nl * nl : nl;
+  m->stage_doubles = (size_t)maxnf * p->N * p->N;
+  CK(cudaMalloc(&m->d_stage, m->stage_doubles * sizeof(double)));
+  CK(cudaMalloc(&m->d_scal, 64 * sizeof(double)));
+  CK(cudaMallocHost(&m->h_scal, 64 * sizeof(double)));
+  CK(cudaMalloc(&m->d_wind, (size_t)p->N * sizeof(double)));
+  CK(cudaMemsetAsync(m->d_wind, 0, (size_t)p->N * sizeof(double), m->stream));
+  CK(cudaMalloc(&m->d_kepart, (size_t)((p->N + 15) / 16) * ((p->N + 15) / 16) * sizeof(double)));
+  CK(cudaMalloc(&m->d_err, sizeof(int)));
+  CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
+  CK(cudaMallocHost(&m->h_err, sizeof(int)));
+  m->mailbox = nullptr; m->mailbox_words = 0;
+  for (int l = 0; l < nl; l++) m->dhf[l] = p->dh[l]; /* qg.h:895-896 */
+  m->iRe = p->iRe; m->iRe4 = p->iRe4; m->Eks = p->Eks; m->Ekb = p->Ekb;
+  m->ts_previous = 0.; m->corrector_step = 0; m->noise_seeded = 0;
+  m->flag_topo = 0; m->has_qforc = 0; m->has_zp = 0; m->const_set = 0;
+  m->total_cycles = 0; m->launches = 0; m->keep_dq = 0;
+  memset(&m->mgpsi, 0, sizeof(m->mgpsi));
+  memset(m->mgmode, 0, sizeof(m->mgmode));
+  memset(m->umax_pg, 0, sizeof(m->umax_pg));
+  /* Frl = Frm, ppl = vpg*x - upg*y, Ro = Rom, Rd = 1, topo = 0 (qg.h:898-915) */
+  {
+    const int n = p->N;
+    const double Delta = p->L0 / n;
+    std::vector<double> h((size_t)nl * n * n, 0.);
+    m->h_fr.assign((size_t)nl * n * n, 0.);
+    for (int l = 0; l < nl - 1; l++)
+      for (size_t c = 0; c < (size_t)n * n; c++) m->h_fr[(size_t)l * n * n + c] = p->Fr[l];
+    if ((rc = pack_to(m, m->fr, m->h_fr.data()))) { msqg_destroy(m); return rc; }
+    m->has_pg = 0;
+    for (int l = 0; l < nl; l++) if (p->upg[l] != 0 || p->vpg[l] != 0) m->has_pg = 1;
+    if (m->has_pg) {
+      for (int l = 0; l < nl; l++)
+        for (int j = 0; j < n; j++)
+          for (int i = 0; i < n; i++) {
+            const double x = (i + 0.5) * Delta, y = (j + 0.5) * Delta;
+            h[((size_t)l * n + j) * n + i] = p->vpg[l] * x - p->upg[l] * y;
+          }
+      if ((rc = pack_to(m, m->psipg, h.data()))) { msqg_destroy(m); return rc; }
+    }
+    std::vector<double> one((size_t)n * n, 1.);
+    if ((rc = pack_to(m, m->rd, one.data()))) { msqg_destroy(m); return rc; }
+  }
+  CK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return MSQG_OK;
+}
+
+extern "C" void msqg_destroy(msqg_model *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  List *all[] = {&m->psi, &m->q, &m->qpred, &m->dq, &m->zeta, &m->tmp, &m->psipg, &m->zetap, &m->qforc, &m->fr,
+                 &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->sstoch, &m->nstoch, &m->da, &m->res,
+                 &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l};
+  for (List *L : all) free_list(*L);
+  if (m->d_stage) cudaFree(m->d_stage);
+  if (m->d_scal) cudaFree(m->d_scal);
+  if (m->h_scal) cudaFreeHost(m->h_scal);
+  if (m->d_wind) cudaFree(m->d_wind);
+  if (m->d_kepart) cudaFree(m->d_kepart);
+  if (m->d_err) cudaFree(m->d_err);
+  if (m->h_err) cudaFreeHost(m->h_err);
+  if (m->mailbox) cudaFree(m->mailbox);
+  if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+extern "C" int msqg_set_stream(msqg_model *m, void *s) {
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  if (m->own_stream) cudaStreamDestroy(m->stream);
+  m->stream = (cudaStream_t)s;
+  m->own_stream = false;
+  return MSQG_OK;
+}
+extern "C" int msqg_nfields(msqg_model *m, int id) {
+  List *L = list_by_id(m, id);
+  return (L && L->lev[m->depth]) ? L->nf : 0;
+}
+extern "C" long msqg_launch_count(msqg_model *m) { return m->launches; }
+extern "C" long msqg_total_cycles(msqg_model *m) { return m->total_cycles; }
+extern "C" double msqg_get_ts_previous(msqg_model *m) { return m->ts_previous; }
+extern "C" void msqg_set_ts_previous(msqg_model *m, double v) { m->ts_previous = v; }
+extern "C" void msqg_seed_noise(msqg_model *m, unsigned seed) { srand(seed); m->noise_seeded = 1; }
+extern "C" int msqg_set_flag_topo(msqg_model *m, int flag) { m->flag_topo = flag; return MSQG_OK; }
+extern "C" int msqg_set_keep_dq(msqg_model *m, int keep) { m->keep_dq = keep; return MSQG_OK; }
+extern "C" int msqg_set_dissipation(msqg_model *m, double iRe, double iRe4, double Eks, double Ekb) {
+  m->iRe = iRe; m->iRe4 = iRe4; m->Eks = Eks; m->Ekb = Ekb; /* pystep_bfn flips these, qg_bfn.h:34-44 */
+  return MSQG_OK;
+}
+extern "C" int msqg_last_mgstats(msqg_model *m, int mode, msqg_mgstats *out) {
+  if (mode >= m->nl) FAIL(MSQG_ERR_ARG, "bad mode");
+  *out = mode < 0 ? m->mgpsi : m->mgmode[mode];
+  return MSQG_OK;
+}
+
+static int max_face_speed(msqg_model *m, List &L, double *umax_host);
+
+extern "C" int msqg_set_field(msqg_model *m, int id, const double *host) {
+  CK(cudaSetDevice(m->device));
+  List *L = list_by_id(m, id);
+  if (!L || !L->lev[m->depth]) FAIL(MSQG_ERR_ARG, "field list %d is not allocated", id);
+  int rc = pack_to(m, *L, host);
+  if (rc) return rc;
+  const size_t cnt = (size_t)L->nf * m->N * m->N;
+  if (id == MSQG_FR) m->h_fr.assign(host, host + cnt);
+  if (id == MSQG_SSTOCH) m->h_sstoch.assign(host, host + cnt);
+  if (id == MSQG_PSIPG || id == MSQG_QFORC) {
+    int nz = 0;
+    for (size_t c = 0; c < cnt && !nz; c++) nz = host[c] != 0.;
+    if (id == MSQG_PSIPG) m->has_pg = nz; else m->has_qforc = nz;
+  }
+  return MSQG_OK;
+}
+extern "C" int msqg_get_field(msqg_model *m, int id, double *host) {
+  CK(cudaSetDevice(m->device));
+  List *L = list_by_id(m, id);
+  if (!L || !L->lev[m->depth]) FAIL(MSQG_ERR_ARG, "field list %d is not allocated", id);
+  return unpack_from(m, *L, host);
+}
+
+/* ------------------------------------------------------------------ coefficients */
+static LayerMetrics metrics_of(msqg_model *m) {
+  LayerMetrics M;
+  for (int l = 0; l < MSQG_NLMAX; l++) { M.idh0[l] = 0.; M.idh1[l] = 0.; }
+  for (int l = 0; l < m->nl; l++) { M.idh0[l] = m->idh0[l]; M.idh1[l] = m->idh1[l]; }
+  return M;
+}
+
+/* Thomas coefficients of relax_layer for horizontally uniform stretching
+ * (poisson_layer.h:89-139, same expression order; host fp64 without FMA). */
+template <int NL>
+static RelaxCoef<NL> relax_coef_layers(msqg_model *m, int lev) {
+  RelaxCoef<NL> C;
+  const double Delta = m->g[lev].Delta;
+  const double *s = &m->s_lev[(size_t)lev * m->nl];
+  double t0[NL], t1[NL], t2[NL];
+  for (int l = 0; l < NL; l++) { t0[l] = t1[l] = t2[l] = 0.; }
+  if (NL > 1) {
+    int ll = 0;
+    t2[ll] = -sq(Delta) * s[ll] * m->idh1[ll];
+    t1[ll] = -t2[ll];
+    t1[ll] += 1. + 1.; t1[ll] += 1. + 1.;
+    for (ll = 1; ll < NL - 1; ll++) {
+      t0[ll] = -sq(Delta) * s[ll - 1] * m->idh0[ll];
+      t2[ll] = -sq(Delta) * s[ll] * m->idh1[ll];
+      t1[ll] = -t0[ll] - t2[ll];
+      t1[ll] += 1. + 1.; t1[ll] += 1. + 1.;
+    }
+    ll = NL - 1;
+    t0[ll] = -sq(Delta) * s[ll - 1] * m->idh0[ll];
+    t1[ll] = -t0[ll];
+    t1[ll] += 1. + 1.; t1[ll] += 1. + 1.;
+    for (ll = 1; ll < NL; ll++) t1[ll] -= t0[ll] * t2[ll - 1] / t1[ll - 1];
+  }
+  for (int l = 0; l < NL; l++) { C.t0[l] = t0[l]; C.t2[l] = t2[l]; C.t1p[l] = t1[l]; C.rinv[l] = 1. / t1[l]; }
+  C.msd2 = -sq(Delta);
+  return C;
+}
+/* [BASILISK] poisson.h relax(): d = -lambda*sq(Delta) + 2 + 2 */
+static RelaxCoef<1> relax_coef_scalar(msqg_model *m, int lev, double lambda) {
+  RelaxCoef<1> C;
+  const double Delta = m->g[lev].Delta;
+  double d = -lambda * sq(Delta);
+  d += 1. + 1.; d += 1. + 1.;
+  C.t0[0] = 0.; C.t2[0] = 0.; C.t1p[0] = d; C.rinv[0] = 1. / d;
+  C.msd2 = -sq(Delta);
+  return C;
+}
+
+/* ------------------------------------------------------------------ relax launch */
+static int ensure_mailbox(msqg_model *m, size_t words) {
+  if (words <= m->mailbox_words) return MSQG_OK;
+  if (m->mailbox) { CK(cudaStreamSynchronize(m->stream)); CK(cudaFree(m->mailbox)); m->mailbox = nullptr; }
+  CK(cudaMalloc(&m->mailbox, words * sizeof(unsigned long long)));
+  /* arm every entry with the "empty" NaN payload: byte pattern is not uniform, use a fill kernel */
+  m->mailbox_words = words;
+  return MSQG_OK;
+}
+__global__ void k_fill_u64(unsigned long long *p, size_t n, unsigned long long v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+template <int NL, int K>
+static int launch_relax_t(msqg_model *m, double *da, const double *res, int lev, int nsweeps, int init_zero,
+                          const RelaxCoef<NL> &C) {
+  constexpr int WPC = 4;
+  using Cfg = RelaxCfg<NL, K>;
+  const Geom &g = m->g[lev];
+  const int nworkers = (g.n + K - 1 + Cfg::W - 1) / Cfg::W;
+  const size_t words = (size_t)nworkers * K * g.n * NL;
+  /* size the mailbox once for the finest level of this K */
+  {
+    const Geom &gf = m->g[m->depth];
+    const int nwf = (gf.n + K - 1 + Cfg::W - 1) / Cfg::W;
+    const size_t wf = (size_t)nwf * K * gf.n * (size_t)m->nl;
+    const size_t need = words > wf ? words : wf;
+    if (need > m->mailbox_words) {
+      int rc = ensure_mailbox(m, need);
+      if (rc) return rc;
+      k_fill_u64<<<m->num_sms * 4, 256, 0, m->stream>>>(m->mailbox, m->mailbox_words, MAIL_EMPTY);
+      m->launches++;
+      CK(cudaGetLastError());
+    }
+  }
+  RelaxArgs A;
+  A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps; A.init_zero = init_zero;
+  A.mailbox = m->mailbox; A.err = m->d_err;
+  const size_t smem = Cfg::smem_per_warp * WPC;
+  auto kern = k_relax_lex<NL, K, WPC>;
+  static bool attr_set = false;
+  static int max_blocks_per_sm = 0;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, 32 * WPC, smem));
+    attr_set = true;
+  }
+  const int grid = (nworkers + WPC - 1) / WPC;
+  if (grid > max_blocks_per_sm * m->num_sms)
+    FAIL(MSQG_ERR_ARG, "relax wavefront needs %d co-resident CTAs, device holds %d (N too large for nl=%d)", grid,
+         max_blocks_per_sm * m->num_sms, NL);
+  RelaxCoef<NL> Cc = C;
+  void *args[] = {(void *)&A, (void *)&Cc};
+  /* workers spin on their left neighbour: cooperative launch guarantees co-residency */
+  CK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(32 * WPC), args, smem, m->stream));
+  m->launches++;
+  return MSQG_OK;
+}
+
+template <int NL>
+static int launch_relax(msqg_model *m, double *da, const double *res, int lev, int nrelax, int init_zero,
+                        const RelaxCoef<NL> &C) {
+  int done = 0;
+  while (done < nrelax) {
+    int ns = nrelax - done;
+    int rc;
+    if (ns <= 4) rc = launch_relax_t<NL, 4>(m, da, res, lev, ns, init_zero && done == 0, C);
+    else { if (ns > 8) ns = 8; rc = launch_relax_t<NL, 8>(m, da, res, lev, ns, init_zero && done == 0, C); }
+    if (rc) return rc;
+    done += ns;
+  }
+  return MSQG_OK;
+}
+
+#define NL_CASE(n, ...) case n: { constexpr int NL = n; __VA_ARGS__; } break;
+#define NL_SWITCH(nl, ...)                                  \
+  switch (nl) {                                             \
+    NL_CASE(2, __VA_ARGS__) NL_CASE(3, __VA_ARGS__) NL_CASE(4, __VA_ARGS__) NL_CASE(5, __VA_ARGS__)   \
+    NL_CASE(6, __VA_ARGS__) NL_CASE(7, __VA_ARGS__) NL_CASE(8, __VA_ARGS__) NL_CASE(9, __VA_ARGS__)   \
+    NL_CASE(10, __VA_ARGS__) NL_CASE(11, __VA_ARGS__) NL_CASE(12, __VA_ARGS__)                        \
+    default: FAIL(MSQG_ERR_ARG, "unsupported nl=%d", nl);   \
+  }
+
+static int check_relax_err(msqg_model *m) {
+  CK(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  if (*m->h_err) {
+    CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
+    k_fill_u64<<<m->num_sms * 4, 256, 0, m->stream>>>(m->mailbox, m->mailbox_words, MAIL_EMPTY);
+    FAIL(MSQG_ERR_CUDA, "relax wavefront timed out waiting on a neighbour strip");
+  }
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ multigrid */
+struct MgProblem {
+  int nf;            /* nl (layer-coupled) or 1 (one vertical mode) */
+  int mode;          /* -1 layer-coupled, else mode index */
+  double *a;         /* finest-level unknown, nf planes, ghosts maintained */
+  const double *b;   /* finest-level rhs */
+};
+
+static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), m->stream));
+  dim3 b(64, 4);
+  if (P.mode < 0) {
+    LayerMetrics M = metrics_of(m);
+    NL_SWITCH(m->nl, k_residual<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->str.lev[D], g, M, m->d_scal));
+  } else {
+    k_residual_scalar<<<grid2(g.n, g.n, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->ibu.lev[D] + (size_t)P.mode * g.plane, g, m->d_scal);
+  }
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(m->h_scal, m->d_scal, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  *maxres = m->h_scal[0];
+  return MSQG_OK;
+}
+
+/* mg_cycle, mspg/elliptic.h:43-99 with minlevel = 1 (poisson_layer.h:297) */
+static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
+  const int D = m->depth;
+  dim3 b(32, 8);
+  /* restriction(res): levels D-1..1 (level 0 is never read with minlevel = 1) */
+  for (int l = D - 1; l >= 1; l--) {
+    k_restrict<<<grid2(m->g[l].n, m->g[l].n, b, P.nf), b, 0, m->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
+    m->launches++;
+  }
+  CK(cudaGetLastError());
+  const int minlevel = D < 1 ? D : 1;
+  for (int l = minlevel; l <= D; l++) {
+    const Geom &g = m->g[l];
+    int init_zero = 0;
+    if (l == minlevel) init_zero = 1; /* da = 0 on the coarsest level */
+    else {
+      k_prolong<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
+      m->launches++;
+      CK(cudaGetLastError());
+    }
+    int rc;
+    if (P.mode < 0) {
+      NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, init_zero, C); });
+    } else {
+      auto C = relax_coef_scalar(m, l, m->lam_lev[(size_t)l * m->nl + P.mode]);
+      rc = launch_relax<1>(m, m->da.lev[l], m->res.lev[l], l, nrelax, init_zero, C);
+    }
+    if (rc) return rc;
+  }
+  const Geom &g = m->g[D];
+  k_correct<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(P.a, m->da.lev[D], g);
+  m->launches++;
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+
+/* mg_solve, mspg/elliptic.h:145-229: NITERMIN=1, NITERMAX=100, nrelax starts at 4 */
+static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mgstats *st) {
+  msqg_mgstats s;
+  memset(&s, 0, sizeof(s));
+  s.nrelax = 4;
+  double resb;
+  int rc = mg_residual(m, P, &resb);
+  if (rc) return rc;
+  s.resb = s.resa = resb;
+  for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > tolerance); s.i++) {
+    if ((rc = mg_cycle(m, P, s.nrelax))) return rc;
+    if ((rc = mg_residual(m, P, &s.resa))) return rc;
+    if (s.resa > tolerance) {
+      if (resb / s.resa < 1.2 && s.nrelax < 100) s.nrelax++;
+      else if (resb / s.resa > 10 && s.nrelax > 2) s.nrelax--;
+    }
+    resb = s.resa;
+  }
+  if ((rc = check_relax_err(m))) return rc;
+  m->total_cycles += s.i;
+  *st = s;
+  return MSQG_OK;
+}
+
+/* invertq, msqg/qg.h:113-163 */
+static int invertq_list(msqg_model *m, List &ql) {
+  if (!m->const_set) FAIL(MSQG_ERR_ARG, "set_const must be called before invertq");
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  int rc;
+  if (!m->p.mode_pv_invert) {
+    if (!m->s_uniform) FAIL(MSQG_ERR_ARG, "horizontally varying stretching is not supported by the relax kernel yet");
+    MgProblem P{m->nl, -1, m->psi.lev[D], ql.lev[D]};
+    if ((rc = mg_solve(m, P, 1e-3, &m->mgpsi))) return rc;
+  } else {
+    if (!m->modes_uniform) FAIL(MSQG_ERR_ARG, "horizontally varying vertical modes are not supported yet");
+    dim3 b(64, 4);
+    NL_SWITCH(m->nl, {
+      ModeMat<NL> M;
+      for (int k = 0; k < NL * NL; k++) M.a[k] = m->h_cl2m[k];
+      k_project<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(ql.lev[D], m->qm.lev[D], g, M, nullptr, 0);
+    });
+    m->launches++;
+    CK(cudaGetLastError());
+    for (int l = 0; l < m->nl; l++) {
+      MgProblem P{1, l, m->pm.lev[D] + (size_t)l * g.plane, m->qm.lev[D] + (size_t)l * g.plane};
+      if ((rc = mg_solve(m, P, 1e-3, &m->mgmode[l]))) return rc;
+      m->mgpsi = m->mgmode[l];
+    }
+    NL_SWITCH(m->nl, {
+      ModeMat<NL> M;
+      for (int k = 0; k < NL * NL; k++) M.a[k] = m->h_cm2l[k];
+      k_project<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(m->pm.lev[D], m->psi.lev[D], g, M, nullptr, 1);
+    });
+    m->launches++;
+    CK(cudaGetLastError());
+  }
+  return MSQG_OK;
+}
+extern "C" int msqg_invertq(msqg_model *m, int q_id) {
+  CK(cudaSetDevice(m->device));
+  List *L = list_by_id(m, q_id);
+  if (!L || L->nf != m->nl) FAIL(MSQG_ERR_ARG, "bad q list");
+  return invertq_list(m, *L);
+}
+
+extern "C" int msqg_comp_q(msqg_model *m) {
+  CK(cudaSetDevice(m->device));
+  const Geom &g = m->g[m->depth];
+  dim3 b(64, 4);
+  LayerMetrics M = metrics_of(m);
+  NL_SWITCH(m->nl, k_comp_q<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(m->psi.lev[m->depth], m->str.lev[m->depth], m->q.lev[m->depth], g, M));
+  m->launches++;
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ eigmod (setup) */
+typedef void (*dgeev_fn)(const char *, const char *, const int *, double *, const int *, double *, double *, double *,
+                         const int *, double *, const int *, double *, const int *, int *, size_t, size_t);
+static dgeev_fn find_dgeev() {
+  static dgeev_fn fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  const char *cands[] = {getenv("MSQG_LAPACK"), "liblapack.so.3", "liblapack.so", "libopenblas.so.0", "libopenblas.so"};
+  for (const char *c : cands) {
+    if (!c) continue;
+    void *h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) continue;
+    fn = (dgeev_fn)dlsym(h, "dgeev_");
+    if (!fn) fn = (dgeev_fn)dlsym(h, "scipy_dgeev_");
+    if (fn) break;
+  }
+  return fn;
+}
+struct eig_pair { double v; int idx; };
+static int cmp_eig(const void *a, const void *b) {
+  double x = ((const eig_pair *)a)->v, y = ((const eig_pair *)b)->v;
+  return (x > y) - (x < y);
+}
+/* eigmod for one column, msqg/eigmode.h:74-266 (LAPACKE_dgeev row-major == dgeev_
+ * on the transposed matrix with vl/vr transposed back) */
+static int eigmod_column(int nl, const double *dhf, const double *Fr, double Ro, double *cl2m, double *cm2l, double *iBu) {
+  dgeev_fn dgeev = find_dgeev();
+  if (!dgeev) FAIL(MSQG_ERR_CONFIG, "MODE_PV_INVERT needs LAPACK dgeev (msqg/eigmode.h:153): set MSQG_LAPACK to a LAPACK/OpenBLAS shared library");
+  double dhc[MSQG_MAXL];
+  for (int l = 0; l < nl - 1; l++) dhc[l] = 0.5 * (dhf[l] + dhf[l + 1]);
+  std::vector<double> amat((size_t)nl * nl, 0.), acm((size_t)nl * nl), vl((size_t)nl * nl), vr((size_t)nl * nl),
+      vlc((size_t)nl * nl), vrc((size_t)nl * nl), tmp((size_t)nl * nl);
+  double wr[MSQG_MAXL], wi[MSQG_MAXL];
+  eig_pair wr2[MSQG_MAXL];
+  {
+    int l = 0;
+    amat[nl * l + l + 1] = -sq(Fr[l] / Ro) / (dhc[l] * dhf[l]);
+    amat[nl * l + l] = -amat[nl * l + l + 1];
+    for (l = 1; l < nl - 1; l++) {
+      amat[nl * l + l - 1] = -sq(Fr[l - 1] / Ro) / (dhc[l - 1] * dhf[l]);
+      amat[nl * l + l + 1] = -sq(Fr[l] / Ro) / (dhc[l] * dhf[l]);
+      amat[nl * l + l] = -amat[nl * l + l - 1] - amat[nl * l + l + 1];
+    }
+    l = nl - 1;
+    amat[nl * l + l - 1] = -sq(Fr[l - 1] / Ro) / (dhc[l - 1] * dhf[l]);
+    amat[nl * l + l] = -amat[nl * l + l - 1];
+  }
+  for (int r = 0; r < nl; r++)
+    for (int c = 0; c < nl; c++) acm[r + nl * c] = amat[nl * r + c];
+  int info = 0, lwork = 8 * nl + 64;
+  std::vector<double> work(lwork);
+  dgeev("V", "V", &nl, acm.data(), &nl, wr, wi, vlc.data(), &nl, vrc.data(), &nl, work.data(), &lwork, &info, 1, 1);
+  if (info < 0) FAIL(MSQG_ERR_CONFIG, "issue with lapack in eigmode (info=%d)", info);
+  for (int r = 0; r < nl; r++)
+    for (int c = 0; c < nl; c++) { vl[r * nl + c] = vlc[r + nl * c]; vr[r * nl + c] = vrc[r + nl * c]; }
+  for (int l = 0; l < nl; l++) { wr2[l].v = wr[l]; wr2[l].idx = l; }
+  qsort(wr2, nl, sizeof(eig_pair), cmp_eig);
+  for (int l = 0; l < nl; l++) wr[l] = wr2[l].v;
+  tmp = vr;
+  for (int mm = 0; mm < nl; mm++)
+    for (int k = 0; k < nl; k++) vr[k * nl + mm] = tmp[k * nl + wr2[mm].idx];
+  tmp = vl;
+  for (int mm = 0; mm < nl; mm++)
+    for (int k = 0; k < nl; k++) vl[k * nl + mm] = tmp[k * nl + wr2[mm].idx];
+  const double htotal = 1.;
+  for (int mm = 0; mm < nl; mm++) {
+    double dotp = 0.;
+    for (int k = 0; k < nl; k++) dotp += dhf[k] * vr[k * nl + mm] * vr[k * nl + mm];
+    const double flfac = (vr[mm] > 0 ? 1 : -1) * sqrt(htotal / dotp);
+    for (int k = 0; k < nl; k++) vr[k * nl + mm] = flfac * vr[k * nl + mm];
+  }
+  for (int mm = 0; mm < nl; mm++) {
+    double dotp = 0.;
+    for (int k = 0; k < nl; k++) dotp += vr[k * nl + mm] * vl[k * nl + mm];
+    for (int k = 0; k < nl; k++) vl[k * nl + mm] = vl[k * nl + mm] / dotp;
+  }
+  for (int mm = 0; mm < nl; mm++)
+    for (int k = 0; k < nl; k++) {
+      cl2m[k * nl + mm] = vl[mm * nl + k];
+      cm2l[k * nl + mm] = vr[k * nl + mm];
+    }
+  for (int l = 0; l < nl; l++) iBu[l] = -wr[l];
+  iBu[0] = 0.;
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ set_const */
+static inline double avg4(double a, double b, double c, double d) {
+  /* [BASILISK] restriction_average order */
+  double sum = 0.;
+  sum += a; sum += b; sum += c; sum += d;
+  return sum / 4;
+}
+
+static int max_face_speed(msqg_model *m, List &L, double *umax_host) {
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
+  dim3 b(64, 4);
+  /* out-of-place laplacian into tmp is a by-product; only umax is wanted */
+  k_lap<<<grid2(g.n + 1, g.n + 1, b, m->nl), b, 0, m->stream>>>(L.lev[D], m->tmp.lev[D], g, m->d_scal + 1);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(m->h_scal + 1, m->d_scal + 1, m->nl * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  for (int l = 0; l < m->nl; l++) umax_host[l] = m->h_scal[1 + l];
+  return MSQG_OK;
+}
+
+extern "C" int msqg_set_const(msqg_model *m) {
+  CK(cudaSetDevice(m->device));
+  const int n = m->N, nl = m->nl, D = m->depth;
+  const Geom &g = m->g[D];
+  const double Delta = m->p.L0 / n;
+  /* sanity checks, qg.h:990-1012 */
+  for (int l = 0; l < nl; l++)
+    if (m->dhf[l] == 0) FAIL(MSQG_ERR_CONFIG, "thickness = 0: aborting\nCheck the definition of dh in params.in");
+  if (m->p.Rom <= 0) FAIL(MSQG_ERR_CONFIG, "Rom <= 0: aborting");
+  /* layer metrics, qg.h:1017-1027 */
+  for (int l = 0; l < nl - 1; l++) m->dhc[l] = 0.5 * (m->dhf[l] + m->dhf[l + 1]);
+  m->idh0[0] = 0.;
+  m->idh1[0] = 1. / (m->dhc[0] * m->dhf[0]);
+  for (int l = 1; l < nl - 1; l++) {
+    m->idh0[l] = 1. / (m->dhc[l - 1] * m->dhf[l]);
+    m->idh1[l] = 1. / (m->dhc[l] * m->dhf[l]);
+  }
+  m->idh0[nl - 1] = 1. / (m->dhc[nl - 2] * m->dhf[nl - 1]);
+  m->idh1[nl - 1] = 0.;
+  /* Ro(y), qg.h:1032-1037 */
+  std::vector<double> ro_y(n);
+  for (int j = 0; j < n; j++) {
+    const double y = (j + 0.5) * Delta;
+    ro_y[j] = m->p.varRo > 0 ? m->p.Rom / (1 + m->p.Rom * m->p.beta * (y - 0.5 * m->p.L0)) : m->p.Rom;
+  }
+  int rc;
+  {
+    std::vector<double> h((size_t)n * n);
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) h[(size_t)j * n + i] = ro_y[j];
+    if ((rc = pack_to(m, m->ro, h.data()))) return rc;
+  }
+  /* strl = sq(Fr/Ro), qg.h:1043-1048 (layers 0..nl-2; layer nl-1 stays 0) */
+  std::vector<double> hs((size_t)nl * n * n, 0.);
+  bool uniform = true;
+  for (int l = 0; l < nl - 1; l++) {
+    const double *fr = &m->h_fr[(size_t)l * n * n];
+    double *s = &hs[(size_t)l * n * n];
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) s[(size_t)j * n + i] = sq(fr[(size_t)j * n + i] / ro_y[j]);
+    for (size_t c = 1; c < (size_t)n * n && uniform; c++) uniform = s[c] == s[0];
+  }
+  if ((rc = pack_to(m, m->str, hs.data()))) return rc;
+  m->s_uniform = uniform;
+  /* restriction(strl) (poisson_layer.h:284): fields on the device, per-level
+     constants on the host for the uniform case (same summation order) */
+  {
+    dim3 b(32, 8);
+    for (int l = D - 1; l >= 1; l--) {
+      k_restrict<<<grid2(m->g[l].n, m->g[l].n, b, nl), b, 0, m->stream>>>(m->str.lev[l + 1], m->str.lev[l], m->g[l + 1], m->g[l], 1., 1);
+      m->launches++;
+    }
+    CK(cudaGetLastError());
+  }
+  m->s_lev.assign((size_t)(D + 1) * nl, 0.);
+  if (uniform) {
+    for (int l = 0; l < nl - 1; l++) m->s_lev[(size_t)D * nl + l] = hs[(size_t)l * n * n];
+    for (int lev = D - 1; lev >= 0; lev--)
+      for (int l = 0; l < nl; l++) {
+        const double v = m->s_lev[(size_t)(lev + 1) * nl + l];
+        m->s_lev[(size_t)lev * nl + l] = avg4(v, v, v, v);
+      }
+  }
+  /* wind forcing table, qg.h:451, host libm so that sin() matches the reference */
+  {
+    std::vector<double> w(n);
+    const double pi = 3.14159265358979323846, L0 = m->p.L0;
+    for (int j = 0; j < n; j++) {
+      const double y = (j + 0.5) * Delta;
+      w[j] = m->p.tau0 / (m->p.Rom * m->dhf[0]) * sin(2 * pi * y / L0) * sin(pi * y / L0);
+    }
+    CK(cudaMemcpyAsync(m->d_wind, w.data(), n * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  std::vector<double> sig((size_t)n * n);
+  if (m->p.mode_pv_invert) {
+    /* eigmod, qg.h:1053 -> eigmode.h:65-308.  Inputs depend on (Fr, Ro) only. */
+    bool fr_uniform = true;
+    for (int l = 0; l < nl - 1 && fr_uniform; l++)
+      for (size_t c = 1; c < (size_t)n * n && fr_uniform; c++) fr_uniform = m->h_fr[(size_t)l * n * n + c] == m->h_fr[(size_t)l * n * n];
+    m->modes_uniform = fr_uniform && m->p.varRo <= 0;
+    if (!m->modes_uniform) FAIL(MSQG_ERR_ARG, "MODE_PV_INVERT with spatially varying Fr/Ro is not supported yet");
+    double fr[MSQG_MAXL];
+    for (int l = 0; l < nl - 1; l++) fr[l] = m->h_fr[(size_t)l * n * n];
+    if ((rc = eigmod_column(nl, m->dhf, fr, ro_y[0], m->h_cl2m, m->h_cm2l, m->h_ibu))) return rc;
+    std::vector<double> h((size_t)nl * nl * n * n);
+    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < (size_t)n * n; c++) h[(size_t)k * n * n + c] = m->h_cl2m[k];
+    if ((rc = pack_to(m, m->cl2m, h.data()))) return rc;
+    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < (size_t)n * n; c++) h[(size_t)k * n * n + c] = m->h_cm2l[k];
+    if ((rc = pack_to(m, m->cm2l, h.data()))) return rc;
+    for (int k = 0; k < nl; k++) for (size_t c = 0; c < (size_t)n * n; c++) h[(size_t)k * n * n + c] = m->h_ibu[k];
+    if ((rc = pack_to(m, m->ibu, h.data()))) return rc;
+    /* poisson(): restriction({alpha,lambda}) [BASILISK] -> per-level lambda */
+    m->lam_lev.assign((size_t)(D + 1) * nl, 0.);
+    for (int l = 0; l < nl; l++) m->lam_lev[(size_t)D * nl + l] = m->h_ibu[l];
+    for (int lev = D - 1; lev >= 0; lev--)
+      for (int l = 0; l < nl; l++) {
+        const double v = m->lam_lev[(size_t)(lev + 1) * nl + l];
+        m->lam_lev[(size_t)lev * nl + l] = avg4(v, v, v, v);
+      }
+    for (size_t c = 0; c < (size_t)n * n; c++) sig[c] = fmin(m->p.afilt * sqrt(-1 / m->h_ibu[1]), m->p.Lfmax);
+  } else {
+    std::vector<double> rd((size_t)n * n);
+    if ((rc = unpack_from(m, m->rd, rd.data()))) return rc;
+    for (size_t c = 0; c < (size_t)n * n; c++) sig[c] = fmin(m->p.afilt * rd[c], m->p.Lfmax);
+  }
+  if ((rc = pack_to(m, m->sigfilt, sig.data()))) return rc;
+  m->const_set = 1;
+  /* comp_q(pol,qol), qg.h:1092 */
+  if ((rc = msqg_comp_q(m))) return rc;
+  /* flsrv: zeta_pg = laplacian(psi_pg), qg.h:1094-1097; also its CFL speeds (static) */
+  m->has_zp = 0;
+  if (m->has_pg) {
+    if ((rc = max_face_speed(m, m->psipg, m->umax_pg))) return rc;
+    if (m->p.flsrv == 1) {
+      dim3 b(64, 4);
+      k_lap<<<grid2(g.n + 1, g.n + 1, b, nl), b, 0, m->stream>>>(m->psipg.lev[D], m->zetap.lev[D], g, nullptr);
+      m->launches++;
+      CK(cudaGetLastError());
+      m->has_zp = 1;
+    }
+  } else
+    for (int l = 0; l < nl; l++) m->umax_pg[l] = 0.;
+  CK(cudaStreamSynchronize(m->stream));
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ RHS */
+/* timestep() [BASILISK] given the max face speed of one face vector */
+static double timestep_chain(msqg_model *m, double umax, double dtmax, double Delta) {
+  const double CFL = m->p.CFL;
+  dtmax /= CFL;
+  if (umax != 0.) {
+    const double dt = Delta / umax;
+    if (dt < dtmax) dtmax = dt;
+  }
+  dtmax *= CFL;
+  if (dtmax > m->ts_previous) dtmax = (m->ts_previous + 0.1 * dtmax) / 1.1;
+  m->ts_previous = dtmax;
+  return dtmax;
+}
+
+/* zeta = laplacian(psi) (+ umax), tmp = laplacian(zeta) if viscosity is on */
+static int rhs_prepare(msqg_model *m) {
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  dim3 b(64, 4);
+  CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
+  k_lap<<<grid2(g.n + 1, g.n + 1, b, m->nl), b, 0, m->stream>>>(m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
+  m->launches++;
+  if (m->iRe != 0. || m->iRe4 != 0.) {
+    k_lap<<<grid2(g.n + 1, g.n + 1, b, m->nl), b, 0, m->stream>>>(m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+    m->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(m->h_scal + 1, m->d_scal + 1, m->nl * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  return MSQG_OK;
+}
+/* dtmax chain of advection_pv, qg.h:383-391 (needs the umax D2H to have completed) */
+static double dt_chain(msqg_model *m, double dtmax) {
+  const double Delta = m->g[m->depth].Delta;
+  for (int l = 0; l < m->nl; l++) {
+    dtmax = timestep_chain(m, m->h_scal[1 + l], dtmax, Delta);
+    dtmax = timestep_chain(m, m->umax_pg[l], dtmax, Delta);
+  }
+  return dtmax;
+}
+
+static int rhs_launch(msqg_model *m, List &q_ev, const double *q_in, double *q_out, double *dq, double dt, float dts) {
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  const int nl = m->nl;
+  RhsArgs A;
+  memset(&A, 0, sizeof(A));
+  A.psi = m->psi.lev[D]; A.zeta = m->zeta.lev[D]; A.tmp = m->tmp.lev[D]; A.pp = m->psipg.lev[D];
+  A.zp = m->zetap.lev[D]; A.s = m->str.lev[D]; A.qforc = m->has_qforc ? m->qforc.lev[D] : nullptr;
+  A.topo = m->topo.lev[D]; A.ro = m->ro.lev[D];
+  A.q_in = q_in; A.q_ev = q_ev.lev[D]; A.q_out = q_out; A.dq = dq;
+  A.noise = m->p.stochastic ? m->nstoch.lev[D] : nullptr;
+  A.wind = m->d_wind; A.g = g;
+  for (int l = 0; l < nl; l++) { A.idh0[l] = m->idh0[l]; A.idh1[l] = m->idh1[l]; }
+  A.beta = m->p.beta; A.iRe = m->iRe; A.iRe4 = m->iRe4;
+  A.ceks = m->Eks / (m->p.Rom * 2 * m->dhf[0]);
+  A.cekb = m->Ekb / (m->p.Rom * 2 * m->dhf[nl - 1]);
+  A.dhb = m->dhf[nl - 1];
+  A.dt = dt; A.itr = m->p.itr_stoch; A.dts = dts;
+  A.has_pg = m->has_pg; A.has_zp = m->has_zp; A.use_tmp = (m->iRe != 0. || m->iRe4 != 0.);
+  A.flag_topo = m->flag_topo; A.stochastic = m->p.stochastic;
+  dim3 b(32, 4);
+  NL_SWITCH(nl, k_rhs<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(A));
+  m->launches++;
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+
+/* update_qg(evolving = q_id, updates = DQ, dtmax), qg.h:609-650 */
+extern "C" int msqg_update(msqg_model *m, int q_id, double dtmax, double *dtmax_out) {
+  CK(cudaSetDevice(m->device));
+  List *L = list_by_id(m, q_id);
+  if (!L || L->nf != m->nl) FAIL(MSQG_ERR_ARG, "bad q list");
+  int rc;
+  if ((rc = invertq_list(m, *L))) return rc;
+  if ((rc = rhs_prepare(m))) return rc;
+  if ((rc = rhs_launch(m, *L, nullptr, nullptr, m->dq.lev[m->depth], 0., 0.f))) return rc;
+  CK(cudaStreamSynchronize(m->stream));
+  if (dtmax_out) *dtmax_out = dt_chain(m, dtmax);
+  return MSQG_OK;
+}
+
+/* normal_noise / generate_noise, qg_stochastic.h:9,117-126: libc rand() in the
+ * reference traversal order (x outer, y inner, layer innermost) on the host. */
+static int generate_noise(msqg_model *m) {
+  const int n = m->N, nl = m->nl;
+  const double pi = 3.14159265358979323846;
+  if (m->h_sstoch.empty()) m->h_sstoch.assign((size_t)nl * n * n, 0.);
+  m->h_noise.resize((size_t)nl * n * n);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) {
+        const double gsn = sqrt(-2. * log(((double)(rand()) + 1.) / ((double)(RAND_MAX) + 2.))) *
+                           cos(2 * pi * rand() / (double)RAND_MAX);
+        const size_t c = ((size_t)l * n + j) * n + i;
+        m->h_noise[c] = m->p.amp_stoch * m->h_sstoch[c] * gsn;
+      }
+  return pack_to(m, m->nstoch, m->h_noise.data());
+}
+
+/* advance_qg(output, input, updates = DQ, dt), qg.h:594-606 / qg_stochastic.h:128-149 */
+extern "C" int msqg_advance(msqg_model *m, int out_id, int in_id, double dt) {
+  CK(cudaSetDevice(m->device));
+  List *O = list_by_id(m, out_id), *I = list_by_id(m, in_id);
+  if (!O || !I || O->nf != m->nl || I->nf != m->nl) FAIL(MSQG_ERR_ARG, "bad list");
+  const Geom &g = m->g[m->depth];
+  float dts = 0.f;
+  const double *noise = nullptr;
+  if (m->p.stochastic) {
+    m->corrector_step = (m->corrector_step + 1) % 2;
+    dts = sqrt(dt);
+    if (m->corrector_step) {
+      int rc = generate_noise(m);
+      if (rc) return rc;
+      dts = dts / sqrt(2);
+    }
+    noise = m->nstoch.lev[m->depth];
+  }
+  dim3 b(64, 4);
+  k_advance<<<grid2(g.n, g.n, b, m->nl), b, 0, m->stream>>>(O->lev[m->depth], I->lev[m->depth], m->dq.lev[m->depth], noise, g, dt, dts);
+  m->launches++;
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+
+/* One iteration of [BASILISK] run() (predictor-corrector.h), SURVEY.md 3.1:
+ *   dt = dtnext(update(evolving, updates, DT));
+ *   advance(predictor, evolving, updates, dt/2); update(predictor, updates, dt);
+ *   advance(evolving, evolving, updates, dt)
+ * with RHS and stage update fused (k_rhs).  dtnext() [BASILISK] rounds dt so
+ * that t lands on tnext_event (pass a negative value for "no pending event"). */
+extern "C" int msqg_step(msqg_model *m, double t, double tnext_event, double *dt_out, double *tnext_out) {
+  CK(cudaSetDevice(m->device));
+  const int D = m->depth;
+  int rc;
+  /* stage 1 */
+  if ((rc = invertq_list(m, m->q))) return rc;
+  if ((rc = rhs_prepare(m))) return rc;
+  CK(cudaStreamSynchronize(m->stream));
+  double dt = dt_chain(m, m->p.DT);
+  double tnext;
+  if (tnext_event >= 0 && tnext_event > t) {
+    /* dtnext(), [BASILISK] events: TEPS = 1e-9 */
+    unsigned int nn = (tnext_event - t) / dt;
+    tnext = tnext_event;
+    if (nn == 0) dt = tnext_event - t;
+    else {
+      const double dt1 = (tnext_event - t) / nn;
+      if (dt1 > dt * (1. + 1e-9)) dt = (tnext_event - t) / (nn + 1);
+      else if (dt1 < dt) dt = dt1;
+      tnext = t + dt;
+    }
+  } else
+    tnext = t + dt;
+  float dts = 0.f;
+  if (m->p.stochastic) {
+    m->corrector_step = (m->corrector_step + 1) % 2;
+    dts = sqrt(dt / 2.);
+    if (m->corrector_step) {
+      if ((rc = generate_noise(m))) return rc;
+      dts = dts / sqrt(2);
+    }
+  }
+  double *dqp = m->keep_dq ? m->dq.lev[D] : nullptr;
+  if ((rc = rhs_launch(m, m->q, m->q.lev[D], m->qpred.lev[D], dqp, dt / 2., dts))) return rc;
+  /* stage 2 */
+  if ((rc = invertq_list(m, m->qpred))) return rc;
+  if ((rc = rhs_prepare(m))) return rc;
+  if (m->p.stochastic) {
+    m->corrector_step = (m->corrector_step + 1) % 2;
+    dts = sqrt(dt);
+    if (m->corrector_step) {
+      if ((rc = generate_noise(m))) return rc;
+      dts = dts / sqrt(2);
+    }
+  }
+  if ((rc = rhs_launch(m, m->qpred, m->q.lev[D], m->q.lev[D], dqp, dt, dts))) return rc;
+  CK(cudaStreamSynchronize(m->stream));
+  (void)dt_chain(m, dt); /* update()'s return value is ignored in stage 2; timestep()'s static state is not */
+  if (dt_out) *dt_out = dt;
+  if (tnext_out) *tnext_out = tnext;
+  return MSQG_OK;
+}
+
+/* writestdout, qg.c:101-106 */
+extern "C" int msqg_ke1(msqg_model *m, double *ke) {
+  CK(cudaSetDevice(m->device));
+  const Geom &g = m->g[m->depth];
+  dim3 b(16, 16);
+  dim3 gr = grid2(g.n, g.n, b);
+  k_ke_partial<<<gr, b, 0, m->stream>>>(m->psi.lev[m->depth], g, m->d_kepart);
+  m->launches++;
+  CK(cudaGetLastError());
+  std::vector<double> part((size_t)gr.x * gr.y);
+  CK(cudaMemcpyAsync(part.data(), m->d_kepart, part.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  double s = 0.;
+  for (double v : part) s -= v;
+  *ke = s;
+  return MSQG_OK;
+}
+
+/* tendency of pystep_bfn (qg_bfn.h:46-63, vartype == 1): like update_qg without
+ * qforcing; the caller has set q and the signed dissipation coefficients. */
+extern "C" int msqg_tendency_bfn(msqg_model *m, double direction) {
+  CK(cudaSetDevice(m->device));
+  const double Re = m->p.Re, Re4 = m->p.Re4;
+  if (direction > 0) {
+    m->iRe = (Re == 0) ? 0. : 1 / Re; m->iRe4 = (Re4 == 0) ? 0. : -1 / Re4;
+    m->Eks = fabs(m->Eks); m->Ekb = fabs(m->Ekb);
+  } else {
+    m->iRe = (Re == 0) ? 0. : -1 / Re; m->iRe4 = (Re4 == 0) ? 0. : 1 / Re4;
+    m->Eks = -fabs(m->Eks); m->Ekb = -fabs(m->Ekb);
+  }
+  int rc;
+  if ((rc = invertq_list(m, m->q))) return rc;
+  if ((rc = rhs_prepare(m))) return rc;
+  const int hq = m->has_qforc;
+  m->has_qforc = 0;
+  rc = rhs_launch(m, m->q, nullptr, nullptr, m->dq.lev[m->depth], 0., 0.f);
+  m->has_qforc = hq;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(m->stream));
+  (void)dt_chain(m, m->p.DT); /* advection_pv still runs timestep(): static state advances */
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ test hooks */
+static int upload_level(msqg_model *m, double *dst, const double *host, int nf, int lev, double sg) {
+  const Geom &g = m->g[lev];
+  size_t cnt = (size_t)nf * g.n * g.n;
+  if (cnt > m->stage_doubles) FAIL(MSQG_ERR_ARG, "staging buffer too small");
+  CK(cudaMemcpyAsync(m->d_stage, host, cnt * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  dim3 b(32, 8);
+  k_pack<<<grid2(g.n + 2, g.n + 2, b, nf), b, 0, m->stream>>>(dst, m->d_stage, nf, g, sg);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->stream));
+  return MSQG_OK;
+}
+static int download_level(msqg_model *m, double *host, const double *src, int nf, int lev) {
+  const Geom &g = m->g[lev];
+  size_t cnt = (size_t)nf * g.n * g.n;
+  dim3 b(32, 8);
+  k_unpack<<<grid2(g.n, g.n, b, nf), b, 0, m->stream>>>(m->d_stage, src, nf, g);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host, m->d_stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return MSQG_OK;
+}
+
+/* nsweeps x { relax_layer ; boundary_level } on level `level` with the model's
+ * stretching and metrics; a, b host [nl][n][n]. */
+extern "C" int msqg_test_relax(msqg_model *m, int level, double *a, const double *b, int nsweeps) {
+  CK(cudaSetDevice(m->device));
+  if (level < 1 || level > m->depth) FAIL(MSQG_ERR_ARG, "bad level");
+  if (!m->const_set || !m->s_uniform) FAIL(MSQG_ERR_ARG, "needs set_const and uniform stretching");
+  int rc;
+  if ((rc = upload_level(m, m->da.lev[level], a, m->nl, level, -1.))) return rc;
+  if ((rc = upload_level(m, m->res.lev[level], b, m->nl, level, -1.))) return rc;
+  NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, level); rc = launch_relax<NL>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, 0, C); });
+  if (rc) return rc;
+  if ((rc = check_relax_err(m))) return rc;
+  return download_level(m, a, m->da.lev[level], m->nl, level);
+}
+/* scalar Helmholtz relax (modal path) with constant lambda */
+extern "C" int msqg_test_relax_scalar(msqg_model *m, int level, double lambda, double *a, const double *b, int nsweeps) {
+  CK(cudaSetDevice(m->device));
+  if (level < 1 || level > m->depth) FAIL(MSQG_ERR_ARG, "bad level");
+  int rc;
+  if ((rc = upload_level(m, m->da.lev[level], a, 1, level, -1.))) return rc;
+  if ((rc = upload_level(m, m->res.lev[level], b, 1, level, -1.))) return rc;
+  auto C = relax_coef_scalar(m, level, lambda);
+  if ((rc = launch_relax<1>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, 0, C))) return rc;
+  if ((rc = check_relax_err(m))) return rc;
+  return download_level(m, a, m->da.lev[level], 1, level);
+}
+extern "C" int msqg_test_residual(msqg_model *m, const double *a, const double *b, double *res, double *maxres) {
+  CK(cudaSetDevice(m->device));
+  if (!m->const_set) FAIL(MSQG_ERR_ARG, "needs set_const");
+  const int D = m->depth;
+  int rc;
+  if ((rc = upload_level(m, m->psi.lev[D], a, m->nl, D, -1.))) return rc;
+  if ((rc = upload_level(m, m->q.lev[D], b, m->nl, D, -1.))) return rc;
+  MgProblem P{m->nl, -1, m->psi.lev[D], m->q.lev[D]};
+  if ((rc = mg_residual(m, P, maxres))) return rc;
+  return download_level(m, res, m->res.lev[D], m->nl, D);
+}
+extern "C" int msqg_test_restrict(msqg_model *m, int level, const double *fine, double *coarse) {
+  CK(cudaSetDevice(m->device));
+  if (level < 2 || level > m->depth) FAIL(MSQG_ERR_ARG, "bad level");
+  int rc;
+  if ((rc = upload_level(m, m->res.lev[level], fine, m->nl, level, -1.))) return rc;
+  dim3 b(32, 8);
+  k_restrict<<<grid2(m->g[level - 1].n, m->g[level - 1].n, b, m->nl), b, 0, m->stream>>>(m->res.lev[level], m->res.lev[level - 1], m->g[level], m->g[level - 1], -1., 0);
+  CK(cudaGetLastError());
+  return download_level(m, coarse, m->res.lev[level - 1], m->nl, level - 1);
+}
+extern "C" int msqg_test_prolong(msqg_model *m, int level, const double *coarse, double *fine) {
+  CK(cudaSetDevice(m->device));
+  if (level < 2 || level > m->depth) FAIL(MSQG_ERR_ARG, "bad level");
+  int rc;
+  if ((rc = upload_level(m, m->da.lev[level - 1], coarse, m->nl, level - 1, -1.))) return rc;
+  dim3 b(32, 8);
+  k_prolong<<<grid2(m->g[level].n, m->g[level].n, b, m->nl), b, 0, m->stream>>>(m->da.lev[level - 1], m->da.lev[level], m->g[level - 1], m->g[level]);
+  CK(cudaGetLastError());
+  return download_level(m, fine, m->da.lev[level], m->nl, level);
+}
+
+/* exact-division self test: out[i] = div_by(x[i], d[i], 1/d[i]) next to x[i]/d[i] */
+__global__ void k_divtest(const double *x, const double *d, double *q_fast, double *q_ieee, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = 1. / d[i];
+  q_fast[i] = div_by(x[i], d[i], r);
+  q_ieee[i] = x[i] / d[i];
+}
+extern "C" int msqg_test_div(int device, const double *x, const double *d, double *q_fast, double *q_ieee, int n) {
+  CK(cudaSetDevice(device));
+  double *dx, *dd, *df, *di;
+  CK(cudaMalloc(&dx, n * sizeof(double))); CK(cudaMalloc(&dd, n * sizeof(double)));
+  CK(cudaMalloc(&df, n * sizeof(double))); CK(cudaMalloc(&di, n * sizeof(double)));
+  CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dd, d, n * sizeof(double), cudaMemcpyHostToDevice));
+  k_divtest<<<(n + 255) / 256, 256>>>(dx, dd, df, di, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(q_fast, df, n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(q_ieee, di, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dd); cudaFree(df); cudaFree(di);
+  return MSQG_OK;
+}
+
+/* One mg_cycle + residual on the model's current (psi, q), timed with CUDA
+ * events on the model's stream; reps cycles, average ms.  The iterate keeps
+ * converging, which does not change the work per cycle. */
+extern "C" int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_out) {
+  CK(cudaSetDevice(m->device));
+  if (!m->const_set || m->p.mode_pv_invert) FAIL(MSQG_ERR_ARG, "needs set_const (layer-coupled mode)");
+  const int D = m->depth;
+  MgProblem P{m->nl, -1, m->psi.lev[D], m->q.lev[D]};
+  double r;
+  int rc;
+  if ((rc = mg_residual(m, P, &r))) return rc;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, m->stream));
+  for (int i = 0; i < reps; i++) {
+    if ((rc = mg_cycle(m, P, nrelax))) return rc;
+    if ((rc = mg_residual(m, P, &r))) return rc;
+  }
+  CK(cudaEventRecord(e1, m->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if ((rc = check_relax_err(m))) return rc;
+  *ms_out = ms / reps;
+  return MSQG_OK;
+}

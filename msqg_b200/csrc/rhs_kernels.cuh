@@ -1,0 +1,303 @@
+/*
+ * rhs_kernels.cuh -- right-hand side of the PV equation and stage update.
+ *
+ * One RHS evaluation of the reference (update_qg, msqg/qg.h:609-650) is ~45
+ * full passes over the layer lists.  Here it is three:
+ *   k_zeta : zeta = laplacian(psi) + dirichlet ghosts            (comp_del2, qg.h:171-181)
+ *            + per-layer max|u_face|                             (comp_vel + timestep, qg.h:275-283,383-391)
+ *   k_lap  : tmp  = laplacian(zeta) + ghosts                     (dissip's comp_del2, qg.h:411), only if Re/Re4 != 0
+ *   k_rhs  : every tendency term in the reference's accumulation order, then
+ *            the stage update q_out = q_in + dq*dt               (advance_qg, qg.h:594-606)
+ * Floating-point association follows the reference expressions token by token;
+ * the library is compiled with -fmad=false so results are bit-identical to an
+ * x86-64 build of the reference without FMA contraction.
+ */
+#pragma once
+#include "layout.cuh"
+#include "mg_kernels.cuh"
+
+/* laplacian macro, qg.h:169.  The reference macro has no outer parentheses, so
+ * `fac*laplacian(po)` is (fac*(sum))/sq(Delta): lapf() keeps that association. */
+__device__ __forceinline__ double lapf(double fac, const double *__restrict__ p, size_t c, int pitch, double D) {
+  return (fac * (p[c + 1] + p[c - 1] + p[c + pitch] + p[c - pitch] - 4 * p[c])) / (D * D);
+}
+__device__ __forceinline__ double lap5(const double *__restrict__ p, size_t c, int pitch, double D) {
+  return (p[c + 1] + p[c - 1] + p[c + pitch] + p[c - pitch] - 4 * p[c]) / (D * D);
+}
+
+__device__ __forceinline__ void write_ghosts(double *__restrict__ p, const Geom &g, int x, int y, double v, double sg) {
+  const int n = g.n;
+  const bool l = x == 0, r = x == n - 1, bo = y == 0, t = y == n - 1;
+  if (l) p[GIDX(g.pitch, y, -1)] = sg * v;
+  if (r) p[GIDX(g.pitch, y, n)] = sg * v;
+  if (bo) p[GIDX(g.pitch, -1, x)] = sg * v;
+  if (t) p[GIDX(g.pitch, n, x)] = sg * v;
+  if (l && bo) p[GIDX(g.pitch, -1, -1)] = v;
+  if (l && t) p[GIDX(g.pitch, n, -1)] = v;
+  if (r && bo) p[GIDX(g.pitch, -1, n)] = v;
+  if (r && t) p[GIDX(g.pitch, n, n)] = v;
+}
+
+/* out = laplacian(in) on every layer (blockIdx.z) + dirichlet(0) ghosts.
+ * If umax != NULL also reduces max |u| over the faces of layer z:
+ *   u.x[i,j] = -0.25*(p[i,j+1]-p[i,j-1]+p[i-1,j+1]-p[i-1,j-1])/Delta   faces i=0..n, j=0..n-1
+ *   u.y[i,j] = +0.25*(p[i+1,j]-p[i-1,j]+p[i+1,j-1]-p[i-1,j-1])/Delta   faces j=0..n, i=0..n-1
+ * min over faces of Delta/|u| (timestep.h) == Delta / max|u| exactly (division
+ * is monotone), so the host rebuilds the reference's dt chain from umax. */
+__global__ void __launch_bounds__(256)
+k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *__restrict__ umax) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  const double *p = in + (size_t)f * g.plane;
+  double um = 0.;
+  if (x <= g.n && y <= g.n) {
+    const size_t c = GIDX(g.pitch, y, x);
+    if (x < g.n && y < g.n) {
+      double *o = out + (size_t)f * g.plane;
+      const double v = lap5(p, c, g.pitch, g.Delta);
+      o[c] = v;
+      write_ghosts(o, g, x, y, v, -1.);
+    }
+    if (umax) {
+      const int P = g.pitch;
+      if (y < g.n) { /* x-face (x, y), x = 0..n */
+        const double u = 0.25 * (p[c + P] - p[c - P] + p[c - 1 + P] - p[c - 1 - P]) / g.Delta;
+        const double a = fabs(u);
+        if (a > um) um = a;
+      }
+      if (x < g.n) { /* y-face (x, y), y = 0..n */
+        const double u = 0.25 * (p[c + 1] - p[c - 1] + p[c + 1 - P] - p[c - 1 - P]) / g.Delta;
+        const double a = fabs(u);
+        if (a > um) um = a;
+      }
+    }
+  }
+  if (umax) block_max_to(umax + f, um);
+}
+
+/* jacobian macro, qg.h:252-262: returns -J(p,q), 3x3 neighbourhoods */
+__device__ __forceinline__ double jac(const double *__restrict__ po, const double *__restrict__ qo, size_t c, int P,
+                                      double D) {
+  const long long cc = (long long)c;
+#define PO(a, b) po[cc + (a) + (b) * P]
+#define QO(a, b) qo[cc + (a) + (b) * P]
+  return (((QO(1, 0) - QO(-1, 0)) * (PO(0, 1) - PO(0, -1))
+         + (QO(0, -1) - QO(0, 1)) * (PO(1, 0) - PO(-1, 0))
+         + QO(1, 0) * (PO(1, 1) - PO(1, -1))
+         - QO(-1, 0) * (PO(-1, 1) - PO(-1, -1))
+         - QO(0, 1) * (PO(1, 1) - PO(-1, 1))
+         + QO(0, -1) * (PO(1, -1) - PO(-1, -1))
+         + PO(0, 1) * (QO(1, 1) - QO(-1, 1))
+         - PO(0, -1) * (QO(1, -1) - QO(-1, -1))
+         - PO(1, 0) * (QO(1, 1) - QO(1, -1))
+         + PO(-1, 0) * (QO(-1, 1) - QO(-1, -1)))
+        / (12. * D * D));
+#undef PO
+#undef QO
+}
+
+struct RhsArgs {
+  const double *psi, *zeta, *tmp, *pp, *zp, *s, *qforc, *topo, *ro, *sstoch_unused;
+  const double *q_in; /* stage input (advance_qg's `input`) */
+  const double *q_ev; /* evolving list of this RHS (stochastic relaxation term) */
+  double *q_out;      /* may alias q_in; NULL: no stage update */
+  double *dq;         /* NULL: tendency not stored */
+  const double *noise;     /* stochastic: n_stochl, else NULL */
+  const double *wind;      /* [n] tau0/(Rom*dh0)*sin(2 pi y/L0)*sin(pi y/L0), host glibc */
+  Geom g;
+  double idh0[MSQG_NLMAX], idh1[MSQG_NLMAX];
+  double beta, iRe, iRe4, ceks, cekb; /* ceks = Eks/(Rom*2*dh[0]), cekb = Ekb/(Rom*2*dh[nl-1]) */
+  double dhb;                         /* dh[nl-1] */
+  double dt, itr;
+  float dts;                          /* stochastic: float, qg_stochastic.h:133-136 */
+  int has_pg, has_zp, use_tmp, flag_topo, stochastic;
+};
+
+/* advection_pv (qg.h:287-380; stochastic variant qg_stochastic.h:17-111),
+ * dissip (:406-422), ekman_friction (:428-440), surface_forcing (:446-459),
+ * qforcing (:465-474), bottom_topography (:480-488), advance_qg (:594-606;
+ * stochastic qg_stochastic.h:128-149), one thread per column, layers in
+ * registers so that ju = -jd is reused exactly as the reference does. */
+template <int NL>
+__global__ void __launch_bounds__(128)
+k_rhs(RhsArgs A) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const Geom g = A.g;
+  if (x >= g.n || y >= g.n) return;
+  const size_t c = GIDX(g.pitch, y, x);
+  const int P = g.pitch;
+  const size_t pl = g.plane;
+  const double D = g.Delta;
+  double jd = 0., ju;
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const double *po = A.psi + l * pl, *qo = A.zeta + l * pl;
+    const double *pp = A.pp + l * pl;
+    double dq = 0.;
+    ju = -jd;
+    /* --- advection_pv */
+    if (l < NL - 1) {
+      const double *po2 = A.psi + (l + 1) * pl, *pp2 = A.pp + (l + 1) * pl;
+      if (!A.stochastic) {
+        jd = jac(po, po2, c, P, D);
+        if (A.has_pg) jd = jd + jac(pp, po2, c, P, D) + jac(po, pp2, c, P, D);
+      } else {
+        jd = A.has_pg ? jac(pp, po2, c, P, D) + jac(po, pp2, c, P, D) : 0.;
+      }
+    }
+    double adv;
+    const double be = A.beta * (po[c - 1] - po[c + 1]) / (2 * D);
+    if (!A.stochastic || l > 0) {
+      adv = jac(po, qo, c, P, D);
+      if (A.has_pg) adv = adv + jac(pp, qo, c, P, D);
+      adv = adv + be;
+    } else { /* stochastic top layer omits J(psi,zeta), qg_stochastic.h:39-40 */
+      adv = A.has_pg ? jac(pp, qo, c, P, D) + be : be;
+    }
+    if (l == 0)
+      adv = adv + A.s[c] * jd * A.idh1[0];
+    else if (l < NL - 1)
+      adv = adv + A.s[(l - 1) * pl + c] * ju * A.idh0[l] + A.s[l * pl + c] * jd * A.idh1[l];
+    else
+      adv = adv + A.s[(l - 1) * pl + c] * ju * A.idh0[l];
+    dq += adv;
+    if (A.has_zp) dq += jac(po, A.zp + l * pl, c, P, D);
+    if (A.stochastic) dq += -A.q_ev[l * pl + c] * A.itr;
+    /* --- dissip */
+    if (A.use_tmp) {
+      const double *z1 = qo, *t1 = A.tmp + l * pl;
+      if (l == 0) {
+        dq = 1. * dq + A.iRe * A.s[c] * (z1[pl + c] - z1[c]) * A.idh1[0];
+      } else if (l < NL - 1) {
+        dq = 1. * dq + A.iRe * (A.s[(l - 1) * pl + c] * (z1[c - pl] - z1[c]) * A.idh0[l] +
+                                A.s[l * pl + c] * (z1[c + pl] - z1[c]) * A.idh1[l]);
+      } else {
+        dq = 1. * dq + A.iRe * A.s[(l - 1) * pl + c] * (z1[c - pl] - z1[c]) * A.idh0[l];
+      }
+      dq += t1[c] * A.iRe;
+      if (l == 0) {
+        dq = 1. * dq + A.iRe4 * A.s[c] * (t1[pl + c] - t1[c]) * A.idh1[0];
+      } else if (l < NL - 1) {
+        dq = 1. * dq + A.iRe4 * (A.s[(l - 1) * pl + c] * (t1[c - pl] - t1[c]) * A.idh0[l] +
+                                 A.s[l * pl + c] * (t1[c + pl] - t1[c]) * A.idh1[l]);
+      } else {
+        dq = 1. * dq + A.iRe4 * A.s[(l - 1) * pl + c] * (t1[c - pl] - t1[c]) * A.idh0[l];
+      }
+      dq = 1. * dq + lapf(A.iRe4, t1, c, P, D);
+    }
+    /* --- ekman_friction */
+    if (l == 0) dq -= A.ceks * qo[c];
+    if (l == NL - 1) dq -= A.cekb * qo[c];
+    /* --- surface_forcing */
+    if (l == 0) dq -= A.wind[y];
+    /* --- qforcing */
+    if (A.qforc) dq += A.qforc[l * pl + c];
+    /* --- bottom_topography */
+    if (l == NL - 1 && A.flag_topo) dq += jac(po, A.topo, c, P, D) / (A.ro[c] * A.dhb);
+    if (A.dq) A.dq[l * pl + c] = dq;
+    /* --- advance_qg */
+    if (A.q_out) {
+      double v;
+      if (!A.stochastic)
+        v = A.q_in[l * pl + c] + dq * A.dt;
+      else
+        v = A.q_in[l * pl + c] + dq * A.dt + A.noise[l * pl + c] * A.dts;
+      A.q_out[l * pl + c] = v;
+    }
+  }
+}
+
+/* advance_qg alone (API parity with the function-pointer plugin, qg.h:594-606) */
+__global__ void k_advance(double *__restrict__ out, const double *__restrict__ in, const double *__restrict__ dq,
+                          const double *__restrict__ noise, Geom g, double dt, float dts) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (x >= g.n || y >= g.n) return;
+  const size_t c = (size_t)f * g.plane + GIDX(g.pitch, y, x);
+  if (noise)
+    out[c] = in[c] + dq[c] * dt + noise[c] * dts;
+  else
+    out[c] = in[c] + dq[c] * dt;
+}
+
+/* comp_q: q = laplacian(psi) + stretching(psi)  (qg.h:396-403 -> :171-181, :202-246) */
+template <int NL>
+__global__ void __launch_bounds__(256)
+k_comp_q(const double *__restrict__ psi, const double *__restrict__ s, double *__restrict__ q, Geom g, LayerMetrics M) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= g.n || y >= g.n) return;
+  const size_t c = GIDX(g.pitch, y, x);
+  const size_t pl = g.plane;
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const double *p = psi + l * pl;
+    double v = 0. * 0. + 1. * lap5(p, c, g.pitch, g.Delta);
+    if (l == 0)
+      v = 1. * v + 1. * s[c] * (p[pl + c] - p[c]) * M.idh1[0];
+    else if (l < NL - 1)
+      v = 1. * v + 1. * (s[(l - 1) * pl + c] * (p[c - pl] - p[c]) * M.idh0[l] + s[l * pl + c] * (p[c + pl] - p[c]) * M.idh1[l]);
+    else
+      v = 1. * v + 1. * s[(l - 1) * pl + c] * (p[c - pl] - p[c]) * M.idh0[l];
+    q[l * pl + c] = v;
+    write_ghosts(q + l * pl, g, x, y, v, -1.);
+  }
+}
+
+/* modal projections, invertq's MODE_PV_INVERT branch (qg.h:118-131, :144-157):
+ *   out_m = sum_l mat[m*nl+l] * in_l   accumulated from 0. in the reference order.
+ * The matrices are fields in the reference (nl^2 scalars per column); they are
+ * kept as fields here only when they vary in space, else passed as constants. */
+template <int NL>
+struct ModeMat {
+  double a[NL * NL];
+};
+
+template <int NL>
+__global__ void __launch_bounds__(256)
+k_project(const double *__restrict__ in, double *__restrict__ out, Geom g, ModeMat<NL> M,
+          const double *__restrict__ matf /* optional per-cell matrix planes */, int ghosts) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= g.n || y >= g.n) return;
+  const size_t c = GIDX(g.pitch, y, x);
+  const size_t pl = g.plane;
+  double v[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) v[l] = in[l * pl + c];
+#pragma unroll
+  for (int m = 0; m < NL; m++) {
+    double acc = 0.;
+#pragma unroll
+    for (int l = 0; l < NL; l++) acc += (matf ? matf[(size_t)(m * NL + l) * pl + c] : M.a[m * NL + l]) * v[l];
+    out[m * pl + c] = acc;
+    if (ghosts) write_ghosts(out + m * pl, g, x, y, acc, -1.);
+  }
+}
+
+/* ke_1 of writestdout (qg.c:101-106): ke -= 0.5*psi0*laplacian(psi0)*sq(Delta).
+ * The reference sums in traversal order; a parallel sum differs in the last
+ * bits, so this is a diagnostic (deterministic two-stage tree), not a parity
+ * quantity. */
+__global__ void __launch_bounds__(256)
+k_ke_partial(const double *__restrict__ p, Geom g, double *__restrict__ part) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  double v = 0.;
+  if (x < g.n && y < g.n) {
+    const size_t c = GIDX(g.pitch, y, x);
+    v = lapf(0.5 * p[c], p, c, g.pitch, g.Delta) * (g.Delta * g.Delta);
+  }
+  __shared__ double sh[256];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) sh[tid] += sh[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
+}

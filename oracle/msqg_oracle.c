@@ -346,10 +346,12 @@ void orc_set_flag_topo(orc_model *m, int flag) { m->flag_topo = flag; }
 void orc_set_decomp(orc_model *m, int px, int py, int agg_n) { m->p.px = px; m->p.py = py; m->agg_n = agg_n; }
 
 /* ------------------------------------------------------------ operators */
-/* laplacian macro, qg.h:169 */
+/* laplacian macro, qg.h:169.  Like the reference's it has NO outer parentheses:
+ * `fac*laplacian(po)` therefore associates as (fac*(sum))/sq(Delta), and the
+ * ke_1 expression of qg.c:106 as ((0.5*po*(sum))/sq(Delta))*sq(Delta). */
 #define LAP(a, n, i, j, D)                                                            \
-  ((a[IDX(n, (i) + 1, j)] + a[IDX(n, (i) - 1, j)] + a[IDX(n, i, (j) + 1)] +           \
-    a[IDX(n, i, (j) - 1)] - 4 * a[IDX(n, i, j)]) / (sq(D)))
+  (a[IDX(n, (i) + 1, j)] + a[IDX(n, (i) - 1, j)] + a[IDX(n, i, (j) + 1)] +            \
+   a[IDX(n, i, (j) - 1)] - 4 * a[IDX(n, i, j)]) / (sq(D))
 
 /* comp_del2, qg.h:171-200 (sbc == 0 only) */
 static void comp_del2(orc_model *m, flist *pl, flist *zl, double add, double fac) {

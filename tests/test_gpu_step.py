@@ -1,0 +1,82 @@
+"""GPU parity of the whole path (set_const, invertq, update_qg, the RK2 step)
+against the CPU oracle through the C ABI.  north_star tolerances: relative L2
+of psi and q <= 1e-12 after one step, <= 1e-9 after 100 steps, equal multigrid
+cycle counts; the implementation is in fact bit-identical."""
+import numpy as np
+import pytest
+
+from common import make_pair, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,nl", [(64, 2), (256, 2), (128, 3), (128, 4), (64, 10)])
+def test_set_const_and_invertq(gpu, N, nl):
+    from oracle import oracle as O
+    from msqg_b200 import capi as G
+    mo, mg, psi = make_pair(N, nl)
+    mo.set_const(); mg.set_const()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))          # comp_q
+    assert np.array_equal(mg.get(G.STR)[: nl - 1], mo.get(O.STR)[: nl - 1])
+    # cold start: psi = 0, several cycles with nrelax adaptation
+    z = np.zeros_like(psi)
+    mo.set(O.PSI, z); mg.set(G.PSI, z)
+    mo.invertq(); mg.invertq()
+    so, sg = mo.mgstats(), mg.mgstats()
+    assert (sg.i, sg.nrelax) == (so.i, so.nrelax)
+    assert sg.resb == so.resb and sg.resa == so.resa
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+
+
+@pytest.mark.parametrize("N,nl", [(256, 2), (128, 3), (128, 4)])
+def test_update_qg(gpu, N, nl):
+    from oracle import oracle as O
+    from msqg_b200 import capi as G
+    mo, mg, _ = make_pair(N, nl)
+    mo.set_const(); mg.set_const()
+    dto = mo.update(mo.p.DT)
+    dtg = mg.update(mg.p.DT)
+    assert dtg == dto
+    assert np.array_equal(mg.get(G.ZETA), mo.get(O.ZETA))
+    assert np.array_equal(mg.get(G.DQ), mo.get(O.DQ))
+
+
+@pytest.mark.parametrize("N,nl,nsteps", [(256, 2, 1), (256, 2, 100), (128, 3, 20), (128, 4, 20)])
+def test_steps(gpu, N, nl, nsteps):
+    """BASELINE config 1 (256^2 x 2): 1 and 100 steps."""
+    from oracle import oracle as O
+    from msqg_b200 import capi as G
+    mo, mg, _ = make_pair(N, nl)
+    mo.set_const(); mg.set_const()
+    for _ in range(nsteps):
+        dto = mo.step()
+        dtg = mg.step()
+        assert dtg == dto
+    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)     # equal multigrid iteration counts
+    tol = 1e-12 if nsteps == 1 else 1e-9
+    for fg, fo in ((G.PSI, O.PSI), (G.Q, O.Q)):
+        a, b = mg.get(fg), mo.get(fo)
+        assert rel_l2(a, b) <= tol
+        assert np.array_equal(a, b)                           # in fact bit-identical
+
+
+def test_viscous_and_pg_terms(gpu):
+    """Re, Re4, Eks, background flow (upg/vpg), flsrv, q_forc, topography all on."""
+    from oracle import oracle as O
+    from msqg_b200 import capi as G
+    N, nl = 64, 3
+    over = dict(Re=500., Eks=0.001, flsrv=1, upg=[0.1, 0.05, 0.0], vpg=[0.02, 0.0, -0.01])
+    mo, mg, psi = make_pair(N, nl, **over)
+    rng = np.random.default_rng(2)
+    qf = 1e-3 * rng.standard_normal((nl, N, N))
+    topo = 0.1 * rng.standard_normal((1, N, N))
+    mo.set(O.QFORC, qf); mg.set(G.QFORC, qf)
+    mo.set(O.TOPO, topo); mg.set(G.TOPO, topo)
+    mo.L.orc_set_flag_topo(mo.h, 1); G.check(mg.L.msqg_set_flag_topo(mg.h, 1))
+    mo.set_const(); mg.set_const()
+    assert mg.update(mg.p.DT) == mo.update(mo.p.DT)
+    assert np.array_equal(mg.get(G.DQ), mo.get(O.DQ))
+    for _ in range(3):
+        assert mg.step() == mo.step()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
