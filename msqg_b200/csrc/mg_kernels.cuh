@@ -267,28 +267,36 @@ __global__ void k_correct(double *__restrict__ a, const double *__restrict__ da,
  *     i = w*W + c - k.  Shifting the strip left by one column per sweep keeps
  *     the east dependency (sweep k-1, column i+1) inside the warp, so workers
  *     form a one-directional chain w-1 -> w.
- *   - lane (k,c) handles row j = tau - c - k - 1 at step tau: the values it needs
- *     were all produced in step tau-1 and arrive by warp shuffles:
- *       west  (sweep k,   i-1, j)   <- lane-1
- *       east  (sweep k-1, i+1, j)   <- lane-W
- *       north (sweep k-1, i,   j+1) <- lane-W-1
+ *   - lane (k,c) handles row j = tau - c - 2k - 1 at step tau.  All neighbour
+ *     values are warp shuffles of the results the lanes hold at the top of a
+ *     step (= what they computed in step tau-1):
+ *       west  (sweep k,   i-1, j)   <- lane-1,   used in this step (critical path)
  *       south (sweep k,   i,   j-1) =  own previous result
- *     sweep 0 reads east/north from the initial iterate, staged through a
- *     shared-memory row ring filled with cp.async; res comes from the same ring.
+ *       east  (sweep k-1, i+1, j)   <- lane-W,   used in the NEXT step
+ *       north (sweep k-1, i,   j+1) <- lane-W-1, used in the NEXT step
+ *     (sweep groups lag each other by two steps, which takes east/north off the
+ *     critical path.)  Sweep 0 reads east/north from the initial iterate,
+ *     streamed from HBM into a shared-memory row ring with cp.async a fixed
+ *     number of rows ahead; res streams the same way.
  *   - the west column of a strip comes from the neighbouring worker through a
  *     global-memory mailbox whose entries are self-validating (a reserved NaN
  *     payload means "not yet written"), so no flags or fences are needed; the
- *     consumer re-arms each entry after reading it.
+ *     consumer prefetches the next entry one step ahead and re-arms what it
+ *     read.
  *   - dirichlet ghosts are evaluated as -(pre-sweep centre value), exactly what
  *     boundary_level left in the ghost ring before the sweep.
  *   - only the last sweep's values are stored: HBM sees one read of da/res and
  *     one write of da for all nsweeps sweeps.
  *
+ * A step is latency-bound by the Thomas recurrence (~50 dependent fp64 ops,
+ * ~8 cycles each); the loop body is one basic block (plus rare slow paths) so
+ * that loads, stores, streaming and mailbox traffic issue in the shadow of
+ * that chain, and it is executed once "dry" to warm the instruction cache.
  * The Thomas pivots do not depend on the iterate; for horizontally uniform
  * stretching they are per-level constants computed on the host with the
- * reference's expression order (RelaxCoef), and divisions by them use div_by().
- * Every worker waits only on lower-numbered workers; the kernel is launched
- * cooperatively so all of them are resident.  Spins are bounded.
+ * reference's expression order (RelaxCoef), and divisions by them use
+ * div_by().  Every worker waits only on its left neighbour; the kernel is
+ * launched cooperatively so all workers are resident.  Spins are bounded.
  */
 template <int NL>
 struct RelaxCoef {
@@ -301,192 +309,247 @@ struct RelaxArgs {
   const double *res; /* rhs of the correction equation */
   Geom g;
   int nsweeps;                  /* 1..K */
-  int init_zero;                /* initial iterate is identically zero (coarsest level) */
-  unsigned long long *mailbox;  /* [nworkers][K][n][NL] doubles, armed with MAIL_EMPTY */
+  unsigned long long *mailbox;  /* [nworkers][K][n][NLP] words, armed with MAIL_EMPTY */
   int *err;                     /* set to 1 on spin timeout */
+  long long *dbg;               /* optional [nworkers][4]: start ns, end ns, spins, - */
 };
 
 #define MAIL_EMPTY 0xFFF8DEADBEEF0001ull
 #define SPIN_LIMIT (1 << 22)
 
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+__device__ __forceinline__ void cp_async8_if(bool p, unsigned smem_addr, const void *gsrc) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %0, 0;\n @q cp.async.ca.shared.global [%1], [%2], 8;\n}\n"
+               ::"r"((int)p), "r"(smem_addr), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void ld_mail2_if(bool p, const unsigned long long *a, unsigned long long &v0,
+                                            unsigned long long &v1) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.volatile.global.v2.u64 {%0, %1}, [%3];\n}\n"
+               : "+l"(v0), "+l"(v1) : "r"((int)p), "l"(a));
+}
+__device__ __forceinline__ void st_mail2_if(bool p, unsigned long long *a, unsigned long long v0, unsigned long long v1) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %0, 0;\n @q st.global.cg.v2.u64 [%1], {%2, %3};\n}\n"
+               ::"r"((int)p), "l"(a), "l"(v0), "l"(v1) : "memory");
+}
 
 template <int NL, int K>
 struct RelaxCfg {
+  static_assert(K == 4 || K == 8, "ring sizing assumes W + 2K <= 20");
   static constexpr int W = 32 / K;
-  static constexpr int RC = W + K - 1; /* res columns per ring row */
-  static constexpr int DC = W + 1;     /* da columns per ring row */
-  static constexpr int B = 8;          /* rows per cp.async batch */
-  static constexpr int R = 32;         /* ring rows: skew (W+K) + 2 batches */
-  static_assert(K == 4 || K == 8, "ring sizing assumes W + K < 18");
-  static constexpr int ROWD = NL * (RC + DC);
-  static constexpr size_t smem_per_warp = (size_t)R * ROWD * sizeof(double);
+  static constexpr int S = W + 1;      /* da ring columns: slot s <-> column w*W + s */
+  static constexpr int RC = W + K - 1; /* res ring columns: rc <-> column w*W - (K-1) + rc */
+  static constexpr int RIN = 32;       /* ring rows */
+  static constexpr int P = 10;         /* rows streamed ahead of the leading lane */
+  static constexpr int NLP = (NL + 1) & ~1; /* mailbox entry padded to 16 bytes */
+  static constexpr int DROW = NL * S, RROW = NL * RC;
+  static constexpr int DOUBLES = RIN * (DROW + RROW);
+  static constexpr size_t smem_per_warp = (size_t)DOUBLES * sizeof(double);
+  static constexpr int EPL_D = (DROW + 31) / 32, EPL_R = (RROW + 31) / 32;
+  static constexpr int SKEW = (W - 1) + 2 * (K - 1) + 1; /* rows between leading and trailing lane */
+  static_assert(P + SKEW + 3 <= RIN, "ring too small");
 };
 
 template <int NL, int K, int WPC>
 __global__ void __launch_bounds__(32 * WPC)
 k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
   using Cfg = RelaxCfg<NL, K>;
-  constexpr int W = Cfg::W, RC = Cfg::RC, DC = Cfg::DC, B = Cfg::B, R = Cfg::R, ROWD = Cfg::ROWD;
+  constexpr int W = Cfg::W, S = Cfg::S, RC = Cfg::RC, RIN = Cfg::RIN, P = Cfg::P;
+  constexpr int NLP = Cfg::NLP, DROW = Cfg::DROW, RROW = Cfg::RROW;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = A.g.n;
   const int w = blockIdx.x * WPC + warp;
   const int nworkers = (n + K - 1 + W - 1) / W;
   if (w >= nworkers) return;
-  double *ring = smem + (size_t)warp * R * ROWD; /* [R][ res NL*RC | da NL*DC ] */
+  double *sm_da = smem + (size_t)warp * Cfg::DOUBLES; /* [RIN][NL][S] */
+  double *sm_res = sm_da + RIN * DROW;                /* [RIN][NL][RC] */
   const int k = lane / W, c = lane % W;
   const int i = w * W + c - k;
   const int nsw = A.nsweeps;
   const bool col_ok = (i >= 0 && i < n && k < nsw);
-  const int rcol = c - k + K - 1;        /* my res column inside a ring row */
-  const int col0r = w * W - (K - 1);     /* global column of ring res col 0 */
-  const int col0d = w * W;               /* global column of ring da col 0 */
   const int pitch = A.g.pitch;
   const size_t plane = A.g.plane;
+  const bool k0 = (k == 0);
+  const bool left = (i == 0), right = (i == n - 1);
+  const bool last = (k == nsw - 1);
+  const bool use_mail = (c == 0 && w > 0);
+  const bool use_mail_n = use_mail && k > 0;
+  /* mailboxes: entry (k, row) = NLP words */
   const bool has_consumer = (w + 1 < nworkers);
-  /* mailbox written by me (read by w+1) / read by me (written by w-1) */
-  unsigned long long *mb_out = A.mailbox + (size_t)w * K * n * NL;
-  unsigned long long *mb_in = A.mailbox + (size_t)(w > 0 ? w - 1 : 0) * K * n * NL;
-  const bool mb_reader = (w > 0 && c == 0 && k < nsw && (w * W - 1 - k) >= 0 && (w * W - 1 - k) < n);
-  const bool mb_writer = (has_consumer && c == W - 1 && col_ok);
+  const bool mb_writer = has_consumer && c == W - 1 && col_ok;
+  const int prodcol = w * W - 1 - k;
+  const bool mb_reader = (use_mail && k < nsw && prodcol >= 0 && prodcol < n);
+  unsigned long long *mb_out = A.mailbox + ((size_t)w * K + k) * (size_t)n * NLP;
+  unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + k) * (size_t)n * NLP;
+  double *out_g = A.da + GIDX(pitch, 0, col_ok ? i : 0);
+  const double *res_l = sm_res + (c - k + K - 1);
+  const double *da_l = sm_da + c;
 
-  const int T = n + W + K - 1; /* steps */
-  const int nbatch = (n + B - 1) / B;
-
-  auto issue_batch = [&](int m) {
-    if (m < nbatch) {
-      const int r0 = m * B;
-      constexpr int PER_ROW = NL * (RC + DC);
-      for (int e = lane; e < B * PER_ROW; e += 32) {
-        const int rr = e / PER_ROW, q = e % PER_ROW;
-        const int row = r0 + rr;
-        if (row >= n) continue;
-        double *dst = ring + (size_t)(row % R) * ROWD + q;
-        if (q < NL * RC) {
-          const int l = q / RC, x = col0r + q % RC;
-          if (x >= 0 && x < n) cp_async8(dst, A.res + l * plane + GIDX(pitch, row, x));
-        } else if (!A.init_zero) {
-          const int q2 = q - NL * RC;
-          const int l = q2 / DC, x = col0d + q2 % DC;
-          if (x < n) cp_async8(dst, A.da + l * plane + GIDX(pitch, row, x));
-        }
-      }
-    }
+  /* loader: element e of a ring row <-> (layer, column); per-lane source pointers */
+  const double *ld_d[Cfg::EPL_D];
+  const double *ld_r[Cfg::EPL_R];
+  unsigned st_d[Cfg::EPL_D], st_r[Cfg::EPL_R];
+  bool ok_d[Cfg::EPL_D], ok_r[Cfg::EPL_R];
+#pragma unroll
+  for (int q = 0; q < Cfg::EPL_D; q++) {
+    const int e = lane + 32 * q, l = e / S, x = w * W + e % S;
+    ok_d[q] = (e < DROW) && (x < n);
+    ld_d[q] = A.da + (size_t)(ok_d[q] ? l : 0) * plane + GIDX(pitch, 0, ok_d[q] ? x : 0);
+    st_d[q] = (unsigned)__cvta_generic_to_shared(sm_da + e);
+  }
+#pragma unroll
+  for (int q = 0; q < Cfg::EPL_R; q++) {
+    const int e = lane + 32 * q, l = e / RC, x = w * W - (K - 1) + e % RC;
+    ok_r[q] = (e < RROW) && (x >= 0) && (x < n);
+    ld_r[q] = A.res + (size_t)(ok_r[q] ? l : 0) * plane + GIDX(pitch, 0, ok_r[q] ? x : 0);
+    st_r[q] = (unsigned)__cvta_generic_to_shared(sm_res + e);
+  }
+  auto load_row = [&](int r) {
+    const bool in = r < n;
+    const unsigned ro = (unsigned)(r & (RIN - 1));
+    const size_t go = (size_t)(in ? r : 0) * pitch;
+#pragma unroll
+    for (int q = 0; q < Cfg::EPL_D; q++) cp_async8_if(in && ok_d[q], st_d[q] + ro * (DROW * 8), ld_d[q] + go);
+#pragma unroll
+    for (int q = 0; q < Cfg::EPL_R; q++) cp_async8_if(in && ok_r[q], st_r[q] + ro * (RROW * 8), ld_r[q] + go);
     cp_async_commit();
   };
 
-  double cur[NL], nprev[NL];
-  unsigned long long pend[NL];
-  bool pend_ok = false;
+  /* state carried from step to step */
+  double cur[NL];   /* result of the previous step (row j-1 of sweep k) */
+  double En[NL];    /* east  value for the coming step */
+  double Nn[NL];    /* north value for the coming step (raw, before ghost substitution) */
+  double cold[NL];  /* pre-sweep value of the coming step's cell (= last step's north) */
+  double bn[NL];    /* res of the coming step's cell */
+  double mailw[NL]; /* west value received through the mailbox for the coming step */
+  unsigned long long pend[NLP];
 #pragma unroll
-  for (int l = 0; l < NL; l++) { cur[l] = 0.; nprev[l] = 0.; }
+  for (int l = 0; l < NL; l++) { cur[l] = En[l] = Nn[l] = cold[l] = bn[l] = mailw[l] = 0.; }
+#pragma unroll
+  for (int l = 0; l < NLP; l++) pend[l] = MAIL_EMPTY;
+  long long t_start = 0, n_spins = 0;
+  if (A.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
-  issue_batch(0);
-  for (int m = 0; m * B < T; m++) {
-    issue_batch(m + 1);
-    cp_async_wait<1>();
-    __syncwarp();
-    for (int t = 0; t < B; t++) {
-      const int tau = m * B + t;
-      if (tau >= T) break;
-      const int j = tau - c - k - 1;
-      const bool row_ok = (j >= 0 && j < n);
-      /* values produced in step tau-1 by the lanes to the "left" */
-      double Wv[NL], Ev[NL], Nv[NL], mail[NL];
+#pragma unroll 1
+  for (int r = 0; r < P; r++) load_row(r);
+
+  /* steps: lane (k,c) does row j = tau - c - 2k - 1.  tau = -2 is a dry run that warms the
+     instruction cache, tau = -1 primes the software pipeline (loads for step 0). */
+  const int T = n + W + 2 * K - 2;
+#pragma unroll 1
+  for (int tau = -2; tau < T; tau++) {
+    const int j = tau - c - 2 * k - 1;
+    const bool row_ok = (unsigned)j < (unsigned)n;
+    const bool active = col_ok && row_ok;
+    __syncwarp(); /* cp.async rows waited for in the previous step are visible to all lanes */
+
+    /* ---- mailbox entry for THIS step's west value was prefetched during the previous step */
+    const bool rd = mb_reader && row_ok;
+    {
+      bool miss = false;
 #pragma unroll
-      for (int l = 0; l < NL; l++) mail[l] = 0.;
-      if (mb_reader && row_ok) {
-        unsigned long long *p = mb_in + ((size_t)k * n + j) * NL;
+      for (int l = 0; l < NL; l++) miss |= (pend[l] == MAIL_EMPTY);
+      miss = miss && rd;
+      if (__any_sync(FULLMASK, miss)) { /* rare: producer not far enough ahead */
+        const unsigned long long *p = mb_in + (size_t)(rd ? j : 0) * NLP;
+        int spins = 0;
+        while (miss) {
+          if (++spins > SPIN_LIMIT) { *A.err = 1; break; }
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-          unsigned long long v = pend_ok ? pend[l] : __ldcg(p + l);
-          int spins = 0;
-          while (v == MAIL_EMPTY) {
-            if (++spins > SPIN_LIMIT) { *A.err = 1; break; }
-            v = *((volatile const unsigned long long *)(p + l));
-          }
-          mail[l] = __longlong_as_double((long long)v);
+          for (int l = 0; l < NLP; l += 2) ld_mail2_if(true, p + l, pend[l], pend[l + 1]);
+          miss = false;
+#pragma unroll
+          for (int l = 0; l < NL; l++) miss |= (pend[l] == MAIL_EMPTY);
         }
-        /* re-arm the entries for the next launch */
-#pragma unroll
-        for (int l = 0; l < NL; l++) __stcg(p + l, MAIL_EMPTY);
+        n_spins += spins;
       }
-      /* prefetch next step's mailbox entry: its L2 latency overlaps this step */
-      pend_ok = false;
-      if (mb_reader && j + 1 >= 0 && j + 1 < n) {
-        const unsigned long long *p = mb_in + ((size_t)k * n + j + 1) * NL;
+    }
 #pragma unroll
-        for (int l = 0; l < NL; l++) pend[l] = __ldcg(p + l);
-        pend_ok = true;
-      }
+    for (int l = 0; l < NL; l++) mailw[l] = __longlong_as_double((long long)pend[l]);
+
+    /* ---- west (critical), and next step's east/north, all from the values held at the top of the step */
+    double Wv[NL], Sv[NL], Ev[NL], Nv[NL], b[NL], g[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const double wsh = __shfl_up_sync(FULLMASK, cur[l], 1);
+      g[l] = -cold[l];
+      Wv[l] = use_mail ? mailw[l] : wsh;
+      Wv[l] = left ? g[l] : Wv[l];
+      Sv[l] = (j == 0) ? g[l] : cur[l];
+      Ev[l] = right ? g[l] : En[l];
+      Nv[l] = (j == n - 1) ? g[l] : Nn[l];
+      b[l] = bn[l];
+    }
+    /* next step's inputs (off the critical path) */
+    {
+      const int jn = j + 1; /* row of the coming step */
+      const double *rd_e = da_l + (size_t)(jn & (RIN - 1)) * DROW + 1;
+      const double *rd_n = da_l + (size_t)((jn + 1) & (RIN - 1)) * DROW;
+      const double *rd_b = res_l + (size_t)(jn & (RIN - 1)) * RROW;
 #pragma unroll
       for (int l = 0; l < NL; l++) {
-        Wv[l] = __shfl_up_sync(FULLMASK, cur[l], 1);
-        Ev[l] = __shfl_up_sync(FULLMASK, cur[l], W);
-        Nv[l] = __shfl_up_sync(FULLMASK, cur[l], W + 1);
-        const double mN = __shfl_up_sync(FULLMASK, mail[l], W);
-        if (c == 0 && w > 0) {
-          Wv[l] = mail[l];
-          if (k > 0) Nv[l] = mN;
-        }
+        const double esh = __shfl_up_sync(FULLMASK, cur[l], W);
+        const double nsh = __shfl_up_sync(FULLMASK, cur[l], W + 1);
+        const double msh = __shfl_up_sync(FULLMASK, mailw[l], W);
+        cold[l] = Nn[l];
+        En[l] = k0 ? rd_e[l * S] : esh;
+        Nn[l] = k0 ? rd_n[l * S] : (use_mail_n ? msh : nsh);
+        bn[l] = rd_b[l * RC];
       }
-      if (k == 0) {
-        if (A.init_zero) {
+    }
+    /* stream the rings P rows ahead; re-arm and prefetch the mailbox */
+    load_row(tau < 0 ? n : tau + P);
+    cp_async_wait<P - 2>();
+    {
+      unsigned long long *p = mb_in + (size_t)(rd ? j : 0) * NLP;
 #pragma unroll
-          for (int l = 0; l < NL; l++) { Ev[l] = 0.; Nv[l] = 0.; }
-        } else {
-          const double *rj = ring + (size_t)((j + R) % R) * ROWD + NL * RC;
-          const double *rn = ring + (size_t)((j + 1 + R) % R) * ROWD + NL * RC;
+      for (int l = 0; l < NLP; l += 2) st_mail2_if(rd, p + l, MAIL_EMPTY, MAIL_EMPTY);
+      const bool rn = mb_reader && ((unsigned)(j + 1) < (unsigned)n);
+      const unsigned long long *pn = mb_in + (size_t)(rn ? j + 1 : 0) * NLP;
 #pragma unroll
-          for (int l = 0; l < NL; l++) {
-            Ev[l] = rj[l * DC + c + 1];
-            Nv[l] = rn[l * DC + c];
-          }
-        }
+      for (int l = 0; l < NLP; l += 2) ld_mail2_if(rn, pn + l, pend[l], pend[l + 1]);
+    }
+
+    /* ---- Thomas solve (computed by every lane; only active lanes commit) */
+    double rhs[NL], out[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      double r = C.msd2 * b[l];
+      r += Ev[l] + Wv[l];
+      r += Nv[l] + Sv[l];
+      rhs[l] = r;
+    }
+#pragma unroll
+    for (int l = 1; l < NL; l++) rhs[l] -= div_by(C.t0[l] * rhs[l - 1], C.t1p[l - 1], C.rinv[l - 1]);
+    out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
+#pragma unroll
+    for (int l = NL - 2; l >= 0; l--) out[l] = div_by(rhs[l] - C.t2[l] * out[l + 1], C.t1p[l], C.rinv[l]);
+#pragma unroll
+    for (int l = 0; l < NL; l++) cur[l] = out[l];
+    if (active && last) {
+      double *o = out_g + (size_t)j * pitch;
+#pragma unroll
+      for (int l = 0; l < NL; l++) o[l * plane] = out[l];
+    }
+    {
+      const bool wr = mb_writer && row_ok;
+      unsigned long long *p = mb_out + (size_t)(wr ? j : 0) * NLP;
+#pragma unroll
+      for (int l = 0; l < NLP; l += 2) {
+        const unsigned long long v0 = (unsigned long long)__double_as_longlong(out[l]);
+        const unsigned long long v1 = (l + 1 < NL) ? (unsigned long long)__double_as_longlong(out[l + 1]) : 0ull;
+        st_mail2_if(wr, p + l, v0, v1);
       }
-      if (col_ok && row_ok) {
-        const double *rr = ring + (size_t)(j % R) * ROWD;
-        double rhs[NL];
-#pragma unroll
-        for (int l = 0; l < NL; l++) {
-          const double cold = nprev[l]; /* pre-sweep value of this cell */
-          const double aw = (i == 0) ? -cold : Wv[l];
-          const double ae = (i == n - 1) ? -cold : Ev[l];
-          const double as = (j == 0) ? -cold : cur[l];
-          const double an = (j == n - 1) ? -cold : Nv[l];
-          double r = C.msd2 * rr[l * RC + rcol];
-          r += ae + aw;
-          r += an + as;
-          rhs[l] = r;
-        }
-#pragma unroll
-        for (int l = 1; l < NL; l++) rhs[l] -= div_by(C.t0[l] * rhs[l - 1], C.t1p[l - 1], C.rinv[l - 1]);
-        double out[NL];
-        out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
-#pragma unroll
-        for (int l = NL - 2; l >= 0; l--) out[l] = div_by(rhs[l] - C.t2[l] * out[l + 1], C.t1p[l], C.rinv[l]);
-#pragma unroll
-        for (int l = 0; l < NL; l++) cur[l] = out[l];
-        if (k == nsw - 1) {
-#pragma unroll
-          for (int l = 0; l < NL; l++) A.da[l * plane + GIDX(pitch, j, i)] = out[l];
-        }
-        if (mb_writer) {
-          unsigned long long *p = mb_out + ((size_t)k * n + j) * NL;
-#pragma unroll
-          for (int l = 0; l < NL; l++) __stcg(p + l, (unsigned long long)__double_as_longlong(out[l]));
-        }
-      }
-#pragma unroll
-      for (int l = 0; l < NL; l++) nprev[l] = Nv[l];
     }
   }
   cp_async_wait<0>();
+  if (A.dbg) {
+    long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    n_spins += __shfl_down_sync(FULLMASK, n_spins, 16);
+    n_spins += __shfl_down_sync(FULLMASK, n_spins, 8);
+    if (lane == 0) { A.dbg[w * 4 + 0] = t_start; A.dbg[w * 4 + 1] = t_end; A.dbg[w * 4 + 2] = n_spins; }
+  }
 }

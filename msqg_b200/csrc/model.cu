@@ -78,6 +78,7 @@ struct msqg_model {
   size_t mailbox_words;
   int *d_err;
   int *h_err;
+  long long *d_dbg; /* optional relax profiling buffer */
   int num_sms;
   /* state */
   double ts_previous;
@@ -273,7 +274,7 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   CK(cudaMalloc(&m->d_err, sizeof(int)));
   CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
   CK(cudaMallocHost(&m->h_err, sizeof(int)));
-  m->mailbox = nullptr; m->mailbox_words = 0;
+  m->mailbox = nullptr; m->mailbox_words = 0; m->d_dbg = nullptr;
   for (int l = 0; l < nl; l++) m->dhf[l] = p->dh[l]; /* qg.h:895-896 */
   m->iRe = p->iRe; m->iRe4 = p->iRe4; m->Eks = p->Eks; m->Ekb = p->Ekb;
   m->ts_previous = 0.; m->corrector_step = 0; m->noise_seeded = 0;
@@ -448,31 +449,29 @@ __global__ void k_fill_u64(unsigned long long *p, size_t n, unsigned long long v
   for (; i < n; i += stride) p[i] = v;
 }
 
-template <int NL, int K>
-static int launch_relax_t(msqg_model *m, double *da, const double *res, int lev, int nsweeps, int init_zero,
-                          const RelaxCoef<NL> &C) {
-  constexpr int WPC = 4;
+template <int NL, int K, int WPC>
+static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   using Cfg = RelaxCfg<NL, K>;
   const Geom &g = m->g[lev];
   const int nworkers = (g.n + K - 1 + Cfg::W - 1) / Cfg::W;
-  const size_t words = (size_t)nworkers * K * g.n * NL;
-  /* size the mailbox once for the finest level of this K */
-  {
+  const size_t words = (size_t)nworkers * K * g.n * Cfg::NLP;
+  if (words > m->mailbox_words) {
+    /* size the mailbox for the finest level (K = 8 layout is the larger one) */
     const Geom &gf = m->g[m->depth];
-    const int nwf = (gf.n + K - 1 + Cfg::W - 1) / Cfg::W;
-    const size_t wf = (size_t)nwf * K * gf.n * (size_t)m->nl;
-    const size_t need = words > wf ? words : wf;
-    if (need > m->mailbox_words) {
-      int rc = ensure_mailbox(m, need);
-      if (rc) return rc;
-      k_fill_u64<<<m->num_sms * 4, 256, 0, m->stream>>>(m->mailbox, m->mailbox_words, MAIL_EMPTY);
-      m->launches++;
-      CK(cudaGetLastError());
-    }
+    const size_t nlp = (size_t)((m->nl + 1) & ~1);
+    const size_t wf = (size_t)((gf.n + 8 - 1 + 4 - 1) / 4) * 8 * gf.n * nlp;
+    const size_t w4 = (size_t)((gf.n + 4 - 1 + 8 - 1) / 8) * 4 * gf.n * nlp;
+    size_t need = K == 8 ? wf : w4;
+    if (words > need) need = words;
+    int rc = ensure_mailbox(m, need);
+    if (rc) return rc;
+    k_fill_u64<<<m->num_sms * 4, 256, 0, m->stream>>>(m->mailbox, m->mailbox_words, MAIL_EMPTY);
+    m->launches++;
+    CK(cudaGetLastError());
   }
   RelaxArgs A;
-  A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps; A.init_zero = init_zero;
-  A.mailbox = m->mailbox; A.err = m->d_err;
+  A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
+  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg;
   const size_t smem = Cfg::smem_per_warp * WPC;
   auto kern = k_relax_lex<NL, K, WPC>;
   static bool attr_set = false;
@@ -493,16 +492,22 @@ static int launch_relax_t(msqg_model *m, double *da, const double *res, int lev,
   m->launches++;
   return MSQG_OK;
 }
+template <int NL, int K>
+static int launch_relax_t(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
+  /* warps per CTA limited by the per-warp shared-memory rings */
+  constexpr size_t spw = RelaxCfg<NL, K>::smem_per_warp;
+  if constexpr (spw * 4 <= 200 * 1024) return launch_relax_w<NL, K, 4>(m, da, res, lev, nsweeps, C);
+  else return launch_relax_w<NL, K, 2>(m, da, res, lev, nsweeps, C);
+}
 
 template <int NL>
-static int launch_relax(msqg_model *m, double *da, const double *res, int lev, int nrelax, int init_zero,
-                        const RelaxCoef<NL> &C) {
+static int launch_relax(msqg_model *m, double *da, const double *res, int lev, int nrelax, const RelaxCoef<NL> &C) {
   int done = 0;
   while (done < nrelax) {
     int ns = nrelax - done;
     int rc;
-    if (ns <= 4) rc = launch_relax_t<NL, 4>(m, da, res, lev, ns, init_zero && done == 0, C);
-    else { if (ns > 8) ns = 8; rc = launch_relax_t<NL, 8>(m, da, res, lev, ns, init_zero && done == 0, C); }
+    if (ns <= 4) rc = launch_relax_t<NL, 4>(m, da, res, lev, ns, C);
+    else { if (ns > 8) ns = 8; rc = launch_relax_t<NL, 8>(m, da, res, lev, ns, C); }
     if (rc) return rc;
     done += ns;
   }
@@ -569,19 +574,19 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
   const int minlevel = D < 1 ? D : 1;
   for (int l = minlevel; l <= D; l++) {
     const Geom &g = m->g[l];
-    int init_zero = 0;
-    if (l == minlevel) init_zero = 1; /* da = 0 on the coarsest level */
-    else {
+    if (l == minlevel) { /* da = 0 on the coarsest level */
+      CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)P.nf * g.plane * sizeof(double), m->stream));
+    } else {
       k_prolong<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
       m->launches++;
       CK(cudaGetLastError());
     }
     int rc;
     if (P.mode < 0) {
-      NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, init_zero, C); });
+      NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C); });
     } else {
       auto C = relax_coef_scalar(m, l, m->lam_lev[(size_t)l * m->nl + P.mode]);
-      rc = launch_relax<1>(m, m->da.lev[l], m->res.lev[l], l, nrelax, init_zero, C);
+      rc = launch_relax<1>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C);
     }
     if (rc) return rc;
   }
@@ -1165,7 +1170,7 @@ extern "C" int msqg_test_relax(msqg_model *m, int level, double *a, const double
   int rc;
   if ((rc = upload_level(m, m->da.lev[level], a, m->nl, level, -1.))) return rc;
   if ((rc = upload_level(m, m->res.lev[level], b, m->nl, level, -1.))) return rc;
-  NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, level); rc = launch_relax<NL>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, 0, C); });
+  NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, level); rc = launch_relax<NL>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, C); });
   if (rc) return rc;
   if ((rc = check_relax_err(m))) return rc;
   return download_level(m, a, m->da.lev[level], m->nl, level);
@@ -1178,7 +1183,7 @@ extern "C" int msqg_test_relax_scalar(msqg_model *m, int level, double lambda, d
   if ((rc = upload_level(m, m->da.lev[level], a, 1, level, -1.))) return rc;
   if ((rc = upload_level(m, m->res.lev[level], b, 1, level, -1.))) return rc;
   auto C = relax_coef_scalar(m, level, lambda);
-  if ((rc = launch_relax<1>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, 0, C))) return rc;
+  if ((rc = launch_relax<1>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, C))) return rc;
   if ((rc = check_relax_err(m))) return rc;
   return download_level(m, a, m->da.lev[level], 1, level);
 }
@@ -1262,5 +1267,24 @@ extern "C" int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if ((rc = check_relax_err(m))) return rc;
   *ms_out = ms / reps;
+  return MSQG_OK;
+}
+
+/* per-worker timeline of one relax launch: out[w] = {start ns, end ns, spins, 0} */
+extern "C" int msqg_test_relax_profile(msqg_model *m, int level, int nsweeps, long long *out, int max_workers) {
+  CK(cudaSetDevice(m->device));
+  if (level < 1 || level > m->depth) FAIL(MSQG_ERR_ARG, "bad level");
+  if (!m->const_set || !m->s_uniform) FAIL(MSQG_ERR_ARG, "needs set_const and uniform stretching");
+  long long *d;
+  CK(cudaMalloc(&d, (size_t)max_workers * 4 * sizeof(long long)));
+  CK(cudaMemset(d, 0, (size_t)max_workers * 4 * sizeof(long long)));
+  m->d_dbg = d;
+  int rc;
+  NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, level); rc = launch_relax<NL>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, C); });
+  m->d_dbg = nullptr;
+  if (rc) return rc;
+  if ((rc = check_relax_err(m))) return rc;
+  CK(cudaMemcpy(out, d, (size_t)max_workers * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  cudaFree(d);
   return MSQG_OK;
 }
