@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- cell-layer updates/s of the msqg timestep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one full predictor-corrector timestep (2 x (PV inversion + RHS +
+stage update)) of the 4096^2 x nl=4 synthetic double-gyre workload of
+SURVEY.md 8(d).  `value` is measured with the state resident in HBM; `e2e` is
+the same step driven through the C ABI with HOST buffers (q uploaded from and
+downloaded to pinned host memory every step).  `--impl reference` times the
+CPU oracle (the reference itself cannot be built here: Basilisk/qcc absent) on
+all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "cell-layer updates/s"
+UNIT = "cell-layer updates/s"
+N_DEFAULT, NL_DEFAULT = 4096, 4
+
+
+def workload_kw(N, nl):
+    from common import base_kw
+    return base_kw(N, nl)
+
+
+def workload_psi(N, nl):
+    from common import synth_psi
+    return synth_psi(N, nl)
+
+
+def algorithmic_bytes(nl):
+    """bytes per cell-layer of each piece (F = 8 B, sigma = (nl-1)/nl)."""
+    sig = (nl - 1.0) / nl
+    return dict(relax_sweep=(3 + sig) * 8, residual=(3 + sig) * 8, restrict=5.0 / 3 * 8, prolong=5.0 / 3 * 8,
+                correct=3 * 8.0, rhs=(5 + sig) * 8)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(N, nl, steps, warmup):
+    """The CPU oracle built with OpenMP (same algorithm and loop order as the reference,
+    foreach() as an omp-for like `qcc -fopenmp`), on all host cores."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    m = O.Model(O.make_params(omp=True, **workload_kw(N, nl)), omp=True)
+    m.set(O.PSI, workload_psi(N, nl))
+    m.set_const()
+    for _ in range(warmup):
+        m.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.step()
+    dt = time.perf_counter() - t0
+    cyc = m.L.orc_total_cycles(m.h)
+    m.close()
+    return N * N * nl * steps / dt, dt / steps * 1e3, int(os.environ["OMP_NUM_THREADS"]), cyc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    Ns = 2048 if cores >= 32 else 1024
+    val, ms, threads, _ = cpu_oracle_run(Ns, args.nl, args.steps, args.warmup)
+    sample = ("%d^2 x nl=%d grid with the parameters of the %d^2 workload (metric is per cell-layer); "
+              "%d steps after %d warm-up" % (Ns, args.nl, args.N, args.steps, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "msqg double-gyre %d^2 x nl=%d, layer-coupled multigrid inversion" % (args.N, args.nl),
+                       "reference": "CPU oracle (C restatement of msqg, OpenMP; the Basilisk build itself needs qcc, absent here)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from msqg_b200 import capi as G
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the msqg timestep has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, nl = args.N, args.nl
+    m = G.Model(G.make_params(**workload_kw(N, nl)), local)
+    stream = torch.cuda.Stream(device=local)
+    m.set_stream(stream.cuda_stream)
+    m.set(G.PSI, workload_psi(N, nl))
+    m.set_const()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        m.step()
+    # ---- timed region: K steps, state resident in HBM, per-launch events on the same stream
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    m.profile(True)
+    c0, l0 = m.total_cycles, m.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            m.step()
+        e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = m.profile_read()
+    m.profile(False)
+    cycles, launches = m.total_cycles - c0, m.launches - l0
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * N * N * nl * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: q up, step, q down, every step
+    esteps = max(1, min(args.steps, 5))
+    hq = torch.empty((nl, N, N), dtype=torch.float64).pin_memory()
+    hq_np = hq.numpy()
+    G.check(m.L.msqg_get_field(m.h, G.Q, hq_np))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        G.check(m.L.msqg_set_field(m.h, G.Q, hq_np))
+        m.step()
+        G.check(m.L.msqg_get_field(m.h, G.Q, hq_np))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * N * N * nl * esteps / e2e_s
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: finest-level relax launches
+    ab = algorithmic_bytes(nl)
+    peak, peak_src = peaks()
+    rf = prof["relax_fine"]
+    cells = float(N) * N * nl
+    roof = None
+    if rf["count"] > 0 and rf["ms"] > 0:
+        alg_bytes_per_launch = ab["relax_sweep"] * cells * (rf["aux"] / rf["count"])
+        ach = alg_bytes_per_launch / (rf["ms"] / rf["count"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_relax_lex (finest level)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": rf["ms"] / rf["count"], "sweeps_per_launch": rf["aux"] / rf["count"],
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "share_of_step": rf["ms"] / ms_total,
+                "note": "latency-bound wavefront (exact reference sweep order): all sweeps of a launch are one HBM pass"}
+    kern_ms = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}
+    # whole-step algorithmic bytes with the measured cycle counts
+    sweeps_all = prof["relax_fine"]["aux"]  # every level does the same number of sweeps per cycle
+    step_bytes = (2 * (ab["rhs"] + ab["residual"]) * args.steps +
+                  cycles * (ab["restrict"] * 1.0 + ab["prolong"] * 1.0 + ab["correct"] + ab["residual"]) +
+                  sweeps_all * ab["relax_sweep"] * 4.0 / 3) * cells / args.steps
+    step_roof = step_bytes / (ms_step * 1e-3) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            Ns = 1024
+            cv, cms, threads, _ = cpu_oracle_run(Ns, nl, 3, 1)
+            cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "%d^2 x nl=%d grid, same parameters, 3 steps after 1 warm-up (metric is per cell-layer)" % (Ns, nl),
+                   "ms_per_step": cms}
+        except Exception as ex:  # the baseline is a report, never a gate
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "msqg double-gyre %d^2 x nl=%d, layer-coupled multigrid inversion (MODE_PV_INVERT 0), "
+                                   "tolerance 1e-3, reference-order Gauss-Seidel" % (N, nl),
+                       "N": N, "nl": nl, "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
+                       "l2": "inputs larger than L2 (each layer list is %.0f MB)" % (cells * 8 / 1e6),
+                       "mg_cycles_per_step": cycles / args.steps},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(cells * 8), "d2h_bytes_per_step": int(cells * 8),
+                    "steps": esteps, "ms_per_step": e2e_s / esteps * 1e3},
+            "roofline": roof, "cpu_baseline": cpu,
+            "kernel_ms_per_step": kern_ms,
+            "step_roofline": {"algorithmic_bytes_per_cell_layer_per_step": step_bytes / cells, "achieved": step_roof,
+                              "peak": peak, "unit": "GB/s", "frac": step_roof / peak}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--N", type=int, default=N_DEFAULT)
+    ap.add_argument("--nl", type=int, default=NL_DEFAULT)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,7 @@ enum {
   MSQG_TMP,       /* tmpl     msqg/qg.h:57  */
   MSQG_ZETAP,     /* zetapl   msqg/qg.h:26  */
   MSQG_QPRED,     /* "predictor" list of the predictor-corrector */
+  MSQG_SIGFILT,   /* sig_filt msqg/qg.h:48  (1 scalar) */
   MSQG_NFIELDS
 };
 
@@ -106,6 +107,11 @@ int msqg_set_field(msqg_model *m, int id, const double *host);
 /* pyget_field (qg.h:1177-1189) */
 int msqg_get_field(msqg_model *m, int id, double *host);
 int msqg_set_flag_topo(msqg_model *m, int flag);  /* flag_topo, qg.h:971-977 */
+/* reset_layer_var (layer.h:37-41): zero the interior, ghost ring untouched */
+int msqg_reset_field(msqg_model *m, int id);
+/* layer thicknesses dhf (qg.h:895-896; overridden by dh_%dl.bin, qg.h:940-948) */
+int msqg_set_dh(msqg_model *m, const double *dh);
+int msqg_get_dh(msqg_model *m, double *dh);
 /* set_const (qg.h:931-1116) minus the file reads (done by the C host, which
  * pushes file contents through msqg_set_field first) */
 int msqg_set_const(msqg_model *m);
@@ -129,6 +135,8 @@ int msqg_step(msqg_model *m, double t, double tnext, double *dt_out, double *tne
 int msqg_ke1(msqg_model *m, double *ke);          /* writestdout, qg.c:101-106 */
 /* the tendency of pystep_bfn (qg_bfn.h:21-80, vartype==1): q already set */
 int msqg_tendency_bfn(msqg_model *m, double direction);
+/* only the sign flips of pystep_bfn (qg_bfn.h:34-44) */
+int msqg_bfn_direction(msqg_model *m, double direction);
 /* timestep()'s static `previous` (Basilisk timestep.h): get / reset */
 double msqg_get_ts_previous(msqg_model *m);
 void msqg_set_ts_previous(msqg_model *m, double v);
@@ -157,6 +165,12 @@ int msqg_test_restrict(msqg_model *m, int level, const double *fine, double *coa
 int msqg_test_prolong(msqg_model *m, int level, const double *coarse, double *fine);
 /* div_by() (exact division by a pivot with known reciprocal) next to IEEE x/d */
 int msqg_test_div(int device, const double *x, const double *d, double *q_fast, double *q_ieee, int n);
+/* per-launch CUDA-event timing by kernel category (8 categories: relax finest,
+ * relax coarser, residual, restrict, prolong, correct, laplacians, rhs) */
+int msqg_profile_enable(msqg_model *m, int on);
+int msqg_profile_read(msqg_model *m, double *ms, long *count, long *aux_sum);
+/* per-worker timeline of one relax launch (debug): out[w] = {start ns, end ns, spins, 0} */
+int msqg_test_relax_profile(msqg_model *m, int level, int nsweeps, long long *out, int max_workers);
 /* one mg_cycle + residual at the model's shape, timed with CUDA events (ms) */
 int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_out);
 
@@ -186,6 +200,16 @@ int qg_set_device(int device);
 int qg_set_mode_pv_invert(int mode);              /* MODE_PV_INVERT, qg.h:4 */
 int qg_set_stochastic(int on);                    /* -D_STOCHASTIC, qg.c:25 */
 /* .bas files (auxiliar_input.h:24-59,101-149) on host arrays [nf][N][N] */
+int qg_set_verbose(int v);
+double qg_time(void);
+int qg_iter(void);
+const char *qg_outdir(void);
+int qg_set_outdir(const char *d);
+/* pieces of run(): init event (qg.c:53-72), event-loop reset, one iteration
+ * (events + one step; returns 1 while running, 0 at the end, <0 on error) */
+int qg_init_event(void);
+int qg_run_reset(void);
+int qg_run_iteration(int write_files);
 int qg_write_bas(const char *name, int nf, int N, double L0, const double *v);
 int qg_read_bas(const char *name, int nf, int N, double L0, double *v);
 

@@ -110,6 +110,9 @@ def lib():
     L.msqg_test_prolong.argtypes = [vp, C.c_int, dp, dp]
     L.msqg_test_div.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int]
     L.msqg_time_vcycle.argtypes = [vp, C.c_int, C.c_int, pd]
+    L.msqg_profile_enable.argtypes = [vp, C.c_int]
+    L.msqg_profile_read.argtypes = [vp, pd, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    L.msqg_reset_field.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -219,6 +222,19 @@ class Model:
         ms = C.c_double()
         check(self.L.msqg_time_vcycle(self.h, nrelax, reps, C.byref(ms)))
         return ms.value
+
+    PROF_CATS = ("relax_fine", "relax_coarse", "residual", "restrict", "prolong", "correct", "laplacian", "rhs")
+
+    def set_stream(self, cuda_stream):
+        check(self.L.msqg_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def profile(self, on=True):
+        check(self.L.msqg_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        ms = (C.c_double * 8)(); cnt = (C.c_long * 8)(); aux = (C.c_long * 8)()
+        check(self.L.msqg_profile_read(self.h, ms, cnt, aux))
+        return {k: dict(ms=ms[i], count=cnt[i], aux=aux[i]) for i, k in enumerate(self.PROF_CATS)}
 
     @property
     def total_cycles(self):

@@ -37,6 +37,8 @@ extern "C" const char *msqg_last_error(void) { return g_err; }
 
 static inline double sq(double x) { return x * x; }
 
+enum { PROF_RELAX_FINE = 0, PROF_RELAX_COARSE, PROF_RESIDUAL, PROF_RESTRICT, PROF_PROLONG, PROF_CORRECT, PROF_LAP, PROF_RHS, PROF_NCAT };
+
 struct List {
   int nf = 0;
   double sg = -1.;               /* -1 dirichlet(0), +1 symmetry (layer.h:5-35) */
@@ -89,6 +91,28 @@ struct msqg_model {
   msqg_mgstats mgpsi, mgmode[MSQG_MAXL];
   long total_cycles, launches;
   int keep_dq;
+  /* optional per-launch timing (CUDA events on the model's stream) */
+  int prof_on;
+  std::vector<cudaEvent_t> prof_pool;
+  struct ProfRec { int cat, aux; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  size_t prof_next;
+};
+
+struct ProfScope {
+  msqg_model *m; cudaEvent_t e1; bool on;
+  ProfScope(msqg_model *m_, int cat, int aux) : m(m_), e1(nullptr), on(m_->prof_on != 0) {
+    if (!on) return;
+    cudaEvent_t ev[2];
+    for (int k = 0; k < 2; k++) {
+      if (m->prof_next >= m->prof_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); m->prof_pool.push_back(e); }
+      ev[k] = m->prof_pool[m->prof_next++];
+    }
+    cudaEventRecord(ev[0], m->stream);
+    e1 = ev[1];
+    m->prof_recs.push_back({cat, aux, ev[0], ev[1]});
+  }
+  ~ProfScope() { if (on) cudaEventRecord(e1, m->stream); }
 };
 
 /* ------------------------------------------------------------------ params */
@@ -189,6 +213,7 @@ static List *list_by_id(msqg_model *m, int id) {
     case MSQG_CM2L: return &m->cm2l;   case MSQG_PM: return &m->pm;
     case MSQG_QM: return &m->qm;       case MSQG_TMP: return &m->tmp;
     case MSQG_ZETAP: return &m->zetap; case MSQG_QPRED: return &m->qpred;
+    case MSQG_SIGFILT: return &m->sigfilt;
   }
   return nullptr;
 }
@@ -279,7 +304,7 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   m->iRe = p->iRe; m->iRe4 = p->iRe4; m->Eks = p->Eks; m->Ekb = p->Ekb;
   m->ts_previous = 0.; m->corrector_step = 0; m->noise_seeded = 0;
   m->flag_topo = 0; m->has_qforc = 0; m->has_zp = 0; m->const_set = 0;
-  m->total_cycles = 0; m->launches = 0; m->keep_dq = 0;
+  m->total_cycles = 0; m->launches = 0; m->keep_dq = 0; m->prof_on = 0; m->prof_next = 0;
   memset(&m->mgpsi, 0, sizeof(m->mgpsi));
   memset(m->mgmode, 0, sizeof(m->mgmode));
   memset(m->umax_pg, 0, sizeof(m->umax_pg));
@@ -327,6 +352,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->d_err) cudaFree(m->d_err);
   if (m->h_err) cudaFreeHost(m->h_err);
   if (m->mailbox) cudaFree(m->mailbox);
+  for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
   if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -352,6 +378,35 @@ extern "C" int msqg_set_flag_topo(msqg_model *m, int flag) { m->flag_topo = flag
 extern "C" int msqg_set_keep_dq(msqg_model *m, int keep) { m->keep_dq = keep; return MSQG_OK; }
 extern "C" int msqg_set_dissipation(msqg_model *m, double iRe, double iRe4, double Eks, double Ekb) {
   m->iRe = iRe; m->iRe4 = iRe4; m->Eks = Eks; m->Ekb = Ekb; /* pystep_bfn flips these, qg_bfn.h:34-44 */
+  return MSQG_OK;
+}
+extern "C" int msqg_set_dh(msqg_model *m, const double *dh) {
+  for (int l = 0; l < m->nl; l++) m->dhf[l] = dh[l];
+  return MSQG_OK;
+}
+extern "C" int msqg_get_dh(msqg_model *m, double *dh) {
+  for (int l = 0; l < m->nl; l++) dh[l] = m->dhf[l];
+  return MSQG_OK;
+}
+extern "C" int msqg_bfn_direction(msqg_model *m, double direction) {
+  const double Re = m->p.Re, Re4 = m->p.Re4;
+  if (direction > 0) {
+    m->iRe = (Re == 0) ? 0. : 1 / Re; m->iRe4 = (Re4 == 0) ? 0. : -1 / Re4;
+    m->Eks = fabs(m->Eks); m->Ekb = fabs(m->Ekb);
+  } else {
+    m->iRe = (Re == 0) ? 0. : -1 / Re; m->iRe4 = (Re4 == 0) ? 0. : 1 / Re4;
+    m->Eks = -fabs(m->Eks); m->Ekb = -fabs(m->Ekb);
+  }
+  return MSQG_OK;
+}
+extern "C" int msqg_reset_field(msqg_model *m, int id) {
+  CK(cudaSetDevice(m->device));
+  List *L = list_by_id(m, id);
+  if (!L || !L->lev[m->depth]) FAIL(MSQG_ERR_ARG, "field list %d is not allocated", id);
+  const Geom &g = m->g[m->depth];
+  for (int f = 0; f < L->nf; f++)
+    CK(cudaMemset2DAsync(L->lev[m->depth] + (size_t)f * g.plane + GIDX(g.pitch, 0, 0), (size_t)g.pitch * sizeof(double), 0,
+                         (size_t)g.n * sizeof(double), g.n, m->stream));
   return MSQG_OK;
 }
 extern "C" int msqg_last_mgstats(msqg_model *m, int mode, msqg_mgstats *out) {
@@ -547,11 +602,13 @@ static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
   const Geom &g = m->g[D];
   CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), m->stream));
   dim3 b(64, 4);
+  { ProfScope ps(m, PROF_RESIDUAL, 0);
   if (P.mode < 0) {
     LayerMetrics M = metrics_of(m);
     NL_SWITCH(m->nl, k_residual<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->str.lev[D], g, M, m->d_scal));
   } else {
     k_residual_scalar<<<grid2(g.n, g.n, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->ibu.lev[D] + (size_t)P.mode * g.plane, g, m->d_scal);
+  }
   }
   m->launches++;
   CK(cudaGetLastError());
@@ -567,6 +624,7 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
   dim3 b(32, 8);
   /* restriction(res): levels D-1..1 (level 0 is never read with minlevel = 1) */
   for (int l = D - 1; l >= 1; l--) {
+    ProfScope ps(m, PROF_RESTRICT, l);
     k_restrict<<<grid2(m->g[l].n, m->g[l].n, b, P.nf), b, 0, m->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
     m->launches++;
   }
@@ -577,11 +635,13 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
     if (l == minlevel) { /* da = 0 on the coarsest level */
       CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)P.nf * g.plane * sizeof(double), m->stream));
     } else {
+      ProfScope ps(m, PROF_PROLONG, l);
       k_prolong<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
       m->launches++;
       CK(cudaGetLastError());
     }
     int rc;
+    ProfScope ps(m, l == D ? PROF_RELAX_FINE : PROF_RELAX_COARSE, nrelax);
     if (P.mode < 0) {
       NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C); });
     } else {
@@ -591,7 +651,8 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
     if (rc) return rc;
   }
   const Geom &g = m->g[D];
-  k_correct<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(P.a, m->da.lev[D], g);
+  { ProfScope ps(m, PROF_CORRECT, 0);
+  k_correct<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(P.a, m->da.lev[D], g); }
   m->launches++;
   CK(cudaGetLastError());
   return MSQG_OK;
@@ -932,6 +993,7 @@ static int rhs_prepare(msqg_model *m) {
   const Geom &g = m->g[D];
   dim3 b(64, 4);
   CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
+  ProfScope ps(m, PROF_LAP, 0);
   k_lap<<<grid2(g.n + 1, g.n + 1, b, m->nl), b, 0, m->stream>>>(m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
   m->launches++;
   if (m->iRe != 0. || m->iRe4 != 0.) {
@@ -973,6 +1035,7 @@ static int rhs_launch(msqg_model *m, List &q_ev, const double *q_in, double *q_o
   A.has_pg = m->has_pg; A.has_zp = m->has_zp; A.use_tmp = (m->iRe != 0. || m->iRe4 != 0.);
   A.flag_topo = m->flag_topo; A.stochastic = m->p.stochastic;
   dim3 b(32, 4);
+  ProfScope ps(m, PROF_RHS, 0);
   NL_SWITCH(nl, k_rhs<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(A));
   m->launches++;
   CK(cudaGetLastError());
@@ -1117,14 +1180,7 @@ extern "C" int msqg_ke1(msqg_model *m, double *ke) {
  * qforcing; the caller has set q and the signed dissipation coefficients. */
 extern "C" int msqg_tendency_bfn(msqg_model *m, double direction) {
   CK(cudaSetDevice(m->device));
-  const double Re = m->p.Re, Re4 = m->p.Re4;
-  if (direction > 0) {
-    m->iRe = (Re == 0) ? 0. : 1 / Re; m->iRe4 = (Re4 == 0) ? 0. : -1 / Re4;
-    m->Eks = fabs(m->Eks); m->Ekb = fabs(m->Ekb);
-  } else {
-    m->iRe = (Re == 0) ? 0. : -1 / Re; m->iRe4 = (Re4 == 0) ? 0. : 1 / Re4;
-    m->Eks = -fabs(m->Eks); m->Ekb = -fabs(m->Ekb);
-  }
+  msqg_bfn_direction(m, direction);
   int rc;
   if ((rc = invertq_list(m, m->q))) return rc;
   if ((rc = rhs_prepare(m))) return rc;
@@ -1286,5 +1342,27 @@ extern "C" int msqg_test_relax_profile(msqg_model *m, int level, int nsweeps, lo
   if ((rc = check_relax_err(m))) return rc;
   CK(cudaMemcpy(out, d, (size_t)max_workers * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
   cudaFree(d);
+  return MSQG_OK;
+}
+
+/* per-launch timing: enable, run, then read per-category totals.
+ * cats: 0 relax(finest level) 1 relax(coarser levels) 2 residual 3 restrict 4 prolong 5 correct 6 laplacians 7 rhs.
+ * aux_sum[0] = total sweeps of the finest-level relax launches. */
+extern "C" int msqg_profile_enable(msqg_model *m, int on) {
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  m->prof_on = on; m->prof_recs.clear(); m->prof_next = 0;
+  return MSQG_OK;
+}
+extern "C" int msqg_profile_read(msqg_model *m, double *ms, long *count, long *aux_sum) {
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->stream));
+  for (int c = 0; c < PROF_NCAT; c++) { ms[c] = 0.; count[c] = 0; aux_sum[c] = 0; }
+  for (auto &r : m->prof_recs) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.cat] += t; count[r.cat]++; aux_sum[r.cat] += r.aux;
+  }
+  m->prof_recs.clear(); m->prof_next = 0;
   return MSQG_OK;
 }

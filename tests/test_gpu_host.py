@@ -1,0 +1,80 @@
+"""GPU parity through the reference-facing surfaces: the `qg` Python module
+(msqg/qg.i, qg_bfn.i entry points) and the qg.e process (msqg/qg.c) with its
+outdir_NNNN/*.bas outputs, against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import base_kw, synth_psi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_params(path, N, nl, tend=0.2, dtout=0.1, extra=""):
+    kw = base_kw(N, nl)
+    with open(path, "w") as f:
+        f.write("#!sh\nN  = %d\nnl = %d\nL0 = %g\nRom = %g\nEkb = %g\ntau0 = %g\nRe4 = %r\nbeta = %g\n"
+                "Fr = [%s]\ndh = [%s]\nDT = %g\ntend = %g\ndtout = %g\nCFL = %g\n%s" % (
+                    N, nl, kw["L0"], kw["Rom"], kw["Ekb"], kw["tau0"], kw["Re4"], kw["beta"],
+                    ",".join(repr(float(x)) for x in kw["Fr"]), ",".join(repr(float(x)) for x in kw["dh"]),
+                    kw["DT"], tend, dtout, kw["CFL"], extra))
+
+
+def test_python_module_matches_oracle(gpu, tmp_path, monkeypatch):
+    """read_params -> init_grid -> set_vars -> set_vars_bfn -> set_const -> pyp2q -> pystep_bfn -> pyq2p
+    (the call order of msqg/qg_bfn.py) against the oracle's restatement of qg_bfn.h."""
+    from oracle import oracle as O
+    import msqg_b200.qg as bas
+    N, nl = 64, 3
+    monkeypatch.chdir(tmp_path)
+    _write_params("params.in", N, nl)
+    bas.read_params("params.in"); bas.init_grid(N); bas.set_vars(); bas.set_vars_bfn(); bas.set_const()
+    po = O.Params(); O.lib().orc_default_params(po); O.lib().orc_read_params(b"params.in", po)
+    mo = O.Model(po); mo.set_const()
+    p = synth_psi(N, nl)
+    q = np.zeros_like(p); q_ref = np.zeros_like(p)
+    bas.pyp2q(p, q); mo.L.orc_pyp2q(mo.h, p, q_ref)
+    assert np.array_equal(q, q_ref)
+    for direction in (1.0, -1.0):
+        F = np.zeros_like(p); F_ref = np.zeros_like(p)
+        bas.pystep_bfn(q, F, direction, 1); mo.L.orc_pystep_bfn(mo.h, q, F_ref, direction, 1)
+        assert np.array_equal(F, F_ref)
+    p2 = np.zeros_like(p); p2_ref = np.zeros_like(p)
+    bas.pyq2p(p2, q); mo.L.orc_pyq2p(mo.h, p2_ref, q)
+    assert np.array_equal(p2, p2_ref)
+    bas.trash_vars(); bas.trash_vars_bfn()
+
+
+def test_qg_exe_outputs_match_oracle_run(gpu, tmp_path):
+    """./qg.e with p0.bas: same stdout cadence and bit-identical po/qo .bas files as the oracle's run()."""
+    from oracle import oracle as O
+    N, nl = 64, 2
+    wd = tmp_path / "gpu"; wd.mkdir()
+    wo = tmp_path / "orc"; wo.mkdir()
+    _write_params(str(wd / "params.in"), N, nl, tend=0.1, dtout=0.05)
+    psi = synth_psi(N, nl)
+    O.lib().orc_write_bas(str(wd / "p0.bas").encode(), nl, N, 80., psi)
+    exe = os.path.join(ROOT, "msqg_b200", "lib", "qg.e")
+    out = subprocess.run([exe], cwd=str(wd), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Config: N = 64, nl = 2, L0 = 80" in out.stdout and "write file" in out.stdout
+    # oracle: same init path (psi read back through float32 p0.bas, mean removed)
+    po = O.Params(); O.lib().orc_default_params(po); O.lib().orc_read_params(str(wd / "params.in").encode(), po)
+    mo = O.Model(po)
+    p0 = np.zeros_like(psi); O.lib().orc_read_bas(str(wd / "p0.bas").encode(), nl, N, 80., p0)
+    mo.set(O.PSI, p0); mo.L.orc_remove_mean_psi(mo.h); mo.set_const()
+    nsteps = mo.run(outdir=str(wo))
+    gdir = wd / "outdir_0001"
+    names = sorted(f for f in os.listdir(wo) if f.endswith(".bas"))
+    assert len(names) == 6 and nsteps > 0          # po/qo at t = 0, 0.05, 0.1
+    for f in names:
+        assert (gdir / f).read_bytes() == (wo / f).read_bytes(), f
+    for f in ("params.in", "sig_filt.bas", "rdpg_2l_N64.bas", "psipg_2l_N64.bas", "frpg_2l_N64.bas",
+              "qforc_2l_N64.bas", "dh_2l.bin"):
+        assert (gdir / f).exists(), f
+    # the readers of msqg/scripts/read_data.py:22-46 see the field
+    a = np.fromfile(str(gdir / names[0]), "f4").reshape(nl, N + 1, N + 1).transpose(0, 2, 1)[:, 1:, 1:]
+    assert a.shape == (nl, N, N) and np.isfinite(a).all()
