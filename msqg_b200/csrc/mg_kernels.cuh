@@ -312,6 +312,7 @@ struct RelaxArgs {
   unsigned long long *mailbox;  /* [nworkers][K][n][NLP] words, armed with MAIL_EMPTY */
   int *err;                     /* set to 1 on spin timeout */
   long long *dbg;               /* optional [nworkers][4]: start ns, end ns, spins, - */
+  int flags;                    /* reserved for timing experiments */
 };
 
 #define MAIL_EMPTY 0xFFF8DEADBEEF0001ull

@@ -248,14 +248,14 @@ static int unpack_from(msqg_model *m, List &L, double *host) {
 /* ------------------------------------------------------------------ create / destroy */
 extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   *out = nullptr;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    FAIL(MSQG_ERR_CUDA, "no CUDA device: the msqg timestep has no CPU path");
-  if (device < 0 || device >= ndev) FAIL(MSQG_ERR_ARG, "bad device %d", device);
   if (p->nl < 2 || p->nl > MSQG_NLMAX) FAIL(MSQG_ERR_ARG, "nl must be in [2,%d] (nl==1 is not functional in the reference)", MSQG_NLMAX);
   if (p->N < 8 || (p->N & (p->N - 1))) FAIL(MSQG_ERR_ARG, "N must be a power of two >= 8");
   if (p->sbc != 0) FAIL(MSQG_ERR_ARG, "only sbc == 0 (free slip) is supported");
   if (p->nptr != 0) FAIL(MSQG_ERR_ARG, "passive tracers (nptr > 0) are out of scope");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    FAIL(MSQG_ERR_CUDA, "no CUDA device: the msqg timestep has no CPU path");
+  if (device < 0 || device >= ndev) FAIL(MSQG_ERR_ARG, "bad device %d", device);
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -527,6 +527,7 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
   RelaxArgs A;
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
   A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg;
+  { const char *f = getenv("MSQG_RELAX_FLAGS"); A.flags = f ? atoi(f) : 0; }
   const size_t smem = Cfg::smem_per_warp * WPC;
   auto kern = k_relax_lex<NL, K, WPC>;
   static bool attr_set = false;

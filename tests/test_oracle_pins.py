@@ -1,0 +1,175 @@
+"""Known-answer pins of the CPU oracle: the reference ships
+no golden vectors and cannot be built here, so the oracle is pinned by identities
+that follow from the reference's own formulas, plus regression fixtures generated
+by the oracle itself (tests/golden, made by tests/golden/make_golden.py)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from common import DH, FR, base_kw, rel_l2, synth_psi
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _model(N, nl, **over):
+    m = O.Model(O.make_params(**base_kw(N, nl, **over)))
+    m.set(O.PSI, synth_psi(N, nl))
+    m.set_const()
+    return m
+
+
+def test_read_params_double_gyre_fixture(tmp_path):
+    """read_params on the reference's only shipped configuration (values of
+    msqg/test/params.double_gyre.in) incl. the derived values of qg.h:739-746."""
+    f = tmp_path / "params.in"
+    f.write_text("#!sh\n# Double gyre configuration of Verron 1992\n\nN  = 256\nnl = 3\nL0 = 80\n\nRom   = 0.025\n"
+                 "Ekb   = 0.002\ntau0  = 0.0001\nRe4   = 1563\nbeta  = 0.5\nFr = [0.0023669,0.0076173]\n"
+                 "dh = [0.06,0.14,0.8]\n\nDT    = 5.e-2\ntend  = 500.\ndtout = 1.\nCFL   = 0.6\n")
+    p = O.Params()
+    O.lib().orc_default_params(p)
+    assert O.lib().orc_read_params(str(f).encode(), p) == 0
+    assert (p.N, p.nl, p.L0, p.Rom, p.Ekb, p.tau0, p.Re4, p.beta) == (256, 3, 80., 0.025, 0.002, 1e-4, 1563., 0.5)
+    assert list(p.Fr)[:2] == [0.0023669, 0.0076173] and list(p.dh)[:3] == [0.06, 0.14, 0.8]
+    assert (p.tend, p.dtout, p.CFL) == (500., 1., 0.6)
+    assert p.iRe == 0. and p.iRe4 == -1 / 1563.
+    # DT = 0.5*min(DT, Delta^4*Re4/32) -- the 0.5 applies even when min picks DT
+    d2 = (80. / 256) * (80. / 256)
+    assert p.DT == 0.5 * min(5e-2, d2 * d2 * 1563. / 32.)
+    assert O.lib().orc_read_params(b"/nonexistent/params.in", p) == -1
+
+
+def test_arakawa_invariants():
+    """Arakawa (1966) Jacobian (qg.h:252-262): for fields supported away from the walls,
+    sum J = sum psi*J = sum zeta*J = 0 to round-off.  Checked through update_qg with every
+    other tendency switched off (beta = Ekb = tau0 = Re4 = 0, negligible stretching)."""
+    N, nl = 64, 2
+    m = O.Model(O.make_params(**base_kw(N, nl, beta=0., Ekb=0., tau0=0., Re4=0., Fr=[1e-30], DT=1e-3)))
+    rng = np.random.default_rng(0)
+    psi = np.zeros((nl, N, N))
+    psi[:, 6:-6, 6:-6] = rng.standard_normal((nl, N - 12, N - 12))
+    for _ in range(3):  # smooth a little, support stays >= 3 cells away from the walls
+        psi[:, 1:-1, 1:-1] = 0.25 * (psi[:, :-2, 1:-1] + psi[:, 2:, 1:-1] + psi[:, 1:-1, :-2] + psi[:, 1:-1, 2:])
+    m.set(O.PSI, psi)
+    m.set_const()          # q = comp_q(psi): invertq inside update_qg then returns psi to round-off
+    m.update(1e-3)
+    p, z, dq = m.get(O.PSI), m.get(O.ZETA), m.get(O.DQ)
+    assert rel_l2(p, psi) < 1e-9
+    for l in range(nl):
+        assert np.abs(dq[l]).max() > 0
+        assert abs(dq[l].sum()) < 1e-9 * np.abs(dq[l]).sum()
+        assert abs((z[l] * dq[l]).sum()) < 1e-9 * np.abs(z[l] * dq[l]).sum()
+        assert abs((p[l] * dq[l]).sum()) < 1e-9 * np.abs(p[l] * dq[l]).sum()
+
+
+def test_thomas_line_solve_matches_dense():
+    """One relax_layer sweep on a single interior cell == dense solve of the nl x nl system
+    (poisson_layer.h:80-146)."""
+    nl, level = 4, 1
+    n = 2
+    kw = base_kw(32, nl)
+    dh = np.array(DH[nl])
+    s = np.array([(f / kw["Rom"]) ** 2 for f in FR[nl]])
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal((nl, n, n))
+    a = np.zeros((nl, n, n))
+    sf = np.stack([np.full((n, n), v) for v in s])
+    O.lib().orc_test_relax(nl, level, kw["L0"], dh, sf, a, b, 1, 1, 1)
+    # first cell in sweep order (x=0,y=0): all neighbours are zero (ghost = -0, others not yet updated = 0)
+    D = kw["L0"] / n
+    dhc = 0.5 * (dh[:-1] + dh[1:])
+    A = np.zeros((nl, nl))
+    for l in range(nl):
+        t0 = -D * D * s[l - 1] / (dhc[l - 1] * dh[l]) if l > 0 else 0.
+        t2 = -D * D * s[l] / (dhc[l] * dh[l]) if l < nl - 1 else 0.
+        A[l, l] = 4 - t0 - t2
+        if l > 0:
+            A[l, l - 1] = t0
+        if l < nl - 1:
+            A[l, l + 1] = t2
+    ref = np.linalg.solve(A, -D * D * b[:, 0, 0])
+    assert np.allclose(a[:, 0, 0], ref, rtol=1e-12, atol=0)
+
+
+def test_eigenmode_identities():
+    """eigmode.h:213-266: cl2m*cm2l = I, sum_k dh_k vr_km^2 = 1, surface-positive, iBu[0] = 0,
+    and the 2-layer analytic deformation radius."""
+    for nl in (2, 3, 4, 10):
+        dh = np.array(DH[nl]); fr = np.array(FR[nl] + [0.]); Ro = 0.025
+        cl, cm, ib = np.zeros(nl * nl), np.zeros(nl * nl), np.zeros(nl)
+        rc = O.lib().orc_eigmod_column(nl, dh, fr, Ro, cl, cm, ib)
+        if rc == -2:
+            pytest.skip("no LAPACK dgeev available")
+        assert rc == 0
+        L2M, M2L = cl.reshape(nl, nl).T, cm.reshape(nl, nl)   # cl2m[k*nl+m] = vl[m][k]; cm2l[k*nl+m] = vr[k][m]
+        # reference layout: qm[m] = sum_l cl2m[m*nl+l] q_l ; po[l] = sum_m cm2l[l*nl+m] pm
+        A = cl.reshape(nl, nl) @ cm.reshape(nl, nl)
+        assert np.allclose(A, np.eye(nl), atol=1e-10)
+        vr = cm.reshape(nl, nl)
+        assert np.allclose((dh[:, None] * vr ** 2).sum(0), 1., rtol=1e-12)
+        assert (vr[0] > 0).all()
+        assert ib[0] == 0. and (ib[1:] < 0).all() and np.all(np.diff(ib) <= 0)
+    dh = np.array(DH[2]); F = FR[2][0]; Ro = 0.025
+    cl, cm, ib = np.zeros(4), np.zeros(4), np.zeros(2)
+    O.lib().orc_eigmod_column(2, dh, np.array([F, 0.]), Ro, cl, cm, ib)
+    dhc = 0.5 * (dh[0] + dh[1])
+    lam = (F / Ro) ** 2 / dhc * (1 / dh[0] + 1 / dh[1])
+    assert np.isclose(-ib[1], lam, rtol=1e-12)
+
+
+def test_q2p_p2q_round_trip():
+    """comp_q(invertq(q)) == q to the solver tolerance (max-norm residual <= 1e-3, qg.h:159)."""
+    N, nl = 64, 3
+    m = _model(N, nl)
+    q = m.get(O.Q)
+    p = np.zeros_like(q); q2 = np.zeros_like(q)
+    m.L.orc_pyq2p(m.h, p, q)
+    s = m.mgstats()
+    assert s.resa <= 1e-3 and s.i >= 1
+    m.L.orc_pyp2q(m.h, p, q2)
+    assert np.abs(q2 - q).max() <= 1e-3 * 1.0000001
+    assert np.abs(q2 - q).max() == pytest.approx(s.resa, rel=1e-6)
+
+
+def test_bas_format_round_trip(tmp_path):
+    """.bas records (auxiliar_input.h:128-141) as the readers of msqg/scripts/read_data.py:22-46 see them."""
+    N, nl, L0 = 32, 3, 80.
+    v = synth_psi(N, nl)
+    f = str(tmp_path / "po.bas")
+    assert O.lib().orc_write_bas(f.encode(), nl, N, L0, v) == 0
+    raw = np.fromfile(f, "f4").reshape(nl, N + 1, N + 1)
+    assert (raw[:, 0, 0] == N).all()
+    assert np.allclose(raw[0, 0, 1:], (np.arange(N) + 0.5) * L0 / N, rtol=1e-6)
+    a = raw.transpose(0, 2, 1)[:, 1:, 1:]
+    assert np.array_equal(a, v.astype("f4"))
+    back = np.zeros_like(v)
+    assert O.lib().orc_read_bas(f.encode(), nl, N, L0, back) == 0
+    assert np.array_equal(back, v.astype("f4").astype("f8"))
+
+
+def test_timestep_ramp_and_ke():
+    """timestep() static state ([BASILISK] timestep.h): first dt = DT/11, geometric ramp toward DT."""
+    m = _model(64, 2)
+    DT = m.p.DT
+    dts = [m.step() for _ in range(4)]
+    assert dts[0] == pytest.approx(DT / 11, rel=1e-14)
+    assert dts[1] == pytest.approx((dts[0] + 0.1 * DT) / 1.1, rel=1e-14)
+    assert all(b > a for a, b in zip(dts, dts[1:]))
+    assert m.ke1() > 0
+
+
+def test_golden_regression():
+    """The oracle reproduces its committed outputs (guards the oracle against accidental edits)."""
+    g = np.load(os.path.join(HERE, "golden", "oracle_32x2_3steps.npz"))
+    m = _model(32, 2)
+    dts = [m.step() for _ in range(3)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert np.array_equal(m.get(O.PSI), g["psi"]) and np.array_equal(m.get(O.Q), g["q"])
+    g = np.load(os.path.join(HERE, "golden", "oracle_32x3_modal_2steps.npz"))
+    if O._lapack_path() is None:
+        pytest.skip("no LAPACK for eigmod")
+    m = _model(32, 3, mode_pv_invert=1)
+    dts = [m.step() for _ in range(2)]
+    assert rel_l2(m.get(O.PSI), g["psi"]) < 1e-11   # LAPACK builds may differ in the last bits
