@@ -407,7 +407,23 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
     ld_r[q] = A.res + (size_t)(ok_r[q] ? l : 0) * plane + GIDX(pitch, 0, ok_r[q] ? x : 0);
     st_r[q] = (unsigned)__cvta_generic_to_shared(sm_res + e);
   }
+  /* L2 prefetch distance (rows): the L1TEX return queue of an SM is in order, so a DRAM-missing
+     cp.async would delay every later L2-hit load (the mailbox) behind it; prefetching the streamed
+     rows into L2 well ahead keeps all of the strip's loads at L2 latency */
+  constexpr int PF = 48;
   auto load_row = [&](int r) {
+    {
+      const int rp = r + PF;
+      if (rp < n) {
+        const size_t gp = (size_t)rp * pitch;
+#pragma unroll
+        for (int q = 0; q < Cfg::EPL_D; q++)
+          if (ok_d[q]) asm volatile("prefetch.global.L2 [%0];" ::"l"(ld_d[q] + gp));
+#pragma unroll
+        for (int q = 0; q < Cfg::EPL_R; q++)
+          if (ok_r[q]) asm volatile("prefetch.global.L2 [%0];" ::"l"(ld_r[q] + gp));
+      }
+    }
     const bool in = r < n;
     const unsigned ro = (unsigned)(r & (RIN - 1));
     const size_t go = (size_t)(in ? r : 0) * pitch;
@@ -439,8 +455,14 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
   /* steps: lane (k,c) does row j = tau - c - 2k - 1.  tau = -2 is a dry run that warms the
      instruction cache, tau = -1 primes the software pipeline (loads for step 0). */
   const int T = n + W + 2 * K - 2;
+  /* A worker whose first mailbox entry has not arrived yet keeps executing the priming pair
+     tau = -1, 0 (idempotent: it only re-primes lane 0 and re-polls entry (0,row 0) through the
+     normal prefetch) instead of parking in a spin loop, so that its instruction cache and
+     streamed rows are hot the moment the wavefront reaches it. */
+  const bool wait_first = __shfl_sync(FULLMASK, (int)mb_reader, 0) != 0;
+  int waited = 0;
 #pragma unroll 1
-  for (int tau = -2; tau < T; tau++) {
+  for (int tau = -2; tau < T;) {
     const int j = tau - c - 2 * k - 1;
     const bool row_ok = (unsigned)j < (unsigned)n;
     const bool active = col_ok && row_ok;
@@ -465,7 +487,9 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
           for (int l = 0; l < NL; l++) miss |= (pend[l] == MAIL_EMPTY);
         }
         n_spins += spins;
+        if (A.dbg && rd && k == 0 && j == 0) { long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); A.dbg[(size_t)nworkers * 4 + w * 8 + 7] = tt; }
       }
+      __syncwarp(); /* reconverge after the (divergent) spin: the shuffles below must not take the slow BRA.DIV path */
     }
 #pragma unroll
     for (int l = 0; l < NL; l++) mailw[l] = __longlong_as_double((long long)pend[l]);
@@ -501,6 +525,7 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
       }
     }
     /* stream the rings P rows ahead; re-arm and prefetch the mailbox */
+    if (A.dbg && lane == 0 && (tau == 1 || tau == 2 || tau == 4 || tau == 8 || tau == 16 || tau == 64)) { long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); A.dbg[(size_t)nworkers * 4 + w * 8 + (tau == 1 ? 0 : tau == 2 ? 1 : tau == 4 ? 2 : tau == 8 ? 3 : tau == 16 ? 4 : 5)] = tt; }
     load_row(tau < 0 ? n : tau + P);
     cp_async_wait<P - 2>();
     {
@@ -543,7 +568,16 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
         const unsigned long long v1 = (l + 1 < NL) ? (unsigned long long)__double_as_longlong(out[l + 1]) : 0ull;
         st_mail2_if(wr, p + l, v0, v1);
       }
+      if (A.dbg && wr && k == 0 && j == 0) { long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); A.dbg[(size_t)nworkers * 4 + w * 8 + 6] = tt; }
     }
+    if (tau == 0 && wait_first) {
+      bool have = true;
+#pragma unroll
+      for (int l = 0; l < NL; l++) have = have && (pend[l] != MAIL_EMPTY);
+      have = __shfl_sync(FULLMASK, (int)have, 0) != 0;
+      if (!have && ++waited < SPIN_LIMIT) { tau = -1; continue; }
+    }
+    tau++;
   }
   cp_async_wait<0>();
   if (A.dbg) {

@@ -1333,15 +1333,15 @@ extern "C" int msqg_test_relax_profile(msqg_model *m, int level, int nsweeps, lo
   if (level < 1 || level > m->depth) FAIL(MSQG_ERR_ARG, "bad level");
   if (!m->const_set || !m->s_uniform) FAIL(MSQG_ERR_ARG, "needs set_const and uniform stretching");
   long long *d;
-  CK(cudaMalloc(&d, (size_t)max_workers * 4 * sizeof(long long)));
-  CK(cudaMemset(d, 0, (size_t)max_workers * 4 * sizeof(long long)));
+  CK(cudaMalloc(&d, (size_t)max_workers * 12 * sizeof(long long)));
+  CK(cudaMemset(d, 0, (size_t)max_workers * 12 * sizeof(long long)));
   m->d_dbg = d;
   int rc;
   NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, level); rc = launch_relax<NL>(m, m->da.lev[level], m->res.lev[level], level, nsweeps, C); });
   m->d_dbg = nullptr;
   if (rc) return rc;
   if ((rc = check_relax_err(m))) return rc;
-  CK(cudaMemcpy(out, d, (size_t)max_workers * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, d, (size_t)max_workers * 12 * sizeof(long long), cudaMemcpyDeviceToHost));
   cudaFree(d);
   return MSQG_OK;
 }
