@@ -588,3 +588,349 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
     if (lane == 0) { A.dbg[w * 4 + 0] = t_start; A.dbg[w * 4 + 1] = t_end; A.dbg[w * 4 + 2] = n_spins; }
   }
 }
+
+/* ------------------------------------------------------------------ relax_layer, warp-specialised
+ * Same arithmetic, schedule (lane (k,c) does row tau - c - 2k - 1 at step tau) and mailbox protocol
+ * as k_relax_lex, but each strip is served by TWO warps so that the warp on the critical path
+ * issues nothing but the Thomas recurrence and shared-memory traffic:
+ *
+ *   compute warp C : W shuffle, Thomas solve, results -> shared-memory ring of its sweep;
+ *                    east/north of sweep k come from the ring of sweep k-1 (slot c+1 / slot c),
+ *                    sweep 0 reads the same way from the ring of the initial iterate, res from
+ *                    its own ring; the strip's west column sits in slot 0 of each sweep ring.
+ *   helper warp H  : streams da/res rows HBM -> rings (cp.async, L2-prefetched ahead), polls the
+ *                    global mailbox of the left neighbour and deposits entries into slot 0,
+ *                    re-arms them, drains slot W of every sweep ring to the right neighbour's
+ *                    mailbox and the last sweep's rows to HBM.
+ *
+ * C and H talk through monotone counters in shared memory (rows loaded, mailbox rows deposited per
+ * sweep, rows drained per sweep, steps completed); C loads its next-step inputs speculatively
+ * before the recurrence and verifies the counters after it, so nothing but the W shuffle sits
+ * between two recurrences.
+ */
+template <int NL, int K>
+struct WsCfg {
+  static_assert(K == 4 || K == 8, "lanes = K sweeps x 32/K columns");
+  static constexpr int W = 32 / K, S = W + 1, RC = W + K - 1;
+  static constexpr int RIN = 32, R2 = 16;
+  static constexpr int NLP = (NL + 1) & ~1;
+  static constexpr int DROW = NL * S, RROW = NL * RC;
+  static constexpr int TAIL = W + 2 * K - 2; /* steps after which a streamed row is dead */
+  static constexpr int NCNT = 32;            /* ints of counters per worker */
+  static constexpr int DOUBLES = RIN * DROW + RIN * RROW + K * R2 * DROW + NCNT / 2;
+  static constexpr size_t smem_per_worker = (size_t)DOUBLES * sizeof(double);
+  static constexpr int EPL_D = (DROW + 31) / 32, EPL_R = (RROW + 31) / 32;
+  static constexpr int Q = 32 / K; /* mailbox rows polled per sweep per helper iteration */
+  enum { C_DONE = 0, IN_READY = 1, MAIL_READY = 2, DRAINED = 2 + 8 };
+};
+
+__device__ __forceinline__ int ld_cnt(const volatile int *p) { return *p; }
+
+template <int NL, int K, int WPC>
+__global__ void __launch_bounds__(64 * WPC)
+k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
+  using Cfg = WsCfg<NL, K>;
+  constexpr int W = Cfg::W, S = Cfg::S, RC = Cfg::RC, RIN = Cfg::RIN, R2 = Cfg::R2;
+  constexpr int NLP = Cfg::NLP, DROW = Cfg::DROW, RROW = Cfg::RROW, Q = Cfg::Q;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool helper = warp >= WPC;
+  const int wl = helper ? warp - WPC : warp; /* worker slot inside the CTA */
+  const int n = A.g.n;
+  const int w = blockIdx.x * WPC + wl;
+  const int nworkers = (n + K - 1 + W - 1) / W;
+  double *base = smem + (size_t)wl * Cfg::DOUBLES;
+  double *IN = base;                    /* [RIN][NL][S]  initial iterate, slot s <-> column w*W + s */
+  double *RES = IN + RIN * DROW;        /* [RIN][NL][RC] rc <-> column w*W - (K-1) + rc */
+  double *XR = RES + RIN * RROW;        /* K rings [R2][NL][S]: slot 0 west column, slot c+1 lane c */
+  volatile int *cnt = (volatile int *)(XR + K * R2 * DROW);
+  const int nsw = A.nsweeps;
+  const int kf = nsw - 1;
+  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE) ? -2 : 0;
+  __syncthreads();
+  if (w >= nworkers) return;
+  const int pitch = A.g.pitch;
+  const size_t plane = A.g.plane;
+  const bool has_consumer = (w + 1 < nworkers);
+
+  if (!helper) {
+    /* ================================================================ compute warp */
+    const int k = lane / W, c = lane % W;
+    const int i = w * W + c - k;
+    const bool col_ok = (i >= 0 && i < n && k < nsw);
+    const bool k0 = (k == 0);
+    const bool left = (i == 0), right = (i == n - 1);
+    const bool use_mail = (c == 0 && w > 0);
+    const bool use_mail_n = use_mail && k > 0;
+    const int prodcol = w * W - 1 - k;
+    const bool mb_reader = use_mail && k < nsw && prodcol >= 0 && prodcol < n;
+    const bool wr_valid = has_consumer && (w * W + W - 1 - k) >= 0 && (w * W + W - 1 - k) < n;
+    const bool drained_by_h = col_ok && (k == kf);
+    const bool mb_writer = wr_valid && c == W - 1 && col_ok;
+    unsigned long long *mo = A.mailbox + ((size_t)w * K + k) * (size_t)n * NLP + (long long)(-2 - c - 2 * k - 1) * NLP;
+    /* inputs of sweep k: ring of sweep k-1 (sweep 0: the streamed initial iterate); slot c north, slot c+1 east */
+    const double *in_l = (k0 ? IN : XR + (size_t)(k - 1) * R2 * DROW) + c;
+    const int in_mask = k0 ? RIN - 1 : R2 - 1;
+    double *ring = XR + (size_t)(k < K ? k : 0) * R2 * DROW;       /* own ring: slot 0 west column (from H), slot c+1 results */
+    const double *res_l = RES + (c - k + K - 1);
+    const bool wait_first = __shfl_sync(FULLMASK, (int)mb_reader, 0) != 0;
+
+    double cur[NL], En[NL], Nn[NL], cold[NL], bn[NL], wm[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) { cur[l] = En[l] = Nn[l] = cold[l] = bn[l] = wm[l] = 0.; }
+    long long t_start = 0, n_spins = 0;
+    if (A.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    const int T = n + W + 2 * K - 2;
+    int waited = 0;
+#pragma unroll 1
+    for (int tau = -2; tau < T;) {
+      const int j = tau - c - 2 * k - 1;
+      const int jn = j + 1;
+      const bool row_ok = (unsigned)j < (unsigned)n;
+      const bool nrow_ok = (unsigned)jn < (unsigned)n;
+      __syncwarp();
+      /* ---- (A) the only work ahead of the recurrence: west value and right-hand side */
+      double rhs[NL], out[NL], Wv[NL];
+#pragma unroll
+      for (int l = 0; l < NL; l++) {
+        const double wsh = __shfl_up_sync(FULLMASK, cur[l], 1);
+        Wv[l] = use_mail ? wm[l] : wsh;
+        double r = C.msd2 * bn[l];
+        r += En[l] + Wv[l];
+        r += Nn[l] + cur[l];
+        rhs[l] = r;
+      }
+      const bool edge = col_ok && ((row_ok && (left || right)) || j == 0 || j == n - 1);
+      if (__any_sync(FULLMASK, edge) || tau == -2) {
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+          const double g = -cold[l];
+          const double aw = left ? g : Wv[l];
+          const double ae = right ? g : En[l];
+          const double as = (j == 0) ? g : cur[l];
+          const double an = (j == n - 1) ? g : Nn[l];
+          double r = C.msd2 * bn[l];
+          r += ae + aw;
+          r += an + as;
+          rhs[l] = r;
+        }
+      }
+      /* ---- (B) next step's inputs, independent of this step's result: issued in the shadow of
+         the recurrence.  Counters are read BEFORE the data they guard and checked afterwards. */
+      const int c_in = ld_cnt(cnt + Cfg::IN_READY);
+      const int c_mail = ld_cnt(cnt + Cfg::MAIL_READY + (k < 8 ? k : 0));
+      const int c_dr = ld_cnt(cnt + Cfg::DRAINED + (k < 8 ? k : 0));
+      asm volatile("" ::: "memory");
+      double En2[NL], Nn2[NL], bn2[NL], wm2[NL];
+      {
+        const double *pe = in_l + (size_t)(jn & in_mask) * DROW + 1;
+        const double *pn = in_l + (size_t)((jn + 1) & in_mask) * DROW;
+        const double *pb = res_l + (size_t)(jn & (RIN - 1)) * RROW;
+        const double *pw = ring + (size_t)(jn & (R2 - 1)) * DROW;
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+          En2[l] = ((volatile const double *)pe)[l * S];
+          Nn2[l] = ((volatile const double *)pn)[l * S];
+          bn2[l] = ((volatile const double *)pb)[l * RC];
+          wm2[l] = ((volatile const double *)pw)[l * S];
+        }
+      }
+      const int need_in = (jn >= -1 && jn < n) ? min(jn + 1, n - 1) + 1 : 0;
+      bool ok = (c_in >= need_in);
+      if (mb_reader && nrow_ok) ok = ok && (c_mail > jn);
+      if (drained_by_h && nrow_ok) ok = ok && (c_dr > jn - R2);
+      /* ---- (C) Thomas recurrence */
+#pragma unroll
+      for (int l = 1; l < NL; l++) rhs[l] -= div_by(C.t0[l] * rhs[l - 1], C.t1p[l - 1], C.rinv[l - 1]);
+      out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
+#pragma unroll
+      for (int l = NL - 2; l >= 0; l--) out[l] = div_by(rhs[l] - C.t2[l] * out[l + 1], C.t1p[l], C.rinv[l]);
+      /* ---- (D) results: last sweep -> ring for H; east column -> right neighbour's mailbox */
+      if (row_ok && k < nsw) {
+        double *po = ring + (size_t)(j & (R2 - 1)) * DROW + c + 1;
+#pragma unroll
+        for (int l = 0; l < NL; l++) po[l * S] = out[l];
+      }
+      if (row_ok && mb_writer) {
+#pragma unroll
+        for (int l = 0; l < NLP; l += 2) {
+          const unsigned long long v0 = (unsigned long long)__double_as_longlong(out[l]);
+          const unsigned long long v1 = (l + 1 < NL) ? (unsigned long long)__double_as_longlong(out[l + 1]) : 0ull;
+          asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(mo + l), "l"(v0), "l"(v1) : "memory");
+        }
+      }
+      __syncwarp();
+      if (lane == 0) cnt[Cfg::C_DONE] = tau + 1;
+      /* ---- (E) was the speculation of (B) valid? */
+      if (!__all_sync(FULLMASK, ok)) {
+        if (tau == 0 && wait_first && ++waited < SPIN_LIMIT) {
+          /* first mailbox row not here yet: stay hot by repeating the priming pair tau = -1, 0 */
+          if (__all_sync(FULLMASK, c_in >= need_in)) { tau = -1; mo -= NLP; continue; }
+        }
+        int spins = 0;
+        while (!__all_sync(FULLMASK, ok)) {
+          if (++spins > SPIN_LIMIT) { if (lane == 0) *A.err = 1; break; }
+          ok = (ld_cnt(cnt + Cfg::IN_READY) >= need_in);
+          if (mb_reader && nrow_ok) ok = ok && (ld_cnt(cnt + Cfg::MAIL_READY + k) > jn);
+          if (drained_by_h && nrow_ok) ok = ok && (ld_cnt(cnt + Cfg::DRAINED + k) > jn - R2);
+        }
+        n_spins += spins;
+        __syncwarp();
+        const double *pe = in_l + (size_t)(jn & in_mask) * DROW + 1;
+        const double *pn = in_l + (size_t)((jn + 1) & in_mask) * DROW;
+        const double *pb = res_l + (size_t)(jn & (RIN - 1)) * RROW;
+        const double *pw = ring + (size_t)(jn & (R2 - 1)) * DROW;
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+          En2[l] = ((volatile const double *)pe)[l * S];
+          Nn2[l] = ((volatile const double *)pn)[l * S];
+          bn2[l] = ((volatile const double *)pb)[l * RC];
+          wm2[l] = ((volatile const double *)pw)[l * S];
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < NL; l++) { cur[l] = out[l]; cold[l] = Nn[l]; En[l] = En2[l]; Nn[l] = Nn2[l]; bn[l] = bn2[l]; wm[l] = wm2[l]; }
+      tau++;
+      mo += NLP;
+    }
+    if (A.dbg) {
+      long long t_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      if (lane == 0) { A.dbg[w * 4 + 0] = t_start; A.dbg[w * 4 + 1] = t_end; A.dbg[w * 4 + 2] = n_spins; }
+    }
+  } else {
+    /* ================================================================ helper warp */
+    /* streaming: element e of a ring row <-> (layer, column) */
+    const double *ld_d[Cfg::EPL_D];
+    const double *ld_r[Cfg::EPL_R];
+    unsigned st_d[Cfg::EPL_D], st_r[Cfg::EPL_R];
+    bool ok_d[Cfg::EPL_D], ok_r[Cfg::EPL_R];
+#pragma unroll
+    for (int q = 0; q < Cfg::EPL_D; q++) {
+      const int e = lane + 32 * q, l = e / S, x = w * W + e % S;
+      ok_d[q] = (e < DROW) && (x < n);
+      ld_d[q] = A.da + (size_t)(ok_d[q] ? l : 0) * plane + GIDX(pitch, 0, ok_d[q] ? x : 0);
+      st_d[q] = (unsigned)__cvta_generic_to_shared(IN + e);
+    }
+#pragma unroll
+    for (int q = 0; q < Cfg::EPL_R; q++) {
+      const int e = lane + 32 * q, l = e / RC, x = w * W - (K - 1) + e % RC;
+      ok_r[q] = (e < RROW) && (x >= 0) && (x < n);
+      ld_r[q] = A.res + (size_t)(ok_r[q] ? l : 0) * plane + GIDX(pitch, 0, ok_r[q] ? x : 0);
+      st_r[q] = (unsigned)__cvta_generic_to_shared(RES + e);
+    }
+    constexpr int PF = 48;
+    /* mailbox lanes: (kk, q) */
+    const int kk = lane / Q, q = lane % Q;
+    const bool rd_valid = (w > 0) && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < n;
+    const bool wr_valid = has_consumer && kk < nsw && (w * W + W - 1 - kk) >= 0 && (w * W + W - 1 - kk) < n;
+    const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)n * NLP;
+    double *ringk = XR + (size_t)kk * R2 * DROW;
+    const unsigned gmask = (Q == 32) ? 0xffffffffu : (((1u << Q) - 1u) << (kk * Q));
+    int mail_rd = rd_valid ? 0 : n;   /* rows deposited for sweep kk */
+    int da_dr = 0;                    /* rows of the last sweep written to HBM */
+    int in_issued = 0, h1 = 0, h2 = 0, h3 = 0, in_done = 0; /* streaming: rows issued now / 1,2,3 iterations ago */
+    constexpr int EPL_O = (NL * W + 31) / 32;
+    (void)wr_valid;
+    int idle = 0;
+#pragma unroll 1
+    for (long long it = 0;; it++) {
+      const int cd = ld_cnt(cnt + Cfg::C_DONE);
+      bool progress = false;
+      /* ---- (1) mailbox in: Q rows of each sweep per iteration (the latency-critical hand-off) */
+      {
+        const int r = mail_rd + q;
+        const bool can = rd_valid && r < n && (cd >= r - R2 + 2 * kk + 2);
+        unsigned long long v[NLP];
+#pragma unroll
+        for (int l = 0; l < NLP; l++) v[l] = MAIL_EMPTY;
+        if (can) {
+          const unsigned long long *p = mb_in + (size_t)r * NLP;
+#pragma unroll
+          for (int l = 0; l < NLP; l += 2)
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[l]), "=l"(v[l + 1]) : "l"(p + l));
+        }
+        /* ---- (2) meanwhile: stream up to 2 rows; rows issued three iterations ago have landed */
+        {
+          const int rmax = min(n - 1, cd + RIN - Cfg::TAIL - 1);
+          const int b1 = min(in_issued + 2, rmax + 1);
+          for (int r2 = in_issued; r2 < b1; r2++) {
+            const unsigned ro = (unsigned)(r2 & (RIN - 1));
+            const size_t go = (size_t)r2 * pitch;
+#pragma unroll
+            for (int u = 0; u < Cfg::EPL_D; u++)
+              if (ok_d[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_d[u] + ro * (DROW * 8)), "l"(ld_d[u] + go));
+#pragma unroll
+            for (int u = 0; u < Cfg::EPL_R; u++)
+              if (ok_r[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_r[u] + ro * (RROW * 8)), "l"(ld_r[u] + go));
+            const int rp = r2 + PF;
+            if (rp < n) {
+              const size_t gp = (size_t)rp * pitch;
+#pragma unroll
+              for (int u = 0; u < Cfg::EPL_D; u++)
+                if (ok_d[u]) asm volatile("prefetch.global.L2 [%0];" ::"l"(ld_d[u] + gp));
+#pragma unroll
+              for (int u = 0; u < Cfg::EPL_R; u++)
+                if (ok_r[u]) asm volatile("prefetch.global.L2 [%0];" ::"l"(ld_r[u] + gp));
+            }
+          }
+          cp_async_commit();
+          if (b1 > in_issued) progress = true;
+          cp_async_wait<3>(); /* all but the three newest batches have landed: rows < h3 */
+          h3 = h2; h2 = h1; h1 = in_issued; in_issued = b1;
+        }
+        /* ---- (3) last sweep's rows -> HBM, up to 2 rows */
+        {
+          const double *ringf = XR + (size_t)kf * R2 * DROW;
+          int done = 0;
+          for (; done < 2; done++) {
+            const int r3 = da_dr + done;
+            if (!(r3 < n && cd >= r3 + W + 2 * kf + 1)) break;
+#pragma unroll
+            for (int u = 0; u < EPL_O; u++) {
+              const int e = lane + 32 * u, l = e / W, cs = e % W;
+              const int col = w * W + cs - kf;
+              if (e < NL * W && col >= 0 && col < n)
+                A.da[(size_t)l * plane + GIDX(pitch, r3, col)] = ((volatile const double *)ringf)[(size_t)(r3 & (R2 - 1)) * DROW + l * S + cs + 1];
+            }
+          }
+          da_dr += done;
+          if (done > 0) progress = true;
+        }
+        /* ---- back to the mailbox: deposit the leading valid rows of each sweep, re-arm them */
+        bool valid = can;
+#pragma unroll
+        for (int l = 0; l < NL; l++) valid = valid && (v[l] != MAIL_EMPTY);
+        const unsigned bal = (__ballot_sync(FULLMASK, valid) & gmask) >> (kk * Q);
+        const int adv = __ffs(~bal) - 1;
+        if (q < adv) {
+          double *d = ringk + (size_t)(r & (R2 - 1)) * DROW;
+#pragma unroll
+          for (int l = 0; l < NL; l++) d[l * S] = __longlong_as_double((long long)v[l]);
+          unsigned long long *p = (unsigned long long *)mb_in + (size_t)r * NLP;
+#pragma unroll
+          for (int l = 0; l < NLP; l += 2)
+            asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(p + l), "l"(MAIL_EMPTY), "l"(MAIL_EMPTY) : "memory");
+        }
+        mail_rd += adv;
+        if (adv > 0) progress = true;
+      }
+      /* ---- publish: mailbox rows, streamed rows, drained rows */
+      __syncwarp();
+      __threadfence_block();
+      if (q == 0 && kk < 8) {
+        cnt[Cfg::MAIL_READY + kk] = mail_rd;
+        cnt[Cfg::DRAINED + kk] = (kk == kf) ? da_dr : n;
+      }
+      if (h3 > in_done) { in_done = h3; progress = true; if (lane == 0) cnt[Cfg::IN_READY] = in_done; }
+      /* ---- done? */
+      const bool fin = (in_done >= n) && (mail_rd >= n) && (da_dr >= n);
+      if (__all_sync(FULLMASK, fin)) break;
+      if (in_issued >= n && in_done < n) progress = true; /* flushing the last batches */
+      if (!__any_sync(FULLMASK, progress)) {
+        if (++idle > SPIN_LIMIT) { if (lane == 0) *A.err = 2; break; }
+      } else idle = 0;
+    }
+    cp_async_wait<0>();
+  }
+}

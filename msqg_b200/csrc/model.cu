@@ -548,8 +548,64 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
   m->launches++;
   return MSQG_OK;
 }
+/* warp-specialised variant (k_relax_ws): two warps per strip */
+template <int NL, int K, int WPC>
+static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
+  using Cfg = WsCfg<NL, K>;
+  const Geom &g = m->g[lev];
+  const int nworkers = (g.n + K - 1 + Cfg::W - 1) / Cfg::W;
+  const size_t words = (size_t)nworkers * K * g.n * Cfg::NLP;
+  if (words > m->mailbox_words) {
+    const Geom &gf = m->g[m->depth];
+    const size_t nlp = (size_t)((m->nl + 1) & ~1);
+    const size_t wf = (size_t)((gf.n + 8 - 1 + 4 - 1) / 4) * 8 * gf.n * nlp;
+    const size_t w4 = (size_t)((gf.n + 4 - 1 + 8 - 1) / 8) * 4 * gf.n * nlp;
+    size_t need = K == 8 ? wf : w4;
+    if (words > need) need = words;
+    int rc = ensure_mailbox(m, need);
+    if (rc) return rc;
+    k_fill_u64<<<m->num_sms * 4, 256, 0, m->stream>>>(m->mailbox, m->mailbox_words, MAIL_EMPTY);
+    m->launches++;
+    CK(cudaGetLastError());
+  }
+  RelaxArgs A;
+  A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
+  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0;
+  const size_t smem = Cfg::smem_per_worker * WPC;
+  auto kern = k_relax_ws<NL, K, WPC>;
+  static bool attr_set = false;
+  static int max_blocks_per_sm = 0;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, 64 * WPC, smem));
+    attr_set = true;
+  }
+  const int grid = (nworkers + WPC - 1) / WPC;
+  if (grid > max_blocks_per_sm * m->num_sms)
+    FAIL(MSQG_ERR_ARG, "relax wavefront needs %d co-resident CTAs, device holds %d (N too large for nl=%d)", grid,
+         max_blocks_per_sm * m->num_sms, NL);
+  RelaxCoef<NL> Cc = C;
+  void *args[] = {(void *)&A, (void *)&Cc};
+  CK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(64 * WPC), args, smem, m->stream));
+  m->launches++;
+  return MSQG_OK;
+}
+template <int NL, int K>
+static int launch_relax_ws(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
+  constexpr size_t spw = WsCfg<NL, K>::smem_per_worker;
+  if constexpr (spw * 4 <= 220 * 1024) return launch_relax_ws_w<NL, K, 4>(m, da, res, lev, nsweeps, C);
+  else if constexpr (spw * 2 <= 220 * 1024) return launch_relax_ws_w<NL, K, 2>(m, da, res, lev, nsweeps, C);
+  else return launch_relax_ws_w<NL, K, 1>(m, da, res, lev, nsweeps, C);
+}
+static int relax_variant() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("MSQG_RELAX"); v = (e && !strcmp(e, "v3")) ? 0 : 1; }
+  return v;
+}
+
 template <int NL, int K>
 static int launch_relax_t(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
+  if (relax_variant() == 1) return launch_relax_ws<NL, K>(m, da, res, lev, nsweeps, C);
   /* warps per CTA limited by the per-warp shared-memory rings */
   constexpr size_t spw = RelaxCfg<NL, K>::smem_per_warp;
   if constexpr (spw * 4 <= 200 * 1024) return launch_relax_w<NL, K, 4>(m, da, res, lev, nsweeps, C);
