@@ -23,6 +23,11 @@ struct Geom {
   int pitch;    /* doubles per row */
   size_t plane; /* doubles per scalar = (n+2)*pitch */
   double Delta; /* L0/n */
+  /* divisors used by the stencils and their correctly rounded reciprocals (for div_by) */
+  double rD;          /* 1/Delta */
+  double D2, rD2;     /* sq(Delta) */
+  double D12, rD12;   /* 12.*Delta*Delta (jacobian macro) */
+  double D2x, rD2x;   /* 2*Delta (beta_effect macro) */
 };
 
 static inline int msqg_pitch(int n) { return ((n + MSQG_OX + 1 + 15) / 16) * 16; }

@@ -270,6 +270,10 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
     Geom &g = m->g[l];
     g.n = 1 << l; g.pitch = msqg_pitch(g.n); g.plane = (size_t)(g.n + 2) * g.pitch;
     g.Delta = p->L0 / g.n; /* == L0*(1./(1 << level)) [BASILISK], exact power-of-two scaling */
+    g.rD = 1. / g.Delta;
+    g.D2 = g.Delta * g.Delta; g.rD2 = 1. / g.D2;
+    g.D12 = 12. * g.Delta * g.Delta; g.rD12 = 1. / g.D12;
+    g.D2x = 2 * g.Delta; g.rD2x = 1. / g.D2x;
   }
   CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   m->own_stream = true;
