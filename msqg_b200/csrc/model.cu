@@ -85,7 +85,10 @@ struct msqg_model {
   /* state */
   double ts_previous;
   int corrector_step;
-  unsigned noise_seeded;
+  /* libc rand() stream of this model (random_r on a TYPE_3 state == srand(seed); rand()) so that
+     ensemble members in one process replay the sequence a one-member reference process would draw */
+  struct random_data rng;
+  char rng_state[128];
   std::vector<double> h_noise, h_sstoch;
   double umax_pg[MSQG_MAXL];
   msqg_mgstats mgpsi, mgmode[MSQG_MAXL];
@@ -306,7 +309,9 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   m->mailbox = nullptr; m->mailbox_words = 0; m->d_dbg = nullptr;
   for (int l = 0; l < nl; l++) m->dhf[l] = p->dh[l]; /* qg.h:895-896 */
   m->iRe = p->iRe; m->iRe4 = p->iRe4; m->Eks = p->Eks; m->Ekb = p->Ekb;
-  m->ts_previous = 0.; m->corrector_step = 0; m->noise_seeded = 0;
+  m->ts_previous = 0.; m->corrector_step = 0;
+  memset(&m->rng, 0, sizeof(m->rng));
+  initstate_r(1u, m->rng_state, sizeof(m->rng_state), &m->rng); /* C default: srand(1) */
   m->flag_topo = 0; m->has_qforc = 0; m->has_zp = 0; m->const_set = 0;
   m->total_cycles = 0; m->launches = 0; m->keep_dq = 0; m->prof_on = 0; m->prof_next = 0;
   memset(&m->mgpsi, 0, sizeof(m->mgpsi));
@@ -377,7 +382,10 @@ extern "C" long msqg_launch_count(msqg_model *m) { return m->launches; }
 extern "C" long msqg_total_cycles(msqg_model *m) { return m->total_cycles; }
 extern "C" double msqg_get_ts_previous(msqg_model *m) { return m->ts_previous; }
 extern "C" void msqg_set_ts_previous(msqg_model *m, double v) { m->ts_previous = v; }
-extern "C" void msqg_seed_noise(msqg_model *m, unsigned seed) { srand(seed); m->noise_seeded = 1; }
+extern "C" void msqg_seed_noise(msqg_model *m, unsigned seed) {
+  memset(&m->rng, 0, sizeof(m->rng));
+  initstate_r(seed, m->rng_state, sizeof(m->rng_state), &m->rng);
+}
 extern "C" int msqg_set_flag_topo(msqg_model *m, int flag) { m->flag_topo = flag; return MSQG_OK; }
 extern "C" int msqg_set_keep_dq(msqg_model *m, int keep) { m->keep_dq = keep; return MSQG_OK; }
 extern "C" int msqg_set_dissipation(msqg_model *m, double iRe, double iRe4, double Eks, double Ekb) {
@@ -1127,8 +1135,12 @@ static int generate_noise(msqg_model *m) {
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++)
       for (int l = 0; l < nl; l++) {
-        const double gsn = sqrt(-2. * log(((double)(rand()) + 1.) / ((double)(RAND_MAX) + 2.))) *
-                           cos(2 * pi * rand() / (double)RAND_MAX);
+        /* normal_noise(): the two rand() calls in the order gcc evaluates the reference macro's operands */
+        int32_t r1, r2;
+        random_r(&m->rng, &r1);
+        random_r(&m->rng, &r2);
+        const double gsn = sqrt(-2. * log(((double)(r1) + 1.) / ((double)(RAND_MAX) + 2.))) *
+                           cos(2 * pi * r2 / (double)RAND_MAX);
         const size_t c = ((size_t)l * n + j) * n + i;
         m->h_noise[c] = m->p.amp_stoch * m->h_sstoch[c] * gsn;
       }

@@ -48,9 +48,9 @@ def test_stochastic_forcing(gpu, N, nl, nsteps):
     sig = np.full((nl, N, N), 1e-3)
     mo.set(O.SSTOCH, sig); mg.set(G.SSTOCH, sig)
     mo.set_const(); mg.set_const()
-    libc.srand(1000)
+    libc.srand(1000)                      # the oracle draws from the process-wide rand() like the reference
     dto = [mo.step() for _ in range(nsteps)]
-    libc.srand(1000)
+    mg.L.msqg_seed_noise(mg.h, 1000)      # the GPU model owns a random_r state seeded like srand(1000)
     dtg = [mg.step() for _ in range(nsteps)]
     assert dtg == dto
     assert np.array_equal(mg.get(G.NSTOCH), mo.get(O.NSTOCH))
@@ -109,3 +109,33 @@ def test_full_size_properties(gpu, N, nl, modal):
     assert dt == pytest.approx(m.p.DT / 11, rel=1e-12)
     assert np.isfinite(m.get(G.Q)).all() and np.isfinite(m.get(G.PSI)).all()
     del rng
+
+
+def test_ensemble_members_concurrent(gpu):
+    """BASELINE config 5 in miniature: stochastic members batched on one GPU (own streams, own rand() replay)
+    give, member by member, the bits of the same member run alone and of the oracle."""
+    import time
+    from oracle import oracle as O
+    from msqg_b200 import capi as G
+    from msqg_b200.ensemble import Ensemble
+    N, nl, nmem, nsteps = 64, 3, 4, 3
+    kw = base_kw(N, nl, stochastic=1, tr_stoch=10., amp_stoch=1.)
+    sig = np.full((nl, N, N), 1e-3)
+    psi = synth_psi(N, nl)
+    ens = Ensemble(G.make_params(**kw), nmem, gpu)
+    ens.set(G.PSI, psi); ens.set(G.SSTOCH, sig); ens.set_const()
+    dts = ens.step(nsteps)
+    qs = ens.get(G.Q)
+    assert not np.array_equal(qs[0], qs[1])           # different seeds -> different members
+    for i in (0, nmem - 1):
+        solo = G.Model(G.make_params(**kw), gpu)
+        solo.L.msqg_seed_noise(solo.h, 1000 + i)
+        solo.set(G.PSI, psi); solo.set(G.SSTOCH, sig); solo.set_const()
+        assert [solo.step() for _ in range(nsteps)] == dts[i]
+        assert np.array_equal(solo.get(G.Q), qs[i])
+    mo = O.Model(O.make_params(**kw))
+    mo.set(O.PSI, psi); mo.set(O.SSTOCH, sig); mo.set_const()
+    libc.srand(1000 + 1)
+    assert [mo.step() for _ in range(nsteps)] == dts[1]
+    assert np.array_equal(mo.get(O.Q), qs[1])
+    ens.close()
