@@ -2,7 +2,7 @@
  * layout.cuh -- HBM data layout of the msqg layer fields.
  *
  * A "list" (the reference's `scalar *`, msqg/qg.h:23-59) on multigrid level L is
- *     double [nf][n+2][pitch]          n = 2^L, x fastest
+ *     double [nf][ny+2][pitch]         nx = ny = 2^L on one GPU, x fastest
  * with one ghost ring ([BASILISK] allocates two, msqg only ever reads one).
  * Interior cell (x=0,y=0) of a plane sits at element  pitch + OX, OX = 16, so
  * every interior row starts 128-byte aligned; pitch is a multiple of 16 doubles.
@@ -19,9 +19,11 @@
 #define MSQG_NLMAX 12 /* device kernels are instantiated for 1..12 layers */
 
 struct Geom {
-  int n;        /* cells per side */
+  int nx, ny;   /* cells of this tile in x and y (single GPU: nx == ny == 2^level) */
+  int bc;       /* bit mask of INTERNAL sides (1 left, 2 right, 4 bottom, 8 top): their ghosts come from a
+                   neighbouring tile by halo exchange; physical sides get the boundary condition */
   int pitch;    /* doubles per row */
-  size_t plane; /* doubles per scalar = (n+2)*pitch */
+  size_t plane; /* doubles per scalar = (ny+2)*pitch */
   double Delta; /* L0/n */
   /* divisors used by the stencils and their correctly rounded reciprocals (for div_by) */
   double rD;          /* 1/Delta */

@@ -68,39 +68,41 @@ __global__ void k_pack(double *__restrict__ dst, const double *__restrict__ src,
   const int x = blockIdx.x * blockDim.x + threadIdx.x - 1;
   const int y = blockIdx.y * blockDim.y + threadIdx.y - 1;
   const int f = blockIdx.z;
-  if (x > g.n || y > g.n) return;
+  if (x > g.nx || y > g.ny) return;
   int xs = x, ys = y;
   double s = 1.;
-  if (x < 0) { xs = 0; s *= sg; } else if (x >= g.n) { xs = g.n - 1; s *= sg; }
-  if (y < 0) { ys = 0; s *= sg; } else if (y >= g.n) { ys = g.n - 1; s *= sg; }
-  dst[(size_t)f * g.plane + GIDX(g.pitch, y, x)] = s * src[((size_t)f * g.n + ys) * g.n + xs];
+  if (x < 0) { xs = 0; s *= sg; } else if (x >= g.nx) { xs = g.nx - 1; s *= sg; }
+  if (y < 0) { ys = 0; s *= sg; } else if (y >= g.ny) { ys = g.ny - 1; s *= sg; }
+  dst[(size_t)f * g.plane + GIDX(g.pitch, y, x)] = s * src[((size_t)f * g.ny + ys) * g.nx + xs];
 }
 
 __global__ void k_unpack(double *__restrict__ dst, const double *__restrict__ src, int nf, Geom g) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
-  if (x >= g.n || y >= g.n) return;
-  dst[((size_t)f * g.n + y) * g.n + x] = src[(size_t)f * g.plane + GIDX(g.pitch, y, x)];
+  if (x >= g.nx || y >= g.ny) return;
+  dst[((size_t)f * g.ny + y) * g.nx + x] = src[(size_t)f * g.plane + GIDX(g.pitch, y, x)];
 }
 
-/* boundary_level on a padded list (ghost ring from interior) */
+/* boundary_level on a padded list: ghost ring from the interior on the PHYSICAL sides of the tile
+ * (sides in g.bc are internal: their ghosts belong to the halo exchange and are left alone).
+ * Corner ghosts next to an internal side are filled from that side's ghost column/row, which is how
+ * [BASILISK]'s x-then-y boundary sweeps build them; call after the halo exchange. */
 __global__ void k_ghosts(double *__restrict__ a, int nf, Geom g, double sg) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int f = blockIdx.y;
-  const int n = g.n;
-  if (t >= 4 * (n + 1)) return;
-  /* perimeter walk over the (n+2)^2 ring */
-  int x, y;
-  const int side = t / (n + 1), o = t % (n + 1);
-  if (side == 0) { x = -1 + o; y = -1; }
-  else if (side == 1) { x = n; y = -1 + o; }
-  else if (side == 2) { x = n - o; y = n; }
-  else { x = -1; y = n - o; }
+  const int x = blockIdx.x * blockDim.x + threadIdx.x - 1;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y - 1;
+  const int f = blockIdx.z;
+  if (x > g.nx || y > g.ny) return;
+  const bool gx = (x < 0 || x >= g.nx), gy = (y < 0 || y >= g.ny);
+  if (!gx && !gy) return;
+  const bool xin = (x < 0) ? (g.bc & 1) : (x >= g.nx ? (g.bc & 2) : 0);
+  const bool yin = (y < 0) ? (g.bc & 4) : (y >= g.ny ? (g.bc & 8) : 0);
+  if ((gx && xin && !gy) || (gy && yin && !gx)) return;       /* pure halo cell */
+  if (gx && gy && xin && yin) return;                          /* corner owned by the diagonal neighbour */
   int xs = x, ys = y;
   double s = 1.;
-  if (x < 0) { xs = 0; s *= sg; } else if (x >= n) { xs = n - 1; s *= sg; }
-  if (y < 0) { ys = 0; s *= sg; } else if (y >= n) { ys = n - 1; s *= sg; }
+  if (gx && !xin) { xs = x < 0 ? 0 : g.nx - 1; s *= sg; }
+  if (gy && !yin) { ys = y < 0 ? 0 : g.ny - 1; s *= sg; }
   double *p = a + (size_t)f * g.plane;
   p[GIDX(g.pitch, y, x)] = s * p[GIDX(g.pitch, ys, xs)];
 }
@@ -122,7 +124,7 @@ k_residual(const double *__restrict__ a, const double *__restrict__ b, double *_
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   double m = 0.;
-  if (x < g.n && y < g.n) {
+  if (x < g.nx && y < g.ny) {
     const size_t c = GIDX(g.pitch, y, x);
     const double D = g.Delta, rD = g.rD; /* x/Delta via div_by: same bits as the IEEE division, 6x fewer instructions */
     double ac[NL];
@@ -159,7 +161,7 @@ k_residual_scalar(const double *__restrict__ a, const double *__restrict__ b, do
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   double m = 0.;
-  if (x < g.n && y < g.n) {
+  if (x < g.nx && y < g.ny) {
     const size_t c = GIDX(g.pitch, y, x);
     const double D = g.Delta, rD = g.rD;
     const double ac = a[c];
@@ -181,7 +183,7 @@ __global__ void k_restrict(const double *__restrict__ fine, double *__restrict__
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
-  if (x >= gc.n || y >= gc.n) return;
+  if (x >= gc.nx || y >= gc.ny) return;
   const double *a = fine + (size_t)f * gf.plane;
   const size_t c00 = GIDX(gf.pitch, 2 * y, 2 * x);
   double sum = 0.;
@@ -193,16 +195,16 @@ __global__ void k_restrict(const double *__restrict__ fine, double *__restrict__
   double *cp = coarse + (size_t)f * gc.plane;
   cp[GIDX(gc.pitch, y, x)] = v;
   if (write_ghosts) {
-    const int n = gc.n;
-    const bool l = x == 0, r = x == n - 1, bo = y == 0, t = y == n - 1;
+    const int nx = gc.nx, ny = gc.ny;
+    const bool l = x == 0, r = x == nx - 1, bo = y == 0, t = y == ny - 1;
     if (l) cp[GIDX(gc.pitch, y, -1)] = sg * v;
-    if (r) cp[GIDX(gc.pitch, y, n)] = sg * v;
+    if (r) cp[GIDX(gc.pitch, y, nx)] = sg * v;
     if (bo) cp[GIDX(gc.pitch, -1, x)] = sg * v;
-    if (t) cp[GIDX(gc.pitch, n, x)] = sg * v;
+    if (t) cp[GIDX(gc.pitch, ny, x)] = sg * v;
     if (l && bo) cp[GIDX(gc.pitch, -1, -1)] = v;
-    if (l && t) cp[GIDX(gc.pitch, n, -1)] = v;
-    if (r && bo) cp[GIDX(gc.pitch, -1, n)] = v;
-    if (r && t) cp[GIDX(gc.pitch, n, n)] = v;
+    if (l && t) cp[GIDX(gc.pitch, ny, -1)] = v;
+    if (r && bo) cp[GIDX(gc.pitch, -1, nx)] = v;
+    if (r && t) cp[GIDX(gc.pitch, ny, nx)] = v;
   }
 }
 
@@ -212,8 +214,9 @@ __global__ void k_restrict(const double *__restrict__ fine, double *__restrict__
  * (ghost = -mirror, corner = +mirror), so da ghosts are never stored. */
 __device__ __forceinline__ double coarse_at(const double *__restrict__ c, const Geom &gc, int x, int y) {
   double s = 1.;
-  if (x < 0) { x = 0; s = -s; } else if (x >= gc.n) { x = gc.n - 1; s = -s; }
-  if (y < 0) { y = 0; s = -s; } else if (y >= gc.n) { y = gc.n - 1; s = -s; }
+  /* physical side: homogeneous-dirichlet ghost by reflection; internal side: stored halo value */
+  if (x < 0) { if (!(gc.bc & 1)) { x = 0; s = -s; } } else if (x >= gc.nx) { if (!(gc.bc & 2)) { x = gc.nx - 1; s = -s; } }
+  if (y < 0) { if (!(gc.bc & 4)) { y = 0; s = -s; } } else if (y >= gc.ny) { if (!(gc.bc & 8)) { y = gc.ny - 1; s = -s; } }
   return s * c[GIDX(gc.pitch, y, x)];
 }
 
@@ -221,7 +224,7 @@ __global__ void k_prolong(const double *__restrict__ coarse, double *__restrict_
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
-  if (x >= gf.n || y >= gf.n) return;
+  if (x >= gf.nx || y >= gf.ny) return;
   const double *c = coarse + (size_t)f * gc.plane;
   const int xc = x >> 1, yc = y >> 1;
   const int cx = (x & 1) ? 1 : -1, cy = (y & 1) ? 1 : -1;
@@ -238,21 +241,21 @@ __global__ void k_correct(double *__restrict__ a, const double *__restrict__ da,
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
-  if (x >= g.n || y >= g.n) return;
+  if (x >= g.nx || y >= g.ny) return;
   double *ap = a + (size_t)f * g.plane;
   const size_t c = GIDX(g.pitch, y, x);
   const double v = ap[c] + da[(size_t)f * g.plane + c];
   ap[c] = v;
-  const int n = g.n;
-  const bool l = x == 0, r = x == n - 1, bo = y == 0, t = y == n - 1;
+  const int nx = g.nx, ny = g.ny;
+  const bool l = x == 0, r = x == nx - 1, bo = y == 0, t = y == ny - 1;
   if (l) ap[GIDX(g.pitch, y, -1)] = -v;
-  if (r) ap[GIDX(g.pitch, y, n)] = -v;
+  if (r) ap[GIDX(g.pitch, y, nx)] = -v;
   if (bo) ap[GIDX(g.pitch, -1, x)] = -v;
-  if (t) ap[GIDX(g.pitch, n, x)] = -v;
+  if (t) ap[GIDX(g.pitch, ny, x)] = -v;
   if (l && bo) ap[GIDX(g.pitch, -1, -1)] = v;
-  if (l && t) ap[GIDX(g.pitch, n, -1)] = v;
-  if (r && bo) ap[GIDX(g.pitch, -1, n)] = v;
-  if (r && t) ap[GIDX(g.pitch, n, n)] = v;
+  if (l && t) ap[GIDX(g.pitch, ny, -1)] = v;
+  if (r && bo) ap[GIDX(g.pitch, -1, nx)] = v;
+  if (r && t) ap[GIDX(g.pitch, ny, nx)] = v;
 }
 
 /* ------------------------------------------------------------------ relax_layer
@@ -360,7 +363,7 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
   constexpr int NLP = Cfg::NLP, DROW = Cfg::DROW, RROW = Cfg::RROW;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = A.g.n;
+  const int n = A.g.nx; /* this variant handles square single-GPU levels only */
   const int w = blockIdx.x * WPC + warp;
   const int nworkers = (n + K - 1 + W - 1) / W;
   if (w >= nworkers) return;
@@ -626,7 +629,7 @@ struct WsCfg {
 
 __device__ __forceinline__ int ld_cnt(const volatile int *p) { return *p; }
 
-template <int NL, int K, int WPC>
+template <int NL, int K, int WPC, bool TILE>
 __global__ void __launch_bounds__(64 * WPC)
 k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   using Cfg = WsCfg<NL, K>;
@@ -636,9 +639,12 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool helper = warp >= WPC;
   const int wl = helper ? warp - WPC : warp; /* worker slot inside the CTA */
-  const int n = A.g.n;
+  const int nx = A.g.nx, ny = A.g.ny; /* columns / rows of this tile */
+  /* internal sides (multi-GPU tiles, single-sweep launches only): ghosts are stored halo values */
+  const bool lint = TILE && (A.g.bc & 1), rint = TILE && (A.g.bc & 2), bint = TILE && (A.g.bc & 4), tint = TILE && (A.g.bc & 8);
+  const int r_first = bint ? -1 : 0, r_last = tint ? ny : ny - 1; /* rows of the iterate that are streamed */
   const int w = blockIdx.x * WPC + wl;
-  const int nworkers = (n + K - 1 + W - 1) / W;
+  const int nworkers = (nx + K - 1 + W - 1) / W;
   double *base = smem + (size_t)wl * Cfg::DOUBLES;
   double *IN = base;                    /* [RIN][NL][S]  initial iterate, slot s <-> column w*W + s */
   double *RES = IN + RIN * DROW;        /* [RIN][NL][RC] rc <-> column w*W - (K-1) + rc */
@@ -646,7 +652,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   volatile int *cnt = (volatile int *)(XR + K * R2 * DROW);
   const int nsw = A.nsweeps;
   const int kf = nsw - 1;
-  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE) ? -2 : 0;
+  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE) ? -2 : (lane == Cfg::IN_READY ? r_first : 0);
   __syncthreads();
   if (w >= nworkers) return;
   const int pitch = A.g.pitch;
@@ -657,17 +663,17 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     /* ================================================================ compute warp */
     const int k = lane / W, c = lane % W;
     const int i = w * W + c - k;
-    const bool col_ok = (i >= 0 && i < n && k < nsw);
+    const bool col_ok = (i >= 0 && i < nx && k < nsw);
     const bool k0 = (k == 0);
-    const bool left = (i == 0), right = (i == n - 1);
-    const bool use_mail = (c == 0 && w > 0);
+    const bool left = (i == 0) && !lint, right = (i == nx - 1) && !rint;
+    const bool use_mail = (c == 0) && (w > 0 || lint);
     const bool use_mail_n = use_mail && k > 0;
     const int prodcol = w * W - 1 - k;
-    const bool mb_reader = use_mail && k < nsw && prodcol >= 0 && prodcol < n;
-    const bool wr_valid = has_consumer && (w * W + W - 1 - k) >= 0 && (w * W + W - 1 - k) < n;
+    const bool mb_reader = use_mail && k < nsw && (w > 0 ? (prodcol >= 0 && prodcol < nx) : (k == 0));
+    const bool wr_valid = has_consumer && (w * W + W - 1 - k) >= 0 && (w * W + W - 1 - k) < nx;
     const bool drained_by_h = col_ok && (k == kf);
     const bool mb_writer = wr_valid && c == W - 1 && col_ok;
-    unsigned long long *mo = A.mailbox + ((size_t)w * K + k) * (size_t)n * NLP + (long long)(-2 - c - 2 * k - 1) * NLP;
+    unsigned long long *mo = A.mailbox + ((size_t)w * K + k) * (size_t)ny * NLP + (long long)(-2 - c - 2 * k - 1) * NLP;
     /* inputs of sweep k: ring of sweep k-1 (sweep 0: the streamed initial iterate); slot c north, slot c+1 east */
     const double *in_l = (k0 ? IN : XR + (size_t)(k - 1) * R2 * DROW) + c;
     const int in_mask = k0 ? RIN - 1 : R2 - 1;
@@ -680,14 +686,14 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     for (int l = 0; l < NL; l++) { cur[l] = En[l] = Nn[l] = cold[l] = bn[l] = wm[l] = 0.; }
     long long t_start = 0, n_spins = 0;
     if (A.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-    const int T = n + W + 2 * K - 2;
+    const int T = ny + W + 2 * K - 2;
     int waited = 0;
 #pragma unroll 1
     for (int tau = -2; tau < T;) {
       const int j = tau - c - 2 * k - 1;
       const int jn = j + 1;
-      const bool row_ok = (unsigned)j < (unsigned)n;
-      const bool nrow_ok = (unsigned)jn < (unsigned)n;
+      const bool row_ok = (unsigned)j < (unsigned)ny;
+      const bool nrow_ok = (unsigned)jn < (unsigned)ny;
       __syncwarp();
       /* ---- (A) the only work ahead of the recurrence: west value and right-hand side */
       double rhs[NL], out[NL], Wv[NL];
@@ -700,15 +706,17 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         r += Nn[l] + cur[l];
         rhs[l] = r;
       }
-      const bool edge = col_ok && ((row_ok && (left || right)) || j == 0 || j == n - 1);
+      const bool edge = col_ok && ((row_ok && (left || right)) || j == 0 || j == ny - 1);
       if (__any_sync(FULLMASK, edge) || tau == -2) {
 #pragma unroll
         for (int l = 0; l < NL; l++) {
           const double g = -cold[l];
           const double aw = left ? g : Wv[l];
           const double ae = right ? g : En[l];
-          const double as = (j == 0) ? g : cur[l];
-          const double an = (j == n - 1) ? g : Nn[l];
+          /* bottom/top: physical -> -(pre-sweep centre); internal -> stored halo row -1 / ny of the iterate */
+          const double sgh = ((volatile const double *)in_l)[(size_t)((-1) & in_mask) * DROW + l * S];
+          const double as = (j == 0) ? (bint ? sgh : g) : cur[l];
+          const double an = (j == ny - 1 && !tint) ? g : Nn[l];
           double r = C.msd2 * bn[l];
           r += ae + aw;
           r += an + as;
@@ -735,7 +743,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           wm2[l] = ((volatile const double *)pw)[l * S];
         }
       }
-      const int need_in = (jn >= -1 && jn < n) ? min(jn + 1, n - 1) + 1 : 0;
+      const int need_in = (jn >= -1 && jn < ny) ? min(jn + 1, r_last) + 1 : r_first;
       bool ok = (c_in >= need_in);
       if (mb_reader && nrow_ok) ok = ok && (c_mail > jn);
       if (drained_by_h && nrow_ok) ok = ok && (c_dr > jn - R2);
@@ -808,28 +816,29 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
 #pragma unroll
     for (int q = 0; q < Cfg::EPL_D; q++) {
       const int e = lane + 32 * q, l = e / S, x = w * W + e % S;
-      ok_d[q] = (e < DROW) && (x < n);
+      ok_d[q] = (e < DROW) && (x < nx || (x == nx && rint));
       ld_d[q] = A.da + (size_t)(ok_d[q] ? l : 0) * plane + GIDX(pitch, 0, ok_d[q] ? x : 0);
       st_d[q] = (unsigned)__cvta_generic_to_shared(IN + e);
     }
 #pragma unroll
     for (int q = 0; q < Cfg::EPL_R; q++) {
       const int e = lane + 32 * q, l = e / RC, x = w * W - (K - 1) + e % RC;
-      ok_r[q] = (e < RROW) && (x >= 0) && (x < n);
+      ok_r[q] = (e < RROW) && (x >= 0) && (x < nx);
       ld_r[q] = A.res + (size_t)(ok_r[q] ? l : 0) * plane + GIDX(pitch, 0, ok_r[q] ? x : 0);
       st_r[q] = (unsigned)__cvta_generic_to_shared(RES + e);
     }
     constexpr int PF = 48;
     /* mailbox lanes: (kk, q) */
     const int kk = lane / Q, q = lane % Q;
-    const bool rd_valid = (w > 0) && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < n;
-    const bool wr_valid = has_consumer && kk < nsw && (w * W + W - 1 - kk) >= 0 && (w * W + W - 1 - kk) < n;
-    const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)n * NLP;
+    const bool rd_ghost = (w == 0) && lint && kk == 0; /* west column = stored halo column -1 of the iterate */
+    const bool rd_valid = rd_ghost || ((w > 0) && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
+    const bool wr_valid = has_consumer && kk < nsw && (w * W + W - 1 - kk) >= 0 && (w * W + W - 1 - kk) < nx;
+    const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)ny * NLP;
     double *ringk = XR + (size_t)kk * R2 * DROW;
     const unsigned gmask = (Q == 32) ? 0xffffffffu : (((1u << Q) - 1u) << (kk * Q));
-    int mail_rd = rd_valid ? 0 : n;   /* rows deposited for sweep kk */
+    int mail_rd = rd_valid ? 0 : ny;  /* rows deposited for sweep kk */
     int da_dr = 0;                    /* rows of the last sweep written to HBM */
-    int in_issued = 0, h1 = 0, h2 = 0, h3 = 0, in_done = 0; /* streaming: rows issued now / 1,2,3 iterations ago */
+    int in_issued = r_first, h1 = r_first, h2 = r_first, h3 = r_first, in_done = r_first; /* rows issued now / 1,2,3 iterations ago */
     constexpr int EPL_O = (NL * W + 31) / 32;
     (void)wr_valid;
     int idle = 0;
@@ -840,19 +849,23 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       /* ---- (1) mailbox in: Q rows of each sweep per iteration (the latency-critical hand-off) */
       {
         const int r = mail_rd + q;
-        const bool can = rd_valid && r < n && (cd >= r - R2 + 2 * kk + 2);
+        const bool can = rd_valid && r < ny && (cd >= r - R2 + 2 * kk + 2);
         unsigned long long v[NLP];
 #pragma unroll
         for (int l = 0; l < NLP; l++) v[l] = MAIL_EMPTY;
-        if (can) {
+        if (can && !rd_ghost) {
           const unsigned long long *p = mb_in + (size_t)r * NLP;
 #pragma unroll
           for (int l = 0; l < NLP; l += 2)
             asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[l]), "=l"(v[l + 1]) : "l"(p + l));
         }
+        if (can && rd_ghost) {
+#pragma unroll
+          for (int l = 0; l < NL; l++) v[l] = (unsigned long long)__double_as_longlong(A.da[(size_t)l * plane + GIDX(pitch, r, -1)]);
+        }
         /* ---- (2) meanwhile: stream up to 2 rows; rows issued three iterations ago have landed */
         {
-          const int rmax = min(n - 1, cd + RIN - Cfg::TAIL - 1);
+          const int rmax = min(r_last, cd + RIN - Cfg::TAIL - 1);
           const int b1 = min(in_issued + 2, rmax + 1);
           for (int r2 = in_issued; r2 < b1; r2++) {
             const unsigned ro = (unsigned)(r2 & (RIN - 1));
@@ -864,7 +877,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
             for (int u = 0; u < Cfg::EPL_R; u++)
               if (ok_r[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_r[u] + ro * (RROW * 8)), "l"(ld_r[u] + go));
             const int rp = r2 + PF;
-            if (rp < n) {
+            if (rp < ny) {
               const size_t gp = (size_t)rp * pitch;
 #pragma unroll
               for (int u = 0; u < Cfg::EPL_D; u++)
@@ -885,12 +898,12 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           int done = 0;
           for (; done < 2; done++) {
             const int r3 = da_dr + done;
-            if (!(r3 < n && cd >= r3 + W + 2 * kf + 1)) break;
+            if (!(r3 < ny && cd >= r3 + W + 2 * kf + 1)) break;
 #pragma unroll
             for (int u = 0; u < EPL_O; u++) {
               const int e = lane + 32 * u, l = e / W, cs = e % W;
               const int col = w * W + cs - kf;
-              if (e < NL * W && col >= 0 && col < n)
+              if (e < NL * W && col >= 0 && col < nx)
                 A.da[(size_t)l * plane + GIDX(pitch, r3, col)] = ((volatile const double *)ringf)[(size_t)(r3 & (R2 - 1)) * DROW + l * S + cs + 1];
             }
           }
@@ -908,9 +921,11 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
 #pragma unroll
           for (int l = 0; l < NL; l++) d[l * S] = __longlong_as_double((long long)v[l]);
           unsigned long long *p = (unsigned long long *)mb_in + (size_t)r * NLP;
+          if (!rd_ghost) {
 #pragma unroll
-          for (int l = 0; l < NLP; l += 2)
-            asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(p + l), "l"(MAIL_EMPTY), "l"(MAIL_EMPTY) : "memory");
+            for (int l = 0; l < NLP; l += 2)
+              asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(p + l), "l"(MAIL_EMPTY), "l"(MAIL_EMPTY) : "memory");
+          }
         }
         mail_rd += adv;
         if (adv > 0) progress = true;
@@ -920,13 +935,13 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       __threadfence_block();
       if (q == 0 && kk < 8) {
         cnt[Cfg::MAIL_READY + kk] = mail_rd;
-        cnt[Cfg::DRAINED + kk] = (kk == kf) ? da_dr : n;
+        cnt[Cfg::DRAINED + kk] = (kk == kf) ? da_dr : ny;
       }
       if (h3 > in_done) { in_done = h3; progress = true; if (lane == 0) cnt[Cfg::IN_READY] = in_done; }
       /* ---- done? */
-      const bool fin = (in_done >= n) && (mail_rd >= n) && (da_dr >= n);
+      const bool fin = (in_done > r_last) && (mail_rd >= ny) && (da_dr >= ny);
       if (__all_sync(FULLMASK, fin)) break;
-      if (in_issued >= n && in_done < n) progress = true; /* flushing the last batches */
+      if (in_issued > r_last && in_done <= r_last) progress = true; /* flushing the last batches */
       if (!__any_sync(FULLMASK, progress)) {
         if (++idle > SPIN_LIMIT) { if (lane == 0) *A.err = 2; break; }
       } else idle = 0;

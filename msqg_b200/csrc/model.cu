@@ -225,11 +225,11 @@ static dim3 grid2(int nx, int ny, dim3 b, int nz = 1) { return dim3((nx + b.x - 
 
 static int pack_to(msqg_model *m, List &L, const double *host) {
   const Geom &g = m->g[m->depth];
-  size_t cnt = (size_t)L.nf * g.n * g.n;
+  size_t cnt = (size_t)L.nf * g.nx * g.ny;
   if (cnt > m->stage_doubles) FAIL(MSQG_ERR_ARG, "staging buffer too small");
   CK(cudaMemcpyAsync(m->d_stage, host, cnt * sizeof(double), cudaMemcpyHostToDevice, m->stream));
   dim3 b(32, 8);
-  k_pack<<<grid2(g.n + 2, g.n + 2, b, L.nf), b, 0, m->stream>>>(L.lev[m->depth], m->d_stage, L.nf, g, L.sg);
+  k_pack<<<grid2(g.nx + 2, g.ny + 2, b, L.nf), b, 0, m->stream>>>(L.lev[m->depth], m->d_stage, L.nf, g, L.sg);
   m->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->stream)); /* host buffer is borrowed for the call only */
@@ -237,10 +237,10 @@ static int pack_to(msqg_model *m, List &L, const double *host) {
 }
 static int unpack_from(msqg_model *m, List &L, double *host) {
   const Geom &g = m->g[m->depth];
-  size_t cnt = (size_t)L.nf * g.n * g.n;
+  size_t cnt = (size_t)L.nf * g.nx * g.ny;
   if (cnt > m->stage_doubles) FAIL(MSQG_ERR_ARG, "staging buffer too small");
   dim3 b(32, 8);
-  k_unpack<<<grid2(g.n, g.n, b, L.nf), b, 0, m->stream>>>(m->d_stage, L.lev[m->depth], L.nf, g);
+  k_unpack<<<grid2(g.nx, g.ny, b, L.nf), b, 0, m->stream>>>(m->d_stage, L.lev[m->depth], L.nf, g);
   m->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(host, m->d_stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -271,8 +271,8 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   m->depth = depth;
   for (int l = 0; l <= depth; l++) {
     Geom &g = m->g[l];
-    g.n = 1 << l; g.pitch = msqg_pitch(g.n); g.plane = (size_t)(g.n + 2) * g.pitch;
-    g.Delta = p->L0 / g.n; /* == L0*(1./(1 << level)) [BASILISK], exact power-of-two scaling */
+    g.nx = g.ny = 1 << l; g.bc = 0; g.pitch = msqg_pitch(g.nx); g.plane = (size_t)(g.ny + 2) * g.pitch;
+    g.Delta = p->L0 / (1 << l); /* == L0*(1./(1 << level)) [BASILISK], exact power-of-two scaling */
     g.rD = 1. / g.Delta;
     g.D2 = g.Delta * g.Delta; g.rD2 = 1. / g.D2;
     g.D12 = 12. * g.Delta * g.Delta; g.rD12 = 1. / g.D12;
@@ -418,7 +418,7 @@ extern "C" int msqg_reset_field(msqg_model *m, int id) {
   const Geom &g = m->g[m->depth];
   for (int f = 0; f < L->nf; f++)
     CK(cudaMemset2DAsync(L->lev[m->depth] + (size_t)f * g.plane + GIDX(g.pitch, 0, 0), (size_t)g.pitch * sizeof(double), 0,
-                         (size_t)g.n * sizeof(double), g.n, m->stream));
+                         (size_t)g.nx * sizeof(double), g.ny, m->stream));
   return MSQG_OK;
 }
 extern "C" int msqg_last_mgstats(msqg_model *m, int mode, msqg_mgstats *out) {
@@ -520,14 +520,14 @@ template <int NL, int K, int WPC>
 static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   using Cfg = RelaxCfg<NL, K>;
   const Geom &g = m->g[lev];
-  const int nworkers = (g.n + K - 1 + Cfg::W - 1) / Cfg::W;
-  const size_t words = (size_t)nworkers * K * g.n * Cfg::NLP;
+  const int nworkers = (g.nx + K - 1 + Cfg::W - 1) / Cfg::W;
+  const size_t words = (size_t)nworkers * K * g.ny * Cfg::NLP;
   if (words > m->mailbox_words) {
     /* size the mailbox for the finest level (K = 8 layout is the larger one) */
     const Geom &gf = m->g[m->depth];
     const size_t nlp = (size_t)((m->nl + 1) & ~1);
-    const size_t wf = (size_t)((gf.n + 8 - 1 + 4 - 1) / 4) * 8 * gf.n * nlp;
-    const size_t w4 = (size_t)((gf.n + 4 - 1 + 8 - 1) / 8) * 4 * gf.n * nlp;
+    const size_t wf = (size_t)((gf.nx + 8 - 1 + 4 - 1) / 4) * 8 * gf.ny * nlp;
+    const size_t w4 = (size_t)((gf.nx + 4 - 1 + 8 - 1) / 8) * 4 * gf.ny * nlp;
     size_t need = K == 8 ? wf : w4;
     if (words > need) need = words;
     int rc = ensure_mailbox(m, need);
@@ -565,13 +565,13 @@ template <int NL, int K, int WPC>
 static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   using Cfg = WsCfg<NL, K>;
   const Geom &g = m->g[lev];
-  const int nworkers = (g.n + K - 1 + Cfg::W - 1) / Cfg::W;
-  const size_t words = (size_t)nworkers * K * g.n * Cfg::NLP;
+  const int nworkers = (g.nx + K - 1 + Cfg::W - 1) / Cfg::W;
+  const size_t words = (size_t)nworkers * K * g.ny * Cfg::NLP;
   if (words > m->mailbox_words) {
     const Geom &gf = m->g[m->depth];
     const size_t nlp = (size_t)((m->nl + 1) & ~1);
-    const size_t wf = (size_t)((gf.n + 8 - 1 + 4 - 1) / 4) * 8 * gf.n * nlp;
-    const size_t w4 = (size_t)((gf.n + 4 - 1 + 8 - 1) / 8) * 4 * gf.n * nlp;
+    const size_t wf = (size_t)((gf.nx + 8 - 1 + 4 - 1) / 4) * 8 * gf.ny * nlp;
+    const size_t w4 = (size_t)((gf.nx + 4 - 1 + 8 - 1) / 8) * 4 * gf.ny * nlp;
     size_t need = K == 8 ? wf : w4;
     if (words > need) need = words;
     int rc = ensure_mailbox(m, need);
@@ -584,14 +584,16 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
   A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0;
   const size_t smem = Cfg::smem_per_worker * WPC;
-  auto kern = k_relax_ws<NL, K, WPC>;
-  static bool attr_set = false;
-  static int max_blocks_per_sm = 0;
-  if (!attr_set) {
+  const int tv = g.bc ? 1 : 0;
+  auto kern = tv ? k_relax_ws<NL, K, WPC, true> : k_relax_ws<NL, K, WPC, false>;
+  static bool attr_set[2] = {false, false};
+  static int max_blocks[2] = {0, 0};
+  if (!attr_set[tv]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, 64 * WPC, smem));
-    attr_set = true;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks[tv], kern, 64 * WPC, smem));
+    attr_set[tv] = true;
   }
+  const int max_blocks_per_sm = max_blocks[tv];
   const int grid = (nworkers + WPC - 1) / WPC;
   if (grid > max_blocks_per_sm * m->num_sms)
     FAIL(MSQG_ERR_ARG, "relax wavefront needs %d co-resident CTAs, device holds %d (N too large for nl=%d)", grid,
@@ -674,9 +676,9 @@ static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
   { ProfScope ps(m, PROF_RESIDUAL, 0);
   if (P.mode < 0) {
     LayerMetrics M = metrics_of(m);
-    NL_SWITCH(m->nl, k_residual<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->str.lev[D], g, M, m->d_scal));
+    NL_SWITCH(m->nl, k_residual<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->str.lev[D], g, M, m->d_scal));
   } else {
-    k_residual_scalar<<<grid2(g.n, g.n, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->ibu.lev[D] + (size_t)P.mode * g.plane, g, m->d_scal);
+    k_residual_scalar<<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(P.a, P.b, m->res.lev[D], m->ibu.lev[D] + (size_t)P.mode * g.plane, g, m->d_scal);
   }
   }
   m->launches++;
@@ -694,7 +696,7 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
   /* restriction(res): levels D-1..1 (level 0 is never read with minlevel = 1) */
   for (int l = D - 1; l >= 1; l--) {
     ProfScope ps(m, PROF_RESTRICT, l);
-    k_restrict<<<grid2(m->g[l].n, m->g[l].n, b, P.nf), b, 0, m->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
+    k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, P.nf), b, 0, m->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
     m->launches++;
   }
   CK(cudaGetLastError());
@@ -705,7 +707,7 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
       CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)P.nf * g.plane * sizeof(double), m->stream));
     } else {
       ProfScope ps(m, PROF_PROLONG, l);
-      k_prolong<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
+      k_prolong<<<grid2(g.nx, g.ny, b, P.nf), b, 0, m->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
       m->launches++;
       CK(cudaGetLastError());
     }
@@ -721,7 +723,7 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
   }
   const Geom &g = m->g[D];
   { ProfScope ps(m, PROF_CORRECT, 0);
-  k_correct<<<grid2(g.n, g.n, b, P.nf), b, 0, m->stream>>>(P.a, m->da.lev[D], g); }
+  k_correct<<<grid2(g.nx, g.ny, b, P.nf), b, 0, m->stream>>>(P.a, m->da.lev[D], g); }
   m->launches++;
   CK(cudaGetLastError());
   return MSQG_OK;
@@ -767,7 +769,7 @@ static int invertq_list(msqg_model *m, List &ql) {
     NL_SWITCH(m->nl, {
       ModeMat<NL> M;
       for (int k = 0; k < NL * NL; k++) M.a[k] = m->h_cl2m[k];
-      k_project<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(ql.lev[D], m->qm.lev[D], g, M, nullptr, 0);
+      k_project<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(ql.lev[D], m->qm.lev[D], g, M, nullptr, 0);
     });
     m->launches++;
     CK(cudaGetLastError());
@@ -779,7 +781,7 @@ static int invertq_list(msqg_model *m, List &ql) {
     NL_SWITCH(m->nl, {
       ModeMat<NL> M;
       for (int k = 0; k < NL * NL; k++) M.a[k] = m->h_cm2l[k];
-      k_project<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(m->pm.lev[D], m->psi.lev[D], g, M, nullptr, 1);
+      k_project<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(m->pm.lev[D], m->psi.lev[D], g, M, nullptr, 1);
     });
     m->launches++;
     CK(cudaGetLastError());
@@ -798,7 +800,7 @@ extern "C" int msqg_comp_q(msqg_model *m) {
   const Geom &g = m->g[m->depth];
   dim3 b(64, 4);
   LayerMetrics M = metrics_of(m);
-  NL_SWITCH(m->nl, k_comp_q<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(m->psi.lev[m->depth], m->str.lev[m->depth], m->q.lev[m->depth], g, M));
+  NL_SWITCH(m->nl, k_comp_q<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(m->psi.lev[m->depth], m->str.lev[m->depth], m->q.lev[m->depth], g, M));
   m->launches++;
   CK(cudaGetLastError());
   return MSQG_OK;
@@ -905,7 +907,7 @@ static int max_face_speed(msqg_model *m, List &L, double *umax_host) {
   CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
   dim3 b(64, 4);
   /* out-of-place laplacian into tmp is a by-product; only umax is wanted */
-  k_lap<<<grid2(g.n + 1, g.n + 1, b, m->nl), b, 0, m->stream>>>(L.lev[D], m->tmp.lev[D], g, m->d_scal + 1);
+  k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, m->stream>>>(L.lev[D], m->tmp.lev[D], g, m->d_scal + 1);
   m->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(m->h_scal + 1, m->d_scal + 1, m->nl * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -963,7 +965,7 @@ extern "C" int msqg_set_const(msqg_model *m) {
   {
     dim3 b(32, 8);
     for (int l = D - 1; l >= 1; l--) {
-      k_restrict<<<grid2(m->g[l].n, m->g[l].n, b, nl), b, 0, m->stream>>>(m->str.lev[l + 1], m->str.lev[l], m->g[l + 1], m->g[l], 1., 1);
+      k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, m->stream>>>(m->str.lev[l + 1], m->str.lev[l], m->g[l + 1], m->g[l], 1., 1);
       m->launches++;
     }
     CK(cudaGetLastError());
@@ -1030,7 +1032,7 @@ extern "C" int msqg_set_const(msqg_model *m) {
     if ((rc = max_face_speed(m, m->psipg, m->umax_pg))) return rc;
     if (m->p.flsrv == 1) {
       dim3 b(64, 4);
-      k_lap<<<grid2(g.n + 1, g.n + 1, b, nl), b, 0, m->stream>>>(m->psipg.lev[D], m->zetap.lev[D], g, nullptr);
+      k_lap<<<grid2(g.nx + 1, g.ny + 1, b, nl), b, 0, m->stream>>>(m->psipg.lev[D], m->zetap.lev[D], g, nullptr);
       m->launches++;
       CK(cudaGetLastError());
       m->has_zp = 1;
@@ -1063,10 +1065,10 @@ static int rhs_prepare(msqg_model *m) {
   dim3 b(64, 4);
   CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
   ProfScope ps(m, PROF_LAP, 0);
-  k_lap<<<grid2(g.n + 1, g.n + 1, b, m->nl), b, 0, m->stream>>>(m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
+  k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, m->stream>>>(m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
   m->launches++;
   if (m->iRe != 0. || m->iRe4 != 0.) {
-    k_lap<<<grid2(g.n + 1, g.n + 1, b, m->nl), b, 0, m->stream>>>(m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+    k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, m->stream>>>(m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
     m->launches++;
   }
   CK(cudaGetLastError());
@@ -1105,7 +1107,7 @@ static int rhs_launch(msqg_model *m, List &q_ev, const double *q_in, double *q_o
   A.flag_topo = m->flag_topo; A.stochastic = m->p.stochastic;
   dim3 b(32, 4);
   ProfScope ps(m, PROF_RHS, 0);
-  NL_SWITCH(nl, k_rhs<NL><<<grid2(g.n, g.n, b), b, 0, m->stream>>>(A));
+  NL_SWITCH(nl, k_rhs<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(A));
   m->launches++;
   CK(cudaGetLastError());
   return MSQG_OK;
@@ -1166,7 +1168,7 @@ extern "C" int msqg_advance(msqg_model *m, int out_id, int in_id, double dt) {
     noise = m->nstoch.lev[m->depth];
   }
   dim3 b(64, 4);
-  k_advance<<<grid2(g.n, g.n, b, m->nl), b, 0, m->stream>>>(O->lev[m->depth], I->lev[m->depth], m->dq.lev[m->depth], noise, g, dt, dts);
+  k_advance<<<grid2(g.nx, g.ny, b, m->nl), b, 0, m->stream>>>(O->lev[m->depth], I->lev[m->depth], m->dq.lev[m->depth], noise, g, dt, dts);
   m->launches++;
   CK(cudaGetLastError());
   return MSQG_OK;
@@ -1236,7 +1238,7 @@ extern "C" int msqg_ke1(msqg_model *m, double *ke) {
   CK(cudaSetDevice(m->device));
   const Geom &g = m->g[m->depth];
   dim3 b(16, 16);
-  dim3 gr = grid2(g.n, g.n, b);
+  dim3 gr = grid2(g.nx, g.ny, b);
   k_ke_partial<<<gr, b, 0, m->stream>>>(m->psi.lev[m->depth], g, m->d_kepart);
   m->launches++;
   CK(cudaGetLastError());
@@ -1270,20 +1272,20 @@ extern "C" int msqg_tendency_bfn(msqg_model *m, double direction) {
 /* ------------------------------------------------------------------ test hooks */
 static int upload_level(msqg_model *m, double *dst, const double *host, int nf, int lev, double sg) {
   const Geom &g = m->g[lev];
-  size_t cnt = (size_t)nf * g.n * g.n;
+  size_t cnt = (size_t)nf * g.nx * g.ny;
   if (cnt > m->stage_doubles) FAIL(MSQG_ERR_ARG, "staging buffer too small");
   CK(cudaMemcpyAsync(m->d_stage, host, cnt * sizeof(double), cudaMemcpyHostToDevice, m->stream));
   dim3 b(32, 8);
-  k_pack<<<grid2(g.n + 2, g.n + 2, b, nf), b, 0, m->stream>>>(dst, m->d_stage, nf, g, sg);
+  k_pack<<<grid2(g.nx + 2, g.ny + 2, b, nf), b, 0, m->stream>>>(dst, m->d_stage, nf, g, sg);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->stream));
   return MSQG_OK;
 }
 static int download_level(msqg_model *m, double *host, const double *src, int nf, int lev) {
   const Geom &g = m->g[lev];
-  size_t cnt = (size_t)nf * g.n * g.n;
+  size_t cnt = (size_t)nf * g.nx * g.ny;
   dim3 b(32, 8);
-  k_unpack<<<grid2(g.n, g.n, b, nf), b, 0, m->stream>>>(m->d_stage, src, nf, g);
+  k_unpack<<<grid2(g.nx, g.ny, b, nf), b, 0, m->stream>>>(m->d_stage, src, nf, g);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(host, m->d_stage, cnt * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
@@ -1333,7 +1335,7 @@ extern "C" int msqg_test_restrict(msqg_model *m, int level, const double *fine, 
   int rc;
   if ((rc = upload_level(m, m->res.lev[level], fine, m->nl, level, -1.))) return rc;
   dim3 b(32, 8);
-  k_restrict<<<grid2(m->g[level - 1].n, m->g[level - 1].n, b, m->nl), b, 0, m->stream>>>(m->res.lev[level], m->res.lev[level - 1], m->g[level], m->g[level - 1], -1., 0);
+  k_restrict<<<grid2(m->g[level - 1].nx, m->g[level - 1].ny, b, m->nl), b, 0, m->stream>>>(m->res.lev[level], m->res.lev[level - 1], m->g[level], m->g[level - 1], -1., 0);
   CK(cudaGetLastError());
   return download_level(m, coarse, m->res.lev[level - 1], m->nl, level - 1);
 }
@@ -1343,7 +1345,7 @@ extern "C" int msqg_test_prolong(msqg_model *m, int level, const double *coarse,
   int rc;
   if ((rc = upload_level(m, m->da.lev[level - 1], coarse, m->nl, level - 1, -1.))) return rc;
   dim3 b(32, 8);
-  k_prolong<<<grid2(m->g[level].n, m->g[level].n, b, m->nl), b, 0, m->stream>>>(m->da.lev[level - 1], m->da.lev[level], m->g[level - 1], m->g[level]);
+  k_prolong<<<grid2(m->g[level].nx, m->g[level].ny, b, m->nl), b, 0, m->stream>>>(m->da.lev[level - 1], m->da.lev[level], m->g[level - 1], m->g[level]);
   CK(cudaGetLastError());
   return download_level(m, fine, m->da.lev[level], m->nl, level);
 }

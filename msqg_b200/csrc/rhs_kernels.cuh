@@ -28,16 +28,16 @@ __device__ __forceinline__ double lap5(const double *__restrict__ p, size_t c, i
 }
 
 __device__ __forceinline__ void write_ghosts(double *__restrict__ p, const Geom &g, int x, int y, double v, double sg) {
-  const int n = g.n;
-  const bool l = x == 0, r = x == n - 1, bo = y == 0, t = y == n - 1;
+  const int nx = g.nx, ny = g.ny;
+  const bool l = x == 0, r = x == nx - 1, bo = y == 0, t = y == ny - 1;
   if (l) p[GIDX(g.pitch, y, -1)] = sg * v;
-  if (r) p[GIDX(g.pitch, y, n)] = sg * v;
+  if (r) p[GIDX(g.pitch, y, nx)] = sg * v;
   if (bo) p[GIDX(g.pitch, -1, x)] = sg * v;
-  if (t) p[GIDX(g.pitch, n, x)] = sg * v;
+  if (t) p[GIDX(g.pitch, ny, x)] = sg * v;
   if (l && bo) p[GIDX(g.pitch, -1, -1)] = v;
-  if (l && t) p[GIDX(g.pitch, n, -1)] = v;
-  if (r && bo) p[GIDX(g.pitch, -1, n)] = v;
-  if (r && t) p[GIDX(g.pitch, n, n)] = v;
+  if (l && t) p[GIDX(g.pitch, ny, -1)] = v;
+  if (r && bo) p[GIDX(g.pitch, -1, nx)] = v;
+  if (r && t) p[GIDX(g.pitch, ny, nx)] = v;
 }
 
 /* out = laplacian(in) on every layer (blockIdx.z) + dirichlet(0) ghosts.
@@ -53,9 +53,9 @@ k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *_
   const int f = blockIdx.z;
   const double *p = in + (size_t)f * g.plane;
   double um = 0.;
-  if (x <= g.n && y <= g.n) {
+  if (x <= g.nx && y <= g.ny) {
     const size_t c = GIDX(g.pitch, y, x);
-    if (x < g.n && y < g.n) {
+    if (x < g.nx && y < g.ny) {
       double *o = out + (size_t)f * g.plane;
       const double v = lap5(p, c, g.pitch, g);
       o[c] = v;
@@ -63,12 +63,12 @@ k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *_
     }
     if (umax) {
       const int P = g.pitch;
-      if (y < g.n) { /* x-face (x, y), x = 0..n */
+      if (y < g.ny) { /* x-face (x, y), x = 0..nx */
         const double u = div_by(0.25 * (p[c + P] - p[c - P] + p[c - 1 + P] - p[c - 1 - P]), g.Delta, g.rD);
         const double a = fabs(u);
         if (a > um) um = a;
       }
-      if (x < g.n) { /* y-face (x, y), y = 0..n */
+      if (x < g.nx) { /* y-face (x, y), y = 0..ny */
         const double u = div_by(0.25 * (p[c + 1] - p[c - 1] + p[c + 1 - P] - p[c - 1 - P]), g.Delta, g.rD);
         const double a = fabs(u);
         if (a > um) um = a;
@@ -127,7 +127,7 @@ k_rhs(RhsArgs A) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const Geom g = A.g;
-  if (x >= g.n || y >= g.n) return;
+  if (x >= g.nx || y >= g.ny) return;
   const size_t c = GIDX(g.pitch, y, x);
   const int P = g.pitch;
   const size_t pl = g.plane;
@@ -216,7 +216,7 @@ __global__ void k_advance(double *__restrict__ out, const double *__restrict__ i
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
-  if (x >= g.n || y >= g.n) return;
+  if (x >= g.nx || y >= g.ny) return;
   const size_t c = (size_t)f * g.plane + GIDX(g.pitch, y, x);
   if (noise)
     out[c] = in[c] + dq[c] * dt + noise[c] * dts;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256)
 k_comp_q(const double *__restrict__ psi, const double *__restrict__ s, double *__restrict__ q, Geom g, LayerMetrics M) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= g.n || y >= g.n) return;
+  if (x >= g.nx || y >= g.ny) return;
   const size_t c = GIDX(g.pitch, y, x);
   const size_t pl = g.plane;
 #pragma unroll
@@ -263,7 +263,7 @@ k_project(const double *__restrict__ in, double *__restrict__ out, Geom g, ModeM
           const double *__restrict__ matf /* optional per-cell matrix planes */, int ghosts) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= g.n || y >= g.n) return;
+  if (x >= g.nx || y >= g.ny) return;
   const size_t c = GIDX(g.pitch, y, x);
   const size_t pl = g.plane;
   double v[NL];
@@ -288,7 +288,7 @@ k_ke_partial(const double *__restrict__ p, Geom g, double *__restrict__ part) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   double v = 0.;
-  if (x < g.n && y < g.n) {
+  if (x < g.nx && y < g.ny) {
     const size_t c = GIDX(g.pitch, y, x);
     v = lapf(0.5 * p[c], p, c, g.pitch, g) * (g.Delta * g.Delta);
   }
