@@ -174,6 +174,35 @@ int msqg_test_relax_profile(msqg_model *m, int level, int nsweeps, long long *ou
 /* one mg_cycle + residual at the model's shape, timed with CUDA events (ms) */
 int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_out);
 
+/* ---- (1b) 2-D domain decomposition: one tile per GPU, halo exchange == boundary() -------------
+ * The semantics of the reference built with -D_MPI=1 (msqg/qg.c:12-19): px x py tiles on every
+ * multigrid level whose global size is >= agg_n (coarser levels are agglomerated on tile (0,0)),
+ * lexicographic Gauss-Seidel inside each tile with the neighbours' pre-sweep halo, halo exchange
+ * after every sweep.  `local` keeps all tiles in one process on one device (tests / emulation),
+ * `nccl` is one tile per process: rank = iy*px + ix, uid from msqg_nccl_unique_id on rank 0.
+ * Field buffers are the TILE's [nf][ny][nx] block of the global [nf][N][N] array. */
+typedef struct msqg_group msqg_group;
+int msqg_nccl_unique_id(void *out128);
+int msqg_group_create_local(const msqg_params *p, int device, int px, int py, int agg_n, msqg_group **out);
+int msqg_group_create_nccl(const msqg_params *p, int device, int px, int py, int agg_n, int rank, int nranks,
+                           const void *uid128, msqg_group **out);
+void msqg_group_destroy(msqg_group *g);
+int msqg_group_ntiles(msqg_group *g);                       /* tiles held by this process */
+msqg_model *msqg_group_tile(msqg_group *g, int t);
+int msqg_group_tile_info(msqg_group *g, int t, int *info6); /* ix, iy, x0, y0, nx, ny */
+int msqg_group_set_field(msqg_group *g, int t, int id, const double *host_tile);
+int msqg_group_get_field(msqg_group *g, int t, int id, double *host_tile);
+int msqg_group_set_const(msqg_group *g);
+int msqg_group_invertq(msqg_group *g, int q_id);
+int msqg_group_step(msqg_group *g, double t, double tnext, double *dt_out, double *tnext_out);
+int msqg_group_last_mgstats(msqg_group *g, msqg_mgstats *out);
+long msqg_group_total_cycles(msqg_group *g);
+long msqg_group_exchanges(msqg_group *g);
+long msqg_group_launches(msqg_group *g);
+int msqg_group_set_stream_sync(msqg_group *g);
+int msqg_group_profile_enable(msqg_group *g, int on);
+int msqg_group_profile_read(msqg_group *g, double *ms, long *count, long *aux_sum);
+
 /* ---- (2) reference surface (global state, like the SWIG module `qg`) --- */
 
 int read_params(char *path2file);                 /* qg.h:689 */

@@ -1,0 +1,597 @@
+/*
+ * dist_impl.cuh -- 2-D domain decomposition of the msqg timestep (included by model.cu).
+ *
+ * Semantics = the reference built with -D_MPI=1 (msqg/qg.c:12-19): every rank owns a px x py tile on
+ * each multigrid level; a relaxation sweep is lexicographic Gauss-Seidel INSIDE the tile with the
+ * neighbours' pre-sweep values in the halo, refreshed after every sweep (boundary_level ==
+ * halo exchange, [BASILISK] C3 of SURVEY.md 2c); every other operator is order-independent.  Levels
+ * whose global size is below `agg_n` are agglomerated onto tile (0,0) and swept serially there.
+ * This is exactly what oracle/msqg_oracle.c emulates with orc_set_decomp(px, py, agg_n), so the
+ * decomposed GPU path is checked bit for bit against the CPU oracle.
+ *
+ * Two exchange back-ends behind the same driver:
+ *   local : all tiles live in this process on one device (tests, 1-GPU emulation): device copies
+ *   nccl  : one tile per process/GPU: grouped ncclSend/ncclRecv on the model stream (NVLink),
+ *           ncclAllReduce for the 8-byte reductions.  NCCL is loaded lazily with dlopen.
+ * Halo exchange is x-phase then y-phase (rows include the ghost columns) so corner ghosts propagate.
+ */
+#pragma once
+
+/* ------------------------------------------------------------------ NCCL, loaded lazily */
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+struct NcclApi {
+  int (*GetUniqueId)(ncclUniqueId_t *);
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_t, int);
+  int (*CommDestroy)(ncclComm_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(int);
+  bool ok;
+};
+static NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  api.ok = false;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return nullptr;
+#define NCSYM(f, name) *(void **)(&api.f) = dlsym(h, name); if (!api.f) return nullptr;
+  NCSYM(GetUniqueId, "ncclGetUniqueId") NCSYM(CommInitRank, "ncclCommInitRank") NCSYM(CommDestroy, "ncclCommDestroy")
+  NCSYM(GroupStart, "ncclGroupStart") NCSYM(GroupEnd, "ncclGroupEnd") NCSYM(Send, "ncclSend") NCSYM(Recv, "ncclRecv")
+  NCSYM(AllReduce, "ncclAllReduce") NCSYM(GetErrorString, "ncclGetErrorString")
+#undef NCSYM
+  api.ok = true;
+  return &api;
+}
+#define NCCL_DOUBLE 8 /* ncclFloat64 */
+#define NCCL_MAX 2    /* ncclMax */
+#define NCK(call)                                                                                   \
+  do {                                                                                              \
+    int r_ = (call);                                                                                \
+    if (r_ != 0) FAIL(MSQG_ERR_CUDA, "%s:%d NCCL: %s", __FILE__, __LINE__, G->nccl->GetErrorString(r_)); \
+  } while (0)
+
+extern "C" int msqg_nccl_unique_id(void *out128) {
+  NcclApi *a = nccl_api();
+  if (!a) FAIL(MSQG_ERR_CUDA, "libnccl.so.2 not found");
+  ncclUniqueId_t id;
+  int r = a->GetUniqueId(&id);
+  if (r) FAIL(MSQG_ERR_CUDA, "ncclGetUniqueId: %s", a->GetErrorString(r));
+  memcpy(out128, &id, 128);
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ exchange kernels */
+__global__ void k_pack_cols(const double *__restrict__ a, int nf, Geom g, double *__restrict__ bl, double *__restrict__ br) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+  if (y >= g.ny) return;
+  const double *p = a + (size_t)f * g.plane;
+  bl[(size_t)f * g.ny + y] = p[GIDX(g.pitch, y, 0)];
+  br[(size_t)f * g.ny + y] = p[GIDX(g.pitch, y, g.nx - 1)];
+}
+__global__ void k_unpack_cols(double *__restrict__ a, int nf, Geom g, const double *__restrict__ fl, const double *__restrict__ fr) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+  if (y >= g.ny) return;
+  double *p = a + (size_t)f * g.plane;
+  if (g.bc & 1) p[GIDX(g.pitch, y, -1)] = fl[(size_t)f * g.ny + y];
+  if (g.bc & 2) p[GIDX(g.pitch, y, g.nx)] = fr[(size_t)f * g.ny + y];
+}
+__global__ void k_pack_rows(const double *__restrict__ a, int nf, Geom g, double *__restrict__ bb, double *__restrict__ bt) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x - 1, f = blockIdx.y;
+  if (x > g.nx) return;
+  const double *p = a + (size_t)f * g.plane;
+  bb[(size_t)f * (g.nx + 2) + x + 1] = p[GIDX(g.pitch, 0, x)];
+  bt[(size_t)f * (g.nx + 2) + x + 1] = p[GIDX(g.pitch, g.ny - 1, x)];
+}
+__global__ void k_unpack_rows(double *__restrict__ a, int nf, Geom g, const double *__restrict__ fb, const double *__restrict__ ft) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x - 1, f = blockIdx.y;
+  if (x > g.nx) return;
+  double *p = a + (size_t)f * g.plane;
+  if (g.bc & 4) p[GIDX(g.pitch, -1, x)] = fb[(size_t)f * (g.nx + 2) + x + 1];
+  if (g.bc & 8) p[GIDX(g.pitch, g.ny, x)] = ft[(size_t)f * (g.nx + 2) + x + 1];
+}
+/* gather: contiguous tile block [nf][hy][hx] -> interior of the full padded level at (ox, oy) */
+__global__ void k_place(double *__restrict__ full, Geom gfull, const double *__restrict__ src, int hx, int hy, int ox, int oy) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+  if (x >= hx || y >= hy) return;
+  full[(size_t)f * gfull.plane + GIDX(gfull.pitch, oy + y, ox + x)] = src[((size_t)f * hy + y) * hx + x];
+}
+/* scatter: (hx+2) x (hy+2) patch around the tile block of the full level; values outside the
+ * domain are the homogeneous-dirichlet ghosts of da (coarse_at with bc = 0) */
+__global__ void k_extract_patch(const double *__restrict__ full, Geom gfull, double *__restrict__ dst, int hx, int hy, int ox, int oy) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x - 1, y = blockIdx.y * blockDim.y + threadIdx.y - 1, f = blockIdx.z;
+  if (x > hx || y > hy) return;
+  dst[((size_t)f * (hy + 2) + y + 1) * (hx + 2) + x + 1] = coarse_at(full + (size_t)f * gfull.plane, gfull, ox + x, oy + y);
+}
+__global__ void k_load_patch(double *__restrict__ dst, Geom gp, const double *__restrict__ src) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x - 1, y = blockIdx.y * blockDim.y + threadIdx.y - 1, f = blockIdx.z;
+  if (x > gp.nx || y > gp.ny) return;
+  dst[(size_t)f * gp.plane + GIDX(gp.pitch, y, x)] = src[((size_t)f * (gp.ny + 2) + y + 1) * (gp.nx + 2) + x + 1];
+}
+
+/* ------------------------------------------------------------------ the group */
+struct msqg_group {
+  msqg_params p;
+  int px, py, agg_n, device, kind; /* kind 0 local, 1 nccl */
+  int rank, nranks;
+  std::vector<msqg_model *> tiles; /* local: all tiles, index iy*px+ix; nccl: this rank's tile */
+  cudaStream_t stream;
+  NcclApi *nccl;
+  ncclComm_t comm;
+  double *d_red, *h_red; /* reduction scratch (device / pinned host), 64 doubles */
+  double ts_previous;
+  msqg_mgstats mgpsi;
+  long total_cycles;
+  double umax_pg[MSQG_MAXL];
+  long exchanges;
+};
+
+static inline int tile_rank(msqg_group *G, int ix, int iy) { return iy * G->px + ix; }
+static inline msqg_model *tile_at(msqg_group *G, int ix, int iy) {
+  return G->kind == 0 ? G->tiles[tile_rank(G, ix, iy)] : G->tiles[0];
+}
+static inline msqg_model *root_tile(msqg_group *G) { return (G->kind == 0 || G->rank == 0) ? G->tiles[0] : nullptr; }
+
+typedef double *(*tile_ptr_fn)(msqg_model *, int);
+static double *ptr_da(msqg_model *m, int l) { return m->da.lev[l]; }
+static double *ptr_patch(msqg_model *m, int) { return m->da_patch; }
+
+/* halo exchange of `nf` planes of the array ptr(tile) with geometry geo(tile) */
+static int halo_exchange(msqg_group *G, std::vector<double *> &arr, std::vector<Geom> &geo, int nf) {
+  G->exchanges++;
+  const int nt = (int)G->tiles.size();
+  for (int phase = 0; phase < 2; phase++) {
+    /* pack */
+    for (int t = 0; t < nt; t++) {
+      msqg_model *m = G->tiles[t];
+      const Geom &g = geo[t];
+      if (phase == 0) k_pack_cols<<<dim3((g.ny + 127) / 128, nf), 128, 0, G->stream>>>(arr[t], nf, g, m->halo_send[0], m->halo_send[1]);
+      else k_pack_rows<<<dim3((g.nx + 2 + 127) / 128, nf), 128, 0, G->stream>>>(arr[t], nf, g, m->halo_send[2], m->halo_send[3]);
+    }
+    CK(cudaGetLastError());
+    /* transfer: side 0 <-> neighbour's side 1 (x), side 2 <-> neighbour's side 3 (y) */
+    if (G->kind == 0) {
+      for (int t = 0; t < nt; t++) {
+        msqg_model *m = G->tiles[t];
+        const Geom &g = geo[t];
+        const size_t cnt = (size_t)nf * (phase == 0 ? g.ny : g.nx + 2) * sizeof(double);
+        const int lo = phase == 0 ? 0 : 2, hi = lo + 1;
+        if (g.bc & (phase == 0 ? 1 : 4)) { /* neighbour on the low side: its high-side send -> my low-side recv */
+          msqg_model *nb = phase == 0 ? tile_at(G, m->ix - 1, m->iy) : tile_at(G, m->ix, m->iy - 1);
+          CK(cudaMemcpyAsync(m->halo_recv[lo], nb->halo_send[hi], cnt, cudaMemcpyDeviceToDevice, G->stream));
+        }
+        if (g.bc & (phase == 0 ? 2 : 8)) {
+          msqg_model *nb = phase == 0 ? tile_at(G, m->ix + 1, m->iy) : tile_at(G, m->ix, m->iy + 1);
+          CK(cudaMemcpyAsync(m->halo_recv[hi], nb->halo_send[lo], cnt, cudaMemcpyDeviceToDevice, G->stream));
+        }
+      }
+    } else {
+      msqg_model *m = G->tiles[0];
+      const Geom &g = geo[0];
+      const size_t cnt = (size_t)nf * (phase == 0 ? g.ny : g.nx + 2);
+      const int lo = phase == 0 ? 0 : 2, hi = lo + 1;
+      NCK(G->nccl->GroupStart());
+      if (g.bc & (phase == 0 ? 1 : 4)) {
+        const int peer = phase == 0 ? tile_rank(G, m->ix - 1, m->iy) : tile_rank(G, m->ix, m->iy - 1);
+        NCK(G->nccl->Send(m->halo_send[lo], cnt, NCCL_DOUBLE, peer, G->comm, G->stream));
+        NCK(G->nccl->Recv(m->halo_recv[lo], cnt, NCCL_DOUBLE, peer, G->comm, G->stream));
+      }
+      if (g.bc & (phase == 0 ? 2 : 8)) {
+        const int peer = phase == 0 ? tile_rank(G, m->ix + 1, m->iy) : tile_rank(G, m->ix, m->iy + 1);
+        NCK(G->nccl->Send(m->halo_send[hi], cnt, NCCL_DOUBLE, peer, G->comm, G->stream));
+        NCK(G->nccl->Recv(m->halo_recv[hi], cnt, NCCL_DOUBLE, peer, G->comm, G->stream));
+      }
+      NCK(G->nccl->GroupEnd());
+    }
+    /* unpack */
+    for (int t = 0; t < nt; t++) {
+      msqg_model *m = G->tiles[t];
+      const Geom &g = geo[t];
+      if (phase == 0) k_unpack_cols<<<dim3((g.ny + 127) / 128, nf), 128, 0, G->stream>>>(arr[t], nf, g, m->halo_recv[0], m->halo_recv[1]);
+      else k_unpack_rows<<<dim3((g.nx + 2 + 127) / 128, nf), 128, 0, G->stream>>>(arr[t], nf, g, m->halo_recv[2], m->halo_recv[3]);
+    }
+    CK(cudaGetLastError());
+  }
+  return MSQG_OK;
+}
+static int exchange_list(msqg_group *G, int id, int lev) {
+  std::vector<double *> arr;
+  std::vector<Geom> geo;
+  int nf = 0;
+  for (msqg_model *m : G->tiles) {
+    List *L = list_by_id(m, id);
+    arr.push_back(L->lev[lev]); geo.push_back(m->g[lev]); nf = L->nf;
+  }
+  return halo_exchange(G, arr, geo, nf);
+}
+static int exchange_da(msqg_group *G, int lev) {
+  std::vector<double *> arr;
+  std::vector<Geom> geo;
+  for (msqg_model *m : G->tiles) { arr.push_back(m->da.lev[lev]); geo.push_back(m->g[lev]); }
+  return halo_exchange(G, arr, geo, G->p.nl);
+}
+
+/* max over tiles/ranks of n doubles that every tile holds at d_scal + off */
+static int reduce_max(msqg_group *G, int off, int n, double *out) {
+  const int nt = (int)G->tiles.size();
+  for (int k = 0; k < n; k++) out[k] = 0.;
+  if (G->kind == 1) {
+    msqg_model *m = G->tiles[0];
+    NCK(G->nccl->AllReduce(m->d_scal + off, G->d_red, n, NCCL_DOUBLE, NCCL_MAX, G->comm, G->stream));
+    CK(cudaMemcpyAsync(G->h_red, G->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, G->stream));
+    CK(cudaStreamSynchronize(G->stream));
+    for (int k = 0; k < n; k++) out[k] = G->h_red[k];
+    return MSQG_OK;
+  }
+  for (int t = 0; t < nt; t++)
+    CK(cudaMemcpyAsync(G->h_red + (size_t)t * n, G->tiles[t]->d_scal + off, n * sizeof(double), cudaMemcpyDeviceToHost, G->stream));
+  CK(cudaStreamSynchronize(G->stream));
+  for (int t = 0; t < nt; t++)
+    for (int k = 0; k < n; k++) out[k] = fmax(out[k], G->h_red[(size_t)t * n + k]);
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ create / destroy */
+static int group_create(const msqg_params *p, int device, int px, int py, int agg_n, int kind, int rank, int nranks,
+                        const void *uid, msqg_group **out) {
+  *out = nullptr;
+  if (px * py < 2) FAIL(MSQG_ERR_ARG, "a group needs px*py >= 2 tiles");
+  if (p->mode_pv_invert || p->stochastic) FAIL(MSQG_ERR_ARG, "decomposed grids support the layer-coupled, deterministic path only");
+  if (kind == 1 && nranks != px * py) FAIL(MSQG_ERR_ARG, "nranks must equal px*py");
+  msqg_group *G = new msqg_group();
+  G->p = *p; G->px = px; G->py = py; G->agg_n = agg_n; G->device = device; G->kind = kind;
+  G->rank = rank; G->nranks = nranks; G->nccl = nullptr; G->comm = nullptr;
+  G->ts_previous = 0.; G->total_cycles = 0; G->exchanges = 0;
+  memset(&G->mgpsi, 0, sizeof(G->mgpsi));
+  memset(G->umax_pg, 0, sizeof(G->umax_pg));
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&G->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&G->d_red, 64 * sizeof(double)));
+  CK(cudaMallocHost(&G->h_red, 64 * 64 * sizeof(double)));
+  int rc;
+  if (kind == 0) {
+    for (int iy = 0; iy < py; iy++)
+      for (int ix = 0; ix < px; ix++) {
+        msqg_model *m;
+        if ((rc = create_model(p, device, px, py, ix, iy, agg_n, G->stream, &m))) return rc;
+        G->tiles.push_back(m);
+      }
+  } else {
+    G->nccl = nccl_api();
+    if (!G->nccl) FAIL(MSQG_ERR_CUDA, "libnccl.so.2 not found");
+    ncclUniqueId_t id;
+    memcpy(&id, uid, 128);
+    NCK(G->nccl->CommInitRank(&G->comm, nranks, id, rank));
+    msqg_model *m;
+    if ((rc = create_model(p, device, px, py, rank % px, rank / px, agg_n, G->stream, &m))) return rc;
+    G->tiles.push_back(m);
+  }
+  *out = G;
+  return MSQG_OK;
+}
+extern "C" int msqg_group_create_local(const msqg_params *p, int device, int px, int py, int agg_n, msqg_group **out) {
+  return group_create(p, device, px, py, agg_n, 0, 0, 1, nullptr, out);
+}
+extern "C" int msqg_group_create_nccl(const msqg_params *p, int device, int px, int py, int agg_n, int rank, int nranks,
+                                      const void *uid128, msqg_group **out) {
+  return group_create(p, device, px, py, agg_n, 1, rank, nranks, uid128, out);
+}
+extern "C" void msqg_group_destroy(msqg_group *G) {
+  if (!G) return;
+  cudaSetDevice(G->device);
+  cudaStreamSynchronize(G->stream);
+  for (msqg_model *m : G->tiles) msqg_destroy(m);
+  if (G->comm && G->nccl) G->nccl->CommDestroy(G->comm);
+  cudaFree(G->d_red);
+  cudaFreeHost(G->h_red);
+  cudaStreamDestroy(G->stream);
+  delete G;
+}
+extern "C" int msqg_group_ntiles(msqg_group *G) { return (int)G->tiles.size(); }
+extern "C" msqg_model *msqg_group_tile(msqg_group *G, int t) { return G->tiles[t]; }
+extern "C" int msqg_group_tile_info(msqg_group *G, int t, int *info /*ix,iy,x0,y0,nx,ny*/) {
+  msqg_model *m = G->tiles[t];
+  info[0] = m->ix; info[1] = m->iy; info[2] = m->x0; info[3] = m->y0; info[4] = m->tnx; info[5] = m->tny;
+  return MSQG_OK;
+}
+extern "C" long msqg_group_total_cycles(msqg_group *G) { return G->total_cycles; }
+extern "C" long msqg_group_exchanges(msqg_group *G) { return G->exchanges; }
+extern "C" long msqg_group_launches(msqg_group *G) { long s = 0; for (msqg_model *m : G->tiles) s += m->launches; return s; }
+extern "C" int msqg_group_last_mgstats(msqg_group *G, msqg_mgstats *out) { *out = G->mgpsi; return MSQG_OK; }
+extern "C" int msqg_group_set_stream_sync(msqg_group *G) { CK(cudaStreamSynchronize(G->stream)); return MSQG_OK; }
+
+/* ------------------------------------------------------------------ multigrid on tiles */
+static int g_residual(msqg_group *G, int q_id, double *maxres) {
+  for (msqg_model *m : G->tiles) {
+    const int D = m->depth;
+    const Geom &g = m->g[D];
+    List *ql = list_by_id(m, q_id);
+    CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), G->stream));
+    dim3 b(64, 4);
+    LayerMetrics M = metrics_of(m);
+    ProfScope ps(m, PROF_RESIDUAL, 0);
+    NL_SWITCH(m->nl, k_residual<NL><<<grid2(g.nx, g.ny, b), b, 0, G->stream>>>(m->psi.lev[D], ql->lev[D], m->res.lev[D], m->str.lev[D], g, M, m->d_scal));
+    m->launches++;
+  }
+  CK(cudaGetLastError());
+  return reduce_max(G, 0, 1, maxres);
+}
+
+static int g_relax_level(msqg_group *G, msqg_model *m, int l, int nsweeps) {
+  int rc;
+  ProfScope ps(m, l == m->depth ? PROF_RELAX_FINE : PROF_RELAX_COARSE, nsweeps);
+  NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nsweeps, C); });
+  return rc;
+}
+
+static int g_cycle(msqg_group *G, int nrelax) {
+  msqg_model *m0 = G->tiles[0];
+  const int D = m0->depth, La = m0->agg_level, nl = G->p.nl;
+  dim3 b(32, 8);
+  /* restriction(res) on the distributed levels, then onto this tile's share of level La-1 */
+  for (msqg_model *m : G->tiles) {
+    for (int l = D - 1; l >= La; l--) {
+      k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, G->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
+      m->launches++;
+    }
+    k_restrict<<<grid2(m->gpatch.nx, m->gpatch.ny, b, nl), b, 0, G->stream>>>(m->res.lev[La], m->res_patch, m->g[La], m->gpatch, -1., 0);
+    k_unpack<<<grid2(m->gpatch.nx, m->gpatch.ny, b, nl), b, 0, G->stream>>>(m->patch_stage, m->res_patch, nl, m->gpatch);
+    m->launches += 2;
+  }
+  CK(cudaGetLastError());
+  /* gather onto tile (0,0) */
+  msqg_model *root = root_tile(G);
+  const int hx = m0->gpatch.nx, hy = m0->gpatch.ny;
+  const size_t blk = (size_t)nl * hx * hy;
+  if (G->kind == 0) {
+    for (msqg_model *m : G->tiles) {
+      k_place<<<grid2(hx, hy, b, nl), b, 0, G->stream>>>(root->res.lev[La - 1], root->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy);
+      root->launches++;
+    }
+  } else {
+    if (G->rank == 0) {
+      k_place<<<grid2(hx, hy, b, nl), b, 0, G->stream>>>(root->res.lev[La - 1], root->g[La - 1], root->patch_stage, hx, hy, 0, 0);
+      for (int r = 1; r < G->nranks; r++) {
+        NCK(G->nccl->Recv(root->d_stage, blk, NCCL_DOUBLE, r, G->comm, G->stream));
+        k_place<<<grid2(hx, hy, b, nl), b, 0, G->stream>>>(root->res.lev[La - 1], root->g[La - 1], root->d_stage, hx, hy, (r % G->px) * hx, (r / G->px) * hy);
+      }
+    } else
+      NCK(G->nccl->Send(m0->patch_stage, blk, NCCL_DOUBLE, 0, G->comm, G->stream));
+  }
+  CK(cudaGetLastError());
+  int rc;
+  if (root) {
+    /* agglomerated levels: serial reference sweep on one GPU */
+    for (int l = La - 2; l >= 1; l--) {
+      k_restrict<<<grid2(root->g[l].nx, root->g[l].ny, b, nl), b, 0, G->stream>>>(root->res.lev[l + 1], root->res.lev[l], root->g[l + 1], root->g[l], -1., 0);
+      root->launches++;
+    }
+    for (int l = 1; l <= La - 1; l++) {
+      const Geom &g = root->g[l];
+      if (l == 1) CK(cudaMemsetAsync(root->da.lev[l], 0, (size_t)nl * g.plane * sizeof(double), G->stream));
+      else {
+        k_prolong<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(root->da.lev[l - 1], root->da.lev[l], root->g[l - 1], g);
+        root->launches++;
+      }
+      if ((rc = g_relax_level(G, root, l, nrelax))) return rc;
+    }
+  }
+  /* scatter level La-1 of da: each tile gets its block plus a one-cell ring */
+  const size_t pblk = (size_t)nl * (hx + 2) * (hy + 2);
+  if (G->kind == 0) {
+    for (msqg_model *m : G->tiles) {
+      k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy);
+      k_load_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da_patch, m->gpatch, m->patch_stage);
+      m->launches += 2;
+    }
+  } else {
+    if (G->rank == 0) {
+      for (int r = 1; r < G->nranks; r++) {
+        k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], root->d_stage, hx, hy, (r % G->px) * hx, (r / G->px) * hy);
+        NCK(G->nccl->Send(root->d_stage, pblk, NCCL_DOUBLE, r, G->comm, G->stream));
+      }
+      k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], root->patch_stage, hx, hy, 0, 0);
+    } else
+      NCK(G->nccl->Recv(m0->patch_stage, pblk, NCCL_DOUBLE, 0, G->comm, G->stream));
+    k_load_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m0->da_patch, m0->gpatch, m0->patch_stage);
+  }
+  CK(cudaGetLastError());
+  /* distributed levels: prolong, halo, nrelax x { one sweep inside the tile, halo } */
+  for (int l = La; l <= D; l++) {
+    for (msqg_model *m : G->tiles) {
+      const Geom &g = m->g[l];
+      ProfScope ps(m, PROF_PROLONG, l);
+      if (l == La) k_prolong<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->da_patch, m->da.lev[l], m->gpatch, g);
+      else k_prolong<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
+      m->launches++;
+    }
+    CK(cudaGetLastError());
+    if ((rc = exchange_da(G, l))) return rc;
+    for (int s = 0; s < nrelax; s++) {
+      for (msqg_model *m : G->tiles)
+        if ((rc = g_relax_level(G, m, l, 1))) return rc;
+      if ((rc = exchange_da(G, l))) return rc;
+    }
+  }
+  /* a += da ; boundary(a) */
+  for (msqg_model *m : G->tiles) {
+    const Geom &g = m->g[D];
+    ProfScope ps(m, PROF_CORRECT, 0);
+    k_correct<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->psi.lev[D], m->da.lev[D], g);
+    m->launches++;
+  }
+  CK(cudaGetLastError());
+  return exchange_list(G, MSQG_PSI, D);
+}
+
+static int g_check_err(msqg_group *G) {
+  for (msqg_model *m : G->tiles) {
+    int rc = check_relax_err(m);
+    if (rc) return rc;
+  }
+  return MSQG_OK;
+}
+
+/* mg_solve + poisson_layer + invertq on the decomposed grid */
+static int g_invertq(msqg_group *G, int q_id) {
+  for (msqg_model *m : G->tiles) {
+    if (!m->const_set) FAIL(MSQG_ERR_ARG, "set_const must be called before invertq");
+    if (!m->s_uniform) FAIL(MSQG_ERR_ARG, "horizontally varying stretching is not supported by the relax kernel yet");
+  }
+  int rc;
+  if ((rc = exchange_list(G, MSQG_PSI, G->tiles[0]->depth))) return rc;
+  msqg_mgstats s;
+  memset(&s, 0, sizeof(s));
+  s.nrelax = 4;
+  double resb;
+  if ((rc = g_residual(G, q_id, &resb))) return rc;
+  s.resb = s.resa = resb;
+  for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > 1e-3); s.i++) {
+    if ((rc = g_cycle(G, s.nrelax))) return rc;
+    if ((rc = g_residual(G, q_id, &s.resa))) return rc;
+    if (s.resa > 1e-3) {
+      if (resb / s.resa < 1.2 && s.nrelax < 100) s.nrelax++;
+      else if (resb / s.resa > 10 && s.nrelax > 2) s.nrelax--;
+    }
+    resb = s.resa;
+  }
+  if ((rc = g_check_err(G))) return rc;
+  G->total_cycles += s.i;
+  G->mgpsi = s;
+  return MSQG_OK;
+}
+extern "C" int msqg_group_invertq(msqg_group *G, int q_id) {
+  CK(cudaSetDevice(G->device));
+  return g_invertq(G, q_id);
+}
+
+/* ------------------------------------------------------------------ fields, set_const */
+extern "C" int msqg_group_set_field(msqg_group *G, int t, int id, const double *host_tile) {
+  return msqg_set_field(G->tiles[t], id, host_tile);
+}
+extern "C" int msqg_group_get_field(msqg_group *G, int t, int id, double *host_tile) {
+  return msqg_get_field(G->tiles[t], id, host_tile);
+}
+extern "C" int msqg_group_set_const(msqg_group *G) {
+  CK(cudaSetDevice(G->device));
+  int rc;
+  const int D = G->tiles[0]->depth;
+  for (msqg_model *m : G->tiles)
+    if ((rc = set_const_local(m))) return rc;
+  for (int id : {MSQG_PSI, MSQG_PSIPG, MSQG_TOPO})
+    if ((rc = exchange_list(G, id, D))) return rc;
+  for (msqg_model *m : G->tiles)
+    if ((rc = set_const_finish(m))) return rc;
+  if ((rc = exchange_list(G, MSQG_ZETAP, D))) return rc;
+  /* CFL speeds of the static background flow: max over tiles */
+  int has_pg = 0;
+  for (msqg_model *m : G->tiles) has_pg |= m->has_pg;
+  for (int l = 0; l < G->p.nl; l++) G->umax_pg[l] = 0.;
+  if (G->kind == 0) {
+    for (msqg_model *m : G->tiles)
+      for (int l = 0; l < G->p.nl; l++) G->umax_pg[l] = fmax(G->umax_pg[l], m->umax_pg[l]);
+  } else {
+    msqg_model *m = G->tiles[0];
+    CK(cudaMemcpyAsync(m->d_scal + 1, m->umax_pg, G->p.nl * sizeof(double), cudaMemcpyHostToDevice, G->stream));
+    if ((rc = reduce_max(G, 1, G->p.nl, G->umax_pg))) return rc;
+  }
+  (void)has_pg;
+  CK(cudaStreamSynchronize(G->stream));
+  return MSQG_OK;
+}
+
+/* ------------------------------------------------------------------ RHS and the step */
+static int g_rhs_prepare(msqg_group *G, double *umax) {
+  const int D = G->tiles[0]->depth;
+  int rc;
+  dim3 b(64, 4);
+  bool use_tmp = false;
+  for (msqg_model *m : G->tiles) {
+    const Geom &g = m->g[D];
+    CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), G->stream));
+    ProfScope ps(m, PROF_LAP, 0);
+    k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, G->stream>>>(m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
+    m->launches++;
+    use_tmp = (m->iRe != 0. || m->iRe4 != 0.);
+  }
+  CK(cudaGetLastError());
+  if ((rc = exchange_list(G, MSQG_ZETA, D))) return rc;
+  if (use_tmp) {
+    for (msqg_model *m : G->tiles) {
+      const Geom &g = m->g[D];
+      ProfScope ps(m, PROF_LAP, 0);
+      k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, G->stream>>>(m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+      m->launches++;
+    }
+    CK(cudaGetLastError());
+    if ((rc = exchange_list(G, MSQG_TMP, D))) return rc;
+  }
+  return reduce_max(G, 1, G->p.nl, umax);
+}
+static double g_dt_chain(msqg_group *G, const double *umax, double dtmax) {
+  msqg_model *m = G->tiles[0];
+  const double Delta = m->g[m->depth].Delta;
+  m->ts_previous = G->ts_previous;
+  for (int l = 0; l < m->nl; l++) {
+    dtmax = timestep_chain(m, umax[l], dtmax, Delta);
+    dtmax = timestep_chain(m, G->umax_pg[l], dtmax, Delta);
+  }
+  G->ts_previous = m->ts_previous;
+  return dtmax;
+}
+extern "C" int msqg_group_step(msqg_group *G, double t, double tnext_event, double *dt_out, double *tnext_out) {
+  CK(cudaSetDevice(G->device));
+  int rc;
+  double umax[MSQG_MAXL];
+  if ((rc = g_invertq(G, MSQG_Q))) return rc;
+  if ((rc = g_rhs_prepare(G, umax))) return rc;
+  double dt = g_dt_chain(G, umax, G->p.DT);
+  double tnext;
+  if (tnext_event >= 0 && tnext_event > t) {
+    unsigned int nn = (tnext_event - t) / dt;
+    tnext = tnext_event;
+    if (nn == 0) dt = tnext_event - t;
+    else {
+      const double dt1 = (tnext_event - t) / nn;
+      if (dt1 > dt * (1. + 1e-9)) dt = (tnext_event - t) / (nn + 1);
+      else if (dt1 < dt) dt = dt1;
+      tnext = t + dt;
+    }
+  } else
+    tnext = t + dt;
+  for (msqg_model *m : G->tiles) {
+    const int D = m->depth;
+    if ((rc = rhs_launch(m, m->q, m->q.lev[D], m->qpred.lev[D], nullptr, dt / 2., 0.f))) return rc;
+  }
+  if ((rc = g_invertq(G, MSQG_QPRED))) return rc;
+  if ((rc = g_rhs_prepare(G, umax))) return rc;
+  for (msqg_model *m : G->tiles) {
+    const int D = m->depth;
+    if ((rc = rhs_launch(m, m->qpred, m->q.lev[D], m->q.lev[D], nullptr, dt, 0.f))) return rc;
+  }
+  CK(cudaStreamSynchronize(G->stream));
+  (void)g_dt_chain(G, umax, dt);
+  if (dt_out) *dt_out = dt;
+  if (tnext_out) *tnext_out = tnext;
+  return MSQG_OK;
+}
+extern "C" int msqg_group_profile_enable(msqg_group *G, int on) {
+  for (msqg_model *m : G->tiles) { int rc = msqg_profile_enable(m, on); if (rc) return rc; }
+  return MSQG_OK;
+}
+extern "C" int msqg_group_profile_read(msqg_group *G, double *ms, long *count, long *aux_sum) {
+  for (int c = 0; c < PROF_NCAT; c++) { ms[c] = 0.; count[c] = 0; aux_sum[c] = 0; }
+  for (msqg_model *m : G->tiles) {
+    double a[PROF_NCAT]; long b[PROF_NCAT], c2[PROF_NCAT];
+    int rc = msqg_profile_read(m, a, b, c2);
+    if (rc) return rc;
+    for (int c = 0; c < PROF_NCAT; c++) { ms[c] += a[c]; count[c] += b[c]; aux_sum[c] += c2[c]; }
+  }
+  return MSQG_OK;
+}

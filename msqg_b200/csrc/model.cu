@@ -49,6 +49,14 @@ struct List {
 struct msqg_model {
   msqg_params p;
   int N, nl, depth, device;
+  /* tile of a px x py decomposition (single GPU: 1 x 1).  Levels < agg_level exist only on tile (0,0),
+     as full square grids (agglomerated coarse levels); finest tile is tnx x tny cells at (x0, y0). */
+  int px, py, ix, iy, agg_level, tnx, tny, x0, y0;
+  bool has_lev[MSQG_MAXLEV + 1];
+  Geom gpatch;                 /* level agg_level-1 restricted to this tile (+ halo ring): scatter/gather scratch */
+  double *da_patch, *res_patch; /* [nl] planes of gpatch */
+  double *halo_send[4], *halo_recv[4], *patch_stage; /* contiguous exchange buffers */
+  size_t halo_doubles, patch_doubles;
   cudaStream_t stream;
   bool own_stream;
   Geom g[MSQG_MAXLEV + 1];
@@ -193,6 +201,7 @@ extern "C" int msqg_read_params(const char *path, msqg_params *p) {
 static int alloc_list(msqg_model *m, List &L, int nf, double sg, int lev_lo, int lev_hi) {
   L.nf = nf; L.sg = sg;
   for (int l = lev_lo; l <= lev_hi; l++) {
+    if (!m->has_lev[l]) continue;
     size_t bytes = (size_t)nf * m->g[l].plane * sizeof(double);
     CK(cudaMalloc(&L.lev[l], bytes));
     CK(cudaMemsetAsync(L.lev[l], 0, bytes, m->stream));
@@ -249,12 +258,22 @@ static int unpack_from(msqg_model *m, List &L, double *host) {
 }
 
 /* ------------------------------------------------------------------ create / destroy */
-extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
+static void fill_geom_consts(Geom &g, double Delta) {
+  g.Delta = Delta; /* == L0*(1./(1 << level)) [BASILISK], exact power-of-two scaling */
+  g.rD = 1. / g.Delta;
+  g.D2 = g.Delta * g.Delta; g.rD2 = 1. / g.D2;
+  g.D12 = 12. * g.Delta * g.Delta; g.rD12 = 1. / g.D12;
+  g.D2x = 2 * g.Delta; g.rD2x = 1. / g.D2x;
+}
+
+static int create_model(const msqg_params *p, int device, int px, int py, int ix, int iy, int agg_n, cudaStream_t shared,
+                        msqg_model **out) {
   *out = nullptr;
   if (p->nl < 2 || p->nl > MSQG_NLMAX) FAIL(MSQG_ERR_ARG, "nl must be in [2,%d] (nl==1 is not functional in the reference)", MSQG_NLMAX);
   if (p->N < 8 || (p->N & (p->N - 1))) FAIL(MSQG_ERR_ARG, "N must be a power of two >= 8");
   if (p->sbc != 0) FAIL(MSQG_ERR_ARG, "only sbc == 0 (free slip) is supported");
   if (p->nptr != 0) FAIL(MSQG_ERR_ARG, "passive tracers (nptr > 0) are out of scope");
+  if (px < 1 || py < 1 || (px & (px - 1)) || (py & (py - 1))) FAIL(MSQG_ERR_ARG, "px, py must be powers of two");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     FAIL(MSQG_ERR_CUDA, "no CUDA device: the msqg timestep has no CPU path");
@@ -269,17 +288,39 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   int depth = 0;
   while ((1 << depth) < p->N) depth++;
   m->depth = depth;
+  m->px = px; m->py = py; m->ix = ix; m->iy = iy;
+  m->agg_level = 0;
+  if (px * py > 1) {
+    int la = 1;
+    while ((1 << la) < agg_n) la++;
+    if (la > depth) FAIL(MSQG_ERR_ARG, "agglomeration threshold %d exceeds N", agg_n);
+    if (((1 << la) / px) < 8 || ((1 << la) / py) < 8) FAIL(MSQG_ERR_ARG, "tiles must keep >= 8 cells per side on every distributed level (raise agg_n)");
+    if (la < 2) FAIL(MSQG_ERR_ARG, "agg_n too small");
+    m->agg_level = la;
+  }
   for (int l = 0; l <= depth; l++) {
     Geom &g = m->g[l];
-    g.nx = g.ny = 1 << l; g.bc = 0; g.pitch = msqg_pitch(g.nx); g.plane = (size_t)(g.ny + 2) * g.pitch;
-    g.Delta = p->L0 / (1 << l); /* == L0*(1./(1 << level)) [BASILISK], exact power-of-two scaling */
-    g.rD = 1. / g.Delta;
-    g.D2 = g.Delta * g.Delta; g.rD2 = 1. / g.D2;
-    g.D12 = 12. * g.Delta * g.Delta; g.rD12 = 1. / g.D12;
-    g.D2x = 2 * g.Delta; g.rD2x = 1. / g.D2x;
+    const bool dist = (px * py > 1) && l >= m->agg_level;
+    if (dist) {
+      g.nx = (1 << l) / px; g.ny = (1 << l) / py;
+      g.bc = (ix > 0 ? 1 : 0) | (ix < px - 1 ? 2 : 0) | (iy > 0 ? 4 : 0) | (iy < py - 1 ? 8 : 0);
+      m->has_lev[l] = true;
+    } else {
+      g.nx = g.ny = 1 << l; g.bc = 0;
+      m->has_lev[l] = (ix == 0 && iy == 0);
+    }
+    g.pitch = msqg_pitch(g.nx); g.plane = (size_t)(g.ny + 2) * g.pitch;
+    fill_geom_consts(g, p->L0 / (1 << l));
   }
-  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  m->own_stream = true;
+  m->tnx = m->g[depth].nx; m->tny = m->g[depth].ny;
+  m->x0 = ix * m->tnx; m->y0 = iy * m->tny;
+  m->da_patch = m->res_patch = m->patch_stage = nullptr;
+  for (int k = 0; k < 4; k++) m->halo_send[k] = m->halo_recv[k] = nullptr;
+  if (shared) { m->stream = shared; m->own_stream = false; }
+  else {
+    CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    m->own_stream = true;
+  }
   const int nl = p->nl, D = depth;
   int rc;
 #define AL(L, nf, sg, lo, hi) if ((rc = alloc_list(m, L, nf, sg, lo, hi))) { msqg_destroy(m); return rc; }
@@ -296,7 +337,11 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   if (p->stochastic) { AL(m->sstoch, nl, -1., D, D) AL(m->nstoch, nl, -1., D, D) }
 #undef AL
   const int maxnf = p->mode_pv_invert ? nl * nl : nl;
-  m->stage_doubles = (size_t)maxnf * p->N * p->N;
+  m->stage_doubles = (size_t)maxnf * m->tnx * m->tny;
+  if (m->has_lev[0]) { /* tile (0,0) also stages the agglomerated square levels */
+    const size_t sq0 = m->agg_level > 0 ? (size_t)nl * (1 << (m->agg_level - 1)) * (1 << (m->agg_level - 1)) : 0;
+    if (sq0 > m->stage_doubles) m->stage_doubles = sq0;
+  }
   CK(cudaMalloc(&m->d_stage, m->stage_doubles * sizeof(double)));
   CK(cudaMalloc(&m->d_scal, 64 * sizeof(double)));
   CK(cudaMallocHost(&m->h_scal, 64 * sizeof(double)));
@@ -319,30 +364,53 @@ extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   memset(m->umax_pg, 0, sizeof(m->umax_pg));
   /* Frl = Frm, ppl = vpg*x - upg*y, Ro = Rom, Rd = 1, topo = 0 (qg.h:898-915) */
   {
-    const int n = p->N;
-    const double Delta = p->L0 / n;
-    std::vector<double> h((size_t)nl * n * n, 0.);
-    m->h_fr.assign((size_t)nl * n * n, 0.);
+    const int tx = m->tnx, ty = m->tny;
+    const size_t tc = (size_t)tx * ty;
+    const double Delta = p->L0 / p->N;
+    std::vector<double> h((size_t)nl * tc, 0.);
+    m->h_fr.assign((size_t)nl * tc, 0.);
     for (int l = 0; l < nl - 1; l++)
-      for (size_t c = 0; c < (size_t)n * n; c++) m->h_fr[(size_t)l * n * n + c] = p->Fr[l];
+      for (size_t c = 0; c < tc; c++) m->h_fr[(size_t)l * tc + c] = p->Fr[l];
     if ((rc = pack_to(m, m->fr, m->h_fr.data()))) { msqg_destroy(m); return rc; }
     m->has_pg = 0;
     for (int l = 0; l < nl; l++) if (p->upg[l] != 0 || p->vpg[l] != 0) m->has_pg = 1;
     if (m->has_pg) {
       for (int l = 0; l < nl; l++)
-        for (int j = 0; j < n; j++)
-          for (int i = 0; i < n; i++) {
-            const double x = (i + 0.5) * Delta, y = (j + 0.5) * Delta;
-            h[((size_t)l * n + j) * n + i] = p->vpg[l] * x - p->upg[l] * y;
+        for (int j = 0; j < ty; j++)
+          for (int i = 0; i < tx; i++) {
+            const double x = (m->x0 + i + 0.5) * Delta, y = (m->y0 + j + 0.5) * Delta;
+            h[((size_t)l * ty + j) * tx + i] = p->vpg[l] * x - p->upg[l] * y;
           }
       if ((rc = pack_to(m, m->psipg, h.data()))) { msqg_destroy(m); return rc; }
     }
-    std::vector<double> one((size_t)n * n, 1.);
+    std::vector<double> one(tc, 1.);
     if ((rc = pack_to(m, m->rd, one.data()))) { msqg_destroy(m); return rc; }
+  }
+  if (px * py > 1) { /* exchange / scatter-gather scratch */
+    const int la = m->agg_level;
+    Geom &gp = m->gpatch;
+    gp.nx = m->g[la].nx / 2; gp.ny = m->g[la].ny / 2; gp.bc = 15;
+    gp.pitch = msqg_pitch(gp.nx); gp.plane = (size_t)(gp.ny + 2) * gp.pitch;
+    fill_geom_consts(gp, p->L0 / (1 << (la - 1)));
+    CK(cudaMalloc(&m->da_patch, (size_t)nl * gp.plane * sizeof(double)));
+    CK(cudaMalloc(&m->res_patch, (size_t)nl * gp.plane * sizeof(double)));
+    CK(cudaMemsetAsync(m->da_patch, 0, (size_t)nl * gp.plane * sizeof(double), m->stream));
+    CK(cudaMemsetAsync(m->res_patch, 0, (size_t)nl * gp.plane * sizeof(double), m->stream));
+    m->patch_doubles = (size_t)nl * (gp.nx + 2) * (gp.ny + 2);
+    CK(cudaMalloc(&m->patch_stage, m->patch_doubles * sizeof(double)));
+    m->halo_doubles = (size_t)nl * ((m->tnx > m->tny ? m->tnx : m->tny) + 2);
+    for (int k = 0; k < 4; k++) {
+      CK(cudaMalloc(&m->halo_send[k], m->halo_doubles * sizeof(double)));
+      CK(cudaMalloc(&m->halo_recv[k], m->halo_doubles * sizeof(double)));
+    }
   }
   CK(cudaStreamSynchronize(m->stream));
   *out = m;
   return MSQG_OK;
+}
+
+extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
+  return create_model(p, device, 1, 1, 0, 0, 0, nullptr, out);
 }
 
 extern "C" void msqg_destroy(msqg_model *m) {
@@ -361,6 +429,10 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->d_err) cudaFree(m->d_err);
   if (m->h_err) cudaFreeHost(m->h_err);
   if (m->mailbox) cudaFree(m->mailbox);
+  if (m->da_patch) cudaFree(m->da_patch);
+  if (m->res_patch) cudaFree(m->res_patch);
+  if (m->patch_stage) cudaFree(m->patch_stage);
+  for (int k = 0; k < 4; k++) { if (m->halo_send[k]) cudaFree(m->halo_send[k]); if (m->halo_recv[k]) cudaFree(m->halo_recv[k]); }
   for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
   if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -435,7 +507,7 @@ extern "C" int msqg_set_field(msqg_model *m, int id, const double *host) {
   if (!L || !L->lev[m->depth]) FAIL(MSQG_ERR_ARG, "field list %d is not allocated", id);
   int rc = pack_to(m, *L, host);
   if (rc) return rc;
-  const size_t cnt = (size_t)L->nf * m->N * m->N;
+  const size_t cnt = (size_t)L->nf * m->tnx * m->tny;
   if (id == MSQG_FR) m->h_fr.assign(host, host + cnt);
   if (id == MSQG_SSTOCH) m->h_sstoch.assign(host, host + cnt);
   if (id == MSQG_PSIPG || id == MSQG_QFORC) {
@@ -916,11 +988,13 @@ static int max_face_speed(msqg_model *m, List &L, double *umax_host) {
   return MSQG_OK;
 }
 
-extern "C" int msqg_set_const(msqg_model *m) {
+/* set_const up to (not including) comp_q: everything that is local to a tile */
+static int set_const_local(msqg_model *m) {
   CK(cudaSetDevice(m->device));
-  const int n = m->N, nl = m->nl, D = m->depth;
-  const Geom &g = m->g[D];
-  const double Delta = m->p.L0 / n;
+  const int nl = m->nl, D = m->depth;
+  const int tx = m->tnx, ty = m->tny; /* finest tile (whole grid on one GPU) */
+  const size_t tc = (size_t)tx * ty;
+  const double Delta = m->p.L0 / m->N;
   /* sanity checks, qg.h:990-1012 */
   for (int l = 0; l < nl; l++)
     if (m->dhf[l] == 0) FAIL(MSQG_ERR_CONFIG, "thickness = 0: aborting\nCheck the definition of dh in params.in");
@@ -936,27 +1010,27 @@ extern "C" int msqg_set_const(msqg_model *m) {
   m->idh0[nl - 1] = 1. / (m->dhc[nl - 2] * m->dhf[nl - 1]);
   m->idh1[nl - 1] = 0.;
   /* Ro(y), qg.h:1032-1037 */
-  std::vector<double> ro_y(n);
-  for (int j = 0; j < n; j++) {
-    const double y = (j + 0.5) * Delta;
+  std::vector<double> ro_y(ty);
+  for (int j = 0; j < ty; j++) {
+    const double y = (m->y0 + j + 0.5) * Delta;
     ro_y[j] = m->p.varRo > 0 ? m->p.Rom / (1 + m->p.Rom * m->p.beta * (y - 0.5 * m->p.L0)) : m->p.Rom;
   }
   int rc;
   {
-    std::vector<double> h((size_t)n * n);
-    for (int j = 0; j < n; j++)
-      for (int i = 0; i < n; i++) h[(size_t)j * n + i] = ro_y[j];
+    std::vector<double> h(tc);
+    for (int j = 0; j < ty; j++)
+      for (int i = 0; i < tx; i++) h[(size_t)j * tx + i] = ro_y[j];
     if ((rc = pack_to(m, m->ro, h.data()))) return rc;
   }
   /* strl = sq(Fr/Ro), qg.h:1043-1048 (layers 0..nl-2; layer nl-1 stays 0) */
-  std::vector<double> hs((size_t)nl * n * n, 0.);
+  std::vector<double> hs((size_t)nl * tc, 0.);
   bool uniform = true;
   for (int l = 0; l < nl - 1; l++) {
-    const double *fr = &m->h_fr[(size_t)l * n * n];
-    double *s = &hs[(size_t)l * n * n];
-    for (int j = 0; j < n; j++)
-      for (int i = 0; i < n; i++) s[(size_t)j * n + i] = sq(fr[(size_t)j * n + i] / ro_y[j]);
-    for (size_t c = 1; c < (size_t)n * n && uniform; c++) uniform = s[c] == s[0];
+    const double *fr = &m->h_fr[(size_t)l * tc];
+    double *s = &hs[(size_t)l * tc];
+    for (int j = 0; j < ty; j++)
+      for (int i = 0; i < tx; i++) s[(size_t)j * tx + i] = sq(fr[(size_t)j * tx + i] / ro_y[j]);
+    for (size_t c = 1; c < tc && uniform; c++) uniform = s[c] == s[0];
   }
   if ((rc = pack_to(m, m->str, hs.data()))) return rc;
   m->s_uniform = uniform;
@@ -964,7 +1038,9 @@ extern "C" int msqg_set_const(msqg_model *m) {
      constants on the host for the uniform case (same summation order) */
   {
     dim3 b(32, 8);
-    for (int l = D - 1; l >= 1; l--) {
+    /* tiles restrict only their distributed levels: coarser-level stretching enters the kernels
+       through the per-level constants s_lev (uniform stretching) */
+    for (int l = D - 1; l >= (m->agg_level > 1 ? m->agg_level : 1); l--) {
       k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, m->stream>>>(m->str.lev[l + 1], m->str.lev[l], m->g[l + 1], m->g[l], 1., 1);
       m->launches++;
     }
@@ -972,7 +1048,7 @@ extern "C" int msqg_set_const(msqg_model *m) {
   }
   m->s_lev.assign((size_t)(D + 1) * nl, 0.);
   if (uniform) {
-    for (int l = 0; l < nl - 1; l++) m->s_lev[(size_t)D * nl + l] = hs[(size_t)l * n * n];
+    for (int l = 0; l < nl - 1; l++) m->s_lev[(size_t)D * nl + l] = hs[(size_t)l * tc];
     for (int lev = D - 1; lev >= 0; lev--)
       for (int l = 0; l < nl; l++) {
         const double v = m->s_lev[(size_t)(lev + 1) * nl + l];
@@ -981,32 +1057,32 @@ extern "C" int msqg_set_const(msqg_model *m) {
   }
   /* wind forcing table, qg.h:451, host libm so that sin() matches the reference */
   {
-    std::vector<double> w(n);
+    std::vector<double> w(ty);
     const double pi = 3.14159265358979323846, L0 = m->p.L0;
-    for (int j = 0; j < n; j++) {
-      const double y = (j + 0.5) * Delta;
+    for (int j = 0; j < ty; j++) {
+      const double y = (m->y0 + j + 0.5) * Delta;
       w[j] = m->p.tau0 / (m->p.Rom * m->dhf[0]) * sin(2 * pi * y / L0) * sin(pi * y / L0);
     }
-    CK(cudaMemcpyAsync(m->d_wind, w.data(), n * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->d_wind, w.data(), ty * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     CK(cudaStreamSynchronize(m->stream));
   }
-  std::vector<double> sig((size_t)n * n);
+  std::vector<double> sig(tc);
   if (m->p.mode_pv_invert) {
     /* eigmod, qg.h:1053 -> eigmode.h:65-308.  Inputs depend on (Fr, Ro) only. */
     bool fr_uniform = true;
     for (int l = 0; l < nl - 1 && fr_uniform; l++)
-      for (size_t c = 1; c < (size_t)n * n && fr_uniform; c++) fr_uniform = m->h_fr[(size_t)l * n * n + c] == m->h_fr[(size_t)l * n * n];
+      for (size_t c = 1; c < tc && fr_uniform; c++) fr_uniform = m->h_fr[(size_t)l * tc + c] == m->h_fr[(size_t)l * tc];
     m->modes_uniform = fr_uniform && m->p.varRo <= 0;
     if (!m->modes_uniform) FAIL(MSQG_ERR_ARG, "MODE_PV_INVERT with spatially varying Fr/Ro is not supported yet");
     double fr[MSQG_MAXL];
-    for (int l = 0; l < nl - 1; l++) fr[l] = m->h_fr[(size_t)l * n * n];
+    for (int l = 0; l < nl - 1; l++) fr[l] = m->h_fr[(size_t)l * tc];
     if ((rc = eigmod_column(nl, m->dhf, fr, ro_y[0], m->h_cl2m, m->h_cm2l, m->h_ibu))) return rc;
-    std::vector<double> h((size_t)nl * nl * n * n);
-    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < (size_t)n * n; c++) h[(size_t)k * n * n + c] = m->h_cl2m[k];
+    std::vector<double> h((size_t)nl * nl * tc);
+    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_cl2m[k];
     if ((rc = pack_to(m, m->cl2m, h.data()))) return rc;
-    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < (size_t)n * n; c++) h[(size_t)k * n * n + c] = m->h_cm2l[k];
+    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_cm2l[k];
     if ((rc = pack_to(m, m->cm2l, h.data()))) return rc;
-    for (int k = 0; k < nl; k++) for (size_t c = 0; c < (size_t)n * n; c++) h[(size_t)k * n * n + c] = m->h_ibu[k];
+    for (int k = 0; k < nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_ibu[k];
     if ((rc = pack_to(m, m->ibu, h.data()))) return rc;
     /* poisson(): restriction({alpha,lambda}) [BASILISK] -> per-level lambda */
     m->lam_lev.assign((size_t)(D + 1) * nl, 0.);
@@ -1016,14 +1092,22 @@ extern "C" int msqg_set_const(msqg_model *m) {
         const double v = m->lam_lev[(size_t)(lev + 1) * nl + l];
         m->lam_lev[(size_t)lev * nl + l] = avg4(v, v, v, v);
       }
-    for (size_t c = 0; c < (size_t)n * n; c++) sig[c] = fmin(m->p.afilt * sqrt(-1 / m->h_ibu[1]), m->p.Lfmax);
+    for (size_t c = 0; c < tc; c++) sig[c] = fmin(m->p.afilt * sqrt(-1 / m->h_ibu[1]), m->p.Lfmax);
   } else {
-    std::vector<double> rd((size_t)n * n);
+    std::vector<double> rd(tc);
     if ((rc = unpack_from(m, m->rd, rd.data()))) return rc;
-    for (size_t c = 0; c < (size_t)n * n; c++) sig[c] = fmin(m->p.afilt * rd[c], m->p.Lfmax);
+    for (size_t c = 0; c < tc; c++) sig[c] = fmin(m->p.afilt * rd[c], m->p.Lfmax);
   }
   if ((rc = pack_to(m, m->sigfilt, sig.data()))) return rc;
   m->const_set = 1;
+  return MSQG_OK;
+}
+
+/* the rest of set_const: needs psi / psi_pg ghosts (already consistent on one GPU) */
+static int set_const_finish(msqg_model *m) {
+  const int nl = m->nl, D = m->depth;
+  const Geom &g = m->g[D];
+  int rc;
   /* comp_q(pol,qol), qg.h:1092 */
   if ((rc = msqg_comp_q(m))) return rc;
   /* flsrv: zeta_pg = laplacian(psi_pg), qg.h:1094-1097; also its CFL speeds (static) */
@@ -1041,6 +1125,12 @@ extern "C" int msqg_set_const(msqg_model *m) {
     for (int l = 0; l < nl; l++) m->umax_pg[l] = 0.;
   CK(cudaStreamSynchronize(m->stream));
   return MSQG_OK;
+}
+
+extern "C" int msqg_set_const(msqg_model *m) {
+  int rc = set_const_local(m);
+  if (rc) return rc;
+  return set_const_finish(m);
 }
 
 /* ------------------------------------------------------------------ RHS */
@@ -1132,6 +1222,7 @@ extern "C" int msqg_update(msqg_model *m, int q_id, double dtmax, double *dtmax_
 static int generate_noise(msqg_model *m) {
   const int n = m->N, nl = m->nl;
   const double pi = 3.14159265358979323846;
+  if (m->px * m->py > 1) FAIL(MSQG_ERR_ARG, "stochastic forcing is not supported on decomposed grids");
   if (m->h_sstoch.empty()) m->h_sstoch.assign((size_t)nl * n * n, 0.);
   m->h_noise.resize((size_t)nl * n * n);
   for (int i = 0; i < n; i++)
@@ -1441,3 +1532,5 @@ extern "C" int msqg_profile_read(msqg_model *m, double *ms, long *count, long *a
   m->prof_recs.clear(); m->prof_next = 0;
   return MSQG_OK;
 }
+
+#include "dist_impl.cuh"
