@@ -200,6 +200,8 @@ long msqg_group_total_cycles(msqg_group *g);
 long msqg_group_exchanges(msqg_group *g);
 long msqg_group_launches(msqg_group *g);
 int msqg_group_set_stream_sync(msqg_group *g);
+/* CUDA events on the group's stream: which 0 = start, 1 = stop + elapsed ms */
+int msqg_group_timer(msqg_group *g, int which, double *ms);
 int msqg_group_profile_enable(msqg_group *g, int on);
 int msqg_group_profile_read(msqg_group *g, double *ms, long *count, long *aux_sum);
 

@@ -581,6 +581,20 @@ extern "C" int msqg_group_step(msqg_group *G, double t, double tnext_event, doub
   if (tnext_out) *tnext_out = tnext;
   return MSQG_OK;
 }
+/* CUDA-event timing on the group's stream: which = 0 records the start, 1 records the stop,
+ * waits for it and returns the elapsed milliseconds */
+extern "C" int msqg_group_timer(msqg_group *G, int which, double *ms) {
+  static thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CK(cudaSetDevice(G->device));
+  if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); }
+  if (which == 0) { CK(cudaEventRecord(e0, G->stream)); return MSQG_OK; }
+  CK(cudaEventRecord(e1, G->stream));
+  CK(cudaEventSynchronize(e1));
+  float t = 0.f;
+  CK(cudaEventElapsedTime(&t, e0, e1));
+  if (ms) *ms = t;
+  return MSQG_OK;
+}
 extern "C" int msqg_group_profile_enable(msqg_group *G, int on) {
   for (msqg_model *m : G->tiles) { int rc = msqg_profile_enable(m, on); if (rc) return rc; }
   return MSQG_OK;

@@ -42,6 +42,7 @@ def _bind():
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_long
     L.msqg_group_set_stream_sync.argtypes = [vp]
+    L.msqg_group_timer.argtypes = [vp, C.c_int, pd]
     L.msqg_group_profile_enable.argtypes = [vp, C.c_int]
     L.msqg_group_profile_read.argtypes = [vp, pd, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     _bound = True
@@ -131,6 +132,14 @@ class Group:
         self.t = tn.value
         return dt.value
 
+    def timer_start(self):
+        G.check(self.L.msqg_group_timer(self.h, 0, None))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        G.check(self.L.msqg_group_timer(self.h, 1, C.byref(ms)))
+        return ms.value
+
     def profile(self, on=True):
         G.check(self.L.msqg_group_profile_enable(self.h, 1 if on else 0))
 
@@ -152,9 +161,20 @@ class Group:
         return self.L.msqg_group_launches(self.h)
 
 
-def nccl_group(params, agg_n, device):
-    """One tile per rank of the default torch.distributed process group."""
+def broadcast_bytes(payload, nbytes, device=None):
+    """rank 0's `payload` (bytes of length nbytes) to every rank of the default process group"""
     import torch
+    import torch.distributed as dist
+    src = bytearray(payload if dist.get_rank() == 0 else bytes(nbytes))
+    t = torch.frombuffer(src, dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def nccl_group(params, agg_n, device):
+    """One tile per rank of the default torch.distributed process group (torch only carries the NCCL id)."""
     import torch.distributed as dist
     L = _bind()
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -162,9 +182,5 @@ def nccl_group(params, agg_n, device):
     buf = C.create_string_buffer(128)
     if rank == 0:
         G.check(L.msqg_nccl_unique_id(buf))
-    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-    if dist.get_backend() == "nccl":
-        t = t.cuda(device)
-    dist.broadcast(t, 0)
-    uid = bytes(t.cpu().numpy().tobytes())
+    uid = broadcast_bytes(buf.raw, 128, device)
     return Group(params, px, py, agg_n, device, "nccl", rank, world, uid)
