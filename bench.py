@@ -129,7 +129,7 @@ def run_reference(args):
               "%d steps after %d warm-up" % (Ns, args.nl, args.N, args.steps, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "msqg double-gyre %d^2 x nl=%d, layer-coupled multigrid inversion" % (args.N, args.nl),
                        "reference": "CPU oracle (C restatement of msqg, OpenMP; the Basilisk build itself needs qcc, absent here)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -148,13 +148,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the msqg timestep has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, nl = args.N, args.nl
-    m = G.Model(G.make_params(**workload_kw(N, nl)), local)
-    stream = torch.cuda.Stream(device=local)
-    m.set_stream(stream.cuda_stream)
-    m.set(G.PSI, workload_psi(N, nl))
-    m.set_const()
+    cells = float(N) * N * nl
 
     def barrier():
         torch.cuda.synchronize()
@@ -162,8 +159,34 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if world == 1:
+        m = G.Model(G.make_params(**workload_kw(N, nl)), local)
+        stream = torch.cuda.Stream(device=local)
+        m.set_stream(stream.cuda_stream)
+        m.set(G.PSI, workload_psi(N, nl))
+        m.set_const()
+        step = m.step
+        parallelism = "1 GPU"
+    else:
+        # strong scaling: the SAME 4096^2 x 4 grid cut into px x py tiles, one per GPU (reference -D_MPI=1
+        # semantics: Gauss-Seidel inside the tile, NCCL halo exchange after every sweep, coarse levels
+        # below agg_n agglomerated on rank 0)
+        from msqg_b200.dist import nccl_group
+        m = nccl_group(G.make_params(**workload_kw(N, nl)), args.agg_n, local)
+        m.set_global(G.PSI, workload_psi(N, nl))
+        m.set_const()
+        step = m.step
+        parallelism = "%dx%d tiles, NCCL halo exchange, levels < %d agglomerated on rank 0" % (m.px, m.py, args.agg_n)
+
     for _ in range(args.warmup):
-        m.step()
+        step()
     # ---- timed region: K steps, state resident in HBM, per-launch events on the same stream
     barrier()
     sampler = ClockSampler(local)
@@ -171,46 +194,55 @@ def run_ours(args):
         sampler.start()
     m.profile(True)
     c0, l0 = m.total_cycles, m.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
+    if world == 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.steps):
+                step()
+            e1.record(stream)
+        e1.synchronize()
+        ms_total = e0.elapsed_time(e1)
+    else:
+        m.timer_start()
         for _ in range(args.steps):
-            m.step()
-        e1.record(stream)
-    e1.synchronize()
+            step()
+        ms_total = m.timer_stop()
     barrier()
-    ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     prof = m.profile_read()
     m.profile(False)
     cycles, launches = m.total_cycles - c0, m.launches - l0
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = allmax(ms_total)
     ms_step = ms_total / args.steps
-    value = world * N * N * nl * args.steps / (ms_total * 1e-3)
+    value = N * N * nl * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers: q up, step, q down, every step
     esteps = max(1, min(args.steps, 5))
-    hq = torch.empty((nl, N, N), dtype=torch.float64).pin_memory()
+    if world == 1:
+        tile_shape, getq, setq = (nl, N, N), (lambda a: G.check(m.L.msqg_get_field(m.h, G.Q, a))), \
+            (lambda a: G.check(m.L.msqg_set_field(m.h, G.Q, a)))
+    else:
+        _, _, _, _, tnx, tny = m.boxes[0]
+        tile_shape = (nl, tny, tnx)
+        getq = lambda a: G.check(m.L.msqg_group_get_field(m.h, 0, G.Q, a))
+        setq = lambda a: G.check(m.L.msqg_group_set_field(m.h, 0, G.Q, a))
+    hq = torch.empty(tile_shape, dtype=torch.float64).pin_memory()
     hq_np = hq.numpy()
-    G.check(m.L.msqg_get_field(m.h, G.Q, hq_np))
+    getq(hq_np)
     barrier()
     t0 = time.perf_counter()
     for _ in range(esteps):
-        G.check(m.L.msqg_set_field(m.h, G.Q, hq_np))
-        m.step()
-        G.check(m.L.msqg_get_field(m.h, G.Q, hq_np))
+        setq(hq_np)
+        step()
+        getq(hq_np)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = world * N * N * nl * esteps / e2e_s
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_val = N * N * nl * esteps / e2e_s
+    tile_cells = float(np.prod(tile_shape))
     if rank != 0:
         if world > 1:
+            m.close()
             dist.destroy_process_group()
         return
 
@@ -218,10 +250,9 @@ def run_ours(args):
     ab = algorithmic_bytes(nl)
     peak, peak_src = peaks()
     rf = prof["relax_fine"]
-    cells = float(N) * N * nl
     roof = None
     if rf["count"] > 0 and rf["ms"] > 0:
-        alg_bytes_per_launch = ab["relax_sweep"] * cells * (rf["aux"] / rf["count"])
+        alg_bytes_per_launch = ab["relax_sweep"] * tile_cells * (rf["aux"] / rf["count"])
         ach = alg_bytes_per_launch / (rf["ms"] / rf["count"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_relax_lex (finest level)", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": None, "peak_source": peak_src,
@@ -249,15 +280,16 @@ def run_ours(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "msqg double-gyre %d^2 x nl=%d, layer-coupled multigrid inversion (MODE_PV_INVERT 0), "
                                    "tolerance 1e-3, reference-order Gauss-Seidel" % (N, nl),
-                       "N": N, "nl": nl, "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
+                       "N": N, "nl": nl, "parallelism": parallelism,
                        "l2": "inputs larger than L2 (each layer list is %.0f MB)" % (cells * 8 / 1e6),
                        "mg_cycles_per_step": cycles / args.steps},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(cells * 8), "d2h_bytes_per_step": int(cells * 8),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(tile_cells * 8), "d2h_bytes_per_step": int(tile_cells * 8),
                     "steps": esteps, "ms_per_step": e2e_s / esteps * 1e3},
             "roofline": roof, "cpu_baseline": cpu,
             "kernel_ms_per_step": kern_ms,
@@ -265,6 +297,7 @@ def run_ours(args):
                               "peak": peak, "unit": "GB/s", "frac": step_roof / peak}}
     print(json.dumps(line))
     if world > 1:
+        m.close()
         dist.destroy_process_group()
 
 
@@ -277,6 +310,8 @@ def main():
     ap.add_argument("--N", type=int, default=N_DEFAULT)
     ap.add_argument("--nl", type=int, default=NL_DEFAULT)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--agg-n", type=int, default=1024, dest="agg_n",
+                    help="multi-GPU: levels with fewer than agg_n cells per side are agglomerated on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
