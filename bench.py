@@ -140,7 +140,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,7 +178,7 @@ def run_ours(args):
         # strong scaling: the SAME 4096^2 x 4 grid cut into px x py tiles, one per GPU (reference -D_MPI=1
         # semantics: Gauss-Seidel inside the tile, NCCL halo exchange after every sweep, coarse levels
         # below agg_n agglomerated on rank 0)
-        from msqg_b200.dist import nccl_group
+        from msom_b200.dist import nccl_group
         m = nccl_group(G.make_params(**workload_kw(N, nl)), args.agg_n, local)
         m.set_global(G.PSI, workload_psi(N, nl))
         m.set_const()

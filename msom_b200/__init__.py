@@ -1,4 +1,4 @@
-"""msqg_b200 -- B200-native (sm_100a) multilayer quasi-geostrophic timestep.
+"""msom_b200 -- B200-native (sm_100a) multilayer quasi-geostrophic timestep.
 
 Drop-in for the hot path of bderembl/msom's msqg (qg.c + qg.h + layer.h +
 poisson_layer.h + eigmode.h).  Layers:

@@ -2,7 +2,7 @@
 
 Usage is the reference's own (msqg/qg_bfn.py:33-86):
 
-    import msqg_b200.qg as bas
+    import msom_b200.qg as bas
     bas.read_params("params.in"); bas.init_grid(N); bas.set_vars(); bas.set_vars_bfn()
     bas.set_const(); bas.pyp2q(p, q); bas.pystep_bfn(var, F1, direction, flag_q); bas.pyq2p(p, q)
     bas.trash_vars(); bas.trash_vars_bfn()

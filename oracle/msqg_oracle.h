@@ -5,7 +5,7 @@
  * algorithm (bderembl/msom, msqg/qg.h + poisson_layer.h + eigmode.h + layer.h +
  * qg.c, and the Basilisk runtime pieces they call).  Only tests/, the
  * __graft_entry__.smoke() check and bench.py's cpu_baseline / --impl reference
- * legs may load it.  The product (msqg_b200/) never links or calls it.
+ * legs may load it.  The product (msom_b200/) never links or calls it.
  *
  * PARITY UNPINNED: the reference ships no golden vectors or tests and cannot
  * be built here (qcc/Basilisk absent), so this oracle is pinned only by

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  The product package
-(msqg_b200) must never import this module.
+(msom_b200) must never import this module.
 """
 import ctypes as C
 import glob

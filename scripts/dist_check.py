@@ -7,8 +7,8 @@ import numpy as np
 import torch, torch.distributed as dist
 from common import base_kw, synth_psi
 from oracle import oracle as O
-from msqg_b200 import capi as G
-from msqg_b200.dist import nccl_group, grid_for
+from msom_b200 import capi as G
+from msom_b200.dist import nccl_group, grid_for
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)

@@ -3,7 +3,7 @@ sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import ctypes as C
 import numpy as np
 from common import base_kw, synth_psi
-from msqg_b200 import capi as G
+from msom_b200 import capi as G
 N = int(sys.argv[1]); nl = int(sys.argv[2]); nsw = int(sys.argv[3])
 m = G.Model(G.make_params(**base_kw(N, nl)))
 m.set(G.PSI, synth_psi(N, nl)); m.set_const()

@@ -34,7 +34,7 @@ def rel_l2(a, b):
 def make_pair(N, nl, **over):
     """(oracle model, gpu model) with identical parameters and initial psi."""
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     kw = base_kw(N, nl, **over)
     po = O.make_params(**kw)
     pg = G.make_params(**kw)

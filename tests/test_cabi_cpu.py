@@ -12,7 +12,7 @@ import pytest
 from common import base_kw, synth_psi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIBDIR = os.path.join(ROOT, "msqg_b200", "lib")
+LIBDIR = os.path.join(ROOT, "msom_b200", "lib")
 
 
 def _have_gpu():
@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_params_match_oracle(tmp_path):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     f = tmp_path / "params.in"
     f.write_text("#!sh\nN = 128\nnl = 4\nL0 = 80\nRom = 0.025\nEkb = 0.002\nEks = 0.001\ntau0 = 0.0001\nRe = 300\n"
                  "Re4 = 97.6875\nbeta = 0.5\nFr = [0.0024, 0.0050,0.0076]\ndh = [0.05,0.1,0.25,0.6]\nupg = [0.1,0,0,0]\n"
@@ -60,7 +60,7 @@ def test_params_match_oracle(tmp_path):
 
 def test_bas_files_match_oracle(tmp_path):
     from oracle import oracle as O
-    import msqg_b200.qg as bas
+    import msom_b200.qg as bas
     L = bas._L()
     N, nl = 32, 3
     v = synth_psi(N, nl)
@@ -82,7 +82,7 @@ def test_bas_files_match_oracle(tmp_path):
 
 @pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
 def test_compute_fails_loudly_without_gpu(tmp_path):
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     with pytest.raises(G.MsqgError) as e:
         G.Model(G.make_params(**base_kw(64, 2)))
     assert e.value.code == G.ERR_CUDA and "no CPU path" in str(e.value)
@@ -100,7 +100,7 @@ def test_qg_exe_missing_params(tmp_path):
 
 
 def test_argument_validation():
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     for kw, frag in ((dict(nl=1), "nl must be"), (dict(N=100), "power of two"), (dict(sbc=1.0), "sbc"),
                      (dict(nptr=1), "tracers")):
         k = base_kw(64, 2); k.update(kw)

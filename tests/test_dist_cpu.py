@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_grids_and_boxes_tile_the_domain():
-    from msqg_b200.dist import grid_for, tile_box
+    from msom_b200.dist import grid_for, tile_box
     for world in (1, 2, 4, 8):
         px, py = grid_for(world)
         assert px * py == world
@@ -29,7 +29,7 @@ _WORKER = r"""
 import os, sys
 sys.path.insert(0, %r)
 import torch.distributed as dist
-from msqg_b200.dist import broadcast_bytes, grid_for, tile_box
+from msom_b200.dist import broadcast_bytes, grid_for, tile_box
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 payload = bytes(range(128)) if rank == 0 else None

@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 
 def _pair(N, nl, px, py, agg_n, gpu):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
-    from msqg_b200.dist import Group
+    from msom_b200 import capi as G
+    from msom_b200.dist import Group
     kw = base_kw(N, nl)
     mo = O.Model(O.make_params(**kw))
     mo.L.orc_set_decomp(mo.h, px, py, agg_n)
@@ -27,7 +27,7 @@ def _pair(N, nl, px, py, agg_n, gpu):
 @pytest.mark.parametrize("N,nl,px,py,agg_n", [(128, 2, 2, 1, 32), (128, 3, 2, 2, 32), (256, 2, 4, 2, 64), (128, 4, 1, 2, 64)])
 def test_decomposed_invertq_and_steps(gpu, N, nl, px, py, agg_n):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     mo, g, psi = _pair(N, nl, px, py, agg_n, gpu)
     assert np.array_equal(g.get_global(G.Q), mo.get(O.Q))
     z = np.zeros_like(psi)
@@ -47,8 +47,8 @@ def test_decomposed_invertq_and_steps(gpu, N, nl, px, py, agg_n):
 def test_decomposition_differs_from_serial_only_at_solver_tolerance(gpu):
     """block Gauss-Seidel is a different iterate from the serial sweep (poisson_layer.h:55-65) but the
     same solution to the solver tolerance"""
-    from msqg_b200 import capi as G
-    from msqg_b200.dist import Group
+    from msom_b200 import capi as G
+    from msom_b200.dist import Group
     N, nl = 128, 2
     kw = base_kw(N, nl)
     psi = synth_psi(N, nl)

@@ -27,7 +27,7 @@ def test_python_module_matches_oracle(gpu, tmp_path, monkeypatch):
     """read_params -> init_grid -> set_vars -> set_vars_bfn -> set_const -> pyp2q -> pystep_bfn -> pyq2p
     (the call order of msqg/qg_bfn.py) against the oracle's restatement of qg_bfn.h."""
     from oracle import oracle as O
-    import msqg_b200.qg as bas
+    import msom_b200.qg as bas
     N, nl = 64, 3
     monkeypatch.chdir(tmp_path)
     _write_params("params.in", N, nl)
@@ -57,7 +57,7 @@ def test_qg_exe_outputs_match_oracle_run(gpu, tmp_path):
     _write_params(str(wd / "params.in"), N, nl, tend=0.1, dtout=0.05)
     psi = synth_psi(N, nl)
     O.lib().orc_write_bas(str(wd / "p0.bas").encode(), nl, N, 80., psi)
-    exe = os.path.join(ROOT, "msqg_b200", "lib", "qg.e")
+    exe = os.path.join(ROOT, "msom_b200", "lib", "qg.e")
     out = subprocess.run([exe], cwd=str(wd), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Config: N = 64, nl = 2, L0 = 80" in out.stdout and "write file" in out.stdout

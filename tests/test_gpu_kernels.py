@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _model(gpu, N, nl):
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     m = G.Model(G.make_params(**base_kw(N, nl)), gpu)
     m.set(G.PSI, synth_psi(N, nl))
     m.set_const()
@@ -18,7 +18,7 @@ def _model(gpu, N, nl):
 
 
 def test_div_by_is_ieee_division(gpu):
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     rng = np.random.default_rng(7)
     n = 1 << 22
     x = rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 8, n)
@@ -35,7 +35,7 @@ def test_div_by_is_ieee_division(gpu):
                                                (3, 7, 7), (2, 6, 13), (10, 5, 4), (4, 1, 4), (4, 2, 5), (2, 8, 4)])
 def test_relax_matches_oracle(gpu, nl, level, nsweeps):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     N = max(1 << level, 32)
     m = _model(gpu, N, nl)
     n = 1 << level
@@ -60,7 +60,7 @@ def test_relax_matches_oracle(gpu, nl, level, nsweeps):
 @pytest.mark.parametrize("level,nsweeps,lam", [(4, 4, 0.0), (6, 4, -3.7), (7, 2, -50.0), (5, 8, -0.3)])
 def test_relax_scalar_matches_oracle(gpu, level, nsweeps, lam):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     N = max(1 << level, 32)
     m = _model(gpu, N, 2)
     n = 1 << level
@@ -79,7 +79,7 @@ def test_relax_scalar_matches_oracle(gpu, level, nsweeps, lam):
 def test_residual_matches_oracle(gpu, nl, N):
     import ctypes as C
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     m = _model(gpu, N, nl)
     level = int(np.log2(N))
     rng = np.random.default_rng(3)
@@ -101,7 +101,7 @@ def test_residual_matches_oracle(gpu, nl, N):
 @pytest.mark.parametrize("nl,level", [(2, 5), (4, 7)])
 def test_restrict_prolong_match_oracle(gpu, nl, level):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     N = 1 << level
     m = _model(gpu, N, nl)
     rng = np.random.default_rng(11)

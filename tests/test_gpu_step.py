@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("N,nl", [(64, 2), (256, 2), (128, 3), (128, 4), (64, 10)])
 def test_set_const_and_invertq(gpu, N, nl):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     mo, mg, psi = make_pair(N, nl)
     mo.set_const(); mg.set_const()
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q))          # comp_q
@@ -31,7 +31,7 @@ def test_set_const_and_invertq(gpu, N, nl):
 @pytest.mark.parametrize("N,nl", [(256, 2), (128, 3), (128, 4)])
 def test_update_qg(gpu, N, nl):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     mo, mg, _ = make_pair(N, nl)
     mo.set_const(); mg.set_const()
     dto = mo.update(mo.p.DT)
@@ -45,7 +45,7 @@ def test_update_qg(gpu, N, nl):
 def test_steps(gpu, N, nl, nsteps):
     """BASELINE config 1 (256^2 x 2): 1 and 100 steps."""
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     mo, mg, _ = make_pair(N, nl)
     mo.set_const(); mg.set_const()
     for _ in range(nsteps):
@@ -63,7 +63,7 @@ def test_steps(gpu, N, nl, nsteps):
 def test_viscous_and_pg_terms(gpu):
     """Re, Re4, Eks, background flow (upg/vpg), flsrv, q_forc, topography all on."""
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     N, nl = 64, 3
     over = dict(Re=500., Eks=0.001, flsrv=1, upg=[0.1, 0.05, 0.0], vpg=[0.02, 0.0, -0.01])
     mo, mg, psi = make_pair(N, nl, **over)

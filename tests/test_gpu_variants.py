@@ -16,7 +16,7 @@ libc = C.CDLL(None)
 @pytest.mark.parametrize("N,nl,nsteps", [(64, 2, 3), (128, 3, 5), (64, 10, 3)])
 def test_modal_inversion(gpu, N, nl, nsteps):
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     if O._lapack_path() is None:
         pytest.skip("no LAPACK dgeev (eigmode.h:153)")
     mo, mg, psi = make_pair(N, nl, mode_pv_invert=1)
@@ -42,7 +42,7 @@ def test_stochastic_forcing(gpu, N, nl, nsteps):
     """qg_stochastic.h: noise on libc rand() in the reference traversal order, float dts, relaxation term,
     no J(psi,zeta) in the top layer.  Both sides replay the same rand() stream (same seed, run in turn)."""
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     over = dict(stochastic=1, tr_stoch=10., amp_stoch=1.)
     mo, mg, _ = make_pair(N, nl, **over)
     sig = np.full((nl, N, N), 1e-3)
@@ -66,7 +66,7 @@ def test_stochastic_forcing(gpu, N, nl, nsteps):
 def test_plugin_sequence_equals_fused_step(gpu):
     """update_qg / advance_qg called as the predictor-corrector does (msqg/qg.h:922-923 plugin surface)
     give the same bits as the fused msqg_step."""
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     N, nl = 128, 3
     kw = base_kw(N, nl)
     a, b = G.Model(G.make_params(**kw), gpu), G.Model(G.make_params(**kw), gpu)
@@ -87,7 +87,7 @@ def test_full_size_properties(gpu, N, nl, modal):
     """BASELINE configs 2, 3 and the metric shape: q -> psi -> q round trip within the solver tolerance,
     residual statistic consistent, dt ramp of timestep() (DT/11 first), finite fields after a step."""
     from oracle import oracle as O
-    from msqg_b200 import capi as G
+    from msom_b200 import capi as G
     if modal and O._lapack_path() is None:
         pytest.skip("no LAPACK dgeev")
     m = G.Model(G.make_params(**base_kw(N, nl, mode_pv_invert=modal)), gpu)
@@ -116,8 +116,8 @@ def test_ensemble_members_concurrent(gpu):
     give, member by member, the bits of the same member run alone and of the oracle."""
     import time
     from oracle import oracle as O
-    from msqg_b200 import capi as G
-    from msqg_b200.ensemble import Ensemble
+    from msom_b200 import capi as G
+    from msom_b200.ensemble import Ensemble
     N, nl, nmem, nsteps = 64, 3, 4, 3
     kw = base_kw(N, nl, stochastic=1, tr_stoch=10., amp_stoch=1.)
     sig = np.full((nl, N, N), 1e-3)
