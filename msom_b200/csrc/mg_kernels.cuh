@@ -13,6 +13,7 @@
 #pragma once
 #include "layout.cuh"
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #define FULLMASK 0xffffffffu
 
@@ -304,6 +305,7 @@ __global__ void k_correct(double *__restrict__ a, const double *__restrict__ da,
 template <int NL>
 struct RelaxCoef {
   double t0[NL], t2[NL], t1p[NL], rinv[NL]; /* t1p: pivots after forward elimination */
+  double cf[NL], cb[NL];                    /* RN(t0[l]*rinv[l-1]), RN(t2[l]*rinv[l]): quotient estimates of k_relax_ws */
   double msd2;                              /* -sq(Delta) */
 };
 
@@ -593,9 +595,9 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
 }
 
 /* ------------------------------------------------------------------ relax_layer, warp-specialised
- * Same arithmetic, schedule (lane (k,c) does row tau - c - 2k - 1 at step tau) and mailbox protocol
- * as k_relax_lex, but each strip is served by TWO warps so that the warp on the critical path
- * issues nothing but the Thomas recurrence and shared-memory traffic:
+ * Same arithmetic results, schedule (lane (k,c) does row tau - c - 2k - 1 at step tau) and mailbox
+ * protocol as k_relax_lex, but each strip is served by TWO warps so that the warp on the critical
+ * path issues little more than the Thomas recurrence:
  *
  *   compute warp C : W shuffle, Thomas solve, results -> shared-memory ring of its sweep;
  *                    east/north of sweep k come from the ring of sweep k-1 (slot c+1 / slot c),
@@ -603,39 +605,84 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
  *                    its own ring; the strip's west column sits in slot 0 of each sweep ring.
  *   helper warp H  : streams da/res rows HBM -> rings (cp.async, L2-prefetched ahead), polls the
  *                    global mailbox of the left neighbour and deposits entries into slot 0,
- *                    re-arms them, drains slot W of every sweep ring to the right neighbour's
- *                    mailbox and the last sweep's rows to HBM.
+ *                    re-arms them, drains the last sweep's rows to HBM.
  *
- * C and H talk through monotone counters in shared memory (rows loaded, mailbox rows deposited per
- * sweep, rows drained per sweep, steps completed); C loads its next-step inputs speculatively
- * before the recurrence and verifies the counters after it, so nothing but the W shuffle sits
- * between two recurrences.
+ * H publishes, per sweep, ONE number: the last row whose inputs are complete (streamed rows landed,
+ * mailbox row deposited, ring row drained); C loads the inputs of step tau+1 speculatively at the
+ * start of step tau, in the shadow of the recurrence, and checks that number afterwards.
+ *
+ * A step costs (nx + ny) times on the critical path of a sweep, so the dependent chain is kept as
+ * short as IEEE-exact arithmetic allows (measured on B200: fp64 add/mul/fma 8.3 cycles, 64-bit
+ * shuffle 24, scripts/ubench):
+ *   - x/d for the constant pivots d is RN(x/d) by two Newton-Markstein corrections of ANY estimate
+ *     q0 that is within a few ulps (div_fix): the first correction makes it faithful, the second
+ *     correctly rounded.  The estimate is formed in parallel with x itself from pre-multiplied
+ *     constants (cf = t0*r, cb = t2*r, rr = rhs*r), which takes one operation off the chain per
+ *     layer in each direction: 6*(NL-1) + 5 + 6*(NL-1) + 3 dependent operations per step.
+ *   - every out[l] is shuffled / stored as soon as it exists; only out[0] -> W -> rhs[0] is exposed.
+ *   - rings hold layer PAIRS as 16-byte vectors, [row][pair][slot]: a sweep group (quarter warp)
+ *     reads consecutive 16-byte slots, so the 128-bit loads are conflict-free.
+ *   - rows 0 and ny-1 and the first/last W+2K steps run an EDGE instance of the step (ghost
+ *     substitution for south/north); the steady state runs a leaner instance, unrolled twice.
  */
 template <int NL, int K>
 struct WsCfg {
   static_assert(K == 4 || K == 8, "lanes = K sweeps x 32/K columns");
   static constexpr int W = 32 / K, S = W + 1, RC = W + K - 1;
   static constexpr int RIN = 32, R2 = 16;
-  static constexpr int NLP = (NL + 1) & ~1;
-  static constexpr int DROW = NL * S, RROW = NL * RC;
+  static constexpr int NLP = (NL + 1) & ~1;   /* mailbox entry padded to 16 bytes */
+  static constexpr int NV = NLP / 2;          /* 16-byte vectors (layer pairs) per cell */
+  static constexpr int DROW = NV * S, RROW = NV * RC; /* ring row, in vectors */
+  static constexpr int XRS = R2 * DROW + (K == 8 ? 4 : 0); /* sweep-ring stride (K = 8: two groups per quarter warp, skew the banks) */
   static constexpr int TAIL = W + 2 * K - 2; /* steps after which a streamed row is dead */
   static constexpr int NCNT = 32;            /* ints of counters per worker */
-  static constexpr int DOUBLES = RIN * DROW + RIN * RROW + K * R2 * DROW + NCNT / 2;
+  static constexpr int VECS = RIN * DROW + RIN * RROW + K * XRS + NCNT / 4;
+  static constexpr int DOUBLES = 2 * VECS;
   static constexpr size_t smem_per_worker = (size_t)DOUBLES * sizeof(double);
-  static constexpr int EPL_D = (DROW + 31) / 32, EPL_R = (RROW + 31) / 32;
+  static constexpr int EPL_D = (NL * S + 31) / 32, EPL_R = (NL * RC + 31) / 32;
   static constexpr int Q = 32 / K; /* mailbox rows polled per sweep per helper iteration */
-  enum { C_DONE = 0, IN_READY = 1, MAIL_READY = 2, DRAINED = 2 + 8 };
+  enum { C_DONE = 0, LIM = 8 };    /* LIM + k: last row jn whose inputs are complete for sweep k */
 };
+#define WS_INF 0x3fffffff
 
-__device__ __forceinline__ int ld_cnt(const volatile int *p) { return *p; }
+__device__ __forceinline__ int ld_cnt(const volatile int *p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared((const void *)p)));
+  return v;
+}
+__device__ __forceinline__ double2 lds2(unsigned a) {
+  double2 v;
+  asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts2(unsigned a, double x, double y) {
+  asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ double2 lds2_if(bool p, unsigned a) {
+  double2 v = make_double2(0., 0.);
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.volatile.shared.v2.f64 {%0, %1}, [%3];\n}\n"
+               : "+d"(v.x), "+d"(v.y) : "r"((int)p), "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts2_if(bool p, unsigned a, double x, double y) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %0, 0;\n @q st.volatile.shared.v2.f64 [%1], {%2, %3};\n}\n"
+               ::"r"((int)p), "r"(a), "d"(x), "d"(y) : "memory");
+}
+/* RN(x/d) from any estimate q of x/d that is good to a few ulps; r = RN(1/d) */
+__device__ __forceinline__ double div_fix(double x, double q, double d, double r) {
+  double e = __fma_rn(-d, q, x);
+  q = __fma_rn(e, r, q);
+  e = __fma_rn(-d, q, x);
+  return __fma_rn(e, r, q);
+}
 
 template <int NL, int K, int WPC, bool TILE>
 __global__ void __launch_bounds__(64 * WPC)
 k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   using Cfg = WsCfg<NL, K>;
   constexpr int W = Cfg::W, S = Cfg::S, RC = Cfg::RC, RIN = Cfg::RIN, R2 = Cfg::R2;
-  constexpr int NLP = Cfg::NLP, DROW = Cfg::DROW, RROW = Cfg::RROW, Q = Cfg::Q;
-  extern __shared__ double smem[];
+  constexpr int NLP = Cfg::NLP, NV = Cfg::NV, DROW = Cfg::DROW, RROW = Cfg::RROW, XRS = Cfg::XRS, Q = Cfg::Q;
+  extern __shared__ double2 smem2[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool helper = warp >= WPC;
   const int wl = helper ? warp - WPC : warp; /* worker slot inside the CTA */
@@ -645,14 +692,14 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   const int r_first = bint ? -1 : 0, r_last = tint ? ny : ny - 1; /* rows of the iterate that are streamed */
   const int w = blockIdx.x * WPC + wl;
   const int nworkers = (nx + K - 1 + W - 1) / W;
-  double *base = smem + (size_t)wl * Cfg::DOUBLES;
-  double *IN = base;                    /* [RIN][NL][S]  initial iterate, slot s <-> column w*W + s */
-  double *RES = IN + RIN * DROW;        /* [RIN][NL][RC] rc <-> column w*W - (K-1) + rc */
-  double *XR = RES + RIN * RROW;        /* K rings [R2][NL][S]: slot 0 west column, slot c+1 lane c */
-  volatile int *cnt = (volatile int *)(XR + K * R2 * DROW);
+  double2 *base = smem2 + (size_t)wl * Cfg::VECS;
+  double2 *IN = base;                   /* [RIN][NV][S]  initial iterate, slot s <-> column w*W + s */
+  double2 *RES = IN + RIN * DROW;       /* [RIN][NV][RC] rc <-> column w*W - (K-1) + rc */
+  double2 *XR = RES + RIN * RROW;       /* K rings [R2][NV][S]: slot 0 west column, slot c+1 lane c */
+  volatile int *cnt = (volatile int *)(XR + K * XRS);
   const int nsw = A.nsweeps;
   const int kf = nsw - 1;
-  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE) ? -2 : (lane == Cfg::IN_READY ? r_first : 0);
+  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE) ? 0 : -1000;
   __syncthreads();
   if (w >= nworkers) return;
   const int pitch = A.g.pitch;
@@ -667,140 +714,147 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     const bool k0 = (k == 0);
     const bool left = (i == 0) && !lint, right = (i == nx - 1) && !rint;
     const bool use_mail = (c == 0) && (w > 0 || lint);
-    const bool use_mail_n = use_mail && k > 0;
-    const int prodcol = w * W - 1 - k;
-    const bool mb_reader = use_mail && k < nsw && (w > 0 ? (prodcol >= 0 && prodcol < nx) : (k == 0));
+    const bool lr_any = __any_sync(FULLMASK, left || right);
     const bool wr_valid = has_consumer && (w * W + W - 1 - k) >= 0 && (w * W + W - 1 - k) < nx;
-    const bool drained_by_h = col_ok && (k == kf);
     const bool mb_writer = wr_valid && c == W - 1 && col_ok;
-    unsigned long long *mo = A.mailbox + ((size_t)w * K + k) * (size_t)ny * NLP + (long long)(-2 - c - 2 * k - 1) * NLP;
-    /* inputs of sweep k: ring of sweep k-1 (sweep 0: the streamed initial iterate); slot c north, slot c+1 east */
-    const double *in_l = (k0 ? IN : XR + (size_t)(k - 1) * R2 * DROW) + c;
+    const bool st_lane = (k < nsw);
+    unsigned long long *mo = A.mailbox + ((size_t)w * K + k) * (size_t)ny * NLP; /* + j*NLP */
+    /* shared-memory byte addresses */
+    const unsigned a_in = (unsigned)__cvta_generic_to_shared(k0 ? IN : XR + (size_t)(k - 1) * XRS) + 16u * c;
     const int in_mask = k0 ? RIN - 1 : R2 - 1;
-    double *ring = XR + (size_t)(k < K ? k : 0) * R2 * DROW;       /* own ring: slot 0 west column (from H), slot c+1 results */
-    const double *res_l = RES + (c - k + K - 1);
-    const bool wait_first = __shfl_sync(FULLMASK, (int)mb_reader, 0) != 0;
+    const unsigned a_ring = (unsigned)__cvta_generic_to_shared(XR + (size_t)(k < K ? k : 0) * XRS);
+    const unsigned a_res = (unsigned)__cvta_generic_to_shared(RES) + 16u * (c - k + K - 1);
+    const volatile int *plim = cnt + Cfg::LIM + k;
 
-    double cur[NL], En[NL], Nn[NL], cold[NL], bn[NL], wm[NL];
+    /* loop-carried state: the right-hand side of the coming step, complete (west value included),
+       and the raw north values loaded for it (= pre-sweep centre of the step after) */
+    double rhs[NL], Nraw[NL];
 #pragma unroll
-    for (int l = 0; l < NL; l++) { cur[l] = En[l] = Nn[l] = cold[l] = bn[l] = wm[l] = 0.; }
+    for (int l = 0; l < NL; l++) rhs[l] = Nraw[l] = 0.;
     long long t_start = 0, n_spins = 0;
     if (A.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const int T = ny + W + 2 * K - 2;
-    int waited = 0;
-#pragma unroll 1
-    for (int tau = -2; tau < T;) {
+
+    /* EDGE: rows 0 / ny-1 may occur (ghost substitution for south/north); LR: some lane of the warp
+       sits on a physical left/right boundary */
+    auto step = [&](auto edge_tag, auto lr_tag, const int tau) {
+      constexpr bool EDGE = decltype(edge_tag)::value, LR = decltype(lr_tag)::value;
       const int j = tau - c - 2 * k - 1;
       const int jn = j + 1;
-      const bool row_ok = (unsigned)j < (unsigned)ny;
-      const bool nrow_ok = (unsigned)jn < (unsigned)ny;
-      __syncwarp();
-      /* ---- (A) the only work ahead of the recurrence: west value and right-hand side */
-      double rhs[NL], out[NL], Wv[NL];
+      /* ---- (B) inputs of the next step (row jn), speculatively; the guard is read first */
+      const int lim = ld_cnt(plim);
+      double2 e2[NV], n2[NV], b2[NV], w2[NV], s2[NV];
+      auto load_inputs = [&]() {
+        const unsigned pe = a_in + 16u * (unsigned)((jn & in_mask) * DROW + 1);
+        const unsigned pn = a_in + 16u * (unsigned)(((jn + 1) & in_mask) * DROW);
+        const unsigned pb = a_res + 16u * (unsigned)((jn & (RIN - 1)) * RROW);
+        const unsigned pw = a_ring + 16u * (unsigned)((jn & (R2 - 1)) * DROW);
 #pragma unroll
-      for (int l = 0; l < NL; l++) {
-        const double wsh = __shfl_up_sync(FULLMASK, cur[l], 1);
-        Wv[l] = use_mail ? wm[l] : wsh;
-        double r = C.msd2 * bn[l];
-        r += En[l] + Wv[l];
-        r += Nn[l] + cur[l];
-        rhs[l] = r;
+        for (int v = 0; v < NV; v++) {
+          e2[v] = lds2(pe + 16u * (v * S));
+          n2[v] = lds2(pn + 16u * (v * S));
+          b2[v] = lds2(pb + 16u * (v * RC));
+          w2[v] = lds2_if(use_mail, pw + 16u * (v * S));
+          if (EDGE && TILE) s2[v] = lds2(a_in + 16u * (unsigned)(((-1) & in_mask) * DROW + v * S)); /* stored halo row -1 */
+          else s2[v] = make_double2(0., 0.);
+        }
+      };
+      load_inputs();
+      /* ---- (C) Thomas recurrence (msqg/poisson_layer.h:137-146), results leave as they appear */
+      const unsigned po = a_ring + 16u * (unsigned)((j & (R2 - 1)) * DROW + c + 1);
+      const bool row_ok = EDGE ? ((unsigned)j < (unsigned)ny) : true;
+      const bool do_st = row_ok && st_lane;
+      const bool do_mb = row_ok && mb_writer;
+      unsigned long long *mrow = mo + (long long)j * NLP;
+      double out[NL], wsh[NL];
+      if (NL == 1) {
+        out[0] = div_by(rhs[0], C.t1p[0], C.rinv[0]);
+      } else {
+        double q = 0.;
+#pragma unroll
+        for (int l = 1; l < NL; l++) {
+          const double x = C.t0[l] * rhs[l - 1];
+          const double q0 = rhs[l - 1] * C.cf[l];
+          q = div_fix(x, q0, C.t1p[l - 1], C.rinv[l - 1]);
+          if (l < NL - 1) rhs[l] -= q;
+        }
+        {
+          const double rr = rhs[NL - 1] * C.rinv[NL - 1]; /* off the chain: rhs before elimination */
+          const double x = rhs[NL - 1] - q;
+          const double q0 = __fma_rn(-q, C.rinv[NL - 1], rr);
+          out[NL - 1] = div_fix(x, q0, C.t1p[NL - 1], C.rinv[NL - 1]);
+        }
       }
-      const bool edge = col_ok && ((row_ok && (left || right)) || j == 0 || j == ny - 1);
-      if (__any_sync(FULLMASK, edge) || tau == -2) {
+#pragma unroll
+      for (int l = NL - 1; l >= 0; l--) {
+        if (l < NL - 1) {
+          const double rr = rhs[l] * C.rinv[l];
+          const double m = C.t2[l] * out[l + 1];
+          const double q0 = __fma_rn(-C.cb[l], out[l + 1], rr);
+          const double x = rhs[l] - m;
+          out[l] = div_fix(x, q0, C.t1p[l], C.rinv[l]);
+        }
+        wsh[l] = __shfl_up_sync(FULLMASK, out[l], 1);
+        if ((l & 1) == 0) { /* layer pair (l, l+1) complete */
+          const double hi = (l + 1 < NL) ? out[l + 1 < NL ? l + 1 : l] : 0.;
+          sts2_if(do_st, po + 16u * ((l >> 1) * S), out[l], hi);
+          st_mail2_if(do_mb, mrow + l, (unsigned long long)__double_as_longlong(out[l]), (unsigned long long)__double_as_longlong(hi));
+        }
+      }
+      /* ---- (D) right-hand side of the next step (speculative, redone below if (B) was too early);
+         r = -sq(Delta)*b; r += E + W; r += N + S in the reference's association order */
+      double cold[NL];
+#pragma unroll
+      for (int l = 0; l < NL; l++) cold[l] = Nraw[l];
+      auto next_rhs = [&]() {
 #pragma unroll
         for (int l = 0; l < NL; l++) {
-          const double g = -cold[l];
-          const double aw = left ? g : Wv[l];
-          const double ae = right ? g : En[l];
-          /* bottom/top: physical -> -(pre-sweep centre); internal -> stored halo row -1 / ny of the iterate */
-          const double sgh = ((volatile const double *)in_l)[(size_t)((-1) & in_mask) * DROW + l * S];
-          const double as = (j == 0) ? (bint ? sgh : g) : cur[l];
-          const double an = (j == ny - 1 && !tint) ? g : Nn[l];
-          double r = C.msd2 * bn[l];
+          const double ev = (l & 1) ? e2[l >> 1].y : e2[l >> 1].x;
+          const double nv = (l & 1) ? n2[l >> 1].y : n2[l >> 1].x;
+          const double bv = (l & 1) ? b2[l >> 1].y : b2[l >> 1].x;
+          const double wv = (l & 1) ? w2[l >> 1].y : w2[l >> 1].x;
+          const double sv = (l & 1) ? s2[l >> 1].y : s2[l >> 1].x;
+          const double g = -cold[l]; /* dirichlet ghost: -(pre-sweep centre of the next step's cell) */
+          double aw, ae, as, an;
+          if (LR) { aw = left ? g : (use_mail ? wv : wsh[l]); ae = right ? g : ev; }
+          else { aw = use_mail ? wv : wsh[l]; ae = ev; }
+          if (EDGE) { as = (jn == 0) ? ((TILE && bint) ? sv : g) : out[l]; an = (jn == ny - 1 && !tint) ? g : nv; }
+          else { as = out[l]; an = nv; }
+          double r = C.msd2 * bv;
           r += ae + aw;
           r += an + as;
           rhs[l] = r;
+          Nraw[l] = nv;
         }
-      }
-      /* ---- (B) next step's inputs, independent of this step's result: issued in the shadow of
-         the recurrence.  Counters are read BEFORE the data they guard and checked afterwards. */
-      const int c_in = ld_cnt(cnt + Cfg::IN_READY);
-      const int c_mail = ld_cnt(cnt + Cfg::MAIL_READY + (k < 8 ? k : 0));
-      const int c_dr = ld_cnt(cnt + Cfg::DRAINED + (k < 8 ? k : 0));
-      asm volatile("" ::: "memory");
-      double En2[NL], Nn2[NL], bn2[NL], wm2[NL];
-      {
-        const double *pe = in_l + (size_t)(jn & in_mask) * DROW + 1;
-        const double *pn = in_l + (size_t)((jn + 1) & in_mask) * DROW;
-        const double *pb = res_l + (size_t)(jn & (RIN - 1)) * RROW;
-        const double *pw = ring + (size_t)(jn & (R2 - 1)) * DROW;
-#pragma unroll
-        for (int l = 0; l < NL; l++) {
-          En2[l] = ((volatile const double *)pe)[l * S];
-          Nn2[l] = ((volatile const double *)pn)[l * S];
-          bn2[l] = ((volatile const double *)pb)[l * RC];
-          wm2[l] = ((volatile const double *)pw)[l * S];
-        }
-      }
-      const int need_in = (jn >= -1 && jn < ny) ? min(jn + 1, r_last) + 1 : r_first;
-      bool ok = (c_in >= need_in);
-      if (mb_reader && nrow_ok) ok = ok && (c_mail > jn);
-      if (drained_by_h && nrow_ok) ok = ok && (c_dr > jn - R2);
-      /* ---- (C) Thomas recurrence */
-#pragma unroll
-      for (int l = 1; l < NL; l++) rhs[l] -= div_by(C.t0[l] * rhs[l - 1], C.t1p[l - 1], C.rinv[l - 1]);
-      out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
-#pragma unroll
-      for (int l = NL - 2; l >= 0; l--) out[l] = div_by(rhs[l] - C.t2[l] * out[l + 1], C.t1p[l], C.rinv[l]);
-      /* ---- (D) results: last sweep -> ring for H; east column -> right neighbour's mailbox */
-      if (row_ok && k < nsw) {
-        double *po = ring + (size_t)(j & (R2 - 1)) * DROW + c + 1;
-#pragma unroll
-        for (int l = 0; l < NL; l++) po[l * S] = out[l];
-      }
-      if (row_ok && mb_writer) {
-#pragma unroll
-        for (int l = 0; l < NLP; l += 2) {
-          const unsigned long long v0 = (unsigned long long)__double_as_longlong(out[l]);
-          const unsigned long long v1 = (l + 1 < NL) ? (unsigned long long)__double_as_longlong(out[l + 1]) : 0ull;
-          asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(mo + l), "l"(v0), "l"(v1) : "memory");
-        }
-      }
-      __syncwarp();
-      if (lane == 0) cnt[Cfg::C_DONE] = tau + 1;
+      };
+      next_rhs();
       /* ---- (E) was the speculation of (B) valid? */
-      if (!__all_sync(FULLMASK, ok)) {
-        if (tau == 0 && wait_first && ++waited < SPIN_LIMIT) {
-          /* first mailbox row not here yet: stay hot by repeating the priming pair tau = -1, 0 */
-          if (__all_sync(FULLMASK, c_in >= need_in)) { tau = -1; mo -= NLP; continue; }
-        }
+      if (!__all_sync(FULLMASK, jn <= lim)) {
         int spins = 0;
-        while (!__all_sync(FULLMASK, ok)) {
+        while (!__all_sync(FULLMASK, jn <= ld_cnt(plim))) {
           if (++spins > SPIN_LIMIT) { if (lane == 0) *A.err = 1; break; }
-          ok = (ld_cnt(cnt + Cfg::IN_READY) >= need_in);
-          if (mb_reader && nrow_ok) ok = ok && (ld_cnt(cnt + Cfg::MAIL_READY + k) > jn);
-          if (drained_by_h && nrow_ok) ok = ok && (ld_cnt(cnt + Cfg::DRAINED + k) > jn - R2);
         }
         n_spins += spins;
         __syncwarp();
-        const double *pe = in_l + (size_t)(jn & in_mask) * DROW + 1;
-        const double *pn = in_l + (size_t)((jn + 1) & in_mask) * DROW;
-        const double *pb = res_l + (size_t)(jn & (RIN - 1)) * RROW;
-        const double *pw = ring + (size_t)(jn & (R2 - 1)) * DROW;
-#pragma unroll
-        for (int l = 0; l < NL; l++) {
-          En2[l] = ((volatile const double *)pe)[l * S];
-          Nn2[l] = ((volatile const double *)pn)[l * S];
-          bn2[l] = ((volatile const double *)pb)[l * RC];
-          wm2[l] = ((volatile const double *)pw)[l * S];
-        }
+        load_inputs();
+        next_rhs();
       }
-#pragma unroll
-      for (int l = 0; l < NL; l++) { cur[l] = out[l]; cold[l] = Nn[l]; En[l] = En2[l]; Nn[l] = Nn2[l]; bn[l] = bn2[l]; wm[l] = wm2[l]; }
-      tau++;
-      mo += NLP;
-    }
+      /* ---- (F) publish progress: results of this step are in the rings */
+      __syncwarp();
+      if (lane == 0) cnt[Cfg::C_DONE] = tau + 1;
+    };
+
+    auto run = [&](auto lr_tag) {
+      int tau = -1; /* step -1 only loads: the pre-sweep value of row 0 is the ghost source of the first row */
+      const int t_fast0 = min(T, W + 2 * K - 2), t_fast1 = ny - 2; /* FAST steps: [t_fast0, t_fast1] */
+#pragma unroll 1
+      for (; tau < t_fast0; tau++) step(std::true_type{}, lr_tag, tau);
+#pragma unroll 1
+      for (; tau + 1 <= t_fast1; tau += 2) { step(std::false_type{}, lr_tag, tau); step(std::false_type{}, lr_tag, tau + 1); }
+#pragma unroll 1
+      for (; tau < T; tau++) step(std::true_type{}, lr_tag, tau);
+    };
+    if (lr_any) run(std::true_type{}); else run(std::false_type{});
     if (A.dbg) {
       long long t_end;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -815,32 +869,31 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     bool ok_d[Cfg::EPL_D], ok_r[Cfg::EPL_R];
 #pragma unroll
     for (int q = 0; q < Cfg::EPL_D; q++) {
-      const int e = lane + 32 * q, l = e / S, x = w * W + e % S;
-      ok_d[q] = (e < DROW) && (x < nx || (x == nx && rint));
+      const int e = lane + 32 * q, l = e / S, xs = e % S, x = w * W + xs;
+      ok_d[q] = (e < NL * S) && (x < nx || (x == nx && rint));
       ld_d[q] = A.da + (size_t)(ok_d[q] ? l : 0) * plane + GIDX(pitch, 0, ok_d[q] ? x : 0);
-      st_d[q] = (unsigned)__cvta_generic_to_shared(IN + e);
+      st_d[q] = (unsigned)__cvta_generic_to_shared(IN) + 16u * (unsigned)((l >> 1) * S + xs) + 8u * (l & 1);
     }
 #pragma unroll
     for (int q = 0; q < Cfg::EPL_R; q++) {
-      const int e = lane + 32 * q, l = e / RC, x = w * W - (K - 1) + e % RC;
-      ok_r[q] = (e < RROW) && (x >= 0) && (x < nx);
+      const int e = lane + 32 * q, l = e / RC, xs = e % RC, x = w * W - (K - 1) + xs;
+      ok_r[q] = (e < NL * RC) && (x >= 0) && (x < nx);
       ld_r[q] = A.res + (size_t)(ok_r[q] ? l : 0) * plane + GIDX(pitch, 0, ok_r[q] ? x : 0);
-      st_r[q] = (unsigned)__cvta_generic_to_shared(RES + e);
+      st_r[q] = (unsigned)__cvta_generic_to_shared(RES) + 16u * (unsigned)((l >> 1) * RC + xs) + 8u * (l & 1);
     }
     constexpr int PF = 48;
     /* mailbox lanes: (kk, q) */
     const int kk = lane / Q, q = lane % Q;
     const bool rd_ghost = (w == 0) && lint && kk == 0; /* west column = stored halo column -1 of the iterate */
     const bool rd_valid = rd_ghost || ((w > 0) && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
-    const bool wr_valid = has_consumer && kk < nsw && (w * W + W - 1 - kk) >= 0 && (w * W + W - 1 - kk) < nx;
     const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)ny * NLP;
-    double *ringk = XR + (size_t)kk * R2 * DROW;
+    const unsigned a_ringk = (unsigned)__cvta_generic_to_shared(XR + (size_t)kk * XRS);
+    const unsigned a_ringf = (unsigned)__cvta_generic_to_shared(XR + (size_t)kf * XRS);
     const unsigned gmask = (Q == 32) ? 0xffffffffu : (((1u << Q) - 1u) << (kk * Q));
     int mail_rd = rd_valid ? 0 : ny;  /* rows deposited for sweep kk */
     int da_dr = 0;                    /* rows of the last sweep written to HBM */
     int in_issued = r_first, h1 = r_first, h2 = r_first, h3 = r_first, in_done = r_first; /* rows issued now / 1,2,3 iterations ago */
     constexpr int EPL_O = (NL * W + 31) / 32;
-    (void)wr_valid;
     int idle = 0;
 #pragma unroll 1
     for (long long it = 0;; it++) {
@@ -849,7 +902,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       /* ---- (1) mailbox in: Q rows of each sweep per iteration (the latency-critical hand-off) */
       {
         const int r = mail_rd + q;
-        const bool can = rd_valid && r < ny && (cd >= r - R2 + 2 * kk + 2);
+        const bool can = rd_valid && r < ny && (cd >= r - R2 + 2 * kk + 3);
         unsigned long long v[NLP];
 #pragma unroll
         for (int l = 0; l < NLP; l++) v[l] = MAIL_EMPTY;
@@ -865,17 +918,17 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         }
         /* ---- (2) meanwhile: stream up to 2 rows; rows issued three iterations ago have landed */
         {
-          const int rmax = min(r_last, cd + RIN - Cfg::TAIL - 1);
+          const int rmax = min(r_last, cd + RIN - Cfg::TAIL - 2);
           const int b1 = min(in_issued + 2, rmax + 1);
           for (int r2 = in_issued; r2 < b1; r2++) {
             const unsigned ro = (unsigned)(r2 & (RIN - 1));
             const size_t go = (size_t)r2 * pitch;
 #pragma unroll
             for (int u = 0; u < Cfg::EPL_D; u++)
-              if (ok_d[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_d[u] + ro * (DROW * 8)), "l"(ld_d[u] + go));
+              if (ok_d[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_d[u] + ro * (DROW * 16)), "l"(ld_d[u] + go));
 #pragma unroll
             for (int u = 0; u < Cfg::EPL_R; u++)
-              if (ok_r[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_r[u] + ro * (RROW * 8)), "l"(ld_r[u] + go));
+              if (ok_r[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_r[u] + ro * (RROW * 16)), "l"(ld_r[u] + go));
             const int rp = r2 + PF;
             if (rp < ny) {
               const size_t gp = (size_t)rp * pitch;
@@ -894,7 +947,6 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         }
         /* ---- (3) last sweep's rows -> HBM, up to 2 rows */
         {
-          const double *ringf = XR + (size_t)kf * R2 * DROW;
           int done = 0;
           for (; done < 2; done++) {
             const int r3 = da_dr + done;
@@ -903,8 +955,12 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
             for (int u = 0; u < EPL_O; u++) {
               const int e = lane + 32 * u, l = e / W, cs = e % W;
               const int col = w * W + cs - kf;
-              if (e < NL * W && col >= 0 && col < nx)
-                A.da[(size_t)l * plane + GIDX(pitch, r3, col)] = ((volatile const double *)ringf)[(size_t)(r3 & (R2 - 1)) * DROW + l * S + cs + 1];
+              if (e < NL * W && col >= 0 && col < nx) {
+                double val;
+                asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(val)
+                             : "r"(a_ringf + 16u * (unsigned)((r3 & (R2 - 1)) * DROW + (l >> 1) * S + cs + 1) + 8u * (l & 1)));
+                A.da[(size_t)l * plane + GIDX(pitch, r3, col)] = val;
+              }
             }
           }
           da_dr += done;
@@ -917,9 +973,10 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         const unsigned bal = (__ballot_sync(FULLMASK, valid) & gmask) >> (kk * Q);
         const int adv = __ffs(~bal) - 1;
         if (q < adv) {
-          double *d = ringk + (size_t)(r & (R2 - 1)) * DROW;
+          const unsigned d = a_ringk + 16u * (unsigned)((r & (R2 - 1)) * DROW);
 #pragma unroll
-          for (int l = 0; l < NL; l++) d[l * S] = __longlong_as_double((long long)v[l]);
+          for (int l = 0; l < NLP; l += 2)
+            sts2(d + 16u * ((l >> 1) * S), __longlong_as_double((long long)v[l]), __longlong_as_double((long long)v[l + 1]));
           unsigned long long *p = (unsigned long long *)mb_in + (size_t)r * NLP;
           if (!rd_ghost) {
 #pragma unroll
@@ -930,14 +987,17 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         mail_rd += adv;
         if (adv > 0) progress = true;
       }
-      /* ---- publish: mailbox rows, streamed rows, drained rows */
+      /* ---- publish: per sweep, the last row whose inputs are complete */
+      if (h3 > in_done) { in_done = h3; progress = true; }
       __syncwarp();
       __threadfence_block();
-      if (q == 0 && kk < 8) {
-        cnt[Cfg::MAIL_READY + kk] = mail_rd;
-        cnt[Cfg::DRAINED + kk] = (kk == kf) ? da_dr : ny;
+      if (q == 0 && kk < K) {
+        int lim = (in_done > r_last) ? WS_INF : in_done - 2;
+        lim = min(lim, (mail_rd >= ny) ? WS_INF : mail_rd - 1);
+        if (kk == kf) lim = min(lim, (da_dr >= ny - R2) ? WS_INF : da_dr + R2 - 1);
+        if (kk >= nsw) lim = WS_INF;
+        cnt[Cfg::LIM + kk] = lim;
       }
-      if (h3 > in_done) { in_done = h3; progress = true; if (lane == 0) cnt[Cfg::IN_READY] = in_done; }
       /* ---- done? */
       const bool fin = (in_done > r_last) && (mail_rd >= ny) && (da_dr >= ny);
       if (__all_sync(FULLMASK, fin)) break;

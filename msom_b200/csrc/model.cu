@@ -559,6 +559,7 @@ static RelaxCoef<NL> relax_coef_layers(msqg_model *m, int lev) {
     for (ll = 1; ll < NL; ll++) t1[ll] -= t0[ll] * t2[ll - 1] / t1[ll - 1];
   }
   for (int l = 0; l < NL; l++) { C.t0[l] = t0[l]; C.t2[l] = t2[l]; C.t1p[l] = t1[l]; C.rinv[l] = 1. / t1[l]; }
+  for (int l = 0; l < NL; l++) { C.cf[l] = l > 0 ? t0[l] * C.rinv[l - 1] : 0.; C.cb[l] = t2[l] * C.rinv[l]; }
   C.msd2 = -sq(Delta);
   return C;
 }
@@ -568,7 +569,7 @@ static RelaxCoef<1> relax_coef_scalar(msqg_model *m, int lev, double lambda) {
   const double Delta = m->g[lev].Delta;
   double d = -lambda * sq(Delta);
   d += 1. + 1.; d += 1. + 1.;
-  C.t0[0] = 0.; C.t2[0] = 0.; C.t1p[0] = d; C.rinv[0] = 1. / d;
+  C.t0[0] = 0.; C.t2[0] = 0.; C.t1p[0] = d; C.rinv[0] = 1. / d; C.cf[0] = C.cb[0] = 0.;
   C.msd2 = -sq(Delta);
   return C;
 }

@@ -21,14 +21,5 @@ st = (out[:, 0] - t0) / 1e3; en = (out[:, 1] - t0) / 1e3
 print("N=%d nl=%d nsweeps=%d workers=%d steps/worker=%d" % (N, nl, nsw, nw, N + W + K - 1))
 for w in list(range(0, min(nw, 6))) + list(range(nw // 2, nw // 2 + 2)) + [nw - 2, nw - 1]:
     print(" w=%4d start %9.1f us end %9.1f us dur %9.1f us spins %d" % (w, st[w], en[w], en[w] - st[w], out[w, 2]))
-te = (ext[:, :6] - t0) / 1e3
-print('times (us) at tau=1,2,4,8,16,64 for workers 0..5 and 200,201:')
-for w in list(range(6)) + [200, 201]:
-    print('  w=%3d' % w, np.round(te[w], 2))
-st = (ext[:, 6] - t0) / 1e3; ob = (ext[:, 7] - t0) / 1e3
-print('producer store of entry(0,row0) at:', np.round(st[:5], 2), ' consumer w+1 observed at:', np.round(ob[1:6], 2))
-print('handoff latency (us): median %.2f' % np.median((ob[1:] - st[:-1])[:400]))
-d16 = np.diff(te[:, 4])
-print('step-16 diffs: median %.2f' % np.median(d16))
 print("end diffs: median %.2f us" % np.median(np.diff(en)))
 print("total %.1f us; worker0 %.3f us/step; mean end-lag between workers %.2f us" % (en.max(), (en[0] - st[0]) / (N + W + K - 1), (en[-1] - en[0]) / (nw - 1)))
