@@ -650,6 +650,14 @@ __device__ __forceinline__ int ld_cnt(const volatile int *p) {
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared((const void *)p)));
   return v;
 }
+__device__ __forceinline__ int ld_cnt_a(unsigned a) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_cnt_if(bool p, unsigned a, int v) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %0, 0;\n @q st.volatile.shared.s32 [%1], %2;\n}\n" ::"r"((int)p), "r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ double2 lds2(unsigned a) {
   double2 v;
   asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
@@ -716,82 +724,90 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     const bool use_mail = (c == 0) && (w > 0 || lint);
     const bool lr_any = __any_sync(FULLMASK, left || right);
     const bool wr_valid = has_consumer && (w * W + W - 1 - k) >= 0 && (w * W + W - 1 - k) < nx;
-    const bool mb_writer = wr_valid && c == W - 1 && col_ok;
+    /* Neighbouring strips of the SAME CTA hand their boundary column over through shared memory:
+       the consumer reads slot W of the producer's sweep rings directly, guarded by the producer's
+       step counter (and the producer checks the consumer's counter before it reuses a ring row).
+       Only the first strip of a CTA goes through the global mailbox and its helper warp. */
+    const bool din = (wl > 0), dout = has_consumer && (wl + 1 < WPC);
+    const bool mb_writer = wr_valid && c == W - 1 && col_ok && !dout;
     const bool st_lane = (k < nsw);
     unsigned long long *mo = A.mailbox + ((size_t)w * K + k) * (size_t)ny * NLP; /* + j*NLP */
     /* shared-memory byte addresses */
     const unsigned a_in = (unsigned)__cvta_generic_to_shared(k0 ? IN : XR + (size_t)(k - 1) * XRS) + 16u * c;
     const int in_mask = k0 ? RIN - 1 : R2 - 1;
     const unsigned a_ring = (unsigned)__cvta_generic_to_shared(XR + (size_t)(k < K ? k : 0) * XRS);
+    const double2 *XRL = XR - Cfg::VECS; /* sweep rings of the left neighbour in this CTA (din only) */
+    /* west column of sweep k: slot 0 of the own ring (mailbox deposits) or slot W of the neighbour's ring */
+    const unsigned a_west = din ? (unsigned)__cvta_generic_to_shared(XRL + (size_t)(k < K ? k : 0) * XRS) + 16u * W : a_ring;
+    /* north of lane c = 0, sweep k > 0, is the west column of sweep k-1 */
+    const unsigned a_north = (din && c == 0 && !k0) ? (unsigned)__cvta_generic_to_shared(XRL + (size_t)(k - 1) * XRS) + 16u * W : a_in;
+    const unsigned a_cdp = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE)) - (din ? (unsigned)(Cfg::VECS * 16) : 0u);
+    const unsigned a_cdc = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE)) + (dout ? (unsigned)(Cfg::VECS * 16) : 0u);
     const unsigned a_res = (unsigned)__cvta_generic_to_shared(RES) + 16u * (c - k + K - 1);
-    const volatile int *plim = cnt + Cfg::LIM + k;
+    const unsigned a_lim = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::LIM + k));
+    const unsigned a_cdone = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE));
 
-    /* loop-carried state: the right-hand side of the coming step, complete (west value included),
-       and the raw north values loaded for it (= pre-sweep centre of the step after) */
-    double rhs[NL], Nraw[NL];
+    /* The loop is rotated by half a step: iteration tau does the BACK SUBSTITUTION of step tau (row j)
+       and then the right-hand side and FORWARD ELIMINATION of step tau+1 (row jn = j+1).
+       Why: ptxas schedules a basic block bottom-up (everything as late as its consumers allow).  With
+       the block boundary between two steps, every load, ghost substitution, shuffle and store of a step
+       is "needed at the block end" and gets bunched after out[0], on the critical path of the next
+       step (measured: ~700 cycles per step against a ~400-cycle chain).  With the boundary in the
+       middle of the recurrence the consumers of that work (rhs of the next step, its forward
+       elimination) sit in the same block, so it lands in the stall slots of the back substitution.
+       Loop-carried: rp[] = right-hand side after forward elimination, q0p = quotient estimate of the
+       pivot row, ncur[] = raw north values of the row being solved (= pre-sweep centre of the next). */
+    double rp[NL], ncur[NL], q0p = 0.;
 #pragma unroll
-    for (int l = 0; l < NL; l++) rhs[l] = Nraw[l] = 0.;
+    for (int l = 0; l < NL; l++) rp[l] = ncur[l] = 0.;
     long long t_start = 0, n_spins = 0;
     if (A.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const int T = ny + W + 2 * K - 2;
 
-    /* EDGE: rows 0 / ny-1 may occur (ghost substitution for south/north); LR: some lane of the warp
-       sits on a physical left/right boundary */
+    /* EDGE: rows 0 / ny-1 may occur (ghost substitution for south/north, partial stores); LR: some
+       lane of the warp sits on a physical left/right boundary (MODE) */
     auto step = [&](auto edge_tag, auto lr_tag, const int tau) {
-      constexpr bool EDGE = decltype(edge_tag)::value, LR = decltype(lr_tag)::value;
+      constexpr bool EDGE = decltype(edge_tag)::value;
+      constexpr int MODE = decltype(lr_tag)::value; /* 0 interior strip, 1 leftmost strip (no mailbox), 2 general */
       const int j = tau - c - 2 * k - 1;
       const int jn = j + 1;
-      /* ---- (B) inputs of the next step (row jn), speculatively; the guard is read first */
-      const int lim = ld_cnt(plim);
+      /* ---- (B) inputs of step tau+1 (row jn), speculatively; the guard is read first */
+      const int lim = ld_cnt_a(a_lim);
+      const int cdp = ld_cnt_a(a_cdp), cdc = ld_cnt_a(a_cdc); /* neighbours' step counters (own counter if not direct) */
       double2 e2[NV], n2[NV], b2[NV], w2[NV], s2[NV];
       auto load_inputs = [&]() {
         const unsigned pe = a_in + 16u * (unsigned)((jn & in_mask) * DROW + 1);
-        const unsigned pn = a_in + 16u * (unsigned)(((jn + 1) & in_mask) * DROW);
+        const unsigned pn = a_north + 16u * (unsigned)(((jn + 1) & in_mask) * DROW);
         const unsigned pb = a_res + 16u * (unsigned)((jn & (RIN - 1)) * RROW);
-        const unsigned pw = a_ring + 16u * (unsigned)((jn & (R2 - 1)) * DROW);
+        const unsigned pw = a_west + 16u * (unsigned)((jn & (R2 - 1)) * DROW);
 #pragma unroll
         for (int v = 0; v < NV; v++) {
           e2[v] = lds2(pe + 16u * (v * S));
           n2[v] = lds2(pn + 16u * (v * S));
           b2[v] = lds2(pb + 16u * (v * RC));
-          w2[v] = lds2_if(use_mail, pw + 16u * (v * S));
+          if (MODE != 1) w2[v] = lds2_if(use_mail, pw + 16u * (v * S));
+          else w2[v] = make_double2(0., 0.);
           if (EDGE && TILE) s2[v] = lds2(a_in + 16u * (unsigned)(((-1) & in_mask) * DROW + v * S)); /* stored halo row -1 */
           else s2[v] = make_double2(0., 0.);
         }
       };
       load_inputs();
-      /* ---- (C) Thomas recurrence (msqg/poisson_layer.h:137-146), results leave as they appear */
+      /* ---- (C) back substitution of step tau (msqg/poisson_layer.h:141-146); results leave as they appear */
       const unsigned po = a_ring + 16u * (unsigned)((j & (R2 - 1)) * DROW + c + 1);
       const bool row_ok = EDGE ? ((unsigned)j < (unsigned)ny) : true;
       const bool do_st = row_ok && st_lane;
       const bool do_mb = row_ok && mb_writer;
       unsigned long long *mrow = mo + (long long)j * NLP;
       double out[NL], wsh[NL];
-      if (NL == 1) {
-        out[0] = div_by(rhs[0], C.t1p[0], C.rinv[0]);
-      } else {
-        double q = 0.;
-#pragma unroll
-        for (int l = 1; l < NL; l++) {
-          const double x = C.t0[l] * rhs[l - 1];
-          const double q0 = rhs[l - 1] * C.cf[l];
-          q = div_fix(x, q0, C.t1p[l - 1], C.rinv[l - 1]);
-          if (l < NL - 1) rhs[l] -= q;
-        }
-        {
-          const double rr = rhs[NL - 1] * C.rinv[NL - 1]; /* off the chain: rhs before elimination */
-          const double x = rhs[NL - 1] - q;
-          const double q0 = __fma_rn(-q, C.rinv[NL - 1], rr);
-          out[NL - 1] = div_fix(x, q0, C.t1p[NL - 1], C.rinv[NL - 1]);
-        }
-      }
+      if (NL == 1) out[0] = div_by(rp[0], C.t1p[0], C.rinv[0]);
+      else out[NL - 1] = div_fix(rp[NL - 1], q0p, C.t1p[NL - 1], C.rinv[NL - 1]);
 #pragma unroll
       for (int l = NL - 1; l >= 0; l--) {
         if (l < NL - 1) {
-          const double rr = rhs[l] * C.rinv[l];
+          const double rr = rp[l] * C.rinv[l];
           const double m = C.t2[l] * out[l + 1];
           const double q0 = __fma_rn(-C.cb[l], out[l + 1], rr);
-          const double x = rhs[l] - m;
+          const double x = rp[l] - m;
           out[l] = div_fix(x, q0, C.t1p[l], C.rinv[l]);
         }
         wsh[l] = __shfl_up_sync(FULLMASK, out[l], 1);
@@ -801,12 +817,16 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           st_mail2_if(do_mb, mrow + l, (unsigned long long)__double_as_longlong(out[l]), (unsigned long long)__double_as_longlong(hi));
         }
       }
-      /* ---- (D) right-hand side of the next step (speculative, redone below if (B) was too early);
-         r = -sq(Delta)*b; r += E + W; r += N + S in the reference's association order */
+      /* results of step tau are in the rings: publish (helper: drain / ring reuse; right neighbour: hand-off) */
+      __syncwarp();
+      st_cnt_if(lane == 0, a_cdone, tau + 1);
+      /* ---- (D) step tau+1: right-hand side r = -sq(Delta)*b; r += E + W; r += N + S (reference association
+         order, msqg/poisson_layer.h:88-94) and forward elimination (:137-140) */
       double cold[NL];
 #pragma unroll
-      for (int l = 0; l < NL; l++) cold[l] = Nraw[l];
-      auto next_rhs = [&]() {
+      for (int l = 0; l < NL; l++) cold[l] = ncur[l];
+      auto next_forward = [&]() {
+        double rhs[NL];
 #pragma unroll
         for (int l = 0; l < NL; l++) {
           const double ev = (l & 1) ? e2[l >> 1].y : e2[l >> 1].x;
@@ -814,9 +834,11 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           const double bv = (l & 1) ? b2[l >> 1].y : b2[l >> 1].x;
           const double wv = (l & 1) ? w2[l >> 1].y : w2[l >> 1].x;
           const double sv = (l & 1) ? s2[l >> 1].y : s2[l >> 1].x;
-          const double g = -cold[l]; /* dirichlet ghost: -(pre-sweep centre of the next step's cell) */
+          /* dirichlet ghost: -(pre-sweep centre of the cell of step tau+1); sign flip on the integer pipe */
+          const double g = __hiloint2double(__double2hiint(cold[l]) ^ 0x80000000, __double2loint(cold[l]));
           double aw, ae, as, an;
-          if (LR) { aw = left ? g : (use_mail ? wv : wsh[l]); ae = right ? g : ev; }
+          if (MODE == 2) { const double alt = left ? g : wv; aw = (left || use_mail) ? alt : wsh[l]; ae = right ? g : ev; }
+          else if (MODE == 1) { aw = left ? g : wsh[l]; ae = ev; }
           else { aw = use_mail ? wv : wsh[l]; ae = ev; }
           if (EDGE) { as = (jn == 0) ? ((TILE && bint) ? sv : g) : out[l]; an = (jn == ny - 1 && !tint) ? g : nv; }
           else { as = out[l]; an = nv; }
@@ -824,29 +846,44 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           r += ae + aw;
           r += an + as;
           rhs[l] = r;
-          Nraw[l] = nv;
+          ncur[l] = nv;
         }
+        if (NL > 1) {
+          double q = 0.;
+#pragma unroll
+          for (int l = 1; l < NL; l++) {
+            const double x = C.t0[l] * rhs[l - 1];
+            const double q0 = rhs[l - 1] * C.cf[l];
+            q = div_fix(x, q0, C.t1p[l - 1], C.rinv[l - 1]);
+            if (l < NL - 1) rhs[l] -= q;
+          }
+          const double rr = rhs[NL - 1] * C.rinv[NL - 1]; /* off the chain: rhs before elimination */
+          q0p = __fma_rn(-q, C.rinv[NL - 1], rr);
+          rhs[NL - 1] -= q;
+        }
+#pragma unroll
+        for (int l = 0; l < NL; l++) rp[l] = rhs[l];
       };
-      next_rhs();
+      next_forward();
       /* ---- (E) was the speculation of (B) valid? */
-      if (!__all_sync(FULLMASK, jn <= lim)) {
+      /* left neighbour (direct): its lane (k, W-1) must have stored row jn of sweep k: counter >= tau + W + 1;
+         right neighbour (direct): must be done with the ring row that iteration tau+1 overwrites */
+      const int need_p = din ? min(tau + W + 1, T) : -WS_INF, need_c = dout ? tau - R2 - W + 4 : -WS_INF; /* T: the neighbour's final count */
+      if (!__all_sync(FULLMASK, jn <= lim && cdp >= need_p && cdc >= need_c)) {
         int spins = 0;
-        while (!__all_sync(FULLMASK, jn <= ld_cnt(plim))) {
+        while (!__all_sync(FULLMASK, jn <= ld_cnt_a(a_lim) && ld_cnt_a(a_cdp) >= need_p && ld_cnt_a(a_cdc) >= need_c)) {
           if (++spins > SPIN_LIMIT) { if (lane == 0) *A.err = 1; break; }
         }
         n_spins += spins;
         __syncwarp();
         load_inputs();
-        next_rhs();
+        next_forward();
       }
-      /* ---- (F) publish progress: results of this step are in the rings */
-      __syncwarp();
-      if (lane == 0) cnt[Cfg::C_DONE] = tau + 1;
     };
 
     auto run = [&](auto lr_tag) {
-      int tau = -1; /* step -1 only loads: the pre-sweep value of row 0 is the ghost source of the first row */
-      const int t_fast0 = min(T, W + 2 * K - 2), t_fast1 = ny - 2; /* FAST steps: [t_fast0, t_fast1] */
+      int tau = -1; /* iteration -1 only loads: the pre-sweep value of row 0 is the ghost source of the first row */
+      const int t_fast0 = min(T, W + 2 * K - 2), t_fast1 = ny - 2; /* FAST iterations [t_fast0, t_fast1]: every lane has 0 <= j, jn < ny-1 */
 #pragma unroll 1
       for (; tau < t_fast0; tau++) step(std::true_type{}, lr_tag, tau);
 #pragma unroll 1
@@ -854,7 +891,9 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
 #pragma unroll 1
       for (; tau < T; tau++) step(std::true_type{}, lr_tag, tau);
     };
-    if (lr_any) run(std::true_type{}); else run(std::false_type{});
+    if (!lr_any) run(std::integral_constant<int, 0>{});
+    else if (!__any_sync(FULLMASK, right || use_mail)) run(std::integral_constant<int, 1>{});
+    else run(std::integral_constant<int, 2>{});
     if (A.dbg) {
       long long t_end;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -882,10 +921,13 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       st_r[q] = (unsigned)__cvta_generic_to_shared(RES) + 16u * (unsigned)((l >> 1) * RC + xs) + 8u * (l & 1);
     }
     constexpr int PF = 48;
+#ifndef HROWS
+#define HROWS 4 /* rows streamed in / drained per helper iteration: must outrun the compute warp */
+#endif
     /* mailbox lanes: (kk, q) */
     const int kk = lane / Q, q = lane % Q;
     const bool rd_ghost = (w == 0) && lint && kk == 0; /* west column = stored halo column -1 of the iterate */
-    const bool rd_valid = rd_ghost || ((w > 0) && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
+    const bool rd_valid = rd_ghost || ((w > 0) && (wl == 0) && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
     const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)ny * NLP;
     const unsigned a_ringk = (unsigned)__cvta_generic_to_shared(XR + (size_t)kk * XRS);
     const unsigned a_ringf = (unsigned)__cvta_generic_to_shared(XR + (size_t)kf * XRS);
@@ -895,8 +937,12 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     int in_issued = r_first, h1 = r_first, h2 = r_first, h3 = r_first, in_done = r_first; /* rows issued now / 1,2,3 iterations ago */
     constexpr int EPL_O = (NL * W + 31) / 32;
     int idle = 0;
+    long long it = 0;
 #pragma unroll 1
-    for (long long it = 0;; it++) {
+    for (;; it++) {
+#ifdef EXP_HSLEEP
+      __nanosleep(EXP_HSLEEP);
+#endif
       const int cd = ld_cnt(cnt + Cfg::C_DONE);
       bool progress = false;
       /* ---- (1) mailbox in: Q rows of each sweep per iteration (the latency-critical hand-off) */
@@ -916,10 +962,10 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
 #pragma unroll
           for (int l = 0; l < NL; l++) v[l] = (unsigned long long)__double_as_longlong(A.da[(size_t)l * plane + GIDX(pitch, r, -1)]);
         }
-        /* ---- (2) meanwhile: stream up to 2 rows; rows issued three iterations ago have landed */
+        /* ---- (2) meanwhile: stream up to HROWS rows; rows issued three iterations ago have landed */
         {
           const int rmax = min(r_last, cd + RIN - Cfg::TAIL - 2);
-          const int b1 = min(in_issued + 2, rmax + 1);
+          const int b1 = min(in_issued + HROWS, rmax + 1);
           for (int r2 = in_issued; r2 < b1; r2++) {
             const unsigned ro = (unsigned)(r2 & (RIN - 1));
             const size_t go = (size_t)r2 * pitch;
@@ -945,10 +991,10 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           cp_async_wait<3>(); /* all but the three newest batches have landed: rows < h3 */
           h3 = h2; h2 = h1; h1 = in_issued; in_issued = b1;
         }
-        /* ---- (3) last sweep's rows -> HBM, up to 2 rows */
+        /* ---- (3) last sweep's rows -> HBM, up to HROWS rows */
         {
           int done = 0;
-          for (; done < 2; done++) {
+          for (; done < HROWS; done++) {
             const int r3 = da_dr + done;
             if (!(r3 < ny && cd >= r3 + W + 2 * kf + 1)) break;
 #pragma unroll
@@ -989,8 +1035,14 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       }
       /* ---- publish: per sweep, the last row whose inputs are complete */
       if (h3 > in_done) { in_done = h3; progress = true; }
+      /* No __threadfence_block() here: it would also wait for the drain's global stores (measured: ~1 us
+         per helper iteration, i.e. per hand-off).  The rings and the counters live in shared memory,
+         the deposits above and the counter store below are volatile shared-memory stores of the SAME
+         warp (the LSU keeps them in order), and cp.async data is complete after wait_group. */
       __syncwarp();
+#ifdef EXP_FENCE
       __threadfence_block();
+#endif
       if (q == 0 && kk < K) {
         int lim = (in_done > r_last) ? WS_INF : in_done - 2;
         lim = min(lim, (mail_rd >= ny) ? WS_INF : mail_rd - 1);
@@ -1007,5 +1059,6 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       } else idle = 0;
     }
     cp_async_wait<0>();
+    if (A.dbg && lane == 0) A.dbg[w * 4 + 3] = it; /* helper iterations (profiling) */
   }
 }
