@@ -254,12 +254,16 @@ def run_ours(args):
     if rf["count"] > 0 and rf["ms"] > 0:
         alg_bytes_per_launch = ab["relax_sweep"] * tile_cells * (rf["aux"] / rf["count"])
         ach = alg_bytes_per_launch / (rf["ms"] / rf["count"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_relax_lex (finest level)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one finest-level launch at 4096^2 x 4 from the ncu --set full
+        # capture in profiles/ncu_r01/relax.raw.csv (1.143 GB + 0.559 GB; independent of the number of fused sweeps)
+        traffic = 1.702e9 * tile_cells / (4096.0 * 4096 * 4) if nl == 4 else None
+        roof = {"bound": "hbm", "kernel": "k_relax_ws (finest level)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": rf["ms"] / rf["count"], "sweeps_per_launch": rf["aux"] / rf["count"],
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "share_of_step": rf["ms"] / ms_total,
-                "note": "latency-bound wavefront (exact reference sweep order): all sweeps of a launch are one HBM pass"}
+                "note": "latency-bound wavefront (exact reference sweep order): the fused sweeps of a launch are ONE HBM pass, "
+                        "so DRAM traffic is below the pass-count algorithmic bytes"}
     kern_ms = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}
     # whole-step algorithmic bytes with the measured cycle counts
     sweeps_all = prof["relax_fine"]["aux"]  # every level does the same number of sweeps per cycle
@@ -271,7 +275,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            Ns = 1024
+            Ns = 2048 if (os.cpu_count() or 1) >= 8 else 1024
             cv, cms, threads, _ = cpu_oracle_run(Ns, nl, 3, 1)
             cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d^2 x nl=%d grid, same parameters, 3 steps after 1 warm-up (metric is per cell-layer)" % (Ns, nl),

@@ -376,7 +376,7 @@ static int g_cycle(msqg_group *G, int nrelax) {
       const Geom &g = root->g[l];
       if (l == 1) CK(cudaMemsetAsync(root->da.lev[l], 0, (size_t)nl * g.plane * sizeof(double), G->stream));
       else {
-        k_prolong<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(root->da.lev[l - 1], root->da.lev[l], root->g[l - 1], g);
+        launch_prolong(G->stream, nl, root->da.lev[l - 1], root->da.lev[l], root->g[l - 1], g);
         root->launches++;
       }
       if ((rc = g_relax_level(G, root, l, nrelax))) return rc;
@@ -407,8 +407,8 @@ static int g_cycle(msqg_group *G, int nrelax) {
     for (msqg_model *m : G->tiles) {
       const Geom &g = m->g[l];
       ProfScope ps(m, PROF_PROLONG, l);
-      if (l == La) k_prolong<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->da_patch, m->da.lev[l], m->gpatch, g);
-      else k_prolong<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
+      if (l == La) launch_prolong(G->stream, nl, m->da_patch, m->da.lev[l], m->gpatch, g);
+      else launch_prolong(G->stream, nl, m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
       m->launches++;
     }
     CK(cudaGetLastError());
@@ -516,7 +516,7 @@ static int g_rhs_prepare(msqg_group *G, double *umax) {
     const Geom &g = m->g[D];
     CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), G->stream));
     ProfScope ps(m, PROF_LAP, 0);
-    k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, G->stream>>>(m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
+    launch_lap(G->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
     m->launches++;
     use_tmp = (m->iRe != 0. || m->iRe4 != 0.);
   }
@@ -526,7 +526,7 @@ static int g_rhs_prepare(msqg_group *G, double *umax) {
     for (msqg_model *m : G->tiles) {
       const Geom &g = m->g[D];
       ProfScope ps(m, PROF_LAP, 0);
-      k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, G->stream>>>(m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+      launch_lap(G->stream, m->nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
       m->launches++;
     }
     CK(cudaGetLastError());

@@ -235,6 +235,43 @@ __global__ void k_prolong(const double *__restrict__ coarse, double *__restrict_
   fine[(size_t)f * gf.plane + GIDX(gf.pitch, y, x)] = v;
 }
 
+/* Same operator, one thread per COARSE cell: the 3x3 coarse neighbourhood is read once and the four
+ * children are written as two 16-byte stores (the per-child kernel above re-reads it four times and is
+ * instruction-bound: ncu, profiles/r01_ncu_kernels.md).  Needs even fine tile sizes aligned with the
+ * coarse cells (always true on one GPU). */
+__global__ void __launch_bounds__(256)
+k_prolong4(const double *__restrict__ coarse, double *__restrict__ fine, Geom gc, Geom gf) {
+  const int xc = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yc = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (xc >= gc.nx || yc >= gc.ny) return;
+  const double *c = coarse + (size_t)f * gc.plane;
+  double v[3][3];
+  if (xc > 0 && xc < gc.nx - 1 && yc > 0 && yc < gc.ny - 1) {
+    const double *p = c + GIDX(gc.pitch, yc, xc);
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) v[dy][dx] = p[(dy - 1) * gc.pitch + (dx - 1)];
+  } else {
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) v[dy][dx] = coarse_at(c, gc, xc + dx - 1, yc + dy - 1);
+  }
+  double *o = fine + (size_t)f * gf.plane + GIDX(gf.pitch, 2 * yc, 2 * xc);
+#pragma unroll
+  for (int oy = 0; oy < 2; oy++) {
+    double r[2];
+#pragma unroll
+    for (int ox = 0; ox < 2; ox++) {
+      const int ix = ox ? 2 : 0, iy = oy ? 2 : 0;
+      r[ox] = (9. * v[1][1] + 3. * (v[1][ix] + v[iy][1]) + v[iy][ix]) / 16.;
+    }
+    *reinterpret_cast<double2 *>(o + (size_t)oy * gf.pitch) = make_double2(r[0], r[1]);
+  }
+}
+
 /* ------------------------------------------------------------------ correction
  * mg_cycle tail: a += da ; boundary(a)   (mspg/elliptic.h:92-98).  Ghost ring of
  * the dirichlet(0) field a is written by the boundary cells themselves. */

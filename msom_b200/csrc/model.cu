@@ -231,6 +231,26 @@ static List *list_by_id(msqg_model *m, int id) {
 }
 
 static dim3 grid2(int nx, int ny, dim3 b, int nz = 1) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, nz); }
+/* laplacian (+ face-speed reduction): two cells per thread when the tile width is even */
+static void launch_lap(cudaStream_t st, int nf, const double *in, double *out, const Geom &g, double *umax) {
+  if ((g.nx & 1) == 0) {
+    dim3 b(32, 8);
+    k_lap2<<<grid2(g.nx / 2, g.ny, b, nf), b, 0, st>>>(in, out, g, umax);
+  } else {
+    dim3 b(64, 4);
+    k_lap<<<grid2(g.nx + 1, g.ny + 1, b, nf), b, 0, st>>>(in, out, g, umax);
+  }
+}
+/* bilinear prolongation: one thread per coarse cell when the fine tile is exactly its 2 x 2 refinement */
+static void launch_prolong(cudaStream_t st, int nf, const double *coarse, double *fine, const Geom &gc, const Geom &gf) {
+  if (gf.nx == 2 * gc.nx && gf.ny == 2 * gc.ny) {
+    dim3 b(32, 8);
+    k_prolong4<<<grid2(gc.nx, gc.ny, b, nf), b, 0, st>>>(coarse, fine, gc, gf);
+  } else {
+    dim3 b(32, 8);
+    k_prolong<<<grid2(gf.nx, gf.ny, b, nf), b, 0, st>>>(coarse, fine, gc, gf);
+  }
+}
 
 static int pack_to(msqg_model *m, List &L, const double *host) {
   const Geom &g = m->g[m->depth];
@@ -780,7 +800,7 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
       CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)P.nf * g.plane * sizeof(double), m->stream));
     } else {
       ProfScope ps(m, PROF_PROLONG, l);
-      k_prolong<<<grid2(g.nx, g.ny, b, P.nf), b, 0, m->stream>>>(m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
+      launch_prolong(m->stream, P.nf, m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
       m->launches++;
       CK(cudaGetLastError());
     }
@@ -980,7 +1000,7 @@ static int max_face_speed(msqg_model *m, List &L, double *umax_host) {
   CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
   dim3 b(64, 4);
   /* out-of-place laplacian into tmp is a by-product; only umax is wanted */
-  k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, m->stream>>>(L.lev[D], m->tmp.lev[D], g, m->d_scal + 1);
+  launch_lap(m->stream, m->nl, L.lev[D], m->tmp.lev[D], g, m->d_scal + 1);
   m->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(m->h_scal + 1, m->d_scal + 1, m->nl * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -1117,7 +1137,7 @@ static int set_const_finish(msqg_model *m) {
     if ((rc = max_face_speed(m, m->psipg, m->umax_pg))) return rc;
     if (m->p.flsrv == 1) {
       dim3 b(64, 4);
-      k_lap<<<grid2(g.nx + 1, g.ny + 1, b, nl), b, 0, m->stream>>>(m->psipg.lev[D], m->zetap.lev[D], g, nullptr);
+      launch_lap(m->stream, nl, m->psipg.lev[D], m->zetap.lev[D], g, nullptr);
       m->launches++;
       CK(cudaGetLastError());
       m->has_zp = 1;
@@ -1156,10 +1176,10 @@ static int rhs_prepare(msqg_model *m) {
   dim3 b(64, 4);
   CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
   ProfScope ps(m, PROF_LAP, 0);
-  k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, m->stream>>>(m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
+  launch_lap(m->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
   m->launches++;
   if (m->iRe != 0. || m->iRe4 != 0.) {
-    k_lap<<<grid2(g.nx + 1, g.ny + 1, b, m->nl), b, 0, m->stream>>>(m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+    launch_lap(m->stream, m->nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
     m->launches++;
   }
   CK(cudaGetLastError());
@@ -1437,7 +1457,7 @@ extern "C" int msqg_test_prolong(msqg_model *m, int level, const double *coarse,
   int rc;
   if ((rc = upload_level(m, m->da.lev[level - 1], coarse, m->nl, level - 1, -1.))) return rc;
   dim3 b(32, 8);
-  k_prolong<<<grid2(m->g[level].nx, m->g[level].ny, b, m->nl), b, 0, m->stream>>>(m->da.lev[level - 1], m->da.lev[level], m->g[level - 1], m->g[level]);
+  launch_prolong(m->stream, m->nl, m->da.lev[level - 1], m->da.lev[level], m->g[level - 1], m->g[level]);
   CK(cudaGetLastError());
   return download_level(m, fine, m->da.lev[level], m->nl, level);
 }

@@ -78,6 +78,79 @@ k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *_
   if (umax) block_max_to(umax + f, um);
 }
 
+/* k_lap with two cells per thread: the 3 x 4 window (rows y-1..y+1, columns x-1..x+2) is read with one 16-byte
+ * and two 8-byte loads per row and serves both laplacians and all face velocities of the two cells.  The face
+ * speed is reduced as max |0.25*(...)| (the numerator) and divided by Delta ONCE per block: correctly rounded
+ * division is monotone and odd, so max_a |RN(x_a/Delta)| == RN(max_a |x_a| / Delta) bit for bit.
+ * (ncu: the one-cell kernel above is instruction-bound at 17-29 % of DRAM peak, profiles/r01_ncu_kernels.md.)
+ * Requires an even nx. */
+__global__ void __launch_bounds__(256)
+k_lap2(const double *__restrict__ in, double *__restrict__ out, Geom g, double *__restrict__ umax) {
+  const int x0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  const double *p = in + (size_t)f * g.plane;
+  double um = 0.;
+  if (x0 < g.nx && y < g.ny) {
+    const int P = g.pitch;
+    const size_t c = GIDX(P, y, x0);
+    double w[3][4]; /* w[r][k] = p(x0 - 1 + k, y - 1 + r) */
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const double *q = p + c + (ptrdiff_t)(r - 1) * P;
+      const double2 m = *reinterpret_cast<const double2 *>(q);
+      w[r][0] = q[-1]; w[r][1] = m.x; w[r][2] = m.y; w[r][3] = q[2];
+    }
+    double *o = out + (size_t)f * g.plane;
+    double v[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) /* p[c+1] + p[c-1] + p[c+P] + p[c-P] - 4*p[c] */
+      v[k] = div_by(w[1][k + 2] + w[1][k] + w[2][k + 1] + w[0][k + 1] - 4 * w[1][k + 1], g.D2, g.rD2);
+    *reinterpret_cast<double2 *>(o + c) = make_double2(v[0], v[1]);
+    if (x0 == 0 || x0 + 2 >= g.nx || y == 0 || y == g.ny - 1) {
+      write_ghosts(o, g, x0, y, v[0], -1.);
+      write_ghosts(o, g, x0 + 1, y, v[1], -1.);
+    }
+    if (umax) {
+      double a;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        /* x-face (x0+k, y): p[c+P] - p[c-P] + p[c-1+P] - p[c-1-P] */
+        a = fabs(0.25 * (w[2][k + 1] - w[0][k + 1] + w[2][k] - w[0][k]));
+        if (a > um) um = a;
+        /* y-face (x0+k, y): p[c+1] - p[c-1] + p[c+1-P] - p[c-1-P] */
+        a = fabs(0.25 * (w[1][k + 2] - w[1][k] + w[0][k + 2] - w[0][k]));
+        if (a > um) um = a;
+      }
+      if (x0 + 2 == g.nx) { /* x-face (nx, y) */
+        a = fabs(0.25 * (w[2][3] - w[0][3] + w[2][2] - w[0][2]));
+        if (a > um) um = a;
+      }
+      if (y == g.ny - 1) { /* y-faces (x0+k, ny) */
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          a = fabs(0.25 * (w[2][k + 2] - w[2][k] + w[1][k + 2] - w[1][k]));
+          if (a > um) um = a;
+        }
+      }
+    }
+  }
+  if (umax) {
+    __shared__ double sh[32];
+    um = warp_max(um);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    if (lane == 0) sh[wid] = um;
+    __syncthreads();
+    if (wid == 0) {
+      um = lane < nw ? sh[lane] : 0.;
+      um = warp_max(um);
+      if (lane == 0 && um > 0.) atomic_max_pos(umax + f, fabs(div_by(um, g.Delta, g.rD)));
+    }
+  }
+}
+
 /* jacobian macro, qg.h:252-262: returns -J(p,q), 3x3 neighbourhoods */
 __device__ __forceinline__ double jac(const double *__restrict__ po, const double *__restrict__ qo, size_t c, int P,
                                       const Geom &G) {
@@ -121,8 +194,11 @@ struct RhsArgs {
  * qforcing (:465-474), bottom_topography (:480-488), advance_qg (:594-606;
  * stochastic qg_stochastic.h:128-149), one thread per column, layers in
  * registers so that ju = -jd is reused exactly as the reference does. */
+#ifndef RHS_MINB
+#define RHS_MINB 6 /* 80 registers: load latency (78 % of the stall cycles at 31 % occupancy, ncu) needs more resident warps */
+#endif
 template <int NL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RHS_MINB)
 k_rhs(RhsArgs A) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
