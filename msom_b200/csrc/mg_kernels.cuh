@@ -355,6 +355,8 @@ struct RelaxArgs {
   int *err;                     /* set to 1 on spin timeout */
   long long *dbg;               /* optional [nworkers][4]: start ns, end ns, spins, - */
   int flags;                    /* reserved for timing experiments */
+  int w_base;                   /* k_relax_ws: index of the first strip of this launch (levels wider than the device holds
+                                   co-resident strips are swept in column panels; the mailbox carries the boundary column) */
 };
 
 #define MAIL_EMPTY 0xFFF8DEADBEEF0001ull
@@ -735,7 +737,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   /* internal sides (multi-GPU tiles, single-sweep launches only): ghosts are stored halo values */
   const bool lint = TILE && (A.g.bc & 1), rint = TILE && (A.g.bc & 2), bint = TILE && (A.g.bc & 4), tint = TILE && (A.g.bc & 8);
   const int r_first = bint ? -1 : 0, r_last = tint ? ny : ny - 1; /* rows of the iterate that are streamed */
-  const int w = blockIdx.x * WPC + wl;
+  const int w = A.w_base + blockIdx.x * WPC + wl;
   const int nworkers = (nx + K - 1 + W - 1) / W;
   double2 *base = smem2 + (size_t)wl * Cfg::VECS;
   double2 *IN = base;                   /* [RIN][NV][S]  initial iterate, slot s <-> column w*W + s */

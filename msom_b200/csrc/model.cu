@@ -631,7 +631,7 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
   }
   RelaxArgs A;
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
-  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg;
+  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.w_base = 0;
   { const char *f = getenv("MSQG_RELAX_FLAGS"); A.flags = f ? atoi(f) : 0; }
   const size_t smem = Cfg::smem_per_warp * WPC;
   auto kern = k_relax_lex<NL, K, WPC>;
@@ -675,7 +675,7 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   }
   RelaxArgs A;
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
-  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0;
+  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0; A.w_base = 0;
   const size_t smem = Cfg::smem_per_worker * WPC;
   const int tv = g.bc ? 1 : 0;
   auto kern = tv ? k_relax_ws<NL, K, WPC, true> : k_relax_ws<NL, K, WPC, false>;
@@ -688,13 +688,19 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   }
   const int max_blocks_per_sm = max_blocks[tv];
   const int grid = (nworkers + WPC - 1) / WPC;
-  if (grid > max_blocks_per_sm * m->num_sms)
-    FAIL(MSQG_ERR_ARG, "relax wavefront needs %d co-resident CTAs, device holds %d (N too large for nl=%d)", grid,
-         max_blocks_per_sm * m->num_sms, NL);
+  int cap = max_blocks_per_sm * m->num_sms; /* co-resident CTAs (strips spin on their left neighbour) */
+  { const char *e = getenv("MSQG_RELAX_CAP"); if (e && atoi(e) > 0 && atoi(e) < cap) cap = atoi(e); } /* tests: force panels */
+  if (cap < 1) FAIL(MSQG_ERR_ARG, "relax kernel does not fit on the device (nl=%d)", NL);
   RelaxCoef<NL> Cc = C;
-  void *args[] = {(void *)&A, (void *)&Cc};
-  CK(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(64 * WPC), args, smem, m->stream));
-  m->launches++;
+  /* a level wider than cap*WPC strips is swept in column panels, left to right: the last strip of a panel
+     leaves its boundary column in the global mailbox, the first strip of the next launch picks it up */
+  for (int b0 = 0; b0 < grid; b0 += cap) {
+    A.w_base = b0 * WPC;
+    const int nb = grid - b0 < cap ? grid - b0 : cap;
+    void *args[] = {(void *)&A, (void *)&Cc};
+    CK(cudaLaunchCooperativeKernel((void *)kern, dim3(nb), dim3(64 * WPC), args, smem, m->stream));
+    m->launches++;
+  }
   return MSQG_OK;
 }
 template <int NL, int K>

@@ -45,7 +45,7 @@ int main(int argc, char **argv) {
   CKC(cudaMemset(err, 0, 4));
   k_fill<<<592, 256>>>(mail, words, MAIL_EMPTY);
   RelaxArgs A;
-  A.da = da; A.res = res; A.g = g; A.nsweeps = nsw; A.mailbox = mail; A.err = err; A.dbg = dbg; A.flags = argc > 3 ? atoi(argv[3]) : 0;
+  A.da = da; A.res = res; A.g = g; A.nsweeps = nsw; A.mailbox = mail; A.err = err; A.dbg = dbg; A.flags = argc > 3 ? atoi(argv[3]) : 0; A.w_base = 0;
   auto kern = k_relax_ws<NL, K, BWPC, false>;
   const size_t smem = Cfg::smem_per_worker * BWPC;
   CKC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

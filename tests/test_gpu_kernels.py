@@ -117,3 +117,11 @@ def test_restrict_prolong_match_oracle(gpu, nl, level):
     O.lib().orc_test_prolong(nl, level, coarse, f_ref)
     G.check(G.lib().msqg_test_prolong(m.h, level, coarse, f_gpu))
     assert np.array_equal(f_gpu, f_ref)
+
+
+@pytest.mark.parametrize("nl,level,nsweeps,cap", [(4, 8, 4, 3), (2, 7, 3, 1), (3, 8, 6, 5)])
+def test_relax_in_column_panels_matches_oracle(gpu, nl, level, nsweeps, cap, monkeypatch):
+    """levels wider than the device holds co-resident strips are swept in column panels (several launches,
+    the global mailbox carries the boundary column): same bits as one launch and as the oracle"""
+    monkeypatch.setenv("MSQG_RELAX_CAP", str(cap))
+    test_relax_matches_oracle(gpu, nl, level, nsweeps)
