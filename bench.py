@@ -147,8 +147,16 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the msqg timestep has no CPU path")
     torch.cuda.set_device(local)
+    # rank 0 prints ONE JSON line: anything a library writes to fd 1 meanwhile (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, nl = args.N, args.nl
     cells = float(N) * N * nl
@@ -299,7 +307,7 @@ def run_ours(args):
             "kernel_ms_per_step": kern_ms,
             "step_roofline": {"algorithmic_bytes_per_cell_layer_per_step": step_bytes / cells, "achieved": step_roof,
                               "peak": peak, "unit": "GB/s", "frac": step_roof / peak}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         m.close()
         dist.destroy_process_group()

@@ -355,6 +355,7 @@ struct RelaxArgs {
   int *err;                     /* set to 1 on spin timeout */
   long long *dbg;               /* optional [nworkers][4]: start ns, end ns, spins, - */
   int flags;                    /* reserved for timing experiments */
+  const double *rowcoef;        /* k_relax_ws<..., RCOEF>: [ny][6][NL] per-row t0, t2, t1p, rinv, cf, cb (stretching varies with y) */
   int w_base;                   /* k_relax_ws: index of the first strip of this launch (levels wider than the device holds
                                    co-resident strips are swept in column panels; the mailbox carries the boundary column) */
 };
@@ -633,6 +634,44 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
   }
 }
 
+/* Per-row Thomas coefficients of one level for stretching that varies with y only (varRo > 0): the expressions
+ * of relax_coef_layers() (msqg/poisson_layer.h:89-139, same order, IEEE division) evaluated with the level's
+ * restricted stretching field at column 0 of every row.  out[j][6][NL] = t0, t2, t1p, rinv, cf, cb. */
+template <int NL>
+__global__ void k_rowcoef(const double *__restrict__ s, Geom g, LayerMetrics M, double *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.ny) return;
+  const double D2 = g.Delta * g.Delta;
+  double sv[NL], t0[NL], t1[NL], t2[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) { sv[l] = (l < NL - 1) ? s[(size_t)l * g.plane + GIDX(g.pitch, j, 0)] : 0.; t0[l] = t1[l] = t2[l] = 0.; }
+  if (NL > 1) {
+    t2[0] = -D2 * sv[0] * M.idh1[0];
+    t1[0] = -t2[0];
+    t1[0] += 1. + 1.; t1[0] += 1. + 1.;
+#pragma unroll
+    for (int l = 1; l < NL - 1; l++) {
+      t0[l] = -D2 * sv[l - 1] * M.idh0[l];
+      t2[l] = -D2 * sv[l] * M.idh1[l];
+      t1[l] = -t0[l] - t2[l];
+      t1[l] += 1. + 1.; t1[l] += 1. + 1.;
+    }
+    t0[NL - 1] = -D2 * sv[NL - 2] * M.idh0[NL - 1];
+    t1[NL - 1] = -t0[NL - 1];
+    t1[NL - 1] += 1. + 1.; t1[NL - 1] += 1. + 1.;
+#pragma unroll
+    for (int l = 1; l < NL; l++) t1[l] -= t0[l] * t2[l - 1] / t1[l - 1];
+  }
+  double *o = out + (size_t)j * 6 * NL;
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const double r = 1. / t1[l];
+    o[0 * NL + l] = t0[l]; o[1 * NL + l] = t2[l]; o[2 * NL + l] = t1[l]; o[3 * NL + l] = r;
+    o[4 * NL + l] = l > 0 ? t0[l] * (1. / t1[l - 1]) : 0.;
+    o[5 * NL + l] = t2[l] * r;
+  }
+}
+
 /* ------------------------------------------------------------------ relax_layer, warp-specialised
  * Same arithmetic results, schedule (lane (k,c) does row tau - c - 2k - 1 at step tau) and mailbox
  * protocol as k_relax_lex, but each strip is served by TWO warps so that the warp on the critical
@@ -723,7 +762,7 @@ __device__ __forceinline__ double div_fix(double x, double q, double d, double r
   return __fma_rn(e, r, q);
 }
 
-template <int NL, int K, int WPC, bool TILE>
+template <int NL, int K, int WPC, bool TILE, bool RCOEF = false>
 __global__ void __launch_bounds__(64 * WPC)
 k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   using Cfg = WsCfg<NL, K>;
@@ -799,6 +838,12 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     double rp[NL], ncur[NL], q0p = 0.;
 #pragma unroll
     for (int l = 0; l < NL; l++) rp[l] = ncur[l] = 0.;
+    /* RCOEF (varRo > 0: Ro and with it the stretching depend on y, msqg/qg.h:1032-1048): the Thomas coefficients
+       are per-row constants read from a table; cj = row j (back substitution), cn = row jn (forward elimination) */
+    constexpr int NCF = RCOEF ? 6 * NL : 2;
+    double cj[NCF];
+#pragma unroll
+    for (int i = 0; i < NCF; i++) cj[i] = 1.;
     long long t_start = 0, n_spins = 0;
     if (A.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const int T = ny + W + 2 * K - 2;
@@ -831,6 +876,20 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         }
       };
       load_inputs();
+      double cn[NCF];
+      if (RCOEF) {
+        const double2 *pc = reinterpret_cast<const double2 *>(A.rowcoef + (size_t)min(max(jn, 0), ny - 1) * (6 * NL));
+#pragma unroll
+        for (int i = 0; i < NCF / 2; i++) { const double2 t = __ldg(pc + i); cn[2 * i] = t.x; cn[2 * i + 1] = t.y; }
+      }
+      auto T2j = [&](int l) { return RCOEF ? cj[(1 * NL + l) % NCF] : C.t2[l]; };
+      auto T1j = [&](int l) { return RCOEF ? cj[(2 * NL + l) % NCF] : C.t1p[l]; };
+      auto RIj = [&](int l) { return RCOEF ? cj[(3 * NL + l) % NCF] : C.rinv[l]; };
+      auto CBj = [&](int l) { return RCOEF ? cj[(5 * NL + l) % NCF] : C.cb[l]; };
+      auto T0n = [&](int l) { return RCOEF ? cn[(0 * NL + l) % NCF] : C.t0[l]; };
+      auto T1n = [&](int l) { return RCOEF ? cn[(2 * NL + l) % NCF] : C.t1p[l]; };
+      auto RIn = [&](int l) { return RCOEF ? cn[(3 * NL + l) % NCF] : C.rinv[l]; };
+      auto CFn = [&](int l) { return RCOEF ? cn[(4 * NL + l) % NCF] : C.cf[l]; };
       /* ---- (C) back substitution of step tau (msqg/poisson_layer.h:141-146); results leave as they appear */
       const unsigned po = a_ring + 16u * (unsigned)((j & (R2 - 1)) * DROW + c + 1);
       const bool row_ok = EDGE ? ((unsigned)j < (unsigned)ny) : true;
@@ -838,16 +897,16 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       const bool do_mb = row_ok && mb_writer;
       unsigned long long *mrow = mo + (long long)j * NLP;
       double out[NL], wsh[NL];
-      if (NL == 1) out[0] = div_by(rp[0], C.t1p[0], C.rinv[0]);
-      else out[NL - 1] = div_fix(rp[NL - 1], q0p, C.t1p[NL - 1], C.rinv[NL - 1]);
+      if (NL == 1) out[0] = div_by(rp[0], T1j(0), RIj(0));
+      else out[NL - 1] = div_fix(rp[NL - 1], q0p, T1j(NL - 1), RIj(NL - 1));
 #pragma unroll
       for (int l = NL - 1; l >= 0; l--) {
         if (l < NL - 1) {
-          const double rr = rp[l] * C.rinv[l];
-          const double m = C.t2[l] * out[l + 1];
-          const double q0 = __fma_rn(-C.cb[l], out[l + 1], rr);
+          const double rr = rp[l] * RIj(l);
+          const double m = T2j(l) * out[l + 1];
+          const double q0 = __fma_rn(-CBj(l), out[l + 1], rr);
           const double x = rp[l] - m;
-          out[l] = div_fix(x, q0, C.t1p[l], C.rinv[l]);
+          out[l] = div_fix(x, q0, T1j(l), RIj(l));
         }
         wsh[l] = __shfl_up_sync(FULLMASK, out[l], 1);
         if ((l & 1) == 0) { /* layer pair (l, l+1) complete */
@@ -891,13 +950,13 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           double q = 0.;
 #pragma unroll
           for (int l = 1; l < NL; l++) {
-            const double x = C.t0[l] * rhs[l - 1];
-            const double q0 = rhs[l - 1] * C.cf[l];
-            q = div_fix(x, q0, C.t1p[l - 1], C.rinv[l - 1]);
+            const double x = T0n(l) * rhs[l - 1];
+            const double q0 = rhs[l - 1] * CFn(l);
+            q = div_fix(x, q0, T1n(l - 1), RIn(l - 1));
             if (l < NL - 1) rhs[l] -= q;
           }
-          const double rr = rhs[NL - 1] * C.rinv[NL - 1]; /* off the chain: rhs before elimination */
-          q0p = __fma_rn(-q, C.rinv[NL - 1], rr);
+          const double rr = rhs[NL - 1] * RIn(NL - 1); /* off the chain: rhs before elimination */
+          q0p = __fma_rn(-q, RIn(NL - 1), rr);
           rhs[NL - 1] -= q;
         }
 #pragma unroll
@@ -917,6 +976,10 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         __syncwarp();
         load_inputs();
         next_forward();
+      }
+      if (RCOEF) {
+#pragma unroll
+        for (int i = 0; i < NCF; i++) cj[i] = cn[i];
       }
     };
 

@@ -71,6 +71,8 @@ struct msqg_model {
   int const_set;
   /* uniform-stretching tables: s per level/layer and Thomas coefficients */
   bool s_uniform;
+  bool s_rowuniform;           /* stretching depends on y only (varRo > 0): per-row relax coefficients */
+  double *rowcoef[MSQG_MAXLEV + 1]; /* device tables [ny][6][nl] per level, or NULL */
   std::vector<double> s_lev;   /* [(depth+1)][nl] */
   std::vector<double> h_fr;    /* host copy of Frl finest [nl][N][N] */
   /* modal */
@@ -372,6 +374,8 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
   CK(cudaMallocHost(&m->h_err, sizeof(int)));
   m->mailbox = nullptr; m->mailbox_words = 0; m->d_dbg = nullptr;
+  for (int l = 0; l <= MSQG_MAXLEV; l++) m->rowcoef[l] = nullptr;
+  m->s_rowuniform = false;
   for (int l = 0; l < nl; l++) m->dhf[l] = p->dh[l]; /* qg.h:895-896 */
   m->iRe = p->iRe; m->iRe4 = p->iRe4; m->Eks = p->Eks; m->Ekb = p->Ekb;
   m->ts_previous = 0.; m->corrector_step = 0;
@@ -449,6 +453,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->d_err) cudaFree(m->d_err);
   if (m->h_err) cudaFreeHost(m->h_err);
   if (m->mailbox) cudaFree(m->mailbox);
+  for (int l = 0; l <= MSQG_MAXLEV; l++) if (m->rowcoef[l]) cudaFree(m->rowcoef[l]);
   if (m->da_patch) cudaFree(m->da_patch);
   if (m->res_patch) cudaFree(m->res_patch);
   if (m->patch_stage) cudaFree(m->patch_stage);
@@ -654,7 +659,7 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
   return MSQG_OK;
 }
 /* warp-specialised variant (k_relax_ws): two warps per strip */
-template <int NL, int K, int WPC>
+template <int NL, int K, int WPC, bool RCOEF = false>
 static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   using Cfg = WsCfg<NL, K>;
   const Geom &g = m->g[lev];
@@ -675,10 +680,11 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   }
   RelaxArgs A;
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
-  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0; A.w_base = 0;
+  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0; A.w_base = 0; A.rowcoef = RCOEF ? m->rowcoef[lev] : nullptr;
+  if (RCOEF && (g.bc || !A.rowcoef)) FAIL(MSQG_ERR_ARG, "y-dependent stretching (varRo) is supported on undecomposed levels only");
   const size_t smem = Cfg::smem_per_worker * WPC;
   const int tv = g.bc ? 1 : 0;
-  auto kern = tv ? k_relax_ws<NL, K, WPC, true> : k_relax_ws<NL, K, WPC, false>;
+  auto kern = RCOEF ? k_relax_ws<NL, K, WPC, false, RCOEF> : (tv ? k_relax_ws<NL, K, WPC, true> : k_relax_ws<NL, K, WPC, false>);
   static bool attr_set[2] = {false, false};
   static int max_blocks[2] = {0, 0};
   if (!attr_set[tv]) {
@@ -702,6 +708,17 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
     m->launches++;
   }
   return MSQG_OK;
+}
+/* stretching that varies with y (varRo > 0): per-row coefficient tables, K = 4 instances only */
+template <int NL>
+static int launch_relax_rowcoef(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
+  if constexpr (NL <= 6) { /* instantiated for the layer counts the coupled solver is used with (build time) */
+    constexpr size_t spw = WsCfg<NL, 4>::smem_per_worker;
+    if constexpr (spw * 4 <= 220 * 1024) return launch_relax_ws_w<NL, 4, 4, true>(m, da, res, lev, nsweeps, C);
+    else return launch_relax_ws_w<NL, 4, 2, true>(m, da, res, lev, nsweeps, C);
+  } else {
+    FAIL(MSQG_ERR_ARG, "varRo > 0 with the layer-coupled solver is built for nl <= 6 (nl = %d)", NL);
+  }
 }
 template <int NL, int K>
 static int launch_relax_ws(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
@@ -731,7 +748,8 @@ static int launch_relax(msqg_model *m, double *da, const double *res, int lev, i
   while (done < nrelax) {
     int ns = nrelax - done;
     int rc;
-    if (ns <= 4) rc = launch_relax_t<NL, 4>(m, da, res, lev, ns, C);
+    if (!m->s_uniform) { if (ns > 4) ns = 4; rc = launch_relax_rowcoef<NL>(m, da, res, lev, ns, C); }
+    else if (ns <= 4) rc = launch_relax_t<NL, 4>(m, da, res, lev, ns, C);
     else { if (ns > 8) ns = 8; rc = launch_relax_t<NL, 8>(m, da, res, lev, ns, C); }
     if (rc) return rc;
     done += ns;
@@ -859,7 +877,8 @@ static int invertq_list(msqg_model *m, List &ql) {
   const Geom &g = m->g[D];
   int rc;
   if (!m->p.mode_pv_invert) {
-    if (!m->s_uniform) FAIL(MSQG_ERR_ARG, "horizontally varying stretching is not supported by the relax kernel yet");
+    if (!m->s_uniform && !m->s_rowuniform)
+      FAIL(MSQG_ERR_ARG, "stretching that varies with x (frpg_*.bas) is not supported by the relax kernel yet");
     MgProblem P{m->nl, -1, m->psi.lev[D], ql.lev[D]};
     if ((rc = mg_solve(m, P, 1e-3, &m->mgpsi))) return rc;
   } else {
@@ -1051,16 +1070,19 @@ static int set_const_local(msqg_model *m) {
   }
   /* strl = sq(Fr/Ro), qg.h:1043-1048 (layers 0..nl-2; layer nl-1 stays 0) */
   std::vector<double> hs((size_t)nl * tc, 0.);
-  bool uniform = true;
+  bool uniform = true, rowuniform = true;
   for (int l = 0; l < nl - 1; l++) {
     const double *fr = &m->h_fr[(size_t)l * tc];
     double *s = &hs[(size_t)l * tc];
     for (int j = 0; j < ty; j++)
       for (int i = 0; i < tx; i++) s[(size_t)j * tx + i] = sq(fr[(size_t)j * tx + i] / ro_y[j]);
     for (size_t c = 1; c < tc && uniform; c++) uniform = s[c] == s[0];
+    for (int j = 0; j < ty && rowuniform; j++)
+      for (int i = 1; i < tx && rowuniform; i++) rowuniform = s[(size_t)j * tx + i] == s[(size_t)j * tx];
   }
   if ((rc = pack_to(m, m->str, hs.data()))) return rc;
   m->s_uniform = uniform;
+  m->s_rowuniform = rowuniform;
   /* restriction(strl) (poisson_layer.h:284): fields on the device, per-level
      constants on the host for the uniform case (same summation order) */
   {
@@ -1081,6 +1103,19 @@ static int set_const_local(msqg_model *m) {
         const double v = m->s_lev[(size_t)(lev + 1) * nl + l];
         m->s_lev[(size_t)lev * nl + l] = avg4(v, v, v, v);
       }
+  }
+  /* varRo > 0: the stretching depends on y only -> per-row Thomas coefficients for the relax kernel, built on the
+     device from the restricted stretching field of every level (same expressions as relax_coef_layers) */
+  for (int l = 0; l <= MSQG_MAXLEV; l++) if (m->rowcoef[l]) { CK(cudaFree(m->rowcoef[l])); m->rowcoef[l] = nullptr; }
+  if (!uniform && rowuniform && m->g[D].bc == 0 && m->agg_level <= 1) {
+    const LayerMetrics M = metrics_of(m);
+    for (int l = 1; l <= D; l++) {
+      const Geom &gl = m->g[l];
+      CK(cudaMalloc(&m->rowcoef[l], (size_t)gl.ny * 6 * nl * sizeof(double)));
+      NL_SWITCH(nl, k_rowcoef<NL><<<(gl.ny + 127) / 128, 128, 0, m->stream>>>(m->str.lev[l], gl, M, m->rowcoef[l]));
+      m->launches++;
+    }
+    CK(cudaGetLastError());
   }
   /* wind forcing table, qg.h:451, host libm so that sin() matches the reference */
   {

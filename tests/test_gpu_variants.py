@@ -139,3 +139,24 @@ def test_ensemble_members_concurrent(gpu):
     assert [mo.step() for _ in range(nsteps)] == dts[1]
     assert np.array_equal(mo.get(O.Q), qs[1])
     ens.close()
+
+
+@pytest.mark.parametrize("N,nl,nsteps", [(128, 3, 3), (64, 4, 4), (256, 2, 2)])
+def test_variable_rossby_number(gpu, N, nl, nsteps):
+    """varRo > 0 (msqg/qg.h:1032-1037): Ro, and with it the stretching strl = (Fr/Ro)^2, depends on y; the relax
+    kernel then reads per-row Thomas coefficients.  Bit-exact against the oracle, equal cycle counts."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    mo, mg, psi = make_pair(N, nl, varRo=1)
+    mo.set_const(); mg.set_const()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+    z = np.zeros_like(psi)
+    mo.set(O.PSI, z); mg.set(G.PSI, z)
+    mo.invertq(); mg.invertq()
+    so, sg = mo.mgstats(), mg.mgstats()
+    assert (sg.i, sg.nrelax, sg.resb, sg.resa) == (so.i, so.nrelax, so.resb, so.resa)
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    for _ in range(nsteps):
+        assert mg.step() == mo.step()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
