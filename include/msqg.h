@@ -83,6 +83,13 @@ enum {
   MSQG_ZETAP,     /* zetapl   msqg/qg.h:26  */
   MSQG_QPRED,     /* "predictor" list of the predictor-corrector */
   MSQG_SIGFILT,   /* sig_filt msqg/qg.h:48  (1 scalar) */
+  MSQG_DE_BF,     /* de_bfl   msqg/qg_energy.h:7   energy diagnostics (allocated on first use) */
+  MSQG_DE_VD,     /* de_vdl   msqg/qg_energy.h:8  */
+  MSQG_DE_J1,     /* de_j1l   msqg/qg_energy.h:9  */
+  MSQG_DE_J2,     /* de_j2l   msqg/qg_energy.h:10 */
+  MSQG_DE_J3,     /* de_j3l   msqg/qg_energy.h:11 */
+  MSQG_DE_FT,     /* de_ftl   msqg/qg_energy.h:12 (stays 0: filter_de needs the wavelet filter, out of scope) */
+  MSQG_PO_MFT,    /* po_mft   msqg/qg_energy.h:15 */
   MSQG_NFIELDS
 };
 
@@ -133,6 +140,10 @@ int msqg_advance(msqg_model *m, int out_id, int in_id, double dt);
  * tnext < 0: no event rounding (dt = update's dtmax).  returns dt in *dt_out. */
 int msqg_step(msqg_model *m, double t, double tnext, double *dt_out, double *tnext_out);
 int msqg_ke1(msqg_model *m, double *ke);          /* writestdout, qg.c:101-106 */
+/* energy diagnostics, msqg/qg_energy.h: energy_tend(pol, dt) of the comp_diag event (:228-242) with the weight
+ * switch `ediag` (0: -psi*dq/dt, 1: dq/dt; qg.h:87).  The de_* lists are created on first use (set_vars_energy). */
+int msqg_energy_tend(msqg_model *m, double dt, double ediag);
+int msqg_reset_energy(msqg_model *m);             /* reset_layer_var(de_*), qg.c:158-164; also creates the lists */
 /* the tendency of pystep_bfn (qg_bfn.h:21-80, vartype==1): q already set */
 int msqg_tendency_bfn(msqg_model *m, double direction);
 /* only the sign flips of pystep_bfn (qg_bfn.h:34-44) */
@@ -223,6 +234,12 @@ int pyq2p(double *po_py, int len7, int len8, int len9,
           double *qo_py, int len10, int len11, int len12);   /* qg_bfn.h:85 */
 int pyp2q(double *po_py, int len13, int len14, int len15,
           double *qo_py, int len16, int len17, int len18);   /* qg_bfn.h:95 */
+int set_vars_energy(void);                        /* qg_energy.h:244 */
+int trash_vars_energy(void);                      /* qg_energy.h:255 */
+int pystep_de(double *po_py, int len1, int len2, int len3, double *de_bf_py, int len4, int len5, int len6,
+              double *de_vd_py, int len7, int len8, int len9, double *de_j1_py, int len10, int len11, int len12,
+              double *de_j2_py, int len13, int len14, int len15, double *de_j3_py, int len16, int len17, int len18,
+              double *de_ft_py, int len19, int len20, int len21, int onlyKE);   /* qg_energy.h:294 (without filter_de) */
 int run(void);                                    /* Basilisk run() + qg.c events */
 /* access to the global handle/params behind the reference surface */
 msqg_model *qg_model(void);

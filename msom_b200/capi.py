@@ -15,7 +15,7 @@ LIB_CUDA = os.path.join(_HERE, "lib", "libmsqg_cuda.so")
 MAXL = 32
 
 (PSI, Q, PSIPG, FR, QFORC, TOPO, RD, SSTOCH, ZETA, DQ, STR, NSTOCH, IBU, CL2M, CM2L, PM, QM, TMP, ZETAP,
- QPRED) = range(20)
+ QPRED, SIGFILT, DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT) = range(28)
 
 OK, ERR_ARG, ERR_CUDA, ERR_FILE, ERR_CONFIG, ERR_NOCONV = 0, -1, -2, -3, -4, -5
 
@@ -81,6 +81,8 @@ def lib():
     L.msqg_destroy.argtypes = [vp]
     L.msqg_set_stream.argtypes = [vp, vp]
     L.msqg_nfields.argtypes = [vp, C.c_int]
+    L.msqg_energy_tend.argtypes = [vp, C.c_double, C.c_double]
+    L.msqg_reset_energy.argtypes = [vp]
     L.msqg_set_field.argtypes = [vp, C.c_int, dp]
     L.msqg_get_field.argtypes = [vp, C.c_int, dp]
     L.msqg_set_flag_topo.argtypes = [vp, C.c_int]
@@ -212,6 +214,13 @@ class Model:
         self.t = tn.value
         self.i += 1
         return dt.value
+
+    def energy_tend(self, dt, ediag=None):
+        """energy_tend(pol, dt), msqg/qg_energy.h:228-242"""
+        check(self.L.msqg_energy_tend(self.h, dt, float(self.p.ediag if ediag is None else ediag)))
+
+    def reset_energy(self):
+        check(self.L.msqg_reset_energy(self.h))
 
     def ke1(self):
         ke = C.c_double()

@@ -63,6 +63,8 @@ struct msqg_model {
   /* layer lists (finest level only unless noted) */
   List psi, q, qpred, dq, zeta, tmp, psipg, zetap, qforc, fr, str /*all levels*/, topo, rd, ro, sigfilt;
   List sstoch, nstoch;
+  List de_bf, de_vd, de_j1, de_j2, de_j3, de_ft, po_mft; /* energy diagnostics, qg_energy.h (allocated on first use) */
+  int nme_ft, energy_vars;
   List da, res; /* all levels; nf = nl */
   List pm, qm, ibu /*all levels*/, cl2m, cm2l;
   double dhf[MSQG_MAXL], dhc[MSQG_MAXL], idh0[MSQG_MAXL], idh1[MSQG_MAXL];
@@ -228,6 +230,10 @@ static List *list_by_id(msqg_model *m, int id) {
     case MSQG_QM: return &m->qm;       case MSQG_TMP: return &m->tmp;
     case MSQG_ZETAP: return &m->zetap; case MSQG_QPRED: return &m->qpred;
     case MSQG_SIGFILT: return &m->sigfilt;
+    case MSQG_DE_BF: return &m->de_bf; case MSQG_DE_VD: return &m->de_vd;
+    case MSQG_DE_J1: return &m->de_j1; case MSQG_DE_J2: return &m->de_j2;
+    case MSQG_DE_J3: return &m->de_j3; case MSQG_DE_FT: return &m->de_ft;
+    case MSQG_PO_MFT: return &m->po_mft;
   }
   return nullptr;
 }
@@ -374,6 +380,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
   CK(cudaMallocHost(&m->h_err, sizeof(int)));
   m->mailbox = nullptr; m->mailbox_words = 0; m->d_dbg = nullptr;
+  m->nme_ft = 0; m->energy_vars = 0;
   for (int l = 0; l <= MSQG_MAXLEV; l++) m->rowcoef[l] = nullptr;
   m->s_rowuniform = false;
   for (int l = 0; l < nl; l++) m->dhf[l] = p->dh[l]; /* qg.h:895-896 */
@@ -443,7 +450,8 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   List *all[] = {&m->psi, &m->q, &m->qpred, &m->dq, &m->zeta, &m->tmp, &m->psipg, &m->zetap, &m->qforc, &m->fr,
                  &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->sstoch, &m->nstoch, &m->da, &m->res,
-                 &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l};
+                 &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l,
+                 &m->de_bf, &m->de_vd, &m->de_j1, &m->de_j2, &m->de_j3, &m->de_ft, &m->po_mft};
   for (List *L : all) free_list(*L);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->d_scal) cudaFree(m->d_scal);
@@ -734,8 +742,7 @@ static int relax_variant() {
 }
 
 template <int NL, int K>
-static int launch_relax_t(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
-  if (relax_variant() == 1) return launch_relax_ws<NL, K>(m, da, res, lev, nsweeps, C);
+static int launch_relax_w_t(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   /* warps per CTA limited by the per-warp shared-memory rings */
   constexpr size_t spw = RelaxCfg<NL, K>::smem_per_warp;
   if constexpr (spw * 4 <= 200 * 1024) return launch_relax_w<NL, K, 4>(m, da, res, lev, nsweeps, C);
@@ -748,9 +755,12 @@ static int launch_relax(msqg_model *m, double *da, const double *res, int lev, i
   while (done < nrelax) {
     int ns = nrelax - done;
     int rc;
+    /* k_relax_ws is instantiated for K = 4 only (build time): more than 4 sweeps are consecutive launches, which
+       is the same arithmetic; the single-warp k_relax_lex keeps its 8-sweep instance */
     if (!m->s_uniform) { if (ns > 4) ns = 4; rc = launch_relax_rowcoef<NL>(m, da, res, lev, ns, C); }
-    else if (ns <= 4) rc = launch_relax_t<NL, 4>(m, da, res, lev, ns, C);
-    else { if (ns > 8) ns = 8; rc = launch_relax_t<NL, 8>(m, da, res, lev, ns, C); }
+    else if (relax_variant() == 1) { if (ns > 4) ns = 4; rc = launch_relax_ws<NL, 4>(m, da, res, lev, ns, C); }
+    else if (ns <= 4) rc = launch_relax_w_t<NL, 4>(m, da, res, lev, ns, C);
+    else { if (ns > 8) ns = 8; rc = launch_relax_w_t<NL, 8>(m, da, res, lev, ns, C); }
     if (rc) return rc;
     done += ns;
   }
@@ -1387,6 +1397,62 @@ extern "C" int msqg_step(msqg_model *m, double t, double tnext_event, double *dt
 }
 
 /* writestdout, qg.c:101-106 */
+/* ------------------------------------------------------------------ energy diagnostics, msqg/qg_energy.h */
+static int ensure_energy_lists(msqg_model *m) { /* set_vars_energy, qg_energy.h:244-253 */
+  if (m->energy_vars) return MSQG_OK;
+  List *L[7] = {&m->de_bf, &m->de_vd, &m->de_j1, &m->de_j2, &m->de_j3, &m->de_ft, &m->po_mft};
+  for (int k = 0; k < 7; k++) {
+    int rc = alloc_list(m, *L[k], m->nl, -1., m->depth, m->depth);
+    if (rc) return rc;
+  }
+  m->nme_ft = 0;
+  m->energy_vars = 1;
+  return MSQG_OK;
+}
+extern "C" int msqg_reset_energy(msqg_model *m) {
+  CK(cudaSetDevice(m->device));
+  int rc = ensure_energy_lists(m);
+  if (rc) return rc;
+  const int ids[6] = {MSQG_DE_BF, MSQG_DE_VD, MSQG_DE_J1, MSQG_DE_J2, MSQG_DE_J3, MSQG_DE_FT};
+  for (int k = 0; k < 6; k++) if ((rc = msqg_reset_field(m, ids[k]))) return rc;
+  return MSQG_OK;
+}
+extern "C" int msqg_energy_tend(msqg_model *m, double dt, double ediag) {
+  CK(cudaSetDevice(m->device));
+  if (!m->const_set) FAIL(MSQG_ERR_ARG, "set_const must be called before energy_tend");
+  if (m->g[m->depth].bc) FAIL(MSQG_ERR_ARG, "energy diagnostics are not available on decomposed grids");
+  int rc = ensure_energy_lists(m);
+  if (rc) return rc;
+  const int D = m->depth, nl = m->nl;
+  const Geom &g = m->g[D];
+  /* comp_del2(pol, zetal, 0., 1.) (:230); dissip_de's comp_del2(zetal, tmpl, 0., 1.) (:159) */
+  launch_lap(m->stream, nl, m->psi.lev[D], m->zeta.lev[D], g, nullptr);
+  m->launches++;
+  if (m->iRe != 0. || m->iRe4 != 0.) {
+    launch_lap(m->stream, nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+    m->launches++;
+  }
+  EnergyArgs A;
+  memset(&A, 0, sizeof(A));
+  A.psi = m->psi.lev[D]; A.zeta = m->zeta.lev[D]; A.tmp = m->tmp.lev[D]; A.pp = m->psipg.lev[D];
+  A.zp = m->zetap.lev[D]; A.s = m->str.lev[D];
+  A.de_bf = m->de_bf.lev[D]; A.de_vd = m->de_vd.lev[D]; A.de_j1 = m->de_j1.lev[D]; A.de_j2 = m->de_j2.lev[D];
+  A.de_j3 = m->de_j3.lev[D]; A.po_mft = m->po_mft.lev[D];
+  A.g = g;
+  for (int l = 0; l < nl; l++) { A.idh0[l] = m->idh0[l]; A.idh1[l] = m->idh1[l]; }
+  A.beta = m->p.beta; A.iRe = m->iRe; A.iRe4 = m->iRe4;
+  A.ceks = m->Eks / (m->p.Rom * 2 * m->dhf[0]);
+  A.cekb = m->Ekb / (m->p.Rom * 2 * m->dhf[nl - 1]);
+  A.dt = dt; A.ediag = ediag;
+  A.has_pg = m->has_pg; A.has_zp = m->has_zp; A.nme_ft = m->nme_ft;
+  dim3 b(32, 4);
+  NL_SWITCH(nl, k_energy<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(A));
+  m->launches++;
+  CK(cudaGetLastError());
+  m->nme_ft += 1;
+  return MSQG_OK;
+}
+
 extern "C" int msqg_ke1(msqg_model *m, double *ke) {
   CK(cudaSetDevice(m->device));
   const Geom &g = m->g[m->depth];

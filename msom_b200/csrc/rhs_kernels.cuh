@@ -286,6 +286,100 @@ k_rhs(RhsArgs A) {
   }
 }
 
+/* ------------------------------------------------------------------ energy diagnostics, msqg/qg_energy.h
+ * energy_tend (:228-242) in one pass: advection_de (:28-154, default build: _LS_RV, no ENERGY_CONSERV),
+ * dissip_de (:157-187), ekman_friction_de (:189-204) and the running mean po_mft, every term multiplied by
+ * dt*(-po*(1-ediag)+ediag) and accumulated in the reference's order.  zeta = laplacian(psi) and
+ * tmp = laplacian(zeta) (with their dirichlet ghosts) are prepared by k_lap2; the two comp_stretch passes of
+ * dissip_de are evaluated in place (add = 0, fac = 1: 0.*old + 1.*x == x for finite old). */
+struct EnergyArgs {
+  const double *psi, *zeta, *tmp, *pp, *zp, *s;
+  double *de_bf, *de_vd, *de_j1, *de_j2, *de_j3, *po_mft;
+  Geom g;
+  double idh0[MSQG_NLMAX], idh1[MSQG_NLMAX];
+  double beta, iRe, iRe4, ceks, cekb, dt, ediag;
+  int has_pg, has_zp, nme_ft;
+};
+
+template <int NL>
+__global__ void __launch_bounds__(128)
+k_energy(EnergyArgs A) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const Geom g = A.g;
+  if (x >= g.nx || y >= g.ny) return;
+  const size_t c = GIDX(g.pitch, y, x);
+  const int P = g.pitch;
+  const size_t pl = g.plane;
+  const double dt = A.dt, ediag = A.ediag;
+  double jd_1 = 0., jd_2 = 0., jd_3 = 0., ju_1, ju_2, ju_3, jc;
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const double *po = A.psi + l * pl, *qo = A.zeta + l * pl, *pp = A.pp + l * pl, *t1 = A.tmp + l * pl;
+    const double w = (-po[c] * (1 - ediag) + ediag);
+    ju_1 = -jd_1;
+    ju_2 = -jd_3; /* swap */
+    ju_3 = -jd_2; /* swap */
+    if (l < NL - 1) {
+      const double *po2 = A.psi + (l + 1) * pl, *pp2 = A.pp + (l + 1) * pl;
+      jd_1 = jac(po, po2, c, P, g);
+      jd_2 = A.has_pg ? jac(pp, po2, c, P, g) : 0.;
+      jd_3 = A.has_pg ? jac(po, pp2, c, P, g) : 0.;
+    }
+    jc = A.has_pg ? jac(po, pp, c, P, g) : 0.;
+    const double j1 = jac(po, qo, c, P, g);
+    const double j2 = A.has_pg ? jac(pp, qo, c, P, g) : 0.;
+    const double be = div_by(A.beta * (po[c - 1] - po[c + 1]), g.D2x, g.rD2x);
+    double a1, a2, a3;
+    if (l == 0) {
+      const double s1 = A.s[c];
+      a1 = j1 + s1 * jd_1 * A.idh1[0];
+      a2 = j2 + s1 * (jd_2 + jc) * A.idh1[0];
+      a3 = be + s1 * (jd_3 - jc) * A.idh1[0];
+    } else if (l < NL - 1) {
+      const double s0 = A.s[(l - 1) * pl + c], s1 = A.s[l * pl + c];
+      a1 = j1 + s0 * ju_1 * A.idh0[l] + s1 * jd_1 * A.idh1[l];
+      a2 = j2 + s0 * (ju_2 + jc) * A.idh0[l] + s1 * (jd_2 + jc) * A.idh1[l];
+      a3 = be + s0 * (ju_3 - jc) * A.idh0[l] + s1 * (jd_3 - jc) * A.idh1[l];
+    } else {
+      const double s0 = A.s[(l - 1) * pl + c];
+      a1 = j1 + s0 * ju_1 * A.idh0[l];
+      a2 = j2 + s0 * (ju_2 + jc) * A.idh0[l];
+      a3 = be + s0 * (ju_3 - jc) * A.idh0[l];
+    }
+    A.de_j1[l * pl + c] += a1 * dt * w;
+    if (A.has_pg) A.de_j2[l * pl + c] += a2 * dt * w;
+    double d3 = A.de_j3[l * pl + c];
+    d3 += a3 * dt * w;
+    if (A.has_zp) d3 += jac(po, A.zp + l * pl, c, P, g) * dt * w;
+    A.de_j3[l * pl + c] = d3;
+    /* dissip_de */
+    if (A.iRe != 0. || A.iRe4 != 0.) {
+      double str, str2;
+      if (l == 0) {
+        str = 1. * A.s[c] * (qo[pl + c] - qo[c]) * A.idh1[0];
+        str2 = 1. * A.s[c] * (t1[pl + c] - t1[c]) * A.idh1[0];
+      } else if (l < NL - 1) {
+        str = 1. * (A.s[(l - 1) * pl + c] * (qo[c - pl] - qo[c]) * A.idh0[l] + A.s[l * pl + c] * (qo[c + pl] - qo[c]) * A.idh1[l]);
+        str2 = 1. * (A.s[(l - 1) * pl + c] * (t1[c - pl] - t1[c]) * A.idh0[l] + A.s[l * pl + c] * (t1[c + pl] - t1[c]) * A.idh1[l]);
+      } else {
+        str = 1. * A.s[(l - 1) * pl + c] * (qo[c - pl] - qo[c]) * A.idh0[l];
+        str2 = 1. * A.s[(l - 1) * pl + c] * (t1[c - pl] - t1[c]) * A.idh0[l];
+      }
+      double dv = A.de_vd[l * pl + c];
+      dv += (t1[c] + str) * A.iRe * dt * w;
+      dv += lapf(A.iRe4, t1, c, P, g) * dt * w;
+      dv += A.iRe4 * (str2) * dt * w;
+      A.de_vd[l * pl + c] = dv;
+    }
+    /* ekman_friction_de */
+    if (l == 0) A.de_bf[c] -= A.ceks * qo[c] * dt * w;
+    if (l == NL - 1) A.de_bf[l * pl + c] -= A.cekb * qo[c] * dt * w;
+    /* running mean of psi for filter_de */
+    A.po_mft[l * pl + c] = (A.po_mft[l * pl + c] * A.nme_ft + po[c]) / (A.nme_ft + 1);
+  }
+}
+
 /* advance_qg alone (API parity with the function-pointer plugin, qg.h:594-606) */
 __global__ void k_advance(double *__restrict__ out, const double *__restrict__ in, const double *__restrict__ dq,
                           const double *__restrict__ noise, Geom g, double dt, float dts) {

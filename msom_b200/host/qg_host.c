@@ -215,6 +215,21 @@ static int write_list(const char *name, int id) {
   return rc;
 }
 
+/* write_field(list, name, rescale), auxiliar_input.h:153-167: psi[] *= rescale, then the float32 matrix */
+static int write_list_scaled(const char *name, int id, double rescale) {
+  const int nf = msqg_nfields(M, id);
+  if (nf <= 0) return MSQG_ERR_ARG;
+  size_t sz = (size_t)nf * P.N * P.N;
+  double *buf = (double *)malloc(sizeof(double) * sz);
+  int rc = msqg_get_field(M, id, buf);
+  if (!rc) {
+    if (rescale != 0) for (size_t c = 0; c < sz; c++) buf[c] *= rescale;
+    rc = qg_write_bas(name, nf, P.N, P.L0, buf);
+  }
+  free(buf);
+  return rc;
+}
+
 int backup_config(void) {
   if (!M) return MSQG_ERR_ARG;
   fprintf(stdout, "Backup config\n");
@@ -299,6 +314,31 @@ int pyp2q(double *po_py, int len13, int len14, int len15, double *qo_py, int len
   return MSQG_OK;
 }
 
+/* ---------------------------------------------------------------- energy diagnostics, qg_energy.h / qg_energy.i */
+int set_vars_energy(void) { return M ? fail(msqg_reset_energy(M)) : MSQG_ERR_ARG; }
+int trash_vars_energy(void) { return MSQG_OK; } /* the lists live and die with the handle (trash_vars) */
+/* pystep_de, qg_energy.h:294-340: ediag = 1, dt = 1 (locals).  filter_de needs the wavelet filter (out of scope):
+ * de_ft is returned as reset.  onlyKE zeroes the stretching field, as the reference does (permanently). */
+int pystep_de(double *po_py, int len1, int len2, int len3, double *de_bf_py, int len4, int len5, int len6,
+              double *de_vd_py, int len7, int len8, int len9, double *de_j1_py, int len10, int len11, int len12,
+              double *de_j2_py, int len13, int len14, int len15, double *de_j3_py, int len16, int len17, int len18,
+              double *de_ft_py, int len19, int len20, int len21, int onlyKE) {
+  if (!M) return MSQG_ERR_ARG;
+  if (!shape_ok(len1, len2, len3) || !shape_ok(len4, len5, len6) || !shape_ok(len7, len8, len9) ||
+      !shape_ok(len10, len11, len12) || !shape_ok(len13, len14, len15) || !shape_ok(len16, len17, len18) ||
+      !shape_ok(len19, len20, len21)) return MSQG_ERR_ARG;
+  int rc;
+  if ((rc = msqg_set_field(M, MSQG_PSI, po_py))) return fail(rc);
+  if ((rc = msqg_reset_energy(M))) return fail(rc);
+  if ((rc = msqg_comp_q(M))) return fail(rc);
+  if (onlyKE == 1 && (rc = msqg_reset_field(M, MSQG_STR))) return fail(rc);
+  if ((rc = msqg_energy_tend(M, 1., 1.))) return fail(rc);
+  double *out[6] = {de_bf_py, de_vd_py, de_j1_py, de_j2_py, de_j3_py, de_ft_py};
+  const int ids[6] = {MSQG_DE_BF, MSQG_DE_VD, MSQG_DE_J1, MSQG_DE_J2, MSQG_DE_J3, MSQG_DE_FT};
+  for (int k = 0; k < 6; k++) if ((rc = msqg_get_field(M, ids[k], out[k]))) return fail(rc);
+  return MSQG_OK;
+}
+
 /* ---------------------------------------------------------------- run() */
 /* init event, qg.c:53-72: psi from p0.bas or 1e-3*noise(), mean removed.
  * noise() = 1 - 2*rand()/RAND_MAX [BASILISK]; traversal x outer, y inner, layers innermost. */
@@ -334,6 +374,11 @@ int qg_run_reset(void) { ev_out_t = 0.; ev_out_alive = 1; g_t = 0.; g_i = 0; g_d
 
 int qg_run_iteration(int write_files) {
   int rc;
+  /* comp_diag (i++), qg_energy.h:289-291: defined before qg.c's events, so it runs first.  `dt` is [BASILISK]'s
+     global time step, 1. before the first step (common.h) */
+  if (P.ediag > -1) {
+    if ((rc = msqg_energy_tend(M, g_i == 0 ? 1. : g_dt, (double)P.ediag))) return fail(rc);
+  }
   /* writestdout (i++), qg.c:101-109 */
   if (g_verbose) {
     double ke = 0.;
@@ -351,6 +396,19 @@ int qg_run_iteration(int write_files) {
       write_list(name, MSQG_PSI);
       snprintf(name, sizeof(name), "%sqo%09d.bas", dpath, g_i);
       write_list(name, MSQG_Q);
+    }
+    if (P.ediag > -1) { /* qg.c:139-166: write_field(de_*, name, 1/dtout), then reset_layer_var */
+      static const char *nm[6] = {"de_bf", "de_vd", "de_j1", "de_j2", "de_j3", "de_ft"};
+      static const int ids[6] = {MSQG_DE_BF, MSQG_DE_VD, MSQG_DE_J1, MSQG_DE_J2, MSQG_DE_J3, MSQG_DE_FT};
+      const double idtout = 1 / P.dtout;
+      if (write_files) {
+        char name[200];
+        for (int k = 0; k < 6; k++) {
+          snprintf(name, sizeof(name), "%s%s%09d.bas", dpath, nm[k], g_i);
+          write_list_scaled(name, ids[k], idtout);
+        }
+      }
+      if ((rc = msqg_reset_energy(M))) return fail(rc);
     }
     ev_out_t += P.dtout;
     if (!(ev_out_t <= P.tend + 1e-10)) ev_out_alive = 0;

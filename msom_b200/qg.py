@@ -37,6 +37,7 @@ def _L():
         L.pystep_bfn.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
         L.pyq2p.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int]
         L.pyp2q.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int]
+        L.pystep_de.argtypes = [dp, C.c_int, C.c_int, C.c_int] * 7 + [C.c_int]
         L.qg_model.restype = C.c_void_p
         L.qg_params.restype = C.POINTER(capi.Params)
         L.qg_set_device.argtypes = [C.c_int]
@@ -117,6 +118,23 @@ def pyq2p(po, qo):
 def pyp2q(po, qo):
     p, q = _in(po), _inplace(qo)
     _ck(_L().pyp2q(p, *p.shape, q, *q.shape), "pyp2q")
+
+
+def set_vars_energy():
+    _ck(_L().set_vars_energy(), "set_vars_energy")
+
+
+def trash_vars_energy():
+    _ck(_L().trash_vars_energy(), "trash_vars_energy")
+
+
+def pystep_de(po, de_bf, de_vd, de_j1, de_j2, de_j3, de_ft, onlyKE=0):
+    """qg_energy.i:30-39: energy tendencies of the state po (all de_* arrays are written in place)"""
+    args = [_in(po)] + [_inplace(a) for a in (de_bf, de_vd, de_j1, de_j2, de_j3, de_ft)]
+    flat = []
+    for a in args:
+        flat += [a, *a.shape]
+    _ck(_L().pystep_de(*flat, int(onlyKE)), "pystep_de")
 
 
 def run():

@@ -144,6 +144,9 @@ struct orc_model {
   flist dql;    /* "updates" */
   flist qpred;  /* "predictor" */
   flist s_stochl, n_stochl;
+  /* qg_energy.h:7-17 */
+  flist de_bfl, de_vdl, de_j1l, de_j2l, de_j3l, de_ftl, tmp2l, po_mft;
+  int nme_ft, energy_vars;
   int flag_topo;
   double iRe, iRe4, Eks, Ekb;
   /* timestep() static, [BASILISK] timestep.h; copy newqg/qg.h:202-219 */
@@ -295,7 +298,8 @@ void orc_destroy(orc_model *m) {
   if (!m) return;
   flist *all[] = {&m->pol, &m->qol, &m->zetal, &m->zetapl, &m->q_forcl, &m->tmpl, &m->ppl,
                   &m->Frl, &m->strl, &m->qom, &m->pom, &m->iBul, &m->cl2m, &m->cm2l, &m->Ro,
-                  &m->Rd, &m->topo, &m->sig_filt, &m->dql, &m->qpred, &m->s_stochl, &m->n_stochl};
+                  &m->Rd, &m->topo, &m->sig_filt, &m->dql, &m->qpred, &m->s_stochl, &m->n_stochl,
+                  &m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl, &m->tmp2l, &m->po_mft};
   for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); k++) fl_free(all[k]);
   free(m->dhc); free(m->dhf); free(m->idh0); free(m->idh1);
   free(m);
@@ -313,6 +317,10 @@ static flist *list_by_id(orc_model *m, int id) {
     case ORC_CM2L: return &m->cm2l; case ORC_PM: return &m->pom;
     case ORC_QM: return &m->qom;    case ORC_TMP: return &m->tmpl;
     case ORC_ZETAP: return &m->zetapl;
+    case ORC_DE_BF: return &m->de_bfl; case ORC_DE_VD: return &m->de_vdl;
+    case ORC_DE_J1: return &m->de_j1l; case ORC_DE_J2: return &m->de_j2l;
+    case ORC_DE_J3: return &m->de_j3l; case ORC_DE_FT: return &m->de_ftl;
+    case ORC_PO_MFT: return &m->po_mft;
   }
   return NULL;
 }
@@ -1155,6 +1163,8 @@ int orc_read_bas(const char *name, int nf, int N, double L0, double *v) {
 
 /* [BASILISK] run() of predictor-corrector.h with the events of qg.c:
  * writestdout (i++), output (t=0; t<=tend+1e-10; t+=dtout), and dtnext(). */
+static void energy_tend(orc_model *m, flist *pl, double dt, double ediag);
+static void reset_layer_var(orc_model *m, flist *f);
 int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, int verbose) {
   double ev_t = 0.;
   int ev_alive = 1, steps = 0;
@@ -1162,6 +1172,9 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
   double *buf = write_files ? (double *)malloc(sizeof(double) * sz) : NULL;
   char name[512];
   while (1) {
+    /* comp_diag (i++), qg_energy.h:289-291: defined before qg.c's events, so it runs first; `dt` is [BASILISK]'s
+       global, 1. before the first step (common.h) */
+    if (m->p.ediag > -1) energy_tend(m, &m->pol, m->iter == 0 ? 1. : m->dt, (double)m->p.ediag);
     if (verbose) {
       double ke = orc_ke1(m);
       fprintf(stdout, "i = %i, dt = %g, t = %g, ke_1 = %g\n", m->iter, m->dt, m->t, ke);
@@ -1177,6 +1190,20 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
         get_list(&m->qol, m->N, buf);
         snprintf(name, sizeof(name), "%s/qo%09d.bas", outdir, m->iter);
         orc_write_bas(name, m->nl, m->N, m->L0, buf);
+      }
+      if (m->p.ediag > -1) { /* qg.c:139-166: write_field(de_*, name, 1/dtout) then reset */
+        static const char *nm[6] = {"de_bf", "de_vd", "de_j1", "de_j2", "de_j3", "de_ft"};
+        flist *L[6] = {&m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl};
+        double idtout = 1 / m->p.dtout;
+        for (int k = 0; k < 6; k++) {
+          if (write_files) {
+            get_list(L[k], m->N, buf);
+            for (size_t c = 0; c < sz; c++) buf[c] *= idtout;
+            snprintf(name, sizeof(name), "%s/%s%09d.bas", outdir, nm[k], m->iter);
+            orc_write_bas(name, m->nl, m->N, m->L0, buf);
+          }
+          reset_layer_var(m, L[k]);
+        }
       }
       ev_t += m->p.dtout;
       if (!(ev_t <= m->p.tend + 1e-10)) ev_alive = 0;
@@ -1203,6 +1230,162 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
   }
   free(buf);
   return steps;
+}
+
+/* ----------------------------------------------------------- energy diagnostics, msqg/qg_energy.h
+ * "We multiply all terms of the PV equation by -po*dt" (:1-5).  Built as the reference is by default:
+ * _LS_RV = 1, no ENERGY_CONSERV. */
+static void set_vars_energy(orc_model *m) { /* qg_energy.h:244-253 */
+  if (m->energy_vars) return;
+  flist *L[8] = {&m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl, &m->tmp2l, &m->po_mft};
+  for (int k = 0; k < 8; k++) *L[k] = create_layer_var(m->nl, 0, m->depth);
+  m->nme_ft = 0;
+  m->energy_vars = 1;
+}
+static void reset_layer_var(orc_model *m, flist *f) { /* layer.h:37-41 */
+  int n = m->N, D = m->depth;
+  for (int l = 0; l < f->nf; l++)
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) FL(f, l, D)[IDX(n, i, j)] = 0.;
+}
+void orc_reset_energy(orc_model *m) {
+  set_vars_energy(m);
+  flist *L[6] = {&m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl};
+  for (int k = 0; k < 6; k++) reset_layer_var(m, L[k]);
+}
+/* advection_de, qg_energy.h:28-154; called with qol = zetal (:231) */
+static void advection_de(orc_model *m, flist *ql, flist *pl, double dt, double ediag) {
+  int n = m->N, D = m->depth, nl = m->nl;
+  double Delta = m->L0 / n, beta = m->p.beta;
+  const double *idh0 = m->idh0, *idh1 = m->idh1;
+#define JC(a, b) jacobian(a, b, n, i, j, Delta)
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      size_t c = IDX(n, i, j);
+      double ju_1, jd_1, ju_2, jd_2, ju_3, jd_3, jc;
+      if (nl > 1) {
+        int l = 0;
+        const double *qo = FL(ql, l, D), *po = FL(pl, l, D), *pp = FL(&m->ppl, l, D), *qp = FL(&m->zetapl, l, D);
+        const double *po2 = FL(pl, l + 1, D), *pp2 = FL(&m->ppl, l + 1, D);
+        const double *s1 = FL(&m->strl, l, D), *s0;
+        double *de_j1 = FL(&m->de_j1l, l, D), *de_j2 = FL(&m->de_j2l, l, D), *de_j3 = FL(&m->de_j3l, l, D);
+        jd_1 = JC(po, po2);
+        jd_2 = JC(pp, po2);
+        jd_3 = JC(po, pp2);
+        jc = JC(po, pp);
+        de_j1[c] += (JC(po, qo) + s1[c] * jd_1 * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        de_j2[c] += (JC(pp, qo) + s1[c] * (jd_2 + jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        de_j3[c] += (BETA_EFFECT(po, n, i, j, beta, Delta) + s1[c] * (jd_3 - jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        de_j3[c] += JC(po, qp) * dt * (-po[c] * (1 - ediag) + ediag);
+        for (l = 1; l < nl - 1; l++) {
+          qo = FL(ql, l, D); po = FL(pl, l, D); pp = FL(&m->ppl, l, D); qp = FL(&m->zetapl, l, D);
+          po2 = FL(pl, l + 1, D); pp2 = FL(&m->ppl, l + 1, D);
+          de_j1 = FL(&m->de_j1l, l, D); de_j2 = FL(&m->de_j2l, l, D); de_j3 = FL(&m->de_j3l, l, D);
+          s0 = FL(&m->strl, l - 1, D); s1 = FL(&m->strl, l, D);
+          ju_1 = -jd_1;
+          ju_2 = -jd_3; /* swap */
+          ju_3 = -jd_2; /* swap */
+          jd_1 = JC(po, po2);
+          jd_2 = JC(pp, po2);
+          jd_3 = JC(po, pp2);
+          jc = JC(po, pp);
+          de_j1[c] += (JC(po, qo) + s0[c] * ju_1 * idh0[l] + s1[c] * jd_1 * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+          de_j2[c] += (JC(pp, qo) + s0[c] * (ju_2 + jc) * idh0[l] + s1[c] * (jd_2 + jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+          de_j3[c] += (BETA_EFFECT(po, n, i, j, beta, Delta) + s0[c] * (ju_3 - jc) * idh0[l] + s1[c] * (jd_3 - jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+          de_j3[c] += JC(po, qp) * dt * (-po[c] * (1 - ediag) + ediag);
+        }
+        l = nl - 1;
+        qo = FL(ql, l, D); po = FL(pl, l, D); pp = FL(&m->ppl, l, D); qp = FL(&m->zetapl, l, D);
+        de_j1 = FL(&m->de_j1l, l, D); de_j2 = FL(&m->de_j2l, l, D); de_j3 = FL(&m->de_j3l, l, D);
+        s0 = FL(&m->strl, l - 1, D);
+        ju_1 = -jd_1;
+        ju_2 = -jd_3; /* swap */
+        ju_3 = -jd_2; /* swap */
+        jc = JC(po, pp);
+        de_j1[c] += (JC(po, qo) + s0[c] * ju_1 * idh0[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        de_j2[c] += (JC(pp, qo) + s0[c] * (ju_2 + jc) * idh0[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        de_j3[c] += (BETA_EFFECT(po, n, i, j, beta, Delta) + s0[c] * (ju_3 - jc) * idh0[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        de_j3[c] += JC(po, qp) * dt * (-po[c] * (1 - ediag) + ediag);
+      } else {
+        FL(&m->de_j1l, 0, D)[c] = 0; FL(&m->de_j2l, 0, D)[c] = 0; FL(&m->de_j3l, 0, D)[c] = 0;
+      }
+    }
+#undef JC
+}
+/* dissip_de, qg_energy.h:157-187 */
+static void dissip_de(orc_model *m, flist *zl, flist *dql, flist *pl, double dt, double ediag) {
+  int n = m->N, D = m->depth, nl = m->nl;
+  double Delta = m->L0 / n;
+  comp_del2(m, zl, &m->tmpl, 0., 1.);
+  comp_stretch(m, zl, &m->tmp2l, 0., 1.);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) {
+        size_t c = IDX(n, i, j);
+        double *dqo = FL(dql, l, D);
+        const double *p4 = FL(&m->tmpl, l, D), *str = FL(&m->tmp2l, l, D), *po = FL(pl, l, D);
+        dqo[c] += (p4[c] + str[c]) * m->iRe * dt * (-po[c] * (1 - ediag) + ediag);
+        dqo[c] += m->iRe4 * LAP(p4, n, i, j, Delta) * dt * (-po[c] * (1 - ediag) + ediag);
+      }
+  comp_stretch(m, &m->tmpl, &m->tmp2l, 0., 1.);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) {
+        size_t c = IDX(n, i, j);
+        double *dqo = FL(dql, l, D);
+        const double *str = FL(&m->tmp2l, l, D), *po = FL(pl, l, D);
+        dqo[c] += m->iRe4 * (str[c]) * dt * (-po[c] * (1 - ediag) + ediag);
+      }
+}
+/* ekman_friction_de, qg_energy.h:189-204 */
+static void ekman_friction_de(orc_model *m, flist *zl, flist *dql, flist *pl, double dt, double ediag) {
+  int n = m->N, D = m->depth, nl = m->nl;
+  double Rom = m->p.Rom;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      size_t c = IDX(n, i, j);
+      FL(dql, 0, D)[c] -= m->Eks / (Rom * 2 * m->dhf[0]) * FL(zl, 0, D)[c] * dt * (-FL(pl, 0, D)[c] * (1 - ediag) + ediag);
+      FL(dql, nl - 1, D)[c] -= m->Ekb / (Rom * 2 * m->dhf[nl - 1]) * FL(zl, nl - 1, D)[c] * dt * (-FL(pl, nl - 1, D)[c] * (1 - ediag) + ediag);
+    }
+}
+/* energy_tend, qg_energy.h:228-242 */
+static void energy_tend(orc_model *m, flist *pl, double dt, double ediag) {
+  int n = m->N, D = m->depth, nl = m->nl;
+  set_vars_energy(m);
+  comp_del2(m, pl, &m->zetal, 0., 1.0);
+  advection_de(m, &m->zetal, pl, dt, ediag);
+  dissip_de(m, &m->zetal, &m->de_vdl, pl, dt, ediag);
+  ekman_friction_de(m, &m->zetal, &m->de_bfl, pl, dt, ediag);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) {
+        size_t c = IDX(n, i, j);
+        double *pm = FL(&m->po_mft, l, D);
+        pm[c] = (pm[c] * m->nme_ft + FL(pl, l, D)[c]) / (m->nme_ft + 1);
+      }
+  m->nme_ft += 1;
+}
+void orc_energy_tend(orc_model *m, double dt) { energy_tend(m, &m->pol, dt, (double)m->p.ediag); }
+/* pystep_de, qg_energy.h:294-340: ediag = 1, dt = 1 (locals shadow the globals); filter_de (wavelet filter) is
+ * out of scope, de_ft is returned as reset (0) */
+void orc_pystep_de(orc_model *m, const double *po_py, double *de_bf, double *de_vd, double *de_j1, double *de_j2,
+                   double *de_j3, double *de_ft, int onlyKE) {
+  int n = m->N, D = m->depth, nl = m->nl;
+  double ediag = 1., dt = 1.;
+  set_list(&m->pol, n, po_py);
+  orc_reset_energy(m);
+  comp_del2(m, &m->pol, &m->zetal, 0., 1.0);
+  comp_q(m, &m->pol, &m->qol);
+  if (onlyKE == 1)
+    for (int l = 0; l < nl - 1; l++)
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) FL(&m->strl, l, D)[IDX(n, i, j)] = 0.;
+  advection_de(m, &m->zetal, &m->pol, dt, ediag);
+  dissip_de(m, &m->zetal, &m->de_vdl, &m->pol, dt, ediag);
+  ekman_friction_de(m, &m->zetal, &m->de_bfl, &m->pol, dt, ediag);
+  get_list(&m->de_bfl, n, de_bf); get_list(&m->de_vdl, n, de_vd);
+  get_list(&m->de_j1l, n, de_j1); get_list(&m->de_j2l, n, de_j2);
+  get_list(&m->de_j3l, n, de_j3); get_list(&m->de_ftl, n, de_ft);
 }
 
 /* python entry points, qg_bfn.h:21-103 */

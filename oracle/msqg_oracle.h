@@ -53,7 +53,9 @@ typedef struct orc_model orc_model;
 enum {
   ORC_PSI = 0, ORC_Q, ORC_PSIPG, ORC_FR, ORC_QFORC, ORC_TOPO, ORC_RD, ORC_SSTOCH,
   ORC_ZETA, ORC_DQ, ORC_STR, ORC_NSTOCH, ORC_IBU, ORC_CL2M, ORC_CM2L, ORC_PM, ORC_QM,
-  ORC_TMP, ORC_ZETAP
+  ORC_TMP, ORC_ZETAP,
+  /* energy diagnostics, msqg/qg_energy.h:7-15 */
+  ORC_DE_BF, ORC_DE_VD, ORC_DE_J1, ORC_DE_J2, ORC_DE_J3, ORC_DE_FT, ORC_PO_MFT
 };
 
 void orc_default_params(orc_params *p);
@@ -87,6 +89,15 @@ double orc_step(orc_model *m);
 int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, int verbose);
 double orc_time(orc_model *m);
 double orc_ke1(orc_model *m);                    /* qg.c:101-106 */
+
+/* energy diagnostics, msqg/qg_energy.h (ediag > -1): energy_tend(pol, dt) of the comp_diag event (:228-242,289-291);
+   the lists are created on first use (set_vars_energy, :244-253).  filter_de needs the wavelet filter, which is
+   out of scope: de_ft stays 0. */
+void orc_energy_tend(orc_model *m, double dt);
+void orc_reset_energy(orc_model *m);             /* reset_layer_var on the de_* lists, qg.c:158-164 */
+/* pystep_de, qg_energy.h:294-340 (ediag = 1, dt = 1; without filter_de) */
+void orc_pystep_de(orc_model *m, const double *po, double *de_bf, double *de_vd, double *de_j1, double *de_j2,
+                   double *de_j3, double *de_ft, int onlyKE);
 
 /* python entry points, msqg/qg_bfn.h */
 void orc_pystep_bfn(orc_model *m, const double *q_in, double *tend, double direction, int vartype);

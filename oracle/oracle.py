@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 MAXL = 32
 
 PSI, Q, PSIPG, FR, QFORC, TOPO, RD, SSTOCH, ZETA, DQ, STR, NSTOCH, IBU, CL2M, CM2L, PM, QM, TMP, ZETAP = range(19)
+DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT = range(19, 26)  # energy diagnostics, qg_energy.h
 
 
 class Params(C.Structure):
@@ -102,6 +103,9 @@ def lib(omp=False):
     L.orc_ke1.argtypes = [vp]
     L.orc_ke1.restype = C.c_double
     L.orc_pystep_bfn.argtypes = [vp, dp, dp, C.c_double, C.c_int]
+    L.orc_energy_tend.argtypes = [vp, C.c_double]
+    L.orc_reset_energy.argtypes = [vp]
+    L.orc_pystep_de.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, C.c_int]
     L.orc_pyq2p.argtypes = [vp, dp, dp]
     L.orc_pyp2q.argtypes = [vp, dp, dp]
     L.orc_test_relax.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int]
@@ -210,3 +214,14 @@ class Model:
 
     def ke1(self):
         return self.L.orc_ke1(self.h)
+
+    def energy_tend(self, dt):
+        self.L.orc_energy_tend(self.h, dt)
+
+    def reset_energy(self):
+        self.L.orc_reset_energy(self.h)
+
+    def pystep_de(self, po, onlyKE=0):
+        out = [np.zeros_like(po) for _ in range(6)]
+        self.L.orc_pystep_de(self.h, np.ascontiguousarray(po), *out, onlyKE)
+        return out

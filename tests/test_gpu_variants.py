@@ -160,3 +160,57 @@ def test_variable_rossby_number(gpu, N, nl, nsteps):
         assert mg.step() == mo.step()
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
     assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
+
+
+@pytest.mark.parametrize("N,nl,ediag,over", [(64, 2, 0, {}), (128, 3, 1, dict(Re=200.)), (64, 4, 0, dict(Re=50., Eks=0.001)),
+                                              (64, 3, 0, dict(upg=[0.3, 0.1, 0.], vpg=[0.05, 0., 0.], flsrv=1))])
+def test_energy_diagnostics(gpu, N, nl, ediag, over):
+    """energy_tend (msqg/qg_energy.h:228-242): advection_de, dissip_de, ekman_friction_de and the running mean
+    po_mft accumulated over several steps, bit-exact against the oracle, with viscosity, surface drag and a
+    background (planetary-geostrophic) flow."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    mo, mg, _ = make_pair(N, nl, ediag=ediag, **over)
+    mo.set_const(); mg.set_const()
+    for k in range(3):
+        dto, dtg = mo.step(), mg.step()
+        assert dto == dtg
+        mo.energy_tend(dto); mg.energy_tend(dtg)
+    for fo, fg in ((O.DE_BF, G.DE_BF), (O.DE_VD, G.DE_VD), (O.DE_J1, G.DE_J1), (O.DE_J2, G.DE_J2), (O.DE_J3, G.DE_J3),
+                   (O.DE_FT, G.DE_FT), (O.PO_MFT, G.PO_MFT), (O.ZETA, G.ZETA)):
+        a, b = mg.get(fg), mo.get(fo)
+        assert np.array_equal(a, b), (fg, float(np.abs(a - b).max()))
+    assert np.abs(mg.get(G.DE_J1)).max() > 0
+    mo.reset_energy(); mg.reset_energy()
+    assert not mg.get(G.DE_J1).any() and not mg.get(G.DE_VD).any()
+
+
+def test_pystep_de_python_entry(gpu):
+    """pystep_de of the SWIG module (msqg/qg_energy.i:30-39) through the ctypes mirror, against the oracle"""
+    from oracle import oracle as O
+    import msom_b200.qg as bas
+    N, nl = 64, 3
+    kw = base_kw(N, nl, Re=100.)
+    mo = O.Model(O.make_params(**kw))
+    psi = synth_psi(N, nl)
+    mo.set(O.PSI, psi); mo.set_const()
+    ref = mo.pystep_de(psi)
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "params.in")
+        with open(path, "w") as f:
+            f.write("#!sh\n")
+            for k, v in kw.items():
+                f.write("%s = %s\n" % (k, ("[" + ",".join(repr(float(x)) for x in v) + "]") if isinstance(v, (list, tuple)) else repr(v)))
+        bas.set_device(gpu)
+        bas.read_params(path)
+        bas.init_grid(N)
+        bas.set_vars()
+        bas.set_vars_energy()
+        bas.set_const()
+        out = [np.zeros_like(psi) for _ in range(6)]
+        bas.pystep_de(psi, *out)
+        bas.trash_vars_energy()
+        bas.trash_vars()
+    for a, b in zip(out, ref):
+        assert np.array_equal(a, b), float(np.abs(a - b).max())

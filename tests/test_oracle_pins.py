@@ -173,3 +173,30 @@ def test_golden_regression():
     m = _model(32, 3, mode_pv_invert=1)
     dts = [m.step() for _ in range(2)]
     assert rel_l2(m.get(O.PSI), g["psi"]) < 1e-11   # LAPACK builds may differ in the last bits
+
+
+def test_energy_budget_identities():
+    """qg_energy.h: with the weight -psi (ediag = 0) the advective terms integrate to zero -- the Arakawa
+    Jacobian conserves energy and the stretching Jacobians of neighbouring layers cancel in the
+    thickness-weighted sum (psi supported away from the walls); viscous and drag terms dissipate."""
+    N, nl = 64, 3
+    kw = base_kw(N, nl, beta=0., tau0=0., Re=500., Eks=0.002, ediag=0)
+    m = O.Model(O.make_params(**kw))
+    rng = np.random.default_rng(1)
+    psi = np.zeros((nl, N, N))
+    psi[:, 8:-8, 8:-8] = rng.standard_normal((nl, N - 16, N - 16))
+    for _ in range(4):
+        psi[:, 1:-1, 1:-1] = 0.25 * (psi[:, :-2, 1:-1] + psi[:, 2:, 1:-1] + psi[:, 1:-1, :-2] + psi[:, 1:-1, 2:])
+    m.set(O.PSI, psi); m.set_const()
+    m.energy_tend(1.0)
+    dh = np.array(kw["dh"])[:, None, None]
+    j1 = m.get(O.DE_J1)
+    assert np.abs(j1).max() > 0
+    assert abs((j1 * dh).sum()) < 1e-9 * (np.abs(j1) * dh).sum()       # sum_l dh_l sum psi_l * (J + stretching) = 0
+    assert not m.get(O.DE_J2).any()                                     # no background flow
+    assert (m.get(O.DE_BF) * dh).sum() < 0                              # Ekman drag removes energy
+    assert np.array_equal(m.get(O.PO_MFT), m.get(O.PSI))                # running mean after one sample
+    m.energy_tend(1.0)
+    assert np.allclose(m.get(O.DE_J1), 2 * j1, rtol=1e-13, atol=0)      # accumulates
+    m.reset_energy()
+    assert not m.get(O.DE_J1).any()
