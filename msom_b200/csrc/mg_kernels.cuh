@@ -776,7 +776,9 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   /* internal sides (multi-GPU tiles, single-sweep launches only): ghosts are stored halo values */
   const bool lint = TILE && (A.g.bc & 1), rint = TILE && (A.g.bc & 2), bint = TILE && (A.g.bc & 4), tint = TILE && (A.g.bc & 8);
   const int r_first = bint ? -1 : 0, r_last = tint ? ny : ny - 1; /* rows of the iterate that are streamed */
-  const int w = A.w_base + blockIdx.x * WPC + wl;
+  /* the same value in every lane; routed through a shuffle because ptxas then keeps the faster schedule of the
+     compute loop (676 instead of 703 cycles per step, scripts/ubench/relax_bench.cu) */
+  const int w = __shfl_sync(FULLMASK, A.w_base + (int)blockIdx.x * WPC + wl, 0);
   const int nworkers = (nx + K - 1 + W - 1) / W;
   double2 *base = smem2 + (size_t)wl * Cfg::VECS;
   double2 *IN = base;                   /* [RIN][NV][S]  initial iterate, slot s <-> column w*W + s */

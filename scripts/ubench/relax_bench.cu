@@ -5,6 +5,7 @@
 //   ./relax_bench [n=4096] [nsweeps=4]
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <algorithm>
 #include "../../msom_b200/csrc/mg_kernels.cuh"
@@ -82,6 +83,21 @@ int main(int argc, char **argv) {
   printf("kernel %.3f ms (err %d) | worker0 %.4f us/step (%.0f cycles @1.965GHz) | end-lag median %.3f us -> handoff %.3f us | checksum %016llx\n",
          ms, herr, (d[1] - d[0]) / 1e3 / steps, (d[1] - d[0]) / 1e3 / steps * 1965, lag[lag.size() / 2],
          lag[lag.size() / 2] - Cfg::W * (d[1] - d[0]) / 1e3 / steps, cs);
+  // determinism stress: the strips synchronise through counters and self-validating mailbox entries only; repeat
+  // the launch and compare the result bit for bit (argv[4] = repetitions)
+  const int reps = argc > 4 ? atoi(argv[4]) : 0;
+  int bad = 0;
+  for (int r = 0; r < reps; r++) {
+    CKC(cudaMemcpy(da, h.data(), nd * 8, cudaMemcpyHostToDevice));
+    CKC(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(64 * BWPC), args, smem, 0));
+    CKC(cudaDeviceSynchronize());
+    std::vector<double> o2(nd);
+    CKC(cudaMemcpy(o2.data(), da, nd * 8, cudaMemcpyDeviceToHost));
+    if (memcmp(o2.data(), o.data(), nd * 8) != 0) bad++;
+    CKC(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
+    if (herr) { printf("err flag %d at repetition %d\n", herr, r); break; }
+  }
+  if (reps) printf("determinism: %d of %d repetitions differ from the first result\n", bad, reps);
   for (int w : {0, 1, 2, 3, 4, nworkers / 2, nworkers - 2, nworkers - 1})
     printf("  w=%4d dur %8.1f us  spins %8lld  helper iters %8lld (%.3f us/iter)\n", w, (d[w * 4 + 1] - d[w * 4]) / 1e3, d[w * 4 + 2], d[w * 4 + 3],
            (d[w * 4 + 1] - d[w * 4]) / 1e3 / (double)std::max(1ll, d[w * 4 + 3]));
