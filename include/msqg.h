@@ -51,6 +51,9 @@ typedef struct msqg_params {
   int stochastic;            /* the -D_STOCHASTIC build (msqg/qg.c:25) */
   double tr_stoch, itr_stoch, amp_stoch;
   int mode_pv_invert;        /* MODE_PV_INVERT (msqg/qg.h:4) as a runtime knob */
+  /* passive tracers (nptr > 0), msqg/qg.h:98-106,726-727: relaxation time scale and Peclet number per tracer, and
+     their inverses (:751-754) */
+  double ptr_r[MSQG_MAXL], Pe[MSQG_MAXL], ptr_ir[MSQG_MAXL], iPe[MSQG_MAXL];
 } msqg_params;
 
 /* mgstats (Basilisk poisson.h; in-tree copy mspg/elliptic.h:118-123) */
@@ -90,6 +93,9 @@ enum {
   MSQG_DE_J3,     /* de_j3l   msqg/qg_energy.h:11 */
   MSQG_DE_FT,     /* de_ftl   msqg/qg_energy.h:12 (stays 0: filter_de needs the wavelet filter, out of scope) */
   MSQG_PO_MFT,    /* po_mft   msqg/qg_energy.h:15 */
+  MSQG_PTR,       /* ptracersl  msqg/qg.h:100 (nl*nptr scalars, index l*nptr + nt; zero-gradient boundaries) */
+  MSQG_PTR_RELAX, /* ptr_relaxl msqg/qg.h:101 */
+  MSQG_DPTR,      /* tracer part of `updates` */
   MSQG_NFIELDS
 };
 

@@ -15,7 +15,7 @@ LIB_CUDA = os.path.join(_HERE, "lib", "libmsqg_cuda.so")
 MAXL = 32
 
 (PSI, Q, PSIPG, FR, QFORC, TOPO, RD, SSTOCH, ZETA, DQ, STR, NSTOCH, IBU, CL2M, CM2L, PM, QM, TMP, ZETAP,
- QPRED, SIGFILT, DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT) = range(28)
+ QPRED, SIGFILT, DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT, PTR, PTR_RELAX, DPTR) = range(31)
 
 OK, ERR_ARG, ERR_CUDA, ERR_FILE, ERR_CONFIG, ERR_NOCONV = 0, -1, -2, -3, -4, -5
 
@@ -30,6 +30,7 @@ class Params(C.Structure):
         + [("iRe", C.c_double), ("iRe4", C.c_double), ("stochastic", C.c_int),
            ("tr_stoch", C.c_double), ("itr_stoch", C.c_double), ("amp_stoch", C.c_double),
            ("mode_pv_invert", C.c_int)]
+        + [(k, C.c_double * MAXL) for k in ("ptr_r", "Pe", "ptr_ir", "iPe")]
     )
 
 
@@ -130,7 +131,7 @@ def make_params(**kw):
     p = Params()
     lib().msqg_default_params(C.byref(p))
     for k, v in kw.items():
-        if k in ("Fr", "dh", "upg", "vpg"):
+        if k in ("Fr", "dh", "upg", "vpg", "ptr_r", "Pe"):
             arr = getattr(p, k)
             for i, x in enumerate(v):
                 arr[i] = float(x)

@@ -63,6 +63,7 @@ struct msqg_model {
   /* layer lists (finest level only unless noted) */
   List psi, q, qpred, dq, zeta, tmp, psipg, zetap, qforc, fr, str /*all levels*/, topo, rd, ro, sigfilt;
   List sstoch, nstoch;
+  List ptr, ptr_pred, dptr, ptr_relax; /* passive tracers, qg.h:100-101 (+ predictor and updates), nf = nl*nptr */
   List de_bf, de_vd, de_j1, de_j2, de_j3, de_ft, po_mft; /* energy diagnostics, qg_energy.h (allocated on first use) */
   int nme_ft, energy_vars;
   List da, res; /* all levels; nf = nl */
@@ -157,6 +158,10 @@ extern "C" void msqg_derive_params(msqg_params *p) {
   if (p->Re != 0) p->DT = 0.5 * fmin(p->DT, sq(p->L0 / p->N) * p->Re / 4.);
   if (p->Re4 != 0) p->DT = 0.5 * fmin(p->DT, sq(sq(p->L0 / p->N)) * p->Re4 / 32.);
   if (p->tr_stoch != 0) p->itr_stoch = 1 / p->tr_stoch;
+  for (int nt = 0; nt < p->nptr && nt < MSQG_MAXL; nt++) { /* qg.h:751-754 */
+    if (p->ptr_r[nt] == 0) p->ptr_ir[nt] = 0.; else p->ptr_ir[nt] = 1 / p->ptr_r[nt];
+    if (p->Pe[nt] == 0) p->iPe[nt] = 0.; else p->iPe[nt] = 1 / p->Pe[nt];
+  }
 }
 extern "C" int msqg_read_params(const char *path, msqg_params *p) {
   FILE *fp = fopen(path, "rt");
@@ -192,6 +197,8 @@ extern "C" int msqg_read_params(const char *path, msqg_params *p) {
     else if (!strcmp(k, "Fr"))    str2array(v, p->Fr);
     else if (!strcmp(k, "dh"))    str2array(v, p->dh);
     else if (!strcmp(k, "upg"))   str2array(v, p->upg);
+    else if (!strcmp(k, "ptr_r")) str2array(v, p->ptr_r);
+    else if (!strcmp(k, "Pe"))    str2array(v, p->Pe);
     else if (!strcmp(k, "vpg"))   str2array(v, p->vpg);
     else if (p->stochastic && !strcmp(k, "tr_stoch"))  p->tr_stoch = atof(v);
     else if (p->stochastic && !strcmp(k, "amp_stoch")) p->amp_stoch = atof(v);
@@ -234,6 +241,7 @@ static List *list_by_id(msqg_model *m, int id) {
     case MSQG_DE_J1: return &m->de_j1; case MSQG_DE_J2: return &m->de_j2;
     case MSQG_DE_J3: return &m->de_j3; case MSQG_DE_FT: return &m->de_ft;
     case MSQG_PO_MFT: return &m->po_mft;
+    case MSQG_PTR: return &m->ptr; case MSQG_PTR_RELAX: return &m->ptr_relax; case MSQG_DPTR: return &m->dptr;
   }
   return nullptr;
 }
@@ -300,7 +308,8 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   if (p->nl < 2 || p->nl > MSQG_NLMAX) FAIL(MSQG_ERR_ARG, "nl must be in [2,%d] (nl==1 is not functional in the reference)", MSQG_NLMAX);
   if (p->N < 8 || (p->N & (p->N - 1))) FAIL(MSQG_ERR_ARG, "N must be a power of two >= 8");
   if (p->sbc != 0) FAIL(MSQG_ERR_ARG, "only sbc == 0 (free slip) is supported");
-  if (p->nptr != 0) FAIL(MSQG_ERR_ARG, "passive tracers (nptr > 0) are out of scope");
+  if (p->nptr < 0 || p->nptr > MSQG_MAXL) FAIL(MSQG_ERR_ARG, "nptr must be in 0..%d", MSQG_MAXL);
+  if (p->nptr > 0 && p->stochastic) FAIL(MSQG_ERR_ARG, "passive tracers are not advanced by the stochastic advance_qg (qg_stochastic.h:139-147)");
   if (px < 1 || py < 1 || (px & (px - 1)) || (py & (py - 1))) FAIL(MSQG_ERR_ARG, "px, py must be powers of two");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -354,6 +363,10 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
 #define AL(L, nf, sg, lo, hi) if ((rc = alloc_list(m, L, nf, sg, lo, hi))) { msqg_destroy(m); return rc; }
   /* set_vars, msqg/qg.h:849-883: bc_type 0 -> dirichlet(0); +1 -> symmetry */
   AL(m->psi, nl, -1., D, D) AL(m->q, nl, -1., D, D) AL(m->qpred, nl, -1., D, D) AL(m->dq, nl, -1., D, D)
+  if (p->nptr > 0) { /* qg.h:867-870: zero-gradient boundaries (bc_type + 1) */
+    const int nt = nl * p->nptr;
+    AL(m->ptr, nt, 1., D, D) AL(m->ptr_pred, nt, 1., D, D) AL(m->dptr, nt, 1., D, D) AL(m->ptr_relax, nt, 1., D, D)
+  }
   AL(m->zeta, nl, -1., D, D) AL(m->tmp, nl, -1., D, D) AL(m->psipg, nl, -1., D, D) AL(m->zetap, nl, -1., D, D)
   AL(m->qforc, nl, -1., D, D) AL(m->fr, nl, 1., D, D) AL(m->str, nl, 1., 1, D)
   AL(m->topo, 1, 1., D, D) AL(m->rd, 1, 1., D, D) AL(m->ro, 1, 1., D, D) AL(m->sigfilt, 1, 1., D, D)
@@ -364,7 +377,8 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   }
   if (p->stochastic) { AL(m->sstoch, nl, -1., D, D) AL(m->nstoch, nl, -1., D, D) }
 #undef AL
-  const int maxnf = p->mode_pv_invert ? nl * nl : nl;
+  int maxnf = p->mode_pv_invert ? nl * nl : nl;
+  if (nl * p->nptr > maxnf) maxnf = nl * p->nptr;
   m->stage_doubles = (size_t)maxnf * m->tnx * m->tny;
   if (m->has_lev[0]) { /* tile (0,0) also stages the agglomerated square levels */
     const size_t sq0 = m->agg_level > 0 ? (size_t)nl * (1 << (m->agg_level - 1)) * (1 << (m->agg_level - 1)) : 0;
@@ -451,7 +465,8 @@ extern "C" void msqg_destroy(msqg_model *m) {
   List *all[] = {&m->psi, &m->q, &m->qpred, &m->dq, &m->zeta, &m->tmp, &m->psipg, &m->zetap, &m->qforc, &m->fr,
                  &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->sstoch, &m->nstoch, &m->da, &m->res,
                  &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l,
-                 &m->de_bf, &m->de_vd, &m->de_j1, &m->de_j2, &m->de_j3, &m->de_ft, &m->po_mft};
+                 &m->de_bf, &m->de_vd, &m->de_j1, &m->de_j2, &m->de_j3, &m->de_ft, &m->po_mft,
+                 &m->ptr, &m->ptr_pred, &m->dptr, &m->ptr_relax};
   for (List *L : all) free_list(*L);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->d_scal) cudaFree(m->d_scal);
@@ -1275,6 +1290,24 @@ static int rhs_launch(msqg_model *m, List &q_ev, const double *q_in, double *q_o
   return MSQG_OK;
 }
 
+/* ptr_rhs on the tracer tail of `evolving` (qg.h:634-647), optionally fused with the stage update of the tracers */
+static int ptr_launch(msqg_model *m, List &tr, const double *tr_in, double *tr_out, double *dptr, double dt) {
+  if (m->p.nptr <= 0) return MSQG_OK;
+  if (m->g[m->depth].bc) FAIL(MSQG_ERR_ARG, "passive tracers are not supported on decomposed grids");
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  PtrArgs A;
+  memset(&A, 0, sizeof(A));
+  A.psi = m->psi.lev[D]; A.ptr = tr.lev[D]; A.relax = m->ptr_relax.lev[D];
+  A.ptr_in = tr_in; A.ptr_out = tr_out; A.dptr = dptr; A.g = g; A.dt = dt; A.nptr = m->p.nptr;
+  for (int nt = 0; nt < m->p.nptr; nt++) { A.iPe[nt] = m->p.iPe[nt]; A.ptr_ir[nt] = m->p.ptr_ir[nt]; }
+  dim3 b(64, 4);
+  k_ptr_rhs<<<grid2(g.nx, g.ny, b, tr.nf), b, 0, m->stream>>>(A);
+  m->launches++;
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+
 /* update_qg(evolving = q_id, updates = DQ, dtmax), qg.h:609-650 */
 extern "C" int msqg_update(msqg_model *m, int q_id, double dtmax, double *dtmax_out) {
   CK(cudaSetDevice(m->device));
@@ -1284,6 +1317,7 @@ extern "C" int msqg_update(msqg_model *m, int q_id, double dtmax, double *dtmax_
   if ((rc = invertq_list(m, *L))) return rc;
   if ((rc = rhs_prepare(m))) return rc;
   if ((rc = rhs_launch(m, *L, nullptr, nullptr, m->dq.lev[m->depth], 0., 0.f))) return rc;
+  if (m->p.nptr > 0 && (rc = ptr_launch(m, q_id == MSQG_QPRED ? m->ptr_pred : m->ptr, nullptr, nullptr, m->dptr.lev[m->depth], 0.))) return rc;
   CK(cudaStreamSynchronize(m->stream));
   if (dtmax_out) *dtmax_out = dt_chain(m, dtmax);
   return MSQG_OK;
@@ -1333,6 +1367,13 @@ extern "C" int msqg_advance(msqg_model *m, int out_id, int in_id, double dt) {
   dim3 b(64, 4);
   k_advance<<<grid2(g.nx, g.ny, b, m->nl), b, 0, m->stream>>>(O->lev[m->depth], I->lev[m->depth], m->dq.lev[m->depth], noise, g, dt, dts);
   m->launches++;
+  if (m->p.nptr > 0) { /* advance_qg runs over (nptr+1)*nl scalars, qg.h:597-603, then boundary(output) */
+    List &po = out_id == MSQG_QPRED ? m->ptr_pred : m->ptr, &pi = in_id == MSQG_QPRED ? m->ptr_pred : m->ptr;
+    k_advance<<<grid2(g.nx, g.ny, b, po.nf), b, 0, m->stream>>>(po.lev[m->depth], pi.lev[m->depth], m->dptr.lev[m->depth], nullptr, g, dt, 0.f);
+    dim3 b2(32, 8);
+    k_ghosts<<<grid2(g.nx + 2, g.ny + 2, b2, po.nf), b2, 0, m->stream>>>(po.lev[m->depth], po.nf, g, 1.);
+    m->launches += 2;
+  }
   CK(cudaGetLastError());
   return MSQG_OK;
 }
@@ -1377,6 +1418,7 @@ extern "C" int msqg_step(msqg_model *m, double t, double tnext_event, double *dt
   }
   double *dqp = m->keep_dq ? m->dq.lev[D] : nullptr;
   if ((rc = rhs_launch(m, m->q, m->q.lev[D], m->qpred.lev[D], dqp, dt / 2., dts))) return rc;
+  if (m->p.nptr > 0 && (rc = ptr_launch(m, m->ptr, m->ptr.lev[D], m->ptr_pred.lev[D], nullptr, dt / 2.))) return rc;
   /* stage 2 */
   if ((rc = invertq_list(m, m->qpred))) return rc;
   if ((rc = rhs_prepare(m))) return rc;
@@ -1389,6 +1431,7 @@ extern "C" int msqg_step(msqg_model *m, double t, double tnext_event, double *dt
     }
   }
   if ((rc = rhs_launch(m, m->qpred, m->q.lev[D], m->q.lev[D], dqp, dt, dts))) return rc;
+  if (m->p.nptr > 0 && (rc = ptr_launch(m, m->ptr_pred, m->ptr.lev[D], m->ptr.lev[D], nullptr, dt))) return rc;
   CK(cudaStreamSynchronize(m->stream));
   (void)dt_chain(m, dt); /* update()'s return value is ignored in stage 2; timestep()'s static state is not */
   if (dt_out) *dt_out = dt;

@@ -380,6 +380,39 @@ k_energy(EnergyArgs A) {
   }
 }
 
+/* ------------------------------------------------------------------ passive tracers
+ * ptr_rhs (msqg/qg.h:573-588): dpdt += jacobian(po, ptr) + iPe*laplacian(ptr) + ptr_ir*(ptr_relax - ptr) with
+ * dpdt zeroed before (:611-613), fused with the stage update ptr_out = ptr_in + dpdt*dt (advance_qg, :597-603)
+ * and the zero-gradient boundary of the tracer lists (create_layer_var(.., bc_type+1), :868).  One thread per
+ * cell, blockIdx.z = scalar index f = l*nptr + nt. */
+struct PtrArgs {
+  const double *psi, *ptr, *relax, *ptr_in;
+  double *ptr_out, *dptr;
+  Geom g;
+  double iPe[MSQG_MAXL], ptr_ir[MSQG_MAXL];
+  double dt;
+  int nptr;
+};
+__global__ void __launch_bounds__(256)
+k_ptr_rhs(PtrArgs A) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  const Geom g = A.g;
+  if (x >= g.nx || y >= g.ny) return;
+  const int l = f / A.nptr, nt = f % A.nptr;
+  const size_t c = GIDX(g.pitch, y, x), pl = g.plane;
+  const double *po = A.psi + l * pl, *tr = A.ptr + f * pl;
+  double dp = 0.;
+  dp += jac(po, tr, c, g.pitch, g) + lapf(A.iPe[nt], tr, c, g.pitch, g) + A.ptr_ir[nt] * (A.relax[f * pl + c] - tr[c]);
+  if (A.dptr) A.dptr[f * pl + c] = dp;
+  if (A.ptr_out) {
+    const double v = A.ptr_in[f * pl + c] + dp * A.dt;
+    A.ptr_out[f * pl + c] = v;
+    write_ghosts(A.ptr_out + f * pl, g, x, y, v, 1.);
+  }
+}
+
 /* advance_qg alone (API parity with the function-pointer plugin, qg.h:594-606) */
 __global__ void k_advance(double *__restrict__ out, const double *__restrict__ in, const double *__restrict__ dq,
                           const double *__restrict__ noise, Geom g, double dt, float dts) {

@@ -362,7 +362,22 @@ int qg_init_event(void) {
   }
   int rc = msqg_set_field(M, MSQG_PSI, psi);
   free(psi);
-  return rc ? fail(rc) : MSQG_OK;
+  if (rc) return fail(rc);
+  if (P.nptr > 0) { /* qg.c:75-90: tracers from ptr0.bas or 1e-3*noise() (the same rand() stream), relaxation field */
+    const int nf = nl * P.nptr;
+    size_t szp = (size_t)nf * N * N;
+    double *tr = (double *)calloc(szp, sizeof(double));
+    if (qg_read_bas("ptr0.bas", nf, N, P.L0, tr) != MSQG_OK) {
+      for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)
+          for (int k = 0; k < nf; k++) tr[(size_t)N * N * k + (size_t)N * j + i] = 1e-3 * (1. - 2. * rand() / (double)RAND_MAX);
+    }
+    rc = msqg_set_field(M, MSQG_PTR, tr);
+    if (!rc && qg_read_bas("ptr_relax.bas", nf, N, P.L0, tr) == MSQG_OK) rc = msqg_set_field(M, MSQG_PTR_RELAX, tr);
+    free(tr);
+    if (rc) return fail(rc);
+  }
+  return MSQG_OK;
 }
 
 /* One pass of the event loop + one predictor-corrector step; returns 1 while the
@@ -396,6 +411,11 @@ int qg_run_iteration(int write_files) {
       write_list(name, MSQG_PSI);
       snprintf(name, sizeof(name), "%sqo%09d.bas", dpath, g_i);
       write_list(name, MSQG_Q);
+    }
+    if (P.nptr > 0 && write_files) { /* qg.c:168-171 */
+      char name[200];
+      snprintf(name, sizeof(name), "%sptr%09d.bas", dpath, g_i);
+      write_list(name, MSQG_PTR);
     }
     if (P.ediag > -1) { /* qg.c:139-166: write_field(de_*, name, 1/dtout), then reset_layer_var */
       static const char *nm[6] = {"de_bf", "de_vd", "de_j1", "de_j2", "de_j3", "de_ft"};

@@ -146,6 +146,8 @@ struct orc_model {
   flist s_stochl, n_stochl;
   /* qg_energy.h:7-17 */
   flist de_bfl, de_vdl, de_j1l, de_j2l, de_j3l, de_ftl, tmp2l, po_mft;
+  /* passive tracers, qg.h:100-101,867-870 (+ their predictor and updates: the tail of [BASILISK]'s evolving lists) */
+  flist ptracersl, ptr_relaxl, ptr_pred, dptrl;
   int nme_ft, energy_vars;
   int flag_topo;
   double iRe, iRe4, Eks, Ekb;
@@ -191,6 +193,10 @@ static void derive_params(orc_params *p) {
   if (p->Re != 0) p->DT = 0.5 * fmin(p->DT, sq(p->L0 / p->N) * p->Re / 4.);
   if (p->Re4 != 0) p->DT = 0.5 * fmin(p->DT, sq(sq(p->L0 / p->N)) * p->Re4 / 32.);
   if (p->tr_stoch != 0) p->itr_stoch = 1 / p->tr_stoch; /* qg.h:757 */
+  for (int nt = 0; nt < p->nptr && nt < ORC_MAXL; nt++) { /* qg.h:751-754 */
+    if (p->ptr_r[nt] == 0) p->ptr_ir[nt] = 0.; else p->ptr_ir[nt] = 1 / p->ptr_r[nt];
+    if (p->Pe[nt] == 0) p->iPe[nt] = 0.; else p->iPe[nt] = 1 / p->Pe[nt];
+  }
 }
 int orc_read_params(const char *path, orc_params *p) {
   FILE *fp = fopen(path, "rt");
@@ -226,6 +232,8 @@ int orc_read_params(const char *path, orc_params *p) {
     else if (!strcmp(k, "Fr"))    str2array(v, p->Fr);
     else if (!strcmp(k, "dh"))    str2array(v, p->dh);
     else if (!strcmp(k, "upg"))   str2array(v, p->upg);
+    else if (!strcmp(k, "ptr_r")) str2array(v, p->ptr_r);
+    else if (!strcmp(k, "Pe"))    str2array(v, p->Pe);
     else if (!strcmp(k, "vpg"))   str2array(v, p->vpg);
     else if (!strcmp(k, "tr_stoch"))  p->tr_stoch = atof(v);
     else if (!strcmp(k, "amp_stoch")) p->amp_stoch = atof(v);
@@ -266,6 +274,12 @@ orc_model *orc_create(const orc_params *p) {
     m->s_stochl = create_layer_var(nl, 0, depth);
     m->n_stochl = create_layer_var(nl, 0, depth);
   }
+  if (p->nptr > 0) { /* qg.h:867-870: bc_type+1 (Basilisk's default, zero-gradient, boundaries); clones inherit them */
+    m->ptracersl = create_layer_var(nl * p->nptr, bc + 1, depth);
+    m->ptr_relaxl = create_layer_var(nl * p->nptr, bc + 1, depth);
+    m->ptr_pred = create_layer_var(nl * p->nptr, bc + 1, depth);
+    m->dptrl = create_layer_var(nl * p->nptr, bc + 1, depth);
+  }
   m->Ro = create_layer_var(1, 1, depth);
   m->Rd = create_layer_var(1, 1, depth);
   m->topo = create_layer_var(1, 1, depth);
@@ -299,7 +313,8 @@ void orc_destroy(orc_model *m) {
   flist *all[] = {&m->pol, &m->qol, &m->zetal, &m->zetapl, &m->q_forcl, &m->tmpl, &m->ppl,
                   &m->Frl, &m->strl, &m->qom, &m->pom, &m->iBul, &m->cl2m, &m->cm2l, &m->Ro,
                   &m->Rd, &m->topo, &m->sig_filt, &m->dql, &m->qpred, &m->s_stochl, &m->n_stochl,
-                  &m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl, &m->tmp2l, &m->po_mft};
+                  &m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl, &m->tmp2l, &m->po_mft,
+                  &m->ptracersl, &m->ptr_relaxl, &m->ptr_pred, &m->dptrl};
   for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); k++) fl_free(all[k]);
   free(m->dhc); free(m->dhf); free(m->idh0); free(m->idh1);
   free(m);
@@ -321,6 +336,8 @@ static flist *list_by_id(orc_model *m, int id) {
     case ORC_DE_J1: return &m->de_j1l; case ORC_DE_J2: return &m->de_j2l;
     case ORC_DE_J3: return &m->de_j3l; case ORC_DE_FT: return &m->de_ftl;
     case ORC_PO_MFT: return &m->po_mft;
+    case ORC_PTR: return &m->ptracersl; case ORC_PTR_RELAX: return &m->ptr_relaxl;
+    case ORC_DPTR: return &m->dptrl;
   }
   return NULL;
 }
@@ -1016,6 +1033,13 @@ void orc_init_noise(orc_model *m, unsigned seed) {
       for (int l = 0; l < nl; l++)
         FL(&m->pol, l, D)[IDX(n, i, j)] = 1e-3 * (1. - 2. * rand() / (double)RAND_MAX);
   orc_remove_mean_psi(m);
+  if (m->p.nptr > 0) { /* qg.c:75-84 (no ptr0.bas): the same rand() stream continues */
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++)
+        for (int k = 0; k < m->ptracersl.nf; k++)
+          FL(&m->ptracersl, k, D)[IDX(n, i, j)] = 1e-3 * (1. - 2. * rand() / (double)RAND_MAX);
+    boundary(&m->ptracersl);
+  }
 }
 /* qg.c:66-72 with [BASILISK] statsf: sum += dv()*f, volume += dv() */
 void orc_remove_mean_psi(orc_model *m) {
@@ -1030,6 +1054,24 @@ void orc_remove_mean_psi(orc_model *m) {
       for (int j = 0; j < n; j++) po[IDX(n, i, j)] -= sum / volume;
   }
   boundary(&m->pol);
+}
+
+/* ptr_rhs, qg.h:573-588: advection + diffusion + relaxation of the passive tracers */
+static void ptr_rhs(orc_model *m, flist *ptl, flist *pl, flist *dpl) {
+  int n = m->N, D = m->depth, nl = m->nl, nptr = m->p.nptr;
+  double Delta = m->L0 / n;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) {
+        const double *po = FL(pl, l, D);
+        for (int nt = 0; nt < nptr; nt++) {
+          const double *ptracers = FL(ptl, l * nptr + nt, D), *ptr_relax = FL(&m->ptr_relaxl, l * nptr + nt, D);
+          double *dpdt = FL(dpl, l * nptr + nt, D);
+          size_t c = IDX(n, i, j);
+          dpdt[c] += jacobian(po, ptracers, n, i, j, Delta) + m->p.iPe[nt] * LAP(ptracers, n, i, j, Delta)
+                     + m->p.ptr_ir[nt] * (ptr_relax[c] - ptracers[c]);
+        }
+      }
 }
 
 /* ------------------------------------------------------- time stepping */
@@ -1047,6 +1089,13 @@ static double update_qg(orc_model *m, flist *evolving, flist *updates, double dt
   surface_forcing(m, updates);
   qforcing(m, updates);
   if (m->flag_topo) bottom_topography(m, &m->pol, updates);
+  if (m->p.nptr > 0) { /* qg.h:634-647: the tracers are the tail of `evolving`, their tendencies the tail of `updates` */
+    flist *ptr = (evolving == &m->qpred) ? &m->ptr_pred : &m->ptracersl;
+    for (int k = 0; k < m->dptrl.nf; k++) /* updates were zeroed at :611-613 */
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) FL(&m->dptrl, k, D)[IDX(n, i, j)] = 0.;
+    ptr_rhs(m, ptr, &m->pol, &m->dptrl);
+  }
   return dtmax;
 }
 double orc_update(orc_model *m, double dtmax) { return update_qg(m, &m->qol, &m->dql, dtmax); }
@@ -1086,6 +1135,16 @@ static void advance_qg(orc_model *m, flist *out, flist *in, flist *upd, double d
                                         FL(&m->n_stochl, l, D)[IDX(n, i, j)] * dts;
   }
   boundary(out);
+  if (m->p.nptr > 0) { /* qg.h:597-603 runs over (nptr+1)*nl scalars (the stochastic variant, qg_stochastic.h:139-147,
+                          only over nl: tracers are not supported together with -D_STOCHASTIC there either) */
+    flist *pto = (out == &m->qpred) ? &m->ptr_pred : &m->ptracersl;
+    flist *pti = (in == &m->qpred) ? &m->ptr_pred : &m->ptracersl;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++)
+        for (int k = 0; k < pto->nf; k++)
+          FL(pto, k, D)[IDX(n, i, j)] = FL(pti, k, D)[IDX(n, i, j)] + FL(&m->dptrl, k, D)[IDX(n, i, j)] * dt;
+    boundary(pto);
+  }
 }
 
 /* one iteration of [BASILISK] predictor-corrector.h run() given dt */
@@ -1204,6 +1263,14 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
           }
           reset_layer_var(m, L[k]);
         }
+      }
+      if (m->p.nptr > 0 && write_files) { /* qg.c:168-171 */
+        size_t szp = (size_t)m->ptracersl.nf * m->N * m->N;
+        double *bp = (double *)malloc(sizeof(double) * szp);
+        get_list(&m->ptracersl, m->N, bp);
+        snprintf(name, sizeof(name), "%s/ptr%09d.bas", outdir, m->iter);
+        orc_write_bas(name, m->ptracersl.nf, m->N, m->L0, bp);
+        free(bp);
       }
       ev_t += m->p.dtout;
       if (!(ev_t <= m->p.tend + 1e-10)) ev_alive = 0;

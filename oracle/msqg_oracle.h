@@ -36,6 +36,8 @@ typedef struct {
   double tr_stoch, itr_stoch, amp_stoch;
   /* compile-time switch MODE_PV_INVERT (msqg/qg.h:4) made a runtime knob */
   int mode_pv_invert;
+  /* passive tracers, msqg/qg.h:98-106,726-727,751-754: relaxation time scales and Peclet numbers per tracer */
+  double ptr_r[ORC_MAXL], Pe[ORC_MAXL], ptr_ir[ORC_MAXL], iPe[ORC_MAXL];
   /* emulate Basilisk's MPI px*py block decomposition of the GS sweep
      (1,1 = serial reference order) */
   int px, py;
@@ -55,7 +57,9 @@ enum {
   ORC_ZETA, ORC_DQ, ORC_STR, ORC_NSTOCH, ORC_IBU, ORC_CL2M, ORC_CM2L, ORC_PM, ORC_QM,
   ORC_TMP, ORC_ZETAP,
   /* energy diagnostics, msqg/qg_energy.h:7-15 */
-  ORC_DE_BF, ORC_DE_VD, ORC_DE_J1, ORC_DE_J2, ORC_DE_J3, ORC_DE_FT, ORC_PO_MFT
+  ORC_DE_BF, ORC_DE_VD, ORC_DE_J1, ORC_DE_J2, ORC_DE_J3, ORC_DE_FT, ORC_PO_MFT,
+  /* passive tracers, msqg/qg.h:100-101: nl*nptr scalars, index l*nptr + nt */
+  ORC_PTR, ORC_PTR_RELAX, ORC_DPTR
 };
 
 void orc_default_params(orc_params *p);

@@ -16,6 +16,7 @@ MAXL = 32
 
 PSI, Q, PSIPG, FR, QFORC, TOPO, RD, SSTOCH, ZETA, DQ, STR, NSTOCH, IBU, CL2M, CM2L, PM, QM, TMP, ZETAP = range(19)
 DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT = range(19, 26)  # energy diagnostics, qg_energy.h
+PTR, PTR_RELAX, DPTR = range(26, 29)  # passive tracers, qg.h:100-101
 
 
 class Params(C.Structure):
@@ -26,7 +27,9 @@ class Params(C.Structure):
         + [(k, C.c_double * MAXL) for k in ("Fr", "dh", "upg", "vpg")]
         + [("iRe", C.c_double), ("iRe4", C.c_double), ("stochastic", C.c_int),
            ("tr_stoch", C.c_double), ("itr_stoch", C.c_double), ("amp_stoch", C.c_double),
-           ("mode_pv_invert", C.c_int), ("px", C.c_int), ("py", C.c_int)]
+           ("mode_pv_invert", C.c_int)]
+        + [(k, C.c_double * MAXL) for k in ("ptr_r", "Pe", "ptr_ir", "iPe")]
+        + [("px", C.c_int), ("py", C.c_int)]
     )
 
 
@@ -133,7 +136,7 @@ def make_params(omp=False, **kw):
     p = Params()
     L.orc_default_params(C.byref(p))
     for k, v in kw.items():
-        if k in ("Fr", "dh", "upg", "vpg"):
+        if k in ("Fr", "dh", "upg", "vpg", "ptr_r", "Pe"):
             arr = getattr(p, k)
             for i, x in enumerate(v):
                 arr[i] = float(x)
@@ -148,6 +151,9 @@ def make_params(omp=False, **kw):
         p.DT = 0.5 * min(p.DT, d2 * d2 * p.Re4 / 32.0)
     if p.tr_stoch != 0:
         p.itr_stoch = 1 / p.tr_stoch
+    for nt in range(p.nptr):  # qg.h:751-754
+        p.ptr_ir[nt] = 0.0 if p.ptr_r[nt] == 0 else 1 / p.ptr_r[nt]
+        p.iPe[nt] = 0.0 if p.Pe[nt] == 0 else 1 / p.Pe[nt]
     return p
 
 

@@ -200,3 +200,25 @@ def test_energy_budget_identities():
     assert np.allclose(m.get(O.DE_J1), 2 * j1, rtol=1e-13, atol=0)      # accumulates
     m.reset_energy()
     assert not m.get(O.DE_J1).any()
+
+
+def test_tracer_mean_is_conserved_by_advection_and_diffusion():
+    """ptr_rhs (qg.h:573-588): the Arakawa Jacobian with psi = 0 on the walls and the 5-point laplacian with
+    zero-gradient ghosts both conserve the domain mean of a tracer; relaxation pulls it to the mean of ptr_relax."""
+    N, nl, nptr = 64, 2, 2
+    m = O.Model(O.make_params(**base_kw(N, nl, nptr=nptr, Pe=[30., 0.], ptr_r=[0., 0.05])))
+    rng = np.random.default_rng(2)
+    psi = np.zeros((nl, N, N))
+    psi[:, 6:-6, 6:-6] = rng.standard_normal((nl, N - 12, N - 12))
+    for _ in range(3):
+        psi[:, 1:-1, 1:-1] = 0.25 * (psi[:, :-2, 1:-1] + psi[:, 2:, 1:-1] + psi[:, 1:-1, :-2] + psi[:, 1:-1, 2:])
+    tr = rng.standard_normal((nl * nptr, N, N))
+    m.set(O.PSI, 1e-2 * psi); m.set(O.PTR, tr); m.set(O.PTR_RELAX, np.full_like(tr, 3.0)); m.set_const()
+    for _ in range(5):
+        m.step()
+    t2 = m.get(O.PTR)
+    for l in range(nl):
+        a, b = tr[l * nptr + 0], t2[l * nptr + 0]            # advected + diffused, not relaxed
+        assert np.abs(b - a).max() > 0 and abs(b.mean() - a.mean()) < 1e-12 * np.abs(a).mean()
+        a, b = tr[l * nptr + 1], t2[l * nptr + 1]            # relaxed towards 3
+        assert abs(b.mean() - 3.0) < abs(a.mean() - 3.0)
