@@ -107,3 +107,36 @@ def test_qg_exe_energy_diagnostics_files(gpu, tmp_path):
     # the budget terms are not trivially zero after the first window
     a = np.fromfile(str(gdir / [f for f in names if f.startswith("de_j1")][-1]), "f4")
     assert np.isfinite(a).all() and np.abs(a).max() > 0
+
+
+def test_qg_exe_passive_tracers_files(gpu, tmp_path):
+    """nptr = 2 in params.in: ./qg.e reads ptr0.bas / ptr_relax.bas (qg.c:75-90) and writes ptr%09d.bas at every
+    output (qg.c:168-171); bit-identical to the oracle's run()."""
+    from oracle import oracle as O
+    N, nl, nptr = 64, 2, 2
+    wd = tmp_path / "gpu"; wd.mkdir()
+    wo = tmp_path / "orc"; wo.mkdir()
+    _write_params(str(wd / "params.in"), N, nl, tend=0.1, dtout=0.05, extra="nptr = 2\nPe = [40.,0.]\nptr_r = [0.,2.]\n")
+    psi = synth_psi(N, nl)
+    rng = np.random.default_rng(4)
+    tr = rng.standard_normal((nl * nptr, N, N)); rl = rng.standard_normal((nl * nptr, N, N))
+    O.lib().orc_write_bas(str(wd / "p0.bas").encode(), nl, N, 80., psi)
+    O.lib().orc_write_bas(str(wd / "ptr0.bas").encode(), nl * nptr, N, 80., tr)
+    O.lib().orc_write_bas(str(wd / "ptr_relax.bas").encode(), nl * nptr, N, 80., rl)
+    exe = os.path.join(ROOT, "msom_b200", "lib", "qg.e")
+    out = subprocess.run([exe], cwd=str(wd), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    po = O.Params(); O.lib().orc_default_params(po); O.lib().orc_read_params(str(wd / "params.in").encode(), po)
+    assert po.nptr == 2 and po.iPe[0] == 1 / 40. and po.ptr_ir[1] == 0.5
+    mo = O.Model(po)
+    p0 = np.zeros_like(psi); O.lib().orc_read_bas(str(wd / "p0.bas").encode(), nl, N, 80., p0)
+    t0 = np.zeros_like(tr); O.lib().orc_read_bas(str(wd / "ptr0.bas").encode(), nl * nptr, N, 80., t0)
+    r0 = np.zeros_like(rl); O.lib().orc_read_bas(str(wd / "ptr_relax.bas").encode(), nl * nptr, N, 80., r0)
+    mo.set(O.PSI, p0); mo.L.orc_remove_mean_psi(mo.h)
+    mo.set(O.PTR, t0); mo.set(O.PTR_RELAX, r0); mo.set_const()
+    assert mo.run(outdir=str(wo)) > 0
+    gdir = wd / "outdir_0001"
+    names = sorted(f for f in os.listdir(wo) if f.endswith(".bas"))
+    assert sum(f.startswith("ptr") for f in names) == 3
+    for f in names:
+        assert (gdir / f).read_bytes() == (wo / f).read_bytes(), f
