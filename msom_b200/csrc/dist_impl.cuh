@@ -516,7 +516,7 @@ static int g_rhs_prepare(msqg_group *G, double *umax) {
     const Geom &g = m->g[D];
     CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), G->stream));
     ProfScope ps(m, PROF_LAP, 0);
-    launch_lap(G->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
+    launch_lap(G->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1, 0.);
     m->launches++;
     use_tmp = (m->iRe != 0. || m->iRe4 != 0.);
   }
@@ -526,7 +526,7 @@ static int g_rhs_prepare(msqg_group *G, double *umax) {
     for (msqg_model *m : G->tiles) {
       const Geom &g = m->g[D];
       ProfScope ps(m, PROF_LAP, 0);
-      launch_lap(G->stream, m->nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+      launch_lap(G->stream, m->nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr, 0.);
       m->launches++;
     }
     CK(cudaGetLastError());

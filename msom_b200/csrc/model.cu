@@ -73,6 +73,7 @@ struct msqg_model {
   int flag_topo, has_pg, has_zp, has_qforc;
   int const_set;
   /* uniform-stretching tables: s per level/layer and Thomas coefficients */
+  double sbcc;                 /* partial slip coefficient of comp_del2 (qg.h:185-198), 0 = free slip */
   bool s_uniform;
   bool s_rowuniform;           /* stretching depends on y only (varRo > 0): per-row relax coefficients */
   double *rowcoef[MSQG_MAXLEV + 1]; /* device tables [ny][6][nl] per level, or NULL */
@@ -248,13 +249,14 @@ static List *list_by_id(msqg_model *m, int id) {
 
 static dim3 grid2(int nx, int ny, dim3 b, int nz = 1) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, nz); }
 /* laplacian (+ face-speed reduction): two cells per thread when the tile width is even */
-static void launch_lap(cudaStream_t st, int nf, const double *in, double *out, const Geom &g, double *umax) {
+/* sbcc = sbc/((0.5*sbc+1)*sq(Delta)) for partial slip (qg.h:185-198), 0 for the free-slip default */
+static void launch_lap(cudaStream_t st, int nf, const double *in, double *out, const Geom &g, double *umax, double sbcc) {
   if ((g.nx & 1) == 0) {
     dim3 b(32, 8);
-    k_lap2<<<grid2(g.nx / 2, g.ny, b, nf), b, 0, st>>>(in, out, g, umax);
+    k_lap2<<<grid2(g.nx / 2, g.ny, b, nf), b, 0, st>>>(in, out, g, umax, sbcc);
   } else {
     dim3 b(64, 4);
-    k_lap<<<grid2(g.nx + 1, g.ny + 1, b, nf), b, 0, st>>>(in, out, g, umax);
+    k_lap<<<grid2(g.nx + 1, g.ny + 1, b, nf), b, 0, st>>>(in, out, g, umax, sbcc);
   }
 }
 /* bilinear prolongation: one thread per coarse cell when the fine tile is exactly its 2 x 2 refinement */
@@ -307,7 +309,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   *out = nullptr;
   if (p->nl < 2 || p->nl > MSQG_NLMAX) FAIL(MSQG_ERR_ARG, "nl must be in [2,%d] (nl==1 is not functional in the reference)", MSQG_NLMAX);
   if (p->N < 8 || (p->N & (p->N - 1))) FAIL(MSQG_ERR_ARG, "N must be a power of two >= 8");
-  if (p->sbc != 0) FAIL(MSQG_ERR_ARG, "only sbc == 0 (free slip) is supported");
+  if (p->sbc < 0) FAIL(MSQG_ERR_ARG, "sbc must be >= 0: the periodic variant (sbc = -1) is out of scope");
   if (p->nptr < 0 || p->nptr > MSQG_MAXL) FAIL(MSQG_ERR_ARG, "nptr must be in 0..%d", MSQG_MAXL);
   if (p->nptr > 0 && p->stochastic) FAIL(MSQG_ERR_ARG, "passive tracers are not advanced by the stochastic advance_qg (qg_stochastic.h:139-147)");
   if (px < 1 || py < 1 || (px & (px - 1)) || (py & (py - 1))) FAIL(MSQG_ERR_ARG, "px, py must be powers of two");
@@ -325,8 +327,13 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   int depth = 0;
   while ((1 << depth) < p->N) depth++;
   m->depth = depth;
+  { /* partial slip (sbc > 0), qg.h:185-198: coefficient of the vorticity ghosts, same expression as the reference */
+    const double Delta = p->L0 / p->N;
+    m->sbcc = p->sbc > 0 ? p->sbc / ((0.5 * p->sbc + 1) * sq(Delta)) : 0.;
+  }
   m->px = px; m->py = py; m->ix = ix; m->iy = iy;
   m->agg_level = 0;
+  if (px * py > 1 && p->sbc > 0) { msqg_destroy(m); FAIL(MSQG_ERR_ARG, "partial slip (sbc > 0) is not supported on decomposed grids"); }
   if (px * py > 1) {
     int la = 1;
     while ((1 << la) < agg_n) la++;
@@ -1050,7 +1057,7 @@ static int max_face_speed(msqg_model *m, List &L, double *umax_host) {
   CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
   dim3 b(64, 4);
   /* out-of-place laplacian into tmp is a by-product; only umax is wanted */
-  launch_lap(m->stream, m->nl, L.lev[D], m->tmp.lev[D], g, m->d_scal + 1);
+  launch_lap(m->stream, m->nl, L.lev[D], m->tmp.lev[D], g, m->d_scal + 1, m->sbcc);
   m->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(m->h_scal + 1, m->d_scal + 1, m->nl * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -1203,7 +1210,9 @@ static int set_const_finish(msqg_model *m) {
     if ((rc = max_face_speed(m, m->psipg, m->umax_pg))) return rc;
     if (m->p.flsrv == 1) {
       dim3 b(64, 4);
-      launch_lap(m->stream, nl, m->psipg.lev[D], m->zetap.lev[D], g, nullptr);
+      /* set_const ends with boundary(all) (qg.h:1103), which puts the dirichlet ghosts back on zetapl after the
+         partial-slip fix-up of comp_del2: sbcc = 0 here */
+      launch_lap(m->stream, nl, m->psipg.lev[D], m->zetap.lev[D], g, nullptr, 0.);
       m->launches++;
       CK(cudaGetLastError());
       m->has_zp = 1;
@@ -1242,10 +1251,10 @@ static int rhs_prepare(msqg_model *m) {
   dim3 b(64, 4);
   CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
   ProfScope ps(m, PROF_LAP, 0);
-  launch_lap(m->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1);
+  launch_lap(m->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1, m->sbcc);
   m->launches++;
   if (m->iRe != 0. || m->iRe4 != 0.) {
-    launch_lap(m->stream, m->nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+    launch_lap(m->stream, m->nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr, m->sbcc);
     m->launches++;
   }
   CK(cudaGetLastError());
@@ -1469,10 +1478,10 @@ extern "C" int msqg_energy_tend(msqg_model *m, double dt, double ediag) {
   const int D = m->depth, nl = m->nl;
   const Geom &g = m->g[D];
   /* comp_del2(pol, zetal, 0., 1.) (:230); dissip_de's comp_del2(zetal, tmpl, 0., 1.) (:159) */
-  launch_lap(m->stream, nl, m->psi.lev[D], m->zeta.lev[D], g, nullptr);
+  launch_lap(m->stream, nl, m->psi.lev[D], m->zeta.lev[D], g, nullptr, m->sbcc);
   m->launches++;
   if (m->iRe != 0. || m->iRe4 != 0.) {
-    launch_lap(m->stream, nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr);
+    launch_lap(m->stream, nl, m->zeta.lev[D], m->tmp.lev[D], g, nullptr, m->sbcc);
     m->launches++;
   }
   EnergyArgs A;

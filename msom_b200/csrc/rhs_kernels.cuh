@@ -47,7 +47,7 @@ __device__ __forceinline__ void write_ghosts(double *__restrict__ p, const Geom 
  * min over faces of Delta/|u| (timestep.h) == Delta / max|u| exactly (division
  * is monotone), so the host rebuilds the reference's dt chain from umax. */
 __global__ void __launch_bounds__(256)
-k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *__restrict__ umax) {
+k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *__restrict__ umax, double sbcc) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
@@ -60,6 +60,12 @@ k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *_
       const double v = lap5(p, c, g.pitch, g);
       o[c] = v;
       write_ghosts(o, g, x, y, v, -1.);
+      if (sbcc != 0.) { /* partial slip, qg.h:185-198 */
+        if (x == 0) o[c - 1] = sbcc * (p[c] - p[c - 1]);
+        if (x == g.nx - 1) o[c + 1] = sbcc * (p[c] - p[c + 1]);
+        if (y == 0) o[c - g.pitch] = sbcc * (p[c] - p[c - g.pitch]);
+        if (y == g.ny - 1) o[c + g.pitch] = sbcc * (p[c] - p[c + g.pitch]);
+      }
     }
     if (umax) {
       const int P = g.pitch;
@@ -85,7 +91,7 @@ k_lap(const double *__restrict__ in, double *__restrict__ out, Geom g, double *_
  * (ncu: the one-cell kernel above is instruction-bound at 17-29 % of DRAM peak, profiles/r01_ncu_kernels.md.)
  * Requires an even nx. */
 __global__ void __launch_bounds__(256)
-k_lap2(const double *__restrict__ in, double *__restrict__ out, Geom g, double *__restrict__ umax) {
+k_lap2(const double *__restrict__ in, double *__restrict__ out, Geom g, double *__restrict__ umax, double sbcc) {
   const int x0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
@@ -110,6 +116,16 @@ k_lap2(const double *__restrict__ in, double *__restrict__ out, Geom g, double *
     if (x0 == 0 || x0 + 2 >= g.nx || y == 0 || y == g.ny - 1) {
       write_ghosts(o, g, x0, y, v[0], -1.);
       write_ghosts(o, g, x0 + 1, y, v[1], -1.);
+      if (sbcc != 0.) { /* partial slip (sbc > 0), qg.h:185-198: zeta[ghost] = sbc/((0.5*sbc+1)*sq(Delta))*(po[]-po[ghost])
+                           on the four sides, corners keep the dirichlet value */
+        if (x0 == 0) o[c - 1] = sbcc * (w[1][1] - w[1][0]);
+        if (x0 + 2 == g.nx) o[c + 2] = sbcc * (w[1][2] - w[1][3]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (y == 0) o[c + k - P] = sbcc * (w[1][k + 1] - w[0][k + 1]);
+          if (y == g.ny - 1) o[c + k + P] = sbcc * (w[1][k + 1] - w[2][k + 1]);
+        }
+      }
     }
     if (umax) {
       double a;

@@ -378,7 +378,7 @@ void orc_set_decomp(orc_model *m, int px, int py, int agg_n) { m->p.px = px; m->
   (a[IDX(n, (i) + 1, j)] + a[IDX(n, (i) - 1, j)] + a[IDX(n, i, (j) + 1)] +            \
    a[IDX(n, i, (j) - 1)] - 4 * a[IDX(n, i, j)]) / (sq(D))
 
-/* comp_del2, qg.h:171-200 (sbc == 0 only) */
+/* comp_del2, qg.h:171-200 (sbc >= 0; the periodic variant sbc = -1 is out of scope) */
 static void comp_del2(orc_model *m, flist *pl, flist *zl, double add, double fac) {
   int n = m->N, D = m->depth, nl = m->nl;
   double Delta = m->L0 / n;
@@ -391,6 +391,18 @@ static void comp_del2(orc_model *m, flist *pl, flist *zl, double add, double fac
         ze[IDX(n, i, j)] = add * ze[IDX(n, i, j)] + fac * LAP(po, n, i, j, Delta);
       }
   boundary(zl);
+  /* partial slip, qg.h:185-198: the vorticity ghosts on the four sides (not the corners) */
+  double sbc = m->p.sbc;
+  if (sbc > 0) {
+    for (int l = 0; l < nl; l++) {
+      const double *po = FL(pl, l, D);
+      double *ze = FL(zl, l, D);
+      for (int j = 0; j < n; j++) ze[IDX(n, -1, j)] = sbc / ((0.5 * sbc + 1) * sq(Delta)) * (po[IDX(n, 0, j)] - po[IDX(n, -1, j)]);
+      for (int j = 0; j < n; j++) ze[IDX(n, n, j)] = sbc / ((0.5 * sbc + 1) * sq(Delta)) * (po[IDX(n, n - 1, j)] - po[IDX(n, n, j)]);
+      for (int i = 0; i < n; i++) ze[IDX(n, i, n)] = sbc / ((0.5 * sbc + 1) * sq(Delta)) * (po[IDX(n, i, n - 1)] - po[IDX(n, i, n)]);
+      for (int i = 0; i < n; i++) ze[IDX(n, i, -1)] = sbc / ((0.5 * sbc + 1) * sq(Delta)) * (po[IDX(n, i, 0)] - po[IDX(n, i, -1)]);
+    }
+  }
 }
 
 /* comp_stretch, qg.h:202-246 */

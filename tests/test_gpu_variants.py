@@ -247,3 +247,22 @@ def test_passive_tracers(gpu, N, nl, nptr, over):
         tw.step()
     assert np.array_equal(mg.get(G.PTR), tw.get(O2.PTR)) and np.array_equal(mg.get(G.Q), tw.get(O2.Q))
     assert np.isfinite(mg.get(G.PTR)).all() and np.abs(mg.get(G.PTR) - tr).max() > 0
+
+
+@pytest.mark.parametrize("N,nl,sbc,over", [(64, 2, 0.5, {}), (128, 3, 2.0, dict(Re=300.)), (64, 4, 10.0, dict(upg=[0.2, 0., 0., 0.], flsrv=1))])
+def test_partial_slip_boundary(gpu, N, nl, sbc, over):
+    """sbc > 0 (msqg/qg.h:185-198): comp_del2 overwrites the vorticity ghosts on the four sides with
+    sbc/((0.5*sbc+1)*sq(Delta))*(po[]-po[ghost]); they enter the Jacobians and the viscous terms.
+    Bit-exact against the oracle."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    mo, mg, _ = make_pair(N, nl, sbc=sbc, **over)
+    mo.set_const(); mg.set_const()
+    for _ in range(3):
+        assert mg.step() == mo.step()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    ref, _, _ = make_pair(N, nl, **over)
+    ref.set_const()
+    for _ in range(3):
+        ref.step()
+    assert not np.array_equal(ref.get(O.Q), mo.get(O.Q))      # the boundary condition matters
