@@ -96,6 +96,8 @@ enum {
   MSQG_PTR,       /* ptracersl  msqg/qg.h:100 (nl*nptr scalars, index l*nptr + nt; zero-gradient boundaries) */
   MSQG_PTR_RELAX, /* ptr_relaxl msqg/qg.h:101 */
   MSQG_DPTR,      /* tracer part of `updates` */
+  MSQG_QOF,       /* qofl     msqg/qg.h:27  filter mean (allocated on first use of the wavelet filter) */
+  MSQG_SIGLEV,    /* sig_lev  msqg/qg.h:49  (finest level through get_field) */
   MSQG_NFIELDS
 };
 
@@ -146,6 +148,14 @@ int msqg_advance(msqg_model *m, int out_id, int in_id, double dt);
  * tnext < 0: no event rounding (dt = update's dtmax).  returns dt in *dt_out. */
 int msqg_step(msqg_model *m, double t, double tnext, double *dt_out, double *tnext_out);
 int msqg_ke1(msqg_model *m, double *ke);          /* writestdout, qg.c:101-106 */
+/* multi-scale wavelet filter, msqg/qg.h:509-560: wavelet_filter(qol, pol, qofl, dtflt, nbar) as the `filter` event
+ * calls it (:655-658).  q is replaced by its high-pass filtered version (scales below sig_filt = min(afilt*Rd, Lfmax)),
+ * qofl receives (q_before - q_after)/dtflt.  nbar is passed by value in the reference, i.e. it is always 0. */
+int msqg_wavelet_filter(msqg_model *m, double dtflt);
+/* invertq(tmpl, qofl) of the output event (qg.c:124-129): the filtered-out stream function, left in MSQG_TMP */
+int msqg_invert_filter_mean(msqg_model *m);
+/* filter_de (qg_energy.h:207-226): second filter pass into tmp2l with -dtflt, de_ft += ..., po_mft = 0 */
+int msqg_filter_de(msqg_model *m, double dtflt, double ediag);
 /* energy diagnostics, msqg/qg_energy.h: energy_tend(pol, dt) of the comp_diag event (:228-242) with the weight
  * switch `ediag` (0: -psi*dq/dt, 1: dq/dt; qg.h:87).  The de_* lists are created on first use (set_vars_energy). */
 int msqg_energy_tend(msqg_model *m, double dt, double ediag);

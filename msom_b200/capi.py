@@ -15,7 +15,7 @@ LIB_CUDA = os.path.join(_HERE, "lib", "libmsqg_cuda.so")
 MAXL = 32
 
 (PSI, Q, PSIPG, FR, QFORC, TOPO, RD, SSTOCH, ZETA, DQ, STR, NSTOCH, IBU, CL2M, CM2L, PM, QM, TMP, ZETAP,
- QPRED, SIGFILT, DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT, PTR, PTR_RELAX, DPTR) = range(31)
+ QPRED, SIGFILT, DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT, PTR, PTR_RELAX, DPTR, QOF, SIGLEV) = range(33)
 
 OK, ERR_ARG, ERR_CUDA, ERR_FILE, ERR_CONFIG, ERR_NOCONV = 0, -1, -2, -3, -4, -5
 
@@ -83,6 +83,9 @@ def lib():
     L.msqg_set_stream.argtypes = [vp, vp]
     L.msqg_nfields.argtypes = [vp, C.c_int]
     L.msqg_energy_tend.argtypes = [vp, C.c_double, C.c_double]
+    L.msqg_wavelet_filter.argtypes = [vp, C.c_double]
+    L.msqg_invert_filter_mean.argtypes = [vp]
+    L.msqg_filter_de.argtypes = [vp, C.c_double, C.c_double]
     L.msqg_reset_energy.argtypes = [vp]
     L.msqg_set_field.argtypes = [vp, C.c_int, dp]
     L.msqg_get_field.argtypes = [vp, C.c_int, dp]
@@ -215,6 +218,13 @@ class Model:
         self.t = tn.value
         self.i += 1
         return dt.value
+
+    def wavelet_filter(self, dtflt):
+        """wavelet_filter(qol, pol, qofl, dtflt, nbar), msqg/qg.h:509-560"""
+        check(self.L.msqg_wavelet_filter(self.h, dtflt))
+
+    def filter_de(self, dtflt, ediag=None):
+        check(self.L.msqg_filter_de(self.h, dtflt, float(self.p.ediag if ediag is None else ediag)))
 
     def energy_tend(self, dt, ediag=None):
         """energy_tend(pol, dt), msqg/qg_energy.h:228-242"""

@@ -272,6 +272,99 @@ k_prolong4(const double *__restrict__ coarse, double *__restrict__ fine, Geom gc
   }
 }
 
+/* ------------------------------------------------------------------ wavelet transform
+ * [BASILISK] wavelet() / inverse_wavelet() (grid/multigrid-common.h) for the multi-scale filter of msqg
+ * (wavelet_filter, msqg/qg.h:509-560): the coefficient of a fine cell is its value minus the bilinear
+ * prolongation of the restricted field; the filter multiplies it by sig_lev (qg.h:533-537, fused here).
+ * One thread per coarse cell and layer (blockIdx.z), four children; the field has homogeneous dirichlet
+ * boundaries (psi), evaluated on the fly like in k_prolong. */
+template <bool INVERSE>
+__global__ void __launch_bounds__(256)
+k_wavelet(const double *__restrict__ sc, double *__restrict__ sf, double *__restrict__ wf, const double *__restrict__ sig,
+          Geom gc, Geom gf, int write_ghosts) {
+  const int xc = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yc = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (xc >= gc.nx || yc >= gc.ny) return;
+  const double *c = sc + (size_t)f * gc.plane;
+  double v[3][3];
+#pragma unroll
+  for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+    for (int dx = 0; dx < 3; dx++) v[dy][dx] = coarse_at(c, gc, xc + dx - 1, yc + dy - 1);
+#pragma unroll
+  for (int oy = 0; oy < 2; oy++)
+#pragma unroll
+    for (int ox = 0; ox < 2; ox++) {
+      const int ix = ox ? 2 : 0, iy = oy ? 2 : 0;
+      const double sp = (9. * v[1][1] + 3. * (v[1][ix] + v[iy][1]) + v[iy][ix]) / 16.;
+      const int x = 2 * xc + ox, y = 2 * yc + oy;
+      const size_t o = (size_t)f * gf.plane + GIDX(gf.pitch, y, x);
+      if (!INVERSE) {
+        double w = sf[o];
+        w -= sp; /* difference between fine value and its prolongation */
+        w *= sig[GIDX(gf.pitch, y, x)];
+        wf[o] = w;
+      } else {
+        double s = sp;
+        s += wf[o];
+        sf[o] = s;
+        if (write_ghosts) {
+          double *p = sf + (size_t)f * gf.plane;
+          const bool l = x == 0, r = x == gf.nx - 1, bo = y == 0, t = y == gf.ny - 1;
+          if (l) p[GIDX(gf.pitch, y, -1)] = -s;
+          if (r) p[GIDX(gf.pitch, y, gf.nx)] = -s;
+          if (bo) p[GIDX(gf.pitch, -1, x)] = -s;
+          if (t) p[GIDX(gf.pitch, gf.ny, x)] = -s;
+          if (l && bo) p[GIDX(gf.pitch, -1, -1)] = s;
+          if (l && t) p[GIDX(gf.pitch, gf.ny, -1)] = s;
+          if (r && bo) p[GIDX(gf.pitch, -1, gf.nx)] = s;
+          if (r && t) p[GIDX(gf.pitch, gf.ny, gf.nx)] = s;
+        }
+      }
+    }
+}
+/* root cell: w = s*sig_lev (forward + filter), s = w (inverse); level 0 is one cell per layer */
+__global__ void k_wavelet_root(double *__restrict__ s0, double *__restrict__ w0, Geom g0, double sig0, int nf, int inverse) {
+  const int f = threadIdx.x;
+  if (f >= nf) return;
+  const size_t o = (size_t)f * g0.plane + GIDX(g0.pitch, 0, 0);
+  if (!inverse) { double w = s0[o]; w *= sig0; w0[o] = w; }
+  else s0[o] = w0[o];
+}
+/* qof = (qof*nbar + (tmp - qo)/dtflt)/(nbar+1) + boundary(qofl), qg.h:543-557 */
+__global__ void k_filter_mean(double *__restrict__ qof, const double *__restrict__ tmp, const double *__restrict__ qo, Geom g,
+                              double dtflt, int nbar) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (x >= g.nx || y >= g.ny) return;
+  const size_t c = (size_t)f * g.plane + GIDX(g.pitch, y, x);
+  const double v = (qof[c] * nbar + (tmp[c] - qo[c]) / dtflt) / (nbar + 1);
+  qof[c] = v;
+  double *p = qof + (size_t)f * g.plane;
+  const bool l = x == 0, r = x == g.nx - 1, bo = y == 0, t = y == g.ny - 1;
+  if (l) p[GIDX(g.pitch, y, -1)] = -v;
+  if (r) p[GIDX(g.pitch, y, g.nx)] = -v;
+  if (bo) p[GIDX(g.pitch, -1, x)] = -v;
+  if (t) p[GIDX(g.pitch, g.ny, x)] = -v;
+  if (l && bo) p[GIDX(g.pitch, -1, -1)] = v;
+  if (l && t) p[GIDX(g.pitch, g.ny, -1)] = v;
+  if (r && bo) p[GIDX(g.pitch, -1, g.nx)] = v;
+  if (r && t) p[GIDX(g.pitch, g.ny, g.nx)] = v;
+}
+/* filter_de, qg_energy.h:214-224: de_ft += tmp*dtflt*(-pm*(1-ediag)+ediag); pm = 0 */
+__global__ void k_filter_de(double *__restrict__ de_ft, const double *__restrict__ tmp2, double *__restrict__ pm, Geom g,
+                            double dtflt, double ediag) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (x >= g.nx || y >= g.ny) return;
+  const size_t c = (size_t)f * g.plane + GIDX(g.pitch, y, x);
+  de_ft[c] += tmp2[c] * dtflt * (-pm[c] * (1 - ediag) + ediag);
+  pm[c] = 0;
+}
+
 /* ------------------------------------------------------------------ correction
  * mg_cycle tail: a += da ; boundary(a)   (mspg/elliptic.h:92-98).  Ghost ring of
  * the dirichlet(0) field a is written by the boundary cells themselves. */

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <vector>
+#include <utility>
 
 static thread_local char g_err[512] = "";
 extern "C" const char *msqg_last_error(void) { return g_err; }
@@ -63,6 +64,11 @@ struct msqg_model {
   /* layer lists (finest level only unless noted) */
   List psi, q, qpred, dq, zeta, tmp, psipg, zetap, qforc, fr, str /*all levels*/, topo, rd, ro, sigfilt;
   List sstoch, nstoch;
+  List qof, siglev, wvs, wvw, tmp2; /* wavelet filter: filter mean, sig_lev (all levels), restricted psi (levels < depth),
+                                       coefficients (all levels), second filter mean of filter_de; on first use */
+  int filter_vars;
+  std::vector<double> h_sigfilt;   /* sig_filt on the finest level (host copy for sig_lev) */
+  double siglev0;                  /* sig_lev of the root cell */
   List ptr, ptr_pred, dptr, ptr_relax; /* passive tracers, qg.h:100-101 (+ predictor and updates), nf = nl*nptr */
   List de_bf, de_vd, de_j1, de_j2, de_j3, de_ft, po_mft; /* energy diagnostics, qg_energy.h (allocated on first use) */
   int nme_ft, energy_vars;
@@ -242,6 +248,7 @@ static List *list_by_id(msqg_model *m, int id) {
     case MSQG_DE_J1: return &m->de_j1; case MSQG_DE_J2: return &m->de_j2;
     case MSQG_DE_J3: return &m->de_j3; case MSQG_DE_FT: return &m->de_ft;
     case MSQG_PO_MFT: return &m->po_mft;
+    case MSQG_QOF: return &m->qof; case MSQG_SIGLEV: return &m->siglev;
     case MSQG_PTR: return &m->ptr; case MSQG_PTR_RELAX: return &m->ptr_relax; case MSQG_DPTR: return &m->dptr;
   }
   return nullptr;
@@ -401,7 +408,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
   CK(cudaMallocHost(&m->h_err, sizeof(int)));
   m->mailbox = nullptr; m->mailbox_words = 0; m->d_dbg = nullptr;
-  m->nme_ft = 0; m->energy_vars = 0;
+  m->nme_ft = 0; m->energy_vars = 0; m->filter_vars = 0; m->siglev0 = 0.;
   for (int l = 0; l <= MSQG_MAXLEV; l++) m->rowcoef[l] = nullptr;
   m->s_rowuniform = false;
   for (int l = 0; l < nl; l++) m->dhf[l] = p->dh[l]; /* qg.h:895-896 */
@@ -473,7 +480,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
                  &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->sstoch, &m->nstoch, &m->da, &m->res,
                  &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l,
                  &m->de_bf, &m->de_vd, &m->de_j1, &m->de_j2, &m->de_j3, &m->de_ft, &m->po_mft,
-                 &m->ptr, &m->ptr_pred, &m->dptr, &m->ptr_relax};
+                 &m->ptr, &m->ptr_pred, &m->dptr, &m->ptr_relax, &m->qof, &m->siglev, &m->wvs, &m->wvw, &m->tmp2};
   for (List *L : all) free_list(*L);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->d_scal) cudaFree(m->d_scal);
@@ -1193,6 +1200,8 @@ static int set_const_local(msqg_model *m) {
     for (size_t c = 0; c < tc; c++) sig[c] = fmin(m->p.afilt * rd[c], m->p.Lfmax);
   }
   if ((rc = pack_to(m, m->sigfilt, sig.data()))) return rc;
+  m->h_sigfilt = sig;
+  m->filter_vars = 0; /* sig_lev is rebuilt from the new sig_filt on the next filter call */
   m->const_set = 1;
   return MSQG_OK;
 }
@@ -1449,6 +1458,151 @@ extern "C" int msqg_step(msqg_model *m, double t, double tnext_event, double *dt
 }
 
 /* writestdout, qg.c:101-106 */
+/* ------------------------------------------------------------------ multi-scale wavelet filter, msqg/qg.h:509-560 */
+/* lists + sig_lev (qg.h:1063-1090: restriction(sig_filt), low-pass flags from the finest level down, then 1 - x),
+ * computed on the host with the reference's loop and expression order and uploaded level by level */
+static int ensure_filter_lists(msqg_model *m) {
+  if (m->filter_vars) return MSQG_OK;
+  if (m->px * m->py > 1) FAIL(MSQG_ERR_ARG, "the wavelet filter is not available on decomposed grids");
+  const int D = m->depth, nl = m->nl;
+  int rc;
+  if (!m->qof.nf) {
+    if ((rc = alloc_list(m, m->qof, nl, -1., D, D))) return rc;
+    if ((rc = alloc_list(m, m->tmp2, nl, -1., D, D))) return rc;
+    if ((rc = alloc_list(m, m->siglev, 1, 1., 0, D))) return rc;
+    if ((rc = alloc_list(m, m->wvs, nl, -1., 0, D - 1))) return rc;
+    if ((rc = alloc_list(m, m->wvw, nl, -1., 0, D))) return rc;
+  }
+  std::vector<std::vector<double>> sf(D + 1), sl(D + 1);
+  sf[D] = m->h_sigfilt; /* [y][x] */
+  for (int l = D - 1; l >= 0; l--) { /* restriction_average: children (0,0),(0,1),(1,0),(1,1), x outer */
+    const int n = 1 << l, nf = 2 * n;
+    sf[l].resize((size_t)n * n);
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) {
+        const std::vector<double> &a = sf[l + 1];
+        double sum = 0.;
+        sum += a[(size_t)(2 * j) * nf + 2 * i];
+        sum += a[(size_t)(2 * j + 1) * nf + 2 * i];
+        sum += a[(size_t)(2 * j) * nf + 2 * i + 1];
+        sum += a[(size_t)(2 * j + 1) * nf + 2 * i + 1];
+        sf[l][(size_t)j * n + i] = sum / 4;
+      }
+  }
+  for (int l = D; l >= 0; l--) { /* low pass filter */
+    const int n = 1 << l;
+    const double Dl = m->p.L0 / n;
+    sl[l].resize((size_t)n * n);
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) {
+        double ref_flag = 0;
+        if (l < D) {
+          const std::vector<double> &ch = sl[l + 1];
+          const int nf = 2 * n;
+          for (int a = 0; a < 2; a++)      /* child.x */
+            for (int b = 0; b < 2; b++)    /* child.y */
+              ref_flag += ch[(size_t)(2 * j + b) * nf + 2 * i + a];
+        }
+        const double s = sf[l][(size_t)j * n + i];
+        double v;
+        if (ref_flag > 0) v = 1;
+        else if (s > 2 * Dl) v = 0;
+        else if (s <= 2 * Dl && s > Dl) v = 1 - (s - Dl) / Dl;
+        else v = 1;
+        sl[l][(size_t)j * n + i] = v;
+      }
+  }
+  for (int l = D; l >= 0; l--) { /* high pass filter */
+    for (double &v : sl[l]) v = 1 - v;
+    const Geom &g = m->g[l];
+    std::vector<double> pad(g.plane, 0.);
+    for (int j = 0; j < g.ny; j++)
+      for (int i = 0; i < g.nx; i++) pad[GIDX(g.pitch, j, i)] = sl[l][(size_t)j * g.nx + i];
+    CK(cudaMemcpyAsync(m->siglev.lev[l], pad.data(), g.plane * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  m->siglev0 = sl[0][0];
+  m->filter_vars = 1;
+  return MSQG_OK;
+}
+/* wavelet_filter(qol = Q, pol, qofl = qof_list, dtflt, nbar = 0) */
+static int wavelet_filter(msqg_model *m, List &qof_list, double dtflt) {
+  const int D = m->depth, nl = m->nl;
+  const Geom &g = m->g[D];
+  int rc;
+  if ((rc = ensure_filter_lists(m))) return rc;
+  const size_t bytes = (size_t)nl * g.plane * sizeof(double);
+  CK(cudaMemcpyAsync(m->tmp.lev[D], m->q.lev[D], bytes, cudaMemcpyDeviceToDevice, m->stream)); /* tmp[] = qo[] */
+  if ((rc = invertq_list(m, m->q))) return rc;
+  dim3 b(32, 8);
+  /* restriction({po}) */
+  for (int l = D - 1; l >= 0; l--) {
+    const double *fine = (l + 1 == D) ? m->psi.lev[D] : m->wvs.lev[l + 1];
+    k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, m->stream>>>(fine, m->wvs.lev[l], m->g[l + 1], m->g[l], -1., 0);
+    m->launches++;
+  }
+  /* wavelet(po, w) and w[] *= sig_lev[] on every level */
+  for (int l = D - 1; l >= 0; l--) {
+    double *fine = (l + 1 == D) ? m->psi.lev[D] : m->wvs.lev[l + 1];
+    k_wavelet<false><<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, m->stream>>>(m->wvs.lev[l], fine, m->wvw.lev[l + 1], m->siglev.lev[l + 1],
+                                                                                 m->g[l], m->g[l + 1], 0);
+    m->launches++;
+  }
+  k_wavelet_root<<<1, 32, 0, m->stream>>>(m->wvs.lev[0], m->wvw.lev[0], m->g[0], m->siglev0, nl, 0);
+  /* inverse_wavelet(po, w) */
+  k_wavelet_root<<<1, 32, 0, m->stream>>>(m->wvs.lev[0], m->wvw.lev[0], m->g[0], m->siglev0, nl, 1);
+  m->launches += 2;
+  for (int l = 0; l <= D - 1; l++) {
+    double *fine = (l + 1 == D) ? m->psi.lev[D] : m->wvs.lev[l + 1];
+    k_wavelet<true><<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, m->stream>>>(m->wvs.lev[l], fine, m->wvw.lev[l + 1], nullptr, m->g[l], m->g[l + 1],
+                                                                                l + 1 == D);
+    m->launches++;
+  }
+  CK(cudaGetLastError());
+  if ((rc = msqg_comp_q(m))) return rc; /* comp_q(pol, qol) */
+  dim3 b2(64, 4);
+  k_filter_mean<<<grid2(g.nx, g.ny, b2, nl), b2, 0, m->stream>>>(qof_list.lev[D], m->tmp.lev[D], m->q.lev[D], g, dtflt, 0);
+  m->launches++;
+  if (dtflt < 0.0) /* for energy diag: restore qo to prefiltered value (list_copy_deep(tmpl, qol, nl)) */
+    CK(cudaMemcpyAsync(m->q.lev[D], m->tmp.lev[D], bytes, cudaMemcpyDeviceToDevice, m->stream));
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+extern "C" int msqg_wavelet_filter(msqg_model *m, double dtflt) {
+  CK(cudaSetDevice(m->device));
+  if (!m->const_set) FAIL(MSQG_ERR_ARG, "set_const must be called before the filter");
+  int rc = ensure_filter_lists(m);
+  if (rc) return rc;
+  return wavelet_filter(m, m->qof, dtflt);
+}
+extern "C" int msqg_invert_filter_mean(msqg_model *m) {
+  CK(cudaSetDevice(m->device));
+  int rc = ensure_filter_lists(m);
+  if (rc) return rc;
+  /* invertq(tmpl, qofl): tmpl is the unknown (and the initial guess) */
+  const int D = m->depth;
+  std::swap(m->psi.lev[D], m->tmp.lev[D]);
+  rc = invertq_list(m, m->qof);
+  std::swap(m->psi.lev[D], m->tmp.lev[D]);
+  return rc;
+}
+static int ensure_energy_lists(msqg_model *m);
+extern "C" int msqg_filter_de(msqg_model *m, double dtflt, double ediag) {
+  CK(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = ensure_energy_lists(m))) return rc;
+  if ((rc = ensure_filter_lists(m))) return rc;
+  if ((rc = wavelet_filter(m, m->tmp2, -dtflt))) return rc;
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  dim3 b(64, 4);
+  k_filter_de<<<grid2(g.nx, g.ny, b, m->nl), b, 0, m->stream>>>(m->de_ft.lev[D], m->tmp2.lev[D], m->po_mft.lev[D], g, dtflt, ediag);
+  m->launches++;
+  CK(cudaGetLastError());
+  m->nme_ft = 0;
+  return MSQG_OK;
+}
+
 /* ------------------------------------------------------------------ energy diagnostics, msqg/qg_energy.h */
 static int ensure_energy_lists(msqg_model *m) { /* set_vars_energy, qg_energy.h:244-253 */
   if (m->energy_vars) return MSQG_OK;

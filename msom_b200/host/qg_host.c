@@ -384,11 +384,25 @@ int qg_init_event(void) {
  * run continues, 0 when the last bounded event is exhausted, <0 on error. */
 static double ev_out_t = 0.;
 static int ev_out_alive = 1;
+/* filter (t = dtflt; t <= tend+1e-10; t += dtflt), qg.h:655-658 and qg_energy.h:270-273 */
+static double ev_flt_t = 0.;
+static int ev_flt_alive = 0;
 
-int qg_run_reset(void) { ev_out_t = 0.; ev_out_alive = 1; g_t = 0.; g_i = 0; g_dt = 0.; return MSQG_OK; }
+int qg_run_reset(void) {
+  ev_out_t = 0.; ev_out_alive = 1; g_t = 0.; g_i = 0; g_dt = 0.;
+  ev_flt_t = P.dtflt; ev_flt_alive = (P.dtflt > 0) && (ev_flt_t <= P.tend + 1e-10);
+  return MSQG_OK;
+}
 
 int qg_run_iteration(int write_files) {
   int rc;
+  if (ev_flt_alive && fabs(g_t - ev_flt_t) <= TEPS * g_t) {
+    fprintf(stdout, "Filter solution\n");
+    if ((rc = msqg_wavelet_filter(M, P.dtflt))) return fail(rc);
+    if (P.ediag > -1 && (rc = msqg_filter_de(M, P.dtflt, (double)P.ediag))) return fail(rc);
+    ev_flt_t += P.dtflt;
+    if (!(ev_flt_t <= P.tend + 1e-10)) ev_flt_alive = 0;
+  }
   /* comp_diag (i++), qg_energy.h:289-291: defined before qg.c's events, so it runs first.  `dt` is [BASILISK]'s
      global time step, 1. before the first step (common.h) */
   if (P.ediag > -1) {
@@ -411,6 +425,14 @@ int qg_run_iteration(int write_files) {
       write_list(name, MSQG_PSI);
       snprintf(name, sizeof(name), "%sqo%09d.bas", dpath, g_i);
       write_list(name, MSQG_Q);
+    }
+    if (P.dtflt > 0) { /* qg.c:124-129: invertq(tmpl, qofl), pf file, nbar = 0 */
+      if ((rc = msqg_invert_filter_mean(M))) return fail(rc);
+      if (write_files) {
+        char name[200];
+        snprintf(name, sizeof(name), "%spf%09d.bas", dpath, g_i);
+        write_list(name, MSQG_TMP);
+      }
     }
     if (P.nptr > 0 && write_files) { /* qg.c:168-171 */
       char name[200];
@@ -435,6 +457,7 @@ int qg_run_iteration(int write_files) {
   }
   if (!ev_out_alive) return 0;
   if (ev_out_t > g_t) tnext = ev_out_t;
+  if (ev_flt_alive && ev_flt_t > g_t && ev_flt_t < tnext) tnext = ev_flt_t;
   double dt = 0., tn = 0.;
   if ((rc = msqg_step(M, g_t, tnext == HUGEV ? -1. : tnext, &dt, &tn))) return fail(rc);
   g_dt = dt; g_t = tn; g_i++;

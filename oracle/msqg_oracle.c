@@ -141,6 +141,8 @@ struct orc_model {
   flist pol, qol, zetal, zetapl, q_forcl, tmpl, ppl, Frl, strl;
   flist qom, pom, iBul, cl2m, cm2l;
   flist Ro, Rd, topo, sig_filt;
+  flist sig_lev, qofl, wvl; /* qg.h:49 (all levels), qg.h:27 filter mean, scratch wavelet coefficients */
+  int nbar;                 /* qg.h:86 */
   flist dql;    /* "updates" */
   flist qpred;  /* "predictor" */
   flist s_stochl, n_stochl;
@@ -284,6 +286,9 @@ orc_model *orc_create(const orc_params *p) {
   m->Rd = create_layer_var(1, 1, depth);
   m->topo = create_layer_var(1, 1, depth);
   m->sig_filt = create_layer_var(1, 1, depth);
+  m->sig_lev = create_layer_var(1, 1, depth);
+  m->qofl = create_layer_var(nl, bc, depth);   /* qg.h:860 */
+  m->wvl = create_layer_var(1, 0, depth);      /* scalar w[] with w[top] = w[bottom] = w[right] = w[left] = 0, qg.h:525-529 */
   m->dhc = (double *)calloc(nl, sizeof(double));
   m->dhf = (double *)calloc(nl, sizeof(double));
   m->idh0 = (double *)calloc(nl, sizeof(double));
@@ -312,7 +317,7 @@ void orc_destroy(orc_model *m) {
   if (!m) return;
   flist *all[] = {&m->pol, &m->qol, &m->zetal, &m->zetapl, &m->q_forcl, &m->tmpl, &m->ppl,
                   &m->Frl, &m->strl, &m->qom, &m->pom, &m->iBul, &m->cl2m, &m->cm2l, &m->Ro,
-                  &m->Rd, &m->topo, &m->sig_filt, &m->dql, &m->qpred, &m->s_stochl, &m->n_stochl,
+                  &m->Rd, &m->topo, &m->sig_filt, &m->sig_lev, &m->qofl, &m->wvl, &m->dql, &m->qpred, &m->s_stochl, &m->n_stochl,
                   &m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl, &m->tmp2l, &m->po_mft,
                   &m->ptracersl, &m->ptr_relaxl, &m->ptr_pred, &m->dptrl};
   for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); k++) fl_free(all[k]);
@@ -338,6 +343,7 @@ static flist *list_by_id(orc_model *m, int id) {
     case ORC_PO_MFT: return &m->po_mft;
     case ORC_PTR: return &m->ptracersl; case ORC_PTR_RELAX: return &m->ptr_relaxl;
     case ORC_DPTR: return &m->dptrl;
+    case ORC_QOF: return &m->qofl; case ORC_SIGLEV: return &m->sig_lev;
   }
   return NULL;
 }
@@ -1025,6 +1031,36 @@ int orc_set_const(orc_model *m) {
         size_t c = IDX(n, i, j);
         FL(&m->sig_filt, 0, D)[c] = fmin(m->p.afilt * FL(&m->Rd, 0, D)[c], m->p.Lfmax);
       }
+  /* filter length scale and wavelet coefficients, qg.h:1063-1090 */
+  restriction(&m->sig_filt);
+  for (int l = D; l >= 0; l--) { /* low pass filter */
+    int nn = LN(l);
+    double Dl = m->L0 / nn;
+    double *sl = FL(&m->sig_lev, 0, l);
+    const double *sf = FL(&m->sig_filt, 0, l);
+    for (int i = 0; i < nn; i++)
+      for (int j = 0; j < nn; j++) {
+        double ref_flag = 0;
+        if (l < D) {
+          const double *ch = FL(&m->sig_lev, 0, l + 1);
+          for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++) ref_flag += ch[IDX(2 * nn, 2 * i + a, 2 * j + b)];
+        }
+        size_t c = IDX(nn, i, j);
+        if (ref_flag > 0) sl[c] = 1;
+        else if (sf[c] > 2 * Dl) sl[c] = 0;
+        else if (sf[c] <= 2 * Dl && sf[c] > Dl) sl[c] = 1 - (sf[c] - Dl) / Dl;
+        else sl[c] = 1;
+      }
+    boundary_level(&m->sig_lev, l);
+  }
+  for (int l = D; l >= 0; l--) { /* high pass filter */
+    int nn = LN(l);
+    double *sl = FL(&m->sig_lev, 0, l);
+    for (int i = 0; i < nn; i++)
+      for (int j = 0; j < nn; j++) sl[IDX(nn, i, j)] = 1 - sl[IDX(nn, i, j)];
+    boundary_level(&m->sig_lev, l);
+  }
   comp_q(m, &m->pol, &m->qol);
   if (m->p.flsrv == 1) comp_del2(m, &m->ppl, &m->zetapl, 0., 1.0);
   /* boundary(all), qg.h:1103 */
@@ -1236,13 +1272,25 @@ int orc_read_bas(const char *name, int nf, int N, double L0, double *v) {
  * writestdout (i++), output (t=0; t<=tend+1e-10; t+=dtout), and dtnext(). */
 static void energy_tend(orc_model *m, flist *pl, double dt, double ediag);
 static void reset_layer_var(orc_model *m, flist *f);
+static void filter_de(orc_model *m, double dtflt, double ediag);
+static void wavelet_filter(orc_model *m, flist *ql, flist *pl, flist *qofl, double dtflt, int nbar);
 int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, int verbose) {
   double ev_t = 0.;
   int ev_alive = 1, steps = 0;
+  /* filter (t = dtflt; t <= tend+1e-10; t += dtflt), qg.h:655-658 and qg_energy.h:270-273 */
+  double ev_f = m->p.dtflt;
+  int evf_alive = (m->p.dtflt > 0) && (ev_f <= m->p.tend + 1e-10);
   size_t sz = (size_t)m->nl * m->N * m->N;
   double *buf = write_files ? (double *)malloc(sizeof(double) * sz) : NULL;
   char name[512];
   while (1) {
+    if (evf_alive && fabs(m->t - ev_f) <= TEPS * m->t) {
+      if (verbose) fprintf(stdout, "Filter solution\n");
+      wavelet_filter(m, &m->qol, &m->pol, &m->qofl, m->p.dtflt, m->nbar);
+      if (m->p.ediag > -1) filter_de(m, m->p.dtflt, (double)m->p.ediag);
+      ev_f += m->p.dtflt;
+      if (!(ev_f <= m->p.tend + 1e-10)) evf_alive = 0;
+    }
     /* comp_diag (i++), qg_energy.h:289-291: defined before qg.c's events, so it runs first; `dt` is [BASILISK]'s
        global, 1. before the first step (common.h) */
     if (m->p.ediag > -1) energy_tend(m, &m->pol, m->iter == 0 ? 1. : m->dt, (double)m->p.ediag);
@@ -1276,6 +1324,15 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
           reset_layer_var(m, L[k]);
         }
       }
+      if (m->p.dtflt > 0) { /* qg.c:124-129: filtered stream function from the filter mean, then nbar = 0 */
+        invertq(m, &m->tmpl, &m->qofl);
+        if (write_files) {
+          get_list(&m->tmpl, m->N, buf);
+          snprintf(name, sizeof(name), "%s/pf%09d.bas", outdir, m->iter);
+          orc_write_bas(name, m->nl, m->N, m->L0, buf);
+        }
+        m->nbar = 0;
+      }
       if (m->p.nptr > 0 && write_files) { /* qg.c:168-171 */
         size_t szp = (size_t)m->ptracersl.nf * m->N * m->N;
         double *bp = (double *)malloc(sizeof(double) * szp);
@@ -1289,6 +1346,7 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
     }
     if (!ev_alive) break;
     if (ev_t > m->t) tnext = ev_t;
+    if (evf_alive && ev_f > m->t && ev_f < tnext) tnext = ev_f;
     if (max_steps >= 0 && steps >= max_steps) break;
     /* dt = dtnext(update(evolving, updates, DT)) */
     double dt = update_qg(m, &m->qol, &m->dql, m->p.DT);
@@ -1310,6 +1368,89 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
   free(buf);
   return steps;
 }
+
+/* ----------------------------------------------------------- multi-scale wavelet filter, qg.h:509-560
+ * [BASILISK] wavelet() / inverse_wavelet() (grid/multigrid-common.h), restated: the coefficient of a fine cell is
+ * its value minus the bilinear prolongation of the restricted field; the root keeps the value itself. */
+static inline double bilinear_at(const double *c, int nc, int i, int j) { /* fine cell (i,j), coarse array c */
+  int ic = i >> 1, jc = j >> 1;
+  int cx = (i & 1) ? 1 : -1, cy = (j & 1) ? 1 : -1;
+  return (9. * c[IDX(nc, ic, jc)] + 3. * (c[IDX(nc, ic + cx, jc)] + c[IDX(nc, ic, jc + cy)]) + c[IDX(nc, ic + cx, jc + cy)]) / 16.;
+}
+static void wavelet(orc_model *m, flist *sl, int k, flist *w) {
+  int D = m->depth;
+  /* restriction({s}) was done for the whole list by the caller */
+  for (int l = D - 1; l >= 0; l--) {
+    int nf = LN(l + 1), nc = LN(l);
+    const double *s = FL(sl, k, l + 1), *c = FL(sl, k, l);
+    double *wf = FL(w, 0, l + 1);
+    for (int i = 0; i < nf; i++)
+      for (int j = 0; j < nf; j++) {
+        double wv = s[IDX(nf, i, j)];
+        double sp = bilinear_at(c, nc, i, j);
+        wv -= sp; /* difference between fine value and its prolongation */
+        wf[IDX(nf, i, j)] = wv;
+      }
+    boundary_level(w, l + 1);
+  }
+  FL(w, 0, 0)[IDX(1, 0, 0)] = FL(sl, k, 0)[IDX(1, 0, 0)]; /* root cell */
+  boundary_level(w, 0);
+}
+static void inverse_wavelet(orc_model *m, flist *sl, int k, flist *w) {
+  int D = m->depth;
+  FL(sl, k, 0)[IDX(1, 0, 0)] = FL(w, 0, 0)[IDX(1, 0, 0)];
+  boundary_level(sl, 0);
+  for (int l = 0; l <= D - 1; l++) {
+    int nf = LN(l + 1), nc = LN(l);
+    double *s = FL(sl, k, l + 1);
+    const double *c = FL(sl, k, l), *wf = FL(w, 0, l + 1);
+    for (int i = 0; i < nf; i++)
+      for (int j = 0; j < nf; j++) {
+        double v = bilinear_at(c, nc, i, j);
+        v += wf[IDX(nf, i, j)];
+        s[IDX(nf, i, j)] = v;
+      }
+    boundary_level(sl, l + 1);
+  }
+}
+/* wavelet_filter, qg.h:509-560.  nbar is passed BY VALUE in the reference (the nbar++ at :558 is lost). */
+static void wavelet_filter(orc_model *m, flist *ql, flist *pl, flist *qofl, double dtflt, int nbar) {
+  int n = m->N, D = m->depth, nl = m->nl;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) FL(&m->tmpl, l, D)[IDX(n, i, j)] = FL(ql, l, D)[IDX(n, i, j)];
+  invertq(m, pl, ql);
+  restriction(pl);
+  for (int k = 0; k < nl; k++) {
+    wavelet(m, pl, k, &m->wvl);
+    for (int l = 0; l <= D; l++) {
+      int nn = LN(l);
+      double *w = FL(&m->wvl, 0, l);
+      const double *sg = FL(&m->sig_lev, 0, l);
+      for (int i = 0; i < nn; i++)
+        for (int j = 0; j < nn; j++) w[IDX(nn, i, j)] *= sg[IDX(nn, i, j)];
+      boundary_level(&m->wvl, l);
+    }
+    inverse_wavelet(m, pl, k, &m->wvl);
+  }
+  comp_q(m, pl, ql);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) {
+        size_t c = IDX(n, i, j);
+        double *qof = FL(qofl, l, D);
+        qof[c] = (qof[c] * nbar + (FL(&m->tmpl, l, D)[c] - FL(ql, l, D)[c]) / dtflt) / (nbar + 1);
+      }
+  if (dtflt < 0.0) /* for energy diag: restore qo to prefiltered value */
+    fl_copy_level(ql, &m->tmpl, D); /* list_copy_deep(tmpl, qol, nl) */
+  boundary(qofl);
+}
+void orc_get_siglev(orc_model *m, int level, double *v) {
+  int nn = LN(level);
+  for (int i = 0; i < nn; i++)
+    for (int j = 0; j < nn; j++) v[(size_t)nn * j + i] = FL(&m->sig_lev, 0, level)[IDX(nn, i, j)];
+}
+void orc_wavelet_filter(orc_model *m, double dtflt) { wavelet_filter(m, &m->qol, &m->pol, &m->qofl, dtflt, m->nbar); }
 
 /* ----------------------------------------------------------- energy diagnostics, msqg/qg_energy.h
  * "We multiply all terms of the PV equation by -po*dt" (:1-5).  Built as the reference is by default:
@@ -1427,6 +1568,21 @@ static void ekman_friction_de(orc_model *m, flist *zl, flist *dql, flist *pl, do
       FL(dql, nl - 1, D)[c] -= m->Ekb / (Rom * 2 * m->dhf[nl - 1]) * FL(zl, nl - 1, D)[c] * dt * (-FL(pl, nl - 1, D)[c] * (1 - ediag) + ediag);
     }
 }
+/* filter_de, qg_energy.h:207-226 */
+static void filter_de(orc_model *m, double dtflt, double ediag) {
+  int n = m->N, D = m->depth, nl = m->nl;
+  set_vars_energy(m);
+  wavelet_filter(m, &m->qol, &m->pol, &m->tmp2l, -dtflt, 0);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      for (int l = 0; l < nl; l++) {
+        size_t c = IDX(n, i, j);
+        double *pm = FL(&m->po_mft, l, D);
+        FL(&m->de_ftl, l, D)[c] += FL(&m->tmp2l, l, D)[c] * dtflt * (-pm[c] * (1 - ediag) + ediag);
+        pm[c] = 0;
+      }
+  m->nme_ft = 0;
+}
 /* energy_tend, qg_energy.h:228-242 */
 static void energy_tend(orc_model *m, flist *pl, double dt, double ediag) {
   int n = m->N, D = m->depth, nl = m->nl;
@@ -1444,6 +1600,7 @@ static void energy_tend(orc_model *m, flist *pl, double dt, double ediag) {
       }
   m->nme_ft += 1;
 }
+void orc_filter_de(orc_model *m, double dtflt) { filter_de(m, dtflt, (double)m->p.ediag); }
 void orc_energy_tend(orc_model *m, double dt) { energy_tend(m, &m->pol, dt, (double)m->p.ediag); }
 /* pystep_de, qg_energy.h:294-340: ediag = 1, dt = 1 (locals shadow the globals); filter_de (wavelet filter) is
  * out of scope, de_ft is returned as reset (0) */

@@ -59,7 +59,8 @@ enum {
   /* energy diagnostics, msqg/qg_energy.h:7-15 */
   ORC_DE_BF, ORC_DE_VD, ORC_DE_J1, ORC_DE_J2, ORC_DE_J3, ORC_DE_FT, ORC_PO_MFT,
   /* passive tracers, msqg/qg.h:100-101: nl*nptr scalars, index l*nptr + nt */
-  ORC_PTR, ORC_PTR_RELAX, ORC_DPTR
+  ORC_PTR, ORC_PTR_RELAX, ORC_DPTR,
+  ORC_QOF, ORC_SIGLEV /* qofl (qg.h:27), sig_lev (qg.h:49; finest level through get_field) */
 };
 
 void orc_default_params(orc_params *p);
@@ -93,6 +94,12 @@ double orc_step(orc_model *m);
 int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, int verbose);
 double orc_time(orc_model *m);
 double orc_ke1(orc_model *m);                    /* qg.c:101-106 */
+
+/* wavelet_filter(qol, pol, qofl, dtflt, nbar), msqg/qg.h:509-560 (the `filter` event, :655-658) */
+void orc_wavelet_filter(orc_model *m, double dtflt);
+void orc_filter_de(orc_model *m, double dtflt);   /* filter_de, qg_energy.h:207-226, with the model's ediag */
+/* sig_lev on level l (n = 2^l cells per side), [y][x] */
+void orc_get_siglev(orc_model *m, int level, double *v);
 
 /* energy diagnostics, msqg/qg_energy.h (ediag > -1): energy_tend(pol, dt) of the comp_diag event (:228-242,289-291);
    the lists are created on first use (set_vars_energy, :244-253).  filter_de needs the wavelet filter, which is

@@ -17,6 +17,7 @@ MAXL = 32
 PSI, Q, PSIPG, FR, QFORC, TOPO, RD, SSTOCH, ZETA, DQ, STR, NSTOCH, IBU, CL2M, CM2L, PM, QM, TMP, ZETAP = range(19)
 DE_BF, DE_VD, DE_J1, DE_J2, DE_J3, DE_FT, PO_MFT = range(19, 26)  # energy diagnostics, qg_energy.h
 PTR, PTR_RELAX, DPTR = range(26, 29)  # passive tracers, qg.h:100-101
+QOF, SIGLEV = 29, 30  # wavelet filter: filter mean qofl (qg.h:27), sig_lev (qg.h:49)
 
 
 class Params(C.Structure):
@@ -106,6 +107,9 @@ def lib(omp=False):
     L.orc_ke1.argtypes = [vp]
     L.orc_ke1.restype = C.c_double
     L.orc_pystep_bfn.argtypes = [vp, dp, dp, C.c_double, C.c_int]
+    L.orc_wavelet_filter.argtypes = [vp, C.c_double]
+    L.orc_get_siglev.argtypes = [vp, C.c_int, dp]
+    L.orc_filter_de.argtypes = [vp, C.c_double]
     L.orc_energy_tend.argtypes = [vp, C.c_double]
     L.orc_reset_energy.argtypes = [vp]
     L.orc_pystep_de.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, C.c_int]
@@ -220,6 +224,15 @@ class Model:
 
     def ke1(self):
         return self.L.orc_ke1(self.h)
+
+    def wavelet_filter(self, dtflt):
+        self.L.orc_wavelet_filter(self.h, dtflt)
+
+    def siglev(self, level):
+        n = 1 << level
+        out = np.zeros((n, n))
+        self.L.orc_get_siglev(self.h, level, out)
+        return out
 
     def energy_tend(self, dt):
         self.L.orc_energy_tend(self.h, dt)

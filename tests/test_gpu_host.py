@@ -140,3 +140,29 @@ def test_qg_exe_passive_tracers_files(gpu, tmp_path):
     assert sum(f.startswith("ptr") for f in names) == 3
     for f in names:
         assert (gdir / f).read_bytes() == (wo / f).read_bytes(), f
+
+
+def test_qg_exe_filter_event_files(gpu, tmp_path):
+    """dtflt > 0: the `filter` event (qg.h:655-658) fires every dtflt and enters dtnext(); the output event writes
+    pf%09d.bas = invertq(tmpl, qofl) (qg.c:124-129).  stdout cadence and every file bit-identical to the oracle."""
+    from oracle import oracle as O
+    N, nl = 64, 2
+    wd = tmp_path / "gpu"; wd.mkdir()
+    wo = tmp_path / "orc"; wo.mkdir()
+    _write_params(str(wd / "params.in"), N, nl, tend=0.1, dtout=0.05, extra="dtflt = 0.03\nafilt = 4.\nediag = 0\n")
+    psi = synth_psi(N, nl)
+    O.lib().orc_write_bas(str(wd / "p0.bas").encode(), nl, N, 80., psi)
+    exe = os.path.join(ROOT, "msom_b200", "lib", "qg.e")
+    out = subprocess.run([exe], cwd=str(wd), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("Filter solution") == 3                    # t = 0.03, 0.06, 0.09
+    po = O.Params(); O.lib().orc_default_params(po); O.lib().orc_read_params(str(wd / "params.in").encode(), po)
+    mo = O.Model(po)
+    p0 = np.zeros_like(psi); O.lib().orc_read_bas(str(wd / "p0.bas").encode(), nl, N, 80., p0)
+    mo.set(O.PSI, p0); mo.L.orc_remove_mean_psi(mo.h); mo.set_const()
+    assert mo.run(outdir=str(wo)) > 0
+    gdir = wd / "outdir_0001"
+    names = sorted(f for f in os.listdir(wo) if f.endswith(".bas"))
+    assert sum(f.startswith("pf") for f in names) == 3 and sum(f.startswith("de_ft") for f in names) == 3
+    for f in names:
+        assert (gdir / f).read_bytes() == (wo / f).read_bytes(), f

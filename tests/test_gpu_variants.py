@@ -266,3 +266,32 @@ def test_partial_slip_boundary(gpu, N, nl, sbc, over):
     for _ in range(3):
         ref.step()
     assert not np.array_equal(ref.get(O.Q), mo.get(O.Q))      # the boundary condition matters
+
+
+@pytest.mark.parametrize("N,nl,afilt,modal", [(64, 2, 4.0, 0), (128, 3, 2.5, 0), (64, 4, 7.0, 0), (64, 3, 4.0, 1)])
+def test_wavelet_filter(gpu, N, nl, afilt, modal):
+    """multi-scale wavelet filter (msqg/qg.h:509-560): invertq, [BASILISK] wavelet / sig_lev /
+    inverse_wavelet per layer, comp_q and the filter mean, bit-exact against the oracle; then steps continue from
+    the filtered state and filter_de (qg_energy.h:207-226) feeds the energy budget."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    if modal and O._lapack_path() is None:
+        pytest.skip("no LAPACK dgeev")
+    mo, mg, _ = make_pair(N, nl, afilt=afilt, dtflt=0.05, ediag=0, mode_pv_invert=modal)
+    mo.set_const(); mg.set_const()
+    for _ in range(2):
+        assert mg.step() == mo.step()
+    mo.wavelet_filter(0.05); mg.wavelet_filter(0.05)
+    for fo, fg in ((O.PSI, G.PSI), (O.Q, G.Q), (O.QOF, G.QOF), (O.TMP, G.TMP), (O.SIGLEV, G.SIGLEV)):
+        a, b = mg.get(fg), mo.get(fo)
+        assert np.array_equal(a, b), (fg, float(np.abs(a - b).max()))
+    assert np.abs(mg.get(G.QOF)).max() > 0
+    mo.energy_tend(0.01); mg.energy_tend(0.01)
+    mo.L.orc_filter_de(mo.h, 0.05); mg.filter_de(0.05)
+    for fo, fg in ((O.DE_FT, G.DE_FT), (O.PO_MFT, G.PO_MFT), (O.Q, G.Q), (O.PSI, G.PSI)):
+        a, b = mg.get(fg), mo.get(fo)
+        assert np.array_equal(a, b), (fg, float(np.abs(a - b).max()))
+    assert np.abs(mg.get(G.DE_FT)).max() > 0 and not mg.get(G.PO_MFT).any()
+    for _ in range(2):
+        assert mg.step() == mo.step()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))

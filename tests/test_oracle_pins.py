@@ -222,3 +222,27 @@ def test_tracer_mean_is_conserved_by_advection_and_diffusion():
         assert np.abs(b - a).max() > 0 and abs(b.mean() - a.mean()) < 1e-12 * np.abs(a).mean()
         a, b = tr[l * nptr + 1], t2[l * nptr + 1]            # relaxed towards 3
         assert abs(b.mean() - 3.0) < abs(a.mean() - 3.0)
+
+
+def test_wavelet_filter_limits():
+    """wavelet_filter (qg.h:509-560) with [BASILISK]'s wavelet()/inverse_wavelet(): sig_lev is a high-pass mask built
+    from sig_filt = min(afilt*Rd, Lfmax) (qg.h:1057-1090).  A filter scale above every level keeps all coefficients
+    (the reconstruction is the identity to round-off), a scale below the grid removes the whole field, and in
+    between the filter is a linear projector-like operator: filtering twice changes little more."""
+    N, nl = 64, 2
+    psi = synth_psi(N, nl)
+    out = {}
+    for afilt in (1e9, 1e-3, 4.0):
+        m = O.Model(O.make_params(**base_kw(N, nl, afilt=afilt, dtflt=0.05)))
+        m.set(O.PSI, psi); m.set_const()
+        q0 = m.get(O.Q)
+        m.wavelet_filter(0.05)
+        out[afilt] = (q0, m.get(O.Q), m.get(O.PSI), m.get(O.QOF), [float(m.siglev(l).min()) for l in range(7)],
+                      [float(m.siglev(l).max()) for l in range(7)])
+    q0, q1, p1, qof, lo, hi = out[1e9]
+    assert lo == [1.0] * 7 and np.abs(q1 - q0).max() < 1e-13 and np.abs(p1 - psi).max() < 1e-12
+    q0, q1, p1, qof, lo, hi = out[1e-3]
+    assert hi == [0.0] * 7 and not p1.any() and not q1.any()
+    assert np.allclose(qof, (q0 - q1) / 0.05, rtol=0, atol=1e-15)      # qof = (q_before - q_after)/dtflt with nbar = 0
+    q0, q1, p1, qof, lo, hi = out[4.0]
+    assert 0 < hi[6] and lo[0] == 0.0 and 0 < np.abs(q1).max() < np.abs(q0).max()
