@@ -156,6 +156,9 @@ int msqg_wavelet_filter(msqg_model *m, double dtflt);
 int msqg_invert_filter_mean(msqg_model *m);
 /* filter_de (qg_energy.h:207-226): second filter pass into tmp2l with -dtflt, de_ft += ..., po_mft = 0 */
 int msqg_filter_de(msqg_model *m, double dtflt, double ediag);
+/* the same with the running-mean slot named by the caller: pystep_de passes pol there (qg_energy.h:330), which zeroes
+ * psi.  pm_field is MSQG_PO_MFT or MSQG_PSI. */
+int msqg_filter_de_pm(msqg_model *m, double dtflt, double ediag, int pm_field);
 /* energy diagnostics, msqg/qg_energy.h: energy_tend(pol, dt) of the comp_diag event (:228-242) with the weight
  * switch `ediag` (0: -psi*dq/dt, 1: dq/dt; qg.h:87).  The de_* lists are created on first use (set_vars_energy). */
 int msqg_energy_tend(msqg_model *m, double dt, double ediag);

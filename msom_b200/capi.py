@@ -86,6 +86,7 @@ def lib():
     L.msqg_wavelet_filter.argtypes = [vp, C.c_double]
     L.msqg_invert_filter_mean.argtypes = [vp]
     L.msqg_filter_de.argtypes = [vp, C.c_double, C.c_double]
+    L.msqg_filter_de_pm.argtypes = [vp, C.c_double, C.c_double, C.c_int]
     L.msqg_reset_energy.argtypes = [vp]
     L.msqg_set_field.argtypes = [vp, C.c_int, dp]
     L.msqg_get_field.argtypes = [vp, C.c_int, dp]

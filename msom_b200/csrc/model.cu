@@ -1587,8 +1587,9 @@ extern "C" int msqg_invert_filter_mean(msqg_model *m) {
   return rc;
 }
 static int ensure_energy_lists(msqg_model *m);
-extern "C" int msqg_filter_de(msqg_model *m, double dtflt, double ediag) {
+extern "C" int msqg_filter_de_pm(msqg_model *m, double dtflt, double ediag, int pm_field) {
   CK(cudaSetDevice(m->device));
+  if (pm_field != MSQG_PO_MFT && pm_field != MSQG_PSI) FAIL(MSQG_ERR_ARG, "filter_de: the mean slot is MSQG_PO_MFT or MSQG_PSI");
   int rc;
   if ((rc = ensure_energy_lists(m))) return rc;
   if ((rc = ensure_filter_lists(m))) return rc;
@@ -1596,12 +1597,14 @@ extern "C" int msqg_filter_de(msqg_model *m, double dtflt, double ediag) {
   const int D = m->depth;
   const Geom &g = m->g[D];
   dim3 b(64, 4);
-  k_filter_de<<<grid2(g.nx, g.ny, b, m->nl), b, 0, m->stream>>>(m->de_ft.lev[D], m->tmp2.lev[D], m->po_mft.lev[D], g, dtflt, ediag);
+  k_filter_de<<<grid2(g.nx, g.ny, b, m->nl), b, 0, m->stream>>>(m->de_ft.lev[D], m->tmp2.lev[D],
+                                                                (pm_field == MSQG_PSI ? m->psi : m->po_mft).lev[D], g, dtflt, ediag);
   m->launches++;
   CK(cudaGetLastError());
   m->nme_ft = 0;
   return MSQG_OK;
 }
+extern "C" int msqg_filter_de(msqg_model *m, double dtflt, double ediag) { return msqg_filter_de_pm(m, dtflt, ediag, MSQG_PO_MFT); }
 
 /* ------------------------------------------------------------------ energy diagnostics, msqg/qg_energy.h */
 static int ensure_energy_lists(msqg_model *m) { /* set_vars_energy, qg_energy.h:244-253 */

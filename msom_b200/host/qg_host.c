@@ -317,8 +317,8 @@ int pyp2q(double *po_py, int len13, int len14, int len15, double *qo_py, int len
 /* ---------------------------------------------------------------- energy diagnostics, qg_energy.h / qg_energy.i */
 int set_vars_energy(void) { return M ? fail(msqg_reset_energy(M)) : MSQG_ERR_ARG; }
 int trash_vars_energy(void) { return MSQG_OK; } /* the lists live and die with the handle (trash_vars) */
-/* pystep_de, qg_energy.h:294-340: ediag = 1, dt = 1 (locals).  filter_de needs the wavelet filter (out of scope):
- * de_ft is returned as reset.  onlyKE zeroes the stretching field, as the reference does (permanently). */
+/* pystep_de, qg_energy.h:294-340: ediag = 1, dt = 1 (locals).  filter_de is called with pol in the po_mft slot
+ * (:330): psi is zero afterwards.  onlyKE zeroes the stretching field, as the reference does (permanently). */
 int pystep_de(double *po_py, int len1, int len2, int len3, double *de_bf_py, int len4, int len5, int len6,
               double *de_vd_py, int len7, int len8, int len9, double *de_j1_py, int len10, int len11, int len12,
               double *de_j2_py, int len13, int len14, int len15, double *de_j3_py, int len16, int len17, int len18,
@@ -333,6 +333,7 @@ int pystep_de(double *po_py, int len1, int len2, int len3, double *de_bf_py, int
   if ((rc = msqg_comp_q(M))) return fail(rc);
   if (onlyKE == 1 && (rc = msqg_reset_field(M, MSQG_STR))) return fail(rc);
   if ((rc = msqg_energy_tend(M, 1., 1.))) return fail(rc);
+  if ((rc = msqg_filter_de_pm(M, P.dtflt, 1., MSQG_PSI))) return fail(rc);
   double *out[6] = {de_bf_py, de_vd_py, de_j1_py, de_j2_py, de_j3_py, de_ft_py};
   const int ids[6] = {MSQG_DE_BF, MSQG_DE_VD, MSQG_DE_J1, MSQG_DE_J2, MSQG_DE_J3, MSQG_DE_FT};
   for (int k = 0; k < 6; k++) if ((rc = msqg_get_field(M, ids[k], out[k]))) return fail(rc);

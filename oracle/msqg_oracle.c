@@ -1272,7 +1272,7 @@ int orc_read_bas(const char *name, int nf, int N, double L0, double *v) {
  * writestdout (i++), output (t=0; t<=tend+1e-10; t+=dtout), and dtnext(). */
 static void energy_tend(orc_model *m, flist *pl, double dt, double ediag);
 static void reset_layer_var(orc_model *m, flist *f);
-static void filter_de(orc_model *m, double dtflt, double ediag);
+static void filter_de(orc_model *m, flist *pml, double dtflt, double ediag);
 static void wavelet_filter(orc_model *m, flist *ql, flist *pl, flist *qofl, double dtflt, int nbar);
 int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, int verbose) {
   double ev_t = 0.;
@@ -1287,7 +1287,7 @@ int orc_run(orc_model *m, int max_steps, int write_files, const char *outdir, in
     if (evf_alive && fabs(m->t - ev_f) <= TEPS * m->t) {
       if (verbose) fprintf(stdout, "Filter solution\n");
       wavelet_filter(m, &m->qol, &m->pol, &m->qofl, m->p.dtflt, m->nbar);
-      if (m->p.ediag > -1) filter_de(m, m->p.dtflt, (double)m->p.ediag);
+      if (m->p.ediag > -1) filter_de(m, &m->po_mft, m->p.dtflt, (double)m->p.ediag);
       ev_f += m->p.dtflt;
       if (!(ev_f <= m->p.tend + 1e-10)) evf_alive = 0;
     }
@@ -1569,7 +1569,7 @@ static void ekman_friction_de(orc_model *m, flist *zl, flist *dql, flist *pl, do
     }
 }
 /* filter_de, qg_energy.h:207-226 */
-static void filter_de(orc_model *m, double dtflt, double ediag) {
+static void filter_de(orc_model *m, flist *pml, double dtflt, double ediag) {
   int n = m->N, D = m->depth, nl = m->nl;
   set_vars_energy(m);
   wavelet_filter(m, &m->qol, &m->pol, &m->tmp2l, -dtflt, 0);
@@ -1577,7 +1577,7 @@ static void filter_de(orc_model *m, double dtflt, double ediag) {
     for (int j = 0; j < n; j++)
       for (int l = 0; l < nl; l++) {
         size_t c = IDX(n, i, j);
-        double *pm = FL(&m->po_mft, l, D);
+        double *pm = FL(pml, l, D);
         FL(&m->de_ftl, l, D)[c] += FL(&m->tmp2l, l, D)[c] * dtflt * (-pm[c] * (1 - ediag) + ediag);
         pm[c] = 0;
       }
@@ -1600,10 +1600,11 @@ static void energy_tend(orc_model *m, flist *pl, double dt, double ediag) {
       }
   m->nme_ft += 1;
 }
-void orc_filter_de(orc_model *m, double dtflt) { filter_de(m, dtflt, (double)m->p.ediag); }
+void orc_filter_de(orc_model *m, double dtflt) { filter_de(m, &m->po_mft, dtflt, (double)m->p.ediag); }
 void orc_energy_tend(orc_model *m, double dt) { energy_tend(m, &m->pol, dt, (double)m->p.ediag); }
-/* pystep_de, qg_energy.h:294-340: ediag = 1, dt = 1 (locals shadow the globals); filter_de (wavelet filter) is
- * out of scope, de_ft is returned as reset (0) */
+/* pystep_de, qg_energy.h:294-340: ediag = 1, dt = 1 (locals shadow the globals).  filter_de is called with pol in
+ * the po_mft slot (:330), so psi is zeroed on the way out; with the default dtflt = -1 the inner wavelet_filter sees
+ * +1 and leaves q filtered. */
 void orc_pystep_de(orc_model *m, const double *po_py, double *de_bf, double *de_vd, double *de_j1, double *de_j2,
                    double *de_j3, double *de_ft, int onlyKE) {
   int n = m->N, D = m->depth, nl = m->nl;
@@ -1619,6 +1620,7 @@ void orc_pystep_de(orc_model *m, const double *po_py, double *de_bf, double *de_
   advection_de(m, &m->zetal, &m->pol, dt, ediag);
   dissip_de(m, &m->zetal, &m->de_vdl, &m->pol, dt, ediag);
   ekman_friction_de(m, &m->zetal, &m->de_bfl, &m->pol, dt, ediag);
+  filter_de(m, &m->pol, m->p.dtflt, ediag);
   get_list(&m->de_bfl, n, de_bf); get_list(&m->de_vdl, n, de_vd);
   get_list(&m->de_j1l, n, de_j1); get_list(&m->de_j2l, n, de_j2);
   get_list(&m->de_j3l, n, de_j3); get_list(&m->de_ftl, n, de_ft);

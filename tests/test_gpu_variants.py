@@ -185,12 +185,14 @@ def test_energy_diagnostics(gpu, N, nl, ediag, over):
     assert not mg.get(G.DE_J1).any() and not mg.get(G.DE_VD).any()
 
 
-def test_pystep_de_python_entry(gpu):
-    """pystep_de of the SWIG module (msqg/qg_energy.i:30-39) through the ctypes mirror, against the oracle"""
+@pytest.mark.parametrize("dtflt", [-1.0, 0.05])
+def test_pystep_de_python_entry(gpu, dtflt):
+    """pystep_de of the SWIG module (msqg/qg_energy.i:30-39) through the ctypes mirror, against the oracle; the
+    filter term de_ft (filter_de with pol in the mean slot, qg_energy.h:330) for the default and a positive dtflt"""
     from oracle import oracle as O
     import msom_b200.qg as bas
     N, nl = 64, 3
-    kw = base_kw(N, nl, Re=100.)
+    kw = base_kw(N, nl, Re=100., dtflt=dtflt, afilt=4.0)
     mo = O.Model(O.make_params(**kw))
     psi = synth_psi(N, nl)
     mo.set(O.PSI, psi); mo.set_const()
@@ -214,6 +216,7 @@ def test_pystep_de_python_entry(gpu):
         bas.trash_vars()
     for a, b in zip(out, ref):
         assert np.array_equal(a, b), float(np.abs(a - b).max())
+    assert np.abs(out[5]).max() > 0
 
 
 @pytest.mark.parametrize("N,nl,nptr,over", [(64, 2, 1, dict(Pe=[40.])), (128, 3, 2, dict(Pe=[50., 0.], ptr_r=[0., 5.])),
