@@ -449,6 +449,7 @@ struct RelaxArgs {
   long long *dbg;               /* optional [nworkers][4]: start ns, end ns, spins, - */
   int flags;                    /* reserved for timing experiments */
   const double *rowcoef;        /* k_relax_ws<..., RCOEF>: [ny][6][NL] per-row t0, t2, t1p, rinv, cf, cb (stretching varies with y) */
+  int coef_cell;                /* 1: the table is per cell, [ny][nx][6][NL] (stretching varies with x too: frpg_*.bas, qg.h:957-962) */
   int w_base;                   /* k_relax_ws: index of the first strip of this launch (levels wider than the device holds
                                    co-resident strips are swept in column panels; the mailbox carries the boundary column) */
 };
@@ -731,13 +732,14 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
  * of relax_coef_layers() (msqg/poisson_layer.h:89-139, same order, IEEE division) evaluated with the level's
  * restricted stretching field at column 0 of every row.  out[j][6][NL] = t0, t2, t1p, rinv, cf, cb. */
 template <int NL>
-__global__ void k_rowcoef(const double *__restrict__ s, Geom g, LayerMetrics M, double *__restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.ny) return;
+__global__ void k_rowcoef(const double *__restrict__ s, Geom g, LayerMetrics M, double *__restrict__ out, int cell) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; /* one thread per row, or per cell (x fastest) */
+  if (t >= (size_t)g.ny * (cell ? g.nx : 1)) return;
+  const int j = cell ? (int)(t / g.nx) : (int)t, ix = cell ? (int)(t % g.nx) : 0;
   const double D2 = g.Delta * g.Delta;
   double sv[NL], t0[NL], t1[NL], t2[NL];
 #pragma unroll
-  for (int l = 0; l < NL; l++) { sv[l] = (l < NL - 1) ? s[(size_t)l * g.plane + GIDX(g.pitch, j, 0)] : 0.; t0[l] = t1[l] = t2[l] = 0.; }
+  for (int l = 0; l < NL; l++) { sv[l] = (l < NL - 1) ? s[(size_t)l * g.plane + GIDX(g.pitch, j, ix)] : 0.; t0[l] = t1[l] = t2[l] = 0.; }
   if (NL > 1) {
     t2[0] = -D2 * sv[0] * M.idh1[0];
     t1[0] = -t2[0];
@@ -755,7 +757,7 @@ __global__ void k_rowcoef(const double *__restrict__ s, Geom g, LayerMetrics M, 
 #pragma unroll
     for (int l = 1; l < NL; l++) t1[l] -= t0[l] * t2[l - 1] / t1[l - 1];
   }
-  double *o = out + (size_t)j * 6 * NL;
+  double *o = out + t * 6 * NL;
 #pragma unroll
   for (int l = 0; l < NL; l++) {
     const double r = 1. / t1[l];
@@ -973,7 +975,14 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       load_inputs();
       double cn[NCF];
       if (RCOEF) {
-        const double2 *pc = reinterpret_cast<const double2 *>(A.rowcoef + (size_t)min(max(jn, 0), ny - 1) * (6 * NL));
+        const int rn = min(max(jn, 0), ny - 1);
+        const size_t ce = A.coef_cell ? (size_t)rn * nx + min(max(i, 0), nx - 1) : (size_t)rn;
+        const double2 *pc = reinterpret_cast<const double2 *>(A.rowcoef + ce * (6 * NL));
+        if (A.coef_cell) { /* per-cell tables stream from HBM: pull the lines of this lane's cell 12 rows ahead into L2 */
+          const char *pf = reinterpret_cast<const char *>(A.rowcoef + ((size_t)min(rn + 12, ny - 1) * nx + min(max(i, 0), nx - 1)) * (6 * NL));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128));
+        }
 #pragma unroll
         for (int i = 0; i < NCF / 2; i++) { const double2 t = __ldg(pc + i); cn[2 * i] = t.x; cn[2 * i + 1] = t.y; }
       }

@@ -718,7 +718,8 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   RelaxArgs A;
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
   A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0; A.w_base = 0; A.rowcoef = RCOEF ? m->rowcoef[lev] : nullptr;
-  if (RCOEF && (g.bc || !A.rowcoef)) FAIL(MSQG_ERR_ARG, "y-dependent stretching (varRo) is supported on undecomposed levels only");
+  A.coef_cell = (RCOEF && !m->s_rowuniform) ? 1 : 0;
+  if (RCOEF && (g.bc || !A.rowcoef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
   const size_t smem = Cfg::smem_per_worker * WPC;
   const int tv = g.bc ? 1 : 0;
   auto kern = RCOEF ? k_relax_ws<NL, K, WPC, false, RCOEF> : (tv ? k_relax_ws<NL, K, WPC, true> : k_relax_ws<NL, K, WPC, false>);
@@ -916,8 +917,6 @@ static int invertq_list(msqg_model *m, List &ql) {
   const Geom &g = m->g[D];
   int rc;
   if (!m->p.mode_pv_invert) {
-    if (!m->s_uniform && !m->s_rowuniform)
-      FAIL(MSQG_ERR_ARG, "stretching that varies with x (frpg_*.bas) is not supported by the relax kernel yet");
     MgProblem P{m->nl, -1, m->psi.lev[D], ql.lev[D]};
     if ((rc = mg_solve(m, P, 1e-3, &m->mgpsi))) return rc;
   } else {
@@ -1146,12 +1145,15 @@ static int set_const_local(msqg_model *m) {
   /* varRo > 0: the stretching depends on y only -> per-row Thomas coefficients for the relax kernel, built on the
      device from the restricted stretching field of every level (same expressions as relax_coef_layers) */
   for (int l = 0; l <= MSQG_MAXLEV; l++) if (m->rowcoef[l]) { CK(cudaFree(m->rowcoef[l])); m->rowcoef[l] = nullptr; }
-  if (!uniform && rowuniform && m->g[D].bc == 0 && m->agg_level <= 1) {
+  if (!uniform && m->g[D].bc == 0 && m->agg_level <= 1) {
+    /* stretching that varies with x as well (Fr from frpg_*.bas, qg.h:957-962): the same table per CELL */
     const LayerMetrics M = metrics_of(m);
+    const int cell = rowuniform ? 0 : 1;
     for (int l = 1; l <= D; l++) {
       const Geom &gl = m->g[l];
-      CK(cudaMalloc(&m->rowcoef[l], (size_t)gl.ny * 6 * nl * sizeof(double)));
-      NL_SWITCH(nl, k_rowcoef<NL><<<(gl.ny + 127) / 128, 128, 0, m->stream>>>(m->str.lev[l], gl, M, m->rowcoef[l]));
+      const size_t ent = (size_t)gl.ny * (cell ? gl.nx : 1);
+      CK(cudaMalloc(&m->rowcoef[l], ent * 6 * nl * sizeof(double)));
+      NL_SWITCH(nl, k_rowcoef<NL><<<(unsigned)((ent + 127) / 128), 128, 0, m->stream>>>(m->str.lev[l], gl, M, m->rowcoef[l], cell));
       m->launches++;
     }
     CK(cudaGetLastError());

@@ -162,6 +162,40 @@ def test_variable_rossby_number(gpu, N, nl, nsteps):
     assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
 
 
+@pytest.mark.parametrize("N,nl,varRo,nsteps", [(128, 3, 0, 3), (64, 4, 1, 3), (256, 2, 0, 2)])
+def test_stretching_varies_in_x_and_y(gpu, N, nl, varRo, nsteps):
+    """Fr from the planetary-geostrophic model (frpg_%dl_N%d.bas -> Frl, msqg/qg.h:957-962): the stretching
+    strl = (Fr/Ro)^2 varies with x and y, the relax kernel reads per-CELL Thomas coefficients on every level (built
+    from the restricted stretching field, poisson_layer.h:284).  Bit-exact against the oracle, equal cycle counts."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    mo, mg, psi = make_pair(N, nl, varRo=varRo)
+    rng = np.random.default_rng(77)
+    y, x = np.meshgrid((np.arange(N) + 0.5) / N, (np.arange(N) + 0.5) / N, indexing="ij")
+    fr = np.zeros_like(psi)
+    for l in range(nl - 1):
+        fr[l] = (0.003 + 0.002 * l) * (1 + 0.3 * np.sin(2 * np.pi * x) * np.cos(np.pi * y) + 0.05 * rng.uniform(-1, 1, (N, N)))
+    mo.set(O.FR, fr); mg.set(G.FR, fr)
+    mo.set_const(); mg.set_const()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+    z = np.zeros_like(psi)
+    mo.set(O.PSI, z); mg.set(G.PSI, z)
+    mo.invertq(); mg.invertq()
+    so, sg = mo.mgstats(), mg.mgstats()
+    assert (sg.i, sg.nrelax, sg.resb, sg.resa) == (so.i, so.nrelax, so.resb, so.resa)
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    for _ in range(nsteps):
+        assert mg.step() == mo.step()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
+    # the x-dependence matters: the uniform-Fr model gives a different answer
+    ref, _, _ = make_pair(N, nl, varRo=varRo)
+    ref.set_const()
+    for _ in range(nsteps):
+        ref.step()
+    assert not np.array_equal(ref.get(O.Q), mo.get(O.Q))
+
+
 @pytest.mark.parametrize("N,nl,ediag,over", [(64, 2, 0, {}), (128, 3, 1, dict(Re=200.)), (64, 4, 0, dict(Re=50., Eks=0.001)),
                                               (64, 3, 0, dict(upg=[0.3, 0.1, 0.], vpg=[0.05, 0., 0.], flsrv=1))])
 def test_energy_diagnostics(gpu, N, nl, ediag, over):
