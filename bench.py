@@ -279,6 +279,13 @@ def run_ours(args):
                   cycles * (ab["restrict"] * 1.0 + ab["prolong"] * 1.0 + ab["correct"] + ab["residual"]) +
                   sweeps_all * ab["relax_sweep"] * 4.0 / 3) * cells / args.steps
     step_roof = step_bytes / (ms_step * 1e-3) / 1e9
+    # BASELINE metric, second half: wall-ms of one multigrid cycle (restriction of the residual, relax on every level,
+    # prolongations, correction, residual) = the per-launch device times of those kernels over the timed region / cycles
+    vcycle_ms = None
+    if cycles > 0:
+        res = prof["residual"]
+        vcycle_ms = (prof["relax_fine"]["ms"] + prof["relax_coarse"]["ms"] + prof["restrict"]["ms"] + prof["prolong"]["ms"] +
+                     prof["correct"]["ms"] + (res["ms"] / res["count"] * cycles if res["count"] else 0.)) / cycles
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -304,7 +311,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(tile_cells * 8), "d2h_bytes_per_step": int(tile_cells * 8),
                     "steps": esteps, "ms_per_step": e2e_s / esteps * 1e3},
             "roofline": roof, "cpu_baseline": cpu,
-            "kernel_ms_per_step": kern_ms,
+            "kernel_ms_per_step": kern_ms, "vcycle_ms": vcycle_ms,
             "step_roofline": {"algorithmic_bytes_per_cell_layer_per_step": step_bytes / cells, "achieved": step_roof,
                               "peak": peak, "unit": "GB/s", "frac": step_roof / peak}}
     emit(line)

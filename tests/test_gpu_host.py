@@ -166,3 +166,57 @@ def test_qg_exe_filter_event_files(gpu, tmp_path):
     assert sum(f.startswith("pf") for f in names) == 3 and sum(f.startswith("de_ft") for f in names) == 3
     for f in names:
         assert (gdir / f).read_bytes() == (wo / f).read_bytes(), f
+
+
+def test_qg_exe_planetary_geostrophic_input_files(gpu, tmp_path):
+    """The multiple-scale coupling inputs of set_const (msqg/qg.h:950-969): psipg_%dl_N%d.bas (large-scale stream
+    function), frpg_%dl_N%d.bas (Froude number varying in x and y -> per-cell stretching) and rdpg_%dl_N%d.bas
+    (deformation radius of the filter scale) are read from the working directory, backed up into the output directory
+    (qg.h:806-820) and every output is bit-identical to the oracle's run() fed the same float32 files."""
+    from oracle import oracle as O
+    N, nl = 64, 3
+    wd = tmp_path / "gpu"; wd.mkdir()
+    wo = tmp_path / "orc"; wo.mkdir()
+    _write_params(str(wd / "params.in"), N, nl, tend=0.1, dtout=0.05, extra="flsrv = 1\n")
+    psi = synth_psi(N, nl)
+    y, x = np.meshgrid((np.arange(N) + 0.5) / N, (np.arange(N) + 0.5) / N, indexing="ij")
+    kw = base_kw(N, nl)
+    fr = np.zeros_like(psi); ppg = np.zeros_like(psi)
+    for l in range(nl):
+        if l < nl - 1:
+            fr[l] = kw["Fr"][l] * (1 + 0.25 * np.sin(2 * np.pi * x) * np.sin(np.pi * y))
+        ppg[l] = 0.2 / (l + 1) * np.cos(np.pi * x) * np.sin(np.pi * y)
+    rd = (1.0 + 0.5 * x * y)[None]
+    names_in = {"p0.bas": (nl, psi), "frpg_%dl_N%d.bas" % (nl, N): (nl, fr), "psipg_%dl_N%d.bas" % (nl, N): (nl, ppg),
+                "rdpg_%dl_N%d.bas" % (nl, N): (1, np.ascontiguousarray(rd))}
+    for name, (nf, a) in names_in.items():
+        O.lib().orc_write_bas(str(wd / name).encode(), nf, N, 80., np.ascontiguousarray(a))
+    exe = os.path.join(ROOT, "msom_b200", "lib", "qg.e")
+    out = subprocess.run([exe], cwd=str(wd), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for name in names_in:
+        if name != "p0.bas":
+            assert "%s .. ok" % name in out.stdout
+    po = O.Params(); O.lib().orc_default_params(po); O.lib().orc_read_params(str(wd / "params.in").encode(), po)
+    mo = O.Model(po)
+
+    def rd_file(name, nf):
+        a = np.zeros((nf, N, N)); O.lib().orc_read_bas(str(wd / name).encode(), nf, N, 80., a); return a
+    mo.set(O.PSI, rd_file("p0.bas", nl)); mo.L.orc_remove_mean_psi(mo.h)
+    mo.set(O.FR, rd_file("frpg_%dl_N%d.bas" % (nl, N), nl))
+    mo.set(O.PSIPG, rd_file("psipg_%dl_N%d.bas" % (nl, N), nl))
+    mo.set(O.RD, rd_file("rdpg_%dl_N%d.bas" % (nl, N), 1))
+    mo.set_const()
+    assert mo.run(outdir=str(wo)) > 0
+    gdir = wd / "outdir_0001"
+    names = sorted(f for f in os.listdir(wo) if f.endswith(".bas"))
+    assert len(names) >= 6
+    for f in names:
+        assert (gdir / f).read_bytes() == (wo / f).read_bytes(), f
+    # backup_config: the float32 inputs come back byte for byte; sig_filt = min(afilt*Rd, Lfmax) follows the Rd file
+    for name in names_in:
+        if name != "p0.bas":
+            assert (gdir / name).read_bytes() == (wd / name).read_bytes(), name
+    sig = np.minimum(po.afilt * rd_file("rdpg_%dl_N%d.bas" % (nl, N), 1), po.Lfmax)      # qg.h:1062-1063
+    O.lib().orc_write_bas(str(wo / "sig_filt.bas").encode(), 1, N, 80., np.ascontiguousarray(sig))
+    assert (gdir / "sig_filt.bas").read_bytes() == (wo / "sig_filt.bas").read_bytes()
