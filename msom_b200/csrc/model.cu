@@ -1302,9 +1302,16 @@ static int rhs_launch(msqg_model *m, List &q_ev, const double *q_in, double *q_o
   A.dt = dt; A.itr = m->p.itr_stoch; A.dts = dts;
   A.has_pg = m->has_pg; A.has_zp = m->has_zp; A.use_tmp = (m->iRe != 0. || m->iRe4 != 0.);
   A.flag_topo = m->flag_topo; A.stochastic = m->p.stochastic;
-  dim3 b(32, 4);
   ProfScope ps(m, PROF_RHS, 0);
-  NL_SWITCH(nl, k_rhs<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(A));
+  static int rhs_variant = -1; /* MSQG_RHS=gather keeps the L1-gather kernel on every configuration (A/B measurements) */
+  if (rhs_variant < 0) { const char *e = getenv("MSQG_RHS"); rhs_variant = (e && !strcmp(e, "gather")) ? 0 : 1; }
+  if (rhs_variant == 1 && !A.has_pg && !A.has_zp && !A.flag_topo && !A.stochastic) {
+    dim3 bt(RT_X, RT_Y);
+    NL_SWITCH(nl, k_rhs_t<NL><<<grid2(g.nx, g.ny, bt), bt, 0, m->stream>>>(A));
+  } else {
+    dim3 b(32, 4);
+    NL_SWITCH(nl, k_rhs<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(A));
+  }
   m->launches++;
   CK(cudaGetLastError());
   return MSQG_OK;

@@ -302,6 +302,131 @@ k_rhs(RhsArgs A) {
   }
 }
 
+/* ------------------------------------------------------------------ k_rhs_t: the same right-hand side from
+ * shared-memory tiles.  k_rhs gathers ~26 doubles per cell-layer through L1 and is bound by the latency of those
+ * gathers at 31-37 % occupancy (ncu: 20 % of DRAM peak, 27 % issue active).  Here a 32 x 8 block stages the
+ * 34 x 10 tiles (one-cell halo; the ghost rings are stored, so the halo is always readable) of psi[l], psi[l+1],
+ * zeta[l] and tmp[l] with coalesced loads -- psi[l+1] is kept for the next layer -- and the Jacobians read shared
+ * memory.  Every expression is the one of k_rhs (same tokens, same association): results are bit-identical.
+ * Used for the default terms (no psi_pg / zeta_pg Jacobians, no topography, not stochastic); everything else
+ * stays on k_rhs. */
+#define RT_X 32
+#define RT_Y 8
+#define RT_P (RT_X + 2) /* tile pitch */
+struct TileAcc {
+  const double *t; /* centre of this thread's cell in a [RT_Y+2][RT_P] shared tile */
+  __device__ __forceinline__ double operator()(int a, int b) const { return t[a + b * RT_P]; }
+};
+template <class PA, class QA>
+__device__ __forceinline__ double jac_acc(const PA PO, const QA QO, const Geom &G) {
+  return div_by(((QO(1, 0) - QO(-1, 0)) * (PO(0, 1) - PO(0, -1))
+         + (QO(0, -1) - QO(0, 1)) * (PO(1, 0) - PO(-1, 0))
+         + QO(1, 0) * (PO(1, 1) - PO(1, -1))
+         - QO(-1, 0) * (PO(-1, 1) - PO(-1, -1))
+         - QO(0, 1) * (PO(1, 1) - PO(-1, 1))
+         + QO(0, -1) * (PO(1, -1) - PO(-1, -1))
+         + PO(0, 1) * (QO(1, 1) - QO(-1, 1))
+         - PO(0, -1) * (QO(1, -1) - QO(-1, -1))
+         - PO(1, 0) * (QO(1, 1) - QO(1, -1))
+         + PO(-1, 0) * (QO(-1, 1) - QO(-1, -1))),
+        G.D12, G.rD12);
+}
+__device__ __forceinline__ void rt_load(double *__restrict__ tile, const double *__restrict__ src, const Geom &g, int x0, int y0, int tid) {
+  /* tile[(ry)*RT_P + rx] = src(y0 - 1 + ry, x0 - 1 + rx), rows of the padded plane are contiguous */
+  constexpr int NE = (RT_Y + 2) * RT_P, NT = RT_X * RT_Y;
+#pragma unroll
+  for (int k = 0; k < (NE + NT - 1) / NT; k++) {
+    const int e = tid + k * NT;
+    const int ry = e / RT_P, rx = e - ry * RT_P;
+    const int gx = x0 - 1 + rx, gy = y0 - 1 + ry;
+    if (e < NE && gx <= g.nx && gy <= g.ny) tile[e] = src[GIDX(g.pitch, gy, gx)];
+  }
+}
+template <int NL>
+__global__ void __launch_bounds__(RT_X * RT_Y)
+k_rhs_t(RhsArgs A) {
+  /* tiles of layer l and l+1 (double-buffered): the vertical neighbours zeta[l+-1], tmp[l+-1] of the stretching terms
+     come from the tile staged one layer ahead and from a register of the layer before, so every plane is read once */
+  __shared__ double sp[2][(RT_Y + 2) * RT_P], sz[2][(RT_Y + 2) * RT_P], st[2][(RT_Y + 2) * RT_P];
+  const Geom g = A.g;
+  const int x0 = blockIdx.x * RT_X, y0 = blockIdx.y * RT_Y;
+  const int tid = threadIdx.y * RT_X + threadIdx.x;
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  const bool active = x < g.nx && y < g.ny;
+  const size_t c = GIDX(g.pitch, active ? y : 0, active ? x : 0);
+  const size_t pl = g.plane;
+  const int tc = (threadIdx.y + 1) * RT_P + threadIdx.x + 1;
+  rt_load(sp[0], A.psi, g, x0, y0, tid);
+  rt_load(sz[0], A.zeta, g, x0, y0, tid);
+  if (A.use_tmp) rt_load(st[0], A.tmp, g, x0, y0, tid);
+  double jd = 0., ju;
+  double zm = 0., tm = 0., sm = 0.; /* zeta, tmp, stretching of layer l-1 at this cell */
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    if (l < NL - 1) {
+      rt_load(sp[(l + 1) & 1], A.psi + (l + 1) * pl, g, x0, y0, tid);
+      rt_load(sz[(l + 1) & 1], A.zeta + (l + 1) * pl, g, x0, y0, tid);
+      if (A.use_tmp) rt_load(st[(l + 1) & 1], A.tmp + (l + 1) * pl, g, x0, y0, tid);
+    }
+    __syncthreads();
+    if (active) {
+      const TileAcc po{sp[l & 1] + tc}, po2{sp[(l + 1) & 1] + tc}, qo{sz[l & 1] + tc};
+      const double *t1s = st[l & 1] + tc;
+      const double sl = (l < NL - 1) ? A.s[l * pl + c] : 0.; /* A.s[l*pl + c]; sm = A.s[(l-1)*pl + c] */
+      double dq = 0.;
+      ju = -jd;
+      /* --- advection_pv */
+      if (l < NL - 1) jd = jac_acc(po, po2, g);
+      double adv;
+      const double be = div_by(A.beta * (po(-1, 0) - po(1, 0)), g.D2x, g.rD2x);
+      adv = jac_acc(po, qo, g);
+      adv = adv + be;
+      if (l == 0)
+        adv = adv + sl * jd * A.idh1[0];
+      else if (l < NL - 1)
+        adv = adv + sm * ju * A.idh0[l] + sl * jd * A.idh1[l];
+      else
+        adv = adv + sm * ju * A.idh0[l];
+      dq += adv;
+      /* --- dissip */
+      const double zc = qo(0, 0);
+      if (A.use_tmp) {
+        const double tcv = t1s[0];
+        const double zp = (l < NL - 1) ? sz[(l + 1) & 1][tc] : 0., tp = (l < NL - 1) ? st[(l + 1) & 1][tc] : 0.;
+        if (l == 0) {
+          dq = 1. * dq + A.iRe * sl * (zp - zc) * A.idh1[0];
+        } else if (l < NL - 1) {
+          dq = 1. * dq + A.iRe * (sm * (zm - zc) * A.idh0[l] + sl * (zp - zc) * A.idh1[l]);
+        } else {
+          dq = 1. * dq + A.iRe * sm * (zm - zc) * A.idh0[l];
+        }
+        dq += tcv * A.iRe;
+        if (l == 0) {
+          dq = 1. * dq + A.iRe4 * sl * (tp - tcv) * A.idh1[0];
+        } else if (l < NL - 1) {
+          dq = 1. * dq + A.iRe4 * (sm * (tm - tcv) * A.idh0[l] + sl * (tp - tcv) * A.idh1[l]);
+        } else {
+          dq = 1. * dq + A.iRe4 * sm * (tm - tcv) * A.idh0[l];
+        }
+        dq = 1. * dq + div_by(A.iRe4 * (t1s[1] + t1s[-1] + t1s[RT_P] + t1s[-RT_P] - 4 * tcv), g.D2, g.rD2);
+        tm = tcv;
+      }
+      zm = zc; sm = sl;
+      /* --- ekman_friction */
+      if (l == 0) dq -= A.ceks * zc;
+      if (l == NL - 1) dq -= A.cekb * zc;
+      /* --- surface_forcing */
+      if (l == 0) dq -= A.wind[y];
+      /* --- qforcing */
+      if (A.qforc) dq += A.qforc[l * pl + c];
+      if (A.dq) A.dq[l * pl + c] = dq;
+      /* --- advance_qg */
+      if (A.q_out) A.q_out[l * pl + c] = A.q_in[l * pl + c] + dq * A.dt;
+    }
+    __syncthreads();
+  }
+}
+
 /* ------------------------------------------------------------------ energy diagnostics, msqg/qg_energy.h
  * energy_tend (:228-242) in one pass: advection_de (:28-154, default build: _LS_RV, no ENERGY_CONSERV),
  * dissip_de (:157-187), ekman_friction_de (:189-204) and the running mean po_mft, every term multiplied by
