@@ -11,11 +11,11 @@ cap() { # name regex skip count
   rm -f /tmp/$1.ncu-rep
   tail -1 $out/$1.log
 }
-cap lap      '^k_lap$'      0 2
-cap rhs      '^k_rhs'       0 1
+cap lap      '^k_lap2$'     0 1
+cap rhs      '^k_rhs_t'     0 1
 cap residual '^k_residual$' 0 1
 cap correct  '^k_correct$'  0 1
 cap restrict '^k_restrict$' 0 1
-cap prolong  '^k_prolong$'  10 1
+cap prolong  '^k_prolong4$' 10 1
 cap relax    '^k_relax_ws'  11 1
 du -sh $out
