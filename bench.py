@@ -123,6 +123,10 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    # torchrun pins OMP_NUM_THREADS=1 for its workers when the variable is unset; the reference arm runs on rank 0 alone
+    # and is meant to use every host core, so that default is undone here (an explicit user setting > 1 is kept)
+    if os.environ.get("OMP_NUM_THREADS", "1") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(cores)
     Ns = 2048 if cores >= 32 else 1024
     val, ms, threads, _ = cpu_oracle_run(Ns, args.nl, args.steps, args.warmup)
     sample = ("%d^2 x nl=%d grid with the parameters of the %d^2 workload (metric is per cell-layer); "

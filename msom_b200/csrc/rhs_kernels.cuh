@@ -331,23 +331,27 @@ __device__ __forceinline__ double jac_acc(const PA PO, const QA QO, const Geom &
          + PO(-1, 0) * (QO(-1, 1) - QO(-1, -1))),
         G.D12, G.rD12);
 }
+/* asynchronous tile fill (LDGSTS): tile[ry*RT_P + rx] = src(y0 - 1 + ry, x0 - 1 + rx); the consumer waits with
+ * cp.async.wait_group + __syncthreads, so no thread stalls on its own loads */
 __device__ __forceinline__ void rt_load(double *__restrict__ tile, const double *__restrict__ src, const Geom &g, int x0, int y0, int tid) {
-  /* tile[(ry)*RT_P + rx] = src(y0 - 1 + ry, x0 - 1 + rx), rows of the padded plane are contiguous */
   constexpr int NE = (RT_Y + 2) * RT_P, NT = RT_X * RT_Y;
 #pragma unroll
   for (int k = 0; k < (NE + NT - 1) / NT; k++) {
     const int e = tid + k * NT;
     const int ry = e / RT_P, rx = e - ry * RT_P;
     const int gx = x0 - 1 + rx, gy = y0 - 1 + ry;
-    if (e < NE && gx <= g.nx && gy <= g.ny) tile[e] = src[GIDX(g.pitch, gy, gx)];
+    if (e < NE && gx <= g.nx && gy <= g.ny)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(tile + e)), "l"(src + GIDX(g.pitch, gy, gx)) : "memory");
   }
 }
 template <int NL>
 __global__ void __launch_bounds__(RT_X * RT_Y)
 k_rhs_t(RhsArgs A) {
-  /* tiles of layer l and l+1 (double-buffered): the vertical neighbours zeta[l+-1], tmp[l+-1] of the stretching terms
-     come from the tile staged one layer ahead and from a register of the layer before, so every plane is read once */
-  __shared__ double sp[2][(RT_Y + 2) * RT_P], sz[2][(RT_Y + 2) * RT_P], st[2][(RT_Y + 2) * RT_P];
+  /* three tile sets in flight: layer l and l+1 are read while layer l+2 lands.  The vertical neighbours zeta[l+-1],
+     tmp[l+-1] of the stretching terms come from the tile staged ahead and from a register of the layer before, so
+     every plane is read once */
+  constexpr int TS = (RT_Y + 2) * RT_P;
+  __shared__ double sp[3][TS], sz[3][TS], st[3][TS];
   const Geom g = A.g;
   const int x0 = blockIdx.x * RT_X, y0 = blockIdx.y * RT_Y;
   const int tid = threadIdx.y * RT_X + threadIdx.x;
@@ -356,23 +360,30 @@ k_rhs_t(RhsArgs A) {
   const size_t c = GIDX(g.pitch, active ? y : 0, active ? x : 0);
   const size_t pl = g.plane;
   const int tc = (threadIdx.y + 1) * RT_P + threadIdx.x + 1;
-  rt_load(sp[0], A.psi, g, x0, y0, tid);
-  rt_load(sz[0], A.zeta, g, x0, y0, tid);
-  if (A.use_tmp) rt_load(st[0], A.tmp, g, x0, y0, tid);
+  auto stage = [&](int l) {
+    if (l < NL) {
+      rt_load(sp[l % 3], A.psi + l * pl, g, x0, y0, tid);
+      rt_load(sz[l % 3], A.zeta + l * pl, g, x0, y0, tid);
+      if (A.use_tmp) rt_load(st[l % 3], A.tmp + l * pl, g, x0, y0, tid);
+    }
+    cp_async_commit();
+  };
+  stage(0);
+  stage(1);
   double jd = 0., ju;
   double zm = 0., tm = 0., sm = 0.; /* zeta, tmp, stretching of layer l-1 at this cell */
+  double sl = (NL > 1) ? A.s[c] : 0., qi = (A.q_out && active) ? A.q_in[c] : 0.; /* stretching / stage input of layer l */
 #pragma unroll
   for (int l = 0; l < NL; l++) {
-    if (l < NL - 1) {
-      rt_load(sp[(l + 1) & 1], A.psi + (l + 1) * pl, g, x0, y0, tid);
-      rt_load(sz[(l + 1) & 1], A.zeta + (l + 1) * pl, g, x0, y0, tid);
-      if (A.use_tmp) rt_load(st[(l + 1) & 1], A.tmp + (l + 1) * pl, g, x0, y0, tid);
-    }
-    __syncthreads();
+    cp_async_wait<0>(); /* layers <= l+1 have landed (layer l+1 was issued one layer ago) */
+    __syncthreads();    /* ... for every thread, and everybody is done with the buffer layer l+2 overwrites */
+    stage(l + 2);
     if (active) {
-      const TileAcc po{sp[l & 1] + tc}, po2{sp[(l + 1) & 1] + tc}, qo{sz[l & 1] + tc};
-      const double *t1s = st[l & 1] + tc;
-      const double sl = (l < NL - 1) ? A.s[l * pl + c] : 0.; /* A.s[l*pl + c]; sm = A.s[(l-1)*pl + c] */
+      const TileAcc po{sp[l % 3] + tc}, po2{sp[(l + 1) % 3] + tc}, qo{sz[l % 3] + tc};
+      const double *t1s = st[l % 3] + tc;
+      /* operands of the next layer, requested before this layer's arithmetic */
+      const double sn = (l + 1 < NL - 1) ? A.s[(l + 1) * pl + c] : 0.;
+      const double qn = (A.q_out && l + 1 < NL) ? A.q_in[(l + 1) * pl + c] : 0.;
       double dq = 0.;
       ju = -jd;
       /* --- advection_pv */
@@ -392,7 +403,7 @@ k_rhs_t(RhsArgs A) {
       const double zc = qo(0, 0);
       if (A.use_tmp) {
         const double tcv = t1s[0];
-        const double zp = (l < NL - 1) ? sz[(l + 1) & 1][tc] : 0., tp = (l < NL - 1) ? st[(l + 1) & 1][tc] : 0.;
+        const double zp = (l < NL - 1) ? sz[(l + 1) % 3][tc] : 0., tp = (l < NL - 1) ? st[(l + 1) % 3][tc] : 0.;
         if (l == 0) {
           dq = 1. * dq + A.iRe * sl * (zp - zc) * A.idh1[0];
         } else if (l < NL - 1) {
@@ -421,10 +432,11 @@ k_rhs_t(RhsArgs A) {
       if (A.qforc) dq += A.qforc[l * pl + c];
       if (A.dq) A.dq[l * pl + c] = dq;
       /* --- advance_qg */
-      if (A.q_out) A.q_out[l * pl + c] = A.q_in[l * pl + c] + dq * A.dt;
+      if (A.q_out) A.q_out[l * pl + c] = qi + dq * A.dt;
+      sl = sn; qi = qn;
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
 /* ------------------------------------------------------------------ energy diagnostics, msqg/qg_energy.h
