@@ -114,6 +114,20 @@ __global__ void k_ghosts(double *__restrict__ a, int nf, Geom g, double sg) {
  * face_gradient_x(a,i) = (a[i]-a[i-1])/Delta [BASILISK].  max|res| by warp
  * shuffles + one atomic per block.  res ghosts are never read (relax reads the
  * centre, restriction the interior) so they are not written. */
+/* dirichlet / symmetry ghosts of a boundary cell (value v, sign sg), corners keep +v (layer.h:17-21 through [BASILISK]) */
+__device__ __forceinline__ void write_ghosts_d(double *__restrict__ p, const Geom &g, int x, int y, double v, double sg) {
+  const int nx = g.nx, ny = g.ny;
+  const bool l = x == 0, r = x == nx - 1, bo = y == 0, t = y == ny - 1;
+  if (l) p[GIDX(g.pitch, y, -1)] = sg * v;
+  if (r) p[GIDX(g.pitch, y, nx)] = sg * v;
+  if (bo) p[GIDX(g.pitch, -1, x)] = sg * v;
+  if (t) p[GIDX(g.pitch, ny, x)] = sg * v;
+  if (l && bo) p[GIDX(g.pitch, -1, -1)] = v;
+  if (l && t) p[GIDX(g.pitch, ny, -1)] = v;
+  if (r && bo) p[GIDX(g.pitch, -1, nx)] = v;
+  if (r && t) p[GIDX(g.pitch, ny, nx)] = v;
+}
+
 struct LayerMetrics {
   double idh0[MSQG_NLMAX], idh1[MSQG_NLMAX];
 };
@@ -149,6 +163,91 @@ k_residual(const double *__restrict__ a, const double *__restrict__ b, double *_
       res[l * g.plane + c] = r;
       const double f = fabs(r);
       if (f > m) m = f;
+    }
+  }
+  block_max_to(maxres, m);
+}
+
+/* mg_cycle's tail fused with the residual that always follows it in mg_solve (mspg/elliptic.h:92-98,181-205) and with
+ * the first restriction of the next cycle:
+ *     a' = a + da ; boundary(a')          (k_correct)           -> a_new, OUT of place (neighbours still read a, da)
+ *     res = b - (laplacian + stretching)(a') ; max|res|         (k_residual, same expressions)
+ *     res on level D-1 = average of the four children           (k_restrict, same summation order)
+ * The residual stencil recomputes a' of the four neighbours from a and da (same single addition, same bits); across a
+ * physical side the neighbour is the dirichlet ghost -(a' of this cell), which is what k_correct stores.  Saves one
+ * read of a and one read of res per cycle (7.25 -> 5.25 doubles per cell-layer for the three operators).
+ * CORR = false: plain residual (first residual of a solve) that also leaves the restricted residual.
+ * Block = (64, 4) fine cells = (32, 2) coarse cells; undecomposed levels only (g.bc == 0). */
+#define CR_BX 64
+#define CR_BY 4
+template <int NL, bool CORR>
+__global__ void __launch_bounds__(CR_BX * CR_BY)
+k_corr_res(const double *__restrict__ a, const double *__restrict__ da, double *__restrict__ a_new,
+           const double *__restrict__ b, double *__restrict__ res, double *__restrict__ res_c,
+           const double *__restrict__ s, Geom g, Geom gc, LayerMetrics M, double *__restrict__ maxres) {
+  __shared__ double sr[NL][CR_BY][CR_BX];
+  const int x = blockIdx.x * CR_BX + threadIdx.x;
+  const int y = blockIdx.y * CR_BY + threadIdx.y;
+  const bool in = x < g.nx && y < g.ny;
+  double m = 0.;
+  if (in) {
+    const size_t c = GIDX(g.pitch, y, x);
+    const int P = g.pitch;
+    const double D = g.Delta, rD = g.rD;
+    const bool bl = x == 0, br = x == g.nx - 1, bb = y == 0, bt = y == g.ny - 1;
+    double ac[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const size_t cl = l * g.plane + c;
+      ac[l] = CORR ? a[cl] + da[cl] : a[cl];
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const double *al = a + l * g.plane;
+      double aw, ae, as, an;
+      if (CORR) {
+        const double *dl = da + l * g.plane;
+        const double gh = -1. * ac[l];
+        aw = bl ? gh : al[c - 1] + dl[c - 1];
+        ae = br ? gh : al[c + 1] + dl[c + 1];
+        as = bb ? gh : al[c - P] + dl[c - P];
+        an = bt ? gh : al[c + P] + dl[c + P];
+        double *o = a_new + l * g.plane;
+        o[c] = ac[l];
+        if (bl || br || bb || bt) write_ghosts_d(o, g, x, y, ac[l], -1.);
+      } else {
+        aw = al[c - 1]; ae = al[c + 1]; as = al[c - P]; an = al[c + P];
+      }
+      double r;
+      if (NL == 1)
+        r = b[c];
+      else if (l == 0)
+        r = b[c] + s[c] * (ac[0] - ac[1]) * M.idh1[0];
+      else if (l < NL - 1)
+        r = b[l * g.plane + c] + s[(l - 1) * g.plane + c] * (ac[l] - ac[l - 1]) * M.idh0[l] -
+            s[l * g.plane + c] * (ac[l + 1] - ac[l]) * M.idh1[l];
+      else
+        r = b[l * g.plane + c] + s[(l - 1) * g.plane + c] * (ac[l] - ac[l - 1]) * M.idh0[l];
+      r += div_by(div_by(ac[l] - aw, D, rD) - div_by(ae - ac[l], D, rD), D, rD);
+      r += div_by(div_by(ac[l] - as, D, rD) - div_by(an - ac[l], D, rD), D, rD);
+      res[l * g.plane + c] = r;
+      sr[l][threadIdx.y][threadIdx.x] = r;
+      const double f = fabs(r);
+      if (f > m) m = f;
+    }
+  }
+  __syncthreads();
+  if (res_c && in && !(threadIdx.x & 1) && !(threadIdx.y & 1)) {
+    /* restriction_average: children in the order (0,0), (0,1) [y+1], (1,0) [x+1], (1,1), then /4 (k_restrict) */
+    const size_t cc = GIDX(gc.pitch, y >> 1, x >> 1);
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      double sum = 0.;
+      sum += sr[l][threadIdx.y][threadIdx.x];
+      sum += sr[l][threadIdx.y + 1][threadIdx.x];
+      sum += sr[l][threadIdx.y][threadIdx.x + 1];
+      sum += sr[l][threadIdx.y + 1][threadIdx.x + 1];
+      res_c[l * gc.plane + cc] = sum / 4;
     }
   }
   block_max_to(maxres, m);

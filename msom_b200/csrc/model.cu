@@ -81,6 +81,7 @@ struct msqg_model {
   /* uniform-stretching tables: s per level/layer and Thomas coefficients */
   double sbcc;                 /* partial slip coefficient of comp_del2 (qg.h:185-198), 0 = free slip */
   bool s_uniform;
+  List a_alt;                  /* second buffer of the fused out-of-place correction + residual (k_corr_res) */
   bool s_rowuniform;           /* stretching depends on y only (varRo > 0): per-row relax coefficients */
   double *rowcoef[MSQG_MAXLEV + 1]; /* device tables [ny][6][nl] per level, or NULL */
   std::vector<double> s_lev;   /* [(depth+1)][nl] */
@@ -477,7 +478,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   List *all[] = {&m->psi, &m->q, &m->qpred, &m->dq, &m->zeta, &m->tmp, &m->psipg, &m->zetap, &m->qforc, &m->fr,
-                 &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->sstoch, &m->nstoch, &m->da, &m->res,
+                 &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->a_alt, &m->sstoch, &m->nstoch, &m->da, &m->res,
                  &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l,
                  &m->de_bf, &m->de_vd, &m->de_j1, &m->de_j2, &m->de_j3, &m->de_ft, &m->po_mft,
                  &m->ptr, &m->ptr_pred, &m->dptr, &m->ptr_relax, &m->qof, &m->siglev, &m->wvs, &m->wvw, &m->tmp2};
@@ -823,6 +824,8 @@ struct MgProblem {
   int mode;          /* -1 layer-coupled, else mode index */
   double *a;         /* finest-level unknown, nf planes, ghosts maintained */
   const double *b;   /* finest-level rhs */
+  double **owner = nullptr; /* where the caller keeps `a` (a List slot): lets mg_solve leave the result in the other
+                               buffer of its out-of-place correction instead of copying it back */
 };
 
 static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
@@ -846,12 +849,47 @@ static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
   return MSQG_OK;
 }
 
-/* mg_cycle, mspg/elliptic.h:43-99 with minlevel = 1 (poisson_layer.h:297) */
-static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
+/* experimental fusions of correction + residual + first restriction (k_corr_res), layer-coupled solves on an
+ * undecomposed grid only */
+static int mg_fused(msqg_model *m, const MgProblem &P) {
+  /* 0: k_residual, k_restrict, k_correct (default).  Two fusions of the cycle's tail are kept behind MSQG_MG for A/B
+     measurements; both are bit-identical and both measured SLOWER on B200 at 4096^2 x 4 (ms per step, residual +
+     restrict + correct): split 6.27; MSQG_MG=rr (residual + first restriction in one kernel) 6.47; MSQG_MG=fused
+     (correction too, out of place) 8.03 -- the shared-memory hand-off and the neighbour gathers of a and da cost more
+     than the one or two plane reads they save, the split kernels already stream at 75-100 % of the HBM peak. */
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("MSQG_MG"); v = (e && !strcmp(e, "rr")) ? 1 : (e && !strcmp(e, "fused")) ? 2 : 0; }
+  const Geom &g = m->g[m->depth];
+  return (P.mode < 0 && g.bc == 0 && m->depth >= 1 && !(g.nx & 1) && !(g.ny & 1)) ? v : 0;
+}
+/* residual of P.a (da == NULL) or of P.a + da written to a_new; both leave the residual on levels D and D-1 */
+static int mg_corr_residual(msqg_model *m, const MgProblem &P, const double *da, double *a_new, double *maxres) {
+  const int D = m->depth;
+  const Geom &g = m->g[D];
+  CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), m->stream));
+  dim3 b(CR_BX, CR_BY);
+  double *res_c = (D - 1 >= 1) ? m->res.lev[D - 1] : nullptr;
+  const Geom &gc = m->g[D >= 1 ? D - 1 : 0];
+  { ProfScope ps(m, PROF_RESIDUAL, 0);
+    LayerMetrics M = metrics_of(m);
+    if (da) { NL_SWITCH(m->nl, k_corr_res<NL, true><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(P.a, da, a_new, P.b, m->res.lev[D], res_c, m->str.lev[D], g, gc, M, m->d_scal)); }
+    else { NL_SWITCH(m->nl, k_corr_res<NL, false><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(P.a, nullptr, nullptr, P.b, m->res.lev[D], res_c, m->str.lev[D], g, gc, M, m->d_scal)); }
+  }
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(m->h_scal, m->d_scal, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  *maxres = m->h_scal[0];
+  return MSQG_OK;
+}
+
+/* mg_cycle, mspg/elliptic.h:43-99 with minlevel = 1 (poisson_layer.h:297).  fused: the residual kernel has already
+ * restricted res to level D-1 and the correction a += da is left to the next residual (mg_corr_residual). */
+static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax, int fused = 0) {
   const int D = m->depth;
   dim3 b(32, 8);
   /* restriction(res): levels D-1..1 (level 0 is never read with minlevel = 1) */
-  for (int l = D - 1; l >= 1; l--) {
+  for (int l = fused ? D - 2 : D - 1; l >= 1; l--) {
     ProfScope ps(m, PROF_RESTRICT, l);
     k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, P.nf), b, 0, m->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
     m->launches++;
@@ -878,6 +916,7 @@ static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax) {
     }
     if (rc) return rc;
   }
+  if (fused == 2) return MSQG_OK;
   const Geom &g = m->g[D];
   { ProfScope ps(m, PROF_CORRECT, 0);
   k_correct<<<grid2(g.nx, g.ny, b, P.nf), b, 0, m->stream>>>(P.a, m->da.lev[D], g); }
@@ -892,7 +931,47 @@ static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mg
   memset(&s, 0, sizeof(s));
   s.nrelax = 4;
   double resb;
-  int rc = mg_residual(m, P, &resb);
+  int rc;
+  const int fmode = mg_fused(m, P);
+  if (fmode == 1) { /* residual + first restriction in one kernel */
+    if ((rc = mg_corr_residual(m, P, nullptr, nullptr, &resb))) return rc;
+    s.resb = s.resa = resb;
+    for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > tolerance); s.i++) {
+      if ((rc = mg_cycle(m, P, s.nrelax, 1))) return rc;
+      if ((rc = mg_corr_residual(m, P, nullptr, nullptr, &s.resa))) return rc;
+      if (s.resa > tolerance) {
+        if (resb / s.resa < 1.2 && s.nrelax < 100) s.nrelax++;
+        else if (resb / s.resa > 10 && s.nrelax > 2) s.nrelax--;
+      }
+      resb = s.resa;
+    }
+  } else if (fmode == 2) {
+    /* same operators, same order, same bits; the iterate ping-pongs between P.a and a_alt */
+    const int D = m->depth;
+    if (!m->a_alt.lev[D] || m->a_alt.nf < P.nf) {
+      free_list(m->a_alt);
+      if ((rc = alloc_list(m, m->a_alt, P.nf, -1., D, D))) return rc;
+    }
+    MgProblem Q = P;
+    double *other = m->a_alt.lev[D];
+    if ((rc = mg_corr_residual(m, Q, nullptr, nullptr, &resb))) return rc;
+    s.resb = s.resa = resb;
+    for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > tolerance); s.i++) {
+      if ((rc = mg_cycle(m, Q, s.nrelax, 2))) return rc;
+      if ((rc = mg_corr_residual(m, Q, m->da.lev[D], other, &s.resa))) return rc;
+      std::swap(Q.a, other);
+      if (s.resa > tolerance) {
+        if (resb / s.resa < 1.2 && s.nrelax < 100) s.nrelax++;
+        else if (resb / s.resa > 10 && s.nrelax > 2) s.nrelax--;
+      }
+      resb = s.resa;
+    }
+    if (Q.a != P.a) { /* the result sits in the other buffer: hand it to the owner, or copy it back */
+      if (P.owner && *P.owner == P.a) { *P.owner = Q.a; m->a_alt.lev[D] = P.a; }
+      else CK(cudaMemcpyAsync(P.a, Q.a, (size_t)P.nf * m->g[D].plane * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+    }
+  } else {
+  rc = mg_residual(m, P, &resb);
   if (rc) return rc;
   s.resb = s.resa = resb;
   for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > tolerance); s.i++) {
@@ -903,6 +982,7 @@ static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mg
       else if (resb / s.resa > 10 && s.nrelax > 2) s.nrelax--;
     }
     resb = s.resa;
+  }
   }
   if ((rc = check_relax_err(m))) return rc;
   m->total_cycles += s.i;
@@ -918,6 +998,7 @@ static int invertq_list(msqg_model *m, List &ql) {
   int rc;
   if (!m->p.mode_pv_invert) {
     MgProblem P{m->nl, -1, m->psi.lev[D], ql.lev[D]};
+    P.owner = &m->psi.lev[D];
     if ((rc = mg_solve(m, P, 1e-3, &m->mgpsi))) return rc;
   } else {
     if (!m->modes_uniform) FAIL(MSQG_ERR_ARG, "horizontally varying vertical modes are not supported yet");

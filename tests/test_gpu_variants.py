@@ -3,6 +3,7 @@ MODE_PV_INVERT 1 (modal inversion through eigmode.h, BASELINE config 3) and
 -D_STOCHASTIC=1 (qg_stochastic.h, BASELINE config 5); plus size-independent
 properties at the full BASELINE shapes where the CPU oracle is too slow."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -11,6 +12,7 @@ from common import base_kw, make_pair, rel_l2, synth_psi
 
 pytestmark = pytest.mark.gpu
 libc = C.CDLL(None)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("N,nl,nsteps", [(64, 2, 3), (128, 3, 5), (64, 10, 3)])
@@ -332,3 +334,27 @@ def test_wavelet_filter(gpu, N, nl, afilt, modal):
     for _ in range(2):
         assert mg.step() == mo.step()
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+
+
+@pytest.mark.parametrize("mode", ["rr", "fused"])
+def test_fused_cycle_tail_variants(gpu, mode):
+    """MSQG_MG=rr / fused: the experimental k_corr_res fusions of correction + residual + first restriction (read once
+    per process, hence the subprocess) give the same bits, cycle counts and dt as the oracle."""
+    import subprocess, sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from common import make_pair\n"
+        "from oracle import oracle as O\n"
+        "from msom_b200 import capi as G\n"
+        "for N, nl in ((128, 3), (64, 4), (32, 2)):\n"
+        "    mo, mg, _ = make_pair(N, nl)\n"
+        "    mo.set_const(); mg.set_const()\n"
+        "    for _ in range(3):\n"
+        "        assert mg.step() == mo.step()\n"
+        "    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))\n"
+        "    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)\n"
+        "print('ok')\n") % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, MSQG_MG=mode)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
