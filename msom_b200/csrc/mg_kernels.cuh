@@ -913,7 +913,8 @@ struct WsCfg {
   static constexpr size_t smem_per_worker = (size_t)DOUBLES * sizeof(double);
   static constexpr int EPL_D = (NL * S + 31) / 32, EPL_R = (NL * RC + 31) / 32;
   static constexpr int Q = 32 / K; /* mailbox rows polled per sweep per helper iteration */
-  enum { C_DONE = 0, LIM = 8 };    /* LIM + k: last row jn whose inputs are complete for sweep k */
+  enum { C_DONE = 0, C_PUSH = 1, C_CONS = 2, LIM = 8 }; /* LIM + k: last row jn whose inputs are complete for sweep k;
+     C_PUSH / C_CONS (cluster hand-off): step counter pushed by the left / right neighbour CTA of the cluster */
 };
 #define WS_INF 0x3fffffff
 
@@ -948,6 +949,23 @@ __device__ __forceinline__ void sts2_if(bool p, unsigned a, double x, double y) 
   asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %0, 0;\n @q st.volatile.shared.v2.f64 [%1], {%2, %3};\n}\n"
                ::"r"((int)p), "r"(a), "d"(x), "d"(y) : "memory");
 }
+/* thread-block cluster helpers (hand-off between the CTAs of a cluster through distributed shared memory) */
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned mapa_u32(unsigned a, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster2_if(bool p, unsigned a, double x, double y) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %0, 0;\n @q st.shared::cluster.v2.f64 [%1], {%2, %3};\n}\n"
+               ::"r"((int)p), "r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void st_cluster_cnt_if(bool p, unsigned a, int v) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %0, 0;\n @q st.shared::cluster.s32 [%1], %2;\n}\n" ::"r"((int)p), "r"(a), "r"(v) : "memory");
+}
 /* RN(x/d) from any estimate q of x/d that is good to a few ulps; r = RN(1/d) */
 __device__ __forceinline__ double div_fix(double x, double q, double d, double r) {
   double e = __fma_rn(-d, q, x);
@@ -956,7 +974,7 @@ __device__ __forceinline__ double div_fix(double x, double q, double d, double r
   return __fma_rn(e, r, q);
 }
 
-template <int NL, int K, int WPC, bool TILE, bool RCOEF = false>
+template <int NL, int K, int WPC, bool TILE, bool RCOEF = false, int CS = 1>
 __global__ void __launch_bounds__(64 * WPC)
 k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   using Cfg = WsCfg<NL, K>;
@@ -981,9 +999,18 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   volatile int *cnt = (volatile int *)(XR + K * XRS);
   const int nsw = A.nsweeps;
   const int kf = nsw - 1;
-  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE) ? 0 : -1000;
+  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE || lane == Cfg::C_CONS) ? 0 : -1000;
   __syncthreads();
-  if (w >= nworkers) return;
+  /* CS > 1: the CTAs of a thread-block cluster hand the boundary column over through distributed shared memory
+     instead of the global mailbox: the last strip of a CTA PUSHES its results (and its step counter) into slot 0 of
+     the sweep rings of the first strip of the next CTA, which reads them locally like mailbox deposits; the consumer
+     pushes its own step counter back for ring reuse.  All remote traffic is stores; the counters trail the data by
+     one step.  Counters must be initialised cluster-wide before the first push, and no CTA may exit while a
+     neighbour can still store into it. */
+  const unsigned crank = CS > 1 ? cluster_ctarank() : 0u;
+  if (CS > 1) cluster_sync_all();
+  if (w < nworkers) {
+  const bool pin = CS > 1 && wl == 0 && crank > 0;
   const int pitch = A.g.pitch;
   const size_t plane = A.g.plane;
   const bool has_consumer = (w + 1 < nworkers);
@@ -1003,7 +1030,9 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
        step counter (and the producer checks the consumer's counter before it reuses a ring row).
        Only the first strip of a CTA goes through the global mailbox and its helper warp. */
     const bool din = (wl > 0), dout = has_consumer && (wl + 1 < WPC);
-    const bool mb_writer = wr_valid && c == W - 1 && col_ok && !dout;
+    const bool pout = CS > 1 && has_consumer && wl == WPC - 1 && crank + 1 < (unsigned)CS; /* pushes into the next CTA */
+    const bool mb_writer = wr_valid && c == W - 1 && col_ok && !dout && !pout;
+    const bool push_writer = wr_valid && c == W - 1 && col_ok && pout;
     const bool st_lane = (k < nsw);
     unsigned long long *mo = A.mailbox + ((size_t)w * K + k) * (size_t)ny * NLP; /* + j*NLP */
     /* shared-memory byte addresses */
@@ -1015,8 +1044,22 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     const unsigned a_west = din ? (unsigned)__cvta_generic_to_shared(XRL + (size_t)(k < K ? k : 0) * XRS) + 16u * W : a_ring;
     /* north of lane c = 0, sweep k > 0, is the west column of sweep k-1 */
     const unsigned a_north = (din && c == 0 && !k0) ? (unsigned)__cvta_generic_to_shared(XRL + (size_t)(k - 1) * XRS) + 16u * W : a_in;
-    const unsigned a_cdp = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE)) - (din ? (unsigned)(Cfg::VECS * 16) : 0u);
-    const unsigned a_cdc = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE)) + (dout ? (unsigned)(Cfg::VECS * 16) : 0u);
+    const unsigned a_cdp = pin ? (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_PUSH))
+                               : (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE)) - (din ? (unsigned)(Cfg::VECS * 16) : 0u);
+    const unsigned a_cdc = pout ? (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_CONS))
+                                : (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE)) + (dout ? (unsigned)(Cfg::VECS * 16) : 0u);
+    /* cluster addresses: sweep ring k (slot 0) and C_PUSH of strip 0 of the next CTA; C_CONS of the last strip of the
+       previous CTA (every CTA has the same shared-memory layout) */
+    unsigned a_push = 0u, a_push_cnt = 0u, a_rcons = 0u;
+    if (CS > 1) {
+      const unsigned xr0 = (unsigned)__cvta_generic_to_shared(smem2 + RIN * DROW + RIN * RROW);
+      const unsigned cnt0 = xr0 + 16u * (unsigned)(K * XRS);
+      if (pout) {
+        a_push = mapa_u32(xr0 + 16u * (unsigned)((k < K ? k : 0) * XRS), crank + 1);
+        a_push_cnt = mapa_u32(cnt0 + 4u * Cfg::C_PUSH, crank + 1);
+      }
+      if (pin) a_rcons = mapa_u32(cnt0 + 16u * (unsigned)((WPC - 1) * Cfg::VECS) + 4u * Cfg::C_CONS, crank - 1);
+    }
     const unsigned a_res = (unsigned)__cvta_generic_to_shared(RES) + 16u * (c - k + K - 1);
     const unsigned a_lim = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::LIM + k));
     const unsigned a_cdone = (unsigned)__cvta_generic_to_shared((const void *)(cnt + Cfg::C_DONE));
@@ -1116,11 +1159,17 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
           const double hi = (l + 1 < NL) ? out[l + 1 < NL ? l + 1 : l] : 0.;
           sts2_if(do_st, po + 16u * ((l >> 1) * S), out[l], hi);
           st_mail2_if(do_mb, mrow + l, (unsigned long long)__double_as_longlong(out[l]), (unsigned long long)__double_as_longlong(hi));
+          if (CS > 1) st_cluster2_if(row_ok && push_writer, a_push + 16u * (unsigned)((j & (R2 - 1)) * DROW + (l >> 1) * S), out[l], hi);
         }
       }
       /* results of step tau are in the rings: publish (helper: drain / ring reuse; right neighbour: hand-off) */
       __syncwarp();
       st_cnt_if(lane == 0, a_cdone, tau + 1);
+      if (CS > 1) { /* pushed counters: value v = steps < v are complete; the data of step tau left above, so the
+                       neighbour is told about step tau one step later (a full step between data and counter) */
+        st_cluster_cnt_if(lane == 0 && pout, a_push_cnt, tau);
+        st_cluster_cnt_if(lane == 0 && pin, a_rcons, tau + 1);
+      }
       /* ---- (D) step tau+1: right-hand side r = -sq(Delta)*b; r += E + W; r += N + S (reference association
          order, msqg/poisson_layer.h:88-94) and forward elimination (:137-140) */
       double cold[NL];
@@ -1169,7 +1218,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       /* ---- (E) was the speculation of (B) valid? */
       /* left neighbour (direct): its lane (k, W-1) must have stored row jn of sweep k: counter >= tau + W + 1;
          right neighbour (direct): must be done with the ring row that iteration tau+1 overwrites */
-      const int need_p = din ? min(tau + W + 1, T) : -WS_INF, need_c = dout ? tau - R2 - W + 4 : -WS_INF; /* T: the neighbour's final count */
+      const int need_p = (din || pin) ? min(tau + W + 1, T) : -WS_INF, need_c = (dout || pout) ? tau - R2 - W + 4 : -WS_INF; /* T: the neighbour's final count */
       if (!__all_sync(FULLMASK, jn <= lim && cdp >= need_p && cdc >= need_c)) {
         int spins = 0;
         while (!__all_sync(FULLMASK, jn <= ld_cnt_a(a_lim) && ld_cnt_a(a_cdp) >= need_p && ld_cnt_a(a_cdc) >= need_c)) {
@@ -1199,6 +1248,10 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     if (!lr_any) run(std::integral_constant<int, 0>{});
     else if (!__any_sync(FULLMASK, right || use_mail)) run(std::integral_constant<int, 1>{});
     else run(std::integral_constant<int, 2>{});
+    if (CS > 1 && pout) { /* the last step's data must be in place before the final count */
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      st_cluster_cnt_if(lane == 0, a_push_cnt, T);
+    }
     if (A.dbg) {
       long long t_end;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -1232,7 +1285,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     /* mailbox lanes: (kk, q) */
     const int kk = lane / Q, q = lane % Q;
     const bool rd_ghost = (w == 0) && lint && kk == 0; /* west column = stored halo column -1 of the iterate */
-    const bool rd_valid = rd_ghost || ((w > 0) && (wl == 0) && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
+    const bool rd_valid = rd_ghost || ((w > 0) && (wl == 0) && !pin && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
     const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)ny * NLP;
     const unsigned a_ringk = (unsigned)__cvta_generic_to_shared(XR + (size_t)kk * XRS);
     const unsigned a_ringf = (unsigned)__cvta_generic_to_shared(XR + (size_t)kf * XRS);
@@ -1366,4 +1419,6 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     cp_async_wait<0>();
     if (A.dbg && lane == 0) A.dbg[w * 4 + 3] = it; /* helper iterations (profiling) */
   }
+  } /* w < nworkers */
+  if (CS > 1) cluster_sync_all();
 }

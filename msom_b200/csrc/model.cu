@@ -81,6 +81,7 @@ struct msqg_model {
   /* uniform-stretching tables: s per level/layer and Thomas coefficients */
   double sbcc;                 /* partial slip coefficient of comp_del2 (qg.h:185-198), 0 = free slip */
   bool s_uniform;
+  bool relax_cs_ok = true;     /* thread-block clusters available for the relax hand-off */
   List a_alt;                  /* second buffer of the fused out-of-place correction + residual (k_corr_res) */
   bool s_rowuniform;           /* stretching depends on y only (varRo > 0): per-row relax coefficients */
   double *rowcoef[MSQG_MAXLEV + 1]; /* device tables [ny][6][nl] per level, or NULL */
@@ -697,6 +698,20 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
   return MSQG_OK;
 }
 /* warp-specialised variant (k_relax_ws): two warps per strip */
+/* thread-block cluster size of the relax kernel's DSMEM hand-off (MSQG_RELAX_CS = 1, 2 or 4; 1 = global mailbox
+ * between all CTAs, the default).  Instantiated for nl <= 4 (build time).  Measured on B200, 4096^2 x 4, relax ms per
+ * step (fine + coarse): no clusters 41.9, clusters of 2: 46.3, of 4: 45.8 -- the pushed hand-off is ~1.5 us shorter
+ * than the mailbox one, but the two predicated remote stores and two counter pushes per step lengthen EVERY step of
+ * EVERY strip by ~10 % (the step is bound by the issue slots of the compute warp), so the variant loses; kept for the
+ * next attempt (pushing from the helper warp), bit-identical results (tests/test_gpu_variants.py). */
+#ifndef RELAX_CS
+#define RELAX_CS 1
+#endif
+static int relax_cluster_size() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("MSQG_RELAX_CS"); v = e ? atoi(e) : RELAX_CS; if (v != 2 && v != 4) v = 1; }
+  return v;
+}
 template <int NL, int K, int WPC, bool RCOEF = false>
 static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   using Cfg = WsCfg<NL, K>;
@@ -722,19 +737,41 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   A.coef_cell = (RCOEF && !m->s_rowuniform) ? 1 : 0;
   if (RCOEF && (g.bc || !A.rowcoef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
   const size_t smem = Cfg::smem_per_worker * WPC;
-  const int tv = g.bc ? 1 : 0;
+  /* variant: 0 plain, 1 tile (stored halos), 2 / 3 clusters of 2 / 4 CTAs (undecomposed, uniform stretching, nl <= 4) */
+  int cs = 1;
+  if constexpr (!RCOEF && NL <= 4 && K == 4) { if (!g.bc && m->relax_cs_ok) cs = relax_cluster_size(); }
+  const int tv = g.bc ? 1 : (cs == 2 ? 2 : cs == 4 ? 3 : 0);
   auto kern = RCOEF ? k_relax_ws<NL, K, WPC, false, RCOEF> : (tv ? k_relax_ws<NL, K, WPC, true> : k_relax_ws<NL, K, WPC, false>);
-  static bool attr_set[2] = {false, false};
-  static int max_blocks[2] = {0, 0};
+  if constexpr (!RCOEF && NL <= 4 && K == 4) {
+    if (tv == 2) kern = k_relax_ws<NL, K, WPC, false, false, 2>;
+    if (tv == 3) kern = k_relax_ws<NL, K, WPC, false, false, 4>;
+  }
+  static bool attr_set[4] = {false, false, false, false};
+  static int max_blocks[4] = {0, 0, 0, 0}; /* co-resident CTAs per SM; cluster variants: co-resident CTAs on the device */
   if (!attr_set[tv]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks[tv], kern, 64 * WPC, smem));
+    if (cs == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks[tv], kern, 64 * WPC, smem));
+    else {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3(cs * m->num_sms); cfg.blockDim = dim3(64 * WPC); cfg.dynamicSmemBytes = smem; cfg.attrs = at; cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, (void *)kern, &cfg) != cudaSuccess || ncl < 1) {
+        cudaGetLastError();
+        m->relax_cs_ok = false; /* no clusters on this device / configuration: global mailbox everywhere */
+        return launch_relax_ws_w<NL, K, WPC, RCOEF>(m, da, res, lev, nsweeps, C);
+      }
+      max_blocks[tv] = ncl * cs;
+    }
     attr_set[tv] = true;
   }
-  const int max_blocks_per_sm = max_blocks[tv];
   const int grid = (nworkers + WPC - 1) / WPC;
-  int cap = max_blocks_per_sm * m->num_sms; /* co-resident CTAs (strips spin on their left neighbour) */
+  int cap = cs == 1 ? max_blocks[tv] * m->num_sms : max_blocks[tv]; /* co-resident CTAs (strips spin on their left neighbour) */
   { const char *e = getenv("MSQG_RELAX_CAP"); if (e && atoi(e) > 0 && atoi(e) < cap) cap = atoi(e); } /* tests: force panels */
+  if (cs > 1) cap = cap < cs ? cs : cap - cap % cs;
   if (cap < 1) FAIL(MSQG_ERR_ARG, "relax kernel does not fit on the device (nl=%d)", NL);
   RelaxCoef<NL> Cc = C;
   /* a level wider than cap*WPC strips is swept in column panels, left to right: the last strip of a panel
@@ -743,7 +780,18 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
     A.w_base = b0 * WPC;
     const int nb = grid - b0 < cap ? grid - b0 : cap;
     void *args[] = {(void *)&A, (void *)&Cc};
-    CK(cudaLaunchCooperativeKernel((void *)kern, dim3(nb), dim3(64 * WPC), args, smem, m->stream));
+    if (cs == 1) CK(cudaLaunchCooperativeKernel((void *)kern, dim3(nb), dim3(64 * WPC), args, smem, m->stream));
+    else { /* cooperative (co-residency) + clusters; the grid is padded to whole clusters, surplus CTAs hold no strip */
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+      cfg.gridDim = dim3((nb + cs - 1) / cs * cs); cfg.blockDim = dim3(64 * WPC); cfg.dynamicSmemBytes = smem; cfg.stream = m->stream;
+      cfg.attrs = at; cfg.numAttrs = 2;
+      CK(cudaLaunchKernelExC(&cfg, (void *)kern, args));
+    }
     m->launches++;
   }
   return MSQG_OK;

@@ -336,10 +336,12 @@ def test_wavelet_filter(gpu, N, nl, afilt, modal):
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
 
 
-@pytest.mark.parametrize("mode", ["rr", "fused"])
+@pytest.mark.parametrize("mode", ["MSQG_MG=rr", "MSQG_MG=fused", "MSQG_RELAX_CS=2", "MSQG_RELAX_CS=4"])
 def test_fused_cycle_tail_variants(gpu, mode):
-    """MSQG_MG=rr / fused: the experimental k_corr_res fusions of correction + residual + first restriction (read once
-    per process, hence the subprocess) give the same bits, cycle counts and dt as the oracle."""
+    """Measured-and-rejected variants kept behind environment switches (read once per process, hence the subprocess)
+    give the same bits, cycle counts and dt as the oracle: MSQG_MG=rr / fused (k_corr_res fusions of correction +
+    residual + first restriction) and MSQG_RELAX_CS=2 / 4 (relax hand-off between the CTAs of a thread-block cluster
+    through distributed shared memory)."""
     import subprocess, sys
     code = (
         "import sys, numpy as np\n"
@@ -347,7 +349,7 @@ def test_fused_cycle_tail_variants(gpu, mode):
         "from common import make_pair\n"
         "from oracle import oracle as O\n"
         "from msom_b200 import capi as G\n"
-        "for N, nl in ((128, 3), (64, 4), (32, 2)):\n"
+        "for N, nl in ((128, 3), (256, 4), (32, 2)):\n"
         "    mo, mg, _ = make_pair(N, nl)\n"
         "    mo.set_const(); mg.set_const()\n"
         "    for _ in range(3):\n"
@@ -355,6 +357,6 @@ def test_fused_cycle_tail_variants(gpu, mode):
         "    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))\n"
         "    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)\n"
         "print('ok')\n") % (ROOT, os.path.join(ROOT, "tests"))
-    env = dict(os.environ, MSQG_MG=mode)
+    env = dict(os.environ, **dict([mode.split("=")]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
