@@ -30,9 +30,12 @@ UNIT = "cell-layer updates/s"
 N_DEFAULT, NL_DEFAULT = 4096, 4
 
 
+MODAL = False  # --modal: MODE_PV_INVERT 1 (BASELINE config 3), set by main()
+
+
 def workload_kw(N, nl):
     from common import base_kw
-    return base_kw(N, nl)
+    return base_kw(N, nl, mode_pv_invert=1) if MODAL else base_kw(N, nl)
 
 
 def workload_psi(N, nl):
@@ -265,6 +268,8 @@ def run_ours(args):
     roof = None
     if rf["count"] > 0 and rf["ms"] > 0:
         alg_bytes_per_launch = ab["relax_sweep"] * tile_cells * (rf["aux"] / rf["count"])
+        if MODAL:  # one launch relaxes ONE vertical mode: scalar Helmholtz sweep, R da, res; W da on N^2 cells
+            alg_bytes_per_launch = 3 * 8.0 * tile_cells / nl * (rf["aux"] / rf["count"])
         ach = alg_bytes_per_launch / (rf["ms"] / rf["count"] * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of one finest-level launch at 4096^2 x 4 from the ncu --set full
         # capture in profiles/ncu_r01/relax.raw.csv (1.143 GB + 0.559 GB; independent of the number of fused sweeps)
@@ -306,8 +311,8 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "msqg double-gyre %d^2 x nl=%d, layer-coupled multigrid inversion (MODE_PV_INVERT 0), "
-                                   "tolerance 1e-3, reference-order Gauss-Seidel" % (N, nl),
+            "config": {"workload": "msqg double-gyre %d^2 x nl=%d, %s, tolerance 1e-3, reference-order Gauss-Seidel" % (
+                N, nl, "vertical-mode inversion (MODE_PV_INVERT 1)" if MODAL else "layer-coupled multigrid inversion (MODE_PV_INVERT 0)"),
                        "N": N, "nl": nl, "parallelism": parallelism,
                        "l2": "inputs larger than L2 (each layer list is %.0f MB)" % (cells * 8 / 1e6),
                        "mg_cycles_per_step": cycles / args.steps},
@@ -333,6 +338,8 @@ def main():
     ap.add_argument("--N", type=int, default=N_DEFAULT)
     ap.add_argument("--nl", type=int, default=NL_DEFAULT)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--modal", action="store_true",
+                    help="vertical-mode inversion (MODE_PV_INVERT 1, eigmode.h; BASELINE config 3) instead of the layer-coupled solver")
     ap.add_argument("--agg-n", type=int, default=0, dest="agg_n",
                     help="multi-GPU: levels with fewer than agg_n cells per side are agglomerated on rank 0 (default: N, i.e. "
                          "only the finest level is swept tile by tile -- measured fastest on B200: an agglomerated level runs "
@@ -340,6 +347,8 @@ def main():
     args = ap.parse_args()
     if args.agg_n <= 0:
         args.agg_n = args.N
+    global MODAL
+    MODAL = bool(args.modal)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
