@@ -974,8 +974,20 @@ __device__ __forceinline__ double div_fix(double x, double q, double d, double r
   return __fma_rn(e, r, q);
 }
 
+/* One CTA per SM is all the shared-memory rings allow, so say so: without the second argument ptxas budgets 128
+ * registers for a 256-thread block (spills 16 bytes in the step loop); with it the kernel takes 146, no spill, and the
+ * finest-level launch goes from 3387 to 3304 us (scripts/ubench/relax_bench.cu, same checksum).  WS_MINBLOCKS=0 restores
+ * the default budget (A/B measurements). */
+#ifndef WS_MINBLOCKS
+#define WS_MINBLOCKS 1
+#endif
+#if WS_MINBLOCKS > 0
+#define WS_LAUNCH_BOUNDS(WPC) __launch_bounds__(64 * WPC, WS_MINBLOCKS)
+#else
+#define WS_LAUNCH_BOUNDS(WPC) __launch_bounds__(64 * WPC)
+#endif
 template <int NL, int K, int WPC, bool TILE, bool RCOEF = false, int CS = 1>
-__global__ void __launch_bounds__(64 * WPC)
+__global__ void WS_LAUNCH_BOUNDS(WPC)
 k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   using Cfg = WsCfg<NL, K>;
   constexpr int W = Cfg::W, S = Cfg::S, RC = Cfg::RC, RIN = Cfg::RIN, R2 = Cfg::R2;
