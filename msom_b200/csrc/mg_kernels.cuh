@@ -913,7 +913,7 @@ struct WsCfg {
   static constexpr size_t smem_per_worker = (size_t)DOUBLES * sizeof(double);
   static constexpr int EPL_D = (NL * S + 31) / 32, EPL_R = (NL * RC + 31) / 32;
   static constexpr int Q = 32 / K; /* mailbox rows polled per sweep per helper iteration */
-  enum { C_DONE = 0, C_PUSH = 1, C_CONS = 2, LIM = 8 }; /* LIM + k: last row jn whose inputs are complete for sweep k;
+  enum { C_DONE = 0, C_PUSH = 1, C_CONS = 2, H_DONE = 3, LIM = 8, HLIM = 16 }; /* LIM + k: last row jn whose inputs are complete for sweep k;
      C_PUSH / C_CONS (cluster hand-off): step counter pushed by the left / right neighbour CTA of the cluster */
 };
 #define WS_INF 0x3fffffff
@@ -982,20 +982,25 @@ __device__ __forceinline__ double div_fix(double x, double q, double d, double r
 #define WS_MINBLOCKS 1
 #endif
 #if WS_MINBLOCKS > 0
-#define WS_LAUNCH_BOUNDS(WPC) __launch_bounds__(64 * WPC, WS_MINBLOCKS)
+#define WS_LAUNCH_BOUNDS(NT) __launch_bounds__(NT, WS_MINBLOCKS)
 #else
-#define WS_LAUNCH_BOUNDS(WPC) __launch_bounds__(64 * WPC)
+#define WS_LAUNCH_BOUNDS(NT) __launch_bounds__(NT)
 #endif
-template <int NL, int K, int WPC, bool TILE, bool RCOEF = false, int CS = 1>
-__global__ void WS_LAUNCH_BOUNDS(WPC)
+/* MW: a ninth warp per CTA (the "mail warp") takes the global mailbox of the CTA's first strip off its helper warp:
+ * it does nothing but poll, deposit into slot 0 of the sweep rings, re-arm and publish LIM (= min of the helper's
+ * progress HLIM and its own), so the hand-off between CTAs no longer waits for a helper iteration that also streams
+ * and drains rows. */
+template <int NL, int K, int WPC, bool TILE, bool RCOEF = false, int CS = 1, bool MW = false>
+__global__ void WS_LAUNCH_BOUNDS(64 * WPC + (MW ? 32 : 0))
 k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   using Cfg = WsCfg<NL, K>;
   constexpr int W = Cfg::W, S = Cfg::S, RC = Cfg::RC, RIN = Cfg::RIN, R2 = Cfg::R2;
   constexpr int NLP = Cfg::NLP, NV = Cfg::NV, DROW = Cfg::DROW, RROW = Cfg::RROW, XRS = Cfg::XRS, Q = Cfg::Q;
   extern __shared__ double2 smem2[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool helper = warp >= WPC;
-  const int wl = helper ? warp - WPC : warp; /* worker slot inside the CTA */
+  const bool mailer = MW && warp == 2 * WPC;
+  const bool helper = warp >= WPC && !mailer;
+  const int wl = mailer ? 0 : (helper ? warp - WPC : warp); /* worker slot inside the CTA */
   const int nx = A.g.nx, ny = A.g.ny; /* columns / rows of this tile */
   /* internal sides (multi-GPU tiles, single-sweep launches only): ghosts are stored halo values */
   const bool lint = TILE && (A.g.bc & 1), rint = TILE && (A.g.bc & 2), bint = TILE && (A.g.bc & 4), tint = TILE && (A.g.bc & 8);
@@ -1011,7 +1016,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   volatile int *cnt = (volatile int *)(XR + K * XRS);
   const int nsw = A.nsweeps;
   const int kf = nsw - 1;
-  if (lane < Cfg::NCNT && !helper) cnt[lane] = (lane == Cfg::C_DONE || lane == Cfg::C_CONS) ? 0 : -1000;
+  if (lane < Cfg::NCNT && !helper && !mailer) cnt[lane] = (lane == Cfg::C_DONE || lane == Cfg::C_CONS || lane == Cfg::H_DONE) ? 0 : -1000;
   __syncthreads();
   /* CS > 1: the CTAs of a thread-block cluster hand the boundary column over through distributed shared memory
      instead of the global mailbox: the last strip of a CTA PUSHES its results (and its step counter) into slot 0 of
@@ -1027,7 +1032,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
   const size_t plane = A.g.plane;
   const bool has_consumer = (w + 1 < nworkers);
 
-  if (!helper) {
+  if (!helper && !mailer) {
     /* ================================================================ compute warp */
     const int k = lane / W, c = lane % W;
     const int i = w * W + c - k;
@@ -1253,7 +1258,13 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
 #pragma unroll 1
       for (; tau < t_fast0; tau++) step(std::true_type{}, lr_tag, tau);
 #pragma unroll 1
-      for (; tau + 1 <= t_fast1; tau += 2) { step(std::false_type{}, lr_tag, tau); step(std::false_type{}, lr_tag, tau + 1); }
+#ifndef WS_UNROLL
+#define WS_UNROLL 2 /* steady-state steps per loop iteration (measured 1..4 in scripts/ubench/relax_bench.cu) */
+#endif
+      for (; tau + WS_UNROLL - 1 <= t_fast1; tau += WS_UNROLL) {
+#pragma unroll
+        for (int u = 0; u < WS_UNROLL; u++) step(std::false_type{}, lr_tag, tau + u);
+      }
 #pragma unroll 1
       for (; tau < T; tau++) step(std::true_type{}, lr_tag, tau);
     };
@@ -1269,7 +1280,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
       if (lane == 0) { A.dbg[w * 4 + 0] = t_start; A.dbg[w * 4 + 1] = t_end; A.dbg[w * 4 + 2] = n_spins; }
     }
-  } else {
+  } else if (helper) {
     /* ================================================================ helper warp */
     /* streaming: element e of a ring row <-> (layer, column) */
     const double *ld_d[Cfg::EPL_D];
@@ -1297,7 +1308,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     /* mailbox lanes: (kk, q) */
     const int kk = lane / Q, q = lane % Q;
     const bool rd_ghost = (w == 0) && lint && kk == 0; /* west column = stored halo column -1 of the iterate */
-    const bool rd_valid = rd_ghost || ((w > 0) && (wl == 0) && !pin && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
+    const bool rd_valid = !MW && (rd_ghost || ((w > 0) && (wl == 0) && !pin && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx));
     const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)ny * NLP;
     const unsigned a_ringk = (unsigned)__cvta_generic_to_shared(XR + (size_t)kk * XRS);
     const unsigned a_ringf = (unsigned)__cvta_generic_to_shared(XR + (size_t)kf * XRS);
@@ -1418,7 +1429,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
         lim = min(lim, (mail_rd >= ny) ? WS_INF : mail_rd - 1);
         if (kk == kf) lim = min(lim, (da_dr >= ny - R2) ? WS_INF : da_dr + R2 - 1);
         if (kk >= nsw) lim = WS_INF;
-        cnt[Cfg::LIM + kk] = lim;
+        cnt[(MW && wl == 0 ? Cfg::HLIM : Cfg::LIM) + kk] = lim; /* MW: the mail warp folds its own progress in */
       }
       /* ---- done? */
       const bool fin = (in_done > r_last) && (mail_rd >= ny) && (da_dr >= ny);
@@ -1429,7 +1440,68 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       } else idle = 0;
     }
     cp_async_wait<0>();
+    if (MW && wl == 0 && lane == 0) cnt[Cfg::H_DONE] = 1;
     if (A.dbg && lane == 0) A.dbg[w * 4 + 3] = it; /* helper iterations (profiling) */
+  } else {
+    /* ================================================================ mail warp (MW): first strip of the CTA */
+    const int kk = lane / Q, q = lane % Q; /* mailbox lanes: Q rows of each sweep per iteration */
+    const bool rd_ghost = (w == 0) && lint && kk == 0; /* west column = stored halo column -1 of the iterate */
+    const bool rd_valid = rd_ghost || ((w > 0) && !pin && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
+    const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)ny * NLP;
+    const unsigned a_ringk = (unsigned)__cvta_generic_to_shared(XR + (size_t)kk * XRS);
+    const unsigned gmask = (Q == 32) ? 0xffffffffu : (((1u << Q) - 1u) << (kk * Q));
+    int mail_rd = rd_valid ? 0 : ny; /* rows deposited for sweep kk */
+    int idle = 0;
+#pragma unroll 1
+    for (;;) {
+      const int cd = ld_cnt(cnt + Cfg::C_DONE);
+      const int r = mail_rd + q;
+      const bool can = rd_valid && r < ny && (cd >= r - R2 + 2 * kk + 3);
+      if (!__any_sync(FULLMASK, can)) __nanosleep(200); /* nothing to poll: leave the issue slots to the compute warps */
+      unsigned long long v[NLP];
+#pragma unroll
+      for (int l = 0; l < NLP; l++) v[l] = MAIL_EMPTY;
+      if (can && !rd_ghost) {
+        const unsigned long long *p = mb_in + (size_t)r * NLP;
+#pragma unroll
+        for (int l = 0; l < NLP; l += 2)
+          asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[l]), "=l"(v[l + 1]) : "l"(p + l));
+      }
+      if (can && rd_ghost) {
+#pragma unroll
+        for (int l = 0; l < NL; l++) v[l] = (unsigned long long)__double_as_longlong(A.da[(size_t)l * plane + GIDX(pitch, r, -1)]);
+      }
+      bool valid = can;
+#pragma unroll
+      for (int l = 0; l < NL; l++) valid = valid && (v[l] != MAIL_EMPTY);
+      const unsigned bal = (__ballot_sync(FULLMASK, valid) & gmask) >> (kk * Q);
+      const int adv = __ffs(~bal) - 1;
+      if (q < adv) {
+        const unsigned d = a_ringk + 16u * (unsigned)((r & (R2 - 1)) * DROW);
+#pragma unroll
+        for (int l = 0; l < NLP; l += 2)
+          sts2(d + 16u * ((l >> 1) * S), __longlong_as_double((long long)v[l]), __longlong_as_double((long long)v[l + 1]));
+        unsigned long long *p = (unsigned long long *)mb_in + (size_t)r * NLP;
+        if (!rd_ghost) {
+#pragma unroll
+          for (int l = 0; l < NLP; l += 2)
+            asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(p + l), "l"(MAIL_EMPTY), "l"(MAIL_EMPTY) : "memory");
+        }
+      }
+      mail_rd += adv;
+      __syncwarp();
+      const int hdone = ld_cnt(cnt + Cfg::H_DONE); /* read BEFORE the helper's limits: they are final once it is set */
+      if (q == 0 && kk < K) {
+        int lim = ld_cnt(cnt + Cfg::HLIM + kk);
+        lim = min(lim, (mail_rd >= ny) ? WS_INF : mail_rd - 1);
+        if (kk >= nsw) lim = WS_INF;
+        cnt[Cfg::LIM + kk] = lim;
+      }
+      if (hdone && __all_sync(FULLMASK, mail_rd >= ny)) break;
+      if (!__any_sync(FULLMASK, adv > 0) && !hdone) {
+        if (++idle > SPIN_LIMIT) { if (lane == 0) *A.err = 3; break; }
+      } else idle = 0;
+    }
   }
   } /* w < nworkers */
   if (CS > 1) cluster_sync_all();

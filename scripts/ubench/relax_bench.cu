@@ -47,10 +47,14 @@ int main(int argc, char **argv) {
   k_fill<<<592, 256>>>(mail, words, MAIL_EMPTY);
   RelaxArgs A;
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsw; A.mailbox = mail; A.err = err; A.dbg = dbg; A.flags = argc > 3 ? atoi(argv[3]) : 0; A.w_base = 0;
-  auto kern = k_relax_ws<NL, K, BWPC, false>;
+#ifndef BMW
+#define BMW 0
+#endif
+  constexpr int NTHR = 64 * BWPC + (BMW ? 32 : 0);
+  auto kern = k_relax_ws<NL, K, BWPC, false, false, 1, BMW != 0>;
   const size_t smem = Cfg::smem_per_worker * BWPC;
   CKC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int mb = 0; CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mb, kern, 64 * BWPC, smem));
+  int mb = 0; CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mb, kern, NTHR, smem));
   const int grid = (nworkers + BWPC - 1) / BWPC;
   printf("n=%d nsweeps=%d workers=%d WPC=%d grid=%d smem/CTA=%zu B, CTAs/SM=%d\n", n, nsw, nworkers, BWPC, grid, smem, mb);
   if (grid > mb * 148) { printf("does not fit\n"); return 1; }
@@ -61,7 +65,7 @@ int main(int argc, char **argv) {
     CKC(cudaMemcpy(da, h.data(), nd * 8, cudaMemcpyHostToDevice));
     CKC(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    CKC(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(64 * BWPC), args, smem, 0));
+    CKC(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(NTHR), args, smem, 0));
     cudaEventRecord(e1);
     CKC(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1);
@@ -89,7 +93,7 @@ int main(int argc, char **argv) {
   int bad = 0;
   for (int r = 0; r < reps; r++) {
     CKC(cudaMemcpy(da, h.data(), nd * 8, cudaMemcpyHostToDevice));
-    CKC(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(64 * BWPC), args, smem, 0));
+    CKC(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(NTHR), args, smem, 0));
     CKC(cudaDeviceSynchronize());
     std::vector<double> o2(nd);
     CKC(cudaMemcpy(o2.data(), da, nd * 8, cudaMemcpyDeviceToHost));
