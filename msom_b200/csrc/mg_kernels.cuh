@@ -1236,7 +1236,12 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       /* left neighbour (direct): its lane (k, W-1) must have stored row jn of sweep k: counter >= tau + W + 1;
          right neighbour (direct): must be done with the ring row that iteration tau+1 overwrites */
       const int need_p = (din || pin) ? min(tau + W + 1, T) : -WS_INF, need_c = (dout || pout) ? tau - R2 - W + 4 : -WS_INF; /* T: the neighbour's final count */
-      if (!__all_sync(FULLMASK, jn <= lim && cdp >= need_p && cdc >= need_c)) {
+#ifdef WS_COLD_SPIN /* mark the mis-speculation path unlikely: ptxas then lays it out of line */
+#define WS_EXPECT(x) __builtin_expect(!!(x), 0)
+#else
+#define WS_EXPECT(x) (x)
+#endif
+      if (WS_EXPECT(!__all_sync(FULLMASK, jn <= lim && cdp >= need_p && cdc >= need_c))) {
         int spins = 0;
         while (!__all_sync(FULLMASK, jn <= ld_cnt_a(a_lim) && ld_cnt_a(a_cdp) >= need_p && ld_cnt_a(a_cdc) >= need_c)) {
           if (++spins > SPIN_LIMIT) { if (lane == 0) *A.err = 1; break; }
