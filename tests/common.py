@@ -9,7 +9,8 @@ FR = {2: [0.0045], 3: [0.0023669, 0.0076173], 4: [0.0024, 0.0050, 0.0076],
 
 def base_kw(N, nl, **over):
     kw = dict(N=N, nl=nl, L0=80., Rom=0.025, Ekb=0.002, tau0=1e-4, beta=0.5, CFL=0.6, DT=5e-2, Re=0.,
-              Re4=1563. * (N / 256.) ** 4, dh=DH[nl], Fr=FR[nl], tend=500., dtout=10.)
+              Re4=1563. * (N / 256.) ** 4, dh=DH.get(nl, [1.0 / nl] * nl), Fr=FR.get(nl, list(np.linspace(0.002, 0.008, nl - 1))),
+              tend=500., dtout=10.)
     kw.update(over)
     return kw
 

@@ -80,3 +80,22 @@ def test_viscous_and_pg_terms(gpu):
         assert mg.step() == mo.step()
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
     assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+
+
+@pytest.mark.parametrize("N,nl", [(8, 2), (16, 3), (32, 4), (64, 5), (64, 7), (32, 12), (16, 12)])
+def test_edge_shapes(gpu, N, nl):
+    """Smallest grids (one partial tile in every tiled kernel, a handful of strips in the relax wavefront) and layer
+    counts up to the maximum the kernels are instantiated for (nl = 12): three steps bit-identical to the oracle,
+    equal dt and equal multigrid cycle counts."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    over = {}
+    if nl not in (2, 3, 4, 10):
+        over = dict(dh=[1.0 / nl] * nl, Fr=list(np.linspace(0.002, 0.008, nl - 1)))
+    mo, mg, _ = make_pair(N, nl, **over)
+    mo.set_const(); mg.set_const()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+    for _ in range(3):
+        assert mg.step() == mo.step()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
