@@ -336,12 +336,13 @@ def test_wavelet_filter(gpu, N, nl, afilt, modal):
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
 
 
-@pytest.mark.parametrize("mode", ["MSQG_MG=rr", "MSQG_MG=fused", "MSQG_RELAX_CS=2", "MSQG_RELAX_CS=4"])
+@pytest.mark.parametrize("mode", ["MSQG_MG=rr", "MSQG_MG=fused", "MSQG_RELAX_CS=2", "MSQG_RELAX_CS=4", "MSQG_RELAX=v3", "MSQG_RHS=gather"])
 def test_fused_cycle_tail_variants(gpu, mode):
     """Measured-and-rejected variants kept behind environment switches (read once per process, hence the subprocess)
     give the same bits, cycle counts and dt as the oracle: MSQG_MG=rr / fused (k_corr_res fusions of correction +
     residual + first restriction) and MSQG_RELAX_CS=2 / 4 (relax hand-off between the CTAs of a thread-block cluster
-    through distributed shared memory)."""
+    through distributed shared memory), MSQG_RELAX=v3 (single-warp wavefront k_relax_lex) and MSQG_RHS=gather
+    (L1-gather right-hand side k_rhs instead of the tiled k_rhs_t)."""
     import subprocess, sys
     code = (
         "import sys, numpy as np\n"
