@@ -1264,7 +1264,7 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       for (; tau < t_fast0; tau++) step(std::true_type{}, lr_tag, tau);
 #pragma unroll 1
 #ifndef WS_UNROLL
-#define WS_UNROLL 2 /* steady-state steps per loop iteration (measured 1..4 in scripts/ubench/relax_bench.cu) */
+#define WS_UNROLL 1 /* steady-state steps per loop iteration: 1 / 2 / 3 / 4 measured 3262 / 3290 / 3285 / 3299 us per finest launch */
 #endif
       for (; tau + WS_UNROLL - 1 <= t_fast1; tau += WS_UNROLL) {
 #pragma unroll
