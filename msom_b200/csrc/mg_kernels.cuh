@@ -1306,9 +1306,14 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
       ld_r[q] = A.res + (size_t)(ok_r[q] ? l : 0) * plane + GIDX(pitch, 0, ok_r[q] ? x : 0);
       st_r[q] = (unsigned)__cvta_generic_to_shared(RES) + 16u * (unsigned)((l >> 1) * RC + xs) + 8u * (l & 1);
     }
-    constexpr int PF = 48;
+#ifndef WS_PF
+#define WS_PF 48 /* rows of L2 prefetch ahead of the streamed rows */
+#endif
+    constexpr int PF = WS_PF;
 #ifndef HROWS
-#define HROWS 4 /* rows streamed in / drained per helper iteration: must outrun the compute warp */
+    /* rows streamed in / drained per helper iteration: must outrun the compute warp.  Measured at nl = 4 (finest launch,
+       us): 2: 3784, 3: 3230, 4: 3268, 5: 3256, 6: 3353 -- 3 where a row is at most as long as in the measured case */
+#define HROWS (NL <= 4 ? 3 : 4)
 #endif
     /* mailbox lanes: (kk, q) */
     const int kk = lane / Q, q = lane % Q;
