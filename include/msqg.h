@@ -122,6 +122,15 @@ int msqg_set_field(msqg_model *m, int id, const double *host);
 /* pyget_field (qg.h:1177-1189) */
 int msqg_get_field(msqg_model *m, int id, double *host);
 int msqg_set_flag_topo(msqg_model *m, int flag);  /* flag_topo, qg.h:971-977 */
+/* Ordering of the relaxation sweep inside mg_cycle.  0 (default): the reference's lexicographic in-place sweep
+ * (relax_layer, msqg/poisson_layer.h:75-149, traversal of [BASILISK] foreach_level) -- results identical to a serial
+ * reference build.  1: red-black ordering of the SAME cell update (cells with x+y even, then x+y odd), the
+ * throughput mode: the reference itself documents that its sweep result depends on traversal order, OpenMP threads and
+ * MPI decomposition (poisson_layer.h:55-65); red-black removes that dependence, so one result holds for 1..8 GPUs.
+ * The iterate differs from the lexicographic one at the level of the solver tolerance (1e-3, qg.h:159).  Also set at
+ * creation from the environment variable MSQG_SMOOTHER=rb. */
+int msqg_set_smoother(msqg_model *m, int smoother);
+int msqg_get_smoother(msqg_model *m);
 /* reset_layer_var (layer.h:37-41): zero the interior, ghost ring untouched */
 int msqg_reset_field(msqg_model *m, int id);
 /* layer thicknesses dhf (qg.h:895-896; overridden by dh_%dl.bin, qg.h:940-948) */

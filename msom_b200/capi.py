@@ -91,6 +91,8 @@ def lib():
     L.msqg_set_field.argtypes = [vp, C.c_int, dp]
     L.msqg_get_field.argtypes = [vp, C.c_int, dp]
     L.msqg_set_flag_topo.argtypes = [vp, C.c_int]
+    L.msqg_set_smoother.argtypes = [vp, C.c_int]
+    L.msqg_get_smoother.argtypes = [vp]
     L.msqg_set_keep_dq.argtypes = [vp, C.c_int]
     L.msqg_set_dissipation.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
     L.msqg_set_const.argtypes = [vp]
@@ -190,6 +192,10 @@ class Model:
         out = np.zeros((self.nfields(fid), self.N, self.N))
         check(self.L.msqg_get_field(self.h, fid, out))
         return out
+
+    def set_smoother(self, name):
+        """'lex': the reference's sweep order (default, parity path); 'rb': red-black ordering (throughput mode)"""
+        check(self.L.msqg_set_smoother(self.h, {"lex": 0, "rb": 1}[name]))
 
     def set_const(self):
         check(self.L.msqg_set_const(self.h))

@@ -13,6 +13,7 @@
 #include "../../include/msqg.h"
 #include "layout.cuh"
 #include "mg_kernels.cuh"
+#include "rb_kernels.cuh"
 #include "rhs_kernels.cuh"
 
 #include <cmath>
@@ -73,6 +74,7 @@ struct msqg_model {
   List de_bf, de_vd, de_j1, de_j2, de_j3, de_ft, po_mft; /* energy diagnostics, qg_energy.h (allocated on first use) */
   int nme_ft, energy_vars;
   List da, res; /* all levels; nf = nl */
+  List da2;     /* rb smoother: the relax pass is out of place (a CTA's output block is its neighbours' halo), da and da2 swap */
   List pm, qm, ibu /*all levels*/, cl2m, cm2l;
   double dhf[MSQG_MAXL], dhc[MSQG_MAXL], idh0[MSQG_MAXL], idh1[MSQG_MAXL];
   double iRe, iRe4, Eks, Ekb;
@@ -116,6 +118,8 @@ struct msqg_model {
   msqg_mgstats mgpsi, mgmode[MSQG_MAXL];
   long total_cycles, launches;
   int keep_dq;
+  int smoother;    /* 0: reference-order (lexicographic) Gauss-Seidel, the parity path; 1: red-black ordering (rb_kernels.cuh) */
+  int rb_reuse;    /* rb kernel: neighbours carried in registers (MSQG_RB_REUSE=0 switches it off, A/B tests) */
   /* optional per-launch timing (CUDA events on the model's stream) */
   int prof_on;
   std::vector<cudaEvent_t> prof_pool;
@@ -420,6 +424,8 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   initstate_r(1u, m->rng_state, sizeof(m->rng_state), &m->rng); /* C default: srand(1) */
   m->flag_topo = 0; m->has_qforc = 0; m->has_zp = 0; m->const_set = 0;
   m->total_cycles = 0; m->launches = 0; m->keep_dq = 0; m->prof_on = 0; m->prof_next = 0;
+  { const char *e = getenv("MSQG_SMOOTHER"); m->smoother = (e && !strcmp(e, "rb")) ? 1 : 0; }
+  { const char *e = getenv("MSQG_RB_REUSE"); m->rb_reuse = (e && atoi(e) == 0) ? 0 : 1; }
   memset(&m->mgpsi, 0, sizeof(m->mgpsi));
   memset(m->mgmode, 0, sizeof(m->mgmode));
   memset(m->umax_pg, 0, sizeof(m->umax_pg));
@@ -480,7 +486,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   List *all[] = {&m->psi, &m->q, &m->qpred, &m->dq, &m->zeta, &m->tmp, &m->psipg, &m->zetap, &m->qforc, &m->fr,
                  &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->a_alt, &m->sstoch, &m->nstoch, &m->da, &m->res,
-                 &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l,
+                 &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l, &m->da2,
                  &m->de_bf, &m->de_vd, &m->de_j1, &m->de_j2, &m->de_j3, &m->de_ft, &m->po_mft,
                  &m->ptr, &m->ptr_pred, &m->dptr, &m->ptr_relax, &m->qof, &m->siglev, &m->wvs, &m->wvw, &m->tmp2};
   for (List *L : all) free_list(*L);
@@ -523,6 +529,12 @@ extern "C" void msqg_seed_noise(msqg_model *m, unsigned seed) {
   initstate_r(seed, m->rng_state, sizeof(m->rng_state), &m->rng);
 }
 extern "C" int msqg_set_flag_topo(msqg_model *m, int flag) { m->flag_topo = flag; return MSQG_OK; }
+extern "C" int msqg_set_smoother(msqg_model *m, int smoother) {
+  if (smoother != 0 && smoother != 1) FAIL(MSQG_ERR_ARG, "smoother is 0 (reference order) or 1 (red-black)");
+  m->smoother = smoother;
+  return MSQG_OK;
+}
+extern "C" int msqg_get_smoother(msqg_model *m) { return m->smoother; }
 extern "C" int msqg_set_keep_dq(msqg_model *m, int keep) { m->keep_dq = keep; return MSQG_OK; }
 extern "C" int msqg_set_dissipation(msqg_model *m, double iRe, double iRe4, double Eks, double Ekb) {
   m->iRe = iRe; m->iRe4 = iRe4; m->Eks = Eks; m->Ekb = Ekb; /* pystep_bfn flips these, qg_bfn.h:34-44 */
@@ -829,7 +841,11 @@ static int launch_relax_w_t(msqg_model *m, double *da, const double *res, int le
 }
 
 template <int NL>
+static int launch_relax_rb(msqg_model *m, double *da, const double *res, int lev, int nrelax, const RelaxCoef<NL> &C,
+                           const int *orange, int halo);
+template <int NL>
 static int launch_relax(msqg_model *m, double *da, const double *res, int lev, int nrelax, const RelaxCoef<NL> &C) {
+  if (m->smoother == 1) return launch_relax_rb<NL>(m, da, res, lev, nrelax, C, nullptr, 0);
   int done = 0;
   while (done < nrelax) {
     int ns = nrelax - done;
@@ -842,6 +858,90 @@ static int launch_relax(msqg_model *m, double *da, const double *res, int lev, i
     else { if (ns > 8) ns = 8; rc = launch_relax_w_t<NL, 8>(m, da, res, lev, ns, C); }
     if (rc) return rc;
     done += ns;
+  }
+  return MSQG_OK;
+}
+
+
+/* ------------------------------------------------------------------ red-black relax launch (rb_kernels.cuh) */
+/* per-device launch state of one kernel instance: opt-in shared memory and co-resident CTAs per SM */
+struct KernelDevState { bool set[64] = {}; int occ[64][RB_NSMAX + 1] = {}; };
+template <int NL, bool RCOEF>
+static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, int lev, int ns, const RelaxCoef<NL> &C,
+                                const int *orange /* optional {ox_lo, ox_hi, oy_lo, oy_hi} */, int halo) {
+  using Cfg = RbCfg<NL>;
+  const Geom &g = m->g[lev];
+  const int nh = 2 * ns;
+  if (da != m->da.lev[lev]) FAIL(MSQG_ERR_ARG, "the rb relax pass works on the model's da list");
+  if (!m->da2.lev[lev]) { /* second buffer of the out-of-place pass, allocated on first use */
+    const size_t bytes = (size_t)m->nl * g.plane * sizeof(double);
+    CK(cudaMalloc(&m->da2.lev[lev], bytes));
+    CK(cudaMemsetAsync(m->da2.lev[lev], 0, bytes, m->stream));
+    m->da2.nf = m->nl;
+  }
+  RbArgs A;
+  memset(&A, 0, sizeof(A));
+  A.da = da; A.da_out = m->da2.lev[lev]; A.res = res; A.g = g; A.ns = ns;
+  A.R = 2 * nh + 1 + RB_PF;
+  A.TX = RB_WX - 2 * nh;
+  A.ox_lo = 0; A.ox_hi = g.nx; A.oy_lo = 0; A.oy_hi = g.ny;
+  if (orange) { A.ox_lo = orange[0]; A.ox_hi = orange[1]; A.oy_lo = orange[2]; A.oy_hi = orange[3]; }
+  /* cells that exist: own cells, plus `halo` cells of deep halo on the sides that have a neighbouring tile */
+  A.xlo = (g.bc & 1) ? -halo : 0; A.xhi = g.nx + ((g.bc & 2) ? halo : 0);
+  A.ylo = (g.bc & 4) ? -halo : 0; A.yhi = g.ny + ((g.bc & 8) ? halo : 0);
+  A.par0 = 0; /* tile origins are even on every distributed level (tiles keep >= 8 cells per side) */
+  A.coef = RCOEF ? m->rowcoef[lev] : nullptr;
+  A.coef_cell = (RCOEF && !m->s_rowuniform) ? 1 : 0;
+  A.reuse = m->rb_reuse;
+  if (RCOEF && (g.bc || !A.coef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
+  const size_t smem = (size_t)A.R * Cfg::row_bytes;
+  const int threads = nh * RB_NP;
+  auto kern = k_relax_rb<NL, RCOEF>;
+  static KernelDevState st;
+  const int dev = m->device & 63;
+  if (!st.set[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)((size_t)(4 * Cfg::NSMAX + 1 + RB_PF) * Cfg::row_bytes)));
+    for (int s = 1; s <= Cfg::NSMAX; s++)
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occ[dev][s], kern, 2 * s * RB_NP,
+                                                       (size_t)(4 * s + 1 + RB_PF) * Cfg::row_bytes));
+    st.set[dev] = true;
+  }
+  const int occ = st.occ[dev][ns] > 0 ? st.occ[dev][ns] : 1;
+  const int nxo = A.ox_hi - A.ox_lo, nyo = A.oy_hi - A.oy_lo;
+  const int nstrips = (nxo + A.TX - 1) / A.TX;
+  /* row chunks: about one wave of CTAs; a chunk pays 2 nh halo rows + 2 nh pipeline steps, so keep it >= 32 rows */
+  int nchunks = (m->num_sms * occ + nstrips / 2) / nstrips;
+  if (nchunks > nyo / 32) nchunks = nyo / 32;
+  if (nchunks < 1) nchunks = 1;
+  A.rpc = (nyo + nchunks - 1) / nchunks;
+  nchunks = (nyo + A.rpc - 1) / A.rpc;
+  RelaxCoef<NL> Cc = C;
+  kern<<<dim3(nstrips, nchunks), threads, smem, m->stream>>>(A, Cc);
+  m->launches++;
+  CK(cudaGetLastError());
+  std::swap(m->da.lev[lev], m->da2.lev[lev]);
+  return MSQG_OK;
+}
+/* nrelax sweeps as ceil(nrelax / NSMAX) passes of (almost) equal length; the result does not depend on the split */
+template <int NL>
+static int launch_relax_rb(msqg_model *m, double *da, const double *res, int lev, int nrelax, const RelaxCoef<NL> &C,
+                           const int *orange = nullptr, int halo = 0) {
+  constexpr int NSMAX = RbCfg<NL>::NSMAX;
+  int left = nrelax;
+  if (da != m->da.lev[lev]) FAIL(MSQG_ERR_ARG, "the rb relax pass works on the model's da list");
+  if (orange && nrelax > NSMAX) FAIL(MSQG_ERR_ARG, "a tile relax pass holds at most %d sweeps", NSMAX);
+  while (left > 0) {
+    const int passes = (left + NSMAX - 1) / NSMAX;
+    const int ns = (left + passes - 1) / passes;
+    int rc;
+    if (!m->s_uniform && NL > 1) {
+      if constexpr (NL > 1 && NL <= 6) rc = launch_relax_rb_pass<NL, true>(m, m->da.lev[lev], res, lev, ns, C, orange, halo);
+      else FAIL(MSQG_ERR_ARG, "varRo > 0 with the layer-coupled solver is built for nl <= 6 (nl = %d)", NL);
+    } else
+      rc = launch_relax_rb_pass<NL, false>(m, m->da.lev[lev], res, lev, ns, C, orange, halo);
+    if (rc) return rc;
+    left -= ns;
   }
   return MSQG_OK;
 }

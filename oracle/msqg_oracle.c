@@ -160,6 +160,7 @@ struct orc_model {
   orc_mgstats mgpsi, mgmode[ORC_MAXL];
   int total_cycles;
   int agg_n; /* MPI-emulation: levels with n < agg_n are swept as one block */
+  int smoother; /* 0: the reference's lexicographic sweep; 1: red-black ordering of the same cell update (orc_set_smoother) */
 };
 
 /* create_layer_var, layer.h:5-35 */
@@ -375,6 +376,8 @@ void orc_get_field(orc_model *m, int id, double *v) {
 }
 void orc_set_flag_topo(orc_model *m, int flag) { m->flag_topo = flag; }
 void orc_set_decomp(orc_model *m, int px, int py, int agg_n) { m->p.px = px; m->p.py = py; m->agg_n = agg_n; }
+void orc_set_smoother(orc_model *m, int smoother) { m->smoother = smoother == 1 ? 1 : 0; }
+int orc_get_smoother(orc_model *m) { return m->smoother; }
 
 /* ------------------------------------------------------------ operators */
 /* laplacian macro, qg.h:169.  Like the reference's it has NO outer parentheses:
@@ -607,7 +610,7 @@ static void bottom_topography(orc_model *m, flist *pl, flist *dql) {
  * another block are read from the pre-sweep copy `old` (the halo a rank holds
  * during a sweep); px=py=1 is the serial reference order. */
 static void relax_layer_level(int nl, int l, double L0, const double *idh0, const double *idh1,
-                              flist *al, flist *bl, flist *strl, int px, int py, flist *old) {
+                              flist *al, flist *bl, flist *strl, int px, int py, flist *old, int colour) {
   int n = LN(l);
   double Delta = L0 / n;
   int bx = n / (px > 0 ? px : 1), by = n / (py > 0 ? py : 1);
@@ -632,6 +635,7 @@ static void relax_layer_level(int nl, int l, double L0, const double *idh0, cons
       double t0[ORC_MAXL], t1[ORC_MAXL], t2[ORC_MAXL], rhs[ORC_MAXL];
       size_t c = IDX(n, i, j);
       int ll = 0;
+      if (colour >= 0 && ((i + j) & 1) != colour) continue; /* red-black: one colour per half-sweep */
       rhs[ll] = -sq(Delta) * FL(bl, ll, l)[c];
       t2[ll] = -sq(Delta) * FL(strl, ll, l)[c] * idh1[ll];
       t1[ll] = -t2[ll];
@@ -697,12 +701,16 @@ static double residual_layer_level(int nl, int l, double L0, const double *idh0,
  * (lambda field, alpha = unity); older in-tree copy mspg/elliptic.h:265-359.
  * residual uses the face-gradient form of current Basilisk, the form
  * residual_layer was derived from. */
-static void relax_scalar_level(int l, double L0, double *a, const double *b, const double *lam) {
+static void relax_scalar_level(int l, double L0, double *a, const double *b, const double *lam, int colour) {
   int n = LN(l);
   double Delta = L0 / n;
+#ifdef ORC_OMP_RELAX
+#pragma omp parallel for schedule(static)
+#endif
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) {
       size_t c = IDX(n, i, j);
+      if (colour >= 0 && ((i + j) & 1) != colour) continue;
       double nn = -sq(Delta) * b[c], d = -lam[c] * sq(Delta);
       nn += 1. * a[IDX(n, i + 1, j)] + 1. * a[IDX(n, i - 1, j)]; d += 1. + 1.;
       nn += 1. * a[IDX(n, i, j + 1)] + 1. * a[IDX(n, i, j - 1)]; d += 1. + 1.;
@@ -734,14 +742,30 @@ typedef struct {
   int mode;
 } mgctx;
 
+/* One relaxation sweep.  smoother == 0: the reference's lexicographic in-place sweep.  smoother == 1 ("rb"): the SAME
+ * cell update (poisson_layer.h:80-146 / [BASILISK] relax()) applied to the cells with (i + j) even, then boundary_level,
+ * then to the cells with (i + j) odd.  Cells of one colour only read cells of the other colour, so a half-sweep does
+ * not depend on the traversal order, the thread count or a domain decomposition -- the dependence the reference
+ * documents for its own sweep at poisson_layer.h:55-65 is removed; the iterate differs from the lexicographic one at
+ * the level of the solver tolerance. */
 static void mg_relax(mgctx *c, flist *da, flist *res, int l, flist *old) {
   orc_model *m = c->m;
+  if (m->smoother == 1) {
+    for (int colour = 0; colour < 2; colour++) {
+      if (!c->scalar_mode)
+        relax_layer_level(m->nl, l, m->L0, m->idh0, m->idh1, da, res, &m->strl, 1, 1, NULL, colour);
+      else
+        relax_scalar_level(l, m->L0, FL(da, 0, l), FL(res, 0, l), FL(&m->iBul, c->mode, l), colour);
+      if (colour == 0) boundary_level(da, l);
+    }
+    return;
+  }
   if (!c->scalar_mode) {
     int px = m->p.px, py = m->p.py;
     if (LN(l) < m->agg_n) px = py = 1;
-    relax_layer_level(m->nl, l, m->L0, m->idh0, m->idh1, da, res, &m->strl, px, py, old);
+    relax_layer_level(m->nl, l, m->L0, m->idh0, m->idh1, da, res, &m->strl, px, py, old, -1);
   } else
-    relax_scalar_level(l, m->L0, FL(da, 0, l), FL(res, 0, l), FL(&m->iBul, c->mode, l));
+    relax_scalar_level(l, m->L0, FL(da, 0, l), FL(res, 0, l), FL(&m->iBul, c->mode, l), -1);
 }
 static double mg_residual(mgctx *c, flist *a, flist *b, flist *res) {
   orc_model *m = c->m;
@@ -1705,11 +1729,20 @@ void orc_test_relax(int nl, int level, double L0, const double *dh, const double
   load_level(&A, level, a); load_level(&B, level, b);
   S.nf = nl - 1; load_level(&S, level, s); S.nf = nl;
   for (int k = 0; k < nsweeps; k++) {
-    relax_layer_level(nl, level, L0, idh0, idh1, &A, &B, &S, px, py, &O);
+    if (px < 0) { /* red-black ordering (orc_test_relax_rb) */
+      relax_layer_level(nl, level, L0, idh0, idh1, &A, &B, &S, 1, 1, NULL, 0);
+      boundary_level(&A, level);
+      relax_layer_level(nl, level, L0, idh0, idh1, &A, &B, &S, 1, 1, NULL, 1);
+    } else
+      relax_layer_level(nl, level, L0, idh0, idh1, &A, &B, &S, px, py, &O, -1);
     boundary_level(&A, level);
   }
   store_level(&A, level, a);
   fl_free(&A); fl_free(&B); fl_free(&S); fl_free(&O);
+}
+void orc_test_relax_rb(int nl, int level, double L0, const double *dh, const double *s,
+                       double *a, const double *b, int nsweeps) {
+  orc_test_relax(nl, level, L0, dh, s, a, b, nsweeps, -1, -1);
 }
 double orc_test_residual(int nl, int level, double L0, const double *dh, const double *s,
                          const double *a, const double *b, double *res) {
@@ -1747,11 +1780,23 @@ void orc_test_prolong(int nf, int level, const double *coarse, double *fine) {
   store_level(&F, level, fine);
   fl_free(&F);
 }
+static void test_relax_scalar(int level, double L0, const double *lam, double *a, const double *b, int nsweeps, int rb);
 void orc_test_relax_scalar(int level, double L0, const double *lam, double *a, const double *b, int nsweeps) {
+  test_relax_scalar(level, L0, lam, a, b, nsweeps, 0);
+}
+void orc_test_relax_scalar_rb(int level, double L0, const double *lam, double *a, const double *b, int nsweeps) {
+  test_relax_scalar(level, L0, lam, a, b, nsweeps, 1);
+}
+static void test_relax_scalar(int level, double L0, const double *lam, double *a, const double *b, int nsweeps, int rb) {
   flist A = fl_new(1, BC_DIRICHLET0, level), B = fl_new(1, BC_DIRICHLET0, level), Lm = fl_new(1, BC_NEUMANN, level);
   load_level(&A, level, a); load_level(&B, level, b); load_level(&Lm, level, lam);
   for (int k = 0; k < nsweeps; k++) {
-    relax_scalar_level(level, L0, FL(&A, 0, level), FL(&B, 0, level), FL(&Lm, 0, level));
+    if (rb) {
+      relax_scalar_level(level, L0, FL(&A, 0, level), FL(&B, 0, level), FL(&Lm, 0, level), 0);
+      boundary_level(&A, level);
+      relax_scalar_level(level, L0, FL(&A, 0, level), FL(&B, 0, level), FL(&Lm, 0, level), 1);
+    } else
+      relax_scalar_level(level, L0, FL(&A, 0, level), FL(&B, 0, level), FL(&Lm, 0, level), -1);
     boundary_level(&A, level);
   }
   store_level(&A, level, a);

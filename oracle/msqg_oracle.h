@@ -76,6 +76,13 @@ int  orc_set_const(orc_model *m);                /* set_const; -1 on the exit(0)
 void orc_set_flag_topo(orc_model *m, int flag);
 /* MPI-style block Gauss-Seidel emulation: px*py blocks on levels with n >= agg_n */
 void orc_set_decomp(orc_model *m, int px, int py, int agg_n);
+/* ordering of the relaxation sweep: 0 = the reference's lexicographic in-place sweep (default, the parity path);
+   1 = red-black: the same cell update (poisson_layer.h:80-146) on the cells with (i+j) even, then on the cells with
+   (i+j) odd.  The reference itself states that its sweep result depends on traversal order, OpenMP and MPI
+   (poisson_layer.h:55-65); red-black removes that dependence (and ignores orc_set_decomp: it is decomposition
+   independent).  It pins the throughput mode of the CUDA library (msqg_set_smoother). */
+void orc_set_smoother(orc_model *m, int smoother);
+int orc_get_smoother(orc_model *m);
 void orc_init_noise(orc_model *m, unsigned seed);/* qg.c:60-70 with srand(seed) */
 void orc_remove_mean_psi(orc_model *m);          /* qg.c:66-70 */
 
@@ -122,6 +129,9 @@ void orc_test_relax(int nl, int level, double L0, const double *dh, const double
                     double *a, const double *b, int nsweeps, int px, int py);
 double orc_test_residual(int nl, int level, double L0, const double *dh, const double *s,
                          const double *a, const double *b, double *res);
+void orc_test_relax_rb(int nl, int level, double L0, const double *dh, const double *s,
+                       double *a, const double *b, int nsweeps);
+void orc_test_relax_scalar_rb(int level, double L0, const double *lam, double *a, const double *b, int nsweeps);
 void orc_test_restrict(int nf, int level, const double *fine, double *coarse);
 void orc_test_prolong(int nf, int level, const double *coarse, double *fine); /* level = fine level */
 void orc_test_relax_scalar(int level, double L0, const double *lam, double *a, const double *b, int nsweeps);

@@ -88,6 +88,9 @@ def lib(omp=False):
     L.orc_set_const.restype = C.c_int
     L.orc_set_flag_topo.argtypes = [vp, C.c_int]
     L.orc_set_decomp.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.orc_set_smoother.argtypes = [vp, C.c_int]
+    L.orc_get_smoother.argtypes = [vp]
+    L.orc_get_smoother.restype = C.c_int
     L.orc_init_noise.argtypes = [vp, C.c_uint]
     L.orc_remove_mean_psi.argtypes = [vp]
     L.orc_invertq.argtypes = [vp]
@@ -116,6 +119,8 @@ def lib(omp=False):
     L.orc_pyq2p.argtypes = [vp, dp, dp]
     L.orc_pyp2q.argtypes = [vp, dp, dp]
     L.orc_test_relax.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int]
+    L.orc_test_relax_rb.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, dp, dp, C.c_int]
+    L.orc_test_relax_scalar_rb.argtypes = [C.c_int, C.c_double, dp, dp, dp, C.c_int]
     L.orc_test_residual.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp, dp, dp, dp]
     L.orc_test_residual.restype = C.c_double
     L.orc_test_restrict.argtypes = [C.c_int, C.c_int, dp, dp]
@@ -194,6 +199,10 @@ class Model:
         out = np.zeros((self.nfields(fid), self.N, self.N))
         self.L.orc_get_field(self.h, fid, out)
         return out
+
+    def set_smoother(self, name):
+        """'lex' (reference order, default) or 'rb' (red-black ordering of the same cell update)"""
+        self.L.orc_set_smoother(self.h, {"lex": 0, "rb": 1}[name])
 
     def set_const(self):
         rc = self.L.orc_set_const(self.h)

@@ -32,8 +32,8 @@ def rel_l2(a, b):
     return d / n if n > 0 else d
 
 
-def make_pair(N, nl, **over):
-    """(oracle model, gpu model) with identical parameters and initial psi."""
+def make_pair(N, nl, smoother="lex", **over):
+    """(oracle model, gpu model) with identical parameters, smoother ordering and initial psi."""
     from oracle import oracle as O
     from msom_b200 import capi as G
     kw = base_kw(N, nl, **over)
@@ -41,6 +41,8 @@ def make_pair(N, nl, **over):
     pg = G.make_params(**kw)
     mo = O.Model(po)
     mg = G.Model(pg)
+    mo.set_smoother(smoother)
+    mg.set_smoother(smoother)
     psi = synth_psi(N, nl, kw["L0"])
     mo.set(O.PSI, psi)
     mg.set(G.PSI, psi)
