@@ -895,7 +895,7 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
   A.reuse = m->rb_reuse;
   if (RCOEF && (g.bc || !A.coef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
   const size_t smem = (size_t)A.R * Cfg::row_bytes;
-  const int threads = nh * RB_NP;
+  const int threads = Cfg::NSMAX * 2 * RB_NP; /* fixed block: stages beyond nh only stream */
   auto kern = k_relax_rb<NL, RCOEF>;
   static KernelDevState st;
   const int dev = m->device & 63;
@@ -903,7 +903,7 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)((size_t)(4 * Cfg::NSMAX + 1 + RB_PF) * Cfg::row_bytes)));
     for (int s = 1; s <= Cfg::NSMAX; s++)
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occ[dev][s], kern, 2 * s * RB_NP,
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occ[dev][s], kern, Cfg::NSMAX * 2 * RB_NP,
                                                        (size_t)(4 * s + 1 + RB_PF) * Cfg::row_bytes));
     st.set[dev] = true;
   }
@@ -911,7 +911,7 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
   const int nxo = A.ox_hi - A.ox_lo, nyo = A.oy_hi - A.oy_lo;
   const int nstrips = (nxo + A.TX - 1) / A.TX;
   /* row chunks: about one wave of CTAs; a chunk pays 2 nh halo rows + 2 nh pipeline steps, so keep it >= 32 rows */
-  int nchunks = (m->num_sms * occ + nstrips / 2) / nstrips;
+  int nchunks = (m->num_sms * occ) / nstrips; /* never more CTAs than fit at once: a second, nearly empty wave doubles the time */
   if (nchunks > nyo / 32) nchunks = nyo / 32;
   if (nchunks < 1) nchunks = 1;
   A.rpc = (nyo + nchunks - 1) / nchunks;

@@ -75,14 +75,17 @@ template <int NL, bool RCOEF>
 __global__ void __launch_bounds__(RbCfg<NL>::NSMAX * 2 * RB_NP, 1)
 k_relax_rb(RbArgs A, RelaxCoef<NL> C) {
   using Cfg = RbCfg<NL>;
-  constexpr int WX = RB_WX, NP = RB_NP, PF = RB_PF;
+  constexpr int WX = RB_WX, NP = RB_NP, PF = RB_PF, NSMAX = Cfg::NSMAX;
   constexpr int NL2 = Cfg::NL2, ARR2 = Cfg::ARR2, ROW2 = Cfg::ROW2;
+  constexpr int EPT = (2 * NL + NSMAX - 1) / NSMAX; /* planes (da: 0..NL-1, res: NL..2NL-1) streamed per thread */
+  constexpr int EPO = (NL + NSMAX - 1) / NSMAX;     /* planes stored per thread */
   extern __shared__ double2 ring[];
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int nh = 2 * A.ns, H = nh, R = A.R;
+  /* the block always has NSMAX * 128 threads: stages k >= nh only help with the streaming */
+  const int tid = threadIdx.x;
+  const int nh = 2 * A.ns, H = nh;
   const int k = tid / NP, p = tid % NP;
   const int pitch = A.g.pitch, nx = A.g.nx, ny = A.g.ny, bc = A.g.bc;
-  const size_t plane = A.g.plane;
+  const long long plane = (long long)A.g.plane;
   /* output block and window of this CTA */
   const int ox0 = A.ox_lo + blockIdx.x * A.TX;
   const int ox1 = min(ox0 + A.TX, A.ox_hi);
@@ -92,117 +95,143 @@ k_relax_rb(RbArgs A, RelaxCoef<NL> C) {
   const int jw0 = max(A.ylo, oy0 - H), jw1 = min(A.yhi, oy1 + H);
   const int nrw = jw1 - jw0; /* window rows */
 
-  /* ---- streaming: thread <-> (window column wx, planes q0, q0 + qstep, ...) */
-  const int wx = tid & (WX - 1), q0 = tid >> 7, qstep = nthreads >> 7;
+  /* ---- streaming state: thread <-> window column wx, planes q0 + i * NSMAX; pointers move one row per step */
+  const int wx = tid & (WX - 1), q0 = tid >> 7;
   const int gxl = x0w + wx;
   const bool lvalid = gxl >= A.xlo && gxl < A.xhi;
   const bool ovalid = gxl >= ox0 && gxl < ox1;
   const int colofs = ((wx & 1) * NP + (wx >> 1)) * 2; /* doubles; parity-split column inside a layer-pair block */
   double *ring_d = reinterpret_cast<double *>(ring);
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring_d);
-
-  auto load_row = [&](int r, int slot) {
-    if (r < nrw && lvalid) {
-      const long long go = (long long)(jw0 + r + 1) * pitch + MSQG_OX + gxl;
-      const unsigned dst0 = ring_s + (unsigned)((slot * ROW2 * 2 + colofs) * 8);
-      for (int q = q0; q < 2 * NL; q += qstep) {
-        const int arr = q >= NL ? 1 : 0, l = arr ? q - NL : q;
-        const double *src = (arr ? A.res : A.da) + (long long)l * (long long)plane + go;
-        cp_async8(dst0 + (unsigned)((arr * 2 * ARR2 + (l >> 1) * 2 * WX + (l & 1)) * 8), src);
-      }
+  const double *src[EPT];
+  unsigned dofs[EPT];
+  bool pok[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; i++) {
+    const int q = q0 + i * NSMAX;
+    pok[i] = lvalid && q < 2 * NL;
+    const int arr = q >= NL ? 1 : 0, l = arr ? q - NL : q;
+    src[i] = (arr ? A.res : A.da) + (pok[i] ? (long long)l * plane + (long long)(jw0 + 1) * pitch + MSQG_OX + gxl : 0);
+    dofs[i] = (unsigned)((arr * 2 * ARR2 + (l >> 1) * 2 * WX + (l & 1) + colofs) * 8);
+  }
+  double *dst[EPO];
+  unsigned sofs[EPO];
+  bool sok[EPO];
+#pragma unroll
+  for (int i = 0; i < EPO; i++) {
+    const int q = q0 + i * NSMAX;
+    sok[i] = ovalid && q < NL;
+    dst[i] = A.da_out + (sok[i] ? (long long)q * plane + (long long)(jw0 + 1) * pitch + MSQG_OX + gxl : 0);
+    sofs[i] = (unsigned)((q >> 1) * 2 * WX + (q & 1) + colofs);
+  }
+  int ld_row = 0;      /* next window row to fetch */
+  unsigned ld_off = 0; /* its ring slot, bytes */
+  const unsigned ROWB = (unsigned)Cfg::row_bytes, RTOTB = (unsigned)A.R * ROWB;
+  auto load_row = [&]() {
+    if (ld_row < nrw) {
+#pragma unroll
+      for (int i = 0; i < EPT; i++)
+        if (pok[i]) { cp_async8(ring_s + ld_off + dofs[i], src[i]); src[i] += pitch; }
     }
     cp_async_commit();
+    ld_row++;
+    ld_off = ld_off + ROWB == RTOTB ? 0u : ld_off + ROWB;
   };
-
-  /* prologue: rows 0 .. PF-1 */
 #pragma unroll 1
-  for (int r = 0; r < PF; r++) load_row(r, r % R);
-  int ld_slot = PF % R;                 /* slot of window row t + PF */
-  int sl = ((-1 - 2 * k) % R + R) % R;  /* slot of this stage's row t - 1 - 2k */
-  int out_slot = ((-2 * nh) % R + R) % R; /* slot of the row completed in the previous step, t - 2 nh */
+  for (int r = 0; r < PF; r++) load_row();
+
+  /* ---- stage state: half-sweep k works on window row r = t - 1 - 2k.  Shared memory is addressed with 32-bit
+     byte addresses that move with the row (no generic-pointer arithmetic in the loop). */
+  int r = -1 - 2 * k;
+  unsigned slB = (unsigned)(((-1 - 2 * k) % A.R + A.R) % A.R) * ROWB; /* ring byte offset of row r */
+  int upd = (jw0 + r + k + A.par0 + x0w) & 1;               /* which column of the pair is updated in row r */
+  unsigned cuB = (unsigned)(upd * NP + p) * 16u, ciB = (unsigned)((1 - upd) * NP + p) * 16u;
+  /* outer neighbour for upd = 0 / 1 (clamped at the window edge: those cells are halo garbage anyway) */
+  const unsigned co0B = (unsigned)(NP + (p > 0 ? p - 1 : 0)) * 16u, co1B = (unsigned)(p < NP - 1 ? p + 1 : NP - 1) * 16u;
+  const int gxa = x0w + 2 * p, gxb = gxa + 1;
+  const bool exa = gxa >= A.xlo && gxa < A.xhi, exb = gxb >= A.xlo && gxb < A.xhi;
+  /* physical x-boundaries of this pair: bit 0 = the outer neighbour is a ghost, bit 1 = the in-pair neighbour is */
+  const int pl = !(bc & 1), pr = !(bc & 2);
+  const int xg0 = ((gxa == 0 && pl) ? 1 : 0) | ((gxa == nx - 1 && pr) ? 2 : 0);  /* upd = 0: west is outer, east in-pair */
+  const int xg1 = ((gxb == nx - 1 && pr) ? 1 : 0) | ((gxb == 0 && pl) ? 2 : 0);  /* upd = 1: east is outer, west in-pair */
+  const int r_bot = (bc & 4) ? -(1 << 30) : -jw0, r_top = (bc & 8) ? -(1 << 30) : ny - 1 - jw0;
+  const bool stage_on = k < nh;
+  const bool no_reuse = A.reuse == 0;
+  constexpr unsigned LPB = WX * 16u;      /* bytes between layer pairs */
+  constexpr unsigned RESB = ARR2 * 16u;   /* byte offset of res inside a ring row */
+  /* ---- store state: the row the last half-sweep completed in the previous step */
+  int ro = -2 * nh;
+  unsigned soB = (unsigned)(((-2 * nh) % A.R + A.R) % A.R) * ROWB;
+  const int ro_lo = oy0 - jw0, ro_hi = oy1 - jw0;
   const int T = nrw + 2 * nh;
 
-  double Ireg[NL], Nreg[NL]; /* carried: raw in-pair neighbour of the last step's row, raw north of the last step */
+  /* Of the four neighbours only north and the outer one are loaded: the thread moves one row up and switches column
+     every step, so this step's in-pair neighbour is last step's north and this step's south is last step's in-pair
+     neighbour: a FIFO of the last three north values, rotated by unrolling three steps (no register moves). */
+  double F0[NL], F1[NL], F2[NL];
 #pragma unroll
-  for (int l = 0; l < NL; l++) { Ireg[l] = 0.; Nreg[l] = 0.; }
-  bool have_prev = false;
+  for (int l = 0; l < NL; l++) { F0[l] = 0.; F1[l] = 0.; F2[l] = 0.; }
 
-#pragma unroll 1
-  for (int t = 0; t < T; t++) {
-    load_row(t + PF, ld_slot);
-    ld_slot = ld_slot + 1 == R ? 0 : ld_slot + 1;
-
-    /* ---- half-sweep k on window row r */
-    const int r = t - 1 - 2 * k;
-    if (r >= 0 && r < nrw) {
-      const int j = jw0 + r;
-      const int upd = (j + k + A.par0 + x0w) & 1; /* which column of the pair has the colour of half-sweep k in this row */
-      const int gx = x0w + 2 * p + upd;
-      const bool exist = gx >= A.xlo && gx < A.xhi;
-      const int slN = sl + 1 == R ? 0 : sl + 1, slS = sl == 0 ? R - 1 : sl - 1;
-      const double2 *rowc = ring + sl * ROW2, *rown = ring + slN * ROW2, *rows = ring + slS * ROW2;
-      const int cu = upd * NP + p, ci = (1 - upd) * NP + p;
-      int po = p + (upd ? 1 : -1);
-      po = po < 0 ? 0 : (po > NP - 1 ? NP - 1 : po);
-      const int co = (1 - upd) * NP + po;
-      double b[NL], vi[NL], vo[NL], vn[NL], vs[NL];
-      const bool reuse = A.reuse && have_prev;
+  auto step = [&](double (&Fn)[NL], double (&Fi)[NL], double (&Fs)[NL]) {
+    load_row();
+    if (stage_on && (unsigned)r < (unsigned)nrw) {
+      const unsigned rowc = ring_s + slB;
+      const unsigned rown = ring_s + (slB + ROWB == RTOTB ? 0u : slB + ROWB);
+      const unsigned coB = upd ? co1B : co0B;
+      double b[NL], vo[NL];
 #pragma unroll
       for (int lp = 0; lp < NL2; lp++) {
-        const double2 tb = rowc[ARR2 + lp * WX + cu];
-        const double2 tn = rown[lp * WX + cu];
-        const double2 to = rowc[lp * WX + co];
-        b[2 * lp] = tb.x; vn[2 * lp] = tn.x; vo[2 * lp] = to.x;
-        if (2 * lp + 1 < NL) { b[2 * lp + 1] = tb.y; vn[2 * lp + 1] = tn.y; vo[2 * lp + 1] = to.y; }
+        const double2 tb = lds2(rowc + RESB + lp * LPB + cuB);
+        const double2 tn = lds2(rown + lp * LPB + cuB);
+        const double2 to = lds2(rowc + lp * LPB + coB);
+        b[2 * lp] = tb.x; Fn[2 * lp] = tn.x; vo[2 * lp] = to.x;
+        if (2 * lp + 1 < NL) { b[2 * lp + 1] = tb.y; Fn[2 * lp + 1] = tn.y; vo[2 * lp + 1] = to.y; }
       }
-      if (reuse) {
-#pragma unroll
-        for (int l = 0; l < NL; l++) { vs[l] = Ireg[l]; vi[l] = Nreg[l]; }
-      } else {
+      if (r == 0 || no_reuse) { /* first row of the window: nothing carried yet */
+        const unsigned rows = ring_s + (slB == 0 ? RTOTB - ROWB : slB - ROWB);
 #pragma unroll
         for (int lp = 0; lp < NL2; lp++) {
-          const double2 ti = rowc[lp * WX + ci];
-          const double2 ts = rows[lp * WX + cu];
-          vi[2 * lp] = ti.x; vs[2 * lp] = ts.x;
-          if (2 * lp + 1 < NL) { vi[2 * lp + 1] = ti.y; vs[2 * lp + 1] = ts.y; }
+          const double2 ti = lds2(rowc + lp * LPB + ciB);
+          const double2 ts = lds2(rows + lp * LPB + cuB);
+          Fi[2 * lp] = ti.x; Fs[2 * lp] = ts.x;
+          if (2 * lp + 1 < NL) { Fi[2 * lp + 1] = ti.y; Fs[2 * lp + 1] = ts.y; }
         }
       }
-#pragma unroll
-      for (int l = 0; l < NL; l++) { Ireg[l] = vi[l]; Nreg[l] = vn[l]; }
-      have_prev = true;
-      /* homogeneous dirichlet ghosts on the physical sides: -(this cell before its update) */
-      const bool gl = gx == 0 && !(bc & 1), gr = gx == nx - 1 && !(bc & 2);
-      const bool gb = j == 0 && !(bc & 4), gt = j == ny - 1 && !(bc & 8);
-      if (gl || gr || gb || gt) {
-        /* west is the outer neighbour when the even column of the pair is updated, the in-pair one otherwise */
-        const bool o_ghost = (gl && upd == 0) || (gr && upd == 1);
-        const bool i_ghost = (gl && upd == 1) || (gr && upd == 0);
+      /* relax_layer, poisson_layer.h:80-146 (same expression order as k_relax_lex):
+         rhs = -sq(Delta)*b; rhs += a[1] + a[-1]; rhs += a[0,1] + a[0,-1] */
+      double sh[NL], sv[NL];
+      const int xg = upd ? xg1 : xg0;
+      const bool gb = r == r_bot, gt = r == r_top;
+      if (xg != 0 || gb || gt) {
+        /* homogeneous dirichlet ghosts on the physical sides: -(this cell before its update) */
 #pragma unroll
         for (int lp = 0; lp < NL2; lp++) {
-          const double2 tc = rowc[lp * WX + cu];
-          const double g0 = -tc.x, g1 = -tc.y;
-          if (o_ghost) vo[2 * lp] = g0;
-          if (i_ghost) vi[2 * lp] = g0;
-          if (gb) vs[2 * lp] = g0;
-          if (gt) vn[2 * lp] = g0;
-          if (2 * lp + 1 < NL) {
-            if (o_ghost) vo[2 * lp + 1] = g1;
-            if (i_ghost) vi[2 * lp + 1] = g1;
-            if (gb) vs[2 * lp + 1] = g1;
-            if (gt) vn[2 * lp + 1] = g1;
+          const double2 tc = lds2(rowc + lp * LPB + cuB);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int l = 2 * lp + h;
+            if (l < NL) {
+              const double g = h ? -tc.y : -tc.x;
+              const double o = (xg & 1) ? g : vo[l], i = (xg & 2) ? g : Fi[l];
+              const double s_ = gb ? g : Fs[l], n_ = gt ? g : Fn[l];
+              sh[l] = i + o;
+              sv[l] = n_ + s_;
+            }
           }
         }
-      }
-      /* relax_layer, poisson_layer.h:80-146 (same expression order as k_relax_lex) */
-      double rhs[NL], out[NL];
-      if (!RCOEF) {
+      } else {
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-          double rr = C.msd2 * b[l];
-          rr += vi[l] + vo[l];
-          rr += vn[l] + vs[l];
-          rhs[l] = rr;
-        }
+        for (int l = 0; l < NL; l++) { sh[l] = Fi[l] + vo[l]; sv[l] = Fn[l] + Fs[l]; }
+      }
+      double rhs[NL], out[NL];
+#pragma unroll
+      for (int l = 0; l < NL; l++) {
+        double rr = C.msd2 * b[l];
+        rr += sh[l];
+        rr += sv[l];
+        rhs[l] = rr;
+      }
+      if (!RCOEF) {
 #pragma unroll
         for (int l = 1; l < NL; l++) rhs[l] -= div_by(C.t0[l] * rhs[l - 1], C.t1p[l - 1], C.rinv[l - 1]);
         out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
@@ -210,50 +239,53 @@ k_relax_rb(RbArgs A, RelaxCoef<NL> C) {
         for (int l = NL - 2; l >= 0; l--) out[l] = div_by(rhs[l] - C.t2[l] * out[l + 1], C.t1p[l], C.rinv[l]);
       } else {
         /* horizontally varying stretching: coefficients of this row / cell from the k_rowcoef table (own cells only) */
+        const int j = jw0 + r, gx = upd ? gxb : gxa;
         const int jc = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j), xc = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
         const double *ct = A.coef + (A.coef_cell ? (size_t)jc * nx + xc : (size_t)jc) * 6 * NL;
         double t0[NL], t2[NL], t1p[NL], rinv[NL];
 #pragma unroll
         for (int l = 0; l < NL; l++) { t0[l] = ct[l]; t2[l] = ct[NL + l]; t1p[l] = ct[2 * NL + l]; rinv[l] = ct[3 * NL + l]; }
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-          double rr = C.msd2 * b[l];
-          rr += vi[l] + vo[l];
-          rr += vn[l] + vs[l];
-          rhs[l] = rr;
-        }
-#pragma unroll
         for (int l = 1; l < NL; l++) rhs[l] -= div_by(t0[l] * rhs[l - 1], t1p[l - 1], rinv[l - 1]);
         out[NL - 1] = div_by(rhs[NL - 1], t1p[NL - 1], rinv[NL - 1]);
 #pragma unroll
         for (int l = NL - 2; l >= 0; l--) out[l] = div_by(rhs[l] - t2[l] * out[l + 1], t1p[l], rinv[l]);
       }
-      if (exist) {
-        double2 *wr = ring + sl * ROW2;
+      if (upd ? exb : exa) {
 #pragma unroll
         for (int lp = 0; lp < NL2; lp++)
-          wr[lp * WX + cu] = make_double2(out[2 * lp], (2 * lp + 1 < NL) ? out[2 * lp + 1] : 0.);
+          sts2(rowc + lp * LPB + cuB, out[2 * lp], (2 * lp + 1 < NL) ? out[2 * lp + 1] : 0.);
       }
-    } else
-      have_prev = false;
-    sl = sl + 1 == R ? 0 : sl + 1;
-
-    /* ---- store the row that the last half-sweep completed in the previous step */
-    {
-      const int ro = t - 2 * nh;
-      if (ro >= 0 && ovalid) {
-        const int j = jw0 + ro;
-        if (j >= oy0 && j < oy1) {
-          const long long go = (long long)(j + 1) * pitch + MSQG_OX + gxl;
-          const double *srow = ring_d + (size_t)out_slot * ROW2 * 2 + colofs;
-          for (int q = q0; q < NL; q += qstep)
-            A.da_out[(long long)q * (long long)plane + go] = srow[(q >> 1) * 2 * WX + (q & 1)];
-        }
-      }
-      out_slot = out_slot + 1 == R ? 0 : out_slot + 1;
     }
+    r++;
+    slB = slB + ROWB == RTOTB ? 0u : slB + ROWB;
+    upd ^= 1;
+    { const unsigned tmp = cuB; cuB = ciB; ciB = tmp; }
+    /* ---- store the row completed in the previous step */
+    if (ro >= ro_lo && ro < ro_hi) {
+#pragma unroll
+      for (int i = 0; i < EPO; i++)
+        if (sok[i]) {
+          double v;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ring_s + soB + sofs[i] * 8u));
+          *dst[i] = v;
+        }
+    }
+    if (ro >= 0) {
+#pragma unroll
+      for (int i = 0; i < EPO; i++) dst[i] += pitch;
+    }
+    ro++;
+    soB = soB + ROWB == RTOTB ? 0u : soB + ROWB;
     cp_async_wait<PF - 1>();
     __syncthreads();
+  };
+
+#pragma unroll 1
+  for (int t = 0; t < T; t += 3) {
+    step(F0, F2, F1);
+    if (t + 1 < T) step(F1, F0, F2);
+    if (t + 2 < T) step(F2, F1, F0);
   }
   cp_async_wait<0>();
 }
