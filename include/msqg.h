@@ -225,6 +225,14 @@ int msqg_nccl_unique_id(void *out128);
 int msqg_group_create_local(const msqg_params *p, int device, int px, int py, int agg_n, msqg_group **out);
 int msqg_group_create_nccl(const msqg_params *p, int device, int px, int py, int agg_n, int rank, int nranks,
                            const void *uid128, msqg_group **out);
+/* the same with the smoother named (msqg_set_smoother): 1 = red-black.  A red-black group gives the bits of the
+ * single-GPU red-black solve whatever px, py and agg_n are (a half-sweep is decomposition independent); levels with
+ * fewer than agg_n cells per side are replicated on every GPU (all-gather of the restricted residual, redundant coarse
+ * solve) and the sweeps of a distributed level need ONE halo exchange (deep halos, communication-avoiding). */
+int msqg_group_create_local_sm(const msqg_params *p, int device, int px, int py, int agg_n, int smoother, msqg_group **out);
+int msqg_group_create_nccl_sm(const msqg_params *p, int device, int px, int py, int agg_n, int smoother, int rank, int nranks,
+                              const void *uid128, msqg_group **out);
+int msqg_group_smoother(msqg_group *g);
 void msqg_group_destroy(msqg_group *g);
 int msqg_group_ntiles(msqg_group *g);                       /* tiles held by this process */
 msqg_model *msqg_group_tile(msqg_group *g, int t);

@@ -29,6 +29,7 @@ struct NcclApi {
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
   const char *(*GetErrorString)(int);
   bool ok;
 };
@@ -44,7 +45,7 @@ static NcclApi *nccl_api() {
 #define NCSYM(f, name) *(void **)(&api.f) = dlsym(h, name); if (!api.f) return nullptr;
   NCSYM(GetUniqueId, "ncclGetUniqueId") NCSYM(CommInitRank, "ncclCommInitRank") NCSYM(CommDestroy, "ncclCommDestroy")
   NCSYM(GroupStart, "ncclGroupStart") NCSYM(GroupEnd, "ncclGroupEnd") NCSYM(Send, "ncclSend") NCSYM(Recv, "ncclRecv")
-  NCSYM(AllReduce, "ncclAllReduce") NCSYM(GetErrorString, "ncclGetErrorString")
+  NCSYM(AllReduce, "ncclAllReduce") NCSYM(AllGather, "ncclAllGather") NCSYM(GetErrorString, "ncclGetErrorString")
 #undef NCSYM
   api.ok = true;
   return &api;
@@ -119,6 +120,7 @@ __global__ void k_load_patch(double *__restrict__ dst, Geom gp, const double *__
 struct msqg_group {
   msqg_params p;
   int px, py, agg_n, device, kind; /* kind 0 local, 1 nccl */
+  int rb;                          /* red-black smoother: replicated coarse levels, deep halos (dist_rb.cuh) */
   int rank, nranks;
   std::vector<msqg_model *> tiles; /* local: all tiles, index iy*px+ix; nccl: this rank's tile */
   cudaStream_t stream;
@@ -200,7 +202,11 @@ static int halo_exchange(msqg_group *G, std::vector<double *> &arr, std::vector<
   }
   return MSQG_OK;
 }
+static int exchange_one(msqg_group *G, int id, int lev, int w, int ring);
 static int exchange_list(msqg_group *G, int id, int lev) {
+  /* red-black groups: the 8-neighbour exchange, which also carries the ghost ring of the physical sides along the
+     tile edges, so every halo cell (corners included) holds exactly the value of the undecomposed field */
+  if (G->rb) return exchange_one(G, id, lev, 1, 1);
   std::vector<double *> arr;
   std::vector<Geom> geo;
   int nf = 0;
@@ -239,14 +245,15 @@ static int reduce_max(msqg_group *G, int off, int n, double *out) {
 
 /* ------------------------------------------------------------------ create / destroy */
 static int group_create(const msqg_params *p, int device, int px, int py, int agg_n, int kind, int rank, int nranks,
-                        const void *uid, msqg_group **out) {
+                        const void *uid, msqg_group **out, int smoother = -1) {
+  if (smoother < 0) { const char *e = getenv("MSQG_SMOOTHER"); smoother = (e && !strcmp(e, "rb")) ? 1 : 0; }
   *out = nullptr;
   if (px * py < 2) FAIL(MSQG_ERR_ARG, "a group needs px*py >= 2 tiles");
   if (p->mode_pv_invert || p->stochastic) FAIL(MSQG_ERR_ARG, "decomposed grids support the layer-coupled, deterministic path only");
   if (kind == 1 && nranks != px * py) FAIL(MSQG_ERR_ARG, "nranks must equal px*py");
   msqg_group *G = new msqg_group();
   G->p = *p; G->px = px; G->py = py; G->agg_n = agg_n; G->device = device; G->kind = kind;
-  G->rank = rank; G->nranks = nranks; G->nccl = nullptr; G->comm = nullptr;
+  G->rank = rank; G->nranks = nranks; G->nccl = nullptr; G->comm = nullptr; G->rb = smoother == 1;
   G->ts_previous = 0.; G->total_cycles = 0; G->exchanges = 0;
   memset(&G->mgpsi, 0, sizeof(G->mgpsi));
   memset(G->umax_pg, 0, sizeof(G->umax_pg));
@@ -259,7 +266,8 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
     for (int iy = 0; iy < py; iy++)
       for (int ix = 0; ix < px; ix++) {
         msqg_model *m;
-        if ((rc = create_model(p, device, px, py, ix, iy, agg_n, G->stream, &m))) return rc;
+        if ((rc = create_model(p, device, px, py, ix, iy, agg_n, G->stream, &m, G->rb))) return rc;
+        m->smoother = G->rb;
         G->tiles.push_back(m);
       }
   } else {
@@ -269,7 +277,8 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
     memcpy(&id, uid, 128);
     NCK(G->nccl->CommInitRank(&G->comm, nranks, id, rank));
     msqg_model *m;
-    if ((rc = create_model(p, device, px, py, rank % px, rank / px, agg_n, G->stream, &m))) return rc;
+    if ((rc = create_model(p, device, px, py, rank % px, rank / px, agg_n, G->stream, &m, G->rb))) return rc;
+    m->smoother = G->rb;
     G->tiles.push_back(m);
   }
   *out = G;
@@ -282,6 +291,14 @@ extern "C" int msqg_group_create_nccl(const msqg_params *p, int device, int px, 
                                       const void *uid128, msqg_group **out) {
   return group_create(p, device, px, py, agg_n, 1, rank, nranks, uid128, out);
 }
+extern "C" int msqg_group_create_local_sm(const msqg_params *p, int device, int px, int py, int agg_n, int smoother, msqg_group **out) {
+  return group_create(p, device, px, py, agg_n, 0, 0, 1, nullptr, out, smoother);
+}
+extern "C" int msqg_group_create_nccl_sm(const msqg_params *p, int device, int px, int py, int agg_n, int smoother, int rank,
+                                         int nranks, const void *uid128, msqg_group **out) {
+  return group_create(p, device, px, py, agg_n, 1, rank, nranks, uid128, out, smoother);
+}
+extern "C" int msqg_group_smoother(msqg_group *G) { return G->rb; }
 extern "C" void msqg_group_destroy(msqg_group *G) {
   if (!G) return;
   cudaSetDevice(G->device);
@@ -438,6 +455,8 @@ static int g_check_err(msqg_group *G) {
   return MSQG_OK;
 }
 
+#include "dist_rb.cuh"
+
 /* mg_solve + poisson_layer + invertq on the decomposed grid */
 static int g_invertq(msqg_group *G, int q_id) {
   for (msqg_model *m : G->tiles) {
@@ -453,7 +472,7 @@ static int g_invertq(msqg_group *G, int q_id) {
   if ((rc = g_residual(G, q_id, &resb))) return rc;
   s.resb = s.resa = resb;
   for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > 1e-3); s.i++) {
-    if ((rc = g_cycle(G, s.nrelax))) return rc;
+    if ((rc = G->rb ? g_cycle_rb(G, s.nrelax) : g_cycle(G, s.nrelax))) return rc;
     if ((rc = g_residual(G, q_id, &s.resa))) return rc;
     if (s.resa > 1e-3) {
       if (resb / s.resa < 1.2 && s.nrelax < 100) s.nrelax++;

@@ -1,0 +1,282 @@
+/*
+ * dist_rb.cuh -- multigrid cycle of a px x py group of tiles with the red-black smoother (included by model.cu).
+ *
+ * A red-black half-sweep only reads cells of the other colour, so a decomposed sweep gives the SAME bits as the
+ * undecomposed one provided every tile sees current values in its halo -- unlike the reference's lexicographic sweep,
+ * whose result depends on the MPI decomposition (msqg/poisson_layer.h:55-65; run as `mpirun -np 16`, msqg/qg.c:12-19).
+ * The group therefore reproduces the single-GPU red-black result bit for bit on 1, 2, 4 and 8 GPUs, and it does so with
+ * ONE halo exchange per level and cycle instead of one per sweep:
+ *
+ *   - the planes of a tile carry a frame of MSQG_FRAME cells (layout.cuh); before the nrelax sweeps of a level the
+ *     tiles exchange a halo of 2 nrelax + 1 cells of da (and, once per cycle for all levels, 2 nrelax cells of res);
+ *     k_relax_rb then runs all sweeps on tile + halo, recomputing the neighbours' border cells: after h half-sweeps the
+ *     outermost h halo cells are stale and are simply not used any more (communication-avoiding smoothing);
+ *   - one halo cell survives the sweeps, which is what the bilinear prolongation to the next level reads;
+ *   - the exchange moves the 4 sides and 4 corners in ONE grouped ncclSend/ncclRecv (8 neighbours) -- corners go
+ *     straight to the diagonal neighbour, no x-phase/y-phase;
+ *   - levels below the agglomeration threshold (global size < agg_n) are REPLICATED: the restricted residual is
+ *     all-gathered (ncclAllGather) and every GPU runs the small coarse solve redundantly, so nothing is scattered back
+ *     and no GPU idles while one of them works.
+ * Scalars: one ncclAllReduce(max) per cycle for the residual norm.
+ */
+#pragma once
+
+/* ------------------------------------------------------------------ 8-neighbour halo exchange of width w */
+struct HaloBox { int x0, x1, y0, y1; };
+struct HaloPlan {
+  HaloBox send[9], recv[9]; /* index d = (dy + 1) * 3 + (dx + 1); 4 = the tile itself, unused */
+  int on[9];                /* neighbour exists */
+  long long off[9];         /* offset of this item in the direction's buffer, doubles */
+  double *sbuf[9], *rbuf[9];
+};
+/* blockIdx.y = direction, blockIdx.z = plane; unpack = 1 scatters the receive buffers into the halo */
+__global__ void k_halo_pack(double *__restrict__ a, Geom g, HaloPlan P, int unpack) {
+  const int d = blockIdx.y, f = blockIdx.z;
+  if (!P.on[d]) return;
+  const HaloBox b = unpack ? P.recv[d] : P.send[d];
+  const int bw = b.x1 - b.x0, bh = b.y1 - b.y0;
+  const long long cnt = (long long)bw * bh;
+  double *buf = (unpack ? P.rbuf[d] : P.sbuf[d]) + P.off[d] + (long long)f * cnt;
+  double *pl = a + (size_t)f * g.plane;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x) {
+    const int y = b.y0 + (int)(e / bw), x = b.x0 + (int)(e % bw);
+    const long long c = (long long)(y + 1) * g.pitch + MSQG_OX + x;
+    if (unpack) pl[c] = buf[e]; else buf[e] = pl[c];
+  }
+}
+
+struct XItem {
+  std::vector<double *> arr; /* per local tile */
+  std::vector<Geom> geo;
+  int nf, w, ring;           /* planes, halo width, 1: straight transfers also carry the ghost ring of physical sides */
+};
+
+static void halo_boxes(const Geom &g, int w, int ring, int ix, int iy, int px, int py, HaloPlan &P) {
+  const int eL = (ring && !(g.bc & 1)) ? 1 : 0, eR = (ring && !(g.bc & 2)) ? 1 : 0;
+  const int eB = (ring && !(g.bc & 4)) ? 1 : 0, eT = (ring && !(g.bc & 8)) ? 1 : 0;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++) {
+      const int d = (dy + 1) * 3 + (dx + 1);
+      const int nxx = ix + dx, nyy = iy + dy;
+      P.on[d] = !(dx == 0 && dy == 0) && nxx >= 0 && nxx < px && nyy >= 0 && nyy < py;
+      HaloBox &s = P.send[d], &r = P.recv[d];
+      if (dx < 0) { s.x0 = 0; s.x1 = w; r.x0 = -w; r.x1 = 0; }
+      else if (dx > 0) { s.x0 = g.nx - w; s.x1 = g.nx; r.x0 = g.nx; r.x1 = g.nx + w; }
+      else { s.x0 = r.x0 = -eL; s.x1 = r.x1 = g.nx + eR; }
+      if (dy < 0) { s.y0 = 0; s.y1 = w; r.y0 = -w; r.y1 = 0; }
+      else if (dy > 0) { s.y0 = g.ny - w; s.y1 = g.ny; r.y0 = g.ny; r.y1 = g.ny + w; }
+      else { s.y0 = r.y0 = -eB; s.y1 = r.y1 = g.ny + eT; }
+    }
+}
+
+/* all items in one grouped exchange: pack (one launch per item and tile), one send/recv pair per neighbour, unpack */
+static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
+  G->exchanges++;
+  const int nt = (int)G->tiles.size();
+  std::vector<std::vector<HaloPlan>> plans(items.size(), std::vector<HaloPlan>(nt));
+  std::vector<std::vector<long long>> tot(nt, std::vector<long long>(9, 0));
+  for (size_t it = 0; it < items.size(); it++)
+    for (int t = 0; t < nt; t++) {
+      msqg_model *m = G->tiles[t];
+      HaloPlan &P = plans[it][t];
+      if (items[it].w > MSQG_FRAME - 1) FAIL(MSQG_ERR_ARG, "halo width %d exceeds the frame", items[it].w);
+      halo_boxes(items[it].geo[t], items[it].w, items[it].ring, m->ix, m->iy, G->px, G->py, P);
+      for (int d = 0; d < 9; d++) {
+        P.sbuf[d] = m->xsend[d]; P.rbuf[d] = m->xrecv[d];
+        P.off[d] = tot[t][d];
+        if (P.on[d]) tot[t][d] += (long long)items[it].nf * (P.send[d].x1 - P.send[d].x0) * (P.send[d].y1 - P.send[d].y0);
+        if ((size_t)tot[t][d] > m->xcap) FAIL(MSQG_ERR_ARG, "halo exchange buffer too small");
+      }
+    }
+  auto launch = [&](int unpack) {
+    for (size_t it = 0; it < items.size(); it++)
+      for (int t = 0; t < nt; t++) {
+        const HaloPlan &P = plans[it][t];
+        long long mx = 0;
+        for (int d = 0; d < 9; d++)
+          if (P.on[d]) mx = std::max(mx, (long long)(P.send[d].x1 - P.send[d].x0) * (P.send[d].y1 - P.send[d].y0));
+        if (mx == 0) continue;
+        int gx = (int)((mx + 255) / 256);
+        if (gx > 64) gx = 64;
+        k_halo_pack<<<dim3(gx, 9, items[it].nf), 256, 0, G->stream>>>(items[it].arr[t], items[it].geo[t], P, unpack);
+        G->tiles[t]->launches++;
+      }
+  };
+  launch(0);
+  CK(cudaGetLastError());
+  if (G->kind == 0) {
+    for (int t = 0; t < nt; t++) {
+      msqg_model *m = G->tiles[t];
+      for (int d = 0; d < 9; d++) {
+        if (tot[t][d] == 0) continue;
+        const int dx = d % 3 - 1, dy = d / 3 - 1;
+        msqg_model *nb = tile_at(G, m->ix + dx, m->iy + dy);
+        CK(cudaMemcpyAsync(m->xrecv[d], nb->xsend[8 - d], (size_t)tot[t][d] * sizeof(double), cudaMemcpyDeviceToDevice, G->stream));
+      }
+    }
+  } else {
+    msqg_model *m = G->tiles[0];
+    NCK(G->nccl->GroupStart());
+    for (int d = 0; d < 9; d++) {
+      if (tot[0][d] == 0) continue;
+      const int dx = d % 3 - 1, dy = d / 3 - 1;
+      const int peer = tile_rank(G, m->ix + dx, m->iy + dy);
+      NCK(G->nccl->Send(m->xsend[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
+      NCK(G->nccl->Recv(m->xrecv[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
+    }
+    NCK(G->nccl->GroupEnd());
+  }
+  launch(1);
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+static int exchange_one(msqg_group *G, int id, int lev, int w, int ring) {
+  std::vector<XItem> items(1);
+  XItem &X = items[0];
+  for (msqg_model *m : G->tiles) {
+    List *L = list_by_id(m, id);
+    X.arr.push_back(L->lev[lev]); X.geo.push_back(m->g[lev]); X.nf = L->nf;
+  }
+  X.w = w; X.ring = ring;
+  return exchange_multi(G, items);
+}
+
+/* ------------------------------------------------------------------ relax on a tile with deep halos */
+/* `sweeps` red-black sweeps on tile + halo: the halo holds h_in valid cells on the internal sides on entry and
+ * h_in - 2 sweeps on exit (split into passes of at most NSMAX sweeps; bit-identical to sweeping the whole level) */
+template <int NL>
+static int relax_rb_tile(msqg_model *m, int lev, int sweeps, int h_in, const RelaxCoef<NL> &C) {
+  constexpr int NSMAX = RbCfg<NL>::NSMAX;
+  const Geom &g = m->g[lev];
+  int left = sweeps, h = h_in;
+  while (left > 0) {
+    const int passes = (left + NSMAX - 1) / NSMAX;
+    const int ns = (left + passes - 1) / passes;
+    const int ho = h - 2 * ns;
+    if (ho < 0) FAIL(MSQG_ERR_ARG, "halo of %d cells is too thin for %d sweeps", h_in, sweeps);
+    const int orange[4] = {(g.bc & 1) ? -ho : 0, g.nx + ((g.bc & 2) ? ho : 0), (g.bc & 4) ? -ho : 0, g.ny + ((g.bc & 8) ? ho : 0)};
+    int rc = launch_relax_rb_pass<NL, false>(m, m->da.lev[lev], m->res.lev[lev], lev, ns, C, orange, h);
+    if (rc) return rc;
+    left -= ns; h = ho;
+  }
+  return MSQG_OK;
+}
+
+__global__ void k_place_all(double *__restrict__ full, Geom gfull, const double *__restrict__ gathered, int hx, int hy, int px,
+                            int nranks, int nf) {
+  /* gathered = [rank][nf][hy][hx] blocks of level La-1 -> interior of the full padded level */
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int rf = blockIdx.z, r = rf / nf, f = rf % nf;
+  if (x >= hx || y >= hy) return;
+  const int ox = (r % px) * hx, oy = (r / px) * hy;
+  full[(size_t)f * gfull.plane + GIDX(gfull.pitch, oy + y, ox + x)] = gathered[(((size_t)r * nf + f) * hy + y) * hx + x];
+}
+
+static int g_cycle_rb(msqg_group *G, int nrelax) {
+  msqg_model *m0 = G->tiles[0];
+  const int D = m0->depth, La = m0->agg_level, nl = G->p.nl;
+  const int nt = (int)G->tiles.size(), nranks = G->px * G->py;
+  dim3 b(32, 8);
+  int rc;
+  /* restriction(res) on the distributed levels, then onto this tile's share of level La-1 */
+  for (msqg_model *m : G->tiles) {
+    for (int l = D - 1; l >= La; l--) {
+      ProfScope ps(m, PROF_RESTRICT, l);
+      k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, G->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
+      m->launches++;
+    }
+    k_restrict<<<grid2(m->gpatch.nx, m->gpatch.ny, b, nl), b, 0, G->stream>>>(m->res.lev[La], m->res_patch, m->g[La], m->gpatch, -1., 0);
+    k_unpack<<<grid2(m->gpatch.nx, m->gpatch.ny, b, nl), b, 0, G->stream>>>(m->patch_stage, m->res_patch, nl, m->gpatch);
+    m->launches += 2;
+  }
+  CK(cudaGetLastError());
+  /* every tile receives every tile's block of level La-1 (all-gather) and assembles the full level */
+  const int hx = m0->gpatch.nx, hy = m0->gpatch.ny;
+  const size_t blk = (size_t)nl * hx * hy;
+  if (G->kind == 0) {
+    for (msqg_model *m : G->tiles)
+      for (int r = 0; r < nt; r++)
+        CK(cudaMemcpyAsync(m->gather_buf + (size_t)r * blk, G->tiles[r]->patch_stage, blk * sizeof(double), cudaMemcpyDeviceToDevice, G->stream));
+  } else {
+    NCK(G->nccl->AllGather(m0->patch_stage, m0->gather_buf, blk, NCCL_DOUBLE, G->comm, G->stream));
+  }
+  /* halo of res on the distributed levels: the sweeps recompute up to 2 nrelax border cells of the neighbours */
+  const int chunk0 = nrelax < 7 ? nrelax : 7;
+  {
+    std::vector<XItem> items;
+    for (int l = La; l <= D; l++) {
+      XItem X;
+      for (msqg_model *m : G->tiles) { X.arr.push_back(m->res.lev[l]); X.geo.push_back(m->g[l]); }
+      X.nf = nl; X.w = 2 * chunk0; X.ring = 0;
+      if (X.w > m0->g[l].nx) X.w = m0->g[l].nx;
+      if (X.w > m0->g[l].ny) X.w = m0->g[l].ny;
+      items.push_back(X);
+    }
+    if ((rc = exchange_multi(G, items))) return rc;
+  }
+  /* replicated coarse levels: every tile solves levels 1 .. La-1 (same arithmetic, same bits everywhere) */
+  for (msqg_model *m : G->tiles) {
+    k_place_all<<<grid2(hx, hy, b, nranks * nl), b, 0, G->stream>>>(m->res.lev[La - 1], m->g[La - 1], m->gather_buf, hx, hy, G->px, nranks, nl);
+    m->launches++;
+    for (int l = La - 2; l >= 1; l--) {
+      k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, G->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
+      m->launches++;
+    }
+    for (int l = 1; l <= La - 1; l++) {
+      const Geom &g = m->g[l];
+      if (l == 1) CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)nl * g.plane * sizeof(double), G->stream));
+      else {
+        launch_prolong(G->stream, nl, m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
+        m->launches++;
+      }
+      ProfScope ps(m, PROF_RELAX_COARSE, nrelax);
+      NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C); });
+      if (rc) return rc;
+    }
+    /* this tile's block of level La-1 plus a one-cell ring (homogeneous dirichlet ghosts evaluated on the fly) */
+    k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da.lev[La - 1], m->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy);
+    k_load_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da_patch, m->gpatch, m->patch_stage);
+    m->launches += 2;
+  }
+  CK(cudaGetLastError());
+  /* distributed levels: prolongation, ONE halo exchange, all sweeps on tile + halo */
+  for (int l = La; l <= D; l++) {
+    for (msqg_model *m : G->tiles) {
+      ProfScope ps(m, PROF_PROLONG, l);
+      if (l == La) launch_prolong(G->stream, nl, m->da_patch, m->da.lev[l], m->gpatch, m->g[l]);
+      else launch_prolong(G->stream, nl, m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], m->g[l]);
+      m->launches++;
+    }
+    CK(cudaGetLastError());
+    int left = nrelax;
+    while (left > 0) {
+      const int c = left < 7 ? left : 7;       /* sweeps covered by one exchange: 2c + 1 <= 15 cells of halo */
+      const int last = (left - c == 0);
+      int w = 2 * c + (last ? 1 : 0);          /* one halo cell must survive the last sweep: the prolongation reads it */
+      const Geom &g0 = m0->g[l];
+      if (w > g0.nx) w = g0.nx;
+      if (w > g0.ny) w = g0.ny;
+      if (w < 2 * c) FAIL(MSQG_ERR_ARG, "tiles of level %d are too small for %d fused sweeps (raise agg_n)", l, c);
+      std::vector<XItem> items(1);
+      for (msqg_model *m : G->tiles) { items[0].arr.push_back(m->da.lev[l]); items[0].geo.push_back(m->g[l]); }
+      items[0].nf = nl; items[0].w = w; items[0].ring = 0;
+      if ((rc = exchange_multi(G, items))) return rc;
+      if (c != chunk0 && left != nrelax) { /* later chunks need the halo of res again only if it was thinner: it never is */ }
+      for (msqg_model *m : G->tiles) {
+        ProfScope ps(m, l == D ? PROF_RELAX_FINE : PROF_RELAX_COARSE, c);
+        NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = relax_rb_tile<NL>(m, l, c, w, C); });
+        if (rc) return rc;
+      }
+      left -= c;
+    }
+  }
+  /* a += da ; boundary(a) */
+  for (msqg_model *m : G->tiles) {
+    const Geom &g = m->g[D];
+    ProfScope ps(m, PROF_CORRECT, 0);
+    k_correct<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->psi.lev[D], m->da.lev[D], g);
+    m->launches++;
+  }
+  CK(cudaGetLastError());
+  return exchange_one(G, MSQG_PSI, D, 1, 1);
+}

@@ -16,6 +16,7 @@
 
 #define MSQG_OX 16
 #define MSQG_MAXLEV 16
+#define MSQG_FRAME 16 /* frame (deep halo capacity) of the planes of a tile, cells; <= MSQG_OX */
 #define MSQG_NLMAX 12 /* device kernels are instantiated for 1..12 layers */
 
 struct Geom {

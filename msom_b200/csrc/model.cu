@@ -44,8 +44,10 @@ enum { PROF_RELAX_FINE = 0, PROF_RELAX_COARSE, PROF_RESIDUAL, PROF_RESTRICT, PRO
 struct List {
   int nf = 0;
   double sg = -1.;               /* -1 dirichlet(0), +1 symmetry (layer.h:5-35) */
-  double *lev[MSQG_MAXLEV + 1];  /* device pointers per level (only allocated levels non-NULL) */
-  List() { for (auto &p : lev) p = nullptr; }
+  double *lev[MSQG_MAXLEV + 1];  /* device pointers per level (only allocated levels non-NULL): row -1 of plane 0 */
+  double *base[MSQG_MAXLEV + 1]; /* the allocations themselves (tiles carry extra frame rows below row -1, see msqg_model::fy);
+                                    lev[] entries of two lists of the same level may be swapped, base[] entries stay */
+  List() { for (auto &p : lev) p = nullptr; for (auto &p : base) p = nullptr; }
 };
 
 struct msqg_model {
@@ -55,10 +57,17 @@ struct msqg_model {
      as full square grids (agglomerated coarse levels); finest tile is tnx x tny cells at (x0, y0). */
   int px, py, ix, iy, agg_level, tnx, tny, x0, y0;
   bool has_lev[MSQG_MAXLEV + 1];
+  int fy[MSQG_MAXLEV + 1];     /* frame rows around the cells of a plane: 1 (the ghost ring) on undecomposed levels,
+                                  MSQG_FRAME on the levels of a tile, which hold deep halos for the fused red-black sweeps
+                                  (the row pitch then also keeps MSQG_FRAME columns on the right; MSQG_OX covers the left) */
+  int rb_dist;                 /* tile of a red-black group: the levels below agg_level are REPLICATED on every tile */
   Geom gpatch;                 /* level agg_level-1 restricted to this tile (+ halo ring): scatter/gather scratch */
   double *da_patch, *res_patch; /* [nl] planes of gpatch */
   double *halo_send[4], *halo_recv[4], *patch_stage; /* contiguous exchange buffers */
   size_t halo_doubles, patch_doubles;
+  double *xsend[9], *xrecv[9]; /* red-black group: one buffer per neighbour direction (dist_rb.cuh), xcap doubles each */
+  size_t xcap;
+  double *gather_buf;          /* all-gathered blocks of level agg_level-1, [px*py][nl][hy][hx] */
   cudaStream_t stream;
   bool own_stream;
   Geom g[MSQG_MAXLEV + 1];
@@ -222,18 +231,28 @@ extern "C" int msqg_read_params(const char *path, msqg_params *p) {
 }
 
 /* ------------------------------------------------------------------ allocation */
+static int alloc_level(msqg_model *m, List &L, int nf, int l) {
+  /* nf planes of (ny + 2 fy) rows; lev[] points at row -1 of plane 0; one frame of slack at the end so that
+     "nf * plane doubles from lev[]" stays inside the allocation */
+  const size_t off = (size_t)(m->fy[l] - 1) * m->g[l].pitch;
+  const size_t bytes = ((size_t)nf * m->g[l].plane + 2 * off) * sizeof(double);
+  CK(cudaMalloc(&L.base[l], bytes));
+  CK(cudaMemsetAsync(L.base[l], 0, bytes, m->stream));
+  L.lev[l] = L.base[l] + off;
+  return MSQG_OK;
+}
 static int alloc_list(msqg_model *m, List &L, int nf, double sg, int lev_lo, int lev_hi) {
   L.nf = nf; L.sg = sg;
   for (int l = lev_lo; l <= lev_hi; l++) {
     if (!m->has_lev[l]) continue;
-    size_t bytes = (size_t)nf * m->g[l].plane * sizeof(double);
-    CK(cudaMalloc(&L.lev[l], bytes));
-    CK(cudaMemsetAsync(L.lev[l], 0, bytes, m->stream));
+    int rc = alloc_level(m, L, nf, l);
+    if (rc) return rc;
   }
   return MSQG_OK;
 }
 static void free_list(List &L) {
-  for (auto &p : L.lev) { if (p) cudaFree(p); p = nullptr; }
+  for (auto &p : L.base) { if (p) cudaFree(p); p = nullptr; }
+  for (auto &p : L.lev) p = nullptr;
   L.nf = 0;
 }
 
@@ -318,7 +337,7 @@ static void fill_geom_consts(Geom &g, double Delta) {
 }
 
 static int create_model(const msqg_params *p, int device, int px, int py, int ix, int iy, int agg_n, cudaStream_t shared,
-                        msqg_model **out) {
+                        msqg_model **out, int rb_dist = 0) {
   *out = nullptr;
   if (p->nl < 2 || p->nl > MSQG_NLMAX) FAIL(MSQG_ERR_ARG, "nl must be in [2,%d] (nl==1 is not functional in the reference)", MSQG_NLMAX);
   if (p->N < 8 || (p->N & (p->N - 1))) FAIL(MSQG_ERR_ARG, "N must be a power of two >= 8");
@@ -346,12 +365,15 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   }
   m->px = px; m->py = py; m->ix = ix; m->iy = iy;
   m->agg_level = 0;
+  m->rb_dist = (px * py > 1) ? rb_dist : 0;
   if (px * py > 1 && p->sbc > 0) { msqg_destroy(m); FAIL(MSQG_ERR_ARG, "partial slip (sbc > 0) is not supported on decomposed grids"); }
   if (px * py > 1) {
     int la = 1;
     while ((1 << la) < agg_n) la++;
     if (la > depth) FAIL(MSQG_ERR_ARG, "agglomeration threshold %d exceeds N", agg_n);
     if (((1 << la) / px) < 8 || ((1 << la) / py) < 8) FAIL(MSQG_ERR_ARG, "tiles must keep >= 8 cells per side on every distributed level (raise agg_n)");
+    if (rb_dist && (((1 << la) / px) < MSQG_FRAME || ((1 << la) / py) < MSQG_FRAME))
+      FAIL(MSQG_ERR_ARG, "red-black tiles must keep >= %d cells per side on every distributed level (raise agg_n)", MSQG_FRAME);
     if (la < 2) FAIL(MSQG_ERR_ARG, "agg_n too small");
     m->agg_level = la;
   }
@@ -362,17 +384,23 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
       g.nx = (1 << l) / px; g.ny = (1 << l) / py;
       g.bc = (ix > 0 ? 1 : 0) | (ix < px - 1 ? 2 : 0) | (iy > 0 ? 4 : 0) | (iy < py - 1 ? 8 : 0);
       m->has_lev[l] = true;
+      m->fy[l] = MSQG_FRAME;
+      g.pitch = ((g.nx + MSQG_OX + MSQG_FRAME + 15) / 16) * 16;
     } else {
       g.nx = g.ny = 1 << l; g.bc = 0;
-      m->has_lev[l] = (ix == 0 && iy == 0);
+      m->has_lev[l] = (ix == 0 && iy == 0) || m->rb_dist; /* a red-black group solves the coarse levels redundantly on every tile */
+      m->fy[l] = 1;
+      g.pitch = msqg_pitch(g.nx);
     }
-    g.pitch = msqg_pitch(g.nx); g.plane = (size_t)(g.ny + 2) * g.pitch;
+    g.plane = (size_t)(g.ny + 2 * m->fy[l]) * g.pitch;
     fill_geom_consts(g, p->L0 / (1 << l));
   }
   m->tnx = m->g[depth].nx; m->tny = m->g[depth].ny;
   m->x0 = ix * m->tnx; m->y0 = iy * m->tny;
   m->da_patch = m->res_patch = m->patch_stage = nullptr;
   for (int k = 0; k < 4; k++) m->halo_send[k] = m->halo_recv[k] = nullptr;
+  for (int k = 0; k < 9; k++) m->xsend[k] = m->xrecv[k] = nullptr;
+  m->gather_buf = nullptr; m->xcap = 0;
   if (shared) { m->stream = shared; m->own_stream = false; }
   else {
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -470,6 +498,16 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
       CK(cudaMalloc(&m->halo_send[k], m->halo_doubles * sizeof(double)));
       CK(cudaMalloc(&m->halo_recv[k], m->halo_doubles * sizeof(double)));
     }
+    if (m->rb_dist) {
+      /* one exchange carries at most: MSQG_FRAME-wide halos of one list on every distributed level (sizes halve per level) */
+      m->xcap = (size_t)nl * MSQG_FRAME * 2 * ((m->tnx > m->tny ? m->tnx : m->tny) + 2 * MSQG_FRAME);
+      for (int k = 0; k < 9; k++) {
+        if (k == 4) continue;
+        CK(cudaMalloc(&m->xsend[k], m->xcap * sizeof(double)));
+        CK(cudaMalloc(&m->xrecv[k], m->xcap * sizeof(double)));
+      }
+      CK(cudaMalloc(&m->gather_buf, (size_t)px * py * nl * gp.nx * gp.ny * sizeof(double)));
+    }
   }
   CK(cudaStreamSynchronize(m->stream));
   *out = m;
@@ -503,6 +541,8 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->res_patch) cudaFree(m->res_patch);
   if (m->patch_stage) cudaFree(m->patch_stage);
   for (int k = 0; k < 4; k++) { if (m->halo_send[k]) cudaFree(m->halo_send[k]); if (m->halo_recv[k]) cudaFree(m->halo_recv[k]); }
+  for (int k = 0; k < 9; k++) { if (m->xsend[k]) cudaFree(m->xsend[k]); if (m->xrecv[k]) cudaFree(m->xrecv[k]); }
+  if (m->gather_buf) cudaFree(m->gather_buf);
   for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
   if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -874,9 +914,8 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
   const int nh = 2 * ns;
   if (da != m->da.lev[lev]) FAIL(MSQG_ERR_ARG, "the rb relax pass works on the model's da list");
   if (!m->da2.lev[lev]) { /* second buffer of the out-of-place pass, allocated on first use */
-    const size_t bytes = (size_t)m->nl * g.plane * sizeof(double);
-    CK(cudaMalloc(&m->da2.lev[lev], bytes));
-    CK(cudaMemsetAsync(m->da2.lev[lev], 0, bytes, m->stream));
+    int rc = alloc_level(m, m->da2, m->nl, lev);
+    if (rc) return rc;
     m->da2.nf = m->nl;
   }
   RbArgs A;

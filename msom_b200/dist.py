@@ -1,5 +1,10 @@
 """2-D domain decomposition of the msqg timestep (include/msqg.h layer 1b).
 
+smoother="rb" (throughput mode): red-black sweeps are decomposition independent, so the group reproduces the
+single-GPU red-black result bit for bit on any px x py; levels below `agg_n` are replicated on every GPU
+(all-gather + redundant coarse solve) and each distributed level needs one deep-halo exchange per cycle.
+smoother="lex" is the first-round decomposition of the reference-order sweep (block Gauss-Seidel, rank-0 coarse levels).
+
 `Group(params, px, py, agg_n)` is the reference built with -D_MPI=1: px x py tiles, halo exchange
 after every relaxation sweep, coarse levels below `agg_n` agglomerated on tile (0,0).
 
@@ -27,6 +32,10 @@ def _bind():
     L.msqg_group_create_local.argtypes = [C.POINTER(G.Params), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.msqg_group_create_nccl.argtypes = [C.POINTER(G.Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_char_p, C.POINTER(vp)]
+    L.msqg_group_create_local_sm.argtypes = [C.POINTER(G.Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.msqg_group_create_nccl_sm.argtypes = [C.POINTER(G.Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_char_p, C.POINTER(vp)]
+    L.msqg_group_smoother.argtypes = [vp]
     L.msqg_group_destroy.argtypes = [vp]
     L.msqg_group_ntiles.argtypes = [vp]
     L.msqg_group_tile.argtypes = [vp, C.c_int]
@@ -62,15 +71,17 @@ def tile_box(N, px, py, rank):
 
 
 class Group:
-    def __init__(self, params, px, py, agg_n, device=0, backend="local", rank=0, nranks=1, uid=None):
+    def __init__(self, params, px, py, agg_n, device=0, backend="local", rank=0, nranks=1, uid=None, smoother="lex"):
         self.L = _bind()
         self.p, self.px, self.py, self.agg_n = params, px, py, agg_n
         self.N, self.nl = params.N, params.nl
         h = C.c_void_p()
+        sm = {"lex": 0, "rb": 1}[smoother]
         if backend == "local":
-            G.check(self.L.msqg_group_create_local(C.byref(params), device, px, py, agg_n, C.byref(h)))
+            G.check(self.L.msqg_group_create_local_sm(C.byref(params), device, px, py, agg_n, sm, C.byref(h)))
         else:
-            G.check(self.L.msqg_group_create_nccl(C.byref(params), device, px, py, agg_n, rank, nranks, uid, C.byref(h)))
+            G.check(self.L.msqg_group_create_nccl_sm(C.byref(params), device, px, py, agg_n, sm, rank, nranks, uid, C.byref(h)))
+        self.smoother = smoother
         self.h = h
         self.t = 0.0
         self.ntiles = self.L.msqg_group_ntiles(self.h)
@@ -173,7 +184,7 @@ def broadcast_bytes(payload, nbytes, device=None):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def nccl_group(params, agg_n, device):
+def nccl_group(params, agg_n, device, smoother="lex"):
     """One tile per rank of the default torch.distributed process group (torch only carries the NCCL id)."""
     import torch.distributed as dist
     L = _bind()
@@ -183,4 +194,4 @@ def nccl_group(params, agg_n, device):
     if rank == 0:
         G.check(L.msqg_nccl_unique_id(buf))
     uid = broadcast_bytes(buf.raw, 128, device)
-    return Group(params, px, py, agg_n, device, "nccl", rank, world, uid)
+    return Group(params, px, py, agg_n, device, "nccl", rank, world, uid, smoother=smoother)

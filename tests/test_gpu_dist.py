@@ -59,3 +59,54 @@ def test_decomposition_differs_from_serial_only_at_solver_tolerance(gpu):
     a, b = s.get(G.PSI), g.get_global(G.PSI)
     assert not np.array_equal(a, b)
     assert np.abs(a - b).max() < 1e-3 * np.abs(a).max()
+
+
+@pytest.mark.parametrize("N,nl,px,py,agg_n", [(128, 2, 2, 1, 64), (128, 3, 2, 2, 64), (256, 2, 4, 2, 128), (256, 4, 1, 2, 64),
+                                               (512, 4, 4, 2, 256)])
+def test_red_black_group_equals_single_gpu_and_oracle(gpu, N, nl, px, py, agg_n):
+    """Throughput mode on tiles: a red-black half-sweep does not depend on the decomposition, so the group (deep halos,
+    one exchange per level, replicated coarse levels) must give the bits of the undecomposed solve and of the oracle
+    running the same ordering -- including cold-start solves whose nrelax adapts upwards (several relax passes)."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    from msom_b200.dist import Group
+    kw = base_kw(N, nl)
+    psi = synth_psi(N, nl)
+    mo = O.Model(O.make_params(**kw)); mo.set_smoother("rb")
+    s = G.Model(G.make_params(**kw), gpu); s.set_smoother("rb")
+    g = Group(G.make_params(**kw), px, py, agg_n, gpu, smoother="rb")
+    mo.set(O.PSI, psi); s.set(G.PSI, psi); g.set_global(G.PSI, psi)
+    mo.set_const(); s.set_const(); g.set_const()
+    assert np.array_equal(g.get_global(G.Q), mo.get(O.Q))
+    z = np.zeros_like(psi)
+    mo.set(O.PSI, z); s.set(G.PSI, z); g.set_global(G.PSI, z)
+    mo.invertq(); s.invertq(); g.invertq()
+    so, ss, sg = mo.mgstats(), s.mgstats(), g.mgstats()
+    assert (sg.i, sg.nrelax, sg.resb, sg.resa) == (so.i, so.nrelax, so.resb, so.resa) == (ss.i, ss.nrelax, ss.resb, ss.resa)
+    assert np.array_equal(g.get_global(G.PSI), s.get(G.PSI))
+    assert np.array_equal(g.get_global(G.PSI), mo.get(O.PSI))
+    for _ in range(3):
+        dt = g.step()
+        assert dt == s.step() == mo.step()
+    assert g.total_cycles == s.total_cycles == mo.L.orc_total_cycles(mo.h)
+    for f, fo in ((G.Q, O.Q), (G.PSI, O.PSI)):
+        assert np.array_equal(g.get_global(f), s.get(f))
+        assert np.array_equal(g.get_global(f), mo.get(fo))
+    assert g.exchanges > 0
+
+
+def test_nccl_backend_two_gpus(gpu):
+    """the NCCL back-end (one tile per process) under torchrun on 2 GPUs, both smoothers, bit-exact against the oracle;
+    skipped on a single-GPU box"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for sm in ("rb", "lex"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "dist_check.py"), sm],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
