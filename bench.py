@@ -43,6 +43,11 @@ def workload_psi(N, nl):
     return synth_psi(N, nl)
 
 
+def workload_name(N, nl):
+    return "msqg double-gyre %d^2 x nl=%d, %s, tolerance 1e-3" % (
+        N, nl, "vertical-mode inversion (MODE_PV_INVERT 1)" if MODAL else "layer-coupled multigrid inversion (MODE_PV_INVERT 0)")
+
+
 def algorithmic_bytes(nl):
     """bytes per cell-layer of each piece (F = 8 B, sigma = (nl-1)/nl)."""
     sig = (nl - 1.0) / nl
@@ -101,13 +106,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_run(N, nl, steps, warmup):
+def cpu_oracle_run(N, nl, steps, warmup, smoother="lex"):
     """The CPU oracle built with OpenMP (same algorithm and loop order as the reference,
     foreach() as an omp-for like `qcc -fopenmp`), on all host cores."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     m = O.Model(O.make_params(omp=True, **workload_kw(N, nl)), omp=True)
+    m.set_smoother(smoother)
     m.set(O.PSI, workload_psi(N, nl))
     m.set_const()
     for _ in range(warmup):
@@ -130,15 +136,20 @@ def run_reference(args):
     # and is meant to use every host core, so that default is undone here (an explicit user setting > 1 is kept)
     if os.environ.get("OMP_NUM_THREADS", "1") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
         os.environ["OMP_NUM_THREADS"] = str(cores)
-    Ns = 2048 if cores >= 32 else 1024
-    val, ms, threads, _ = cpu_oracle_run(Ns, args.nl, args.steps, args.warmup)
-    sample = ("%d^2 x nl=%d grid with the parameters of the %d^2 workload (metric is per cell-layer); "
-              "%d steps after %d warm-up" % (Ns, args.nl, args.N, args.steps, args.warmup))
+    # the SAME configuration as our arm: the full args.N^2 x nl grid (4096^2 x 4: a few seconds per step on 16+ cores),
+    # the reference's own sweep (lexicographic, foreach() as an omp-for).  Steps are bounded so that the run ends
+    # within a few minutes whatever K the driver passes; the metric is a rate, so fewer steps do not change it.
+    rsteps, rwarm = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    val, ms, threads, _ = cpu_oracle_run(args.N, args.nl, rsteps, rwarm, "lex")
+    sample = ("the full %d^2 x nl=%d workload, %d timed steps after %d warm-up (bounded: the CPU takes seconds per step)"
+              % (args.N, args.nl, rsteps, rwarm))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "msqg double-gyre %d^2 x nl=%d, layer-coupled multigrid inversion" % (args.N, args.nl),
-                       "reference": "CPU oracle (C restatement of msqg, OpenMP; the Basilisk build itself needs qcc, absent here)"},
+            "config": {"workload": workload_name(args.N, args.nl), "N": args.N, "nl": args.nl,
+                       "timed_steps": rsteps,
+                       "reference": "CPU oracle (C restatement of msqg with the reference's lexicographic sweep, OpenMP; "
+                                    "the Basilisk build itself needs qcc, absent here)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -163,7 +174,6 @@ def run_ours(args):
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, nl = args.N, args.nl
     cells = float(N) * N * nl
@@ -181,8 +191,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sm = args.smoother
     if world == 1:
         m = G.Model(G.make_params(**workload_kw(N, nl)), local)
+        m.set_smoother(sm)
         stream = torch.cuda.Stream(device=local)
         m.set_stream(stream.cuda_stream)
         m.set(G.PSI, workload_psi(N, nl))
@@ -190,15 +202,19 @@ def run_ours(args):
         step = m.step
         parallelism = "1 GPU"
     else:
-        # strong scaling: the SAME 4096^2 x 4 grid cut into px x py tiles, one per GPU (reference -D_MPI=1
-        # semantics: Gauss-Seidel inside the tile, NCCL halo exchange after every sweep, coarse levels
-        # below agg_n agglomerated on rank 0)
+        # strong scaling: the SAME N^2 x nl grid cut into px x py tiles, one per GPU.  rb: deep-halo exchange once per
+        # level and cycle (grouped ncclSend/ncclRecv to the 8 neighbours), levels below agg_n replicated on every GPU
+        # (ncclAllGather of the restricted residual); results identical to the 1-GPU run bit for bit.
         from msom_b200.dist import nccl_group
-        m = nccl_group(G.make_params(**workload_kw(N, nl)), args.agg_n, local)
+        m = nccl_group(G.make_params(**workload_kw(N, nl)), args.agg_n, local, smoother=sm)
         m.set_global(G.PSI, workload_psi(N, nl))
         m.set_const()
         step = m.step
-        parallelism = "%dx%d tiles, NCCL halo exchange, levels < %d agglomerated on rank 0" % (m.px, m.py, args.agg_n)
+        if sm == "rb":
+            parallelism = ("%dx%d tiles, one deep-halo NCCL exchange per level and cycle, levels < %d replicated on every GPU"
+                           % (m.px, m.py, args.agg_n))
+        else:
+            parallelism = "%dx%d tiles, NCCL halo exchange per sweep, levels < %d agglomerated on rank 0" % (m.px, m.py, args.agg_n)
 
     for _ in range(args.warmup):
         step()
@@ -271,16 +287,26 @@ def run_ours(args):
         if MODAL:  # one launch relaxes ONE vertical mode: scalar Helmholtz sweep, R da, res; W da on N^2 cells
             alg_bytes_per_launch = 3 * 8.0 * tile_cells / nl * (rf["aux"] / rf["count"])
         ach = alg_bytes_per_launch / (rf["ms"] / rf["count"] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one finest-level launch at 4096^2 x 4 from the ncu --set full
-        # capture in profiles/ncu_r01/relax.raw.csv (1.143 GB + 0.559 GB; independent of the number of fused sweeps)
-        traffic = 1.702e9 * tile_cells / (4096.0 * 4096 * 4) if nl == 4 else None
-        roof = {"bound": "hbm", "kernel": "k_relax_ws (finest level)", "achieved": ach, "peak": peak, "unit": "GB/s",
+        if sm == "rb":
+            # dram__bytes_read.sum + dram__bytes_write.sum of one finest-level k_relax_rb launch (4 fused sweeps) at
+            # 4096^2 x 4 from the ncu --set full capture profiles/ncu_r02/relax_rb.raw.csv (1.098 GB + 0.508 GB:
+            # da and res read once with 128/112 halo redundancy, da written once, whatever the number of fused sweeps)
+            traffic = 1.606e9 * tile_cells / (4096.0 * 4096 * 4) if nl == 4 else None
+            kname = "k_relax_rb (finest level)"
+            note = ("temporally blocked red-black sweeps: the fused sweeps of a launch are ONE pass over HBM, so the achieved rate "
+                    "on pass-count algorithmic bytes may exceed the HBM peak; the kernel is bound by shared-memory bandwidth "
+                    "and the fp64 pipe, not by DRAM")
+        else:
+            # profiles/ncu_r01/relax.raw.csv (1.143 GB + 0.559 GB; independent of the number of fused sweeps)
+            traffic = 1.702e9 * tile_cells / (4096.0 * 4096 * 4) if nl == 4 else None
+            kname = "k_relax_ws (finest level)"
+            note = ("latency-bound wavefront (exact reference sweep order): the fused sweeps of a launch are ONE HBM pass, "
+                    "so DRAM traffic is below the pass-count algorithmic bytes")
+        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": rf["ms"] / rf["count"], "sweeps_per_launch": rf["aux"] / rf["count"],
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "share_of_step": rf["ms"] / ms_total,
-                "note": "latency-bound wavefront (exact reference sweep order): the fused sweeps of a launch are ONE HBM pass, "
-                        "so DRAM traffic is below the pass-count algorithmic bytes"}
+                "share_of_step": rf["ms"] / ms_total, "note": note}
     kern_ms = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}
     # whole-step algorithmic bytes with the measured cycle counts
     sweeps_all = prof["relax_fine"]["aux"]  # every level does the same number of sweeps per cycle
@@ -296,30 +322,64 @@ def run_ours(args):
         vcycle_ms = (prof["relax_fine"]["ms"] + prof["relax_coarse"]["ms"] + prof["restrict"]["ms"] + prof["prolong"]["ms"] +
                      prof["correct"]["ms"] + (res["ms"] / res["count"] * cycles if res["count"] else 0.)) / cycles
 
+    # ---- the other smoother on the same workload (1 GPU): the parity path (reference sweep order) next to the
+    # throughput path; 3 timed steps after 2 warm-up, same event timing
+    other = None
+    if world == 1 and not args.no_other:
+        osm = "lex" if sm == "rb" else "rb"
+        try:
+            m2 = G.Model(G.make_params(**workload_kw(N, nl)), local)
+            m2.set_smoother(osm)
+            m2.set_stream(stream.cuda_stream)
+            m2.set(G.PSI, workload_psi(N, nl))
+            m2.set_const()
+            for _ in range(3):
+                m2.step()
+            c2 = m2.total_cycles
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                f0.record(stream)
+                for _ in range(3):
+                    m2.step()
+                f1.record(stream)
+            f1.synchronize()
+            oms = f0.elapsed_time(f1) / 3
+            other = {"smoother": osm, "ms_per_step": oms, "value": cells / (oms * 1e-3), "unit": UNIT,
+                     "mg_cycles_per_step": (m2.total_cycles - c2) / 3.0, "steps": 3}
+            m2.close()
+        except Exception as ex:
+            other = {"smoother": osm, "error": repr(ex)}
+
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            Ns = 2048 if (os.cpu_count() or 1) >= 8 else 1024
-            cv, cms, threads, _ = cpu_oracle_run(Ns, nl, 3, 1)
+            # the reference-order OpenMP port on the FULL workload (same N, nl): 2 timed steps after 1 warm-up
+            cv, cms, threads, _ = cpu_oracle_run(N, nl, 2, 1, "lex")
             cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "%d^2 x nl=%d grid, same parameters, 3 steps after 1 warm-up (metric is per cell-layer)" % (Ns, nl),
+                   "sample": "the full %d^2 x nl=%d workload, 2 timed steps after 1 warm-up" % (N, nl),
                    "ms_per_step": cms}
         except Exception as ex:  # the baseline is a report, never a gate
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
+    this_mode = {"smoother": sm, "ms_per_step": ms_step, "value": value, "unit": UNIT, "roofline": roof,
+                 "mg_cycles_per_step": cycles / args.steps}
+    smoother_doc = ("rb = red-black ordering of the reference's relax_layer cell update (throughput mode; bit-exact against the "
+                    "oracle with the same ordering, identical results on 1..8 GPUs; the reference documents its own sweep as "
+                    "order/OpenMP/MPI dependent, poisson_layer.h:55-65); lex = the reference's serial sweep order (parity path)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "msqg double-gyre %d^2 x nl=%d, %s, tolerance 1e-3, reference-order Gauss-Seidel" % (
-                N, nl, "vertical-mode inversion (MODE_PV_INVERT 1)" if MODAL else "layer-coupled multigrid inversion (MODE_PV_INVERT 0)"),
-                       "N": N, "nl": nl, "parallelism": parallelism,
+            "config": {"workload": workload_name(N, nl), "N": N, "nl": nl, "smoother": sm, "smoothers": smoother_doc,
+                       "parallelism": parallelism,
                        "l2": "inputs larger than L2 (each layer list is %.0f MB)" % (cells * 8 / 1e6),
                        "mg_cycles_per_step": cycles / args.steps},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(tile_cells * 8), "d2h_bytes_per_step": int(tile_cells * 8),
                     "steps": esteps, "ms_per_step": e2e_s / esteps * 1e3},
             "roofline": roof, "cpu_baseline": cpu,
+            ("fast_mode" if sm == "rb" else "parity_mode"): this_mode,
+            ("parity_mode" if sm == "rb" else "fast_mode"): other,
             "kernel_ms_per_step": kern_ms, "vcycle_ms": vcycle_ms,
             "step_roofline": {"algorithmic_bytes_per_cell_layer_per_step": step_bytes / cells, "achieved": step_roof,
                               "peak": peak, "unit": "GB/s", "frac": step_roof / peak}}
@@ -338,15 +398,18 @@ def main():
     ap.add_argument("--N", type=int, default=N_DEFAULT)
     ap.add_argument("--nl", type=int, default=NL_DEFAULT)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the leg that times the other smoother (1 GPU)")
+    ap.add_argument("--smoother", default="rb", choices=["rb", "lex"],
+                    help="rb (default): red-black ordering of the relaxation sweep, the throughput mode, same result on any "
+                         "number of GPUs; lex: the reference's serial sweep order (parity path; does not scale)")
     ap.add_argument("--modal", action="store_true",
                     help="vertical-mode inversion (MODE_PV_INVERT 1, eigmode.h; BASELINE config 3) instead of the layer-coupled solver")
     ap.add_argument("--agg-n", type=int, default=0, dest="agg_n",
-                    help="multi-GPU: levels with fewer than agg_n cells per side are agglomerated on rank 0 (default: N, i.e. "
-                         "only the finest level is swept tile by tile -- measured fastest on B200: an agglomerated level runs "
-                         "its nrelax sweeps as ONE fused wavefront, a distributed level needs one launch + halo exchange per sweep)")
+                    help="multi-GPU: levels with fewer than agg_n cells per side are not distributed (rb: replicated on every "
+                         "GPU, default 512; lex: agglomerated on rank 0, default N)")
     args = ap.parse_args()
     if args.agg_n <= 0:
-        args.agg_n = args.N
+        args.agg_n = args.N if args.smoother == "lex" else min(512, args.N)
     global MODAL
     MODAL = bool(args.modal)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
