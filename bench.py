@@ -64,15 +64,54 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread (every 5 ms; a step is ~10-20 ms),
+    nvidia-smi as a fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv = index, [], None, None
+        self.sm, self.reasons, self.mx, self.stop_flag = [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[index])
+                except Exception:
+                    idx = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _nvml_loop(self):
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -87,6 +126,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,7 +147,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_oracle_run(N, nl, steps, warmup, smoother="lex"):

@@ -218,21 +218,7 @@ static int g_cycle_rb(msqg_group *G, int nrelax) {
   for (msqg_model *m : G->tiles) {
     k_place_all<<<grid2(hx, hy, b, nranks * nl), b, 0, G->stream>>>(m->res.lev[La - 1], m->g[La - 1], m->gather_buf, hx, hy, G->px, nranks, nl);
     m->launches++;
-    for (int l = La - 2; l >= 1; l--) {
-      k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, G->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
-      m->launches++;
-    }
-    for (int l = 1; l <= La - 1; l++) {
-      const Geom &g = m->g[l];
-      if (l == 1) CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)nl * g.plane * sizeof(double), G->stream));
-      else {
-        launch_prolong(G->stream, nl, m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
-        m->launches++;
-      }
-      ProfScope ps(m, PROF_RELAX_COARSE, nrelax);
-      NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C); });
-      if (rc) return rc;
-    }
+    if ((rc = mg_levels(m, nl, -1, nrelax, La - 1, La - 1))) return rc;
     /* this tile's block of level La-1 plus a one-cell ring (homogeneous dirichlet ghosts evaluated on the fly) */
     k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da.lev[La - 1], m->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy);
     k_load_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da_patch, m->gpatch, m->patch_stage);

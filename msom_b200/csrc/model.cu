@@ -985,6 +985,43 @@ static int launch_relax_rb(msqg_model *m, double *da, const double *res, int lev
   return MSQG_OK;
 }
 
+/* levels 1 .. Lc of a red-black cycle in one launch (k_coarse_rb): res[Lc] -> da[Lc].  Lc is chosen so that da and res
+ * of all those levels fit in shared memory; 0 = not applicable (lexicographic smoother, varying stretching, tiny grids) */
+static int coarse_top_level(msqg_model *m, int nf_problem, int maxlevel) {
+  if (m->smoother != 1) return 0;
+  if (nf_problem > 1 && !m->s_uniform) return 0;
+  { const char *e = getenv("MSQG_RB_COARSE"); if (e && atoi(e) == 0) return 0; } /* A/B: level-by-level launches */
+  int Lc = RB_COARSE_MAXLEV;
+  if (Lc > maxlevel) Lc = maxlevel;
+  while (Lc >= 2) {
+    size_t cells = 0;
+    for (int l = 1; l <= Lc; l++) cells += (size_t)1 << (2 * l);
+    if (2 * (size_t)nf_problem * cells * sizeof(double) <= 200 * 1024) break;
+    Lc--;
+  }
+  return Lc >= 2 ? Lc : 0;
+}
+template <int NL>
+static int launch_coarse_rb(msqg_model *m, int Lc, int nrelax, const CoarseCoef<NL> &CC) {
+  CoarseArgs A;
+  A.res = m->res.lev[Lc]; A.da = m->da.lev[Lc]; A.g = m->g[Lc]; A.Lc = Lc; A.nrelax = nrelax;
+  size_t cells = 0;
+  for (int l = 1; l <= Lc; l++) cells += (size_t)1 << (2 * l);
+  const size_t smem = 2 * (size_t)NL * cells * sizeof(double);
+  auto kern = k_coarse_rb<NL>;
+  static KernelDevState st;
+  const int dev = m->device & 63;
+  if (!st.set[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    st.set[dev] = true;
+  }
+  CoarseCoef<NL> Cc = CC;
+  kern<<<1, 512, smem, m->stream>>>(A, Cc);
+  m->launches++;
+  CK(cudaGetLastError());
+  return MSQG_OK;
+}
+
 #define NL_CASE(n, ...) case n: { constexpr int NL = n; __VA_ARGS__; } break;
 #define NL_SWITCH(nl, ...)                                  \
   switch (nl) {                                             \
@@ -1072,37 +1109,66 @@ static int mg_corr_residual(msqg_model *m, const MgProblem &P, const double *da,
 
 /* mg_cycle, mspg/elliptic.h:43-99 with minlevel = 1 (poisson_layer.h:297).  fused: the residual kernel has already
  * restricted res to level D-1 and the correction a += da is left to the next residual (mg_corr_residual). */
-static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax, int fused = 0) {
-  const int D = m->depth;
+/* restriction of res from level `from` down to level 1, then the up-leg of the cycle on levels 1 .. top (da = 0 on
+ * level 1, bilinear prolongation, nrelax sweeps).  With the red-black smoother the levels up to 32^2 run as ONE launch
+ * (k_coarse_rb), which also does their restrictions. */
+static int mg_levels(msqg_model *m, int nf, int mode, int nrelax, int from, int top) {
   dim3 b(32, 8);
-  /* restriction(res): levels D-1..1 (level 0 is never read with minlevel = 1) */
-  for (int l = fused ? D - 2 : D - 1; l >= 1; l--) {
+  const int D = m->depth;
+  const int Lc = coarse_top_level(m, nf, top < D ? top : D - 1);
+  for (int l = from - 1; l >= (Lc ? Lc : 1); l--) {
     ProfScope ps(m, PROF_RESTRICT, l);
-    k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, P.nf), b, 0, m->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
+    k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nf), b, 0, m->stream>>>(m->res.lev[l + 1], m->res.lev[l], m->g[l + 1], m->g[l], -1., 0);
     m->launches++;
   }
   CK(cudaGetLastError());
-  const int minlevel = D < 1 ? D : 1;
-  for (int l = minlevel; l <= D; l++) {
+  int rc = MSQG_OK;
+  if (Lc) {
+    ProfScope ps(m, PROF_RELAX_COARSE, nrelax);
+    if (mode < 0) {
+      NL_SWITCH(m->nl, {
+        CoarseCoef<NL> CC;
+        for (int l = 1; l <= Lc; l++) CC.c[l] = relax_coef_layers<NL>(m, l);
+        CC.c[0] = CC.c[1];
+        rc = launch_coarse_rb<NL>(m, Lc, nrelax, CC);
+      });
+    } else {
+      CoarseCoef<1> CC;
+      for (int l = 1; l <= Lc; l++) CC.c[l] = relax_coef_scalar(m, l, m->lam_lev[(size_t)l * m->nl + mode]);
+      CC.c[0] = CC.c[1];
+      rc = launch_coarse_rb<1>(m, Lc, nrelax, CC);
+    }
+    if (rc) return rc;
+  }
+  const int minlevel = top < 1 ? top : 1;
+  for (int l = Lc ? Lc + 1 : minlevel; l <= top; l++) {
     const Geom &g = m->g[l];
     if (l == minlevel) { /* da = 0 on the coarsest level */
-      CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)P.nf * g.plane * sizeof(double), m->stream));
+      CK(cudaMemsetAsync(m->da.lev[l], 0, (size_t)nf * g.plane * sizeof(double), m->stream));
     } else {
       ProfScope ps(m, PROF_PROLONG, l);
-      launch_prolong(m->stream, P.nf, m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
+      launch_prolong(m->stream, nf, m->da.lev[l - 1], m->da.lev[l], m->g[l - 1], g);
       m->launches++;
       CK(cudaGetLastError());
     }
-    int rc;
     ProfScope ps(m, l == D ? PROF_RELAX_FINE : PROF_RELAX_COARSE, nrelax);
-    if (P.mode < 0) {
+    if (mode < 0) {
       NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C); });
     } else {
-      auto C = relax_coef_scalar(m, l, m->lam_lev[(size_t)l * m->nl + P.mode]);
+      auto C = relax_coef_scalar(m, l, m->lam_lev[(size_t)l * m->nl + mode]);
       rc = launch_relax<1>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C);
     }
     if (rc) return rc;
   }
+  return MSQG_OK;
+}
+
+static int mg_cycle(msqg_model *m, const MgProblem &P, int nrelax, int fused = 0) {
+  const int D = m->depth;
+  dim3 b(32, 8);
+  /* restriction(res): levels D-1..1 (level 0 is never read with minlevel = 1), then levels 1 .. D */
+  int rc = mg_levels(m, P.nf, P.mode, nrelax, fused ? D - 1 : D, D);
+  if (rc) return rc;
   if (fused == 2) return MSQG_OK;
   const Geom &g = m->g[D];
   { ProfScope ps(m, PROF_CORRECT, 0);

@@ -289,3 +289,117 @@ k_relax_rb(RbArgs A, RelaxCoef<NL> C) {
   }
   cp_async_wait<0>();
 }
+
+/* ------------------------------------------------------------------ the coarsest levels in ONE launch
+ * Levels 1 .. Lc (2 x 2 .. 32 x 32 cells) hold 0.01 % of the cells of a 4096^2 hierarchy but cost a dozen latency-bound
+ * launches per cycle when swept one by one.  One CTA keeps da and res of all of them in shared memory and runs the
+ * cycle's coarse end by itself ([BASILISK] mg_cycle, in-tree copy mspg/elliptic.h:43-99, with red-black sweeps):
+ *     res[l] = restriction(res[l+1])                 l = Lc-1 .. 1     (restriction_average, same summation order)
+ *     da[1] = 0;  da[l] = bilinear(da[l-1])          l = 2 .. Lc       (same expression as k_prolong4)
+ *     nrelax x { red half-sweep ; black half-sweep } on every level    (same cell update as k_relax_rb)
+ * Input: res on level Lc (global memory); output: da on level Lc.  Bit-identical to the level-by-level kernels. */
+#define RB_COARSE_MAXLEV 5
+template <int NL>
+struct CoarseCoef { RelaxCoef<NL> c[RB_COARSE_MAXLEV + 1]; }; /* index = level */
+struct CoarseArgs {
+  const double *res; /* level Lc, [NL] planes */
+  double *da;        /* level Lc, [NL] planes */
+  Geom g;            /* geometry of level Lc (undecomposed) */
+  int Lc, nrelax;
+};
+template <int NL>
+__device__ __forceinline__ size_t coarse_smem_doubles(int Lc) {
+  size_t cells = 0;
+  for (int l = 1; l <= Lc; l++) cells += (size_t)1 << (2 * l);
+  return 2 * (size_t)NL * cells;
+}
+template <int NL>
+__global__ void __launch_bounds__(512)
+k_coarse_rb(CoarseArgs A, CoarseCoef<NL> CC) {
+  extern __shared__ double csm[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int Lc = A.Lc;
+  /* level l: da at base[l], res right behind it; planes [NL][n][n] without ghosts */
+  int base[RB_COARSE_MAXLEV + 2];
+  {
+    int o = 0;
+    for (int l = 1; l <= Lc; l++) { base[l] = o; o += 2 * NL * (1 << (2 * l)); }
+  }
+  auto DA = [&](int l, int f, int y, int x) -> double & { const int n = 1 << l; return csm[base[l] + (f * n + y) * n + x]; };
+  auto RS = [&](int l, int f, int y, int x) -> double & { const int n = 1 << l; return csm[base[l] + NL * n * n + (f * n + y) * n + x]; };
+  { /* res of level Lc from global memory */
+    const int n = 1 << Lc;
+    for (int e = tid; e < NL * n * n; e += nt) {
+      const int f = e / (n * n), y = (e / n) % n, x = e % n;
+      RS(Lc, f, y, x) = A.res[(size_t)f * A.g.plane + GIDX(A.g.pitch, y, x)];
+    }
+  }
+  __syncthreads();
+  for (int l = Lc - 1; l >= 1; l--) { /* restriction_average: children (0,0), (0,1) [y+1], (1,0) [x+1], (1,1), then /4 */
+    const int n = 1 << l;
+    for (int e = tid; e < NL * n * n; e += nt) {
+      const int f = e / (n * n), y = (e / n) % n, x = e % n;
+      double sum = 0.;
+      sum += RS(l + 1, f, 2 * y, 2 * x);
+      sum += RS(l + 1, f, 2 * y + 1, 2 * x);
+      sum += RS(l + 1, f, 2 * y, 2 * x + 1);
+      sum += RS(l + 1, f, 2 * y + 1, 2 * x + 1);
+      RS(l, f, y, x) = sum / 4;
+    }
+    __syncthreads();
+  }
+  for (int l = 1; l <= Lc; l++) {
+    const int n = 1 << l;
+    if (l == 1) {
+      for (int e = tid; e < NL * n * n; e += nt) csm[base[1] + e] = 0.;
+    } else { /* bilinear: (9 C + 3 (C[cx,0] + C[0,cy]) + C[cx,cy]) / 16, homogeneous dirichlet ghosts by reflection */
+      const int nc = n >> 1;
+      for (int e = tid; e < NL * n * n; e += nt) {
+        const int f = e / (n * n), y = (e / n) % n, x = e % n;
+        const int xc = x >> 1, yc = y >> 1, ix = (x & 1) ? 1 : -1, iy = (y & 1) ? 1 : -1;
+        auto cat = [&](int xx, int yy) {
+          double s = 1.;
+          if (xx < 0) { xx = 0; s = -s; } else if (xx >= nc) { xx = nc - 1; s = -s; }
+          if (yy < 0) { yy = 0; s = -s; } else if (yy >= nc) { yy = nc - 1; s = -s; }
+          return s * DA(l - 1, f, yy, xx);
+        };
+        DA(l, f, y, x) = (9. * cat(xc, yc) + 3. * (cat(xc + ix, yc) + cat(xc, yc + iy)) + cat(xc + ix, yc + iy)) / 16.;
+      }
+    }
+    __syncthreads();
+    const RelaxCoef<NL> &C = CC.c[l];
+    const int half = n >> 1; /* cells of one colour per row */
+    for (int hs = 0; hs < 2 * A.nrelax; hs++) {
+      const int colour = hs & 1;
+      for (int e = tid; e < n * half; e += nt) {
+        const int y = e / half, x = 2 * (e % half) + ((y + colour) & 1);
+        double rhs[NL], out[NL];
+#pragma unroll
+        for (int f = 0; f < NL; f++) {
+          const double c0 = DA(l, f, y, x), gh = -c0;
+          const double aw = x > 0 ? DA(l, f, y, x - 1) : gh, ae = x < n - 1 ? DA(l, f, y, x + 1) : gh;
+          const double as = y > 0 ? DA(l, f, y - 1, x) : gh, an = y < n - 1 ? DA(l, f, y + 1, x) : gh;
+          double rr = C.msd2 * RS(l, f, y, x);
+          rr += ae + aw;
+          rr += an + as;
+          rhs[f] = rr;
+        }
+#pragma unroll
+        for (int f = 1; f < NL; f++) rhs[f] -= div_by(C.t0[f] * rhs[f - 1], C.t1p[f - 1], C.rinv[f - 1]);
+        out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
+#pragma unroll
+        for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - C.t2[f] * out[f + 1], C.t1p[f], C.rinv[f]);
+#pragma unroll
+        for (int f = 0; f < NL; f++) DA(l, f, y, x) = out[f];
+      }
+      __syncthreads();
+    }
+  }
+  { /* da of level Lc to global memory */
+    const int n = 1 << Lc;
+    for (int e = tid; e < NL * n * n; e += nt) {
+      const int f = e / (n * n), y = (e / n) % n, x = e % n;
+      A.da[(size_t)f * A.g.plane + GIDX(A.g.pitch, y, x)] = DA(Lc, f, y, x);
+    }
+  }
+}

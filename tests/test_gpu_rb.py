@@ -153,3 +153,32 @@ def test_modal_rb(gpu):
     assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
     assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+
+
+@pytest.mark.parametrize("N,nl,over", [(256, 4, {}), (128, 3, {"mode_pv_invert": 1}), (64, 10, {}), (16, 2, {})])
+def test_fused_coarse_levels_equal_level_by_level(gpu, N, nl, over, monkeypatch):
+    """k_coarse_rb (levels up to 32^2 in one launch, restrictions and prolongations included) against the
+    level-by-level kernels (MSQG_RB_COARSE=0) and against the oracle: same bits, same cycle counts"""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MSQG_RB_COARSE", flag)
+        mo, mg, psi = make_pair(N, nl, smoother="rb", **over)
+        mo.set_const(); mg.set_const()
+        z = np.zeros_like(psi)
+        mg.set(G.PSI, z)
+        mg.invertq()
+        for _ in range(3):
+            mg.step()
+        res.append((mg.get(G.PSI), mg.get(G.Q), mg.total_cycles, mg.launches))
+        if flag == "1":
+            mo.set(O.PSI, z); mo.invertq()
+            for _ in range(3):
+                mo.step()
+            assert np.array_equal(res[0][0], mo.get(O.PSI)) and np.array_equal(res[0][1], mo.get(O.Q))
+            assert res[0][2] == mo.L.orc_total_cycles(mo.h)
+        mg.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2]
+    assert res[0][3] < res[1][3]      # fewer launches
