@@ -262,12 +262,11 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
-    # ---- timed region: K steps, state resident in HBM, per-launch events on the same stream
+    # ---- timed region: K steps, state resident in HBM (CUDA events on the stream the kernels are launched on)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    m.profile(True)
     c0, l0 = m.total_cycles, m.launches
     if world == 1:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,12 +284,23 @@ def run_ours(args):
         ms_total = m.timer_stop()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    prof = m.profile_read()
-    m.profile(False)
     cycles, launches = m.total_cycles - c0, m.launches - l0
     ms_total = allmax(ms_total)
     ms_step = ms_total / args.steps
     value = N * N * nl * args.steps / (ms_total * 1e-3)
+    # ---- per-kernel device times: a second, untimed pass of the same steps with per-launch events on the same stream
+    # (the library replays recorded CUDA graphs in the timed region; with events between the launches it issues them
+    # one by one, so this pass is slightly slower than the timed one and is used for shares and per-launch times only)
+    psteps = max(1, min(args.steps, 5))
+    m.profile(True)
+    pc0 = m.total_cycles
+    for _ in range(psteps):
+        step()
+    prof = m.profile_read()
+    m.profile(False)
+    pcycles = m.total_cycles - pc0
+    prof_ms_total = sum(v["ms"] for v in prof.values())
+    barrier()
 
     # ---- end to end through the C ABI with host buffers: q up, step, q down, every step
     esteps = max(1, min(args.steps, 5))
@@ -350,21 +360,21 @@ def run_ours(args):
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": rf["ms"] / rf["count"], "sweeps_per_launch": rf["aux"] / rf["count"],
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "share_of_step": rf["ms"] / ms_total, "note": note}
-    kern_ms = {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}
+                "share_of_step": rf["ms"] / prof_ms_total if prof_ms_total > 0 else None, "note": note}
+    kern_ms = {k: round(v["ms"] / psteps, 4) for k, v in prof.items()}
     # whole-step algorithmic bytes with the measured cycle counts
-    sweeps_all = prof["relax_fine"]["aux"]  # every level does the same number of sweeps per cycle
-    step_bytes = (2 * (ab["rhs"] + ab["residual"]) * args.steps +
-                  cycles * (ab["restrict"] * 1.0 + ab["prolong"] * 1.0 + ab["correct"] + ab["residual"]) +
-                  sweeps_all * ab["relax_sweep"] * 4.0 / 3) * cells / args.steps
+    sweeps_all = prof["relax_fine"]["aux"] / psteps  # per step; every level does the same number of sweeps per cycle
+    step_bytes = (2 * (ab["rhs"] + ab["residual"]) +
+                  cycles / args.steps * (ab["restrict"] * 1.0 + ab["prolong"] * 1.0 + ab["correct"] + ab["residual"]) +
+                  sweeps_all * ab["relax_sweep"] * 4.0 / 3) * cells
     step_roof = step_bytes / (ms_step * 1e-3) / 1e9
     # BASELINE metric, second half: wall-ms of one multigrid cycle (restriction of the residual, relax on every level,
     # prolongations, correction, residual) = the per-launch device times of those kernels over the timed region / cycles
     vcycle_ms = None
-    if cycles > 0:
+    if pcycles > 0:
         res = prof["residual"]
         vcycle_ms = (prof["relax_fine"]["ms"] + prof["relax_coarse"]["ms"] + prof["restrict"]["ms"] + prof["prolong"]["ms"] +
-                     prof["correct"]["ms"] + (res["ms"] / res["count"] * cycles if res["count"] else 0.)) / cycles
+                     prof["correct"]["ms"] + (res["ms"] / res["count"] * pcycles if res["count"] else 0.)) / pcycles
 
     # ---- the other smoother on the same workload (1 GPU): the parity path (reference sweep order) next to the
     # throughput path; 3 timed steps after 2 warm-up, same event timing

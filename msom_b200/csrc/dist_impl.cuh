@@ -132,6 +132,7 @@ struct msqg_group {
   long total_cycles;
   double umax_pg[MSQG_MAXL];
   long exchanges;
+  GraphCache graphs;
 };
 
 static inline int tile_rank(msqg_group *G, int ix, int iy) { return iy * G->px + ix; }
@@ -223,24 +224,36 @@ static int exchange_da(msqg_group *G, int lev) {
   return halo_exchange(G, arr, geo, G->p.nl);
 }
 
-/* max over tiles/ranks of n doubles that every tile holds at d_scal + off */
-static int reduce_max(msqg_group *G, int off, int n, double *out) {
+/* max over tiles/ranks of n doubles that every tile holds at d_scal + off: enqueue (capturable in a CUDA graph),
+ * then finish (synchronises the stream and reads the pinned mirror) */
+static int reduce_max_enqueue(msqg_group *G, int off, int n) {
   const int nt = (int)G->tiles.size();
-  for (int k = 0; k < n; k++) out[k] = 0.;
   if (G->kind == 1) {
     msqg_model *m = G->tiles[0];
     NCK(G->nccl->AllReduce(m->d_scal + off, G->d_red, n, NCCL_DOUBLE, NCCL_MAX, G->comm, G->stream));
     CK(cudaMemcpyAsync(G->h_red, G->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, G->stream));
-    CK(cudaStreamSynchronize(G->stream));
-    for (int k = 0; k < n; k++) out[k] = G->h_red[k];
     return MSQG_OK;
   }
   for (int t = 0; t < nt; t++)
     CK(cudaMemcpyAsync(G->h_red + (size_t)t * n, G->tiles[t]->d_scal + off, n * sizeof(double), cudaMemcpyDeviceToHost, G->stream));
+  return MSQG_OK;
+}
+static int reduce_max_finish(msqg_group *G, int n, double *out) {
+  const int nt = (int)G->tiles.size();
   CK(cudaStreamSynchronize(G->stream));
+  for (int k = 0; k < n; k++) out[k] = 0.;
+  if (G->kind == 1) {
+    for (int k = 0; k < n; k++) out[k] = G->h_red[k];
+    return MSQG_OK;
+  }
   for (int t = 0; t < nt; t++)
     for (int k = 0; k < n; k++) out[k] = fmax(out[k], G->h_red[(size_t)t * n + k]);
   return MSQG_OK;
+}
+static int reduce_max(msqg_group *G, int off, int n, double *out) {
+  int rc = reduce_max_enqueue(G, off, n);
+  if (rc) return rc;
+  return reduce_max_finish(G, n, out);
 }
 
 /* ------------------------------------------------------------------ create / destroy */
@@ -268,6 +281,7 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
         msqg_model *m;
         if ((rc = create_model(p, device, px, py, ix, iy, agg_n, G->stream, &m, G->rb))) return rc;
         m->smoother = G->rb;
+        m->tile_index = (int)G->tiles.size();
         G->tiles.push_back(m);
       }
   } else {
@@ -303,6 +317,7 @@ extern "C" void msqg_group_destroy(msqg_group *G) {
   if (!G) return;
   cudaSetDevice(G->device);
   cudaStreamSynchronize(G->stream);
+  G->graphs.clear();
   for (msqg_model *m : G->tiles) msqg_destroy(m);
   if (G->comm && G->nccl) G->nccl->CommDestroy(G->comm);
   cudaFree(G->d_red);
@@ -324,7 +339,7 @@ extern "C" int msqg_group_last_mgstats(msqg_group *G, msqg_mgstats *out) { *out 
 extern "C" int msqg_group_set_stream_sync(msqg_group *G) { CK(cudaStreamSynchronize(G->stream)); return MSQG_OK; }
 
 /* ------------------------------------------------------------------ multigrid on tiles */
-static int g_residual(msqg_group *G, int q_id, double *maxres) {
+static int g_residual_enqueue(msqg_group *G, int q_id) {
   for (msqg_model *m : G->tiles) {
     const int D = m->depth;
     const Geom &g = m->g[D];
@@ -337,7 +352,12 @@ static int g_residual(msqg_group *G, int q_id, double *maxres) {
     m->launches++;
   }
   CK(cudaGetLastError());
-  return reduce_max(G, 0, 1, maxres);
+  return reduce_max_enqueue(G, 0, 1);
+}
+static int g_residual(msqg_group *G, int q_id, double *maxres) {
+  int rc = g_residual_enqueue(G, q_id);
+  if (rc) return rc;
+  return reduce_max_finish(G, 1, maxres);
 }
 
 static int g_relax_level(msqg_group *G, msqg_model *m, int l, int nsweeps) {
@@ -472,8 +492,26 @@ static int g_invertq(msqg_group *G, int q_id) {
   if ((rc = g_residual(G, q_id, &resb))) return rc;
   s.resb = s.resa = resb;
   for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > 1e-3); s.i++) {
-    if ((rc = G->rb ? g_cycle_rb(G, s.nrelax) : g_cycle(G, s.nrelax))) return rc;
-    if ((rc = g_residual(G, q_id, &s.resa))) return rc;
+    if (G->rb) {
+      /* one cycle + residual + its all-reduce: a single graph launch (keyed by nrelax, the right-hand side and the
+         current da buffers of every tile) */
+      msqg_model *m0 = G->tiles[0];
+      unsigned long long mask = 0;
+      for (msqg_model *m : G->tiles) mask = mask * 1315423911ull + da_parity_mask(m);
+      bool graphed = m0->use_graphs != 0;
+      for (msqg_model *m : G->tiles) graphed = graphed && !m->prof_on;
+      GraphKey key(s.nrelax, -1, (const void *)m0->psi.lev[m0->depth], (const void *)list_by_id(m0, q_id)->lev[m0->depth], mask);
+      rc = run_graphed(G->stream, G->graphs, key, G->tiles, &G->exchanges, graphed, [&]() -> int {
+        int r2 = g_cycle_rb(G, s.nrelax);
+        if (r2) return r2;
+        return g_residual_enqueue(G, q_id);
+      });
+      if (rc) return rc;
+      if ((rc = reduce_max_finish(G, 1, &s.resa))) return rc;
+    } else {
+      if ((rc = g_cycle(G, s.nrelax))) return rc;
+      if ((rc = g_residual(G, q_id, &s.resa))) return rc;
+    }
     if (s.resa > 1e-3) {
       if (resb / s.resa < 1.2 && s.nrelax < 100) s.nrelax++;
       else if (resb / s.resa > 10 && s.nrelax > 2) s.nrelax--;
@@ -499,6 +537,7 @@ extern "C" int msqg_group_get_field(msqg_group *G, int t, int id, double *host_t
 }
 extern "C" int msqg_group_set_const(msqg_group *G) {
   CK(cudaSetDevice(G->device));
+  G->graphs.clear();
   int rc;
   const int D = G->tiles[0]->depth;
   for (msqg_model *m : G->tiles)

@@ -23,6 +23,8 @@
 #include <dlfcn.h>
 #include <vector>
 #include <utility>
+#include <map>
+#include <tuple>
 
 static thread_local char g_err[512] = "";
 extern "C" const char *msqg_last_error(void) { return g_err; }
@@ -48,6 +50,20 @@ struct List {
   double *base[MSQG_MAXLEV + 1]; /* the allocations themselves (tiles carry extra frame rows below row -1, see msqg_model::fy);
                                     lev[] entries of two lists of the same level may be swapped, base[] entries stay */
   List() { for (auto &p : lev) p = nullptr; for (auto &p : base) p = nullptr; }
+};
+
+/* CUDA graphs of one multigrid cycle + residual (red-black smoother): the launch sequence of a cycle depends only on
+ * nrelax, the problem (mode, unknown, right-hand side) and on which of the two da buffers is current on every level */
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  std::vector<std::pair<int, int>> swaps; /* (tile, level) buffer swaps the cycle performs on the host side */
+  long launches = 0, exchanges = 0;
+};
+typedef std::tuple<int, int, const void *, const void *, unsigned long long> GraphKey;
+struct GraphCache {
+  std::map<GraphKey, GraphEntry> entries;
+  std::map<GraphKey, int> seen;
+  void clear() { for (auto &e : entries) if (e.second.exec) cudaGraphExecDestroy(e.second.exec); entries.clear(); seen.clear(); }
 };
 
 struct msqg_model {
@@ -127,6 +143,10 @@ struct msqg_model {
   msqg_mgstats mgpsi, mgmode[MSQG_MAXL];
   long total_cycles, launches;
   int keep_dq;
+  GraphCache graphs;
+  std::vector<std::pair<int, int>> *swap_log; /* while a cycle is being recorded: (tile index, level) of every da/da2 swap */
+  int tile_index;
+  int use_graphs;
   int smoother;    /* 0: reference-order (lexicographic) Gauss-Seidel, the parity path; 1: red-black ordering (rb_kernels.cuh) */
   int rb_reuse;    /* rb kernel: neighbours carried in registers (MSQG_RB_REUSE=0 switches it off, A/B tests) */
   /* optional per-launch timing (CUDA events on the model's stream) */
@@ -454,6 +474,8 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   m->total_cycles = 0; m->launches = 0; m->keep_dq = 0; m->prof_on = 0; m->prof_next = 0;
   { const char *e = getenv("MSQG_SMOOTHER"); m->smoother = (e && !strcmp(e, "rb")) ? 1 : 0; }
   { const char *e = getenv("MSQG_RB_REUSE"); m->rb_reuse = (e && atoi(e) == 0) ? 0 : 1; }
+  { const char *e = getenv("MSQG_GRAPH"); m->use_graphs = (e && atoi(e) == 0) ? 0 : 1; }
+  m->swap_log = nullptr; m->tile_index = 0;
   memset(&m->mgpsi, 0, sizeof(m->mgpsi));
   memset(m->mgmode, 0, sizeof(m->mgmode));
   memset(m->umax_pg, 0, sizeof(m->umax_pg));
@@ -522,6 +544,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  m->graphs.clear();
   List *all[] = {&m->psi, &m->q, &m->qpred, &m->dq, &m->zeta, &m->tmp, &m->psipg, &m->zetap, &m->qforc, &m->fr,
                  &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->a_alt, &m->sstoch, &m->nstoch, &m->da, &m->res,
                  &m->pm, &m->qm, &m->ibu, &m->cl2m, &m->cm2l, &m->da2,
@@ -551,6 +574,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
 extern "C" int msqg_set_stream(msqg_model *m, void *s) {
   CK(cudaSetDevice(m->device));
   CK(cudaStreamSynchronize(m->stream));
+  m->graphs.clear();
   if (m->own_stream) cudaStreamDestroy(m->stream);
   m->stream = (cudaStream_t)s;
   m->own_stream = false;
@@ -572,6 +596,7 @@ extern "C" int msqg_set_flag_topo(msqg_model *m, int flag) { m->flag_topo = flag
 extern "C" int msqg_set_smoother(msqg_model *m, int smoother) {
   if (smoother != 0 && smoother != 1) FAIL(MSQG_ERR_ARG, "smoother is 0 (reference order) or 1 (red-black)");
   m->smoother = smoother;
+  m->graphs.clear();
   return MSQG_OK;
 }
 extern "C" int msqg_get_smoother(msqg_model *m) { return m->smoother; }
@@ -960,6 +985,7 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
   m->launches++;
   CK(cudaGetLastError());
   std::swap(m->da.lev[lev], m->da2.lev[lev]);
+  if (m->swap_log) m->swap_log->push_back({m->tile_index, lev});
   return MSQG_OK;
 }
 /* nrelax sweeps as ceil(nrelax / NSMAX) passes of (almost) equal length; the result does not depend on the split */
@@ -1052,7 +1078,7 @@ struct MgProblem {
                                buffer of its out-of-place correction instead of copying it back */
 };
 
-static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
+static int mg_residual_enqueue(msqg_model *m, const MgProblem &P) {
   const int D = m->depth;
   const Geom &g = m->g[D];
   CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), m->stream));
@@ -1068,9 +1094,61 @@ static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
   m->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(m->h_scal, m->d_scal, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  return MSQG_OK;
+}
+static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
+  int rc = mg_residual_enqueue(m, P);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(m->stream));
   *maxres = m->h_scal[0];
   return MSQG_OK;
+}
+
+/* Run `body` (which only enqueues work on `st`) through a CUDA graph: the first use of a key runs eagerly (lazy
+ * allocations, function attributes), the second records and instantiates, later uses replay.  The host-side effects of
+ * the body -- da/da2 buffer swaps, launch counters -- are logged while recording and re-applied on replay. */
+template <class F>
+static int run_graphed(cudaStream_t st, GraphCache &gc, const GraphKey &key, std::vector<msqg_model *> &models, long *exchanges, bool enabled,
+                       F body) {
+  if (!enabled) return body();
+  auto it = gc.entries.find(key);
+  if (it != gc.entries.end()) {
+    GraphEntry &E = it->second;
+    CK(cudaGraphLaunch(E.exec, st));
+    for (auto &sw : E.swaps) { msqg_model *m = models[sw.first]; std::swap(m->da.lev[sw.second], m->da2.lev[sw.second]); }
+    models[0]->launches += E.launches;
+    if (exchanges) *exchanges += E.exchanges;
+    return MSQG_OK;
+  }
+  if (gc.seen[key]++ == 0) return body();
+  GraphEntry E;
+  long l0 = 0, x0 = exchanges ? *exchanges : 0;
+  for (msqg_model *m : models) { l0 += m->launches; m->swap_log = &E.swaps; }
+  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+  int rc = e == cudaSuccess ? body() : MSQG_ERR_CUDA;
+  cudaGraph_t g = nullptr;
+  cudaError_t e2 = cudaStreamEndCapture(st, &g);
+  long l1 = 0;
+  for (msqg_model *m : models) { l1 += m->launches; m->swap_log = nullptr; }
+  if (e != cudaSuccess || rc || e2 != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    if (rc) return rc;
+    FAIL(MSQG_ERR_CUDA, "recording the multigrid cycle as a CUDA graph failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  }
+  e = cudaGraphInstantiate(&E.exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) FAIL(MSQG_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  E.launches = l1 - l0; E.exchanges = exchanges ? *exchanges - x0 : 0;
+  CK(cudaGraphLaunch(E.exec, st));
+  gc.entries[key] = E;
+  return MSQG_OK;
+}
+static unsigned long long da_parity_mask(msqg_model *m) {
+  unsigned long long mask = 0;
+  for (int l = 1; l <= m->depth; l++)
+    if (m->da.lev[l] && m->da.base[l] && m->da.lev[l] != m->da.base[l] + (size_t)(m->fy[l] - 1) * m->g[l].pitch) mask |= 1ull << l;
+  return mask;
 }
 
 /* experimental fusions of correction + residual + first restriction (k_corr_res), layer-coupled solves on an
@@ -1227,9 +1305,19 @@ static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mg
   rc = mg_residual(m, P, &resb);
   if (rc) return rc;
   s.resb = s.resa = resb;
+  const bool graphed = m->smoother == 1 && m->use_graphs && !m->prof_on && (P.nf == 1 || m->s_uniform);
+  std::vector<msqg_model *> self(1, m);
   for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > tolerance); s.i++) {
-    if ((rc = mg_cycle(m, P, s.nrelax))) return rc;
-    if ((rc = mg_residual(m, P, &s.resa))) return rc;
+    /* one cycle + the residual that follows it: a single graph launch in red-black mode */
+    GraphKey key(s.nrelax, P.mode, (const void *)P.a, (const void *)P.b, da_parity_mask(m));
+    rc = run_graphed(m->stream, m->graphs, key, self, nullptr, graphed, [&]() -> int {
+      int r2 = mg_cycle(m, P, s.nrelax);
+      if (r2) return r2;
+      return mg_residual_enqueue(m, P);
+    });
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(m->stream));
+    s.resa = m->h_scal[0];
     if (s.resa > tolerance) {
       if (resb / s.resa < 1.2 && s.nrelax < 100) s.nrelax++;
       else if (resb / s.resa > 10 && s.nrelax > 2) s.nrelax--;
@@ -1409,6 +1497,7 @@ static int max_face_speed(msqg_model *m, List &L, double *umax_host) {
 /* set_const up to (not including) comp_q: everything that is local to a tile */
 static int set_const_local(msqg_model *m) {
   CK(cudaSetDevice(m->device));
+  m->graphs.clear(); /* recorded cycles hold the old coefficients */
   const int nl = m->nl, D = m->depth;
   const int tx = m->tnx, ty = m->tny; /* finest tile (whole grid on one GPU) */
   const size_t tc = (size_t)tx * ty;
