@@ -255,8 +255,8 @@ def run_ours(args):
         m.set_const()
         step = m.step
         if sm == "rb":
-            parallelism = ("%dx%d tiles, one deep-halo NCCL exchange per level and cycle, levels < %d replicated on every GPU"
-                           % (m.px, m.py, args.agg_n))
+            parallelism = ("%dx%d tiles, one deep-halo exchange per level and cycle (%s), levels < %d replicated on every GPU "
+                           "(ncclAllGather), residual norm by ncclAllReduce" % (m.px, m.py, m.transport, args.agg_n))
         else:
             parallelism = "%dx%d tiles, NCCL halo exchange per sweep, levels < %d agglomerated on rank 0" % (m.px, m.py, args.agg_n)
 

@@ -233,6 +233,8 @@ int msqg_group_create_local_sm(const msqg_params *p, int device, int px, int py,
 int msqg_group_create_nccl_sm(const msqg_params *p, int device, int px, int py, int agg_n, int smoother, int rank, int nranks,
                               const void *uid128, msqg_group **out);
 int msqg_group_smoother(msqg_group *g);
+/* 1: halos move by direct stores into the neighbours' memory (CUDA IPC over NVLink, dist_rb.cuh); 0: ncclSend/ncclRecv */
+int msqg_group_transport(msqg_group *g);
 void msqg_group_destroy(msqg_group *g);
 int msqg_group_ntiles(msqg_group *g);                       /* tiles held by this process */
 msqg_model *msqg_group_tile(msqg_group *g, int t);

@@ -121,6 +121,7 @@ struct msqg_group {
   msqg_params p;
   int px, py, agg_n, device, kind; /* kind 0 local, 1 nccl */
   int rb;                          /* red-black smoother: replicated coarse levels, deep halos (dist_rb.cuh) */
+  int p2p;                         /* halo exchange by direct stores into the neighbours' memory (CUDA IPC) instead of NCCL */
   int rank, nranks;
   std::vector<msqg_model *> tiles; /* local: all tiles, index iy*px+ix; nccl: this rank's tile */
   cudaStream_t stream;
@@ -256,6 +257,61 @@ static int reduce_max(msqg_group *G, int off, int n, double *out) {
   return reduce_max_finish(G, n, out);
 }
 
+/* ------------------------------------------------------------------ peer-memory mapping of the neighbours' receive areas */
+static int group_setup_p2p(msqg_group *G) {
+  const int nt = (int)G->tiles.size();
+  if (G->kind == 0) { /* all tiles in this process: plain pointers */
+    for (int t = 0; t < nt; t++) {
+      msqg_model *m = G->tiles[t];
+      for (int d = 0; d < 9; d++) {
+        const int dx = d % 3 - 1, dy = d / 3 - 1, ax = m->ix + dx, ay = m->iy + dy;
+        m->peer_area[d] = (d != 4 && ax >= 0 && ax < G->px && ay >= 0 && ay < G->py) ? tile_at(G, ax, ay)->xarea : nullptr;
+      }
+    }
+    G->p2p = 1;
+    return MSQG_OK;
+  }
+  /* one process per GPU: all-gather the IPC handles of the receive areas, map the (up to 8) neighbours' */
+  msqg_model *m = G->tiles[0];
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, m->xarea) != cudaSuccess) { cudaGetLastError(); return MSQG_OK; } /* stays on NCCL */
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  char *d_all = nullptr;
+  CK(cudaMalloc(&d_all, hb * (G->nranks + 1)));
+  CK(cudaMemcpyAsync(d_all + hb * G->nranks, &mine, hb, cudaMemcpyHostToDevice, G->stream));
+  NCK(G->nccl->AllGather(d_all + hb * G->nranks, d_all, hb, 0 /* ncclInt8 */, G->comm, G->stream));
+  std::vector<cudaIpcMemHandle_t> all(G->nranks);
+  CK(cudaMemcpyAsync(all.data(), d_all, hb * G->nranks, cudaMemcpyDeviceToHost, G->stream));
+  CK(cudaStreamSynchronize(G->stream));
+  cudaFree(d_all);
+  int ok = 1;
+  for (int d = 0; d < 9 && ok; d++) {
+    const int dx = d % 3 - 1, dy = d / 3 - 1, ax = m->ix + dx, ay = m->iy + dy;
+    if (d == 4 || ax < 0 || ax >= G->px || ay < 0 || ay >= G->py) continue;
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[tile_rank(G, ax, ay)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    m->peer_area[d] = (double *)ptr; m->ipc_opened[d] = ptr;
+  }
+  /* every rank must take the same path: all-reduce(min) of the outcome */
+  double v = ok, *dv = G->d_red;
+  CK(cudaMemcpyAsync(dv, &v, sizeof(double), cudaMemcpyHostToDevice, G->stream));
+  NCK(G->nccl->AllReduce(dv, dv + 1, 1, NCCL_DOUBLE, 3 /* ncclMin */, G->comm, G->stream));
+  CK(cudaMemcpyAsync(&v, dv + 1, sizeof(double), cudaMemcpyDeviceToHost, G->stream));
+  CK(cudaStreamSynchronize(G->stream));
+  G->p2p = v > 0.5;
+  return MSQG_OK;
+}
+static int group_check_p2p(msqg_group *G) {
+  if (!G->p2p) return MSQG_OK;
+  for (msqg_model *m : G->tiles) {
+    unsigned long long e = 0;
+    CK(cudaMemcpyAsync(&e, (unsigned long long *)(m->xarea + 2 * 9 * m->xcap) + 17, sizeof(e), cudaMemcpyDeviceToHost, G->stream));
+    CK(cudaStreamSynchronize(G->stream));
+    if (e) FAIL(MSQG_ERR_CUDA, "peer-memory halo exchange timed out waiting for a neighbour");
+  }
+  return MSQG_OK;
+}
+
 /* ------------------------------------------------------------------ create / destroy */
 static int group_create(const msqg_params *p, int device, int px, int py, int agg_n, int kind, int rank, int nranks,
                         const void *uid, msqg_group **out, int smoother = -1) {
@@ -295,9 +351,16 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
     m->smoother = G->rb;
     G->tiles.push_back(m);
   }
+  G->p2p = 0;
+  if (G->rb) {
+    int want = 1;
+    { const char *e = getenv("MSQG_P2P"); if (e && atoi(e) == 0) want = 0; }
+    if (want && (rc = group_setup_p2p(G))) return rc;
+  }
   *out = G;
   return MSQG_OK;
 }
+extern "C" int msqg_group_transport(msqg_group *G) { return G->p2p; } /* 1: peer-memory halo exchange, 0: NCCL send/recv */
 extern "C" int msqg_group_create_local(const msqg_params *p, int device, int px, int py, int agg_n, msqg_group **out) {
   return group_create(p, device, px, py, agg_n, 0, 0, 1, nullptr, out);
 }
@@ -519,6 +582,7 @@ static int g_invertq(msqg_group *G, int q_id) {
     resb = s.resa;
   }
   if ((rc = g_check_err(G))) return rc;
+  if ((rc = group_check_p2p(G))) return rc;
   G->total_cycles += s.i;
   G->mgpsi = s;
   return MSQG_OK;

@@ -45,6 +45,111 @@ __global__ void k_halo_pack(double *__restrict__ a, Geom g, HaloPlan P, int unpa
   }
 }
 
+/* ------------------------------------------------------------------ the same exchange through peer memory
+ * One process per GPU; every tile's receive area is mapped by its neighbours (CUDA IPC) and the PACK kernel stores the
+ * halo straight into the neighbour's memory over NVLink, then raises an arrival flag there; the UNPACK kernel of the
+ * neighbour spins on its own flag and scatters the data into the halo frame.  Two launches per exchange (all lists of
+ * the exchange in one), no NCCL kernel, no host involvement, replayable inside a CUDA graph:
+ *   - the exchange counter lives in device memory (read by pack, advanced by the last block of unpack);
+ *   - two receive buffers alternate (parity of the counter): a tile can be at most one exchange ahead of a neighbour,
+ *     because its unpack of exchange e waits for the neighbour's pack of e, which follows the neighbour's unpack of e-1;
+ *   - flags only grow, spins are bounded (an error word is raised instead of hanging the GPU). */
+#define XCHG_MAXITEMS 6
+#define XCHG_SPIN_NS 4000000000ll
+struct XItemDev { double *arr; Geom g; int nf, w, ring; long long off[9]; };
+struct XchgArgs {
+  XItemDev it[XCHG_MAXITEMS];
+  int nitems;
+  int on[9];
+  double *area;           /* my receive area */
+  double *peer[9];        /* the neighbour's receive area, by direction */
+  unsigned long long xcap;
+};
+__device__ __forceinline__ unsigned long long *xa_flags(double *area, unsigned long long xcap) { return (unsigned long long *)(area + 2 * 9 * xcap); }
+/* words behind the receive space: [0..8] arrival flags, [16] exchange counter, [17] error, [32..40] pack block counters,
+   [48] unpack block counter */
+__device__ __forceinline__ void halo_box_dev(const Geom &g, int w, int ring, int d, bool recv, int &x0, int &x1, int &y0, int &y1) {
+  const int dx = d % 3 - 1, dy = d / 3 - 1;
+  const int eL = (ring && !(g.bc & 1)) ? 1 : 0, eR = (ring && !(g.bc & 2)) ? 1 : 0;
+  const int eB = (ring && !(g.bc & 4)) ? 1 : 0, eT = (ring && !(g.bc & 8)) ? 1 : 0;
+  if (dx < 0) { x0 = recv ? -w : 0; x1 = recv ? 0 : w; }
+  else if (dx > 0) { x0 = recv ? g.nx : g.nx - w; x1 = recv ? g.nx + w : g.nx; }
+  else { x0 = -eL; x1 = g.nx + eR; }
+  if (dy < 0) { y0 = recv ? -w : 0; y1 = recv ? 0 : w; }
+  else if (dy > 0) { y0 = recv ? g.ny : g.ny - w; y1 = recv ? g.ny + w : g.ny; }
+  else { y0 = -eB; y1 = g.ny + eT; }
+}
+/* grid (gx, 9 directions, items) */
+__global__ void __launch_bounds__(256) k_xchg_pack(XchgArgs X) {
+  const int d = blockIdx.y;
+  if (!X.on[d]) return;
+  unsigned long long *w_own = xa_flags(X.area, X.xcap);
+  const unsigned long long seqn = *(volatile unsigned long long *)(w_own + 16) + 1;
+  const XItemDev &I = X.it[blockIdx.z];
+  int x0, x1, y0, y1;
+  halo_box_dev(I.g, I.w, I.ring, d, false, x0, x1, y0, y1);
+  const int bw = x1 - x0, bh = y1 - y0;
+  const long long cnt = (long long)bw * bh, tot = cnt * I.nf;
+  /* the neighbour files what comes from me under ITS direction 8 - d */
+  double *dst = X.peer[d] + ((seqn & 1) * 9 + (8 - d)) * X.xcap + I.off[d];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(e / cnt);
+    const long long r = e - (long long)f * cnt;
+    const int y = y0 + (int)(r / bw), x = x0 + (int)(r % bw);
+    dst[e] = I.arr[(size_t)f * I.g.plane + (long long)(y + 1) * I.g.pitch + MSQG_OX + x];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int *done = (unsigned int *)(w_own + 32) + d;
+    const unsigned int t = atomicAdd(done, 1u);
+    if (t == gridDim.x * gridDim.z - 1) { /* last block of this direction: everything is on its way, raise the flag */
+      *done = 0;
+      __threadfence_system();
+      unsigned long long *pf = xa_flags(X.peer[d], X.xcap) + (8 - d);
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf), "l"(seqn) : "memory");
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_xchg_unpack(XchgArgs X) {
+  const int d = blockIdx.y;
+  unsigned long long *w_own = xa_flags(X.area, X.xcap);
+  const unsigned long long seqn = *(volatile unsigned long long *)(w_own + 16) + 1;
+  if (X.on[d]) {
+    if (threadIdx.x == 0) {
+      unsigned long long v;
+      long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w_own + d) : "memory");
+        if (v >= seqn) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > XCHG_SPIN_NS) { *(volatile unsigned long long *)(w_own + 17) = 1ull; break; }
+      }
+    }
+    __syncthreads();
+    const XItemDev &I = X.it[blockIdx.z];
+    int x0, x1, y0, y1;
+    halo_box_dev(I.g, I.w, I.ring, d, true, x0, x1, y0, y1);
+    const int bw = x1 - x0, bh = y1 - y0;
+    const long long cnt = (long long)bw * bh, tot = cnt * I.nf;
+    const double *src = X.area + ((seqn & 1) * 9 + d) * X.xcap + I.off[d];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+      const int f = (int)(e / cnt);
+      const long long r = e - (long long)f * cnt;
+      const int y = y0 + (int)(r / bw), x = x0 + (int)(r % bw);
+      I.arr[(size_t)f * I.g.plane + (long long)(y + 1) * I.g.pitch + MSQG_OX + x] = __ldcv(src + e);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int *done = (unsigned int *)(w_own + 48);
+    __threadfence();
+    const unsigned int t = atomicAdd(done, 1u);
+    if (t == gridDim.x * gridDim.y * gridDim.z - 1) { *done = 0; *(volatile unsigned long long *)(w_own + 16) = seqn; }
+  }
+}
+
 struct XItem {
   std::vector<double *> arr; /* per local tile */
   std::vector<Geom> geo;
@@ -88,6 +193,39 @@ static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
         if ((size_t)tot[t][d] > m->xcap) FAIL(MSQG_ERR_ARG, "halo exchange buffer too small");
       }
     }
+  if (G->p2p) {
+    if (items.size() > XCHG_MAXITEMS) FAIL(MSQG_ERR_ARG, "too many lists in one halo exchange");
+    std::vector<XchgArgs> args(nt);
+    for (int t = 0; t < nt; t++) {
+      msqg_model *m = G->tiles[t];
+      XchgArgs &X = args[t];
+      memset(&X, 0, sizeof(X));
+      X.nitems = (int)items.size(); X.area = m->xarea; X.xcap = m->xcap;
+      for (int d = 0; d < 9; d++) { X.on[d] = plans[0][t].on[d]; X.peer[d] = m->peer_area[d]; }
+      for (size_t it = 0; it < items.size(); it++) {
+        XItemDev &I = X.it[it];
+        I.arr = items[it].arr[t]; I.g = items[it].geo[t]; I.nf = items[it].nf; I.w = items[it].w; I.ring = items[it].ring;
+        for (int d = 0; d < 9; d++) I.off[d] = plans[it][t].off[d];
+      }
+    }
+    for (int pass = 0; pass < 2; pass++)   /* every pack before any unpack: local tiles share one stream */
+      for (int t = 0; t < nt; t++) {
+        long long mx = 0;
+        for (size_t it = 0; it < items.size(); it++)
+          for (int d = 0; d < 9; d++)
+            if (plans[it][t].on[d])
+              mx = std::max(mx, (long long)items[it].nf * (plans[it][t].send[d].x1 - plans[it][t].send[d].x0) * (plans[it][t].send[d].y1 - plans[it][t].send[d].y0));
+        if (mx == 0) continue;
+        int gx = (int)((mx + 2047) / 2048);
+        if (gx > 32) gx = 32;
+        if (gx < 1) gx = 1;
+        if (pass == 0) k_xchg_pack<<<dim3(gx, 9, (unsigned)items.size()), 256, 0, G->stream>>>(args[t]);
+        else k_xchg_unpack<<<dim3(gx, 9, (unsigned)items.size()), 256, 0, G->stream>>>(args[t]);
+        G->tiles[t]->launches++;
+      }
+    CK(cudaGetLastError());
+    return MSQG_OK;
+  }
   auto launch = [&](int unpack) {
     for (size_t it = 0; it < items.size(); it++)
       for (int t = 0; t < nt; t++) {

@@ -83,6 +83,13 @@ struct msqg_model {
   size_t halo_doubles, patch_doubles;
   double *xsend[9], *xrecv[9]; /* red-black group: one buffer per neighbour direction (dist_rb.cuh), xcap doubles each */
   size_t xcap;
+  /* peer-memory halo exchange (dist_rb.cuh): ONE allocation that neighbours map (CUDA IPC) and write into directly:
+     [2 parities][9 directions][xcap] doubles of receive space, then 16 arrival flags, the exchange counter, block
+     counters and an error word */
+  double *xarea;
+  size_t xarea_bytes;
+  double *peer_area[9];        /* the neighbours' xarea (mapped), by direction; NULL where there is no neighbour */
+  void *ipc_opened[9];
   double *gather_buf;          /* all-gathered blocks of level agg_level-1, [px*py][nl][hy][hx] */
   cudaStream_t stream;
   bool own_stream;
@@ -420,7 +427,8 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   m->da_patch = m->res_patch = m->patch_stage = nullptr;
   for (int k = 0; k < 4; k++) m->halo_send[k] = m->halo_recv[k] = nullptr;
   for (int k = 0; k < 9; k++) m->xsend[k] = m->xrecv[k] = nullptr;
-  m->gather_buf = nullptr; m->xcap = 0;
+  m->gather_buf = nullptr; m->xcap = 0; m->xarea = nullptr; m->xarea_bytes = 0;
+  for (int k = 0; k < 9; k++) { m->peer_area[k] = nullptr; m->ipc_opened[k] = nullptr; }
   if (shared) { m->stream = shared; m->own_stream = false; }
   else {
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -529,6 +537,9 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
         CK(cudaMalloc(&m->xrecv[k], m->xcap * sizeof(double)));
       }
       CK(cudaMalloc(&m->gather_buf, (size_t)px * py * nl * gp.nx * gp.ny * sizeof(double)));
+      m->xarea_bytes = (2 * 9 * m->xcap) * sizeof(double) + 4096;
+      CK(cudaMalloc(&m->xarea, m->xarea_bytes));
+      CK(cudaMemsetAsync(m->xarea, 0, m->xarea_bytes, m->stream));
     }
   }
   CK(cudaStreamSynchronize(m->stream));
@@ -566,6 +577,8 @@ extern "C" void msqg_destroy(msqg_model *m) {
   for (int k = 0; k < 4; k++) { if (m->halo_send[k]) cudaFree(m->halo_send[k]); if (m->halo_recv[k]) cudaFree(m->halo_recv[k]); }
   for (int k = 0; k < 9; k++) { if (m->xsend[k]) cudaFree(m->xsend[k]); if (m->xrecv[k]) cudaFree(m->xrecv[k]); }
   if (m->gather_buf) cudaFree(m->gather_buf);
+  for (int k = 0; k < 9; k++) if (m->ipc_opened[k]) cudaIpcCloseMemHandle(m->ipc_opened[k]);
+  if (m->xarea) cudaFree(m->xarea);
   for (cudaEvent_t e : m->prof_pool) cudaEventDestroy(e);
   if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;

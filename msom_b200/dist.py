@@ -36,6 +36,7 @@ def _bind():
     L.msqg_group_create_nccl_sm.argtypes = [C.POINTER(G.Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_char_p, C.POINTER(vp)]
     L.msqg_group_smoother.argtypes = [vp]
+    L.msqg_group_transport.argtypes = [vp]
     L.msqg_group_destroy.argtypes = [vp]
     L.msqg_group_ntiles.argtypes = [vp]
     L.msqg_group_tile.argtypes = [vp, C.c_int]
@@ -82,6 +83,7 @@ class Group:
         else:
             G.check(self.L.msqg_group_create_nccl_sm(C.byref(params), device, px, py, agg_n, sm, rank, nranks, uid, C.byref(h)))
         self.smoother = smoother
+        self.transport = "peer-memory" if self.L.msqg_group_transport(h) == 1 else "nccl"
         self.h = h
         self.t = 0.0
         self.ntiles = self.L.msqg_group_ntiles(self.h)

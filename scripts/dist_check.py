@@ -34,7 +34,7 @@ ok &= (g.total_cycles == mo.L.orc_total_cycles(mo.h))
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("DIST_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", sm, "world", world, "grid %dx%d" % (px, py), "exchanges", g.exchanges)
+    print("DIST_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", sm, g.transport, "world", world, "grid %dx%d" % (px, py), "exchanges", g.exchanges)
 g.close()
 dist.destroy_process_group()
 sys.exit(0 if int(t.item()) == 1 else 1)

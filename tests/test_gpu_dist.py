@@ -61,20 +61,22 @@ def test_decomposition_differs_from_serial_only_at_solver_tolerance(gpu):
     assert np.abs(a - b).max() < 1e-3 * np.abs(a).max()
 
 
-@pytest.mark.parametrize("N,nl,px,py,agg_n", [(128, 2, 2, 1, 64), (128, 3, 2, 2, 64), (256, 2, 4, 2, 128), (256, 4, 1, 2, 64),
-                                               (512, 4, 4, 2, 256)])
-def test_red_black_group_equals_single_gpu_and_oracle(gpu, N, nl, px, py, agg_n):
+@pytest.mark.parametrize("N,nl,px,py,agg_n,p2p", [(128, 2, 2, 1, 64, 1), (128, 3, 2, 2, 64, 1), (256, 2, 4, 2, 128, 1), (256, 4, 1, 2, 64, 1),
+                                                   (512, 4, 4, 2, 256, 1), (256, 3, 2, 2, 64, 0), (256, 2, 4, 2, 128, 0)])
+def test_red_black_group_equals_single_gpu_and_oracle(gpu, N, nl, px, py, agg_n, p2p, monkeypatch):
     """Throughput mode on tiles: a red-black half-sweep does not depend on the decomposition, so the group (deep halos,
     one exchange per level, replicated coarse levels) must give the bits of the undecomposed solve and of the oracle
     running the same ordering -- including cold-start solves whose nrelax adapts upwards (several relax passes)."""
     from oracle import oracle as O
     from msom_b200 import capi as G
     from msom_b200.dist import Group
+    monkeypatch.setenv("MSQG_P2P", str(p2p))   # halo transport: stores into the neighbours' receive areas / staged copies
     kw = base_kw(N, nl)
     psi = synth_psi(N, nl)
     mo = O.Model(O.make_params(**kw)); mo.set_smoother("rb")
     s = G.Model(G.make_params(**kw), gpu); s.set_smoother("rb")
     g = Group(G.make_params(**kw), px, py, agg_n, gpu, smoother="rb")
+    assert g.transport == ("peer-memory" if p2p else "nccl")
     mo.set(O.PSI, psi); s.set(G.PSI, psi); g.set_global(G.PSI, psi)
     mo.set_const(); s.set_const(); g.set_const()
     assert np.array_equal(g.get_global(G.Q), mo.get(O.Q))
