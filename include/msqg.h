@@ -204,8 +204,8 @@ int msqg_test_restrict(msqg_model *m, int level, const double *fine, double *coa
 int msqg_test_prolong(msqg_model *m, int level, const double *coarse, double *fine);
 /* div_by() (exact division by a pivot with known reciprocal) next to IEEE x/d */
 int msqg_test_div(int device, const double *x, const double *d, double *q_fast, double *q_ieee, int n);
-/* per-launch CUDA-event timing by kernel category (8 categories: relax finest,
- * relax coarser, residual, restrict, prolong, correct, laplacians, rhs) */
+/* per-launch CUDA-event timing by kernel category (9 categories: relax finest,
+ * relax coarser, residual, restrict, prolong, correct, laplacians, rhs, halo exchange) */
 int msqg_profile_enable(msqg_model *m, int on);
 int msqg_profile_read(msqg_model *m, double *ms, long *count, long *aux_sum);
 /* per-worker timeline of one relax launch (debug): out[w] = {start ns, end ns, spins, 0} */

@@ -250,7 +250,7 @@ class Model:
         check(self.L.msqg_time_vcycle(self.h, nrelax, reps, C.byref(ms)))
         return ms.value
 
-    PROF_CATS = ("relax_fine", "relax_coarse", "residual", "restrict", "prolong", "correct", "laplacian", "rhs")
+    PROF_CATS = ("relax_fine", "relax_coarse", "residual", "restrict", "prolong", "correct", "laplacian", "rhs", "exchange")
 
     def set_stream(self, cuda_stream):
         check(self.L.msqg_set_stream(self.h, C.c_void_p(cuda_stream)))
@@ -259,7 +259,7 @@ class Model:
         check(self.L.msqg_profile_enable(self.h, 1 if on else 0))
 
     def profile_read(self):
-        ms = (C.c_double * 8)(); cnt = (C.c_long * 8)(); aux = (C.c_long * 8)()
+        ms = (C.c_double * 9)(); cnt = (C.c_long * 9)(); aux = (C.c_long * 9)()
         check(self.L.msqg_profile_read(self.h, ms, cnt, aux))
         return {k: dict(ms=ms[i], count=cnt[i], aux=aux[i]) for i, k in enumerate(self.PROF_CATS)}
 

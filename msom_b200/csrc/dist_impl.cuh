@@ -231,6 +231,7 @@ static int reduce_max_enqueue(msqg_group *G, int off, int n) {
   const int nt = (int)G->tiles.size();
   if (G->kind == 1) {
     msqg_model *m = G->tiles[0];
+    ProfScope ps_r(m, PROF_XCHG, 1000);
     NCK(G->nccl->AllReduce(m->d_scal + off, G->d_red, n, NCCL_DOUBLE, NCCL_MAX, G->comm, G->stream));
     CK(cudaMemcpyAsync(G->h_red, G->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, G->stream));
     return MSQG_OK;

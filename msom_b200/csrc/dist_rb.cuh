@@ -177,6 +177,7 @@ static void halo_boxes(const Geom &g, int w, int ring, int ix, int iy, int px, i
 /* all items in one grouped exchange: pack (one launch per item and tile), one send/recv pair per neighbour, unpack */
 static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
   G->exchanges++;
+  ProfScope ps_x(G->tiles[0], PROF_XCHG, (int)items.size());
   const int nt = (int)G->tiles.size();
   std::vector<std::vector<HaloPlan>> plans(items.size(), std::vector<HaloPlan>(nt));
   std::vector<std::vector<long long>> tot(nt, std::vector<long long>(9, 0));
@@ -216,8 +217,9 @@ static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
             if (plans[it][t].on[d])
               mx = std::max(mx, (long long)items[it].nf * (plans[it][t].send[d].x1 - plans[it][t].send[d].x0) * (plans[it][t].send[d].y1 - plans[it][t].send[d].y0));
         if (mx == 0) continue;
-        int gx = (int)((mx + 2047) / 2048);
-        if (gx > 32) gx = 32;
+        /* one element per thread where possible: a thread's loads are dependent round trips to HBM / the peer */
+        int gx = (int)((mx + 255) / 256);
+        if (gx > 1024) gx = 1024;
         if (gx < 1) gx = 1;
         if (pass == 0) k_xchg_pack<<<dim3(gx, 9, (unsigned)items.size()), 256, 0, G->stream>>>(args[t]);
         else k_xchg_unpack<<<dim3(gx, 9, (unsigned)items.size()), 256, 0, G->stream>>>(args[t]);
@@ -235,7 +237,7 @@ static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
           if (P.on[d]) mx = std::max(mx, (long long)(P.send[d].x1 - P.send[d].x0) * (P.send[d].y1 - P.send[d].y0));
         if (mx == 0) continue;
         int gx = (int)((mx + 255) / 256);
-        if (gx > 64) gx = 64;
+        if (gx > 1024) gx = 1024;
         k_halo_pack<<<dim3(gx, 9, items[it].nf), 256, 0, G->stream>>>(items[it].arr[t], items[it].geo[t], P, unpack);
         G->tiles[t]->launches++;
       }
@@ -336,6 +338,7 @@ static int g_cycle_rb(msqg_group *G, int nrelax) {
       for (int r = 0; r < nt; r++)
         CK(cudaMemcpyAsync(m->gather_buf + (size_t)r * blk, G->tiles[r]->patch_stage, blk * sizeof(double), cudaMemcpyDeviceToDevice, G->stream));
   } else {
+    ProfScope ps_g(m0, PROF_XCHG, 100);
     NCK(G->nccl->AllGather(m0->patch_stage, m0->gather_buf, blk, NCCL_DOUBLE, G->comm, G->stream));
   }
   /* halo of res on the distributed levels: the sweeps recompute up to 2 nrelax border cells of the neighbours */

@@ -41,7 +41,7 @@ extern "C" const char *msqg_last_error(void) { return g_err; }
 
 static inline double sq(double x) { return x * x; }
 
-enum { PROF_RELAX_FINE = 0, PROF_RELAX_COARSE, PROF_RESIDUAL, PROF_RESTRICT, PROF_PROLONG, PROF_CORRECT, PROF_LAP, PROF_RHS, PROF_NCAT };
+enum { PROF_RELAX_FINE = 0, PROF_RELAX_COARSE, PROF_RESIDUAL, PROF_RESTRICT, PROF_PROLONG, PROF_CORRECT, PROF_LAP, PROF_RHS, PROF_XCHG, PROF_NCAT };
 
 struct List {
   int nf = 0;

@@ -157,7 +157,7 @@ class Group:
         G.check(self.L.msqg_group_profile_enable(self.h, 1 if on else 0))
 
     def profile_read(self):
-        ms = (C.c_double * 8)(); cnt = (C.c_long * 8)(); aux = (C.c_long * 8)()
+        ms = (C.c_double * 9)(); cnt = (C.c_long * 9)(); aux = (C.c_long * 9)()
         G.check(self.L.msqg_group_profile_read(self.h, ms, cnt, aux))
         return {k: dict(ms=ms[i], count=cnt[i], aux=aux[i]) for i, k in enumerate(G.Model.PROF_CATS)}
 
