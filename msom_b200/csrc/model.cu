@@ -971,6 +971,30 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
   A.coef_cell = (RCOEF && !m->s_rowuniform) ? 1 : 0;
   A.reuse = m->rb_reuse;
   if (RCOEF && (g.bc || !A.coef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
+  const int nxo_ = A.ox_hi - A.ox_lo, nyo_ = A.oy_hi - A.oy_lo;
+  if constexpr (!RCOEF && NL <= 4) {
+    /* small levels / tiles: one shared-memory window per CTA instead of the streaming pipeline (k_relax_rb_tile) */
+    int lim = 512;
+    { const char *e = getenv("MSQG_RB_TILE"); if (e) lim = atoi(e); }
+    if ((long long)nxo_ * nyo_ <= (long long)lim * lim) {
+      constexpr int WS = RB_TO + 4 * RB_NSMAX;
+      const size_t tsmem = (size_t)2 * NL * WS * WS * sizeof(double);
+      auto tk = k_relax_rb_tile<NL>;
+      static KernelDevState tst;
+      const int dev = m->device & 63;
+      if (!tst.set[dev]) {
+        CK(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        tst.set[dev] = true;
+      }
+      RelaxCoef<NL> Cc = C;
+      tk<<<dim3((nxo_ + RB_TO - 1) / RB_TO, (nyo_ + RB_TO - 1) / RB_TO), 512, tsmem, m->stream>>>(A, Cc);
+      m->launches++;
+      CK(cudaGetLastError());
+      std::swap(m->da.lev[lev], m->da2.lev[lev]);
+      if (m->swap_log) m->swap_log->push_back({m->tile_index, lev});
+      return MSQG_OK;
+    }
+  }
   const size_t smem = (size_t)A.R * Cfg::row_bytes;
   const int threads = Cfg::NSMAX * 2 * RB_NP; /* fixed block: stages beyond nh only stream */
   auto kern = k_relax_rb<NL, RCOEF>;

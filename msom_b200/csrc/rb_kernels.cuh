@@ -403,3 +403,77 @@ k_coarse_rb(CoarseArgs A, CoarseCoef<NL> CC) {
     }
   }
 }
+
+/* ------------------------------------------------------------------ small levels: one window per CTA, no streaming
+ * The streaming kernel pays 2 nh rows of halo and 2 nh steps of pipeline fill per row chunk, which dominates on levels
+ * (or tiles) of a few hundred cells per side.  Here a CTA loads the whole window of its RB_TO x RB_TO output block
+ * (+ nh cells of halo on every side that has neighbours) into shared memory, runs the nh half-sweeps with one
+ * __syncthreads() each -- half-sweep h only touches the cells whose halo is still complete, a region that shrinks by
+ * one ring per half-sweep -- and stores the block.  Same cell update, same ghost rule, same bits as k_relax_rb. */
+#define RB_TO 32
+template <int NL>
+__global__ void __launch_bounds__(512)
+k_relax_rb_tile(RbArgs A, RelaxCoef<NL> C) {
+  extern __shared__ double tsm[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int nh = 2 * A.ns, H = nh;
+  const int nx = A.g.nx, ny = A.g.ny, bc = A.g.bc, pitch = A.g.pitch;
+  const long long plane = (long long)A.g.plane;
+  const int ox0 = A.ox_lo + blockIdx.x * RB_TO, ox1 = min(ox0 + RB_TO, A.ox_hi);
+  const int oy0 = A.oy_lo + blockIdx.y * RB_TO, oy1 = min(oy0 + RB_TO, A.oy_hi);
+  /* window = output block + halo, clipped to the cells that exist */
+  const int wx0 = max(A.xlo, ox0 - H), wx1 = min(A.xhi, ox1 + H);
+  const int wy0 = max(A.ylo, oy0 - H), wy1 = min(A.yhi, oy1 + H);
+  const int ww = wx1 - wx0, wh = wy1 - wy0;
+  constexpr int WS = RB_TO + 4 * RB_NSMAX;      /* window pitch */
+  double *sda = tsm, *srs = tsm + NL * WS * WS; /* [NL][WS][WS] each */
+  for (int e = tid; e < NL * wh * ww; e += nt) {
+    const int f = e / (wh * ww), r = e - f * wh * ww, y = r / ww, x = r - y * ww;
+    const long long g = (long long)f * plane + (long long)(wy0 + y + 1) * pitch + MSQG_OX + wx0 + x;
+    sda[(f * WS + y) * WS + x] = A.da[g];
+    srs[(f * WS + y) * WS + x] = A.res[g];
+  }
+  __syncthreads();
+  /* sides of the window that are sides of the whole field: no ring is lost there (ghosts instead of neighbours) */
+  const bool eL = wx0 == 0 && !(bc & 1), eR = wx1 == nx && !(bc & 2), eB = wy0 == 0 && !(bc & 4), eT = wy1 == ny && !(bc & 8);
+  for (int hs = 0; hs < nh; hs++) {
+    const int colour = hs & 1;
+    const int lx = eL ? 0 : hs + 1, hx = eR ? ww : ww - hs - 1, ly = eB ? 0 : hs + 1, hy = eT ? wh : wh - hs - 1;
+    const int rw = hx - lx, rh = hy - ly, hw = (rw + 1) >> 1;
+    for (int e = tid; e < rh * hw; e += nt) {
+      const int y = ly + e / hw;
+      int x = lx + 2 * (e % hw);
+      x += ((wx0 + x + wy0 + y + A.par0) & 1) != colour; /* first cell of this colour at or after x */
+      if (x >= hx) continue;
+      const int gx = wx0 + x, gy = wy0 + y;
+      double rhs[NL], out[NL];
+#pragma unroll
+      for (int f = 0; f < NL; f++) {
+        const double *p = sda + (f * WS + y) * WS + x;
+        const double c0 = p[0], gh = -c0;
+        const double aw = (gx == 0 && !(bc & 1)) ? gh : (x > 0 ? p[-1] : c0);
+        const double ae = (gx == nx - 1 && !(bc & 2)) ? gh : (x < ww - 1 ? p[1] : c0);
+        const double as = (gy == 0 && !(bc & 4)) ? gh : (y > 0 ? p[-WS] : c0);
+        const double an = (gy == ny - 1 && !(bc & 8)) ? gh : (y < wh - 1 ? p[WS] : c0);
+        double rr = C.msd2 * srs[(f * WS + y) * WS + x];
+        rr += ae + aw;
+        rr += an + as;
+        rhs[f] = rr;
+      }
+#pragma unroll
+      for (int f = 1; f < NL; f++) rhs[f] -= div_by(C.t0[f] * rhs[f - 1], C.t1p[f - 1], C.rinv[f - 1]);
+      out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
+#pragma unroll
+      for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - C.t2[f] * out[f + 1], C.t1p[f], C.rinv[f]);
+#pragma unroll
+      for (int f = 0; f < NL; f++) sda[(f * WS + y) * WS + x] = out[f];
+    }
+    __syncthreads();
+  }
+  const int bw = ox1 - ox0, bh = oy1 - oy0;
+  for (int e = tid; e < NL * bh * bw; e += nt) {
+    const int f = e / (bh * bw), r = e - f * bh * bw, y = r / bw, x = r - y * bw;
+    A.da_out[(long long)f * plane + (long long)(oy0 + y + 1) * pitch + MSQG_OX + ox0 + x] =
+        sda[(f * WS + (oy0 + y - wy0)) * WS + (ox0 + x - wx0)];
+  }
+}
