@@ -199,6 +199,55 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_ensemble(args):
+    """BASELINE config 5: stochastic ensemble, `--members` members per GPU of 512^2 x nl=3 (32 members on 8 GPUs), replicas
+    only: no communication between members.  Aggregate cell-layer updates/s over all members and GPUs."""
+    import torch
+    import torch.distributed as dist
+    from msom_b200 import capi as G
+    from msom_b200.ensemble import Ensemble
+    from common import base_kw, synth_psi
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, nl, M = args.ens_N, 3, args.members
+    kw = base_kw(N, nl, stochastic=1, tr_stoch=10., amp_stoch=1.)
+    ens = Ensemble(G.make_params(**kw), M, local, seeds=[1000 + rank * M + i for i in range(M)], noise=args.noise, smoother=args.smoother)
+    ens.set(G.PSI, synth_psi(N, nl)); ens.set(G.SSTOCH, np.full((nl, N, N), 1e-3)); ens.set_const()
+    ens.step(max(args.warmup, 3))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ens.step(args.steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    cycles = sum(m.total_cycles for m in ens.members)
+    launches = sum(m.launches for m in ens.members)
+    ens.close()
+    if rank == 0:
+        val = float(N) * N * nl * M * world * args.steps / dt
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "msqg qg_stochastic ensemble, %d members x %d^2 x nl=%d per GPU (BASELINE config 5), noise=%s, smoother=%s"
+                                       % (M, N, nl, args.noise, args.smoother),
+                           "members_total": M * world, "parallelism": "replicas: %d member(s) per GPU on own streams, no communication" % M,
+                           "timing": "wall clock around the concurrent member steps (device-synchronised on both sides), max over ranks"},
+                "gpu_launches": int(launches)}
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -458,6 +507,10 @@ def main():
                          "number of GPUs; lex: the reference's serial sweep order (parity path; does not scale)")
     ap.add_argument("--modal", action="store_true",
                     help="vertical-mode inversion (MODE_PV_INVERT 1, eigmode.h; BASELINE config 3) instead of the layer-coupled solver")
+    ap.add_argument("--ensemble", action="store_true", help="BASELINE config 5: stochastic ensemble, --members per GPU of 512^2 x 3")
+    ap.add_argument("--members", type=int, default=4)
+    ap.add_argument("--ens-N", type=int, default=512, dest="ens_N")
+    ap.add_argument("--noise", default="philox", choices=["philox", "libc"])
     ap.add_argument("--agg-n", type=int, default=0, dest="agg_n",
                     help="multi-GPU: levels with fewer than agg_n cells per side are not distributed (rb: replicated on every "
                          "GPU, default 512; lex: agglomerated on rank 0, default N)")
@@ -469,6 +522,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.ensemble:
+        run_ensemble(args)
     else:
         run_ours(args)
 

@@ -182,6 +182,10 @@ void msqg_set_ts_previous(msqg_model *m, double v);
 /* seed of the host libc rand() stream used by the stochastic forcing
  * (qg_stochastic.h:9); noise is generated on the host in reference order */
 void msqg_seed_noise(msqg_model *m, unsigned seed);
+/* 0 (default): the noise field is drawn on the host from the libc rand() stream in the reference's traversal order
+ * (bit-exact replay of qg_stochastic.h:117-126); 1: Philox4x32-10 on the device, same Box-Muller transform, order
+ * independent -- the production mode of ensembles (seed from msqg_seed_noise) */
+int msqg_set_noise_mode(msqg_model *m, int mode);
 /* number of CUDA kernels launched by this handle since creation */
 long msqg_launch_count(msqg_model *m);
 const char *msqg_last_error(void);

@@ -110,6 +110,7 @@ def lib():
     L.msqg_get_ts_previous.restype = C.c_double
     L.msqg_set_ts_previous.argtypes = [vp, C.c_double]
     L.msqg_seed_noise.argtypes = [vp, C.c_uint]
+    L.msqg_set_noise_mode.argtypes = [vp, C.c_int]
     L.msqg_launch_count.argtypes = [vp]
     L.msqg_launch_count.restype = C.c_long
     L.msqg_test_relax.argtypes = [vp, C.c_int, dp, dp, C.c_int]

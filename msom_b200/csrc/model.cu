@@ -146,6 +146,9 @@ struct msqg_model {
   struct random_data rng;
   char rng_state[128];
   std::vector<double> h_noise, h_sstoch;
+  int noise_mode;               /* 0: host replay of the reference's libc rand() stream; 1: Philox on the device */
+  unsigned int noise_seed;
+  unsigned long long noise_draw;
   double umax_pg[MSQG_MAXL];
   msqg_mgstats mgpsi, mgmode[MSQG_MAXL];
   long total_cycles, launches;
@@ -484,6 +487,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   { const char *e = getenv("MSQG_RB_REUSE"); m->rb_reuse = (e && atoi(e) == 0) ? 0 : 1; }
   { const char *e = getenv("MSQG_GRAPH"); m->use_graphs = (e && atoi(e) == 0) ? 0 : 1; }
   m->swap_log = nullptr; m->tile_index = 0;
+  m->noise_mode = 0; m->noise_seed = 1; m->noise_draw = 0;
   memset(&m->mgpsi, 0, sizeof(m->mgpsi));
   memset(m->mgmode, 0, sizeof(m->mgmode));
   memset(m->umax_pg, 0, sizeof(m->umax_pg));
@@ -601,7 +605,13 @@ extern "C" long msqg_launch_count(msqg_model *m) { return m->launches; }
 extern "C" long msqg_total_cycles(msqg_model *m) { return m->total_cycles; }
 extern "C" double msqg_get_ts_previous(msqg_model *m) { return m->ts_previous; }
 extern "C" void msqg_set_ts_previous(msqg_model *m, double v) { m->ts_previous = v; }
+extern "C" int msqg_set_noise_mode(msqg_model *m, int mode) {
+  if (mode != 0 && mode != 1) FAIL(MSQG_ERR_ARG, "noise mode is 0 (libc rand() replay) or 1 (Philox on the device)");
+  m->noise_mode = mode; m->noise_draw = 0;
+  return MSQG_OK;
+}
 extern "C" void msqg_seed_noise(msqg_model *m, unsigned seed) {
+  m->noise_seed = seed; m->noise_draw = 0;
   memset(&m->rng, 0, sizeof(m->rng));
   initstate_r(seed, m->rng_state, sizeof(m->rng_state), &m->rng);
 }
@@ -1816,6 +1826,16 @@ static int generate_noise(msqg_model *m) {
   const int n = m->N, nl = m->nl;
   const double pi = 3.14159265358979323846;
   if (m->px * m->py > 1) FAIL(MSQG_ERR_ARG, "stochastic forcing is not supported on decomposed grids");
+  if (m->noise_mode == 1) { /* one kernel, no host work: the production mode (and the only one that keeps a GPU busy) */
+    const Geom &g = m->g[m->depth];
+    dim3 b(64, 4);
+    k_noise_philox<<<grid2(g.nx, g.ny, b, nl), b, 0, m->stream>>>(m->nstoch.lev[m->depth], m->sstoch.lev[m->depth], g, m->p.amp_stoch,
+                                                                   m->noise_seed, m->noise_draw);
+    m->launches++;
+    m->noise_draw++;
+    CK(cudaGetLastError());
+    return MSQG_OK;
+  }
   if (m->h_sstoch.empty()) m->h_sstoch.assign((size_t)nl * n * n, 0.);
   m->h_noise.resize((size_t)nl * n * n);
   for (int i = 0; i < n; i++)

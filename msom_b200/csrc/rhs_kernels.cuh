@@ -658,3 +658,39 @@ k_ke_partial(const double *__restrict__ p, Geom g, double *__restrict__ part) {
   }
   if (tid == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
 }
+
+
+/* ------------------------------------------------------------------ stochastic forcing, production noise mode
+ * The reference draws n = amp * sigma * N(0,1) with Box-Muller on sequential libc rand() (qg_stochastic.h:9,117-126);
+ * that stream is replayed on the host in the parity mode.  Here the same transform runs on a counter-based generator
+ * (Philox4x32-10, counter = (cell-layer index, draw number), key = (seed, tag)), so a field of noise is one kernel and
+ * does not depend on traversal order or on how many members share a GPU.  oracle/msqg_oracle.c mirrors it. */
+__device__ __forceinline__ void philox4x32_10(unsigned int (&c)[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const unsigned int n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_noise_philox(double *__restrict__ noise, const double *__restrict__ sigma, Geom g, double amp, unsigned int seed,
+               unsigned long long draw) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int l = blockIdx.z;
+  if (x >= g.nx || y >= g.ny) return;
+  const unsigned long long idx = ((unsigned long long)l * g.ny + y) * g.nx + x;
+  unsigned int c[4] = {(unsigned int)idx, (unsigned int)(idx >> 32), (unsigned int)draw, (unsigned int)(draw >> 32)};
+  philox4x32_10(c, seed, 0x6d737167u);
+  const double u1 = (((double)c[0]) * 4294967296. + (double)c[1] + 0.5) * (1. / 18446744073709551616.);
+  const double u2 = (((double)c[2]) * 4294967296. + (double)c[3] + 0.5) * (1. / 18446744073709551616.);
+  const double gsn = sqrt(-2. * log(u1)) * cos(2 * 3.14159265358979323846 * u2);
+  const size_t cc = (size_t)l * g.plane + GIDX(g.pitch, y, x);
+  const double v = amp * sigma[cc] * gsn;
+  double *p = noise + (size_t)l * g.plane;
+  p[GIDX(g.pitch, y, x)] = v;
+  write_ghosts(p, g, x, y, v, -1.);
+}

@@ -9,11 +9,16 @@ from . import capi as G
 
 
 class Ensemble:
-    def __init__(self, params, nmembers, device=0, seeds=None, threads=None):
+    def __init__(self, params, nmembers, device=0, seeds=None, threads=None, noise="libc", smoother="lex"):
+        """noise: 'libc' replays the reference's rand() stream on the host (parity; ~80 ns of CPU per sample, which at
+        512^2 x 3 is 60 ms per step and member -- the GPU idles), 'philox' draws the field on the device (production).
+        smoother: 'lex' (reference order) or 'rb' (throughput mode, no cooperative launches: members overlap freely)."""
         self.members = [G.Model(params, device) for _ in range(nmembers)]
         self.seeds = list(seeds) if seeds is not None else [1000 + i for i in range(nmembers)]
         for m, s in zip(self.members, self.seeds):
             m.L.msqg_seed_noise(m.h, s)
+            G.check(m.L.msqg_set_noise_mode(m.h, {"libc": 0, "philox": 1}[noise]))
+            m.set_smoother(smoother)
         self.pool = ThreadPoolExecutor(max_workers=threads or nmembers)
 
     def __len__(self):

@@ -160,6 +160,7 @@ struct orc_model {
   orc_mgstats mgpsi, mgmode[ORC_MAXL];
   int total_cycles;
   int agg_n; /* MPI-emulation: levels with n < agg_n are swept as one block */
+  int noise_mode; unsigned int noise_seed; unsigned long long noise_draw; /* orc_set_noise_mode */
   int smoother; /* 0: the reference's lexicographic sweep; 1: red-black ordering of the same cell update (orc_set_smoother) */
 };
 
@@ -376,6 +377,7 @@ void orc_get_field(orc_model *m, int id, double *v) {
 }
 void orc_set_flag_topo(orc_model *m, int flag) { m->flag_topo = flag; }
 void orc_set_decomp(orc_model *m, int px, int py, int agg_n) { m->p.px = px; m->p.py = py; m->agg_n = agg_n; }
+void orc_set_noise_mode(orc_model *m, int mode, unsigned seed) { m->noise_mode = mode == 1; m->noise_seed = seed; m->noise_draw = 0; }
 void orc_set_smoother(orc_model *m, int smoother) { m->smoother = smoother == 1 ? 1 : 0; }
 int orc_get_smoother(orc_model *m) { return m->smoother; }
 
@@ -1173,8 +1175,35 @@ static double update_qg(orc_model *m, flist *evolving, flist *updates, double dt
 double orc_update(orc_model *m, double dtmax) { return update_qg(m, &m->qol, &m->dql, dtmax); }
 
 /* normal_noise, qg_stochastic.h:9 ; generate_noise :117-126 */
+/* counter-based generator of the production noise mode (not in the reference, which draws libc rand() sequentially):
+ * Philox4x32-10 (Salmon et al. 2011), counter = (cell-layer index, draw number), key = (seed, tag); the same Box-Muller
+ * transform as normal_noise (qg_stochastic.h:9) on two 64-bit uniforms.  Mirrors k_noise_philox of the CUDA library. */
+static void philox4x32_10(unsigned int c[4], unsigned int k0, unsigned int k1) {
+  for (int r = 0; r < 10; r++) {
+    unsigned long long p0 = 0xD2511F53ull * c[0], p1 = 0xCD9E8D57ull * c[2];
+    unsigned int hi0 = (unsigned int)(p0 >> 32), lo0 = (unsigned int)p0, hi1 = (unsigned int)(p1 >> 32), lo1 = (unsigned int)p1;
+    unsigned int n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
 static void generate_noise(orc_model *m) {
   int n = m->N, D = m->depth, nl = m->nl;
+  if (m->noise_mode == 1) {
+    for (int l = 0; l < nl; l++)
+      for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+          unsigned long long idx = ((unsigned long long)l * n + j) * n + i;
+          unsigned int c[4] = {(unsigned int)idx, (unsigned int)(idx >> 32), (unsigned int)m->noise_draw, (unsigned int)(m->noise_draw >> 32)};
+          philox4x32_10(c, m->noise_seed, 0x6d737167u);
+          double u1 = (((double)c[0]) * 4294967296. + (double)c[1] + 0.5) * (1. / 18446744073709551616.);
+          double u2 = (((double)c[2]) * 4294967296. + (double)c[3] + 0.5) * (1. / 18446744073709551616.);
+          double g = sqrt(-2. * log(u1)) * cos(2 * pi * u2);
+          FL(&m->n_stochl, l, D)[IDX(n, i, j)] = m->p.amp_stoch * FL(&m->s_stochl, l, D)[IDX(n, i, j)] * g;
+        }
+    m->noise_draw++;
+    return;
+  }
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++)
       for (int l = 0; l < nl; l++) {

@@ -89,6 +89,7 @@ def lib(omp=False):
     L.orc_set_flag_topo.argtypes = [vp, C.c_int]
     L.orc_set_decomp.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.orc_set_smoother.argtypes = [vp, C.c_int]
+    L.orc_set_noise_mode.argtypes = [vp, C.c_int, C.c_uint]
     L.orc_get_smoother.argtypes = [vp]
     L.orc_get_smoother.restype = C.c_int
     L.orc_init_noise.argtypes = [vp, C.c_uint]

@@ -65,6 +65,31 @@ def test_stochastic_forcing(gpu, N, nl, nsteps):
     assert rel_l2(mo.get(O.Q), mo2.get(O.Q)) > 1e-8
 
 
+@pytest.mark.parametrize("smoother", ["lex", "rb"])
+def test_stochastic_forcing_philox(gpu, smoother):
+    """production noise mode: Philox4x32-10 + Box-Muller on the device against the oracle's restatement of the same
+    generator.  The integer stream is identical; log/cos of the CUDA math library and glibc may differ in the last
+    place, so the noise field is compared to 1e-13 relative and the state after 4 steps to 1e-10."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    N, nl, nsteps = 64, 3, 4
+    over = dict(stochastic=1, tr_stoch=10., amp_stoch=1.)
+    mo, mg, _ = make_pair(N, nl, smoother=smoother, **over)
+    sig = np.full((nl, N, N), 1e-3) * (1 + np.arange(nl)[:, None, None])
+    mo.set(O.SSTOCH, sig); mg.set(G.SSTOCH, sig)
+    mo.set_const(); mg.set_const()
+    mo.L.orc_set_noise_mode(mo.h, 1, 4242)
+    mg.L.msqg_seed_noise(mg.h, 4242); G.check(mg.L.msqg_set_noise_mode(mg.h, 1))
+    for _ in range(nsteps):
+        assert abs(mg.step() - mo.step()) <= 1e-15
+    a, b = mg.get(G.NSTOCH), mo.get(O.NSTOCH)
+    assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max() and np.abs(b).max() > 0
+    assert abs(b.mean()) < 5 * b.std() / np.sqrt(b.size)      # N(0, sigma): mean compatible with 0
+    assert abs((b[0] / sig[0]).std() - 1) < 0.05               # unit variance before scaling
+    for fg, fo in ((G.Q, O.Q), (G.PSI, O.PSI)):
+        assert rel_l2(mg.get(fg), mo.get(fo)) <= 1e-10
+
+
 def test_plugin_sequence_equals_fused_step(gpu):
     """update_qg / advance_qg called as the predictor-corrector does (msqg/qg.h:922-923 plugin surface)
     give the same bits as the fused msqg_step."""
@@ -140,6 +165,19 @@ def test_ensemble_members_concurrent(gpu):
     libc.srand(1000 + 1)
     assert [mo.step() for _ in range(nsteps)] == dts[1]
     assert np.array_equal(mo.get(O.Q), qs[1])
+    ens.close()
+    # production configuration: device noise + red-black smoother; members still equal their solo runs bit for bit
+    ens = Ensemble(G.make_params(**kw), nmem, gpu, noise="philox", smoother="rb")
+    ens.set(G.PSI, psi); ens.set(G.SSTOCH, sig); ens.set_const()
+    dts = ens.step(nsteps)
+    qs = ens.get(G.Q)
+    assert not np.array_equal(qs[0], qs[1])
+    solo = G.Model(G.make_params(**kw), gpu)
+    solo.set_smoother("rb")
+    solo.L.msqg_seed_noise(solo.h, 1000 + 2); G.check(solo.L.msqg_set_noise_mode(solo.h, 1))
+    solo.set(G.PSI, psi); solo.set(G.SSTOCH, sig); solo.set_const()
+    assert [solo.step() for _ in range(nsteps)] == dts[2]
+    assert np.array_equal(solo.get(G.Q), qs[2])
     ens.close()
 
 
