@@ -91,7 +91,7 @@ enum {
   MSQG_DE_J1,     /* de_j1l   msqg/qg_energy.h:9  */
   MSQG_DE_J2,     /* de_j2l   msqg/qg_energy.h:10 */
   MSQG_DE_J3,     /* de_j3l   msqg/qg_energy.h:11 */
-  MSQG_DE_FT,     /* de_ftl   msqg/qg_energy.h:12 (stays 0: filter_de needs the wavelet filter, out of scope) */
+  MSQG_DE_FT,     /* de_ftl   msqg/qg_energy.h:12 (accumulated by msqg_filter_de after every wavelet filter pass) */
   MSQG_PO_MFT,    /* po_mft   msqg/qg_energy.h:15 */
   MSQG_PTR,       /* ptracersl  msqg/qg.h:100 (nl*nptr scalars, index l*nptr + nt; zero-gradient boundaries) */
   MSQG_PTR_RELAX, /* ptr_relaxl msqg/qg.h:101 */
@@ -131,6 +131,8 @@ int msqg_set_flag_topo(msqg_model *m, int flag);  /* flag_topo, qg.h:971-977 */
  * creation from the environment variable MSQG_SMOOTHER=rb. */
 int msqg_set_smoother(msqg_model *m, int smoother);
 int msqg_get_smoother(msqg_model *m);
+/* 1 if the library was built with -DMSQG_EXPERIMENTS (rejected kernel variants kept for A/B measurements) */
+int msqg_has_experiments(void);
 /* reset_layer_var (layer.h:37-41): zero the interior, ghost ring untouched */
 int msqg_reset_field(msqg_model *m, int id);
 /* layer thicknesses dhf (qg.h:895-896; overridden by dh_%dl.bin, qg.h:940-948) */

@@ -168,6 +168,7 @@ k_residual(const double *__restrict__ a, const double *__restrict__ b, double *_
   block_max_to(maxres, m);
 }
 
+#ifdef MSQG_EXPERIMENTS /* measured slower than the split kernels; MSQG_MG=rr|fused */
 /* mg_cycle's tail fused with the residual that always follows it in mg_solve (mspg/elliptic.h:92-98,181-205) and with
  * the first restriction of the next cycle:
  *     a' = a + da ; boundary(a')          (k_correct)           -> a_new, OUT of place (neighbours still read a, da)
@@ -252,6 +253,8 @@ k_corr_res(const double *__restrict__ a, const double *__restrict__ da, double *
   }
   block_max_to(maxres, m);
 }
+
+#endif
 
 /* [BASILISK] poisson.h residual(), scalar Helmholtz, lambda field:
  *   res = b - lambda*a + face-gradient form as above */
@@ -573,6 +576,7 @@ __device__ __forceinline__ void st_mail2_if(bool p, unsigned long long *a, unsig
                ::"r"((int)p), "l"(a), "l"(v0), "l"(v1) : "memory");
 }
 
+#ifdef MSQG_EXPERIMENTS /* first, single-warp version of the reference-order wavefront (MSQG_RELAX=v3) */
 template <int NL, int K>
 struct RelaxCfg {
   static_assert(K == 4 || K == 8, "ring sizing assumes W + 2K <= 20");
@@ -827,6 +831,8 @@ k_relax_lex(RelaxArgs A, RelaxCoef<NL> C) {
   }
 }
 
+#endif
+
 /* Per-row Thomas coefficients of one level for stretching that varies with y only (varRo > 0): the expressions
  * of relax_coef_layers() (msqg/poisson_layer.h:89-139, same order, IEEE division) evaluated with the level's
  * restricted stretching field at column 0 of every row.  out[j][6][NL] = t0, t2, t1p, rinv, cf, cb. */
@@ -986,13 +992,10 @@ __device__ __forceinline__ double div_fix(double x, double q, double d, double r
 #else
 #define WS_LAUNCH_BOUNDS(NT) __launch_bounds__(NT)
 #endif
-/* MW: a ninth warp per CTA (the "mail warp") takes the global mailbox of the CTA's first strip off its helper warp:
- * it does nothing but poll, deposit into slot 0 of the sweep rings, re-arm and publish LIM (= min of the helper's
- * progress HLIM and its own), so the hand-off between CTAs no longer waits for a helper iteration that also streams
- * and drains rows. */
-template <int NL, int K, int WPC, bool TILE, bool RCOEF = false, int CS = 1, bool MW = false>
-__global__ void WS_LAUNCH_BOUNDS(64 * WPC + (MW ? 32 : 0))
+template <int NL, int K, int WPC, bool TILE, bool RCOEF = false, int CS = 1>
+__global__ void WS_LAUNCH_BOUNDS(64 * WPC)
 k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
+  constexpr bool MW = false; /* (a dedicated mail warp per CTA was measured slower and has been removed) */
   using Cfg = WsCfg<NL, K>;
   constexpr int W = Cfg::W, S = Cfg::S, RC = Cfg::RC, RIN = Cfg::RIN, R2 = Cfg::R2;
   constexpr int NLP = Cfg::NLP, NV = Cfg::NV, DROW = Cfg::DROW, RROW = Cfg::RROW, XRS = Cfg::XRS, Q = Cfg::Q;
@@ -1452,66 +1455,6 @@ k_relax_ws(RelaxArgs A, RelaxCoef<NL> C) {
     cp_async_wait<0>();
     if (MW && wl == 0 && lane == 0) cnt[Cfg::H_DONE] = 1;
     if (A.dbg && lane == 0) A.dbg[w * 4 + 3] = it; /* helper iterations (profiling) */
-  } else {
-    /* ================================================================ mail warp (MW): first strip of the CTA */
-    const int kk = lane / Q, q = lane % Q; /* mailbox lanes: Q rows of each sweep per iteration */
-    const bool rd_ghost = (w == 0) && lint && kk == 0; /* west column = stored halo column -1 of the iterate */
-    const bool rd_valid = rd_ghost || ((w > 0) && !pin && kk < nsw && (w * W - 1 - kk) >= 0 && (w * W - 1 - kk) < nx);
-    const unsigned long long *mb_in = A.mailbox + ((size_t)(w > 0 ? w - 1 : 0) * K + kk) * (size_t)ny * NLP;
-    const unsigned a_ringk = (unsigned)__cvta_generic_to_shared(XR + (size_t)kk * XRS);
-    const unsigned gmask = (Q == 32) ? 0xffffffffu : (((1u << Q) - 1u) << (kk * Q));
-    int mail_rd = rd_valid ? 0 : ny; /* rows deposited for sweep kk */
-    int idle = 0;
-#pragma unroll 1
-    for (;;) {
-      const int cd = ld_cnt(cnt + Cfg::C_DONE);
-      const int r = mail_rd + q;
-      const bool can = rd_valid && r < ny && (cd >= r - R2 + 2 * kk + 3);
-      if (!__any_sync(FULLMASK, can)) __nanosleep(200); /* nothing to poll: leave the issue slots to the compute warps */
-      unsigned long long v[NLP];
-#pragma unroll
-      for (int l = 0; l < NLP; l++) v[l] = MAIL_EMPTY;
-      if (can && !rd_ghost) {
-        const unsigned long long *p = mb_in + (size_t)r * NLP;
-#pragma unroll
-        for (int l = 0; l < NLP; l += 2)
-          asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[l]), "=l"(v[l + 1]) : "l"(p + l));
-      }
-      if (can && rd_ghost) {
-#pragma unroll
-        for (int l = 0; l < NL; l++) v[l] = (unsigned long long)__double_as_longlong(A.da[(size_t)l * plane + GIDX(pitch, r, -1)]);
-      }
-      bool valid = can;
-#pragma unroll
-      for (int l = 0; l < NL; l++) valid = valid && (v[l] != MAIL_EMPTY);
-      const unsigned bal = (__ballot_sync(FULLMASK, valid) & gmask) >> (kk * Q);
-      const int adv = __ffs(~bal) - 1;
-      if (q < adv) {
-        const unsigned d = a_ringk + 16u * (unsigned)((r & (R2 - 1)) * DROW);
-#pragma unroll
-        for (int l = 0; l < NLP; l += 2)
-          sts2(d + 16u * ((l >> 1) * S), __longlong_as_double((long long)v[l]), __longlong_as_double((long long)v[l + 1]));
-        unsigned long long *p = (unsigned long long *)mb_in + (size_t)r * NLP;
-        if (!rd_ghost) {
-#pragma unroll
-          for (int l = 0; l < NLP; l += 2)
-            asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};\n" ::"l"(p + l), "l"(MAIL_EMPTY), "l"(MAIL_EMPTY) : "memory");
-        }
-      }
-      mail_rd += adv;
-      __syncwarp();
-      const int hdone = ld_cnt(cnt + Cfg::H_DONE); /* read BEFORE the helper's limits: they are final once it is set */
-      if (q == 0 && kk < K) {
-        int lim = ld_cnt(cnt + Cfg::HLIM + kk);
-        lim = min(lim, (mail_rd >= ny) ? WS_INF : mail_rd - 1);
-        if (kk >= nsw) lim = WS_INF;
-        cnt[Cfg::LIM + kk] = lim;
-      }
-      if (hdone && __all_sync(FULLMASK, mail_rd >= ny)) break;
-      if (!__any_sync(FULLMASK, adv > 0) && !hdone) {
-        if (++idle > SPIN_LIMIT) { if (lane == 0) *A.err = 3; break; }
-      } else idle = 0;
-    }
   }
   } /* w < nworkers */
   if (CS > 1) cluster_sync_all();

@@ -400,11 +400,13 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   if (px * py > 1) {
     int la = 1;
     while ((1 << la) < agg_n) la++;
-    if (la > depth) FAIL(MSQG_ERR_ARG, "agglomeration threshold %d exceeds N", agg_n);
-    if (((1 << la) / px) < 8 || ((1 << la) / py) < 8) FAIL(MSQG_ERR_ARG, "tiles must keep >= 8 cells per side on every distributed level (raise agg_n)");
-    if (rb_dist && (((1 << la) / px) < MSQG_FRAME || ((1 << la) / py) < MSQG_FRAME))
-      FAIL(MSQG_ERR_ARG, "red-black tiles must keep >= %d cells per side on every distributed level (raise agg_n)", MSQG_FRAME);
-    if (la < 2) FAIL(MSQG_ERR_ARG, "agg_n too small");
+    const char *why = nullptr;
+    if (la > depth) why = "the agglomeration threshold exceeds N";
+    else if (((1 << la) / px) < 8 || ((1 << la) / py) < 8) why = "tiles must keep >= 8 cells per side on every distributed level (raise agg_n)";
+    else if (rb_dist && (((1 << la) / px) < MSQG_FRAME || ((1 << la) / py) < MSQG_FRAME))
+      why = "red-black tiles must keep >= 16 cells per side on every distributed level (raise agg_n)";
+    else if (la < 2) why = "agg_n too small";
+    if (why) { delete m; FAIL(MSQG_ERR_ARG, "%s", why); }
     m->agg_level = la;
   }
   for (int l = 0; l <= depth; l++) {
@@ -623,6 +625,13 @@ extern "C" int msqg_set_smoother(msqg_model *m, int smoother) {
   return MSQG_OK;
 }
 extern "C" int msqg_get_smoother(msqg_model *m) { return m->smoother; }
+extern "C" int msqg_has_experiments(void) {
+#ifdef MSQG_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" int msqg_set_keep_dq(msqg_model *m, int keep) { m->keep_dq = keep; return MSQG_OK; }
 extern "C" int msqg_set_dissipation(msqg_model *m, double iRe, double iRe4, double Eks, double Ekb) {
   m->iRe = iRe; m->iRe4 = iRe4; m->Eks = Eks; m->Ekb = Ekb; /* pystep_bfn flips these, qg_bfn.h:34-44 */
@@ -753,6 +762,7 @@ __global__ void k_fill_u64(unsigned long long *p, size_t n, unsigned long long v
   for (; i < n; i += stride) p[i] = v;
 }
 
+#ifdef MSQG_EXPERIMENTS /* first version of the reference-order kernel (single-warp wavefront, k_relax_lex): MSQG_RELAX=v3 */
 template <int NL, int K, int WPC>
 static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   using Cfg = RelaxCfg<NL, K>;
@@ -779,8 +789,10 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
   { const char *f = getenv("MSQG_RELAX_FLAGS"); A.flags = f ? atoi(f) : 0; }
   const size_t smem = Cfg::smem_per_warp * WPC;
   auto kern = k_relax_lex<NL, K, WPC>;
-  static bool attr_set = false;
-  static int max_blocks_per_sm = 0;
+  static bool attr_set_d[64] = {};
+  static int max_blocks_d[64] = {};
+  bool &attr_set = attr_set_d[m->device & 63];
+  int &max_blocks_per_sm = max_blocks_d[m->device & 63];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, kern, 32 * WPC, smem));
@@ -797,6 +809,7 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
   m->launches++;
   return MSQG_OK;
 }
+#endif
 /* warp-specialised variant (k_relax_ws): two warps per strip */
 /* thread-block cluster size of the relax kernel's DSMEM hand-off (MSQG_RELAX_CS = 1, 2 or 4; 1 = global mailbox
  * between all CTAs, the default).  Instantiated for nl <= 4 (build time).  Measured on B200, 4096^2 x 4, relax ms per
@@ -808,9 +821,13 @@ static int launch_relax_w(msqg_model *m, double *da, const double *res, int lev,
 #define RELAX_CS 1
 #endif
 static int relax_cluster_size() {
+#ifdef MSQG_EXPERIMENTS
   static int v = -1;
   if (v < 0) { const char *e = getenv("MSQG_RELAX_CS"); v = e ? atoi(e) : RELAX_CS; if (v != 2 && v != 4) v = 1; }
   return v;
+#else
+  return 1; /* the cluster hand-off variants (measured slower) are built with -DMSQG_EXPERIMENTS only */
+#endif
 }
 template <int NL, int K, int WPC, bool RCOEF = false>
 static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
@@ -842,12 +859,18 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   if constexpr (!RCOEF && NL <= 4 && K == 4) { if (!g.bc && m->relax_cs_ok) cs = relax_cluster_size(); }
   const int tv = g.bc ? 1 : (cs == 2 ? 2 : cs == 4 ? 3 : 0);
   auto kern = RCOEF ? k_relax_ws<NL, K, WPC, false, RCOEF> : (tv ? k_relax_ws<NL, K, WPC, true> : k_relax_ws<NL, K, WPC, false>);
+#ifdef MSQG_EXPERIMENTS
   if constexpr (!RCOEF && NL <= 4 && K == 4) {
     if (tv == 2) kern = k_relax_ws<NL, K, WPC, false, false, 2>;
     if (tv == 3) kern = k_relax_ws<NL, K, WPC, false, false, 4>;
   }
-  static bool attr_set[4] = {false, false, false, false};
-  static int max_blocks[4] = {0, 0, 0, 0}; /* co-resident CTAs per SM; cluster variants: co-resident CTAs on the device */
+#endif
+  /* per device (handles may live on several GPUs of one process): opt-in shared memory and co-resident CTAs per SM
+     (cluster variants: co-resident CTAs on the device) */
+  static bool attr_set_d[64][4] = {};
+  static int max_blocks_d[64][4] = {};
+  bool *attr_set = attr_set_d[m->device & 63];
+  int *max_blocks = max_blocks_d[m->device & 63];
   if (!attr_set[tv]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (cs == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks[tv], kern, 64 * WPC, smem));
@@ -915,11 +938,16 @@ static int launch_relax_ws(msqg_model *m, double *da, const double *res, int lev
   else return launch_relax_ws_w<NL, K, 1>(m, da, res, lev, nsweeps, C);
 }
 static int relax_variant() {
+#ifdef MSQG_EXPERIMENTS
   static int v = -1;
   if (v < 0) { const char *e = getenv("MSQG_RELAX"); v = (e && !strcmp(e, "v3")) ? 0 : 1; }
   return v;
+#else
+  return 1;
+#endif
 }
 
+#ifdef MSQG_EXPERIMENTS
 template <int NL, int K>
 static int launch_relax_w_t(msqg_model *m, double *da, const double *res, int lev, int nsweeps, const RelaxCoef<NL> &C) {
   /* warps per CTA limited by the per-warp shared-memory rings */
@@ -927,6 +955,7 @@ static int launch_relax_w_t(msqg_model *m, double *da, const double *res, int le
   if constexpr (spw * 4 <= 200 * 1024) return launch_relax_w<NL, K, 4>(m, da, res, lev, nsweeps, C);
   else return launch_relax_w<NL, K, 2>(m, da, res, lev, nsweeps, C);
 }
+#endif
 
 template <int NL>
 static int launch_relax_rb(msqg_model *m, double *da, const double *res, int lev, int nrelax, const RelaxCoef<NL> &C,
@@ -942,8 +971,12 @@ static int launch_relax(msqg_model *m, double *da, const double *res, int lev, i
        is the same arithmetic; the single-warp k_relax_lex keeps its 8-sweep instance */
     if (!m->s_uniform) { if (ns > 4) ns = 4; rc = launch_relax_rowcoef<NL>(m, da, res, lev, ns, C); }
     else if (relax_variant() == 1) { if (ns > 4) ns = 4; rc = launch_relax_ws<NL, 4>(m, da, res, lev, ns, C); }
+#ifdef MSQG_EXPERIMENTS
     else if (ns <= 4) rc = launch_relax_w_t<NL, 4>(m, da, res, lev, ns, C);
     else { if (ns > 8) ns = 8; rc = launch_relax_w_t<NL, 8>(m, da, res, lev, ns, C); }
+#else
+    else rc = MSQG_ERR_ARG;
+#endif
     if (rc) return rc;
     done += ns;
   }
@@ -954,10 +987,10 @@ static int launch_relax(msqg_model *m, double *da, const double *res, int lev, i
 /* ------------------------------------------------------------------ red-black relax launch (rb_kernels.cuh) */
 /* per-device launch state of one kernel instance: opt-in shared memory and co-resident CTAs per SM */
 struct KernelDevState { bool set[64] = {}; int occ[64][RB_NSMAX + 1] = {}; };
-template <int NL, bool RCOEF>
-static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, int lev, int ns, const RelaxCoef<NL> &C,
+template <int NL, bool RCOEF, int WXT>
+static int launch_relax_rb_pass_w(msqg_model *m, double *da, const double *res, int lev, int ns, const RelaxCoef<NL> &C,
                                 const int *orange /* optional {ox_lo, ox_hi, oy_lo, oy_hi} */, int halo) {
-  using Cfg = RbCfg<NL>;
+  using Cfg = RbCfg<NL, WXT>;
   const Geom &g = m->g[lev];
   const int nh = 2 * ns;
   if (da != m->da.lev[lev]) FAIL(MSQG_ERR_ARG, "the rb relax pass works on the model's da list");
@@ -970,7 +1003,7 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
   memset(&A, 0, sizeof(A));
   A.da = da; A.da_out = m->da2.lev[lev]; A.res = res; A.g = g; A.ns = ns;
   A.R = 2 * nh + 1 + RB_PF;
-  A.TX = RB_WX - 2 * nh;
+  A.TX = WXT - 2 * nh;
   A.ox_lo = 0; A.ox_hi = g.nx; A.oy_lo = 0; A.oy_hi = g.ny;
   if (orange) { A.ox_lo = orange[0]; A.ox_hi = orange[1]; A.oy_lo = orange[2]; A.oy_hi = orange[3]; }
   /* cells that exist: own cells, plus `halo` cells of deep halo on the sides that have a neighbouring tile */
@@ -1006,15 +1039,15 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
     }
   }
   const size_t smem = (size_t)A.R * Cfg::row_bytes;
-  const int threads = Cfg::NSMAX * 2 * RB_NP; /* fixed block: stages beyond nh only stream */
-  auto kern = k_relax_rb<NL, RCOEF>;
+  const int threads = Cfg::NSMAX * WXT; /* fixed block: stages beyond nh only stream */
+  auto kern = k_relax_rb<NL, RCOEF, WXT>;
   static KernelDevState st;
   const int dev = m->device & 63;
   if (!st.set[dev]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)((size_t)(4 * Cfg::NSMAX + 1 + RB_PF) * Cfg::row_bytes)));
     for (int s = 1; s <= Cfg::NSMAX; s++)
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occ[dev][s], kern, Cfg::NSMAX * 2 * RB_NP,
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occ[dev][s], kern, Cfg::NSMAX * WXT,
                                                        (size_t)(4 * s + 1 + RB_PF) * Cfg::row_bytes));
     st.set[dev] = true;
   }
@@ -1034,6 +1067,26 @@ static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, in
   std::swap(m->da.lev[lev], m->da2.lev[lev]);
   if (m->swap_log) m->swap_log->push_back({m->tile_index, lev});
   return MSQG_OK;
+}
+/* window width.  A 64-column window halves the ring so that two CTAs share an SM, but the kernel is bound by
+ * shared-memory bandwidth, not by latency: measured on B200 at 4096^2 x 4 the finest-level relaxation takes 4.96 ms per
+ * step with 64 columns against 4.39 ms with 128 (more halo redundancy, same shared-memory traffic per cell).  The narrow
+ * instance is therefore only built with -DMSQG_EXPERIMENTS (MSQG_RB_WX=64, MSQG_RB_WX_MIN=<smallest level side>). */
+template <int NL, bool RCOEF>
+static int launch_relax_rb_pass(msqg_model *m, double *da, const double *res, int lev, int ns, const RelaxCoef<NL> &C,
+                                const int *orange, int halo) {
+#ifdef MSQG_EXPERIMENTS
+  int wx = 128;
+  { const char *e = getenv("MSQG_RB_WX"); if (e) wx = atoi(e); }
+  if constexpr (NL <= 4) {
+    const Geom &g = m->g[lev];
+    const long long cells = (long long)(orange ? orange[1] - orange[0] : g.nx) * (orange ? orange[3] - orange[2] : g.ny);
+    long long minside = 1024;
+    { const char *e = getenv("MSQG_RB_WX_MIN"); if (e) minside = atoi(e); }
+    if (wx == 64 && cells >= minside * minside) return launch_relax_rb_pass_w<NL, RCOEF, 64>(m, da, res, lev, ns, C, orange, halo);
+  }
+#endif
+  return launch_relax_rb_pass_w<NL, RCOEF, RB_WX>(m, da, res, lev, ns, C, orange, halo);
 }
 /* nrelax sweeps as ceil(nrelax / NSMAX) passes of (almost) equal length; the result does not depend on the split */
 template <int NL>
@@ -1206,11 +1259,17 @@ static int mg_fused(msqg_model *m, const MgProblem &P) {
      restrict + correct): split 6.27; MSQG_MG=rr (residual + first restriction in one kernel) 6.47; MSQG_MG=fused
      (correction too, out of place) 8.03 -- the shared-memory hand-off and the neighbour gathers of a and da cost more
      than the one or two plane reads they save, the split kernels already stream at 75-100 % of the HBM peak. */
+#ifdef MSQG_EXPERIMENTS
   static int v = -1;
   if (v < 0) { const char *e = getenv("MSQG_MG"); v = (e && !strcmp(e, "rr")) ? 1 : (e && !strcmp(e, "fused")) ? 2 : 0; }
   const Geom &g = m->g[m->depth];
-  return (P.mode < 0 && g.bc == 0 && m->depth >= 1 && !(g.nx & 1) && !(g.ny & 1)) ? v : 0;
+  return (P.mode < 0 && g.bc == 0 && m->depth >= 1 && !(g.nx & 1) && !(g.ny & 1) && m->smoother == 0) ? v : 0;
+#else
+  (void)m; (void)P;
+  return 0;
+#endif
 }
+#ifdef MSQG_EXPERIMENTS
 /* residual of P.a (da == NULL) or of P.a + da written to a_new; both leave the residual on levels D and D-1 */
 static int mg_corr_residual(msqg_model *m, const MgProblem &P, const double *da, double *a_new, double *maxres) {
   const int D = m->depth;
@@ -1234,6 +1293,7 @@ static int mg_corr_residual(msqg_model *m, const MgProblem &P, const double *da,
 
 /* mg_cycle, mspg/elliptic.h:43-99 with minlevel = 1 (poisson_layer.h:297).  fused: the residual kernel has already
  * restricted res to level D-1 and the correction a += da is left to the next residual (mg_corr_residual). */
+#endif
 /* restriction of res from level `from` down to level 1, then the up-leg of the cycle on levels 1 .. top (da = 0 on
  * level 1, bilinear prolongation, nrelax sweeps).  With the red-black smoother the levels up to 32^2 run as ONE launch
  * (k_coarse_rb), which also does their restrictions. */
@@ -1311,6 +1371,7 @@ static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mg
   double resb;
   int rc;
   const int fmode = mg_fused(m, P);
+#ifdef MSQG_EXPERIMENTS
   if (fmode == 1) { /* residual + first restriction in one kernel */
     if ((rc = mg_corr_residual(m, P, nullptr, nullptr, &resb))) return rc;
     s.resb = s.resa = resb;
@@ -1348,7 +1409,11 @@ static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mg
       if (P.owner && *P.owner == P.a) { *P.owner = Q.a; m->a_alt.lev[D] = P.a; }
       else CK(cudaMemcpyAsync(P.a, Q.a, (size_t)P.nf * m->g[D].plane * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
     }
-  } else {
+  } else
+#else
+  (void)fmode;
+#endif
+  {
   rc = mg_residual(m, P, &resb);
   if (rc) return rc;
   s.resb = s.resa = resb;

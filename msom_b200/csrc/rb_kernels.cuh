@@ -46,7 +46,7 @@ struct RbArgs {
   Geom g;
   int ns;             /* sweeps of this pass, 1..RB_NSMAX */
   int R;              /* ring rows = 4 ns + 1 + RB_PF */
-  int TX;             /* output columns per strip = RB_WX - 4 ns */
+  int TX;             /* output columns per strip = window columns - 4 ns */
   int rpc;            /* output rows per chunk */
   int ox_lo, ox_hi, oy_lo, oy_hi; /* cells stored by this launch (own cells; a tile may add a ring of halo cells) */
   int xlo, xhi, ylo, yhi;         /* cells that exist in memory: own cells + deep halo on internal sides */
@@ -60,10 +60,10 @@ __device__ __forceinline__ void cp_async8(unsigned smem_addr, const void *gsrc) 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(gsrc));
 }
 
-template <int NL>
+template <int NL, int WXT = RB_WX>
 struct RbCfg {
   static constexpr int NL2 = (NL + 1) / 2;          /* layer pairs (16-byte words per cell) */
-  static constexpr int ARR2 = NL2 * RB_WX;          /* double2 per array per ring row */
+  static constexpr int ARR2 = NL2 * WXT;            /* double2 per array per ring row */
   static constexpr int ROW2 = 2 * ARR2;             /* double2 per ring row: da, then res */
   static constexpr size_t row_bytes = (size_t)ROW2 * 16;
   /* sweeps per pass: bounded by the ring (4 ns + 1 + RB_PF rows <= 227 KB) and by registers (threads = 128 ns) */
@@ -71,11 +71,13 @@ struct RbCfg {
   static_assert((size_t)(4 * NSMAX + 1 + RB_PF) * row_bytes <= 227 * 1024, "ring does not fit");
 };
 
-template <int NL, bool RCOEF>
-__global__ void __launch_bounds__(RbCfg<NL>::NSMAX * 2 * RB_NP, 1)
+/* WXT: window columns, 128 or 64.  The narrow window halves the ring, so two CTAs share an SM (twice the warps to hide
+ * the latency of the Thomas recurrence) at the price of more halo redundancy (64/48 instead of 128/112 at ns = 4). */
+template <int NL, bool RCOEF, int WXT = RB_WX>
+__global__ void __launch_bounds__(RbCfg<NL, WXT>::NSMAX * WXT, WXT == 64 ? 2 : 1)
 k_relax_rb(RbArgs A, RelaxCoef<NL> C) {
-  using Cfg = RbCfg<NL>;
-  constexpr int WX = RB_WX, NP = RB_NP, PF = RB_PF, NSMAX = Cfg::NSMAX;
+  using Cfg = RbCfg<NL, WXT>;
+  constexpr int WX = WXT, NP = WXT / 2, PF = RB_PF, NSMAX = Cfg::NSMAX;
   constexpr int NL2 = Cfg::NL2, ARR2 = Cfg::ARR2, ROW2 = Cfg::ROW2;
   constexpr int EPT = (2 * NL + NSMAX - 1) / NSMAX; /* planes (da: 0..NL-1, res: NL..2NL-1) streamed per thread */
   constexpr int EPO = (NL + NSMAX - 1) / NSMAX;     /* planes stored per thread */
@@ -96,7 +98,7 @@ k_relax_rb(RbArgs A, RelaxCoef<NL> C) {
   const int nrw = jw1 - jw0; /* window rows */
 
   /* ---- streaming state: thread <-> window column wx, planes q0 + i * NSMAX; pointers move one row per step */
-  const int wx = tid & (WX - 1), q0 = tid >> 7;
+  const int wx = tid % WX, q0 = tid / WX;
   const int gxl = x0w + wx;
   const bool lvalid = gxl >= A.xlo && gxl < A.xhi;
   const bool ovalid = gxl >= ox0 && gxl < ox1;

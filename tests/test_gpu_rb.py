@@ -35,8 +35,8 @@ def _level_s(N, nl, level, kw):
 @pytest.mark.parametrize("nl,level,nsweeps", [(2, 3, 1), (2, 5, 4), (3, 6, 4), (4, 7, 4), (4, 6, 3), (4, 5, 2), (4, 8, 1),
                                                (3, 7, 7), (2, 6, 13), (10, 5, 4), (4, 1, 4), (4, 2, 5), (2, 8, 4),
                                                (4, 9, 4), (6, 7, 3), (12, 6, 2), (4, 10, 6)])
-@pytest.mark.parametrize("reuse,tile", [(1, 0), (0, 0), (1, 512)])
-def test_relax_rb_matches_oracle(gpu, nl, level, nsweeps, reuse, tile, monkeypatch):
+@pytest.mark.parametrize("reuse,tile,wxmin", [(1, 0, 1024), (0, 0, 1024), (1, 512, 1024)])
+def test_relax_rb_matches_oracle(gpu, nl, level, nsweeps, reuse, tile, wxmin, monkeypatch):
     """one level, nsweeps red-black sweeps: strips, row chunks, window halos and multi-pass splits all exercised, with the
     streaming kernel (MSQG_RB_TILE=0 forces it on every size) and with the one-window-per-CTA kernel of the small levels"""
     from oracle import oracle as O
@@ -45,6 +45,7 @@ def test_relax_rb_matches_oracle(gpu, nl, level, nsweeps, reuse, tile, monkeypat
         pytest.skip("register-reuse A/B on the smaller levels only")
     monkeypatch.setenv("MSQG_RB_REUSE", str(reuse))
     monkeypatch.setenv("MSQG_RB_TILE", str(tile))
+    monkeypatch.setenv("MSQG_RB_WX_MIN", str(wxmin))   # only read by an EXPERIMENTS build (64-column window)
     N = max(1 << level, 32)
     m = _model(gpu, N, nl)
     n = 1 << level

@@ -380,8 +380,13 @@ def test_fused_cycle_tail_variants(gpu, mode):
     give the same bits, cycle counts and dt as the oracle: MSQG_MG=rr / fused (k_corr_res fusions of correction +
     residual + first restriction) and MSQG_RELAX_CS=2 / 4 (relax hand-off between the CTAs of a thread-block cluster
     through distributed shared memory), MSQG_RELAX=v3 (single-warp wavefront k_relax_lex) and MSQG_RHS=gather
-    (L1-gather right-hand side k_rhs instead of the tiled k_rhs_t)."""
+    (L1-gather right-hand side k_rhs instead of the tiled k_rhs_t).  All but MSQG_RHS=gather exist only in a library built
+    with `make EXPERIMENTS=1` (the default library carries one relax kernel per smoother)."""
     import subprocess, sys
+    from msom_b200 import capi as G0
+    G0.lib().msqg_has_experiments.restype = int
+    if mode != "MSQG_RHS=gather" and not G0.lib().msqg_has_experiments():
+        pytest.skip("rejected variant: built with EXPERIMENTS=1 only")
     code = (
         "import sys, numpy as np\n"
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
