@@ -312,6 +312,24 @@ __global__ void k_place_all(double *__restrict__ full, Geom gfull, const double 
   full[(size_t)f * gfull.plane + GIDX(gfull.pitch, oy + y, ox + x)] = gathered[(((size_t)r * nf + f) * hy + y) * hx + x];
 }
 
+/* a += da on the one-cell halo ring of the INTERNAL sides (cells owned by a neighbouring tile; corners included when both
+ * sides are internal); thread t walks the ring: bottom row, top row, left column, right column */
+__global__ void k_correct_ring(double *__restrict__ a, const double *__restrict__ da, Geom g) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+  const int nx = g.nx, ny = g.ny;
+  int x, y;
+  if (t < nx + 2) { x = t - 1; y = -1; }
+  else if (t < 2 * (nx + 2)) { x = t - (nx + 2) - 1; y = ny; }
+  else if (t < 2 * (nx + 2) + ny) { x = -1; y = t - 2 * (nx + 2); }
+  else if (t < 2 * (nx + 2) + 2 * ny) { x = nx; y = t - 2 * (nx + 2) - ny; }
+  else return;
+  const bool okx = x < 0 ? (g.bc & 1) : (x >= nx ? (g.bc & 2) : true);
+  const bool oky = y < 0 ? (g.bc & 4) : (y >= ny ? (g.bc & 8) : true);
+  if (!okx || !oky) return; /* beyond a physical side: a ghost, rebuilt by k_ghosts */
+  const size_t c = (size_t)f * g.plane + GIDX(g.pitch, y, x);
+  a[c] = a[c] + da[c];
+}
+
 static int g_cycle_rb(msqg_group *G, int nrelax) {
   msqg_model *m0 = G->tiles[0];
   const int D = m0->depth, La = m0->agg_level, nl = G->p.nl;
@@ -341,20 +359,7 @@ static int g_cycle_rb(msqg_group *G, int nrelax) {
     ProfScope ps_g(m0, PROF_XCHG, 100);
     NCK(G->nccl->AllGather(m0->patch_stage, m0->gather_buf, blk, NCCL_DOUBLE, G->comm, G->stream));
   }
-  /* halo of res on the distributed levels: the sweeps recompute up to 2 nrelax border cells of the neighbours */
   const int chunk0 = nrelax < 7 ? nrelax : 7;
-  {
-    std::vector<XItem> items;
-    for (int l = La; l <= D; l++) {
-      XItem X;
-      for (msqg_model *m : G->tiles) { X.arr.push_back(m->res.lev[l]); X.geo.push_back(m->g[l]); }
-      X.nf = nl; X.w = 2 * chunk0; X.ring = 0;
-      if (X.w > m0->g[l].nx) X.w = m0->g[l].nx;
-      if (X.w > m0->g[l].ny) X.w = m0->g[l].ny;
-      items.push_back(X);
-    }
-    if ((rc = exchange_multi(G, items))) return rc;
-  }
   /* replicated coarse levels: every tile solves levels 1 .. La-1 (same arithmetic, same bits everywhere) */
   for (msqg_model *m : G->tiles) {
     k_place_all<<<grid2(hx, hy, b, nranks * nl), b, 0, G->stream>>>(m->res.lev[La - 1], m->g[La - 1], m->gather_buf, hx, hy, G->px, nranks, nl);
@@ -387,8 +392,19 @@ static int g_cycle_rb(msqg_group *G, int nrelax) {
       std::vector<XItem> items(1);
       for (msqg_model *m : G->tiles) { items[0].arr.push_back(m->da.lev[l]); items[0].geo.push_back(m->g[l]); }
       items[0].nf = nl; items[0].w = w; items[0].ring = 0;
+      if (l == La && left == nrelax) {
+        /* the halo of res on ALL distributed levels (the sweeps recompute up to 2 nrelax border cells of the neighbours)
+           rides in the same exchange: one neighbour synchronisation less per cycle */
+        for (int l2 = La; l2 <= D; l2++) {
+          XItem X;
+          for (msqg_model *m : G->tiles) { X.arr.push_back(m->res.lev[l2]); X.geo.push_back(m->g[l2]); }
+          X.nf = nl; X.w = 2 * chunk0; X.ring = 0;
+          if (X.w > m0->g[l2].nx) X.w = m0->g[l2].nx;
+          if (X.w > m0->g[l2].ny) X.w = m0->g[l2].ny;
+          items.push_back(X);
+        }
+      }
       if ((rc = exchange_multi(G, items))) return rc;
-      if (c != chunk0 && left != nrelax) { /* later chunks need the halo of res again only if it was thinner: it never is */ }
       for (msqg_model *m : G->tiles) {
         ProfScope ps(m, l == D ? PROF_RELAX_FINE : PROF_RELAX_COARSE, c);
         NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = relax_rb_tile<NL>(m, l, c, w, C); });
@@ -401,9 +417,19 @@ static int g_cycle_rb(msqg_group *G, int nrelax) {
   for (msqg_model *m : G->tiles) {
     const Geom &g = m->g[D];
     ProfScope ps(m, PROF_CORRECT, 0);
-    k_correct<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->psi.lev[D], m->da.lev[D], g);
+    k_correct<<<grid2(g.nx, g.ny, b, nl), b, 0, G->stream>>>(m->psi.lev[D], m->da.lev[D], g, 1);
     m->launches++;
   }
   CK(cudaGetLastError());
-  return exchange_one(G, MSQG_PSI, D, 1, 1);
+  /* one halo cell of da survived the sweeps: the neighbours' correction of those cells is applied here with the same
+     operands (a_halo + da_halo, the bits the owner computes), then the ghosts of the physical sides next to a halo
+     column / row are rebuilt from it -- no exchange of psi */
+  for (msqg_model *m : G->tiles) {
+    const Geom &g = m->g[D];
+    k_correct_ring<<<dim3((2 * (g.nx + g.ny + 2) + 255) / 256, nl), 256, 0, G->stream>>>(m->psi.lev[D], m->da.lev[D], g);
+    k_ghosts<<<grid2(g.nx + 2, g.ny + 2, b, nl), b, 0, G->stream>>>(m->psi.lev[D], nl, g, -1.);
+    m->launches += 2;
+  }
+  CK(cudaGetLastError());
+  return MSQG_OK;
 }

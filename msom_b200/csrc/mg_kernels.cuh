@@ -470,7 +470,7 @@ __global__ void k_filter_de(double *__restrict__ de_ft, const double *__restrict
 /* ------------------------------------------------------------------ correction
  * mg_cycle tail: a += da ; boundary(a)   (mspg/elliptic.h:92-98).  Ghost ring of
  * the dirichlet(0) field a is written by the boundary cells themselves. */
-__global__ void k_correct(double *__restrict__ a, const double *__restrict__ da, Geom g) {
+__global__ void k_correct(double *__restrict__ a, const double *__restrict__ da, Geom g, int phys_only = 0) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int f = blockIdx.z;
@@ -480,7 +480,11 @@ __global__ void k_correct(double *__restrict__ a, const double *__restrict__ da,
   const double v = ap[c] + da[(size_t)f * g.plane + c];
   ap[c] = v;
   const int nx = g.nx, ny = g.ny;
-  const bool l = x == 0, r = x == nx - 1, bo = y == 0, t = y == ny - 1;
+  /* phys_only: ghosts of the PHYSICAL sides only (red-black tiles keep the neighbour's cells in the ring of an internal
+     side and correct them in place, k_correct_ring); otherwise all four sides, the halo exchange that follows overwrites
+     the internal ones */
+  const int ib = phys_only ? g.bc : 0;
+  const bool l = x == 0 && !(ib & 1), r = x == nx - 1 && !(ib & 2), bo = y == 0 && !(ib & 4), t = y == ny - 1 && !(ib & 8);
   if (l) ap[GIDX(g.pitch, y, -1)] = -v;
   if (r) ap[GIDX(g.pitch, y, nx)] = -v;
   if (bo) ap[GIDX(g.pitch, -1, x)] = -v;

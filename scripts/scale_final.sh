@@ -1,0 +1,13 @@
+#!/bin/bash
+# final multi-GPU lines of the round on an 8-GPU box: strong scaling of 4096^2 x 4 on 4 and 8 GPUs, the 8192^2 x 4
+# points (BASELINE config 4), the 32-member ensemble (config 5)
+run() { # n, tag, extra args
+  n=$1; tag=$2; shift 2
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700+RANDOM%200)) bench.py --gpus $n "$@" > gpurun_out/r02_${tag}.json 2> gpurun_out/r02_${tag}.err
+  echo "$tag rc=$? $(cut -c1-200 gpurun_out/r02_${tag}.json)"
+}
+run 4 scale_4gpu --steps 20 --warmup 5
+run 8 scale_8gpu --steps 20 --warmup 5
+run 4 bench_4gpu_8192x4 --N 8192 --steps 10 --warmup 5
+run 8 bench_8gpu_8192x4 --N 8192 --steps 10 --warmup 5
+run 8 bench_c5_ensemble_8gpu --ensemble --steps 20 --warmup 5
