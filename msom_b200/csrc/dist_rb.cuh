@@ -29,22 +29,6 @@ struct HaloPlan {
   long long off[9];         /* offset of this item in the direction's buffer, doubles */
   double *sbuf[9], *rbuf[9];
 };
-/* blockIdx.y = direction, blockIdx.z = plane; unpack = 1 scatters the receive buffers into the halo */
-__global__ void k_halo_pack(double *__restrict__ a, Geom g, HaloPlan P, int unpack) {
-  const int d = blockIdx.y, f = blockIdx.z;
-  if (!P.on[d]) return;
-  const HaloBox b = unpack ? P.recv[d] : P.send[d];
-  const int bw = b.x1 - b.x0, bh = b.y1 - b.y0;
-  const long long cnt = (long long)bw * bh;
-  double *buf = (unpack ? P.rbuf[d] : P.sbuf[d]) + P.off[d] + (long long)f * cnt;
-  double *pl = a + (size_t)f * g.plane;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x) {
-    const int y = b.y0 + (int)(e / bw), x = b.x0 + (int)(e % bw);
-    const long long c = (long long)(y + 1) * g.pitch + MSQG_OX + x;
-    if (unpack) pl[c] = buf[e]; else buf[e] = pl[c];
-  }
-}
-
 /* ------------------------------------------------------------------ the same exchange through peer memory
  * One process per GPU; every tile's receive area is mapped by its neighbours (CUDA IPC) and the PACK kernel stores the
  * halo straight into the neighbour's memory over NVLink, then raises an arrival flag there; the UNPACK kernel of the
@@ -56,14 +40,21 @@ __global__ void k_halo_pack(double *__restrict__ a, Geom g, HaloPlan P, int unpa
  *   - flags only grow, spins are bounded (an error word is raised instead of hanging the GPU). */
 #define XCHG_MAXITEMS 6
 #define XCHG_SPIN_NS 4000000000ll
+#define XCHG_EPB 1024 /* elements per block: 256 threads x 4 independent loads */
 struct XItemDev { double *arr; Geom g; int nf, w, ring; long long off[9]; };
 struct XchgArgs {
   XItemDev it[XCHG_MAXITEMS];
   int nitems;
   int on[9];
-  double *area;           /* my receive area */
-  double *peer[9];        /* the neighbour's receive area, by direction */
+  int p2p;                /* 1: pack stores into the neighbours' receive areas and raises flags; 0: into local send buffers */
+  double *area;           /* my receive area and control words */
+  double *dst[9];         /* pack destination by direction: the neighbour's receive area (p2p) or my send buffer */
+  double *src[9];         /* unpack source by direction when staged (p2p reads `area`) */
   unsigned long long xcap;
+  int seg[XCHG_MAXITEMS * 9 + 1]; /* prefix sums of the block counts of the segments s = item * 9 + direction: a FLAT grid, every
+                                     block has work (a (blocks, 9, items) grid sized for the largest side spent 10 us per launch on
+                                     scheduling empty blocks for corners and coarse levels) */
+  int nblk_dir[9];        /* pack blocks per direction (last-block detection before the flag is raised) */
 };
 __device__ __forceinline__ unsigned long long *xa_flags(double *area, unsigned long long xcap) { return (unsigned long long *)(area + 2 * 9 * xcap); }
 /* words behind the receive space: [0..8] arrival flags, [16] exchange counter, [17] error, [32..40] pack block counters,
@@ -79,43 +70,60 @@ __device__ __forceinline__ void halo_box_dev(const Geom &g, int w, int ring, int
   else if (dy > 0) { y0 = recv ? g.ny : g.ny - w; y1 = recv ? g.ny + w : g.ny; }
   else { y0 = -eB; y1 = g.ny + eT; }
 }
-/* grid (gx, 9 directions, items) */
+__device__ __forceinline__ void xchg_segment(const XchgArgs &X, int &it, int &d, int &lb) {
+  const int bid = blockIdx.x;
+  int sidx = 0;
+#pragma unroll 1
+  for (int k = 1; k <= X.nitems * 9; k++) sidx += (X.seg[k] <= bid) ? 1 : 0; /* seg is non-decreasing */
+  it = sidx / 9; d = sidx % 9; lb = bid - X.seg[sidx];
+}
 __global__ void __launch_bounds__(256) k_xchg_pack(XchgArgs X) {
-  const int d = blockIdx.y;
-  if (!X.on[d]) return;
+  int it, d, lb;
+  xchg_segment(X, it, d, lb);
   unsigned long long *w_own = xa_flags(X.area, X.xcap);
   const unsigned long long seqn = *(volatile unsigned long long *)(w_own + 16) + 1;
-  const XItemDev &I = X.it[blockIdx.z];
+  const XItemDev &I = X.it[it];
   int x0, x1, y0, y1;
   halo_box_dev(I.g, I.w, I.ring, d, false, x0, x1, y0, y1);
   const int bw = x1 - x0, bh = y1 - y0;
   const long long cnt = (long long)bw * bh, tot = cnt * I.nf;
-  /* the neighbour files what comes from me under ITS direction 8 - d */
-  double *dst = X.peer[d] + ((seqn & 1) * 9 + (8 - d)) * X.xcap + I.off[d];
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(e / cnt);
-    const long long r = e - (long long)f * cnt;
-    const int y = y0 + (int)(r / bw), x = x0 + (int)(r % bw);
-    dst[e] = I.arr[(size_t)f * I.g.plane + (long long)(y + 1) * I.g.pitch + MSQG_OX + x];
+  /* p2p: the neighbour files what comes from me under ITS direction 8 - d, in the buffer of this exchange's parity */
+  double *dst = X.p2p ? X.dst[d] + ((seqn & 1) * 9 + (8 - d)) * X.xcap + I.off[d] : X.dst[d] + I.off[d];
+  double v[4];
+  long long e[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    e[k] = (long long)lb * XCHG_EPB + k * 256 + threadIdx.x;
+    if (e[k] < tot) {
+      const int f = (int)(e[k] / cnt);
+      const long long r = e[k] - (long long)f * cnt;
+      const int y = y0 + (int)(r / bw), x = x0 + (int)(r % bw);
+      v[k] = I.arr[(size_t)f * I.g.plane + (long long)(y + 1) * I.g.pitch + MSQG_OX + x];
+    }
   }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (e[k] < tot) dst[e[k]] = v[k];
+  if (!X.p2p) return;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int *done = (unsigned int *)(w_own + 32) + d;
     const unsigned int t = atomicAdd(done, 1u);
-    if (t == gridDim.x * gridDim.z - 1) { /* last block of this direction: everything is on its way, raise the flag */
+    if (t == (unsigned int)X.nblk_dir[d] - 1) { /* last block of this direction: everything is on its way, raise the flag */
       *done = 0;
       __threadfence_system();
-      unsigned long long *pf = xa_flags(X.peer[d], X.xcap) + (8 - d);
+      unsigned long long *pf = xa_flags(X.dst[d], X.xcap) + (8 - d);
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf), "l"(seqn) : "memory");
     }
   }
 }
 __global__ void __launch_bounds__(256) k_xchg_unpack(XchgArgs X) {
-  const int d = blockIdx.y;
+  int it, d, lb;
+  xchg_segment(X, it, d, lb);
   unsigned long long *w_own = xa_flags(X.area, X.xcap);
   const unsigned long long seqn = *(volatile unsigned long long *)(w_own + 16) + 1;
-  if (X.on[d]) {
+  if (X.p2p) {
     if (threadIdx.x == 0) {
       unsigned long long v;
       long long t0, t1;
@@ -128,25 +136,35 @@ __global__ void __launch_bounds__(256) k_xchg_unpack(XchgArgs X) {
       }
     }
     __syncthreads();
-    const XItemDev &I = X.it[blockIdx.z];
-    int x0, x1, y0, y1;
-    halo_box_dev(I.g, I.w, I.ring, d, true, x0, x1, y0, y1);
-    const int bw = x1 - x0, bh = y1 - y0;
-    const long long cnt = (long long)bw * bh, tot = cnt * I.nf;
-    const double *src = X.area + ((seqn & 1) * 9 + d) * X.xcap + I.off[d];
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
-      const int f = (int)(e / cnt);
-      const long long r = e - (long long)f * cnt;
-      const int y = y0 + (int)(r / bw), x = x0 + (int)(r % bw);
-      I.arr[(size_t)f * I.g.plane + (long long)(y + 1) * I.g.pitch + MSQG_OX + x] = __ldcv(src + e);
-    }
   }
+  const XItemDev &I = X.it[it];
+  int x0, x1, y0, y1;
+  halo_box_dev(I.g, I.w, I.ring, d, true, x0, x1, y0, y1);
+  const int bw = x1 - x0, bh = y1 - y0;
+  const long long cnt = (long long)bw * bh, tot = cnt * I.nf;
+  const double *src = X.p2p ? X.area + ((seqn & 1) * 9 + d) * X.xcap + I.off[d] : X.src[d] + I.off[d];
+  double v[4];
+  long long e[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    e[k] = (long long)lb * XCHG_EPB + k * 256 + threadIdx.x;
+    if (e[k] < tot) v[k] = __ldcv(src + e[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (e[k] < tot) {
+      const int f = (int)(e[k] / cnt);
+      const long long r = e[k] - (long long)f * cnt;
+      const int y = y0 + (int)(r / bw), x = x0 + (int)(r % bw);
+      I.arr[(size_t)f * I.g.plane + (long long)(y + 1) * I.g.pitch + MSQG_OX + x] = v[k];
+    }
+  if (!X.p2p) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int *done = (unsigned int *)(w_own + 48);
     __threadfence();
     const unsigned int t = atomicAdd(done, 1u);
-    if (t == gridDim.x * gridDim.y * gridDim.z - 1) { *done = 0; *(volatile unsigned long long *)(w_own + 16) = seqn; }
+    if (t == gridDim.x - 1) { *done = 0; *(volatile unsigned long long *)(w_own + 16) = seqn; }
   }
 }
 
@@ -194,77 +212,69 @@ static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
         if ((size_t)tot[t][d] > m->xcap) FAIL(MSQG_ERR_ARG, "halo exchange buffer too small");
       }
     }
-  if (G->p2p) {
-    if (items.size() > XCHG_MAXITEMS) FAIL(MSQG_ERR_ARG, "too many lists in one halo exchange");
-    std::vector<XchgArgs> args(nt);
-    for (int t = 0; t < nt; t++) {
-      msqg_model *m = G->tiles[t];
-      XchgArgs &X = args[t];
-      memset(&X, 0, sizeof(X));
-      X.nitems = (int)items.size(); X.area = m->xarea; X.xcap = m->xcap;
-      for (int d = 0; d < 9; d++) { X.on[d] = plans[0][t].on[d]; X.peer[d] = m->peer_area[d]; }
-      for (size_t it = 0; it < items.size(); it++) {
-        XItemDev &I = X.it[it];
-        I.arr = items[it].arr[t]; I.g = items[it].geo[t]; I.nf = items[it].nf; I.w = items[it].w; I.ring = items[it].ring;
-        for (int d = 0; d < 9; d++) I.off[d] = plans[it][t].off[d];
+  if (items.size() > XCHG_MAXITEMS) FAIL(MSQG_ERR_ARG, "too many lists in one halo exchange");
+  std::vector<XchgArgs> args(nt);
+  for (int t = 0; t < nt; t++) {
+    msqg_model *m = G->tiles[t];
+    XchgArgs &X = args[t];
+    memset(&X, 0, sizeof(X));
+    X.nitems = (int)items.size(); X.area = m->xarea; X.xcap = m->xcap; X.p2p = G->p2p;
+    for (int d = 0; d < 9; d++) {
+      X.on[d] = plans[0][t].on[d];
+      X.dst[d] = G->p2p ? m->peer_area[d] : m->xsend[d];
+      X.src[d] = m->xrecv[d];
+      X.nblk_dir[d] = 0;
+    }
+    int nb = 0;
+    for (size_t it = 0; it < items.size(); it++) {
+      XItemDev &I = X.it[it];
+      I.arr = items[it].arr[t]; I.g = items[it].geo[t]; I.nf = items[it].nf; I.w = items[it].w; I.ring = items[it].ring;
+      for (int d = 0; d < 9; d++) {
+        I.off[d] = plans[it][t].off[d];
+        X.seg[it * 9 + d] = nb;
+        if (plans[it][t].on[d]) {
+          const long long tot_e = (long long)items[it].nf * (plans[it][t].send[d].x1 - plans[it][t].send[d].x0) * (plans[it][t].send[d].y1 - plans[it][t].send[d].y0);
+          const int blocks = (int)((tot_e + XCHG_EPB - 1) / XCHG_EPB);
+          nb += blocks; X.nblk_dir[d] += blocks;
+        }
       }
     }
-    for (int pass = 0; pass < 2; pass++)   /* every pack before any unpack: local tiles share one stream */
-      for (int t = 0; t < nt; t++) {
-        long long mx = 0;
-        for (size_t it = 0; it < items.size(); it++)
-          for (int d = 0; d < 9; d++)
-            if (plans[it][t].on[d])
-              mx = std::max(mx, (long long)items[it].nf * (plans[it][t].send[d].x1 - plans[it][t].send[d].x0) * (plans[it][t].send[d].y1 - plans[it][t].send[d].y0));
-        if (mx == 0) continue;
-        /* one element per thread where possible: a thread's loads are dependent round trips to HBM / the peer */
-        int gx = (int)((mx + 255) / 256);
-        if (gx > 1024) gx = 1024;
-        if (gx < 1) gx = 1;
-        if (pass == 0) k_xchg_pack<<<dim3(gx, 9, (unsigned)items.size()), 256, 0, G->stream>>>(args[t]);
-        else k_xchg_unpack<<<dim3(gx, 9, (unsigned)items.size()), 256, 0, G->stream>>>(args[t]);
-        G->tiles[t]->launches++;
-      }
-    CK(cudaGetLastError());
-    return MSQG_OK;
+    X.seg[items.size() * 9] = nb;
   }
-  auto launch = [&](int unpack) {
-    for (size_t it = 0; it < items.size(); it++)
-      for (int t = 0; t < nt; t++) {
-        const HaloPlan &P = plans[it][t];
-        long long mx = 0;
-        for (int d = 0; d < 9; d++)
-          if (P.on[d]) mx = std::max(mx, (long long)(P.send[d].x1 - P.send[d].x0) * (P.send[d].y1 - P.send[d].y0));
-        if (mx == 0) continue;
-        int gx = (int)((mx + 255) / 256);
-        if (gx > 1024) gx = 1024;
-        k_halo_pack<<<dim3(gx, 9, items[it].nf), 256, 0, G->stream>>>(items[it].arr[t], items[it].geo[t], P, unpack);
-        G->tiles[t]->launches++;
-      }
+  auto launch = [&](int unpack) { /* every pack before any unpack: local tiles share one stream */
+    for (int t = 0; t < nt; t++) {
+      const int nb = args[t].seg[items.size() * 9];
+      if (nb == 0) continue;
+      if (!unpack) k_xchg_pack<<<nb, 256, 0, G->stream>>>(args[t]);
+      else k_xchg_unpack<<<nb, 256, 0, G->stream>>>(args[t]);
+      G->tiles[t]->launches++;
+    }
   };
   launch(0);
   CK(cudaGetLastError());
-  if (G->kind == 0) {
-    for (int t = 0; t < nt; t++) {
-      msqg_model *m = G->tiles[t];
-      for (int d = 0; d < 9; d++) {
-        if (tot[t][d] == 0) continue;
-        const int dx = d % 3 - 1, dy = d / 3 - 1;
-        msqg_model *nb = tile_at(G, m->ix + dx, m->iy + dy);
-        CK(cudaMemcpyAsync(m->xrecv[d], nb->xsend[8 - d], (size_t)tot[t][d] * sizeof(double), cudaMemcpyDeviceToDevice, G->stream));
+  if (!G->p2p) {
+    if (G->kind == 0) {
+      for (int t = 0; t < nt; t++) {
+        msqg_model *m = G->tiles[t];
+        for (int d = 0; d < 9; d++) {
+          if (tot[t][d] == 0) continue;
+          const int dx = d % 3 - 1, dy = d / 3 - 1;
+          msqg_model *nb = tile_at(G, m->ix + dx, m->iy + dy);
+          CK(cudaMemcpyAsync(m->xrecv[d], nb->xsend[8 - d], (size_t)tot[t][d] * sizeof(double), cudaMemcpyDeviceToDevice, G->stream));
+        }
       }
+    } else {
+      msqg_model *m = G->tiles[0];
+      NCK(G->nccl->GroupStart());
+      for (int d = 0; d < 9; d++) {
+        if (tot[0][d] == 0) continue;
+        const int dx = d % 3 - 1, dy = d / 3 - 1;
+        const int peer = tile_rank(G, m->ix + dx, m->iy + dy);
+        NCK(G->nccl->Send(m->xsend[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
+        NCK(G->nccl->Recv(m->xrecv[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
+      }
+      NCK(G->nccl->GroupEnd());
     }
-  } else {
-    msqg_model *m = G->tiles[0];
-    NCK(G->nccl->GroupStart());
-    for (int d = 0; d < 9; d++) {
-      if (tot[0][d] == 0) continue;
-      const int dx = d % 3 - 1, dy = d / 3 - 1;
-      const int peer = tile_rank(G, m->ix + dx, m->iy + dy);
-      NCK(G->nccl->Send(m->xsend[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
-      NCK(G->nccl->Recv(m->xrecv[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
-    }
-    NCK(G->nccl->GroupEnd());
   }
   launch(1);
   CK(cudaGetLastError());
