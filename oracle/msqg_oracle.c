@@ -1187,6 +1187,7 @@ static void philox4x32_10(unsigned int c[4], unsigned int k0, unsigned int k1) {
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
 }
+void orc_test_philox(unsigned int *c4, unsigned int k0, unsigned int k1) { philox4x32_10(c4, k0, k1); }
 static void generate_noise(orc_model *m) {
   int n = m->N, D = m->depth, nl = m->nl;
   if (m->noise_mode == 1) {

@@ -85,6 +85,7 @@ void orc_set_smoother(orc_model *m, int smoother);
 /* stochastic forcing: 0 = the reference's sequential libc rand() draws (qg_stochastic.h:9,117-126; default),
    1 = counter-based Philox4x32-10 noise (production mode of the CUDA library: order independent, generated on the device) */
 void orc_set_noise_mode(orc_model *m, int mode, unsigned seed);
+void orc_test_philox(unsigned int *c4, unsigned int k0, unsigned int k1); /* Philox4x32-10 block function (known-answer tests) */
 int orc_get_smoother(orc_model *m);
 void orc_init_noise(orc_model *m, unsigned seed);/* qg.c:60-70 with srand(seed) */
 void orc_remove_mean_psi(orc_model *m);          /* qg.c:66-70 */
