@@ -17,8 +17,9 @@ from common import base_kw, synth_psi  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
-def run(N, nl, steps, **over):
+def run(N, nl, steps, smoother="lex", **over):
     m = O.Model(O.make_params(**base_kw(N, nl, **over)))
+    m.set_smoother(smoother)
     m.set(O.PSI, synth_psi(N, nl))
     m.set_const()
     dts = np.array([m.step() for _ in range(steps)])
@@ -27,4 +28,5 @@ def run(N, nl, steps, **over):
 
 np.savez_compressed(os.path.join(HERE, "oracle_32x2_3steps.npz"), **run(32, 2, 3))
 np.savez_compressed(os.path.join(HERE, "oracle_32x3_modal_2steps.npz"), **run(32, 3, 2, mode_pv_invert=1))
+np.savez_compressed(os.path.join(HERE, "oracle_rb_32x2_3steps.npz"), **run(32, 2, 3, smoother="rb"))
 print("wrote", os.listdir(HERE))

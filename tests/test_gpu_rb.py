@@ -187,3 +187,14 @@ def test_fused_coarse_levels_equal_level_by_level(gpu, N, nl, over, monkeypatch)
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert res[0][2] == res[1][2]
     assert res[0][3] < res[1][3]      # fewer launches
+
+
+def test_rb_against_committed_golden_fixture(gpu):
+    """the CUDA path against the committed fixture of the oracle (regression fixture, tests/golden/make_golden.py)"""
+    import os
+    from msom_b200 import capi as G
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_rb_32x2_3steps.npz"))
+    m = _model(gpu, 32, 2)
+    dts = [m.step() for _ in range(3)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert np.array_equal(m.get(G.PSI), g["psi"]) and np.array_equal(m.get(G.Q), g["q"])

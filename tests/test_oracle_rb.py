@@ -128,3 +128,15 @@ def test_philox_known_answers_and_noise_statistics():
     z = fields[0] / (2. * 0.5)                       # amp * sigma
     assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.std() - 1) < 0.03
     assert abs(np.mean(z ** 3)) < 0.1 and abs(np.mean(z ** 4) - 3) < 0.3
+
+
+def test_red_black_golden_regression():
+    """the oracle with the red-black ordering reproduces its committed outputs (tests/golden/make_golden.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_rb_32x2_3steps.npz"))
+    m = O.Model(O.make_params(**base_kw(32, 2)))
+    m.set_smoother("rb")
+    m.set(O.PSI, synth_psi(32, 2)); m.set_const()
+    dts = [m.step() for _ in range(3)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert np.array_equal(m.get(O.PSI), g["psi"]) and np.array_equal(m.get(O.Q), g["q"])
