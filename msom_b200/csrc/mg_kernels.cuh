@@ -876,6 +876,20 @@ __global__ void k_rowcoef(const double *__restrict__ s, Geom g, LayerMetrics M, 
   }
 }
 
+/* The same table for ONE vertical mode whose lambda = iBu is a field (horizontally varying Fr/Ro, eigmode.h:257-266):
+ * the scalar relaxation divides by d = -lambda[]*sq(Delta) + 2 + 2 ([BASILISK] poisson.h relax(), in-tree copy
+ * mspg/elliptic.h:294-301), accumulated per dimension as the reference does.  out[j][i][6] = 0, 0, d, 1/d, 0, 0 in
+ * the layout of k_rowcoef<1> (per cell), read by the RCOEF instances of the NL = 1 relax kernels. */
+__global__ void k_modecoef(const double *__restrict__ lam, Geom g, double *__restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)g.ny * g.nx) return;
+  const int j = (int)(t / g.nx), ix = (int)(t % g.nx);
+  double d = -lam[GIDX(g.pitch, j, ix)] * (g.Delta * g.Delta);
+  d += 1. + 1.; d += 1. + 1.;
+  double *o = out + t * 6;
+  o[0] = 0.; o[1] = 0.; o[2] = d; o[3] = 1. / d; o[4] = 0.; o[5] = 0.;
+}
+
 /* ------------------------------------------------------------------ relax_layer, warp-specialised
  * Same arithmetic results, schedule (lane (k,c) does row tau - c - 2k - 1 at step tau) and mailbox
  * protocol as k_relax_lex, but each strip is served by TWO warps so that the warp on the critical

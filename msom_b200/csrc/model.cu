@@ -125,6 +125,11 @@ struct msqg_model {
   bool modes_uniform;
   double h_cl2m[MSQG_NLMAX * MSQG_NLMAX], h_cm2l[MSQG_NLMAX * MSQG_NLMAX], h_ibu[MSQG_NLMAX];
   std::vector<double> lam_lev; /* [(depth+1)][nl] lambda per level (restricted) */
+  /* horizontally varying Fr/Ro (eigmod per column, eigmode.h:74-299): lambda = iBu is a field, restricted to every
+     level (poisson(): restriction({alpha, lambda}) [BASILISK]), and the scalar relax kernels read per-cell tables
+     [ny][nx][6] = (0, 0, d, 1/d, 0, 0), d = -lambda*sq(Delta) + 2 + 2, one table per mode and level */
+  double *modecoef[MSQG_NLMAX][MSQG_MAXLEV + 1];
+  int coef_mode;               /* mode whose tables the scalar relax launches read; -1: constant lambda */
   /* scratch */
   double *d_stage;   /* staging [max nf][N][N] */
   size_t stage_doubles;
@@ -477,6 +482,8 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   m->mailbox = nullptr; m->mailbox_words = 0; m->d_dbg = nullptr;
   m->nme_ft = 0; m->energy_vars = 0; m->filter_vars = 0; m->siglev0 = 0.;
   for (int l = 0; l <= MSQG_MAXLEV; l++) m->rowcoef[l] = nullptr;
+  for (int k = 0; k < MSQG_NLMAX; k++) for (int l = 0; l <= MSQG_MAXLEV; l++) m->modecoef[k][l] = nullptr;
+  m->coef_mode = -1; m->modes_uniform = true;
   m->s_rowuniform = false;
   for (int l = 0; l < nl; l++) m->dhf[l] = p->dh[l]; /* qg.h:895-896 */
   m->iRe = p->iRe; m->iRe4 = p->iRe4; m->Eks = p->Eks; m->Ekb = p->Ekb;
@@ -577,6 +584,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->h_err) cudaFreeHost(m->h_err);
   if (m->mailbox) cudaFree(m->mailbox);
   for (int l = 0; l <= MSQG_MAXLEV; l++) if (m->rowcoef[l]) cudaFree(m->rowcoef[l]);
+  for (int k = 0; k < MSQG_NLMAX; k++) for (int l = 0; l <= MSQG_MAXLEV; l++) if (m->modecoef[k][l]) cudaFree(m->modecoef[k][l]);
   if (m->da_patch) cudaFree(m->da_patch);
   if (m->res_patch) cudaFree(m->res_patch);
   if (m->patch_stage) cudaFree(m->patch_stage);
@@ -748,6 +756,15 @@ static RelaxCoef<1> relax_coef_scalar(msqg_model *m, int lev, double lambda) {
 }
 
 /* ------------------------------------------------------------------ relax launch */
+/* coefficient table of the current relax launch: the stretching tables of the layer-coupled solver (k_rowcoef), or
+   the lambda tables of one vertical mode (k_modecoef) while a scalar solve with a lambda FIELD is running */
+static inline const double *relax_table(const msqg_model *m, int lev) {
+  return m->coef_mode >= 0 ? m->modecoef[m->coef_mode][lev] : m->rowcoef[lev];
+}
+static inline bool relax_table_per_cell(const msqg_model *m) { return m->coef_mode >= 0 || !m->s_rowuniform; }
+/* does a relax launch on NL coupled unknowns read tables (true) or per-level constants (false)? */
+template <int NL>
+static inline bool relax_uses_table(const msqg_model *m) { return NL > 1 ? !m->s_uniform : m->coef_mode >= 0; }
 static int ensure_mailbox(msqg_model *m, size_t words) {
   if (words <= m->mailbox_words) return MSQG_OK;
   if (m->mailbox) { CK(cudaStreamSynchronize(m->stream)); CK(cudaFree(m->mailbox)); m->mailbox = nullptr; }
@@ -850,8 +867,8 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
   }
   RelaxArgs A;
   A.da = da; A.res = res; A.g = g; A.nsweeps = nsweeps;
-  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0; A.w_base = 0; A.rowcoef = RCOEF ? m->rowcoef[lev] : nullptr;
-  A.coef_cell = (RCOEF && !m->s_rowuniform) ? 1 : 0;
+  A.mailbox = m->mailbox; A.err = m->d_err; A.dbg = m->d_dbg; A.flags = 0; A.w_base = 0; A.rowcoef = RCOEF ? relax_table(m, lev) : nullptr;
+  A.coef_cell = (RCOEF && relax_table_per_cell(m)) ? 1 : 0;
   if (RCOEF && (g.bc || !A.rowcoef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
   const size_t smem = Cfg::smem_per_worker * WPC;
   /* variant: 0 plain, 1 tile (stored halos), 2 / 3 clusters of 2 / 4 CTAs (undecomposed, uniform stretching, nl <= 4) */
@@ -969,7 +986,7 @@ static int launch_relax(msqg_model *m, double *da, const double *res, int lev, i
     int rc;
     /* k_relax_ws is instantiated for K = 4 only (build time): more than 4 sweeps are consecutive launches, which
        is the same arithmetic; the single-warp k_relax_lex keeps its 8-sweep instance */
-    if (!m->s_uniform) { if (ns > 4) ns = 4; rc = launch_relax_rowcoef<NL>(m, da, res, lev, ns, C); }
+    if (relax_uses_table<NL>(m)) { if (ns > 4) ns = 4; rc = launch_relax_rowcoef<NL>(m, da, res, lev, ns, C); }
     else if (relax_variant() == 1) { if (ns > 4) ns = 4; rc = launch_relax_ws<NL, 4>(m, da, res, lev, ns, C); }
 #ifdef MSQG_EXPERIMENTS
     else if (ns <= 4) rc = launch_relax_w_t<NL, 4>(m, da, res, lev, ns, C);
@@ -1010,8 +1027,8 @@ static int launch_relax_rb_pass_w(msqg_model *m, double *da, const double *res, 
   A.xlo = (g.bc & 1) ? -halo : 0; A.xhi = g.nx + ((g.bc & 2) ? halo : 0);
   A.ylo = (g.bc & 4) ? -halo : 0; A.yhi = g.ny + ((g.bc & 8) ? halo : 0);
   A.par0 = 0; /* tile origins are even on every distributed level (tiles keep >= 8 cells per side) */
-  A.coef = RCOEF ? m->rowcoef[lev] : nullptr;
-  A.coef_cell = (RCOEF && !m->s_rowuniform) ? 1 : 0;
+  A.coef = RCOEF ? relax_table(m, lev) : nullptr;
+  A.coef_cell = (RCOEF && relax_table_per_cell(m)) ? 1 : 0;
   A.reuse = m->rb_reuse;
   if (RCOEF && (g.bc || !A.coef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
   const int nxo_ = A.ox_hi - A.ox_lo, nyo_ = A.oy_hi - A.oy_lo;
@@ -1100,8 +1117,8 @@ static int launch_relax_rb(msqg_model *m, double *da, const double *res, int lev
     const int passes = (left + NSMAX - 1) / NSMAX;
     const int ns = (left + passes - 1) / passes;
     int rc;
-    if (!m->s_uniform && NL > 1) {
-      if constexpr (NL > 1 && NL <= 6) rc = launch_relax_rb_pass<NL, true>(m, m->da.lev[lev], res, lev, ns, C, orange, halo);
+    if (relax_uses_table<NL>(m)) {
+      if constexpr (NL <= 6) rc = launch_relax_rb_pass<NL, true>(m, m->da.lev[lev], res, lev, ns, C, orange, halo);
       else FAIL(MSQG_ERR_ARG, "varRo > 0 with the layer-coupled solver is built for nl <= 6 (nl = %d)", NL);
     } else
       rc = launch_relax_rb_pass<NL, false>(m, m->da.lev[lev], res, lev, ns, C, orange, halo);
@@ -1116,6 +1133,7 @@ static int launch_relax_rb(msqg_model *m, double *da, const double *res, int lev
 static int coarse_top_level(msqg_model *m, int nf_problem, int maxlevel) {
   if (m->smoother != 1) return 0;
   if (nf_problem > 1 && !m->s_uniform) return 0;
+  if (nf_problem == 1 && !m->modes_uniform) return 0; /* lambda is a field: level-by-level launches with tables */
   { const char *e = getenv("MSQG_RB_COARSE"); if (e && atoi(e) == 0) return 0; } /* A/B: level-by-level launches */
   int Lc = RB_COARSE_MAXLEV;
   if (Lc > maxlevel) Lc = maxlevel;
@@ -1341,7 +1359,9 @@ static int mg_levels(msqg_model *m, int nf, int mode, int nrelax, int from, int 
       NL_SWITCH(m->nl, { auto C = relax_coef_layers<NL>(m, l); rc = launch_relax<NL>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C); });
     } else {
       auto C = relax_coef_scalar(m, l, m->lam_lev[(size_t)l * m->nl + mode]);
+      m->coef_mode = m->modes_uniform ? -1 : mode;
       rc = launch_relax<1>(m, m->da.lev[l], m->res.lev[l], l, nrelax, C);
+      m->coef_mode = -1;
     }
     if (rc) return rc;
   }
@@ -1417,7 +1437,7 @@ static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mg
   rc = mg_residual(m, P, &resb);
   if (rc) return rc;
   s.resb = s.resa = resb;
-  const bool graphed = m->smoother == 1 && m->use_graphs && !m->prof_on && (P.nf == 1 || m->s_uniform);
+  const bool graphed = m->smoother == 1 && m->use_graphs && !m->prof_on && (P.nf == 1 ? m->modes_uniform : m->s_uniform);
   std::vector<msqg_model *> self(1, m);
   for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > tolerance); s.i++) {
     /* one cycle + the residual that follows it: a single graph launch in red-black mode */
@@ -1454,12 +1474,14 @@ static int invertq_list(msqg_model *m, List &ql) {
     P.owner = &m->psi.lev[D];
     if ((rc = mg_solve(m, P, 1e-3, &m->mgpsi))) return rc;
   } else {
-    if (!m->modes_uniform) FAIL(MSQG_ERR_ARG, "horizontally varying vertical modes are not supported yet");
+    /* horizontally varying Fr/Ro: the projection matrices are fields (one eigmod per column), as in the reference */
+    const double *matf_l2m = m->modes_uniform ? nullptr : m->cl2m.lev[D];
+    const double *matf_m2l = m->modes_uniform ? nullptr : m->cm2l.lev[D];
     dim3 b(64, 4);
     NL_SWITCH(m->nl, {
       ModeMat<NL> M;
       for (int k = 0; k < NL * NL; k++) M.a[k] = m->h_cl2m[k];
-      k_project<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(ql.lev[D], m->qm.lev[D], g, M, nullptr, 0);
+      k_project<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(ql.lev[D], m->qm.lev[D], g, M, matf_l2m, 0);
     });
     m->launches++;
     CK(cudaGetLastError());
@@ -1471,7 +1493,7 @@ static int invertq_list(msqg_model *m, List &ql) {
     NL_SWITCH(m->nl, {
       ModeMat<NL> M;
       for (int k = 0; k < NL * NL; k++) M.a[k] = m->h_cm2l[k];
-      k_project<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(m->pm.lev[D], m->psi.lev[D], g, M, nullptr, 1);
+      k_project<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(m->pm.lev[D], m->psi.lev[D], g, M, matf_m2l, 1);
     });
     m->launches++;
     CK(cudaGetLastError());
@@ -1711,26 +1733,72 @@ static int set_const_local(msqg_model *m) {
     for (int l = 0; l < nl - 1 && fr_uniform; l++)
       for (size_t c = 1; c < tc && fr_uniform; c++) fr_uniform = m->h_fr[(size_t)l * tc + c] == m->h_fr[(size_t)l * tc];
     m->modes_uniform = fr_uniform && m->p.varRo <= 0;
-    if (!m->modes_uniform) FAIL(MSQG_ERR_ARG, "MODE_PV_INVERT with spatially varying Fr/Ro is not supported yet");
-    double fr[MSQG_MAXL];
-    for (int l = 0; l < nl - 1; l++) fr[l] = m->h_fr[(size_t)l * tc];
-    if ((rc = eigmod_column(nl, m->dhf, fr, ro_y[0], m->h_cl2m, m->h_cm2l, m->h_ibu))) return rc;
-    std::vector<double> h((size_t)nl * nl * tc);
-    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_cl2m[k];
-    if ((rc = pack_to(m, m->cl2m, h.data()))) return rc;
-    for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_cm2l[k];
-    if ((rc = pack_to(m, m->cm2l, h.data()))) return rc;
-    for (int k = 0; k < nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_ibu[k];
-    if ((rc = pack_to(m, m->ibu, h.data()))) return rc;
-    /* poisson(): restriction({alpha,lambda}) [BASILISK] -> per-level lambda */
+    for (int k = 0; k < MSQG_NLMAX; k++)
+      for (int l = 0; l <= MSQG_MAXLEV; l++) if (m->modecoef[k][l]) { CK(cudaFree(m->modecoef[k][l])); m->modecoef[k][l] = nullptr; }
     m->lam_lev.assign((size_t)(D + 1) * nl, 0.);
-    for (int l = 0; l < nl; l++) m->lam_lev[(size_t)D * nl + l] = m->h_ibu[l];
-    for (int lev = D - 1; lev >= 0; lev--)
-      for (int l = 0; l < nl; l++) {
-        const double v = m->lam_lev[(size_t)(lev + 1) * nl + l];
-        m->lam_lev[(size_t)lev * nl + l] = avg4(v, v, v, v);
+    if (m->modes_uniform) {
+      double fr[MSQG_MAXL];
+      for (int l = 0; l < nl - 1; l++) fr[l] = m->h_fr[(size_t)l * tc];
+      if ((rc = eigmod_column(nl, m->dhf, fr, ro_y[0], m->h_cl2m, m->h_cm2l, m->h_ibu))) return rc;
+      std::vector<double> h((size_t)nl * nl * tc);
+      for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_cl2m[k];
+      if ((rc = pack_to(m, m->cl2m, h.data()))) return rc;
+      for (int k = 0; k < nl * nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_cm2l[k];
+      if ((rc = pack_to(m, m->cm2l, h.data()))) return rc;
+      for (int k = 0; k < nl; k++) for (size_t c = 0; c < tc; c++) h[(size_t)k * tc + c] = m->h_ibu[k];
+      if ((rc = pack_to(m, m->ibu, h.data()))) return rc;
+      /* poisson(): restriction({alpha,lambda}) [BASILISK] -> per-level lambda */
+      for (int l = 0; l < nl; l++) m->lam_lev[(size_t)D * nl + l] = m->h_ibu[l];
+      for (int lev = D - 1; lev >= 0; lev--)
+        for (int l = 0; l < nl; l++) {
+          const double v = m->lam_lev[(size_t)(lev + 1) * nl + l];
+          m->lam_lev[(size_t)lev * nl + l] = avg4(v, v, v, v);
+        }
+      for (size_t c = 0; c < tc; c++) sig[c] = fmin(m->p.afilt * sqrt(-1 / m->h_ibu[1]), m->p.Lfmax);
+    } else {
+      /* one dgeev per column, as the reference does (eigmode.h:74-299).  LAPACK is deterministic, so columns with the
+         inputs of the previous one (every column of a row when only Ro(y) varies) reuse its result. */
+      if (m->g[D].bc || m->agg_level > 1) FAIL(MSQG_ERR_ARG, "MODE_PV_INVERT with spatially varying Fr/Ro is not supported on decomposed grids");
+      std::vector<double> hl((size_t)nl * nl * tc), hm((size_t)nl * nl * tc), hb((size_t)nl * tc);
+      double cl[MSQG_NLMAX * MSQG_NLMAX], cm[MSQG_NLMAX * MSQG_NLMAX], ib[MSQG_NLMAX], fr[MSQG_MAXL], last_fr[MSQG_MAXL], last_ro = 0.;
+      bool have = false;
+      for (int j = 0; j < ty; j++)
+        for (int i = 0; i < tx; i++) {
+          const size_t c = (size_t)j * tx + i;
+          for (int l = 0; l < nl - 1; l++) fr[l] = m->h_fr[(size_t)l * tc + c];
+          bool same = have && ro_y[j] == last_ro;
+          for (int l = 0; same && l < nl - 1; l++) same = fr[l] == last_fr[l];
+          if (!same) {
+            if ((rc = eigmod_column(nl, m->dhf, fr, ro_y[j], cl, cm, ib))) return rc;
+            have = true; last_ro = ro_y[j];
+            for (int l = 0; l < nl - 1; l++) last_fr[l] = fr[l];
+          }
+          for (int k = 0; k < nl * nl; k++) { hl[(size_t)k * tc + c] = cl[k]; hm[(size_t)k * tc + c] = cm[k]; }
+          for (int k = 0; k < nl; k++) hb[(size_t)k * tc + c] = ib[k];
+          sig[c] = fmin(m->p.afilt * sqrt(-1 / ib[1]), m->p.Lfmax);
+        }
+      for (int k = 0; k < nl * nl; k++) { m->h_cl2m[k] = hl[(size_t)k * tc]; m->h_cm2l[k] = hm[(size_t)k * tc]; }
+      for (int k = 0; k < nl; k++) m->h_ibu[k] = hb[(size_t)k * tc];
+      if ((rc = pack_to(m, m->cl2m, hl.data()))) return rc;
+      if ((rc = pack_to(m, m->cm2l, hm.data()))) return rc;
+      if ((rc = pack_to(m, m->ibu, hb.data()))) return rc;
+      /* poisson(): restriction({alpha, lambda}) [BASILISK], then the relax tables of every mode and level */
+      dim3 b(32, 8);
+      for (int l = D - 1; l >= 1; l--) {
+        k_restrict<<<grid2(m->g[l].nx, m->g[l].ny, b, nl), b, 0, m->stream>>>(m->ibu.lev[l + 1], m->ibu.lev[l], m->g[l + 1], m->g[l], 1., 1);
+        m->launches++;
       }
-    for (size_t c = 0; c < tc; c++) sig[c] = fmin(m->p.afilt * sqrt(-1 / m->h_ibu[1]), m->p.Lfmax);
+      CK(cudaGetLastError());
+      for (int k = 0; k < nl; k++)
+        for (int l = 1; l <= D; l++) {
+          const Geom &gl = m->g[l];
+          const size_t ent = (size_t)gl.ny * gl.nx;
+          CK(cudaMalloc(&m->modecoef[k][l], ent * 6 * sizeof(double)));
+          k_modecoef<<<(unsigned)((ent + 127) / 128), 128, 0, m->stream>>>(m->ibu.lev[l] + (size_t)k * gl.plane, gl, m->modecoef[k][l]);
+          m->launches++;
+        }
+      CK(cudaGetLastError());
+    }
   } else {
     std::vector<double> rd(tc);
     if ((rc = unpack_from(m, m->rd, rd.data()))) return rc;

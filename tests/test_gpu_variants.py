@@ -39,6 +39,44 @@ def test_modal_inversion(gpu, N, nl, nsteps):
     assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI)) and np.array_equal(mg.get(G.Q), mo.get(O.Q))
 
 
+@pytest.mark.parametrize("smoother", ["lex", "rb"])
+@pytest.mark.parametrize("N,nl,varRo,frfield,nsteps", [(64, 2, 1, 0, 3), (64, 3, 0, 1, 3), (128, 3, 1, 1, 2), (32, 5, 1, 1, 2)])
+def test_modal_inversion_varying_modes(gpu, N, nl, varRo, frfield, nsteps, smoother):
+    """MODE_PV_INVERT 1 with horizontally varying Fr / Ro: the reference runs dgeev in every column (eigmode.h:74-299),
+    so the projection matrices cl2m / cm2l and lambda = iBu are FIELDS; poisson() restricts lambda to every level
+    ([BASILISK] restriction({alpha, lambda})) and relax() divides by -lambda[]*sq(Delta) + 4 cell by cell.  Bit-exact
+    against the oracle in both sweep orders, equal cycle counts in every mode."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    if O._lapack_path() is None:
+        pytest.skip("no LAPACK dgeev (eigmode.h:153)")
+    mo, mg, psi = make_pair(N, nl, smoother=smoother, mode_pv_invert=1, varRo=varRo)
+    if frfield:
+        rng = np.random.default_rng(78)
+        y, x = np.meshgrid((np.arange(N) + 0.5) / N, (np.arange(N) + 0.5) / N, indexing="ij")
+        fr = np.zeros_like(psi)
+        for l in range(nl - 1):
+            fr[l] = (0.003 + 0.002 * l) * (1 + 0.3 * np.sin(2 * np.pi * x) * np.cos(np.pi * y) + 0.05 * rng.uniform(-1, 1, (N, N)))
+        mo.set(O.FR, fr); mg.set(G.FR, fr)
+    mo.set_const(); mg.set_const()
+    ibu = mo.get(O.IBU)
+    assert np.ptp(ibu[1]) > 0                                   # the modes do vary
+    for fid_g, fid_o in ((G.IBU, O.IBU), (G.CL2M, O.CL2M), (G.CM2L, O.CM2L), (G.Q, O.Q)):
+        assert np.array_equal(mg.get(fid_g), mo.get(fid_o))
+    z = np.zeros_like(psi)
+    mo.set(O.PSI, z); mg.set(G.PSI, z)
+    mo.invertq(); mg.invertq()
+    for mode in range(nl):
+        so, sg = mo.mgstats(mode), mg.mgstats(mode)
+        assert (sg.i, sg.nrelax, sg.resb, sg.resa) == (so.i, so.nrelax, so.resb, so.resa), mode
+    assert np.array_equal(mg.get(G.PM), mo.get(O.PM))
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    for _ in range(nsteps):
+        assert mg.step() == mo.step()
+    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI)) and np.array_equal(mg.get(G.Q), mo.get(O.Q))
+
+
 @pytest.mark.parametrize("N,nl,nsteps", [(64, 3, 4), (32, 2, 6)])
 def test_stochastic_forcing(gpu, N, nl, nsteps):
     """qg_stochastic.h: noise on libc rand() in the reference traversal order, float dts, relaxation term,
