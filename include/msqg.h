@@ -131,6 +131,13 @@ int msqg_set_flag_topo(msqg_model *m, int flag);  /* flag_topo, qg.h:971-977 */
  * creation from the environment variable MSQG_SMOOTHER=rb. */
 int msqg_set_smoother(msqg_model *m, int smoother);
 int msqg_get_smoother(msqg_model *m);
+/* The reference's compile-time variant -DENERGY_CONSERV=1 (msqg/qg.h:310-373, qg_energy.h:33-140) as a runtime switch:
+ * advection_pv advects the full PV (jacobian(po, qot)) and drops J(psi_l, psi_l+1) from the stretching Jacobians,
+ * advection_de books jacobian(po, comp_q(po)) in de_j1.  0 (default) is the default build of the reference.  Also set
+ * at creation from the environment variable MSQG_ENERGY_CONSERV=1 (what `qcc -DENERGY_CONSERV=1` is to qg.e).  The
+ * other compile-time switch of qg.h, _LS_RV = 0, needs no entry point: it is the arithmetic of flsrv = 0. */
+int msqg_set_energy_conserv(msqg_model *m, int on);
+int msqg_get_energy_conserv(msqg_model *m);
 /* 1 if the library was built with -DMSQG_EXPERIMENTS (rejected kernel variants kept for A/B measurements) */
 int msqg_has_experiments(void);
 /* reset_layer_var (layer.h:37-41): zero the interior, ghost ring untouched */

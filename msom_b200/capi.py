@@ -93,6 +93,8 @@ def lib():
     L.msqg_set_flag_topo.argtypes = [vp, C.c_int]
     L.msqg_set_smoother.argtypes = [vp, C.c_int]
     L.msqg_get_smoother.argtypes = [vp]
+    L.msqg_set_energy_conserv.argtypes = [vp, C.c_int]
+    L.msqg_get_energy_conserv.argtypes = [vp]
     L.msqg_set_keep_dq.argtypes = [vp, C.c_int]
     L.msqg_set_dissipation.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
     L.msqg_set_const.argtypes = [vp]
@@ -197,6 +199,10 @@ class Model:
     def set_smoother(self, name):
         """'lex': the reference's sweep order (default, parity path); 'rb': red-black ordering (throughput mode)"""
         check(self.L.msqg_set_smoother(self.h, {"lex": 0, "rb": 1}[name]))
+
+    def set_energy_conserv(self, on):
+        """the reference's -DENERGY_CONSERV=1 build (qg.h:310-373) as a runtime switch"""
+        check(self.L.msqg_set_energy_conserv(self.h, int(bool(on))))
 
     def set_const(self):
         check(self.L.msqg_set_const(self.h))

@@ -162,6 +162,7 @@ struct msqg_model {
   std::vector<std::pair<int, int>> *swap_log; /* while a cycle is being recorded: (tile index, level) of every da/da2 swap */
   int tile_index;
   int use_graphs;
+  int econs;       /* the reference's -DENERGY_CONSERV=1 build as a runtime switch (msqg_set_energy_conserv) */
   int smoother;    /* 0: reference-order (lexicographic) Gauss-Seidel, the parity path; 1: red-black ordering (rb_kernels.cuh) */
   int rb_reuse;    /* rb kernel: neighbours carried in registers (MSQG_RB_REUSE=0 switches it off, A/B tests) */
   /* optional per-launch timing (CUDA events on the model's stream) */
@@ -493,6 +494,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   m->flag_topo = 0; m->has_qforc = 0; m->has_zp = 0; m->const_set = 0;
   m->total_cycles = 0; m->launches = 0; m->keep_dq = 0; m->prof_on = 0; m->prof_next = 0;
   { const char *e = getenv("MSQG_SMOOTHER"); m->smoother = (e && !strcmp(e, "rb")) ? 1 : 0; }
+  { const char *e = getenv("MSQG_ENERGY_CONSERV"); m->econs = (e && atoi(e) == 1) ? 1 : 0; }
   { const char *e = getenv("MSQG_RB_REUSE"); m->rb_reuse = (e && atoi(e) == 0) ? 0 : 1; }
   { const char *e = getenv("MSQG_GRAPH"); m->use_graphs = (e && atoi(e) == 0) ? 0 : 1; }
   m->swap_log = nullptr; m->tile_index = 0;
@@ -632,6 +634,12 @@ extern "C" int msqg_set_smoother(msqg_model *m, int smoother) {
   m->graphs.clear();
   return MSQG_OK;
 }
+extern "C" int msqg_set_energy_conserv(msqg_model *m, int on) {
+  if (on != 0 && on != 1) FAIL(MSQG_ERR_ARG, "energy_conserv is 0 or 1");
+  m->econs = on;
+  return MSQG_OK;
+}
+extern "C" int msqg_get_energy_conserv(msqg_model *m) { return m->econs; }
 extern "C" int msqg_get_smoother(msqg_model *m) { return m->smoother; }
 extern "C" int msqg_has_experiments(void) {
 #ifdef MSQG_EXPERIMENTS
@@ -1905,10 +1913,19 @@ static int rhs_launch(msqg_model *m, List &q_ev, const double *q_in, double *q_o
   A.dt = dt; A.itr = m->p.itr_stoch; A.dts = dts;
   A.has_pg = m->has_pg; A.has_zp = m->has_zp; A.use_tmp = (m->iRe != 0. || m->iRe4 != 0.);
   A.flag_topo = m->flag_topo; A.stochastic = m->p.stochastic;
+  A.econs = (m->econs && !m->p.stochastic) ? 1 : 0;
+  if (A.econs) {
+    /* ENERGY_CONSERV (qg.h:310-373): J(psi, q) reads the 3 x 3 neighbourhood of the evolving PV, ghosts included;
+       the fused stage update does not keep them (nothing else reads them), so they are rebuilt here */
+    if (g.bc) FAIL(MSQG_ERR_ARG, "the ENERGY_CONSERV variant is not available on decomposed grids");
+    dim3 bg(32, 8);
+    k_ghosts<<<grid2(g.nx + 2, g.ny + 2, bg, nl), bg, 0, m->stream>>>(q_ev.lev[D], nl, g, -1.);
+    m->launches++;
+  }
   ProfScope ps(m, PROF_RHS, 0);
   static int rhs_variant = -1; /* MSQG_RHS=gather keeps the L1-gather kernel on every configuration (A/B measurements) */
   if (rhs_variant < 0) { const char *e = getenv("MSQG_RHS"); rhs_variant = (e && !strcmp(e, "gather")) ? 0 : 1; }
-  if (rhs_variant == 1 && !A.has_pg && !A.has_zp && !A.flag_topo && !A.stochastic) {
+  if (rhs_variant == 1 && !A.has_pg && !A.has_zp && !A.flag_topo && !A.stochastic && !A.econs) {
     dim3 bt(RT_X, RT_Y);
     NL_SWITCH(nl, k_rhs_t<NL><<<grid2(g.nx, g.ny, bt), bt, 0, m->stream>>>(A));
   } else {
@@ -2090,7 +2107,7 @@ static int ensure_filter_lists(msqg_model *m) {
   int rc;
   if (!m->qof.nf) {
     if ((rc = alloc_list(m, m->qof, nl, -1., D, D))) return rc;
-    if ((rc = alloc_list(m, m->tmp2, nl, -1., D, D))) return rc;
+    if (!m->tmp2.nf && (rc = alloc_list(m, m->tmp2, nl, -1., D, D))) return rc; /* shared with advection_de's ENERGY_CONSERV branch */
     if ((rc = alloc_list(m, m->siglev, 1, 1., 0, D))) return rc;
     if ((rc = alloc_list(m, m->wvs, nl, -1., 0, D - 1))) return rc;
     if ((rc = alloc_list(m, m->wvw, nl, -1., 0, D))) return rc;
@@ -2276,6 +2293,14 @@ extern "C" int msqg_energy_tend(msqg_model *m, double dt, double ediag) {
   A.cekb = m->Ekb / (m->p.Rom * 2 * m->dhf[nl - 1]);
   A.dt = dt; A.ediag = ediag;
   A.has_pg = m->has_pg; A.has_zp = m->has_zp; A.nme_ft = m->nme_ft;
+  if (m->econs) { /* advection_de's ENERGY_CONSERV branch: comp_q(pol, tmp2l), qg_energy.h:33-35 */
+    if (!m->tmp2.nf && (rc = alloc_list(m, m->tmp2, nl, -1., D, D))) return rc;
+    dim3 bq(64, 4);
+    LayerMetrics M = metrics_of(m);
+    NL_SWITCH(nl, k_comp_q<NL><<<grid2(g.nx, g.ny, bq), bq, 0, m->stream>>>(m->psi.lev[D], m->str.lev[D], m->tmp2.lev[D], g, M));
+    m->launches++;
+    A.qt = m->tmp2.lev[D];
+  }
   dim3 b(32, 4);
   NL_SWITCH(nl, k_energy<NL><<<grid2(g.nx, g.ny, b), b, 0, m->stream>>>(A));
   m->launches++;

@@ -203,6 +203,7 @@ struct RhsArgs {
   double dt, itr;
   float dts;                          /* stochastic: float, qg_stochastic.h:133-136 */
   int has_pg, has_zp, use_tmp, flag_topo, stochastic;
+  int econs; /* ENERGY_CONSERV (qg.h:310-373): advect q_ev instead of zeta + J(psi_l, psi_l+1); k_rhs only */
 };
 
 /* advection_pv (qg.h:287-380; stochastic variant qg_stochastic.h:17-111),
@@ -233,17 +234,17 @@ k_rhs(RhsArgs A) {
     /* --- advection_pv */
     if (l < NL - 1) {
       const double *po2 = A.psi + (l + 1) * pl, *pp2 = A.pp + (l + 1) * pl;
-      if (!A.stochastic) {
+      if (!A.stochastic && !A.econs) {
         jd = jac(po, po2, c, P, g);
         if (A.has_pg) jd = jd + jac(pp, po2, c, P, g) + jac(po, pp2, c, P, g);
-      } else {
+      } else { /* stochastic (qg_stochastic.h:35-36) and ENERGY_CONSERV (qg.h:311): no J(psi_l, psi_l+1) */
         jd = A.has_pg ? jac(pp, po2, c, P, g) + jac(po, pp2, c, P, g) : 0.;
       }
     }
     double adv;
     const double be = div_by(A.beta * (po[c - 1] - po[c + 1]), g.D2x, g.rD2x);
     if (!A.stochastic || l > 0) {
-      adv = jac(po, qo, c, P, g);
+      adv = jac(po, A.econs ? A.q_ev + l * pl : qo, c, P, g); /* ENERGY_CONSERV: jacobian(po, qot), qg.h:312 */
       if (A.has_pg) adv = adv + jac(pp, qo, c, P, g);
       adv = adv + be;
     } else { /* stochastic top layer omits J(psi,zeta), qg_stochastic.h:39-40 */
@@ -448,6 +449,7 @@ k_rhs_t(RhsArgs A) {
 struct EnergyArgs {
   const double *psi, *zeta, *tmp, *pp, *zp, *s;
   double *de_bf, *de_vd, *de_j1, *de_j2, *de_j3, *po_mft;
+  const double *qt; /* ENERGY_CONSERV: comp_q(psi) (tmp2l, qg_energy.h:33-35), else NULL */
   Geom g;
   double idh0[MSQG_NLMAX], idh1[MSQG_NLMAX];
   double beta, iRe, iRe4, ceks, cekb, dt, ediag;
@@ -500,6 +502,7 @@ k_energy(EnergyArgs A) {
       a2 = j2 + s0 * (ju_2 + jc) * A.idh0[l];
       a3 = be + s0 * (ju_3 - jc) * A.idh0[l];
     }
+    if (A.qt) a1 = jac(po, A.qt + l * pl, c, P, g); /* ENERGY_CONSERV, qg_energy.h:66,102,134 */
     A.de_j1[l * pl + c] += a1 * dt * w;
     if (A.has_pg) A.de_j2[l * pl + c] += a2 * dt * w;
     double d3 = A.de_j3[l * pl + c];

@@ -32,7 +32,7 @@
 #define HUGEV 1e30
 #define TEPS 1e-9
 
-enum { BC_DIRICHLET0 = 0, BC_NEUMANN = 1 };
+enum { BC_DIRICHLET0 = 0, BC_NEUMANN = 1, BC_PERIODIC = 2 };
 
 /* ------------------------------------------------------------------ grid
  * [BASILISK] grid/multigrid.h: levels 0..depth, level l has 2^l x 2^l cells,
@@ -73,12 +73,22 @@ static void fl_copy_level(flist *dst, const flist *src, int l) {
  * the order right, left, top, bottom; each side's loop runs over the full
  * tangential range *including ghosts*, so corners end up with the y-BC applied
  * to the x-ghost.  dirichlet(0): ghost = -interior (layer.h:17-21);
- * default (symmetry): ghost = interior. */
+ * default (symmetry): ghost = interior.
+ * periodic(right); periodic(top) (qg.h:842-846, sbc = -1): the ghost ring holds the cells of the opposite side,
+ * the y pass again runs over the x ghosts, so a corner holds the diagonally opposite cell; like every ghost it is
+ * only refreshed by boundary calls (a Gauss-Seidel sweep reads the pre-sweep value across the seam). */
 static void boundary_level(flist *f, int l) {
   int n = LN(l);
   double sg = (f->bc == BC_DIRICHLET0) ? -1. : 1.;
   for (int k = 0; k < f->nf; k++) {
     double *a = FL(f, k, l);
+    if (f->bc == BC_PERIODIC) {
+      for (int j = -1; j <= n; j++) a[IDX(n, n, j)] = a[IDX(n, 0, j)];
+      for (int j = -1; j <= n; j++) a[IDX(n, -1, j)] = a[IDX(n, n - 1, j)];
+      for (int i = -1; i <= n; i++) a[IDX(n, i, n)] = a[IDX(n, i, 0)];
+      for (int i = -1; i <= n; i++) a[IDX(n, i, -1)] = a[IDX(n, i, n - 1)];
+      continue;
+    }
     for (int j = -1; j <= n; j++) a[IDX(n, n, j)] = sg * a[IDX(n, n - 1, j)]; /* right */
     for (int j = -1; j <= n; j++) a[IDX(n, -1, j)] = sg * a[IDX(n, 0, j)];    /* left */
     for (int i = -1; i <= n; i++) a[IDX(n, i, n)] = sg * a[IDX(n, i, n - 1)]; /* top */
@@ -161,12 +171,15 @@ struct orc_model {
   int total_cycles;
   int agg_n; /* MPI-emulation: levels with n < agg_n are swept as one block */
   int noise_mode; unsigned int noise_seed; unsigned long long noise_draw; /* orc_set_noise_mode */
+  int energy_conserv; /* the reference's -DENERGY_CONSERV=1 build (qg.h:310-373, qg_energy.h:33-140) as a runtime switch */
   int smoother; /* 0: the reference's lexicographic sweep; 1: red-black ordering of the same cell update (orc_set_smoother) */
 };
 
 /* create_layer_var, layer.h:5-35 */
 static flist create_layer_var(int nf, int bc_type, int depth) {
-  flist f = fl_new(nf, bc_type == 0 ? BC_DIRICHLET0 : BC_NEUMANN, depth);
+  /* bc_type 0: dirichlet(0) on the four sides; > 0: [BASILISK]'s default (symmetry); < 0: nothing set after
+     periodic(right), periodic(top) (qg.h:842-846: bc_type = -2, and bc_type + 1 = -1 for Frl / strl) */
+  flist f = fl_new(nf, bc_type == 0 ? BC_DIRICHLET0 : (bc_type < 0 ? BC_PERIODIC : BC_NEUMANN), depth);
   boundary(&f);
   return f;
 }
@@ -256,6 +269,8 @@ orc_model *orc_create(const orc_params *p) {
   while ((1 << depth) < p->N) depth++;
   m->depth = depth;
   int nl = p->nl, bc = 0;
+  if (p->sbc == -1) bc = -2; /* qg.h:842-846 */
+  const int bcs = bc < 0 ? -1 : 1; /* plain `scalar x[]` globals: default boundaries, periodic after periodic() */
   m->pol = create_layer_var(nl, bc, depth);
   m->qol = create_layer_var(nl, bc, depth);
   m->ppl = create_layer_var(nl, bc, depth);
@@ -275,7 +290,7 @@ orc_model *orc_create(const orc_params *p) {
     m->cm2l = create_layer_var(nl * nl, bc + 1, depth);
   }
   if (p->stochastic) {
-    m->s_stochl = create_layer_var(nl, 0, depth);
+    m->s_stochl = create_layer_var(nl, 0, depth); /* qg_stochastic.h:157-159: bc_type = 0 whatever sbc is */
     m->n_stochl = create_layer_var(nl, 0, depth);
   }
   if (p->nptr > 0) { /* qg.h:867-870: bc_type+1 (Basilisk's default, zero-gradient, boundaries); clones inherit them */
@@ -284,11 +299,11 @@ orc_model *orc_create(const orc_params *p) {
     m->ptr_pred = create_layer_var(nl * p->nptr, bc + 1, depth);
     m->dptrl = create_layer_var(nl * p->nptr, bc + 1, depth);
   }
-  m->Ro = create_layer_var(1, 1, depth);
-  m->Rd = create_layer_var(1, 1, depth);
-  m->topo = create_layer_var(1, 1, depth);
-  m->sig_filt = create_layer_var(1, 1, depth);
-  m->sig_lev = create_layer_var(1, 1, depth);
+  m->Ro = create_layer_var(1, bcs, depth);
+  m->Rd = create_layer_var(1, bcs, depth);
+  m->topo = create_layer_var(1, bcs, depth);
+  m->sig_filt = create_layer_var(1, bcs, depth);
+  m->sig_lev = create_layer_var(1, bcs, depth);
   m->qofl = create_layer_var(nl, bc, depth);   /* qg.h:860 */
   m->wvl = create_layer_var(1, 0, depth);      /* scalar w[] with w[top] = w[bottom] = w[right] = w[left] = 0, qg.h:525-529 */
   m->dhc = (double *)calloc(nl, sizeof(double));
@@ -380,6 +395,8 @@ void orc_set_decomp(orc_model *m, int px, int py, int agg_n) { m->p.px = px; m->
 void orc_set_noise_mode(orc_model *m, int mode, unsigned seed) { m->noise_mode = mode == 1; m->noise_seed = seed; m->noise_draw = 0; }
 void orc_set_smoother(orc_model *m, int smoother) { m->smoother = smoother == 1 ? 1 : 0; }
 int orc_get_smoother(orc_model *m) { return m->smoother; }
+/* the reference's compile-time variant -DENERGY_CONSERV=1 (qg.h:310-373, qg_energy.h:33-140) as a runtime switch */
+void orc_set_energy_conserv(orc_model *m, int on) { m->energy_conserv = on ? 1 : 0; }
 
 /* ------------------------------------------------------------ operators */
 /* laplacian macro, qg.h:169.  Like the reference's it has NO outer parentheses:
@@ -487,14 +504,17 @@ static double comp_vel_timestep(orc_model *m, const double *po, double dtmax) {
   return dtmax;
 }
 
-/* advection_pv, qg.h:287-394 (_LS_RV=1, !ENERGY_CONSERV) and the stochastic
- * replacement qg_stochastic.h:17-111.  Arguments as called from update_qg
+/* advection_pv, qg.h:287-394 (_LS_RV=1; both branches of ENERGY_CONSERV, selected by
+ * m->energy_conserv) and the stochastic replacement qg_stochastic.h:17-111 (which has no
+ * ENERGY_CONSERV branch).  _LS_RV=0 is the same arithmetic as flsrv = 0 (zetapl stays 0, and
+ * x + jacobian(po, 0) == x).  Arguments as called from update_qg
  * (qg.h:623): qol=zeta, qotl=q, pol=psi, dqol=updates. */
 static double advection_pv(orc_model *m, flist *zl, flist *qtl, flist *pl, flist *dql, double dtmax) {
   int n = m->N, D = m->depth, nl = m->nl;
   double Delta = m->L0 / n, beta = m->p.beta;
   const double *idh0 = m->idh0, *idh1 = m->idh1;
   int st = m->p.stochastic;
+  int ec = m->energy_conserv && !st;
   double itr = m->p.itr_stoch;
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < n; i++)
@@ -508,7 +528,11 @@ static double advection_pv(orc_model *m, flist *zl, flist *qtl, flist *pl, flist
         double *dqo = FL(dql, l, D);
         const double *po2 = FL(pl, l + 1, D), *pp2 = FL(&m->ppl, l + 1, D);
         const double *s1 = FL(&m->strl, l, D), *s0;
-        if (!st) {
+        if (ec) { /* qg.h:310-312 */
+          jd = jacobian(pp, po2, n, i, j, Delta) + jacobian(po, pp2, n, i, j, Delta);
+          dqo[c] += jacobian(po, qot, n, i, j, Delta) + jacobian(pp, qo, n, i, j, Delta) +
+                    BETA_EFFECT(po, n, i, j, beta, Delta) + s1[c] * jd * idh1[l];
+        } else if (!st) {
           jd = jacobian(po, po2, n, i, j, Delta) + jacobian(pp, po2, n, i, j, Delta) + jacobian(po, pp2, n, i, j, Delta);
           dqo[c] += jacobian(po, qo, n, i, j, Delta) + jacobian(pp, qo, n, i, j, Delta) +
                     BETA_EFFECT(po, n, i, j, beta, Delta) + s1[c] * jd * idh1[l];
@@ -524,11 +548,11 @@ static double advection_pv(orc_model *m, flist *zl, flist *qtl, flist *pl, flist
           po2 = FL(pl, l + 1, D); pp2 = FL(&m->ppl, l + 1, D);
           s0 = FL(&m->strl, l - 1, D); s1 = FL(&m->strl, l, D);
           ju = -jd;
-          if (!st)
+          if (!st && !ec)
             jd = jacobian(po, po2, n, i, j, Delta) + jacobian(pp, po2, n, i, j, Delta) + jacobian(po, pp2, n, i, j, Delta);
           else
             jd = jacobian(pp, po2, n, i, j, Delta) + jacobian(po, pp2, n, i, j, Delta);
-          dqo[c] += jacobian(po, qo, n, i, j, Delta) + jacobian(pp, qo, n, i, j, Delta) +
+          dqo[c] += jacobian(po, ec ? qot : qo, n, i, j, Delta) + jacobian(pp, qo, n, i, j, Delta) +
                     BETA_EFFECT(po, n, i, j, beta, Delta) + s0[c] * ju * idh0[l] + s1[c] * jd * idh1[l];
           dqo[c] += jacobian(po, qp, n, i, j, Delta);
           if (st) dqo[c] += -qot[c] * itr;
@@ -538,7 +562,7 @@ static double advection_pv(orc_model *m, flist *zl, flist *qtl, flist *pl, flist
         qp = FL(&m->zetapl, l, D); dqo = FL(dql, l, D);
         s0 = FL(&m->strl, l - 1, D);
         ju = -jd;
-        dqo[c] += jacobian(po, qo, n, i, j, Delta) + jacobian(pp, qo, n, i, j, Delta) +
+        dqo[c] += jacobian(po, ec ? qot : qo, n, i, j, Delta) + jacobian(pp, qo, n, i, j, Delta) +
                   BETA_EFFECT(po, n, i, j, beta, Delta) + s0[c] * ju * idh0[l];
         dqo[c] += jacobian(po, qp, n, i, j, Delta);
         if (st) dqo[c] += -qot[c] * itr;
@@ -1507,8 +1531,8 @@ void orc_get_siglev(orc_model *m, int level, double *v) {
 void orc_wavelet_filter(orc_model *m, double dtflt) { wavelet_filter(m, &m->qol, &m->pol, &m->qofl, dtflt, m->nbar); }
 
 /* ----------------------------------------------------------- energy diagnostics, msqg/qg_energy.h
- * "We multiply all terms of the PV equation by -po*dt" (:1-5).  Built as the reference is by default:
- * _LS_RV = 1, no ENERGY_CONSERV. */
+ * "We multiply all terms of the PV equation by -po*dt" (:1-5).  _LS_RV = 1; the ENERGY_CONSERV branch of
+ * advection_de (:33-35, :64-66, :100-102, :132-134) is selected by m->energy_conserv. */
 static void set_vars_energy(orc_model *m) { /* qg_energy.h:244-253 */
   if (m->energy_vars) return;
   flist *L[8] = {&m->de_bfl, &m->de_vdl, &m->de_j1l, &m->de_j2l, &m->de_j3l, &m->de_ftl, &m->tmp2l, &m->po_mft};
@@ -1532,7 +1556,10 @@ static void advection_de(orc_model *m, flist *ql, flist *pl, double dt, double e
   int n = m->N, D = m->depth, nl = m->nl;
   double Delta = m->L0 / n, beta = m->p.beta;
   const double *idh0 = m->idh0, *idh1 = m->idh1;
+  const int ec = m->energy_conserv;
+  if (ec) comp_q(m, pl, &m->tmp2l); /* qg_energy.h:33-35 */
 #define JC(a, b) jacobian(a, b, n, i, j, Delta)
+#define QT(l) FL(&m->tmp2l, l, D)
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) {
       size_t c = IDX(n, i, j);
@@ -1547,7 +1574,8 @@ static void advection_de(orc_model *m, flist *ql, flist *pl, double dt, double e
         jd_2 = JC(pp, po2);
         jd_3 = JC(po, pp2);
         jc = JC(po, pp);
-        de_j1[c] += (JC(po, qo) + s1[c] * jd_1 * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        if (ec) de_j1[c] += (JC(po, QT(l))) * dt * (-po[c] * (1 - ediag) + ediag);
+        else de_j1[c] += (JC(po, qo) + s1[c] * jd_1 * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
         de_j2[c] += (JC(pp, qo) + s1[c] * (jd_2 + jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
         de_j3[c] += (BETA_EFFECT(po, n, i, j, beta, Delta) + s1[c] * (jd_3 - jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
         de_j3[c] += JC(po, qp) * dt * (-po[c] * (1 - ediag) + ediag);
@@ -1563,7 +1591,8 @@ static void advection_de(orc_model *m, flist *ql, flist *pl, double dt, double e
           jd_2 = JC(pp, po2);
           jd_3 = JC(po, pp2);
           jc = JC(po, pp);
-          de_j1[c] += (JC(po, qo) + s0[c] * ju_1 * idh0[l] + s1[c] * jd_1 * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+          if (ec) de_j1[c] += (JC(po, QT(l))) * dt * (-po[c] * (1 - ediag) + ediag);
+          else de_j1[c] += (JC(po, qo) + s0[c] * ju_1 * idh0[l] + s1[c] * jd_1 * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
           de_j2[c] += (JC(pp, qo) + s0[c] * (ju_2 + jc) * idh0[l] + s1[c] * (jd_2 + jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
           de_j3[c] += (BETA_EFFECT(po, n, i, j, beta, Delta) + s0[c] * (ju_3 - jc) * idh0[l] + s1[c] * (jd_3 - jc) * idh1[l]) * dt * (-po[c] * (1 - ediag) + ediag);
           de_j3[c] += JC(po, qp) * dt * (-po[c] * (1 - ediag) + ediag);
@@ -1576,7 +1605,8 @@ static void advection_de(orc_model *m, flist *ql, flist *pl, double dt, double e
         ju_2 = -jd_3; /* swap */
         ju_3 = -jd_2; /* swap */
         jc = JC(po, pp);
-        de_j1[c] += (JC(po, qo) + s0[c] * ju_1 * idh0[l]) * dt * (-po[c] * (1 - ediag) + ediag);
+        if (ec) de_j1[c] += (JC(po, QT(l))) * dt * (-po[c] * (1 - ediag) + ediag);
+        else de_j1[c] += (JC(po, qo) + s0[c] * ju_1 * idh0[l]) * dt * (-po[c] * (1 - ediag) + ediag);
         de_j2[c] += (JC(pp, qo) + s0[c] * (ju_2 + jc) * idh0[l]) * dt * (-po[c] * (1 - ediag) + ediag);
         de_j3[c] += (BETA_EFFECT(po, n, i, j, beta, Delta) + s0[c] * (ju_3 - jc) * idh0[l]) * dt * (-po[c] * (1 - ediag) + ediag);
         de_j3[c] += JC(po, qp) * dt * (-po[c] * (1 - ediag) + ediag);
@@ -1585,6 +1615,7 @@ static void advection_de(orc_model *m, flist *ql, flist *pl, double dt, double e
       }
     }
 #undef JC
+#undef QT
 }
 /* dissip_de, qg_energy.h:157-187 */
 static void dissip_de(orc_model *m, flist *zl, flist *dql, flist *pl, double dt, double ediag) {

@@ -87,6 +87,11 @@ void orc_set_smoother(orc_model *m, int smoother);
 void orc_set_noise_mode(orc_model *m, int mode, unsigned seed);
 void orc_test_philox(unsigned int *c4, unsigned int k0, unsigned int k1); /* Philox4x32-10 block function (known-answer tests) */
 int orc_get_smoother(orc_model *m);
+/* the reference's compile-time variant -DENERGY_CONSERV=1 as a runtime switch: advection_pv advects the full PV q
+   instead of zeta + the stretching Jacobian J(psi_l, psi_l+1) (qg.h:310-312, :338-340, :366-367), and advection_de
+   books J(psi, comp_q(psi)) in de_j1 (qg_energy.h:33-35, :64-66, :100-102, :132-134).  Not used by the stochastic
+   advection_pv (qg_stochastic.h has no such branch).  _LS_RV = 0 needs no switch: it is flsrv = 0. */
+void orc_set_energy_conserv(orc_model *m, int on);
 void orc_init_noise(orc_model *m, unsigned seed);/* qg.c:60-70 with srand(seed) */
 void orc_remove_mean_psi(orc_model *m);          /* qg.c:66-70 */
 

@@ -89,6 +89,7 @@ def lib(omp=False):
     L.orc_set_flag_topo.argtypes = [vp, C.c_int]
     L.orc_set_decomp.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.orc_set_smoother.argtypes = [vp, C.c_int]
+    L.orc_set_energy_conserv.argtypes = [vp, C.c_int]
     L.orc_set_noise_mode.argtypes = [vp, C.c_int, C.c_uint]
     L.orc_get_smoother.argtypes = [vp]
     L.orc_get_smoother.restype = C.c_int
@@ -204,6 +205,10 @@ class Model:
     def set_smoother(self, name):
         """'lex' (reference order, default) or 'rb' (red-black ordering of the same cell update)"""
         self.L.orc_set_smoother(self.h, {"lex": 0, "rb": 1}[name])
+
+    def set_energy_conserv(self, on):
+        """the reference's -DENERGY_CONSERV=1 build (qg.h:310-373) as a runtime switch"""
+        self.L.orc_set_energy_conserv(self.h, int(bool(on)))
 
     def set_const(self):
         rc = self.L.orc_set_const(self.h)

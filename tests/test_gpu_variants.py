@@ -297,6 +297,54 @@ def test_energy_diagnostics(gpu, N, nl, ediag, over):
     assert not mg.get(G.DE_J1).any() and not mg.get(G.DE_VD).any()
 
 
+@pytest.mark.parametrize("smoother", ["lex", "rb"])
+@pytest.mark.parametrize("N,nl,frfield,over", [(64, 2, 0, {}), (128, 3, 1, dict(Re=200.)), (64, 4, 0, dict(flag_topo=1)),
+                                                 (64, 3, 1, dict(upg=[0.3, 0.1, 0.], vpg=[0.05, 0., 0.], flsrv=1, Eks=0.001))])
+def test_energy_conserv_variant(gpu, N, nl, frfield, over, smoother):
+    """The reference's compile-time variant -DENERGY_CONSERV=1 (msqg/qg.h:310-373, qg_energy.h:33-140) as a runtime
+    switch: advection_pv advects the full PV (jacobian(po, qot), ghosts of the evolving list included) and drops
+    J(psi_l, psi_l+1); advection_de books jacobian(po, comp_q(po)).  Bit-exact against the oracle: tendency of one
+    update_qg, several steps, energy diagnostics -- with uniform and x/y-dependent stretching, a background flow,
+    topography, viscosity."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    topo = over.get("flag_topo", 0)
+    over = {k: v for k, v in over.items() if k != "flag_topo"}
+    mo, mg, psi = make_pair(N, nl, smoother=smoother, **over)
+    mo.set_energy_conserv(1); mg.set_energy_conserv(1)
+    y, x = np.meshgrid((np.arange(N) + 0.5) / N, (np.arange(N) + 0.5) / N, indexing="ij")
+    if frfield:
+        fr = np.zeros_like(psi)
+        for l in range(nl - 1):
+            fr[l] = (0.003 + 0.002 * l) * (1 + 0.3 * np.sin(2 * np.pi * x) * np.cos(np.pi * y))
+        mo.set(O.FR, fr); mg.set(G.FR, fr)
+    if topo:
+        h = (0.1 * np.exp(-((x - 0.4) ** 2 + (y - 0.6) ** 2) / 0.02))[None]
+        mo.set(O.TOPO, h); mg.set(G.TOPO, h)
+        mo.L.orc_set_flag_topo(mo.h, 1); G.check(mg.L.msqg_set_flag_topo(mg.h, 1))
+    mo.set_const(); mg.set_const()
+    assert mg.update(1e10) == mo.update(1e10)
+    dqg, dqo = mg.get(G.DQ), mo.get(O.DQ)
+    assert np.array_equal(dqg, dqo), float(np.abs(dqg - dqo).max())
+    for k in range(3):
+        dto, dtg = mo.step(), mg.step()
+        assert dto == dtg
+        mo.energy_tend(dto); mg.energy_tend(dtg)
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    for fo, fg in ((O.DE_BF, G.DE_BF), (O.DE_VD, G.DE_VD), (O.DE_J1, G.DE_J1), (O.DE_J2, G.DE_J2), (O.DE_J3, G.DE_J3)):
+        a, b = mg.get(fg), mo.get(fo)
+        assert np.array_equal(a, b), (fg, float(np.abs(a - b).max()))
+    # the switch matters: the default build gives different bits
+    ref, _, _ = make_pair(N, nl, smoother=smoother, **over)
+    if frfield:
+        ref.set(O.FR, fr)
+    if topo:
+        ref.set(O.TOPO, h); ref.L.orc_set_flag_topo(ref.h, 1)
+    ref.set_const()
+    ref.update(1e10)
+    assert not np.array_equal(ref.get(O.DQ), dqo)
+
+
 @pytest.mark.parametrize("dtflt", [-1.0, 0.05])
 def test_pystep_de_python_entry(gpu, dtflt):
     """pystep_de of the SWIG module (msqg/qg_energy.i:30-39) through the ctypes mirror, against the oracle; the

@@ -246,3 +246,38 @@ def test_wavelet_filter_limits():
     assert np.allclose(qof, (q0 - q1) / 0.05, rtol=0, atol=1e-15)      # qof = (q_before - q_after)/dtflt with nbar = 0
     q0, q1, p1, qof, lo, hi = out[4.0]
     assert 0 < hi[6] and lo[0] == 0.0 and 0 < np.abs(q1).max() < np.abs(q0).max()
+
+
+def test_energy_conserv_variant_is_the_same_operator_for_uniform_stretching():
+    """ENERGY_CONSERV (qg.h:310-373) advects the full PV: jacobian(po, qot) instead of jacobian(po, zeta) plus the
+    stretching Jacobians J(psi_l, psi_l+-1).  The discrete Jacobian is bilinear and J(psi, psi) == 0, so with
+    horizontally uniform stretching q_l = zeta_l + s (psi_l+1 - psi_l) idh1 - ... gives the SAME tendency up to
+    round-off -- an identity that pins the branch (argument order, sign, which list is advected).  With a
+    stretching field s(x, y) the two builds differ by the terms J(psi, s) that only the energy-conserving form
+    keeps.  (_LS_RV = 0, the other switch of qg.h, is the arithmetic of flsrv = 0: zetapl stays zero and the
+    term adds exact zeros.)"""
+    N, nl = 64, 3
+    psi = synth_psi(N, nl)
+
+    def tendency(econs, fr=None, **over):
+        m = O.Model(O.make_params(**base_kw(N, nl, **over)))
+        m.set_energy_conserv(econs)
+        m.set(O.PSI, psi)
+        if fr is not None:
+            m.set(O.FR, fr)
+        m.set_const()
+        m.update(1e10)
+        return m.get(O.DQ)
+
+    a, b = tendency(0), tendency(1)
+    assert not np.array_equal(a, b)
+    assert np.abs(a - b).max() < 1e-11 * np.abs(a).max()
+    over = dict(upg=[0.3, 0.1, 0.], vpg=[0.05, 0., 0.], flsrv=1, Re=200.)
+    a, b = tendency(0, **over), tendency(1, **over)
+    assert np.abs(a - b).max() < 1e-11 * np.abs(a).max()
+    y, x = np.meshgrid((np.arange(N) + 0.5) / N, (np.arange(N) + 0.5) / N, indexing="ij")
+    fr = np.zeros_like(psi)
+    for l in range(nl - 1):
+        fr[l] = (0.003 + 0.002 * l) * (1 + 0.3 * np.sin(2 * np.pi * x) * np.cos(np.pi * y))
+    a, b = tendency(0, fr), tendency(1, fr)
+    assert np.abs(a - b).max() > 1e-6 * np.abs(a).max()
