@@ -105,10 +105,16 @@ __global__ void k_place(double *__restrict__ full, Geom gfull, const double *__r
 }
 /* scatter: (hx+2) x (hy+2) patch around the tile block of the full level; values outside the
  * domain are the homogeneous-dirichlet ghosts of da (coarse_at with bc = 0) */
-__global__ void k_extract_patch(const double *__restrict__ full, Geom gfull, double *__restrict__ dst, int hx, int hy, int ox, int oy) {
+__global__ void k_extract_patch(const double *__restrict__ full, Geom gfull, double *__restrict__ dst, int hx, int hy, int ox, int oy,
+                                int periodic) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x - 1, y = blockIdx.y * blockDim.y + threadIdx.y - 1, f = blockIdx.z;
   if (x > hx || y > hy) return;
-  dst[((size_t)f * (hy + 2) + y + 1) * (hx + 2) + x + 1] = coarse_at(full + (size_t)f * gfull.plane, gfull, ox + x, oy + y);
+  double v;
+  if (periodic) /* sbc = -1: the ring around the block holds the cells across the seam */
+    v = full[(size_t)f * gfull.plane + GIDX(gfull.pitch, (oy + y + gfull.ny) % gfull.ny, (ox + x + gfull.nx) % gfull.nx)];
+  else
+    v = coarse_at(full + (size_t)f * gfull.plane, gfull, ox + x, oy + y);
+  dst[((size_t)f * (hy + 2) + y + 1) * (hx + 2) + x + 1] = v;
 }
 __global__ void k_load_patch(double *__restrict__ dst, Geom gp, const double *__restrict__ src) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x - 1, y = blockIdx.y * blockDim.y + threadIdx.y - 1, f = blockIdx.z;
@@ -136,7 +142,8 @@ struct msqg_group {
   GraphCache graphs;
 };
 
-static inline int tile_rank(msqg_group *G, int ix, int iy) { return iy * G->px + ix; }
+/* periodic groups (sbc = -1): the neighbour across a side of the domain is the tile on the opposite side */
+static inline int tile_rank(msqg_group *G, int ix, int iy) { return ((iy + G->py) % G->py) * G->px + (ix + G->px) % G->px; }
 static inline msqg_model *tile_at(msqg_group *G, int ix, int iy) {
   return G->kind == 0 ? G->tiles[tile_rank(G, ix, iy)] : G->tiles[0];
 }
@@ -318,7 +325,10 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
                         const void *uid, msqg_group **out, int smoother = -1) {
   if (smoother < 0) { const char *e = getenv("MSQG_SMOOTHER"); smoother = (e && !strcmp(e, "rb")) ? 1 : 0; }
   *out = nullptr;
-  if (px * py < 2) FAIL(MSQG_ERR_ARG, "a group needs px*py >= 2 tiles");
+  const int per = p->sbc == -1;
+  if (px * py < 2 && !per) FAIL(MSQG_ERR_ARG, "a group needs px*py >= 2 tiles");
+  if (per && smoother != 1) FAIL(MSQG_ERR_ARG, "periodic boundaries (sbc = -1) need the red-black smoother");
+  if (per && kind != 0) FAIL(MSQG_ERR_ARG, "periodic boundaries (sbc = -1) are built for the tiles of one process (msqg_group_create_local_sm)");
   if (p->mode_pv_invert || p->stochastic) FAIL(MSQG_ERR_ARG, "decomposed grids support the layer-coupled, deterministic path only");
   if (kind == 1 && nranks != px * py) FAIL(MSQG_ERR_ARG, "nranks must equal px*py");
   msqg_group *G = new msqg_group();
@@ -356,6 +366,7 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
   if (G->rb) {
     int want = 1;
     { const char *e = getenv("MSQG_P2P"); if (e && atoi(e) == 0) want = 0; }
+    if (per) want = 0; /* a tile may be its own neighbour in several directions: staged device copies */
     if (want && (rc = group_setup_p2p(G))) return rc;
   }
   *out = G;
@@ -487,17 +498,17 @@ static int g_cycle(msqg_group *G, int nrelax) {
   const size_t pblk = (size_t)nl * (hx + 2) * (hy + 2);
   if (G->kind == 0) {
     for (msqg_model *m : G->tiles) {
-      k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy);
+      k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy, 0);
       k_load_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da_patch, m->gpatch, m->patch_stage);
       m->launches += 2;
     }
   } else {
     if (G->rank == 0) {
       for (int r = 1; r < G->nranks; r++) {
-        k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], root->d_stage, hx, hy, (r % G->px) * hx, (r / G->px) * hy);
+        k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], root->d_stage, hx, hy, (r % G->px) * hx, (r / G->px) * hy, 0);
         NCK(G->nccl->Send(root->d_stage, pblk, NCCL_DOUBLE, r, G->comm, G->stream));
       }
-      k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], root->patch_stage, hx, hy, 0, 0);
+      k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(root->da.lev[La - 1], root->g[La - 1], root->patch_stage, hx, hy, 0, 0, 0);
     } else
       NCK(G->nccl->Recv(m0->patch_stage, pblk, NCCL_DOUBLE, 0, G->comm, G->stream));
     k_load_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m0->da_patch, m0->gpatch, m0->patch_stage);

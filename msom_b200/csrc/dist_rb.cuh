@@ -174,14 +174,14 @@ struct XItem {
   int nf, w, ring;           /* planes, halo width, 1: straight transfers also carry the ghost ring of physical sides */
 };
 
-static void halo_boxes(const Geom &g, int w, int ring, int ix, int iy, int px, int py, HaloPlan &P) {
+static void halo_boxes(const Geom &g, int w, int ring, int ix, int iy, int px, int py, HaloPlan &P, int periodic = 0) {
   const int eL = (ring && !(g.bc & 1)) ? 1 : 0, eR = (ring && !(g.bc & 2)) ? 1 : 0;
   const int eB = (ring && !(g.bc & 4)) ? 1 : 0, eT = (ring && !(g.bc & 8)) ? 1 : 0;
   for (int dy = -1; dy <= 1; dy++)
     for (int dx = -1; dx <= 1; dx++) {
       const int d = (dy + 1) * 3 + (dx + 1);
       const int nxx = ix + dx, nyy = iy + dy;
-      P.on[d] = !(dx == 0 && dy == 0) && nxx >= 0 && nxx < px && nyy >= 0 && nyy < py;
+      P.on[d] = !(dx == 0 && dy == 0) && (periodic || (nxx >= 0 && nxx < px && nyy >= 0 && nyy < py));
       HaloBox &s = P.send[d], &r = P.recv[d];
       if (dx < 0) { s.x0 = 0; s.x1 = w; r.x0 = -w; r.x1 = 0; }
       else if (dx > 0) { s.x0 = g.nx - w; s.x1 = g.nx; r.x0 = g.nx; r.x1 = g.nx + w; }
@@ -204,7 +204,7 @@ static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
       msqg_model *m = G->tiles[t];
       HaloPlan &P = plans[it][t];
       if (items[it].w > MSQG_FRAME - 1) FAIL(MSQG_ERR_ARG, "halo width %d exceeds the frame", items[it].w);
-      halo_boxes(items[it].geo[t], items[it].w, items[it].ring, m->ix, m->iy, G->px, G->py, P);
+      halo_boxes(items[it].geo[t], items[it].w, items[it].ring, m->ix, m->iy, G->px, G->py, P, m->periodic);
       for (int d = 0; d < 9; d++) {
         P.sbuf[d] = m->xsend[d]; P.rbuf[d] = m->xrecv[d];
         P.off[d] = tot[t][d];
@@ -376,7 +376,8 @@ static int g_cycle_rb(msqg_group *G, int nrelax) {
     m->launches++;
     if ((rc = mg_levels(m, nl, -1, nrelax, La - 1, La - 1))) return rc;
     /* this tile's block of level La-1 plus a one-cell ring (homogeneous dirichlet ghosts evaluated on the fly) */
-    k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da.lev[La - 1], m->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy);
+    k_extract_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da.lev[La - 1], m->g[La - 1], m->patch_stage, hx, hy, m->ix * hx, m->iy * hy,
+                                                                        m->periodic);
     k_load_patch<<<grid2(hx + 2, hy + 2, b, nl), b, 0, G->stream>>>(m->da_patch, m->gpatch, m->patch_stage);
     m->launches += 2;
   }

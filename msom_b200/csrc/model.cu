@@ -76,6 +76,8 @@ struct msqg_model {
   int fy[MSQG_MAXLEV + 1];     /* frame rows around the cells of a plane: 1 (the ghost ring) on undecomposed levels,
                                   MSQG_FRAME on the levels of a tile, which hold deep halos for the fused red-black sweeps
                                   (the row pitch then also keeps MSQG_FRAME columns on the right; MSQG_OX covers the left) */
+  int periodic;                /* sbc == -1 (periodic(right); periodic(top), qg.h:842-846): every side of every tile is an
+                                  internal side whose halo comes from the opposite tile (or from the tile itself) */
   int rb_dist;                 /* tile of a red-black group: the levels below agg_level are REPLICATED on every tile */
   Geom gpatch;                 /* level agg_level-1 restricted to this tile (+ halo ring): scatter/gather scratch */
   double *da_patch, *res_patch; /* [nl] planes of gpatch */
@@ -377,7 +379,16 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   *out = nullptr;
   if (p->nl < 2 || p->nl > MSQG_NLMAX) FAIL(MSQG_ERR_ARG, "nl must be in [2,%d] (nl==1 is not functional in the reference)", MSQG_NLMAX);
   if (p->N < 8 || (p->N & (p->N - 1))) FAIL(MSQG_ERR_ARG, "N must be a power of two >= 8");
-  if (p->sbc < 0) FAIL(MSQG_ERR_ARG, "sbc must be >= 0: the periodic variant (sbc = -1) is out of scope");
+  const int per = p->sbc == -1;
+  if (p->sbc < 0 && !per) FAIL(MSQG_ERR_ARG, "sbc is >= 0 (free / partial slip) or -1 (doubly periodic, qg.h:80)");
+  if (per && !rb_dist)
+    FAIL(MSQG_ERR_ARG, "periodic boundaries (sbc = -1) run on the tile machinery with the red-black smoother: "
+                       "create the model with msqg_group_create_local_sm(p, device, px, py, 0, 1, &group), px = py = 1 included");
+  if (per && (p->mode_pv_invert || p->stochastic || p->nptr > 0))
+    FAIL(MSQG_ERR_ARG, "periodic boundaries are built for the layer-coupled, deterministic path without tracers");
+  for (int l = 0; per && l < p->nl; l++)
+    if (p->upg[l] != 0 || p->vpg[l] != 0)
+      FAIL(MSQG_ERR_ARG, "periodic boundaries with a large-scale flow (non-periodic psi_pg, qg.h:1105-1114) are not built");
   if (p->nptr < 0 || p->nptr > MSQG_MAXL) FAIL(MSQG_ERR_ARG, "nptr must be in 0..%d", MSQG_MAXL);
   if (p->nptr > 0 && p->stochastic) FAIL(MSQG_ERR_ARG, "passive tracers are not advanced by the stochastic advance_qg (qg_stochastic.h:139-147)");
   if (px < 1 || py < 1 || (px & (px - 1)) || (py & (py - 1))) FAIL(MSQG_ERR_ARG, "px, py must be powers of two");
@@ -401,9 +412,14 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   }
   m->px = px; m->py = py; m->ix = ix; m->iy = iy;
   m->agg_level = 0;
-  m->rb_dist = (px * py > 1) ? rb_dist : 0;
+  m->periodic = per;
+  const bool tiled = px * py > 1 || per;
+  m->rb_dist = tiled ? rb_dist : 0;
+  if (per) { /* levels <= 32^2 are swept by k_coarse_rb (wrap-around neighbours), everything above lives on tiles */
+    agg_n = p->N < 64 ? p->N : 64;
+  }
   if (px * py > 1 && p->sbc > 0) { msqg_destroy(m); FAIL(MSQG_ERR_ARG, "partial slip (sbc > 0) is not supported on decomposed grids"); }
-  if (px * py > 1) {
+  if (tiled) {
     int la = 1;
     while ((1 << la) < agg_n) la++;
     const char *why = nullptr;
@@ -417,10 +433,11 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   }
   for (int l = 0; l <= depth; l++) {
     Geom &g = m->g[l];
-    const bool dist = (px * py > 1) && l >= m->agg_level;
+    const bool dist = tiled && l >= m->agg_level;
     if (dist) {
       g.nx = (1 << l) / px; g.ny = (1 << l) / py;
       g.bc = (ix > 0 ? 1 : 0) | (ix < px - 1 ? 2 : 0) | (iy > 0 ? 4 : 0) | (iy < py - 1 ? 8 : 0);
+      if (per) g.bc = 15;
       m->has_lev[l] = true;
       m->fy[l] = MSQG_FRAME;
       g.pitch = ((g.nx + MSQG_OX + MSQG_FRAME + 15) / 16) * 16;
@@ -526,7 +543,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
     std::vector<double> one(tc, 1.);
     if ((rc = pack_to(m, m->rd, one.data()))) { msqg_destroy(m); return rc; }
   }
-  if (px * py > 1) { /* exchange / scatter-gather scratch */
+  if (tiled) { /* exchange / scatter-gather scratch */
     const int la = m->agg_level;
     Geom &gp = m->gpatch;
     gp.nx = m->g[la].nx / 2; gp.ny = m->g[la].ny / 2; gp.bc = 15;
@@ -702,6 +719,8 @@ extern "C" int msqg_set_field(msqg_model *m, int id, const double *host) {
   if (id == MSQG_PSIPG || id == MSQG_QFORC) {
     int nz = 0;
     for (size_t c = 0; c < cnt && !nz; c++) nz = host[c] != 0.;
+    if (id == MSQG_PSIPG && nz && m->periodic)
+      FAIL(MSQG_ERR_ARG, "periodic boundaries with a large-scale stream function (qg.h:1105-1114) are not built");
     if (id == MSQG_PSIPG) m->has_pg = nz; else m->has_qforc = nz;
   }
   return MSQG_OK;
@@ -1142,7 +1161,7 @@ static int coarse_top_level(msqg_model *m, int nf_problem, int maxlevel) {
   if (m->smoother != 1) return 0;
   if (nf_problem > 1 && !m->s_uniform) return 0;
   if (nf_problem == 1 && !m->modes_uniform) return 0; /* lambda is a field: level-by-level launches with tables */
-  { const char *e = getenv("MSQG_RB_COARSE"); if (e && atoi(e) == 0) return 0; } /* A/B: level-by-level launches */
+  if (!m->periodic) { const char *e = getenv("MSQG_RB_COARSE"); if (e && atoi(e) == 0) return 0; } /* A/B: level-by-level launches */
   int Lc = RB_COARSE_MAXLEV;
   if (Lc > maxlevel) Lc = maxlevel;
   while (Lc >= 2) {
@@ -1156,7 +1175,7 @@ static int coarse_top_level(msqg_model *m, int nf_problem, int maxlevel) {
 template <int NL>
 static int launch_coarse_rb(msqg_model *m, int Lc, int nrelax, const CoarseCoef<NL> &CC) {
   CoarseArgs A;
-  A.res = m->res.lev[Lc]; A.da = m->da.lev[Lc]; A.g = m->g[Lc]; A.Lc = Lc; A.nrelax = nrelax;
+  A.res = m->res.lev[Lc]; A.da = m->da.lev[Lc]; A.g = m->g[Lc]; A.Lc = Lc; A.nrelax = nrelax; A.periodic = m->periodic;
   size_t cells = 0;
   for (int l = 1; l <= Lc; l++) cells += (size_t)1 << (2 * l);
   const size_t smem = 2 * (size_t)NL * cells * sizeof(double);

@@ -308,6 +308,7 @@ struct CoarseArgs {
   double *da;        /* level Lc, [NL] planes */
   Geom g;            /* geometry of level Lc (undecomposed) */
   int Lc, nrelax;
+  int periodic;      /* sbc = -1: neighbours and bilinear stencils wrap around instead of meeting dirichlet ghosts */
 };
 template <int NL>
 __device__ __forceinline__ size_t coarse_smem_doubles(int Lc) {
@@ -361,8 +362,11 @@ k_coarse_rb(CoarseArgs A, CoarseCoef<NL> CC) {
         const int xc = x >> 1, yc = y >> 1, ix = (x & 1) ? 1 : -1, iy = (y & 1) ? 1 : -1;
         auto cat = [&](int xx, int yy) {
           double s = 1.;
-          if (xx < 0) { xx = 0; s = -s; } else if (xx >= nc) { xx = nc - 1; s = -s; }
-          if (yy < 0) { yy = 0; s = -s; } else if (yy >= nc) { yy = nc - 1; s = -s; }
+          if (A.periodic) { xx = (xx + nc) & (nc - 1); yy = (yy + nc) & (nc - 1); }
+          else {
+            if (xx < 0) { xx = 0; s = -s; } else if (xx >= nc) { xx = nc - 1; s = -s; }
+            if (yy < 0) { yy = 0; s = -s; } else if (yy >= nc) { yy = nc - 1; s = -s; }
+          }
           return s * DA(l - 1, f, yy, xx);
         };
         DA(l, f, y, x) = (9. * cat(xc, yc) + 3. * (cat(xc + ix, yc) + cat(xc, yc + iy)) + cat(xc + ix, yc + iy)) / 16.;
@@ -379,8 +383,15 @@ k_coarse_rb(CoarseArgs A, CoarseCoef<NL> CC) {
 #pragma unroll
         for (int f = 0; f < NL; f++) {
           const double c0 = DA(l, f, y, x), gh = -c0;
-          const double aw = x > 0 ? DA(l, f, y, x - 1) : gh, ae = x < n - 1 ? DA(l, f, y, x + 1) : gh;
-          const double as = y > 0 ? DA(l, f, y - 1, x) : gh, an = y < n - 1 ? DA(l, f, y + 1, x) : gh;
+          double aw, ae, as, an;
+          if (A.periodic) { /* the ghost ring holds the opposite side (refreshed after every half-sweep; those cells
+                               have the other colour, so they are current) */
+            aw = DA(l, f, y, (x + n - 1) & (n - 1)); ae = DA(l, f, y, (x + 1) & (n - 1));
+            as = DA(l, f, (y + n - 1) & (n - 1), x); an = DA(l, f, (y + 1) & (n - 1), x);
+          } else {
+            aw = x > 0 ? DA(l, f, y, x - 1) : gh; ae = x < n - 1 ? DA(l, f, y, x + 1) : gh;
+            as = y > 0 ? DA(l, f, y - 1, x) : gh; an = y < n - 1 ? DA(l, f, y + 1, x) : gh;
+          }
           double rr = C.msd2 * RS(l, f, y, x);
           rr += ae + aw;
           rr += an + as;

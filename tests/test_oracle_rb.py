@@ -140,3 +140,51 @@ def test_red_black_golden_regression():
     dts = [m.step() for _ in range(3)]
     assert np.array_equal(np.array(dts), g["dts"])
     assert np.array_equal(m.get(O.PSI), g["psi"]) and np.array_equal(m.get(O.Q), g["q"])
+
+
+def test_periodic_domain_is_translation_equivariant():
+    """sbc = -1 (qg.h:842-846): with periodic(right); periodic(top) every operator of the step has constant
+    coefficients once the wind forcing is off, and the multigrid hierarchy (minlevel = 1: two cells per side) maps onto
+    itself under a diagonal shift by N/2 cells in x and y.  A red-black half-sweep does not depend on the traversal order, so the whole
+    step -- ghost rings on every level, restriction, bilinear prolongation and the nine-point Jacobian across the seam
+    -- must commute with that shift BIT FOR BIT.  This pins the wrap-around of the oracle's boundary_level()."""
+    import numpy as np
+    from oracle import oracle as O
+    from common import base_kw
+    N, nl = 64, 3
+    rng = np.random.default_rng(11)
+    x = (np.arange(N) + 0.5) / N
+    X, Y = np.meshgrid(x, x)
+    psi = np.zeros((nl, N, N))
+    for l in range(nl):
+        nz = rng.uniform(-1, 1, (N, N))
+        psi[l] = (np.sin(2 * np.pi * X) * np.sin(4 * np.pi * Y) + 0.3 * np.cos(2 * np.pi * (X + 2 * Y)) + 1e-3 * (nz - nz.mean())) / (l + 1)
+
+    def run(p0, nsteps=3):
+        m = O.Model(O.make_params(**base_kw(N, nl, sbc=-1., tau0=0.)))
+        m.set_smoother("rb")
+        m.set(O.PSI, p0); m.set_const()
+        q0 = m.get(O.Q)
+        dts = [m.step() for _ in range(nsteps)]
+        return q0, m.get(O.Q), m.get(O.PSI), dts, m.L.orc_total_cycles(m.h)
+
+    q0, q1, p1, dts, cyc = run(psi)
+    # the discrete PV of a periodic stream function integrates to zero in every layer (compatibility of the singular solve)
+    assert np.abs(q0.sum(axis=(1, 2))).max() < 1e-9 * np.abs(q0).sum()
+    # the shift is diagonal: on level 1 (2 x 2 cells) a shift along one axis alone would swap the two colours
+    sh = lambda a: np.roll(a, (N // 2, N // 2), axis=(1, 2))
+    r0, r1, rp, rdts, rcyc = run(sh(psi))
+    assert rdts == dts and rcyc == cyc
+    assert np.array_equal(r0, sh(q0))
+    assert np.array_equal(r1, sh(q1))
+    assert np.array_equal(rp, sh(p1))
+    # a shift along x alone is the same solve with red and black swapped on level 1: equal to the solver tolerance only
+    r0, r1, rp, rdts, rcyc = run(np.roll(psi, N // 2, axis=2))
+    assert np.array_equal(r0, np.roll(q0, N // 2, axis=2)) and not np.array_equal(rp, np.roll(p1, N // 2, axis=2))
+    d = rp - np.roll(p1, N // 2, axis=2)
+    d -= d.mean(axis=(1, 2), keepdims=True)      # the constant is in the null space of the periodic operator
+    assert np.abs(d).max() < 1e-3 * np.abs(p1).max()
+    # and the seam is really open: the closed basin gives another PV for the same stream function
+    m = O.Model(O.make_params(**base_kw(N, nl, tau0=0.)))
+    m.set(O.PSI, psi); m.set_const()
+    assert not np.array_equal(m.get(O.Q), q0)
