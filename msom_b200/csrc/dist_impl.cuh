@@ -743,3 +743,42 @@ extern "C" int msqg_group_profile_read(msqg_group *G, double *ms, long *count, l
   }
   return MSQG_OK;
 }
+
+/* ------------------------------------------------------------------ a periodic model behind the single-model entry points
+ * msqg_create(p with sbc = -1): a local 1 x 1 red-black group whose only tile is the handle the caller gets. */
+static int pg_create(const msqg_params *p, int device, msqg_model **out) {
+  *out = nullptr;
+  msqg_group *G = nullptr;
+  int rc = group_create(p, device, 1, 1, 0, 0, 0, 1, nullptr, &G, 1);
+  if (rc) { if (G) msqg_group_destroy(G); return rc; }
+  msqg_model *m = G->tiles[0];
+  m->group = G;
+  *out = m;
+  return MSQG_OK;
+}
+static void pg_destroy(msqg_group *G) { msqg_group_destroy(G); }
+static void pg_mirror_stats(msqg_group *G, msqg_model *m) { m->mgpsi = G->mgpsi; m->total_cycles = G->total_cycles; }
+static int pg_set_const(msqg_group *G) { return msqg_group_set_const(G); }
+static int pg_invertq(msqg_group *G, msqg_model *m, int q_id) {
+  int rc = g_invertq(G, q_id);
+  pg_mirror_stats(G, m);
+  return rc;
+}
+static int pg_halo(msqg_group *G, int id) { return exchange_list(G, id, G->tiles[0]->depth); }
+/* update_qg on the periodic tile: msqg_update with the group's inversion, halo exchanges and dt chain */
+static int pg_update(msqg_group *G, msqg_model *m, int q_id, double dtmax, double *dtmax_out) {
+  int rc;
+  double umax[MSQG_MAXL];
+  if ((rc = g_invertq(G, q_id))) return rc;
+  pg_mirror_stats(G, m);
+  if ((rc = g_rhs_prepare(G, umax))) return rc;
+  if ((rc = rhs_launch(m, *list_by_id(m, q_id), nullptr, nullptr, m->dq.lev[m->depth], 0., 0.f))) return rc;
+  CK(cudaStreamSynchronize(G->stream));
+  if (dtmax_out) *dtmax_out = g_dt_chain(G, umax, dtmax);
+  return MSQG_OK;
+}
+static int pg_step(msqg_group *G, msqg_model *m, double t, double tnext_event, double *dt_out, double *tnext_out) {
+  int rc = msqg_group_step(G, t, tnext_event, dt_out, tnext_out);
+  pg_mirror_stats(G, m);
+  return rc;
+}

@@ -76,6 +76,7 @@ struct msqg_model {
   int fy[MSQG_MAXLEV + 1];     /* frame rows around the cells of a plane: 1 (the ghost ring) on undecomposed levels,
                                   MSQG_FRAME on the levels of a tile, which hold deep halos for the fused red-black sweeps
                                   (the row pitch then also keeps MSQG_FRAME columns on the right; MSQG_OX covers the left) */
+  struct msqg_group *group;    /* a periodic model made by msqg_create: the 1 x 1 group that owns this tile (else NULL) */
   int periodic;                /* sbc == -1 (periodic(right); periodic(top), qg.h:842-846): every side of every tile is an
                                   internal side whose halo comes from the opposite tile (or from the tile itself) */
   int rb_dist;                 /* tile of a red-black group: the levels below agg_level are REPLICATED on every tile */
@@ -383,7 +384,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   if (p->sbc < 0 && !per) FAIL(MSQG_ERR_ARG, "sbc is >= 0 (free / partial slip) or -1 (doubly periodic, qg.h:80)");
   if (per && !rb_dist)
     FAIL(MSQG_ERR_ARG, "periodic boundaries (sbc = -1) run on the tile machinery with the red-black smoother: "
-                       "create the model with msqg_group_create_local_sm(p, device, px, py, 0, 1, &group), px = py = 1 included");
+                       "msqg_create does that by itself (a 1 x 1 group); tiles: msqg_group_create_local_sm(p, device, px, py, 0, 1, &group)");
   if (per && (p->mode_pv_invert || p->stochastic || p->nptr > 0))
     FAIL(MSQG_ERR_ARG, "periodic boundaries are built for the layer-coupled, deterministic path without tracers");
   for (int l = 0; per && l < p->nl; l++)
@@ -412,7 +413,7 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   }
   m->px = px; m->py = py; m->ix = ix; m->iy = iy;
   m->agg_level = 0;
-  m->periodic = per;
+  m->periodic = per; m->group = nullptr;
   const bool tiled = px * py > 1 || per;
   m->rb_dist = tiled ? rb_dist : 0;
   if (per) { /* levels <= 32^2 are swept by k_coarse_rb (wrap-around neighbours), everything above lives on tiles */
@@ -579,12 +580,25 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   return MSQG_OK;
 }
 
+/* sbc = -1 through the single-model entry points: msqg_create builds a 1 x 1 periodic group (dist_impl.cuh) and hands out
+   its tile; set_const / invertq / update / step / comp_q / destroy of that handle go through the group */
+struct msqg_group;
+static int pg_create(const msqg_params *p, int device, msqg_model **out);
+static void pg_destroy(msqg_group *G);
+static int pg_set_const(msqg_group *G);
+static int pg_invertq(msqg_group *G, msqg_model *m, int q_id);
+static int pg_update(msqg_group *G, msqg_model *m, int q_id, double dtmax, double *dtmax_out);
+static int pg_step(msqg_group *G, msqg_model *m, double t, double tnext_event, double *dt_out, double *tnext_out);
+static int pg_halo(msqg_group *G, int id);
+
 extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
+  if (p->sbc == -1) return pg_create(p, device, out);
   return create_model(p, device, 1, 1, 0, 0, 0, nullptr, out);
 }
 
 extern "C" void msqg_destroy(msqg_model *m) {
   if (!m) return;
+  if (m->group) { msqg_group *G = m->group; m->group = nullptr; pg_destroy(G); return; } /* destroys this tile too */
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   m->graphs.clear();
@@ -647,6 +661,7 @@ extern "C" void msqg_seed_noise(msqg_model *m, unsigned seed) {
 extern "C" int msqg_set_flag_topo(msqg_model *m, int flag) { m->flag_topo = flag; return MSQG_OK; }
 extern "C" int msqg_set_smoother(msqg_model *m, int smoother) {
   if (smoother != 0 && smoother != 1) FAIL(MSQG_ERR_ARG, "smoother is 0 (reference order) or 1 (red-black)");
+  if (m->periodic && smoother != 1) FAIL(MSQG_ERR_ARG, "periodic boundaries (sbc = -1) need the red-black smoother");
   m->smoother = smoother;
   m->graphs.clear();
   return MSQG_OK;
@@ -1531,11 +1546,13 @@ extern "C" int msqg_invertq(msqg_model *m, int q_id) {
   CK(cudaSetDevice(m->device));
   List *L = list_by_id(m, q_id);
   if (!L || L->nf != m->nl) FAIL(MSQG_ERR_ARG, "bad q list");
+  if (m->group) return pg_invertq(m->group, m, q_id);
   return invertq_list(m, *L);
 }
 
 extern "C" int msqg_comp_q(msqg_model *m) {
   CK(cudaSetDevice(m->device));
+  if (m->group) { int rc = pg_halo(m->group, MSQG_PSI); if (rc) return rc; } /* psi across the seam */
   const Geom &g = m->g[m->depth];
   dim3 b(64, 4);
   LayerMetrics M = metrics_of(m);
@@ -1865,6 +1882,7 @@ static int set_const_finish(msqg_model *m) {
 }
 
 extern "C" int msqg_set_const(msqg_model *m) {
+  if (m->group) return pg_set_const(m->group);
   int rc = set_const_local(m);
   if (rc) return rc;
   return set_const_finish(m);
@@ -1979,6 +1997,7 @@ extern "C" int msqg_update(msqg_model *m, int q_id, double dtmax, double *dtmax_
   CK(cudaSetDevice(m->device));
   List *L = list_by_id(m, q_id);
   if (!L || L->nf != m->nl) FAIL(MSQG_ERR_ARG, "bad q list");
+  if (m->group) return pg_update(m->group, m, q_id, dtmax, dtmax_out);
   int rc;
   if ((rc = invertq_list(m, *L))) return rc;
   if ((rc = rhs_prepare(m))) return rc;
@@ -2062,6 +2081,7 @@ extern "C" int msqg_advance(msqg_model *m, int out_id, int in_id, double dt) {
  * that t lands on tnext_event (pass a negative value for "no pending event"). */
 extern "C" int msqg_step(msqg_model *m, double t, double tnext_event, double *dt_out, double *tnext_out) {
   CK(cudaSetDevice(m->device));
+  if (m->group) return pg_step(m->group, m, t, tnext_event, dt_out, tnext_out);
   const int D = m->depth;
   int rc;
   /* stage 1 */

@@ -80,6 +80,33 @@ def test_qg_exe_outputs_match_oracle_run(gpu, tmp_path):
     assert a.shape == (nl, N, N) and np.isfinite(a).all()
 
 
+def test_qg_exe_periodic_domain(gpu, tmp_path):
+    """sbc = -1 in params.in (qg.h:80,711,842-846): ./qg.e runs the doubly periodic domain (msqg_create makes the 1 x 1
+    periodic group by itself); po/qo files byte for byte those of the oracle's run() with the same sweep ordering."""
+    from oracle import oracle as O
+    from test_gpu_periodic import periodic_psi
+    N, nl = 64, 3
+    wd = tmp_path / "gpu"; wd.mkdir()
+    wo = tmp_path / "orc"; wo.mkdir()
+    _write_params(str(wd / "params.in"), N, nl, tend=0.1, dtout=0.05, extra="sbc = -1\n")
+    psi = periodic_psi(N, nl)
+    O.lib().orc_write_bas(str(wd / "p0.bas").encode(), nl, N, 80., psi)
+    exe = os.path.join(ROOT, "msom_b200", "lib", "qg.e")
+    out = subprocess.run([exe], cwd=str(wd), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    po = O.Params(); O.lib().orc_default_params(po); O.lib().orc_read_params(str(wd / "params.in").encode(), po)
+    assert po.sbc == -1
+    mo = O.Model(po); mo.set_smoother("rb")
+    p0 = np.zeros_like(psi); O.lib().orc_read_bas(str(wd / "p0.bas").encode(), nl, N, 80., p0)
+    mo.set(O.PSI, p0); mo.L.orc_remove_mean_psi(mo.h); mo.set_const()
+    assert mo.run(outdir=str(wo)) > 0
+    gdir = wd / "outdir_0001"
+    names = sorted(f for f in os.listdir(wo) if f.endswith(".bas"))
+    assert len(names) == 6
+    for f in names:
+        assert (gdir / f).read_bytes() == (wo / f).read_bytes(), f
+
+
 def test_qg_exe_energy_diagnostics_files(gpu, tmp_path):
     """ediag = 0 (msqg/qg_energy.h): ./qg.e writes de_{bf,vd,j1,j2,j3,ft}%09d.bas at every output, scaled by
     1/dtout and reset (qg.c:139-166); bit-identical to the oracle's run()."""

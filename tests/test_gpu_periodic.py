@@ -58,12 +58,42 @@ def test_periodic_domain_matches_oracle(gpu, N, nl, px, py, over):
     assert not np.array_equal(mc.get(O.Q), mo.get(O.Q))
 
 
-def test_periodic_needs_the_tile_path(gpu):
+def test_periodic_through_the_single_model_entry_points(gpu):
+    """msqg_create with sbc = -1 hands out the tile of a 1 x 1 periodic group: set_const / invertq / update / advance /
+    step of the plain C ABI (and with it qg.e and the python module) work unchanged; the plugin sequence
+    update -> advance equals the fused step, as on a closed basin."""
+    from oracle import oracle as O
     from msom_b200 import capi as G
+    N, nl = 64, 3
+    kw = base_kw(N, nl, sbc=-1.)
+    psi = periodic_psi(N, nl)
+    mo = O.Model(O.make_params(**kw)); mo.set_smoother("rb")
+    mg = G.Model(G.make_params(**kw), gpu)
+    assert mg.L.msqg_get_smoother(mg.h) == 1
     with pytest.raises(G.MsqgError):
-        G.Model(G.make_params(**base_kw(64, 2, sbc=-1.)), gpu)
+        mg.set_smoother("lex")
+    mo.set(O.PSI, psi); mg.set(G.PSI, psi)
+    mo.set_const(); mg.set_const()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+    assert mg.update(1e10) == mo.update(1e10)
+    assert np.array_equal(mg.get(G.DQ), mo.get(O.DQ))
+    for _ in range(3):
+        assert mg.step() == mo.step()
+    so, sg = mo.mgstats(), mg.mgstats()
+    assert (sg.i, sg.nrelax, sg.resb, sg.resa) == (so.i, so.nrelax, so.resb, so.resa)
+    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    # q -> psi -> q round trip through the entry points the python module uses (pyq2p / pyp2q)
+    mg.invertq(); mg.comp_q(); mo.invertq(); mo.comp_q()
+    assert np.array_equal(mg.get(G.Q), mo.get(O.Q))
+
+
+def test_periodic_rejects_what_is_not_built(gpu):
+    from msom_b200 import capi as G
     from msom_b200.dist import Group
     with pytest.raises(G.MsqgError):
         Group(G.make_params(**base_kw(64, 2, sbc=-1.)), 1, 1, 0, gpu, smoother="lex")
     with pytest.raises(G.MsqgError):
-        Group(G.make_params(**base_kw(64, 2, sbc=-1., upg=[0.1, 0.], vpg=[0., 0.])), 1, 1, 0, gpu, smoother="rb")
+        G.Model(G.make_params(**base_kw(64, 2, sbc=-1., upg=[0.1, 0.], vpg=[0., 0.])), gpu)
+    with pytest.raises(G.MsqgError):
+        G.Model(G.make_params(**base_kw(64, 2, sbc=-1., mode_pv_invert=1)), gpu)
