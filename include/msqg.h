@@ -122,6 +122,19 @@ int msqg_set_field(msqg_model *m, int id, const double *host);
 /* pyget_field (qg.h:1177-1189) */
 int msqg_get_field(msqg_model *m, int id, double *host);
 int msqg_set_flag_topo(msqg_model *m, int flag);  /* flag_topo, qg.h:971-977 */
+/* Pipelined pyset_field / pyget_field for callers that advance a stream of independent states (ensemble members, the
+ * forward / backward sweeps of msqg/qg_bfn.py): the PCIe transfers run on their own streams beside the step.
+ *   msqg_set_field_async(m, id, in)  start the upload of in[nl][ny][nx]; returns at once (at most two in flight)
+ *   msqg_set_field_commit(m)         the compute stream waits for the oldest upload and packs it into its list
+ *   msqg_get_field_async(m, id, out) snapshot the list on the compute stream, start its download; returns at once
+ *   msqg_io_wait(m)                  wait for every transfer started so far
+ * id is MSQG_Q or MSQG_PSI.  Host buffers must be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) and
+ * must not be touched until msqg_io_wait (uploads: until their commit has been followed by a synchronising call).
+ * Typical loop: set_field_async(in[0]); for k: { commit; set_field_async(in[k+1]); step; get_field_async(out[k]); } io_wait. */
+int msqg_set_field_async(msqg_model *m, int id, const double *pinned_host);
+int msqg_set_field_commit(msqg_model *m);
+int msqg_get_field_async(msqg_model *m, int id, double *pinned_host);
+int msqg_io_wait(msqg_model *m);
 /* Ordering of the relaxation sweep inside mg_cycle.  0 (default): the reference's lexicographic in-place sweep
  * (relax_layer, msqg/poisson_layer.h:75-149, traversal of [BASILISK] foreach_level) -- results identical to a serial
  * reference build.  1: red-black ordering of the SAME cell update (cells with x+y even, then x+y odd), the

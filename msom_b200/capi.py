@@ -94,6 +94,10 @@ def lib():
     L.msqg_set_smoother.argtypes = [vp, C.c_int]
     L.msqg_get_smoother.argtypes = [vp]
     L.msqg_set_energy_conserv.argtypes = [vp, C.c_int]
+    L.msqg_set_field_async.argtypes = [vp, C.c_int, dp]
+    L.msqg_set_field_commit.argtypes = [vp]
+    L.msqg_get_field_async.argtypes = [vp, C.c_int, dp]
+    L.msqg_io_wait.argtypes = [vp]
     L.msqg_get_energy_conserv.argtypes = [vp]
     L.msqg_set_keep_dq.argtypes = [vp, C.c_int]
     L.msqg_set_dissipation.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -195,6 +199,20 @@ class Model:
         out = np.zeros((self.nfields(fid), self.N, self.N))
         check(self.L.msqg_get_field(self.h, fid, out))
         return out
+
+    def set_async(self, fid, pinned):
+        """start the upload of a page-locked [nl][N][N] array (msqg_set_field_async); commit() hands it to the model"""
+        check(self.L.msqg_set_field_async(self.h, fid, pinned))
+
+    def commit(self):
+        check(self.L.msqg_set_field_commit(self.h))
+
+    def get_async(self, fid, pinned):
+        """snapshot a list and start its download into a page-locked array (msqg_get_field_async)"""
+        check(self.L.msqg_get_field_async(self.h, fid, pinned))
+
+    def io_wait(self):
+        check(self.L.msqg_io_wait(self.h))
 
     def set_smoother(self, name):
         """'lex': the reference's sweep order (default, parity path); 'rb': red-black ordering (throughput mode)"""

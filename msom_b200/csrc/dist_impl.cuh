@@ -328,7 +328,6 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
   const int per = p->sbc == -1;
   if (px * py < 2 && !per) FAIL(MSQG_ERR_ARG, "a group needs px*py >= 2 tiles");
   if (per && smoother != 1) FAIL(MSQG_ERR_ARG, "periodic boundaries (sbc = -1) need the red-black smoother");
-  if (per && kind != 0) FAIL(MSQG_ERR_ARG, "periodic boundaries (sbc = -1) are built for the tiles of one process (msqg_group_create_local_sm)");
   if (p->mode_pv_invert || p->stochastic) FAIL(MSQG_ERR_ARG, "decomposed grids support the layer-coupled, deterministic path only");
   if (kind == 1 && nranks != px * py) FAIL(MSQG_ERR_ARG, "nranks must equal px*py");
   msqg_group *G = new msqg_group();

@@ -265,15 +265,27 @@ static int exchange_multi(msqg_group *G, std::vector<XItem> &items) {
       }
     } else {
       msqg_model *m = G->tiles[0];
+      /* On a periodic process grid one peer can be the neighbour in several directions (px or py = 2), or the rank
+         itself (px or py = 1).  Sends are posted by ascending direction and receives by descending direction: what I
+         send towards d arrives at the peer from its direction 8 - d, so the k-th send to a peer meets its k-th receive
+         from me.  Directions that wrap onto this rank are device copies. */
       NCK(G->nccl->GroupStart());
       for (int d = 0; d < 9; d++) {
         if (tot[0][d] == 0) continue;
-        const int dx = d % 3 - 1, dy = d / 3 - 1;
-        const int peer = tile_rank(G, m->ix + dx, m->iy + dy);
-        NCK(G->nccl->Send(m->xsend[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
-        NCK(G->nccl->Recv(m->xrecv[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
+        const int peer = tile_rank(G, m->ix + d % 3 - 1, m->iy + d / 3 - 1);
+        if (peer != G->rank) NCK(G->nccl->Send(m->xsend[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
+      }
+      for (int d = 8; d >= 0; d--) {
+        if (tot[0][d] == 0) continue;
+        const int peer = tile_rank(G, m->ix + d % 3 - 1, m->iy + d / 3 - 1);
+        if (peer != G->rank) NCK(G->nccl->Recv(m->xrecv[d], (size_t)tot[0][d], NCCL_DOUBLE, peer, G->comm, G->stream));
       }
       NCK(G->nccl->GroupEnd());
+      for (int d = 0; d < 9; d++) {
+        if (tot[0][d] == 0) continue;
+        const int peer = tile_rank(G, m->ix + d % 3 - 1, m->iy + d / 3 - 1);
+        if (peer == G->rank) CK(cudaMemcpyAsync(m->xrecv[d], m->xsend[8 - d], (size_t)tot[0][d] * sizeof(double), cudaMemcpyDeviceToDevice, G->stream));
+      }
     }
   }
   launch(1);

@@ -76,6 +76,17 @@ struct msqg_model {
   int fy[MSQG_MAXLEV + 1];     /* frame rows around the cells of a plane: 1 (the ghost ring) on undecomposed levels,
                                   MSQG_FRAME on the levels of a tile, which hold deep halos for the fused red-black sweeps
                                   (the row pitch then also keeps MSQG_FRAME columns on the right; MSQG_OX covers the left) */
+  /* pipelined field I/O (msqg_set_field_async / msqg_get_field_async): two staging slots per direction, an upload and a
+     download stream beside the compute stream, events for the hand-offs; created on first use */
+  struct AsyncIO {
+    cudaStream_t up = nullptr, down = nullptr;
+    double *in_stage[2] = {nullptr, nullptr}, *out_stage[2] = {nullptr, nullptr};
+    size_t cap = 0;                       /* doubles per staging slot */
+    cudaEvent_t ev_up[2], ev_packed[2], ev_unpacked[2], ev_down[2];
+    unsigned long up_count = 0, commit_count = 0, down_count = 0;
+    int pending_id[2] = {-1, -1};
+    bool ready = false;
+  } io;
   struct msqg_group *group;    /* a periodic model made by msqg_create: the 1 x 1 group that owns this tile (else NULL) */
   int periodic;                /* sbc == -1 (periodic(right); periodic(top), qg.h:842-846): every side of every tile is an
                                   internal side whose halo comes from the opposite tile (or from the tile itself) */
@@ -590,6 +601,7 @@ static int pg_invertq(msqg_group *G, msqg_model *m, int q_id);
 static int pg_update(msqg_group *G, msqg_model *m, int q_id, double dtmax, double *dtmax_out);
 static int pg_step(msqg_group *G, msqg_model *m, double t, double tnext_event, double *dt_out, double *tnext_out);
 static int pg_halo(msqg_group *G, int id);
+static void io_teardown(msqg_model *m);
 
 extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
   if (p->sbc == -1) return pg_create(p, device, out);
@@ -601,6 +613,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
   if (m->group) { msqg_group *G = m->group; m->group = nullptr; pg_destroy(G); return; } /* destroys this tile too */
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  io_teardown(m);
   m->graphs.clear();
   List *all[] = {&m->psi, &m->q, &m->qpred, &m->dq, &m->zeta, &m->tmp, &m->psipg, &m->zetap, &m->qforc, &m->fr,
                  &m->str, &m->topo, &m->rd, &m->ro, &m->sigfilt, &m->a_alt, &m->sstoch, &m->nstoch, &m->da, &m->res,
@@ -745,6 +758,111 @@ extern "C" int msqg_get_field(msqg_model *m, int id, double *host) {
   List *L = list_by_id(m, id);
   if (!L || !L->lev[m->depth]) FAIL(MSQG_ERR_ARG, "field list %d is not allocated", id);
   return unpack_from(m, *L, host);
+}
+
+/* ------------------------------------------------------------------ pipelined field I/O
+ * A caller that advances a stream of independent states (ensemble members, the forward / backward sweeps of
+ * msqg/qg_bfn.py) can hide the PCIe time of pyset_field / pyget_field behind the step: the upload of the next state runs
+ * on its own stream while the current one is stepped, the download of a result while the next one is stepped.  Host
+ * buffers must be page-locked and stay untouched until msqg_io_wait (uploads: until the matching commit has run). */
+static int io_setup(msqg_model *m) {
+  msqg_model::AsyncIO &io = m->io;
+  if (io.ready) return MSQG_OK;
+  CK(cudaStreamCreateWithFlags(&io.up, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&io.down, cudaStreamNonBlocking));
+  io.cap = (size_t)m->nl * m->tnx * m->tny;
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMalloc(&io.in_stage[k], io.cap * sizeof(double)));
+    CK(cudaMalloc(&io.out_stage[k], io.cap * sizeof(double)));
+    CK(cudaEventCreateWithFlags(&io.ev_up[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&io.ev_packed[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&io.ev_unpacked[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&io.ev_down[k], cudaEventDisableTiming));
+  }
+  io.ready = true;
+  return MSQG_OK;
+}
+static void io_teardown(msqg_model *m) {
+  msqg_model::AsyncIO &io = m->io;
+  if (!io.ready) return;
+  cudaStreamSynchronize(io.up); cudaStreamSynchronize(io.down);
+  for (int k = 0; k < 2; k++) {
+    cudaFree(io.in_stage[k]); cudaFree(io.out_stage[k]);
+    cudaEventDestroy(io.ev_up[k]); cudaEventDestroy(io.ev_packed[k]); cudaEventDestroy(io.ev_unpacked[k]); cudaEventDestroy(io.ev_down[k]);
+  }
+  cudaStreamDestroy(io.up); cudaStreamDestroy(io.down);
+  io.ready = false;
+}
+static int io_list(msqg_model *m, int id, List **out) {
+  if (id != MSQG_Q && id != MSQG_PSI) FAIL(MSQG_ERR_ARG, "asynchronous field I/O moves the evolving lists (MSQG_Q, MSQG_PSI)");
+  List *L = list_by_id(m, id);
+  if (!L || !L->lev[m->depth] || L->nf != m->nl) FAIL(MSQG_ERR_ARG, "field list %d is not allocated", id);
+  *out = L;
+  return MSQG_OK;
+}
+/* start the upload of host[nl][ny][nx] (pinned) for list `id`; returns at once.  At most two uploads may be in flight. */
+extern "C" int msqg_set_field_async(msqg_model *m, int id, const double *pinned_host) {
+  CK(cudaSetDevice(m->device));
+  List *L;
+  int rc;
+  if ((rc = io_list(m, id, &L)) || (rc = io_setup(m))) return rc;
+  msqg_model::AsyncIO &io = m->io;
+  if (io.up_count - io.commit_count >= 2) FAIL(MSQG_ERR_ARG, "two uploads are already waiting for msqg_set_field_commit");
+  const int slot = (int)(io.up_count & 1);
+  if (io.up_count >= 2) CK(cudaStreamWaitEvent(io.up, io.ev_packed[slot], 0)); /* the slot's previous content has been packed */
+  CK(cudaMemcpyAsync(io.in_stage[slot], pinned_host, io.cap * sizeof(double), cudaMemcpyHostToDevice, io.up));
+  CK(cudaEventRecord(io.ev_up[slot], io.up));
+  io.pending_id[slot] = id;
+  io.up_count++;
+  return MSQG_OK;
+}
+/* the compute stream waits for the oldest upload and packs it into its list (interior + ghost ring, as msqg_set_field) */
+extern "C" int msqg_set_field_commit(msqg_model *m) {
+  CK(cudaSetDevice(m->device));
+  msqg_model::AsyncIO &io = m->io;
+  if (!io.ready || io.commit_count >= io.up_count) FAIL(MSQG_ERR_ARG, "no upload to commit");
+  const int slot = (int)(io.commit_count & 1);
+  List *L;
+  int rc;
+  if ((rc = io_list(m, io.pending_id[slot], &L))) return rc;
+  const Geom &g = m->g[m->depth];
+  CK(cudaStreamWaitEvent(m->stream, io.ev_up[slot], 0));
+  dim3 b(32, 8);
+  k_pack<<<grid2(g.nx + 2, g.ny + 2, b, L->nf), b, 0, m->stream>>>(L->lev[m->depth], io.in_stage[slot], L->nf, g, L->sg);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(io.ev_packed[slot], m->stream));
+  io.commit_count++;
+  return MSQG_OK;
+}
+/* snapshot list `id` on the compute stream and start its download into host[nl][ny][nx] (pinned); returns at once */
+extern "C" int msqg_get_field_async(msqg_model *m, int id, double *pinned_host) {
+  CK(cudaSetDevice(m->device));
+  List *L;
+  int rc;
+  if ((rc = io_list(m, id, &L)) || (rc = io_setup(m))) return rc;
+  msqg_model::AsyncIO &io = m->io;
+  const int slot = (int)(io.down_count & 1);
+  const Geom &g = m->g[m->depth];
+  if (io.down_count >= 2) CK(cudaStreamWaitEvent(m->stream, io.ev_down[slot], 0)); /* the slot's previous snapshot has left */
+  dim3 b(32, 8);
+  k_unpack<<<grid2(g.nx, g.ny, b, L->nf), b, 0, m->stream>>>(io.out_stage[slot], L->lev[m->depth], L->nf, g);
+  m->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(io.ev_unpacked[slot], m->stream));
+  CK(cudaStreamWaitEvent(io.down, io.ev_unpacked[slot], 0));
+  CK(cudaMemcpyAsync(pinned_host, io.out_stage[slot], io.cap * sizeof(double), cudaMemcpyDeviceToHost, io.down));
+  CK(cudaEventRecord(io.ev_down[slot], io.down));
+  io.down_count++;
+  return MSQG_OK;
+}
+/* wait for every transfer started so far (host buffers of downloads are valid afterwards) */
+extern "C" int msqg_io_wait(msqg_model *m) {
+  CK(cudaSetDevice(m->device));
+  if (!m->io.ready) return MSQG_OK;
+  CK(cudaStreamSynchronize(m->io.up));
+  CK(cudaStreamSynchronize(m->io.down));
+  return MSQG_OK;
 }
 
 /* ------------------------------------------------------------------ coefficients */

@@ -18,9 +18,16 @@ sm = sys.argv[1] if len(sys.argv) > 1 else "lex"
 if sm == "rb":
     agg_n = 128 if world > 2 else 64
 kw = base_kw(N, nl)
+periodic = sm == "rbper"   # doubly periodic domain (sbc = -1) on the process grid: neighbours wrap around
+if periodic:
+    sm = "rb"
+    kw = base_kw(N, nl, sbc=-1.)
 px, py = grid_for(world)
 g = nccl_group(G.make_params(**kw), agg_n, local, smoother=sm)
 psi = synth_psi(N, nl)
+if periodic:
+    from test_gpu_periodic import periodic_psi
+    psi = periodic_psi(N, nl)
 g.set_global(G.PSI, psi); g.set_const()
 mo = O.Model(O.make_params(**kw)); mo.L.orc_set_decomp(mo.h, px, py, agg_n); mo.set_smoother(sm)
 mo.set(O.PSI, psi); mo.set_const()
@@ -34,7 +41,7 @@ ok &= (g.total_cycles == mo.L.orc_total_cycles(mo.h))
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("DIST_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", sm, g.transport, "world", world, "grid %dx%d" % (px, py), "exchanges", g.exchanges)
+    print("DIST_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", sm + ("-periodic" if periodic else ""), g.transport, "world", world, "grid %dx%d" % (px, py), "exchanges", g.exchanges)
 g.close()
 dist.destroy_process_group()
 sys.exit(0 if int(t.item()) == 1 else 1)

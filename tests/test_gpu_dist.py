@@ -107,7 +107,7 @@ def test_nccl_backend_two_gpus(gpu):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for sm in ("rb", "lex"):
+    for sm in ("rb", "lex", "rbper"):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                             "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "dist_check.py"), sm],
                            capture_output=True, text=True, timeout=600)

@@ -99,3 +99,48 @@ def test_edge_shapes(gpu, N, nl):
         assert mg.step() == mo.step()
     assert np.array_equal(mg.get(G.Q), mo.get(O.Q)) and np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
     assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
+
+
+def test_pipelined_field_io_equals_set_step_get(gpu):
+    """msqg_set_field_async / _commit / msqg_get_field_async (include/msqg.h): a stream of independent states stepped with
+    the uploads and downloads on their own streams gives the bits of msqg_set_field; step; msqg_get_field for every state,
+    whatever the overlap; a third upload without a commit is refused."""
+    import torch
+    from common import base_kw, synth_psi
+    from msom_b200 import capi as G
+    N, nl, nstates = 128, 3, 5
+
+    def model():
+        mm = G.Model(G.make_params(**base_kw(N, nl)), gpu)
+        mm.set_smoother("rb")
+        mm.set(G.PSI, synth_psi(N, nl)); mm.set_const()
+        return mm
+
+    ms, m = model(), model()               # two identical models: warm starts and the dt chain evolve alike
+    rng = np.random.default_rng(3)
+    q0 = m.get(G.Q)
+    states = [q0 * (1 + 0.05 * k) + 1e-3 * rng.standard_normal(q0.shape) for k in range(nstates)]
+    ref = []
+    for s in states:                       # serial: msqg_set_field; step; msqg_get_field
+        ms.set(G.Q, s); ms.step(); ref.append(ms.get(G.Q))
+    hin = [torch.empty(q0.shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+    hout = [torch.empty(q0.shape, dtype=torch.float64).pin_memory() for _ in range(nstates)]
+    hin[0].copy_(torch.from_numpy(states[0]))
+    m.set_async(G.Q, hin[0].numpy())
+    for k in range(nstates):
+        m.commit()
+        if k + 1 < nstates:
+            m.io_wait() if k >= 1 else None          # the other input buffer is about to be rewritten on the host
+            hin[(k + 1) & 1].copy_(torch.from_numpy(states[k + 1]))
+            m.set_async(G.Q, hin[(k + 1) & 1].numpy())
+        m.step()
+        m.get_async(G.Q, hout[k].numpy())
+    m.io_wait()
+    for k in range(nstates):
+        assert np.array_equal(hout[k].numpy(), ref[k]), k
+    m.set_async(G.Q, hin[0].numpy()); m.set_async(G.Q, hin[1].numpy())
+    with pytest.raises(G.MsqgError):
+        m.set_async(G.Q, hin[0].numpy())
+    m.commit(); m.commit(); m.io_wait()
+    with pytest.raises(G.MsqgError):
+        m.set_async(G.FR, hin[0].numpy())
