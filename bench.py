@@ -389,6 +389,13 @@ def run_ours(args):
     for h in hin:
         h.copy_(hq)
     hin_np, hout_np = [h.numpy() for h in hin], [h.numpy() for h in hout]
+    # one untimed pass of the loop body: the first transfer allocates the staging buffers, streams and events
+    G.check(LG.msqg_set_field_async(tile_h, G.Q, hin_np[0]))
+    G.check(LG.msqg_set_field_commit(tile_h))
+    step()
+    G.check(LG.msqg_get_field_async(tile_h, G.Q, hout_np[0]))
+    G.check(LG.msqg_io_wait(tile_h))
+    torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     G.check(LG.msqg_set_field_async(tile_h, G.Q, hin_np[0]))

@@ -111,7 +111,11 @@ int msqg_read_params(const char *path, msqg_params *p);
 
 /* init_grid(N) + set_vars() (msqg/qg.h:837-925): allocates every layer list on
  * `device`, zero fields, ppl = vpg*x - upg*y, Frl = Fr.  N must be a power of
- * two >= 8, 2 <= nl <= 12, sbc == 0. */
+ * two >= 8, 2 <= nl <= 12.  sbc: 0 free slip, > 0 partial slip (qg.h:185-198), -1 doubly periodic (qg.h:842-846).
+ * A periodic model is the tile of a 1 x 1 periodic group (layer 1b) that msqg_create builds by itself: N >= 16, the
+ * red-black smoother, the layer-coupled deterministic path without tracers, energy diagnostics, filter or a
+ * large-scale flow (the non-periodic psi_pg of qg.h:1105-1114); set_const / invertq / update / advance / step /
+ * comp_q / set_field / get_field / ke1 behave as on a closed basin. */
 int msqg_create(const msqg_params *p, int device, msqg_model **out);
 void msqg_destroy(msqg_model *m);                 /* trash_vars, qg.h:1130-1154 */
 /* run on this CUDA stream (a cudaStream_t passed as void*); default: own stream */
@@ -251,7 +255,11 @@ int msqg_nccl_unique_id(void *out128);
 int msqg_group_create_local(const msqg_params *p, int device, int px, int py, int agg_n, msqg_group **out);
 int msqg_group_create_nccl(const msqg_params *p, int device, int px, int py, int agg_n, int rank, int nranks,
                            const void *uid128, msqg_group **out);
-/* the same with the smoother named (msqg_set_smoother): 1 = red-black.  A red-black group gives the bits of the
+/* Periodic boundaries (p->sbc == -1; red-black groups only): every side of every tile is an internal side and the
+ * neighbour across a side of the domain is the tile on the opposite side (the tile itself where px or py is 1, in which
+ * case msqg_group_create_local_sm accepts px = py = 1); levels up to 32^2 are swept by the single-CTA coarse kernel with
+ * wrap-around neighbours, agg_n is chosen by the library.
+ * The same with the smoother named (msqg_set_smoother): 1 = red-black.  A red-black group gives the bits of the
  * single-GPU red-black solve whatever px, py and agg_n are (a half-sweep is decomposition independent); levels with
  * fewer than agg_n cells per side are replicated on every GPU (all-gather of the restricted residual, redundant coarse
  * solve) and the sweeps of a distributed level need ONE halo exchange (deep halos, communication-avoiding). */

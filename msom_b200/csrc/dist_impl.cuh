@@ -240,11 +240,11 @@ static int reduce_max_enqueue(msqg_group *G, int off, int n) {
     msqg_model *m = G->tiles[0];
     ProfScope ps_r(m, PROF_XCHG, 1000);
     NCK(G->nccl->AllReduce(m->d_scal + off, G->d_red, n, NCCL_DOUBLE, NCCL_MAX, G->comm, G->stream));
-    CK(cudaMemcpyAsync(G->h_red, G->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, G->stream));
+    CK(to_host(G->stream, G->h_red, G->d_red, n)); /* by a kernel, not a copy engine (see k_to_host) */
     return MSQG_OK;
   }
   for (int t = 0; t < nt; t++)
-    CK(cudaMemcpyAsync(G->h_red + (size_t)t * n, G->tiles[t]->d_scal + off, n * sizeof(double), cudaMemcpyDeviceToHost, G->stream));
+    CK(to_host(G->stream, G->h_red + (size_t)t * n, G->tiles[t]->d_scal + off, n));
   return MSQG_OK;
 }
 static int reduce_max_finish(msqg_group *G, int n, double *out) {
@@ -312,9 +312,10 @@ static int group_setup_p2p(msqg_group *G) {
 static int group_check_p2p(msqg_group *G) {
   if (!G->p2p) return MSQG_OK;
   for (msqg_model *m : G->tiles) {
-    unsigned long long e = 0;
-    CK(cudaMemcpyAsync(&e, (unsigned long long *)(m->xarea + 2 * 9 * m->xcap) + 17, sizeof(e), cudaMemcpyDeviceToHost, G->stream));
+    unsigned long long *he = (unsigned long long *)(G->h_red + 64 * 63); /* last row of the pinned scratch */
+    CK(to_host(G->stream, he, (const unsigned long long *)(m->xarea + 2 * 9 * m->xcap) + 17, 1));
     CK(cudaStreamSynchronize(G->stream));
+    const unsigned long long e = *he;
     if (e) FAIL(MSQG_ERR_CUDA, "peer-memory halo exchange timed out waiting for a neighbour");
   }
   return MSQG_OK;
@@ -339,7 +340,7 @@ static int group_create(const msqg_params *p, int device, int px, int py, int ag
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&G->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&G->d_red, 64 * sizeof(double)));
-  CK(cudaMallocHost(&G->h_red, 64 * 64 * sizeof(double)));
+  CK(cudaHostAlloc(&G->h_red, 64 * 64 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
   int rc;
   if (kind == 0) {
     for (int iy = 0; iy < py; iy++)
@@ -418,7 +419,7 @@ static int g_residual_enqueue(msqg_group *G, int q_id) {
     const int D = m->depth;
     const Geom &g = m->g[D];
     List *ql = list_by_id(m, q_id);
-    CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), G->stream));
+    CK(zero_words(G->stream, m->d_scal, 1));
     dim3 b(64, 4);
     LayerMetrics M = metrics_of(m);
     ProfScope ps(m, PROF_RESIDUAL, 0);
@@ -647,7 +648,7 @@ static int g_rhs_prepare(msqg_group *G, double *umax) {
   bool use_tmp = false;
   for (msqg_model *m : G->tiles) {
     const Geom &g = m->g[D];
-    CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), G->stream));
+    CK(zero_words(G->stream, m->d_scal + 1, m->nl));
     ProfScope ps(m, PROF_LAP, 0);
     launch_lap(G->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1, 0.);
     m->launches++;

@@ -502,13 +502,13 @@ static int create_model(const msqg_params *p, int device, int px, int py, int ix
   }
   CK(cudaMalloc(&m->d_stage, m->stage_doubles * sizeof(double)));
   CK(cudaMalloc(&m->d_scal, 64 * sizeof(double)));
-  CK(cudaMallocHost(&m->h_scal, 64 * sizeof(double)));
+  CK(cudaHostAlloc(&m->h_scal, 64 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
   CK(cudaMalloc(&m->d_wind, (size_t)p->N * sizeof(double)));
   CK(cudaMemsetAsync(m->d_wind, 0, (size_t)p->N * sizeof(double), m->stream));
   CK(cudaMalloc(&m->d_kepart, (size_t)((p->N + 15) / 16) * ((p->N + 15) / 16) * sizeof(double)));
   CK(cudaMalloc(&m->d_err, sizeof(int)));
   CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
-  CK(cudaMallocHost(&m->h_err, sizeof(int)));
+  CK(cudaHostAlloc(&m->h_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
   m->mailbox = nullptr; m->mailbox_words = 0; m->d_dbg = nullptr;
   m->nme_ft = 0; m->energy_vars = 0; m->filter_vars = 0; m->siglev0 = 0.;
   for (int l = 0; l <= MSQG_MAXLEV; l++) m->rowcoef[l] = nullptr;
@@ -1335,8 +1335,32 @@ static int launch_coarse_rb(msqg_model *m, int Lc, int nrelax, const CoarseCoef<
     default: FAIL(MSQG_ERR_ARG, "unsupported nl=%d", nl);   \
   }
 
+/* A few words from device memory to MAPPED pinned host memory, written by a kernel instead of a copy engine: the
+ * convergence test of mg_solve, the CFL reduction and the error word are read back several times per step, and a
+ * cudaMemcpyAsync of 8 bytes queues behind whatever bulk transfer occupies the device-to-host engine (the pipelined
+ * field downloads of msqg_get_field_async: every read-back then waited ~10 ms for half a gigabyte to leave). */
+template <class T>
+__global__ void k_to_host(T *__restrict__ dst_mapped, const T *__restrict__ src, int n) {
+  const int i = threadIdx.x;
+  if (i < n) dst_mapped[i] = src[i];
+  __threadfence_system();
+}
+template <class T>
+static inline cudaError_t to_host(cudaStream_t st, T *host_mapped, const T *dev, int n) {
+  k_to_host<T><<<1, 64, 0, st>>>(host_mapped, dev, n); /* n <= 64; pinned host memory is device-addressable (UVA) */
+  return cudaGetLastError();
+}
+
+/* the few reduction words of a step are also CLEARED by a kernel: an asynchronous memset may be served by a copy engine
+   and would then wait behind a bulk transfer exactly like the read-backs above */
+__global__ void k_zero_words(double *p, int n) { if ((int)threadIdx.x < n) p[threadIdx.x] = 0.; }
+static inline cudaError_t zero_words(cudaStream_t st, double *p, int n) {
+  k_zero_words<<<1, 64, 0, st>>>(p, n);
+  return cudaGetLastError();
+}
+
 static int check_relax_err(msqg_model *m) {
-  CK(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CK(to_host(m->stream, m->h_err, m->d_err, 1));
   CK(cudaStreamSynchronize(m->stream));
   if (*m->h_err) {
     CK(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
@@ -1359,7 +1383,7 @@ struct MgProblem {
 static int mg_residual_enqueue(msqg_model *m, const MgProblem &P) {
   const int D = m->depth;
   const Geom &g = m->g[D];
-  CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), m->stream));
+  CK(zero_words(m->stream, m->d_scal, 1));
   dim3 b(64, 4);
   { ProfScope ps(m, PROF_RESIDUAL, 0);
   if (P.mode < 0) {
@@ -1371,7 +1395,7 @@ static int mg_residual_enqueue(msqg_model *m, const MgProblem &P) {
   }
   m->launches++;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(m->h_scal, m->d_scal, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(to_host(m->stream, m->h_scal, m->d_scal, 1));
   return MSQG_OK;
 }
 static int mg_residual(msqg_model *m, const MgProblem &P, double *maxres) {
@@ -1452,7 +1476,7 @@ static int mg_fused(msqg_model *m, const MgProblem &P) {
 static int mg_corr_residual(msqg_model *m, const MgProblem &P, const double *da, double *a_new, double *maxres) {
   const int D = m->depth;
   const Geom &g = m->g[D];
-  CK(cudaMemsetAsync(m->d_scal, 0, sizeof(double), m->stream));
+  CK(zero_words(m->stream, m->d_scal, 1));
   dim3 b(CR_BX, CR_BY);
   double *res_c = (D - 1 >= 1) ? m->res.lev[D - 1] : nullptr;
   const Geom &gc = m->g[D >= 1 ? D - 1 : 0];
@@ -1463,7 +1487,7 @@ static int mg_corr_residual(msqg_model *m, const MgProblem &P, const double *da,
   }
   m->launches++;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(m->h_scal, m->d_scal, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(to_host(m->stream, m->h_scal, m->d_scal, 1));
   CK(cudaStreamSynchronize(m->stream));
   *maxres = m->h_scal[0];
   return MSQG_OK;
@@ -1778,7 +1802,7 @@ static inline double avg4(double a, double b, double c, double d) {
 static int max_face_speed(msqg_model *m, List &L, double *umax_host) {
   const int D = m->depth;
   const Geom &g = m->g[D];
-  CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
+  CK(zero_words(m->stream, m->d_scal + 1, m->nl));
   dim3 b(64, 4);
   /* out-of-place laplacian into tmp is a by-product; only umax is wanted */
   launch_lap(m->stream, m->nl, L.lev[D], m->tmp.lev[D], g, m->d_scal + 1, m->sbcc);
@@ -2026,7 +2050,7 @@ static int rhs_prepare(msqg_model *m) {
   const int D = m->depth;
   const Geom &g = m->g[D];
   dim3 b(64, 4);
-  CK(cudaMemsetAsync(m->d_scal + 1, 0, m->nl * sizeof(double), m->stream));
+  CK(zero_words(m->stream, m->d_scal + 1, m->nl));
   ProfScope ps(m, PROF_LAP, 0);
   launch_lap(m->stream, m->nl, m->psi.lev[D], m->zeta.lev[D], g, m->d_scal + 1, m->sbcc);
   m->launches++;
@@ -2035,7 +2059,7 @@ static int rhs_prepare(msqg_model *m) {
     m->launches++;
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(m->h_scal + 1, m->d_scal + 1, m->nl * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(to_host(m->stream, m->h_scal + 1, m->d_scal + 1, m->nl));
   return MSQG_OK;
 }
 /* dtmax chain of advection_pv, qg.h:383-391 (needs the umax D2H to have completed) */
