@@ -604,7 +604,11 @@ static int pg_halo(msqg_group *G, int id);
 static void io_teardown(msqg_model *m);
 
 extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
-  if (p->sbc == -1) return pg_create(p, device, out);
+  if (p->sbc == -1) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(MSQG_ERR_CUDA, "no CUDA device: the msqg timestep has no CPU path");
+    return pg_create(p, device, out);
+  }
   return create_model(p, device, 1, 1, 0, 0, 0, nullptr, out);
 }
 

@@ -101,7 +101,7 @@ def test_qg_exe_missing_params(tmp_path):
 
 def test_argument_validation():
     from msom_b200 import capi as G
-    for kw, frag in ((dict(nl=1), "nl must be"), (dict(N=100), "power of two"), (dict(sbc=-1.0), "sbc"),
+    for kw, frag in ((dict(nl=1), "nl must be"), (dict(N=100), "power of two"), (dict(sbc=-2.0), "sbc"),
                      (dict(nptr=1, stochastic=1), "tracers"), (dict(nptr=99), "nptr")):
         k = base_kw(64, 2); k.update(kw)
         if "nl" in kw:

@@ -97,3 +97,29 @@ def test_periodic_rejects_what_is_not_built(gpu):
         G.Model(G.make_params(**base_kw(64, 2, sbc=-1., upg=[0.1, 0.], vpg=[0., 0.])), gpu)
     with pytest.raises(G.MsqgError):
         G.Model(G.make_params(**base_kw(64, 2, sbc=-1., mode_pv_invert=1)), gpu)
+
+
+def test_periodic_full_size_translation_equivariance(gpu):
+    """2048^2 x 4, where the oracle is too slow: the periodic step commutes BIT FOR BIT with a diagonal shift by N/2 cells
+    (constant coefficients once the wind is off; the hierarchy down to 2 x 2 cells maps onto itself; red-black
+    half-sweeps do not depend on traversal order) -- the property tests/test_oracle_rb.py pins on the oracle, here across
+    hundreds of CTAs, the wrap-around halos of every level and the recorded cycle graphs."""
+    from msom_b200 import capi as G
+    N, nl = 2048, 4
+    psi = periodic_psi(N, nl)
+    sh = lambda a: np.roll(a, (N // 2, N // 2), axis=(1, 2))
+
+    def run(p0, nsteps=3):
+        m = G.Model(G.make_params(**base_kw(N, nl, sbc=-1., tau0=0.)), gpu)
+        m.set(G.PSI, p0); m.set_const()
+        q0 = m.get(G.Q)
+        dts = [m.step() for _ in range(nsteps)]
+        out = (q0, m.get(G.Q), m.get(G.PSI), dts, m.total_cycles)
+        m.close()
+        return out
+
+    q0, q1, p1, dts, cyc = run(psi)
+    r0, r1, rp, rdts, rcyc = run(sh(psi))
+    assert rdts == dts and rcyc == cyc and cyc >= 6
+    assert np.array_equal(r0, sh(q0)) and np.array_equal(r1, sh(q1)) and np.array_equal(rp, sh(p1))
+    assert np.isfinite(q1).all() and not np.array_equal(q1, q0)
