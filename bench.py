@@ -33,19 +33,31 @@ N_DEFAULT, NL_DEFAULT = 4096, 4
 MODAL = False  # --modal: MODE_PV_INVERT 1 (BASELINE config 3), set by main()
 
 
+PERIODIC = False  # --periodic: sbc = -1 (doubly periodic domain, datapoint only)
+VARRO = False  # --varRo: Ro(y) (horizontally varying stretching / vertical modes, datapoint only)
+
+
 def workload_kw(N, nl):
     from common import base_kw
-    return base_kw(N, nl, mode_pv_invert=1) if MODAL else base_kw(N, nl)
+    over = {}
+    if MODAL:
+        over["mode_pv_invert"] = 1
+    if PERIODIC:
+        over["sbc"] = -1.
+    if VARRO:
+        over["varRo"] = 1
+    return base_kw(N, nl, **over)
 
 
 def workload_psi(N, nl):
-    from common import synth_psi
-    return synth_psi(N, nl)
+    from common import synth_psi, periodic_psi
+    return periodic_psi(N, nl) if PERIODIC else synth_psi(N, nl)
 
 
 def workload_name(N, nl):
-    return "msqg double-gyre %d^2 x nl=%d, %s, tolerance 1e-3" % (
-        N, nl, "vertical-mode inversion (MODE_PV_INVERT 1)" if MODAL else "layer-coupled multigrid inversion (MODE_PV_INVERT 0)")
+    return "msqg double-gyre %d^2 x nl=%d, %s, tolerance 1e-3%s%s" % (
+        N, nl, "vertical-mode inversion (MODE_PV_INVERT 1)" if MODAL else "layer-coupled multigrid inversion (MODE_PV_INVERT 0)",
+        ", doubly periodic (sbc = -1)" if PERIODIC else "", ", Ro(y) (varRo = 1)" if VARRO else "")
 
 
 def algorithmic_bytes(nl):
@@ -549,6 +561,8 @@ def main():
                          "number of GPUs; lex: the reference's serial sweep order (parity path; does not scale)")
     ap.add_argument("--modal", action="store_true",
                     help="vertical-mode inversion (MODE_PV_INVERT 1, eigmode.h; BASELINE config 3) instead of the layer-coupled solver")
+    ap.add_argument("--periodic", action="store_true", help="datapoint: doubly periodic domain (sbc = -1)")
+    ap.add_argument("--varRo", action="store_true", help="datapoint: Ro(y), i.e. horizontally varying stretching (with --modal: vertical modes)")
     ap.add_argument("--ensemble", action="store_true", help="BASELINE config 5: stochastic ensemble, --members per GPU of 512^2 x 3")
     ap.add_argument("--members", type=int, default=4)
     ap.add_argument("--ens-N", type=int, default=512, dest="ens_N")
@@ -559,8 +573,11 @@ def main():
     args = ap.parse_args()
     if args.agg_n <= 0:
         args.agg_n = args.N if args.smoother == "lex" else min(512, args.N)
-    global MODAL
+    global MODAL, PERIODIC, VARRO
     MODAL = bool(args.modal)
+    PERIODIC, VARRO = bool(args.periodic), bool(args.varRo)
+    if PERIODIC:
+        args.no_other = True   # the periodic domain runs with the red-black smoother only
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -131,6 +131,7 @@ struct msqg_group {
   int rank, nranks;
   std::vector<msqg_model *> tiles; /* local: all tiles, index iy*px+ix; nccl: this rank's tile */
   cudaStream_t stream;
+  bool own_stream = true;
   NcclApi *nccl;
   ncclComm_t comm;
   double *d_red, *h_red; /* reduction scratch (device / pinned host), 64 doubles */
@@ -397,7 +398,7 @@ extern "C" void msqg_group_destroy(msqg_group *G) {
   if (G->comm && G->nccl) G->nccl->CommDestroy(G->comm);
   cudaFree(G->d_red);
   cudaFreeHost(G->h_red);
-  cudaStreamDestroy(G->stream);
+  if (G->own_stream) cudaStreamDestroy(G->stream);
   delete G;
 }
 extern "C" int msqg_group_ntiles(msqg_group *G) { return (int)G->tiles.size(); }
@@ -757,6 +758,14 @@ static int pg_create(const msqg_params *p, int device, msqg_model **out) {
   return MSQG_OK;
 }
 static void pg_destroy(msqg_group *G) { msqg_group_destroy(G); }
+static int pg_set_stream(msqg_group *G, cudaStream_t s) {
+  CK(cudaStreamSynchronize(G->stream));
+  G->graphs.clear();
+  if (G->own_stream) cudaStreamDestroy(G->stream);
+  G->stream = s; G->own_stream = false;
+  for (msqg_model *m : G->tiles) { m->graphs.clear(); m->stream = s; m->own_stream = false; }
+  return MSQG_OK;
+}
 static void pg_mirror_stats(msqg_group *G, msqg_model *m) { m->mgpsi = G->mgpsi; m->total_cycles = G->total_cycles; }
 static int pg_set_const(msqg_group *G) { return msqg_group_set_const(G); }
 static int pg_invertq(msqg_group *G, msqg_model *m, int q_id) {

@@ -601,6 +601,7 @@ static int pg_invertq(msqg_group *G, msqg_model *m, int q_id);
 static int pg_update(msqg_group *G, msqg_model *m, int q_id, double dtmax, double *dtmax_out);
 static int pg_step(msqg_group *G, msqg_model *m, double t, double tnext_event, double *dt_out, double *tnext_out);
 static int pg_halo(msqg_group *G, int id);
+static int pg_set_stream(msqg_group *G, cudaStream_t s);
 static void io_teardown(msqg_model *m);
 
 extern "C" int msqg_create(const msqg_params *p, int device, msqg_model **out) {
@@ -650,6 +651,7 @@ extern "C" void msqg_destroy(msqg_model *m) {
 
 extern "C" int msqg_set_stream(msqg_model *m, void *s) {
   CK(cudaSetDevice(m->device));
+  if (m->group) return pg_set_stream(m->group, (cudaStream_t)s); /* the group and its tile share one stream */
   CK(cudaStreamSynchronize(m->stream));
   m->graphs.clear();
   if (m->own_stream) cudaStreamDestroy(m->stream);
@@ -2639,6 +2641,7 @@ extern "C" int msqg_test_div(int device, const double *x, const double *d, doubl
 extern "C" int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_out) {
   CK(cudaSetDevice(m->device));
   if (!m->const_set || m->p.mode_pv_invert) FAIL(MSQG_ERR_ARG, "needs set_const (layer-coupled mode)");
+  if (m->g[m->depth].bc) FAIL(MSQG_ERR_ARG, "msqg_time_vcycle times an undecomposed model");
   const int D = m->depth;
   MgProblem P{m->nl, -1, m->psi.lev[D], m->q.lev[D]};
   double r;

@@ -26,6 +26,20 @@ def synth_psi(N, nl, L0=80., seed=1234):
     return psi
 
 
+def periodic_psi(N, nl, L0=80., seed=5):
+    """a doubly periodic stream function (sbc = -1 cases): smooth waves + zero-mean noise"""
+    rng = np.random.default_rng(seed)
+    x = (np.arange(N) + 0.5) * L0 / N
+    X, Y = np.meshgrid(x, x)
+    psi = np.zeros((nl, N, N))
+    for l in range(nl):
+        A = 1.0 / (l + 1)
+        psi[l] = A * np.sin(2 * np.pi * X / L0) * np.sin(4 * np.pi * Y / L0) + 0.3 * A * np.cos(2 * np.pi * (X + 2 * Y) / L0)
+        nz = rng.uniform(-1, 1, (N, N))
+        psi[l] += 1e-3 * A * (nz - nz.mean())
+    return psi
+
+
 def rel_l2(a, b):
     d = np.linalg.norm((a - b).ravel())
     n = np.linalg.norm(b.ravel())
