@@ -281,3 +281,29 @@ def test_energy_conserv_variant_is_the_same_operator_for_uniform_stretching():
         fr[l] = (0.003 + 0.002 * l) * (1 + 0.3 * np.sin(2 * np.pi * x) * np.cos(np.pi * y))
     a, b = tendency(0, fr), tendency(1, fr)
     assert np.abs(a - b).max() > 1e-6 * np.abs(a).max()
+
+
+def test_varying_vertical_modes_fields():
+    """MODE_PV_INVERT with varRo > 0 (eigmode.h:74-299: one dgeev per column): the mode matrices and lambda = iBu are
+    fields.  In every column cl2m*cm2l = I, the first baroclinic lambda is the analytic 2-layer value built from that
+    column's Ro(y) (qg.h:1032-1037) and the columns of one row (same Ro) hold identical matrices."""
+    if O._lapack_path() is None:
+        pytest.skip("no LAPACK dgeev available")
+    N, nl = 32, 2
+    kw = base_kw(N, nl, mode_pv_invert=1, varRo=1)
+    m = O.Model(O.make_params(**kw))
+    m.set(O.PSI, synth_psi(N, nl)); m.set_const()
+    ib, cl, cm = m.get(O.IBU), m.get(O.CL2M), m.get(O.CM2L)
+    dh = np.array(kw["dh"]); F = kw["Fr"][0]; L0, Rom, beta = kw["L0"], kw["Rom"], kw["beta"]
+    y = (np.arange(N) + 0.5) * L0 / N
+    Ro = Rom / (1 + Rom * beta * (y - 0.5 * L0))
+    dhc = 0.5 * (dh[0] + dh[1])
+    lam = (F / Ro) ** 2 / dhc * (1 / dh[0] + 1 / dh[1])
+    assert np.ptp(lam) > 0.1 * lam.mean()
+    assert np.allclose(-ib[1], lam[:, None] * np.ones((1, N)), rtol=1e-11)
+    assert not ib[0].any()
+    for j in (0, N // 2, N - 1):
+        for i in (0, 7):
+            A = cl[:, j, i].reshape(nl, nl) @ cm[:, j, i].reshape(nl, nl)
+            assert np.allclose(A, np.eye(nl), atol=1e-10)
+        assert np.array_equal(cl[:, j, 0], cl[:, j, N - 1]) and np.array_equal(ib[:, j, 0], ib[:, j, 5])
