@@ -1198,14 +1198,15 @@ static int launch_relax_rb_pass_w(msqg_model *m, double *da, const double *res, 
   A.reuse = m->rb_reuse;
   if (RCOEF && (g.bc || !A.coef)) FAIL(MSQG_ERR_ARG, "horizontally varying stretching (varRo, frpg) is supported on undecomposed levels only");
   const int nxo_ = A.ox_hi - A.ox_lo, nyo_ = A.oy_hi - A.oy_lo;
-  if constexpr (!RCOEF && NL <= 4) {
+  if constexpr (NL <= 4) {
     /* small levels / tiles: one shared-memory window per CTA instead of the streaming pipeline (k_relax_rb_tile) */
     int lim = 512;
     { const char *e = getenv("MSQG_RB_TILE"); if (e) lim = atoi(e); }
+    if (RCOEF) { const char *e = getenv("MSQG_RB_COARSE_TABLES"); if (e && atoi(e) == 0) lim = 0; }
     if ((long long)nxo_ * nyo_ <= (long long)lim * lim) {
       constexpr int WS = RB_TO + 4 * RB_NSMAX;
       const size_t tsmem = (size_t)2 * NL * WS * WS * sizeof(double);
-      auto tk = k_relax_rb_tile<NL>;
+      auto tk = k_relax_rb_tile<NL, RCOEF>;
       static KernelDevState tst;
       const int dev = m->device & 63;
       if (!tst.set[dev]) {
@@ -1298,8 +1299,11 @@ static int launch_relax_rb(msqg_model *m, double *da, const double *res, int lev
  * of all those levels fit in shared memory; 0 = not applicable (lexicographic smoother, varying stretching, tiny grids) */
 static int coarse_top_level(msqg_model *m, int nf_problem, int maxlevel) {
   if (m->smoother != 1) return 0;
-  if (nf_problem > 1 && !m->s_uniform) return 0;
-  if (nf_problem == 1 && !m->modes_uniform) return 0; /* lambda is a field: level-by-level launches with tables */
+  /* horizontally varying stretching / lambda: the coarse kernel reads the coefficient tables (built for nl <= 6) */
+  if (nf_problem > 1 && !m->s_uniform && (m->nl > 6 || !m->rowcoef[1] || m->g[1].bc)) return 0;
+  if (nf_problem == 1 && !m->modes_uniform && !m->modecoef[0][1]) return 0;
+  { const char *e = getenv("MSQG_RB_COARSE_TABLES"); /* A/B: tables through the level-by-level streaming kernel */
+    if (e && atoi(e) == 0 && (nf_problem > 1 ? !m->s_uniform : !m->modes_uniform)) return 0; }
   if (!m->periodic) { const char *e = getenv("MSQG_RB_COARSE"); if (e && atoi(e) == 0) return 0; } /* A/B: level-by-level launches */
   int Lc = RB_COARSE_MAXLEV;
   if (Lc > maxlevel) Lc = maxlevel;
@@ -1311,14 +1315,22 @@ static int coarse_top_level(msqg_model *m, int nf_problem, int maxlevel) {
   }
   return Lc >= 2 ? Lc : 0;
 }
-template <int NL>
+template <int NL, bool RCOEF = false>
 static int launch_coarse_rb(msqg_model *m, int Lc, int nrelax, const CoarseCoef<NL> &CC) {
   CoarseArgs A;
+  memset(&A, 0, sizeof(A));
   A.res = m->res.lev[Lc]; A.da = m->da.lev[Lc]; A.g = m->g[Lc]; A.Lc = Lc; A.nrelax = nrelax; A.periodic = m->periodic;
+  if (RCOEF) {
+    for (int l = 1; l <= Lc; l++) {
+      A.coef[l] = relax_table(m, l);
+      if (!A.coef[l]) FAIL(MSQG_ERR_ARG, "no coefficient table on level %d", l);
+    }
+    A.coef_cell = relax_table_per_cell(m) ? 1 : 0;
+  }
   size_t cells = 0;
   for (int l = 1; l <= Lc; l++) cells += (size_t)1 << (2 * l);
   const size_t smem = 2 * (size_t)NL * cells * sizeof(double);
-  auto kern = k_coarse_rb<NL>;
+  auto kern = k_coarse_rb<NL, RCOEF>;
   static KernelDevState st;
   const int dev = m->device & 63;
   if (!st.set[dev]) {
@@ -1523,13 +1535,19 @@ static int mg_levels(msqg_model *m, int nf, int mode, int nrelax, int from, int 
         CoarseCoef<NL> CC;
         for (int l = 1; l <= Lc; l++) CC.c[l] = relax_coef_layers<NL>(m, l);
         CC.c[0] = CC.c[1];
-        rc = launch_coarse_rb<NL>(m, Lc, nrelax, CC);
+        if (relax_uses_table<NL>(m)) {
+          if constexpr (NL <= 6) rc = launch_coarse_rb<NL, true>(m, Lc, nrelax, CC);
+          else rc = MSQG_ERR_ARG;
+        } else
+          rc = launch_coarse_rb<NL>(m, Lc, nrelax, CC);
       });
     } else {
       CoarseCoef<1> CC;
       for (int l = 1; l <= Lc; l++) CC.c[l] = relax_coef_scalar(m, l, m->lam_lev[(size_t)l * m->nl + mode]);
       CC.c[0] = CC.c[1];
-      rc = launch_coarse_rb<1>(m, Lc, nrelax, CC);
+      m->coef_mode = m->modes_uniform ? -1 : mode;
+      rc = m->coef_mode >= 0 ? launch_coarse_rb<1, true>(m, Lc, nrelax, CC) : launch_coarse_rb<1>(m, Lc, nrelax, CC);
+      m->coef_mode = -1;
     }
     if (rc) return rc;
   }
@@ -1627,7 +1645,7 @@ static int mg_solve(msqg_model *m, const MgProblem &P, double tolerance, msqg_mg
   rc = mg_residual(m, P, &resb);
   if (rc) return rc;
   s.resb = s.resa = resb;
-  const bool graphed = m->smoother == 1 && m->use_graphs && !m->prof_on && (P.nf == 1 ? m->modes_uniform : m->s_uniform);
+  const bool graphed = m->smoother == 1 && m->use_graphs && !m->prof_on; /* coefficient tables are fixed between set_const calls */
   std::vector<msqg_model *> self(1, m);
   for (s.i = 0; s.i < 100 && (s.i < 1 || s.resa > tolerance); s.i++) {
     /* one cycle + the residual that follows it: a single graph launch in red-black mode */

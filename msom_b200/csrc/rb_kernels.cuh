@@ -308,6 +308,8 @@ struct CoarseArgs {
   double *da;        /* level Lc, [NL] planes */
   Geom g;            /* geometry of level Lc (undecomposed) */
   int Lc, nrelax;
+  const double *coef[RB_COARSE_MAXLEV + 1]; /* RCOEF: Thomas coefficient table of every level (k_rowcoef / k_modecoef), else unused */
+  int coef_cell;     /* RCOEF: 1 = per cell [ny][nx][6][NL], 0 = per row [ny][6][NL] */
   int periodic;      /* sbc = -1: neighbours and bilinear stencils wrap around instead of meeting dirichlet ghosts */
 };
 template <int NL>
@@ -316,7 +318,7 @@ __device__ __forceinline__ size_t coarse_smem_doubles(int Lc) {
   for (int l = 1; l <= Lc; l++) cells += (size_t)1 << (2 * l);
   return 2 * (size_t)NL * cells;
 }
-template <int NL>
+template <int NL, bool RCOEF = false>
 __global__ void __launch_bounds__(512)
 k_coarse_rb(CoarseArgs A, CoarseCoef<NL> CC) {
   extern __shared__ double csm[];
@@ -397,11 +399,23 @@ k_coarse_rb(CoarseArgs A, CoarseCoef<NL> CC) {
           rr += an + as;
           rhs[f] = rr;
         }
+        if (!RCOEF) {
 #pragma unroll
-        for (int f = 1; f < NL; f++) rhs[f] -= div_by(C.t0[f] * rhs[f - 1], C.t1p[f - 1], C.rinv[f - 1]);
-        out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
+          for (int f = 1; f < NL; f++) rhs[f] -= div_by(C.t0[f] * rhs[f - 1], C.t1p[f - 1], C.rinv[f - 1]);
+          out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
 #pragma unroll
-        for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - C.t2[f] * out[f + 1], C.t1p[f], C.rinv[f]);
+          for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - C.t2[f] * out[f + 1], C.t1p[f], C.rinv[f]);
+        } else { /* horizontally varying stretching / lambda: the coefficients of this row or cell (same tables as k_relax_rb) */
+          const double *ct = A.coef[l] + (A.coef_cell ? (size_t)y * n + x : (size_t)y) * 6 * NL;
+          double t0[NL], t2[NL], t1p[NL], rinv[NL];
+#pragma unroll
+          for (int f = 0; f < NL; f++) { t0[f] = ct[f]; t2[f] = ct[NL + f]; t1p[f] = ct[2 * NL + f]; rinv[f] = ct[3 * NL + f]; }
+#pragma unroll
+          for (int f = 1; f < NL; f++) rhs[f] -= div_by(t0[f] * rhs[f - 1], t1p[f - 1], rinv[f - 1]);
+          out[NL - 1] = div_by(rhs[NL - 1], t1p[NL - 1], rinv[NL - 1]);
+#pragma unroll
+          for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - t2[f] * out[f + 1], t1p[f], rinv[f]);
+        }
 #pragma unroll
         for (int f = 0; f < NL; f++) DA(l, f, y, x) = out[f];
       }
@@ -424,7 +438,7 @@ k_coarse_rb(CoarseArgs A, CoarseCoef<NL> CC) {
  * __syncthreads() each -- half-sweep h only touches the cells whose halo is still complete, a region that shrinks by
  * one ring per half-sweep -- and stores the block.  Same cell update, same ghost rule, same bits as k_relax_rb. */
 #define RB_TO 32
-template <int NL>
+template <int NL, bool RCOEF = false>
 __global__ void __launch_bounds__(512)
 k_relax_rb_tile(RbArgs A, RelaxCoef<NL> C) {
   extern __shared__ double tsm[];
@@ -473,11 +487,23 @@ k_relax_rb_tile(RbArgs A, RelaxCoef<NL> C) {
         rr += an + as;
         rhs[f] = rr;
       }
+      if (!RCOEF) {
 #pragma unroll
-      for (int f = 1; f < NL; f++) rhs[f] -= div_by(C.t0[f] * rhs[f - 1], C.t1p[f - 1], C.rinv[f - 1]);
-      out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
+        for (int f = 1; f < NL; f++) rhs[f] -= div_by(C.t0[f] * rhs[f - 1], C.t1p[f - 1], C.rinv[f - 1]);
+        out[NL - 1] = div_by(rhs[NL - 1], C.t1p[NL - 1], C.rinv[NL - 1]);
 #pragma unroll
-      for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - C.t2[f] * out[f + 1], C.t1p[f], C.rinv[f]);
+        for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - C.t2[f] * out[f + 1], C.t1p[f], C.rinv[f]);
+      } else { /* coefficients of this row / cell from the k_rowcoef / k_modecoef table (undecomposed levels: gx, gy are own cells) */
+        const double *ct = A.coef + (A.coef_cell ? (size_t)gy * nx + gx : (size_t)gy) * 6 * NL;
+        double t0[NL], t2[NL], t1p[NL], rinv[NL];
+#pragma unroll
+        for (int f = 0; f < NL; f++) { t0[f] = ct[f]; t2[f] = ct[NL + f]; t1p[f] = ct[2 * NL + f]; rinv[f] = ct[3 * NL + f]; }
+#pragma unroll
+        for (int f = 1; f < NL; f++) rhs[f] -= div_by(t0[f] * rhs[f - 1], t1p[f - 1], rinv[f - 1]);
+        out[NL - 1] = div_by(rhs[NL - 1], t1p[NL - 1], rinv[NL - 1]);
+#pragma unroll
+        for (int f = NL - 2; f >= 0; f--) out[f] = div_by(rhs[f] - t2[f] * out[f + 1], t1p[f], rinv[f]);
+      }
 #pragma unroll
       for (int f = 0; f < NL; f++) sda[(f * WS + y) * WS + x] = out[f];
     }

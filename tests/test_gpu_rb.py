@@ -198,3 +198,38 @@ def test_rb_against_committed_golden_fixture(gpu):
     dts = [m.step() for _ in range(3)]
     assert np.array_equal(np.array(dts), g["dts"])
     assert np.array_equal(m.get(G.PSI), g["psi"]) and np.array_equal(m.get(G.Q), g["q"])
+
+
+@pytest.mark.parametrize("tables", ["1", "0"])
+@pytest.mark.parametrize("N,nl,over,frfield", [(256, 3, dict(varRo=1), 0), (128, 4, {}, 1), (128, 3, dict(mode_pv_invert=1, varRo=1), 1),
+                                                 (64, 2, dict(mode_pv_invert=1), 1)])
+def test_coefficient_tables_in_the_small_level_kernels(gpu, N, nl, over, frfield, tables, monkeypatch):
+    """Horizontally varying stretching (varRo, Fr(x, y)) and varying vertical modes: the one-window-per-CTA kernel and the
+    single-CTA coarse kernel read the same per-row / per-cell Thomas coefficient tables as the streaming kernel
+    (MSQG_RB_COARSE_TABLES=0 sends every level through the streaming kernel, the first implementation): both give the
+    bits of the oracle, with equal cycle counts."""
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    if over.get("mode_pv_invert") and O._lapack_path() is None:
+        pytest.skip("no LAPACK dgeev (eigmode.h:153)")
+    monkeypatch.setenv("MSQG_RB_COARSE_TABLES", tables)
+    mo, mg, psi = make_pair(N, nl, smoother="rb", **over)
+    if frfield:
+        y, x = np.meshgrid((np.arange(N) + 0.5) / N, (np.arange(N) + 0.5) / N, indexing="ij")
+        fr = np.zeros_like(psi)
+        for l in range(nl - 1):
+            fr[l] = (0.003 + 0.002 * l) * (1 + 0.3 * np.sin(2 * np.pi * x) * np.cos(np.pi * y))
+        mo.set(O.FR, fr); mg.set(G.FR, fr)
+    mo.set_const(); mg.set_const()
+    z = np.zeros_like(psi)
+    mo.set(O.PSI, z); mg.set(G.PSI, z)
+    mo.invertq(); mg.invertq()                      # cold start: several cycles, nrelax adapts
+    for mode in ([-1] if not over.get("mode_pv_invert") else range(nl)):
+        so, sg = mo.mgstats(mode), mg.mgstats(mode)
+        assert (sg.i, sg.nrelax, sg.resb, sg.resa) == (so.i, so.nrelax, so.resb, so.resa), mode
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI))
+    mo.set(O.PSI, psi); mg.set(G.PSI, psi)
+    for _ in range(4):                              # enough steps for the recorded cycle graphs to be replayed
+        assert mg.step() == mo.step()
+    assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
+    assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI)) and np.array_equal(mg.get(G.Q), mo.get(O.Q))
