@@ -233,3 +233,34 @@ def test_coefficient_tables_in_the_small_level_kernels(gpu, N, nl, over, frfield
         assert mg.step() == mo.step()
     assert mg.total_cycles == mo.L.orc_total_cycles(mo.h)
     assert np.array_equal(mg.get(G.PSI), mo.get(O.PSI)) and np.array_equal(mg.get(G.Q), mo.get(O.Q))
+
+
+def test_round2_variants_against_committed_golden_fixtures(gpu):
+    """periodic domain (red-black), ENERGY_CONSERV (reference order) and per-column vertical modes against the committed
+    fixtures of the oracle (tests/golden/make_golden.py; regression fixtures)"""
+    import os
+    from common import periodic_psi
+    from oracle import oracle as O
+    from msom_b200 import capi as G
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "oracle_rb_periodic_32x3_3steps.npz"))
+    m = G.Model(G.make_params(**base_kw(32, 3, sbc=-1.)), gpu)
+    m.set(G.PSI, periodic_psi(32, 3)); m.set_const()
+    dts = [m.step() for _ in range(3)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert np.array_equal(m.get(G.PSI), g["psi"]) and np.array_equal(m.get(G.Q), g["q"])
+    g = np.load(os.path.join(gdir, "oracle_econs_32x2_3steps.npz"))
+    m = G.Model(G.make_params(**base_kw(32, 2)), gpu)
+    m.set_energy_conserv(1)
+    m.set(G.PSI, synth_psi(32, 2)); m.set_const()
+    dts = [m.step() for _ in range(3)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert np.array_equal(m.get(G.PSI), g["psi"]) and np.array_equal(m.get(G.Q), g["q"])
+    if O._lapack_path() is None:
+        pytest.skip("no LAPACK dgeev (eigmode.h:153)")
+    g = np.load(os.path.join(gdir, "oracle_32x3_modal_varRo_2steps.npz"))
+    m = G.Model(G.make_params(**base_kw(32, 3, mode_pv_invert=1, varRo=1)), gpu)
+    m.set(G.PSI, synth_psi(32, 3)); m.set_const()
+    dts = [m.step() for _ in range(2)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert rel_l2(m.get(G.PSI), g["psi"]) < 1e-11   # LAPACK builds may differ in the last bits

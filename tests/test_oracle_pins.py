@@ -175,6 +175,29 @@ def test_golden_regression():
     assert rel_l2(m.get(O.PSI), g["psi"]) < 1e-11   # LAPACK builds may differ in the last bits
 
 
+def test_golden_regression_round2_variants():
+    """periodic domain (red-black), ENERGY_CONSERV, per-column vertical modes: the oracle reproduces the fixtures
+    tests/golden/make_golden.py wrote for them (regression only, like every fixture here)."""
+    from common import periodic_psi
+    g = np.load(os.path.join(HERE, "golden", "oracle_rb_periodic_32x3_3steps.npz"))
+    m = O.Model(O.make_params(**base_kw(32, 3, sbc=-1.))); m.set_smoother("rb")
+    m.set(O.PSI, periodic_psi(32, 3)); m.set_const()
+    dts = [m.step() for _ in range(3)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert np.array_equal(m.get(O.PSI), g["psi"]) and np.array_equal(m.get(O.Q), g["q"])
+    g = np.load(os.path.join(HERE, "golden", "oracle_econs_32x2_3steps.npz"))
+    m = _model(32, 2); m.set_energy_conserv(1)
+    dts = [m.step() for _ in range(3)]
+    assert np.array_equal(np.array(dts), g["dts"])
+    assert np.array_equal(m.get(O.PSI), g["psi"]) and np.array_equal(m.get(O.Q), g["q"])
+    if O._lapack_path() is None:
+        pytest.skip("no LAPACK for eigmod")
+    g = np.load(os.path.join(HERE, "golden", "oracle_32x3_modal_varRo_2steps.npz"))
+    m = _model(32, 3, mode_pv_invert=1, varRo=1)
+    dts = [m.step() for _ in range(2)]
+    assert rel_l2(m.get(O.PSI), g["psi"]) < 1e-11   # LAPACK builds may differ in the last bits
+
+
 def test_energy_budget_identities():
     """qg_energy.h: with the weight -psi (ediag = 0) the advective terms integrate to zero -- the Arakawa
     Jacobian conserves energy and the stretching Jacobians of neighbouring layers cancel in the
