@@ -243,6 +243,21 @@ int msqg_test_relax_profile(msqg_model *m, int level, int nsweeps, long long *ou
 /* one mg_cycle + residual at the model's shape, timed with CUDA events (ms) */
 int msqg_time_vcycle(msqg_model *m, int nrelax, int reps, double *ms_out);
 
+/* ---- (1c) ensembles of independent members on one device (BASELINE config 5; replicas only) ----
+ * The reference runs one member per process (its own libc rand() stream, qg_stochastic.h:9,117-126).  Here the members
+ * of a GPU are handles of one process, each with its own stream and noise stream; msqg_ensemble_step advances all of
+ * them concurrently (one persistent host thread per member inside the library), member by member the bits of the
+ * member run alone.  Fields go in and out through the member handles (msqg_set_field / msqg_get_field). */
+typedef struct msqg_ensemble msqg_ensemble;
+int msqg_ensemble_create(const msqg_params *p, int device, int nmembers, const unsigned *seeds /* NULL: 1000 + k */,
+                         int noise_mode, int smoother, msqg_ensemble **out);
+void msqg_ensemble_destroy(msqg_ensemble *e);
+int msqg_ensemble_size(msqg_ensemble *e);
+msqg_model *msqg_ensemble_member(msqg_ensemble *e, int k);
+int msqg_ensemble_set_const(msqg_ensemble *e);                       /* set_const of every member */
+int msqg_ensemble_step(msqg_ensemble *e, int nsteps, double *dt_last /* [nmembers] or NULL */);
+double msqg_ensemble_time(msqg_ensemble *e, int k);
+
 /* ---- (1b) 2-D domain decomposition: one tile per GPU, halo exchange == boundary() -------------
  * The semantics of the reference built with -D_MPI=1 (msqg/qg.c:12-19): px x py tiles on every
  * multigrid level whose global size is >= agg_n (coarser levels are agglomerated on tile (0,0)),

@@ -94,6 +94,16 @@ def lib():
     L.msqg_set_smoother.argtypes = [vp, C.c_int]
     L.msqg_get_smoother.argtypes = [vp]
     L.msqg_set_energy_conserv.argtypes = [vp, C.c_int]
+    L.msqg_ensemble_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(C.c_uint), C.c_int, C.c_int, C.POINTER(vp)]
+    L.msqg_ensemble_destroy.argtypes = [vp]
+    L.msqg_ensemble_destroy.restype = None
+    L.msqg_ensemble_size.argtypes = [vp]
+    L.msqg_ensemble_member.argtypes = [vp, C.c_int]
+    L.msqg_ensemble_member.restype = vp
+    L.msqg_ensemble_set_const.argtypes = [vp]
+    L.msqg_ensemble_step.argtypes = [vp, C.c_int, pd]
+    L.msqg_ensemble_time.argtypes = [vp, C.c_int]
+    L.msqg_ensemble_time.restype = C.c_double
     L.msqg_set_field_async.argtypes = [vp, C.c_int, dp]
     L.msqg_set_field_commit.argtypes = [vp]
     L.msqg_get_field_async.argtypes = [vp, C.c_int, dp]
@@ -166,19 +176,25 @@ def read_params(path, stochastic=0, mode_pv_invert=0):
 class Model:
     """One msqg model resident on one GPU (msqg_create .. msqg_destroy)."""
 
-    def __init__(self, params, device=0):
+    def __init__(self, params, device=0, handle=None):
+        """handle: wrap a model that something else owns (a member of msqg_ensemble_create) instead of creating one"""
         self.L = lib()
         self.p = params
         self.N, self.nl = params.N, params.nl
-        h = C.c_void_p()
-        check(self.L.msqg_create(C.byref(params), device, C.byref(h)))
+        self.owned = handle is None
+        if handle is None:
+            h = C.c_void_p()
+            check(self.L.msqg_create(C.byref(params), device, C.byref(h)))
+        else:
+            h = C.c_void_p(handle)
         self.h = h
         self.t = 0.0
         self.i = 0
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.msqg_destroy(self.h)
+            if self.owned:
+                self.L.msqg_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -25,6 +25,10 @@
 #include <utility>
 #include <map>
 #include <tuple>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <string>
 
 static thread_local char g_err[512] = "";
 extern "C" const char *msqg_last_error(void) { return g_err; }
@@ -2722,5 +2726,112 @@ extern "C" int msqg_profile_read(msqg_model *m, double *ms, long *count, long *a
   m->prof_recs.clear(); m->prof_next = 0;
   return MSQG_OK;
 }
+
+/* ------------------------------------------------------------------ ensembles (BASELINE config 5): native driver
+ * Members are independent models on one device (replicas only): own handle, own stream, own noise
+ * stream.  One persistent host thread per member issues that member's steps, so the launches and the convergence
+ * read-backs of the members interleave on the device; the red-black kernels need no cooperative launch, members
+ * overlap freely.  Results are, member by member, the bits of the member run alone. */
+struct msqg_ensemble {
+  std::vector<msqg_model *> members;
+  std::vector<double> t;            /* model time of every member */
+  std::vector<double> dt_last;
+  std::vector<int> rc;
+  std::vector<std::string> err;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  unsigned long gen = 0;            /* command generation */
+  int cmd = 0, arg = 0, done = 0;   /* cmd: 1 step x arg, 2 set_const, 3 quit */
+};
+static void ensemble_worker(msqg_ensemble *E, int k) {
+  unsigned long seen = 0;
+  for (;;) {
+    int cmd, arg;
+    {
+      std::unique_lock<std::mutex> lk(E->mu);
+      E->cv_go.wait(lk, [&] { return E->gen != seen; });
+      seen = E->gen; cmd = E->cmd; arg = E->arg;
+    }
+    if (cmd == 3) return;
+    int rc = MSQG_OK;
+    msqg_model *m = E->members[k];
+    if (cmd == 2) rc = msqg_set_const(m);
+    else
+      for (int s = 0; s < arg && rc == MSQG_OK; s++) {
+        double dt = 0., tn = 0.;
+        rc = msqg_step(m, E->t[k], -1., &dt, &tn);
+        if (rc == MSQG_OK) { E->t[k] = tn; E->dt_last[k] = dt; }
+      }
+    E->rc[k] = rc;
+    if (rc) E->err[k] = msqg_last_error(); /* the message lives in this thread */
+    {
+      std::lock_guard<std::mutex> lk(E->mu);
+      E->done++;
+    }
+    E->cv_done.notify_one();
+  }
+}
+static int ensemble_run(msqg_ensemble *E, int cmd, int arg) {
+  const int n = (int)E->members.size();
+  {
+    std::lock_guard<std::mutex> lk(E->mu);
+    E->cmd = cmd; E->arg = arg; E->done = 0; E->gen++;
+  }
+  E->cv_go.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(E->mu);
+    E->cv_done.wait(lk, [&] { return E->done == n; });
+  }
+  for (int k = 0; k < n; k++)
+    if (E->rc[k]) FAIL(E->rc[k], "member %d: %s", k, E->err[k].c_str());
+  return MSQG_OK;
+}
+extern "C" void msqg_ensemble_destroy(msqg_ensemble *E) {
+  if (!E) return;
+  if (!E->workers.empty()) {
+    {
+      std::lock_guard<std::mutex> lk(E->mu);
+      E->cmd = 3; E->gen++;
+    }
+    E->cv_go.notify_all();
+    for (std::thread &w : E->workers) w.join();
+  }
+  for (msqg_model *m : E->members) msqg_destroy(m);
+  delete E;
+}
+/* nmembers models of *p on `device`; seeds[k] (NULL: 1000 + k) seeds member k's noise stream (msqg_seed_noise),
+   noise_mode as msqg_set_noise_mode, smoother as msqg_set_smoother */
+extern "C" int msqg_ensemble_create(const msqg_params *p, int device, int nmembers, const unsigned *seeds, int noise_mode, int smoother,
+                                    msqg_ensemble **out) {
+  *out = nullptr;
+  if (nmembers < 1 || nmembers > 1024) FAIL(MSQG_ERR_ARG, "an ensemble holds 1..1024 members per device");
+  msqg_ensemble *E = new msqg_ensemble();
+  for (int k = 0; k < nmembers; k++) {
+    msqg_model *m = nullptr;
+    int rc = msqg_create(p, device, &m);
+    if (!rc) { msqg_seed_noise(m, seeds ? seeds[k] : 1000u + k); rc = p->stochastic ? msqg_set_noise_mode(m, noise_mode) : MSQG_OK; }
+    if (!rc) rc = msqg_set_smoother(m, smoother);
+    if (rc) { if (m) msqg_destroy(m); msqg_ensemble_destroy(E); return rc; }
+    E->members.push_back(m);
+  }
+  E->t.assign(nmembers, 0.); E->dt_last.assign(nmembers, 0.); E->rc.assign(nmembers, 0); E->err.assign(nmembers, std::string());
+  for (int k = 0; k < nmembers; k++) E->workers.emplace_back(ensemble_worker, E, k);
+  *out = E;
+  return MSQG_OK;
+}
+extern "C" int msqg_ensemble_size(msqg_ensemble *E) { return (int)E->members.size(); }
+extern "C" msqg_model *msqg_ensemble_member(msqg_ensemble *E, int k) {
+  return (k >= 0 && k < (int)E->members.size()) ? E->members[k] : nullptr;
+}
+extern "C" int msqg_ensemble_set_const(msqg_ensemble *E) { return ensemble_run(E, 2, 0); }
+/* nsteps predictor-corrector steps of every member, members concurrently; dt_last[k] (may be NULL) = last dt of member k */
+extern "C" int msqg_ensemble_step(msqg_ensemble *E, int nsteps, double *dt_last) {
+  if (nsteps < 0) FAIL(MSQG_ERR_ARG, "nsteps < 0");
+  int rc = ensemble_run(E, 1, nsteps);
+  if (dt_last) for (size_t k = 0; k < E->members.size(); k++) dt_last[k] = E->dt_last[k];
+  return rc;
+}
+extern "C" double msqg_ensemble_time(msqg_ensemble *E, int k) { return E->t[k]; }
 
 #include "dist_impl.cuh"
