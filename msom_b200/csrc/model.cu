@@ -29,8 +29,10 @@
 #include <mutex>
 #include <condition_variable>
 #include <string>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
+static std::mutex g_kernel_init_mu; /* one-time per-device kernel setup (function attributes, occupancy queries) */
 extern "C" const char *msqg_last_error(void) { return g_err; }
 #define FAIL(code, ...)                        \
   do {                                         \
@@ -1054,11 +1056,13 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
 #endif
   /* per device (handles may live on several GPUs of one process): opt-in shared memory and co-resident CTAs per SM
      (cluster variants: co-resident CTAs on the device) */
-  static bool attr_set_d[64][4] = {};
+  static std::atomic<bool> attr_set_d[64][4];
   static int max_blocks_d[64][4] = {};
-  bool *attr_set = attr_set_d[m->device & 63];
+  std::atomic<bool> *attr_set = attr_set_d[m->device & 63];
   int *max_blocks = max_blocks_d[m->device & 63];
-  if (!attr_set[tv]) {
+  std::unique_lock<std::mutex> init_lk(g_kernel_init_mu, std::defer_lock);
+  if (!attr_set[tv].load(std::memory_order_acquire)) init_lk.lock(); /* first launches of several host threads: one sets up */
+  if (!attr_set[tv].load(std::memory_order_relaxed)) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (cs == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks[tv], kern, 64 * WPC, smem));
     else {
@@ -1072,12 +1076,14 @@ static int launch_relax_ws_w(msqg_model *m, double *da, const double *res, int l
       if (cudaOccupancyMaxActiveClusters(&ncl, (void *)kern, &cfg) != cudaSuccess || ncl < 1) {
         cudaGetLastError();
         m->relax_cs_ok = false; /* no clusters on this device / configuration: global mailbox everywhere */
+        if (init_lk.owns_lock()) init_lk.unlock();
         return launch_relax_ws_w<NL, K, WPC, RCOEF>(m, da, res, lev, nsweeps, C);
       }
       max_blocks[tv] = ncl * cs;
     }
-    attr_set[tv] = true;
+    attr_set[tv].store(true, std::memory_order_release);
   }
+  if (init_lk.owns_lock()) init_lk.unlock();
   const int grid = (nworkers + WPC - 1) / WPC;
   int cap = cs == 1 ? max_blocks[tv] * m->num_sms : max_blocks[tv]; /* co-resident CTAs (strips spin on their left neighbour) */
   { const char *e = getenv("MSQG_RELAX_CAP"); if (e && atoi(e) > 0 && atoi(e) < cap) cap = atoi(e); } /* tests: force panels */
@@ -1173,7 +1179,9 @@ static int launch_relax(msqg_model *m, double *da, const double *res, int lev, i
 
 /* ------------------------------------------------------------------ red-black relax launch (rb_kernels.cuh) */
 /* per-device launch state of one kernel instance: opt-in shared memory and co-resident CTAs per SM */
-struct KernelDevState { bool set[64] = {}; int occ[64][RB_NSMAX + 1] = {}; };
+/* (handles of several host threads -- ensemble members -- may reach a kernel's first launch together: the one-time
+   setup is double-checked under g_kernel_init_mu, the flag is published with release / read with acquire) */
+struct KernelDevState { std::atomic<bool> set[64]; int occ[64][RB_NSMAX + 1]; }; /* only ever `static`: zero-initialised */
 template <int NL, bool RCOEF, int WXT>
 static int launch_relax_rb_pass_w(msqg_model *m, double *da, const double *res, int lev, int ns, const RelaxCoef<NL> &C,
                                 const int *orange /* optional {ox_lo, ox_hi, oy_lo, oy_hi} */, int halo) {
@@ -1213,9 +1221,12 @@ static int launch_relax_rb_pass_w(msqg_model *m, double *da, const double *res, 
       auto tk = k_relax_rb_tile<NL, RCOEF>;
       static KernelDevState tst;
       const int dev = m->device & 63;
-      if (!tst.set[dev]) {
-        CK(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-        tst.set[dev] = true;
+      if (!tst.set[dev].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(g_kernel_init_mu);
+        if (!tst.set[dev].load(std::memory_order_relaxed)) {
+          CK(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+          tst.set[dev].store(true, std::memory_order_release);
+        }
       }
       RelaxCoef<NL> Cc = C;
       tk<<<dim3((nxo_ + RB_TO - 1) / RB_TO, (nyo_ + RB_TO - 1) / RB_TO), 512, tsmem, m->stream>>>(A, Cc);
@@ -1231,13 +1242,16 @@ static int launch_relax_rb_pass_w(msqg_model *m, double *da, const double *res, 
   auto kern = k_relax_rb<NL, RCOEF, WXT>;
   static KernelDevState st;
   const int dev = m->device & 63;
-  if (!st.set[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)((size_t)(4 * Cfg::NSMAX + 1 + RB_PF) * Cfg::row_bytes)));
-    for (int s = 1; s <= Cfg::NSMAX; s++)
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occ[dev][s], kern, Cfg::NSMAX * WXT,
-                                                       (size_t)(4 * s + 1 + RB_PF) * Cfg::row_bytes));
-    st.set[dev] = true;
+  if (!st.set[dev].load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(g_kernel_init_mu);
+    if (!st.set[dev].load(std::memory_order_relaxed)) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((size_t)(4 * Cfg::NSMAX + 1 + RB_PF) * Cfg::row_bytes)));
+      for (int s = 1; s <= Cfg::NSMAX; s++)
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occ[dev][s], kern, Cfg::NSMAX * WXT,
+                                                         (size_t)(4 * s + 1 + RB_PF) * Cfg::row_bytes));
+      st.set[dev].store(true, std::memory_order_release);
+    }
   }
   const int occ = st.occ[dev][ns] > 0 ? st.occ[dev][ns] : 1;
   const int nxo = A.ox_hi - A.ox_lo, nyo = A.oy_hi - A.oy_lo;
@@ -1337,9 +1351,12 @@ static int launch_coarse_rb(msqg_model *m, int Lc, int nrelax, const CoarseCoef<
   auto kern = k_coarse_rb<NL, RCOEF>;
   static KernelDevState st;
   const int dev = m->device & 63;
-  if (!st.set[dev]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    st.set[dev] = true;
+  if (!st.set[dev].load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(g_kernel_init_mu);
+    if (!st.set[dev].load(std::memory_order_relaxed)) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      st.set[dev].store(true, std::memory_order_release);
+    }
   }
   CoarseCoef<NL> Cc = CC;
   kern<<<1, 512, smem, m->stream>>>(A, Cc);
