@@ -5,10 +5,13 @@
 # it is "parity unpinned" until this script has run once somewhere with a Basilisk tree.  Nothing here is needed by the
 # product or by the tests: it only makes the first real-reference comparison a one-liner.
 #
-#   scripts/build_ref.sh [BASILISK_SRC] [REFERENCE_MSQG_DIR] [NSTEPS]
+#   scripts/build_ref.sh [BASILISK_SRC] [REFERENCE_MSQG_DIR] [NSTEPS] [VARIANT]
 #     BASILISK_SRC        Basilisk src/ directory holding qcc (default: $BASILISK, else baseline/_ref/basilisk/src)
 #     REFERENCE_MSQG_DIR  msqg/ of the reference            (default: /root/reference/msqg, else baseline/_ref/msom/msqg)
 #     NSTEPS              steps to compare                  (default 10)
+#     VARIANT             default | econs (qcc -DENERGY_CONSERV=1 against MSQG_ENERGY_CONSERV=1)
+#                         | periodic (sbc = -1 in params.in; ours runs the red-black ordering, the only one built for the
+#                           periodic domain, so the fields agree to the solver tolerance, not bit for bit)
 # Without a Basilisk tree it prints "reference absent" and exits 0.
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
@@ -16,6 +19,12 @@ BAS="${1:-${BASILISK:-$ROOT/baseline/_ref/basilisk/src}}"
 REF="${2:-/root/reference/msqg}"
 [ -d "$REF" ] || REF="$ROOT/baseline/_ref/msom/msqg"
 NSTEPS="${3:-10}"
+VARIANT="${4:-default}"
+QCCFLAGS=""; OURS_ENV="MSQG_SMOOTHER=lex"; TOL="1e-6"
+case "$VARIANT" in
+  econs)    QCCFLAGS="-DENERGY_CONSERV=1"; OURS_ENV="MSQG_SMOOTHER=lex MSQG_ENERGY_CONSERV=1" ;;
+  periodic) OURS_ENV="MSQG_SMOOTHER=rb"; TOL="1e-3" ;;
+esac
 QCC="$BAS/qcc"
 if [ ! -x "$QCC" ] || [ ! -f "$REF/qg.c" ]; then
   echo "reference absent: no qcc at $QCC or no qg.c at $REF -- nothing built, nothing compared (parity stays unpinned)"
@@ -25,33 +34,35 @@ OUT="$ROOT/oracle/_ref"
 mkdir -p "$OUT/run_ref" "$OUT/run_ours"
 export BASILISK="$BAS"
 # 1. the reference, serial, default compile-time switches (MODE_PV_INVERT 0, _LS_RV 1): msqg/qg.c:7-10
-( cd "$REF" && "$QCC" -O3 -Wall -I"$REF" qg.c -o "$OUT/qg_ref.e" -lm ) || { echo "qcc failed"; exit 1; }
+( cd "$REF" && "$QCC" -O3 -Wall $QCCFLAGS -I"$REF" qg.c -o "$OUT/qg_ref.e" -lm ) || { echo "qcc failed"; exit 1; }
 # 2. the shipped configuration (msqg/test/params.double_gyre.in), NSTEPS steps with output at the end:
 #    dtout such that exactly one output event fires after NSTEPS steps of DT (the dt ramp makes the count approximate;
 #    both sides use the same file, so they stop at the same t)
-python3 - "$REF/test/params.double_gyre.in" "$OUT/params.in" "$NSTEPS" <<'PY'
+python3 - "$REF/test/params.double_gyre.in" "$OUT/params.in" "$NSTEPS" "$VARIANT" <<'PY'
 import re, sys
-src, dst, n = sys.argv[1], sys.argv[2], int(sys.argv[3])
+src, dst, n, variant = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
 txt = open(src).read()
 DT = float(re.search(r"^DT\s*=\s*([0-9.eE+-]+)", txt, re.M).group(1))
 tend = n * DT
 txt = re.sub(r"^tend\s*=.*$", "tend = %g" % tend, txt, flags=re.M)
 txt = re.sub(r"^dtout\s*=.*$", "dtout = %g" % tend, txt, flags=re.M)
+if variant == "periodic":   # qg.h:711: sbc = -1 -> periodic(right); periodic(top)
+    txt = re.sub(r"^sbc\s*=.*$", "", txt, flags=re.M) + "\nsbc = -1\n"
 open(dst, "w").write(txt)
 PY
 # identical initial condition on both sides: p0.bas written by OUR writer from the deterministic synthetic field
-( cd "$ROOT" && python3 - "$OUT" <<'PY'
+( cd "$ROOT" && python3 - "$OUT" "$VARIANT" <<'PY'
 import os, sys
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import re
 import numpy as np
-from common import synth_psi
+from common import periodic_psi, synth_psi
 from oracle import oracle as O
-out = sys.argv[1]
+out, variant = sys.argv[1], sys.argv[2]
 txt = open(os.path.join(out, "params.in")).read()
 N = int(re.search(r"^N\s*=\s*(\d+)", txt, re.M).group(1)); nl = int(re.search(r"^nl\s*=\s*(\d+)", txt, re.M).group(1))
 L0 = float(re.search(r"^L0\s*=\s*([0-9.eE+-]+)", txt, re.M).group(1))
-psi = synth_psi(N, nl, L0)
+psi = periodic_psi(N, nl, L0) if variant == "periodic" else synth_psi(N, nl, L0)
 for d in ("run_ref", "run_ours"):
     O.lib().orc_write_bas(os.path.join(out, d, "p0.bas").encode(), nl, N, L0, np.ascontiguousarray(psi))
 PY
@@ -59,14 +70,14 @@ PY
 cp "$OUT/params.in" "$OUT/run_ref/params.in"; cp "$OUT/params.in" "$OUT/run_ours/params.in"
 ( cd "$OUT/run_ref" && "$OUT/qg_ref.e" params.in > stdout.txt ) || { echo "reference run failed"; exit 1; }
 # 3. ours: qg.e (needs a GPU) with the reference-order smoother, same directory layout
-if ! ( cd "$OUT/run_ours" && MSQG_SMOOTHER=lex "$ROOT/msom_b200/lib/qg.e" params.in > stdout.txt ); then
+if ! ( cd "$OUT/run_ours" && env $OURS_ENV "$ROOT/msom_b200/lib/qg.e" params.in > stdout.txt ); then
   echo "qg.e failed (no GPU here?) -- reference outputs are in $OUT/run_ref for a later comparison"; exit 1
 fi
 # 4. diff: stdout (i, dt, t, ke_1 per step) and every po*/qo* file, as float32 arrays
-python3 - "$OUT/run_ref" "$OUT/run_ours" <<'PY'
+python3 - "$OUT/run_ref" "$OUT/run_ours" "$TOL" <<'PY'
 import glob, os, sys
 import numpy as np
-ref, ours = sys.argv[1], sys.argv[2]
+ref, ours, tol = sys.argv[1], sys.argv[2], float(sys.argv[3])
 rd = sorted(glob.glob(os.path.join(ref, "outdir_*")))[-1]; od = sorted(glob.glob(os.path.join(ours, "outdir_*")))[-1]
 ok = True
 for f in sorted(glob.glob(os.path.join(rd, "[pq]o*.bas"))):
@@ -76,7 +87,7 @@ for f in sorted(glob.glob(os.path.join(rd, "[pq]o*.bas"))):
         print("MISSING/SHAPE", os.path.basename(f)); ok = False; continue
     rel = np.linalg.norm(a - b) / max(np.linalg.norm(a), 1e-300)
     print("%-24s identical=%s rel_l2=%.3e" % (os.path.basename(f), np.array_equal(a, b), rel))
-    ok &= rel <= 1e-6   # float32 files: 1e-12 in double is below the file precision; bitwise equality is the real target
+    ok &= rel <= tol    # float32 files: 1e-12 in double is below the file precision; bitwise equality is the real target
 a = [l for l in open(os.path.join(ref, "stdout.txt")) if l.startswith("i = ")]
 b = [l for l in open(os.path.join(ours, "stdout.txt")) if l.startswith("i = ")]
 print("stdout step lines: ref %d ours %d identical=%s" % (len(a), len(b), a == b))
