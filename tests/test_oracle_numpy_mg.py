@@ -20,11 +20,11 @@ def restrict(f):
     return 0.25 * (f[:, 0::2, 0::2] + f[:, 1::2, 0::2] + f[:, 0::2, 1::2] + f[:, 1::2, 1::2])
 
 
-def prolong(c):
+def prolong(c, bc=-1):
     nl, nc = c.shape[0], c.shape[1]
     out = np.zeros((nl, 2 * nc, 2 * nc))
     for l in range(nl):
-        C = pad(c[l], -1)
+        C = pad(c[l], bc)
         for py in (0, 1):
             for px in (0, 1):
                 cx, cy = (1 if px else -1), (1 if py else -1)
@@ -32,13 +32,14 @@ def prolong(c):
     return out
 
 
-def residual(a, b, s, idh0, idh1, D):
-    A = [pad(a[l], -1) for l in range(a.shape[0])]
+def residual(a, b, s, idh0, idh1, D, bc=-1):
+    A = [pad(a[l], bc) for l in range(a.shape[0])]
     r = b - np.array([lap(A[l], D) for l in range(a.shape[0])]) - stretch(a, list(s), idh0, idh1)
     return r, float(np.abs(r).max())
 
 
-def numpy_solve(a, b, s_fine, dh, L0, tol=1e-3):
+def numpy_solve(a, b, s_fine, dh, L0, tol=1e-3, bc=-1):
+    """bc = -1: closed basin (dirichlet(0)); bc = 0: doubly periodic (sbc = -1, qg.h:842-846)"""
     nl, N = a.shape[0], a.shape[1]
     depth = int(np.log2(N))
     dhc = 0.5 * (dh[:-1] + dh[1:])
@@ -49,7 +50,7 @@ def numpy_solve(a, b, s_fine, dh, L0, tol=1e-3):
         s_lev[l] = restrict(s_lev[l + 1])
     a = a.copy()
     hist = []
-    res, resb = residual(a, b, s_fine, idh0, idh1, L0 / N)
+    res, resb = residual(a, b, s_fine, idh0, idh1, L0 / N, bc)
     stats = dict(resb=resb, resa=resb, nrelax=4, i=0)
     while stats["i"] < 100 and (stats["i"] < 1 or stats["resa"] > tol):
         # mg_cycle with minlevel = 1
@@ -59,11 +60,11 @@ def numpy_solve(a, b, s_fine, dh, L0, tol=1e-3):
         da = None
         for l in range(1, depth + 1):
             n = 1 << l
-            da = np.zeros((nl, n, n)) if l == 1 else prolong(da)
-            da = _numpy_rb_sweeps(nl, n, L0, list(dh), s_lev[l], da, r_lev[l], stats["nrelax"])
+            da = np.zeros((nl, n, n)) if l == 1 else prolong(da, bc)
+            da = _numpy_rb_sweeps(nl, n, L0, list(dh), s_lev[l], da, r_lev[l], stats["nrelax"], periodic=(bc == 0))
         a = a + da
         hist.append(stats["nrelax"])
-        res, resa = residual(a, b, s_fine, idh0, idh1, L0 / N)
+        res, resa = residual(a, b, s_fine, idh0, idh1, L0 / N, bc)
         stats["resa"] = resa
         if resa > tol:
             if resb / resa < 1.2 and stats["nrelax"] < 100:
@@ -93,3 +94,32 @@ def test_inversion_against_numpy_multigrid(N, nl, varRo):
         got = m.get(O.PSI)
         assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
     assert so.i >= 1
+
+
+@pytest.mark.parametrize("N,nl", [(32, 2), (64, 3)])
+def test_periodic_inversion_against_numpy_multigrid(N, nl):
+    """sbc = -1: the same solve with wrap-around ghost rings on every level (np.pad(..., mode="wrap") in the numpy
+    version, boundary_level() in the oracle) -- relaxation across the seam, prolongation from the wrapped coarse ring,
+    residual; down to the 2 x 2 level, where east and west neighbour are the same cell."""
+    from common import periodic_psi
+    kw = base_kw(N, nl, sbc=-1.)
+    m = O.Model(O.make_params(**kw)); m.set_smoother("rb")
+    psi0 = periodic_psi(N, nl)
+    m.set(O.PSI, psi0); m.set_const()
+    q = m.get(O.Q)
+    D = kw["L0"] / N
+    dh = np.array(kw["dh"], dtype=float)
+    dhc = 0.5 * (dh[:-1] + dh[1:])
+    idh0 = np.zeros(nl); idh1 = np.zeros(nl)
+    idh1[:-1] = 1. / (dhc * dh[:-1]); idh0[1:] = 1. / (dhc * dh[1:])
+    strl = m.get(O.STR)[:nl - 1]
+    qn = np.array([lap(pad(psi0[l], 0), D) for l in range(nl)]) + stretch(psi0, list(strl), idh0, idh1)   # comp_q, periodic
+    assert np.abs(qn - q).max() <= 1e-12 * np.abs(q).max()
+    for start in (np.zeros_like(psi0), psi0 * (1 + 1e-3)):
+        m.set(O.PSI, start); m.invertq()
+        so = m.mgstats()
+        ref, st, hist = numpy_solve(start, q, strl, dh, kw["L0"], bc=0)
+        assert (so.i, so.nrelax) == (st["i"], st["nrelax"]), (so.i, so.nrelax, st, hist)
+        assert so.resa == pytest.approx(st["resa"], rel=1e-8)
+        got = m.get(O.PSI)
+        assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()

@@ -15,7 +15,10 @@ from oracle import oracle as O
 
 def pad(a, sign):
     """one ghost ring: ghost = sign * interior on the four sides ([BASILISK] dirichlet(0): -1, default: +1), the y sides
-    applied over the x ghosts, so a corner holds sign*sign*interior"""
+    applied over the x ghosts, so a corner holds sign*sign*interior; sign = 0: periodic(right), periodic(top) -- the ring
+    holds the opposite side, corners the diagonally opposite cell"""
+    if sign == 0:
+        return np.pad(a, 1, mode="wrap")
     p = np.zeros((a.shape[0] + 2, a.shape[1] + 2))
     p[1:-1, 1:-1] = a
     p[1:-1, 0] = sign * a[:, 0]; p[1:-1, -1] = sign * a[:, -1]
@@ -59,20 +62,10 @@ def stretch(f, s, idh0, idh1):
     return out
 
 
-@pytest.mark.parametrize("N,nl,over", [(32, 3, dict(Re=200., Eks=0.001, flsrv=1, upg=[0.3, 0.1, 0.], vpg=[0.05, 0., -0.02])),
-                                        (64, 2, {}), (32, 4, dict(Re=50.))])
-def test_rhs_against_numpy_restatement(N, nl, over):
-    kw = base_kw(N, nl, **over)
-    m = O.Model(O.make_params(**kw))
-    rng = np.random.default_rng(8)
-    m.set(O.PSI, synth_psi(N, nl))
-    qf = 1e-3 * rng.standard_normal((nl, N, N))
-    topo = 0.1 * rng.standard_normal((1, N, N))
-    m.set(O.QFORC, qf); m.set(O.TOPO, topo); m.L.orc_set_flag_topo(m.h, 1)
-    m.set_const()
-    dt_oracle = m.update(kw["DT"])
-    psi, dq = m.get(O.PSI), m.get(O.DQ)          # psi is what invertq left: the stream function the RHS was built from
-
+def numpy_tendency(kw, psi, q_ev, qf, topo, iRe, iRe4, econs=False):
+    """one evaluation of the tendencies of update_qg from the stream function psi (what invertq left) and, for the
+    -DENERGY_CONSERV=1 build, the evolving PV q_ev; returns (dq, zeta, padded psi lists)"""
+    nl, N = psi.shape[0], psi.shape[1]
     L0, Rom, beta = kw["L0"], kw["Rom"], kw["beta"]
     D = L0 / N
     dh = np.array(kw["dh"], dtype=float)
@@ -90,20 +83,22 @@ def test_rhs_against_numpy_restatement(N, nl, over):
     Z = [pad(zeta[l], -1) for l in range(nl)]
     zpg = np.array([lap(PP[l], D) for l in range(nl)]) if kw.get("flsrv", 0) == 1 else np.zeros_like(psi)
     ZP = [pad(zpg[l], -1) for l in range(nl)]
-    assert np.abs(zeta - m.get(O.ZETA)).max() <= 1e-12 * np.abs(zeta).max()
-
-    # advection_pv, default build (_LS_RV = 1, no ENERGY_CONSERV)
+    QE = [pad(q_ev[l], -1) for l in range(nl)]
+    # advection_pv (_LS_RV = 1); the -DENERGY_CONSERV=1 build (qg.h:310-312, :338-340, :366-367) advects the full PV and
+    # keeps only the large-scale parts of the stretching Jacobians
     out = np.zeros_like(psi)
-    jd = [jac(P[l], P[l + 1], D) + jac(PP[l], P[l + 1], D) + jac(P[l], PP[l + 1], D) for l in range(nl - 1)]
+    if econs:
+        jd = [jac(PP[l], P[l + 1], D) + jac(P[l], PP[l + 1], D) for l in range(nl - 1)]
+    else:
+        jd = [jac(P[l], P[l + 1], D) + jac(PP[l], P[l + 1], D) + jac(P[l], PP[l + 1], D) for l in range(nl - 1)]
     for l in range(nl):
-        t = jac(P[l], Z[l], D) + jac(PP[l], Z[l], D) + beta * (sh(P[l], -1, 0) - sh(P[l], 1, 0)) / (2 * D)
+        t = jac(P[l], QE[l] if econs else Z[l], D) + jac(PP[l], Z[l], D) + beta * (sh(P[l], -1, 0) - sh(P[l], 1, 0)) / (2 * D)
         if l > 0:
             t = t + s[l - 1] * (-jd[l - 1]) * idh0[l]
         if l < nl - 1:
             t = t + s[l] * jd[l] * idh1[l]
         out[l] = t + jac(P[l], ZP[l], D)
     # dissip
-    iRe, iRe4 = m.p.iRe, m.p.iRe4
     tmp = np.array([lap(Z[l], D) for l in range(nl)])
     T = [pad(tmp[l], -1) for l in range(nl)]
     out += iRe * stretch(zeta, s, idh0, idh1) + iRe * tmp + iRe4 * stretch(tmp, s, idh0, idh1)
@@ -114,11 +109,42 @@ def test_rhs_against_numpy_restatement(N, nl, over):
     out[0] -= kw["tau0"] / (Rom * dh[0]) * np.sin(2 * np.pi * Y / L0) * np.sin(np.pi * Y / L0)
     out += qf
     out[-1] += jac(P[-1], pad(topo[0], +1), D) / (Rom * dh[-1])
-    scale = np.abs(dq).max()
-    assert scale > 0 and np.abs(out - dq).max() <= 2e-12 * scale, float(np.abs(out - dq).max() / scale)
+    return out, zeta, P, PP
 
-    # comp_vel + timestep(): dt = CFL * min Delta/|u| over the faces of psi and psi_pg of every layer, chained through the
-    # static `previous` (0 at the first call: the first dt is ramped to 0.1/1.1 of its value)
+
+@pytest.mark.parametrize("N,nl,over", [(32, 3, dict(Re=200., Eks=0.001, flsrv=1, upg=[0.3, 0.1, 0.], vpg=[0.05, 0., -0.02])),
+                                        (64, 2, {}), (32, 4, dict(Re=50.))])
+def test_rhs_against_numpy_restatement(N, nl, over):
+    kw = base_kw(N, nl, **over)
+    m = O.Model(O.make_params(**kw))
+    rng = np.random.default_rng(8)
+    m.set(O.PSI, synth_psi(N, nl))
+    qf = 1e-3 * rng.standard_normal((nl, N, N))
+    topo = 0.1 * rng.standard_normal((1, N, N))
+    m.set(O.QFORC, qf); m.set(O.TOPO, topo); m.L.orc_set_flag_topo(m.h, 1)
+    m.set_const()
+    D = kw["L0"] / N
+    for econs in (False, True):                    # the default build, then the -DENERGY_CONSERV=1 build
+        m.set_energy_conserv(econs)
+        dt_oracle = m.update(kw["DT"])
+        psi, dq = m.get(O.PSI), m.get(O.DQ)        # psi is what invertq left: the stream function the RHS was built from
+        out, zeta, P, PP = numpy_tendency(kw, psi, m.get(O.Q), qf, topo, m.p.iRe, m.p.iRe4, econs)
+        assert np.abs(zeta - m.get(O.ZETA)).max() <= 1e-12 * np.abs(zeta).max()
+        scale = np.abs(dq).max()
+        assert scale > 0 and np.abs(out - dq).max() <= 2e-12 * scale, (econs, float(np.abs(out - dq).max() / scale))
+        if not econs:
+            dq_default, dt_first = dq, dt_oracle
+    assert np.abs(dq - dq_default).max() > 0       # the two builds are different discretisations
+
+    # comp_vel + timestep() of the FIRST update: dt = CFL * min Delta/|u| over the faces of psi and psi_pg of every layer,
+    # chained through the static `previous` (0 at the first call: the first dt is ramped to 0.1/1.1 of its value)
+    m2 = O.Model(O.make_params(**kw))
+    m2.set(O.PSI, synth_psi(N, nl)); m2.set(O.QFORC, qf); m2.set(O.TOPO, topo); m2.L.orc_set_flag_topo(m2.h, 1)
+    m2.set_const()
+    assert m2.update(kw["DT"]) == dt_first
+    psi = m2.get(O.PSI)
+    _, _, P, PP = numpy_tendency(kw, psi, m2.get(O.Q), qf, topo, m2.p.iRe, m2.p.iRe4)
+
     def umax(Pl):
         n = Pl.shape[0] - 2
         ux = -0.25 * (Pl[2:n + 2, 1:n + 2] - Pl[0:n, 1:n + 2] + Pl[2:n + 2, 0:n + 1] - Pl[0:n, 0:n + 1]) / D   # faces i = 0..n
@@ -136,7 +162,7 @@ def test_rhs_against_numpy_restatement(N, nl, over):
             if dtmax > prev:
                 dtmax = (prev + 0.1 * dtmax) / 1.1
             prev = dtmax
-    assert dt_oracle == pytest.approx(dtmax, rel=1e-12)
+    assert dt_first == pytest.approx(dtmax, rel=1e-12)
 
 
 def test_multigrid_operators_against_numpy_restatement():

@@ -14,7 +14,7 @@ from common import DH, FR, base_kw, rel_l2, synth_psi
 from oracle import oracle as O
 
 
-def _numpy_rb_sweeps(nl, n, L0, dh, s, a, b, nsweeps):
+def _numpy_rb_sweeps(nl, n, L0, dh, s, a, b, nsweeps, periodic=False):
     """poisson_layer.h:80-146 per cell, all cells of one colour at once; same association order, IEEE ops only"""
     Delta = L0 / n
     dhc = [0.5 * (dh[l] + dh[l + 1]) for l in range(nl - 1)]
@@ -24,10 +24,11 @@ def _numpy_rb_sweeps(nl, n, L0, dh, s, a, b, nsweeps):
     yy, xx = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
     for _ in range(nsweeps):
         for colour in (0, 1):
-            g = np.zeros((nl, n + 2, n + 2))
+            g = np.zeros((nl, n + 2, n + 2)) if not periodic else np.pad(a, ((0, 0), (1, 1), (1, 1)), mode="wrap")
             g[:, 1:-1, 1:-1] = a
-            g[:, 0, 1:-1] = -a[:, 0, :]; g[:, -1, 1:-1] = -a[:, -1, :]       # homogeneous dirichlet ghosts
-            g[:, 1:-1, 0] = -a[:, :, 0]; g[:, 1:-1, -1] = -a[:, :, -1]
+            if not periodic:
+                g[:, 0, 1:-1] = -a[:, 0, :]; g[:, -1, 1:-1] = -a[:, -1, :]   # homogeneous dirichlet ghosts
+                g[:, 1:-1, 0] = -a[:, :, 0]; g[:, 1:-1, -1] = -a[:, :, -1]
             E, W = g[:, 1:-1, 2:], g[:, 1:-1, :-2]
             Nn, S = g[:, 2:, 1:-1], g[:, :-2, 1:-1]
             t0 = [None] * nl; t1 = [None] * nl; t2 = [None] * nl; rhs = [None] * nl
