@@ -123,3 +123,46 @@ def test_periodic_inversion_against_numpy_multigrid(N, nl):
         assert so.resa == pytest.approx(st["resa"], rel=1e-8)
         got = m.get(O.PSI)
         assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+def test_reference_order_sweep_against_python_loops():
+    """relax_layer in the REFERENCE order (msqg/poisson_layer.h:75-149: in place, [BASILISK] foreach = x outer, y inner),
+    cell by cell in plain Python with a dense solve of each column's tridiagonal system (numpy.linalg.solve instead of
+    the Thomas recurrence): the lexicographic path of the oracle -- the parity path of the CUDA library -- to round-off."""
+    nl, level, L0, nsweeps = 3, 4, 80., 2
+    n = 1 << level
+    D = L0 / n
+    rng = np.random.default_rng(33)
+    dh = np.array([0.06, 0.14, 0.8])
+    dhc = 0.5 * (dh[:-1] + dh[1:])
+    idh0 = np.zeros(nl); idh1 = np.zeros(nl)
+    idh1[:-1] = 1. / (dhc * dh[:-1]); idh0[1:] = 1. / (dhc * dh[1:])
+    s = np.abs(rng.standard_normal((nl - 1, n, n))) * 5 + 8
+    a = rng.standard_normal((nl, n, n)); b = rng.standard_normal((nl, n, n))
+    got = a.copy()
+    O.lib().orc_test_relax(nl, level, L0, dh, np.ascontiguousarray(s), got, b, nsweeps, 1, 1)
+    g = np.zeros((nl, n + 2, n + 2))                 # [l][y][x] with one ghost ring
+    g[:, 1:-1, 1:-1] = a
+
+    def ghosts():
+        g[:, 1:-1, 0] = -g[:, 1:-1, 1]; g[:, 1:-1, -1] = -g[:, 1:-1, -2]
+        g[:, 0, :] = -g[:, 1, :]; g[:, -1, :] = -g[:, -2, :]
+
+    ghosts()
+    for _ in range(nsweeps):
+        for i in range(n):                           # x outer
+            for j in range(n):                       # y inner
+                A = np.zeros((nl, nl)); r = np.zeros(nl)
+                for l in range(nl):
+                    lo = s[l - 1, j, i] * idh0[l] if l > 0 else 0.
+                    up = s[l, j, i] * idh1[l] if l < nl - 1 else 0.
+                    # -Delta^2 (laplacian(a) + Gamma(a) = b) solved for the column, neighbours taken as they are
+                    A[l, l] = 4. + D * D * (lo + up)
+                    if l > 0:
+                        A[l, l - 1] = -D * D * lo
+                    if l < nl - 1:
+                        A[l, l + 1] = -D * D * up
+                    r[l] = -D * D * b[l, j, i] + g[l, j + 1, i + 2] + g[l, j + 1, i] + g[l, j + 2, i + 1] + g[l, j, i + 1]
+                g[:, j + 1, i + 1] = np.linalg.solve(A, r)
+        ghosts()                                     # boundary_level after the sweep: ghosts keep the pre-sweep values during it
+    assert np.abs(g[:, 1:-1, 1:-1] - got).max() <= 1e-11 * np.abs(got).max()
