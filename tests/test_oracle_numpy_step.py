@@ -91,3 +91,79 @@ def test_timesteps_against_numpy_restatement(N, nl, nsteps):
     assert m.L.orc_total_cycles(m.h) == ref.cycles
     for a, b in ((m.get(O.Q), ref.q), (m.get(O.PSI), ref.psi)):
         assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+
+
+class NumpyStochasticModel(NumpyModel):
+    """the -D_STOCHASTIC=1 build (qg_stochastic.h): no J(psi, zeta) in the top layer and no J(psi_l, psi_l+1) anywhere
+    (:35-40, :56-58), relaxation -q/tr_stoch (:44, :68, :91), and advance_qg adds n*dts with a FLOAT dts and a noise
+    field drawn from libc rand() in traversal order (x outer, y inner, layers innermost) at every other call (:117-149)"""
+
+    def __init__(self, kw, psi, sigma, libc):
+        super().__init__(kw, psi)
+        self.sigma, self.libc = sigma, libc
+        self.corrector_step = 0
+        self.noise = np.zeros_like(psi)
+        self.itr = 1. / kw["tr_stoch"]
+
+    def update(self, q, dtmax):
+        dq, dtmax = super().update(q, dtmax)
+        nl, D = self.nl, self.D
+        P = [pad(self.psi[l], -1) for l in range(nl)]
+        zeta = np.array([lap(P[l], D) for l in range(nl)])
+        Z = [pad(zeta[l], -1) for l in range(nl)]
+        jd = [jac(P[l], P[l + 1], D) for l in range(nl - 1)]
+        for l in range(nl):          # take the terms of the deterministic build back out
+            if l > 0:
+                dq[l] -= self.s[l - 1] * (-jd[l - 1]) * self.idh0[l]
+            if l < nl - 1:
+                dq[l] -= self.s[l] * jd[l] * self.idh1[l]
+        dq[0] -= jac(P[0], Z[0], D)
+        dq += -q * self.itr
+        return dq, dtmax
+
+    def generate_noise(self):
+        RAND_MAX = 2147483647
+        n, nl = self.N, self.nl
+        rand = self.libc.rand
+        for i in range(n):
+            for j in range(n):
+                for l in range(nl):
+                    r1 = rand(); r2 = rand()      # gcc evaluates the left operand of the product first
+                    g = np.sqrt(-2. * np.log((float(r1) + 1.) / (float(RAND_MAX) + 2.))) * np.cos(2 * np.pi * r2 / float(RAND_MAX))
+                    self.noise[l, j, i] = self.kw["amp_stoch"] * self.sigma[l, j, i] * g
+
+    def advance(self, q_in, dq, dt):
+        self.corrector_step = (self.corrector_step + 1) % 2
+        dts = np.float32(np.sqrt(dt))
+        if self.corrector_step:
+            self.generate_noise()
+            dts = np.float32(dts / np.sqrt(2))    # float / double -> double, stored in a float
+        return q_in + dq * dt + self.noise * float(dts)
+
+    def step(self):
+        dq, dt = self.update(self.q, self.DT)
+        qp = self.advance(self.q, dq, dt / 2.)
+        dq, _ = self.update(qp, dt)
+        self.q = self.advance(self.q, dq, dt)
+        return dt
+
+
+def test_stochastic_timesteps_against_numpy_restatement():
+    import ctypes as C
+    libc = C.CDLL(None)
+    N, nl, nsteps = 32, 3, 3
+    kw = base_kw(N, nl, stochastic=1, tr_stoch=10., amp_stoch=1.)
+    psi = synth_psi(N, nl)
+    sigma = 1e-3 * (1 + np.arange(nl)[:, None, None]) * np.ones((nl, N, N))
+    m = O.Model(O.make_params(**kw)); m.set_smoother("rb")
+    m.set(O.PSI, psi); m.set(O.SSTOCH, sigma); m.set_const()
+    libc.srand(77)
+    dto = [m.step() for _ in range(nsteps)]
+    ref = NumpyStochasticModel(kw, psi, sigma, libc)
+    libc.srand(77)
+    dtn = [ref.step() for _ in range(nsteps)]
+    assert dto == pytest.approx(dtn, rel=1e-11)
+    noise = m.get(O.NSTOCH)
+    assert np.abs(noise - ref.noise).max() <= 1e-15 * np.abs(noise).max() and np.abs(noise).max() > 0
+    for a, b in ((m.get(O.Q), ref.q), (m.get(O.PSI), ref.psi)):
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
