@@ -88,3 +88,59 @@ def test_tracer_tendency_against_numpy():
             T = pad(tr[f], +1)
             ref = jac(P, T, D) + iPe[nt] * lap(T, D) + ir[nt] * (relax[f] - tr[f])
             assert np.abs(got[f] - ref).max() <= 5e-12 * np.abs(ref).max(), f
+
+
+def test_wavelet_filter_against_numpy():
+    """The multiple-scale filter (qg.h:509-560) with [BASILISK]'s wavelet() / inverse_wavelet() and the sig_lev mask of
+    set_const (qg.h:1057-1090): psi = invertq(q); w_l = psi_l - bilinear(restriction(psi)_l-1) on every level, times the
+    high-pass mask, summed back up; q = comp_q(psi); qof = (q_before - q_after)/dtflt."""
+    from test_oracle_numpy_mg import numpy_solve, prolong, restrict
+    N, nl, afilt, dtflt = 64, 2, 4.0, 0.05
+    kw = base_kw(N, nl, afilt=afilt, dtflt=dtflt)
+    m = O.Model(O.make_params(**kw)); m.set_smoother("rb")
+    psi0 = synth_psi(N, nl)
+    m.set(O.PSI, psi0); m.set_const()
+    q0 = m.get(O.Q)
+    m.wavelet_filter(dtflt)
+    L0 = kw["L0"]
+    depth = int(np.log2(N))
+    dh = np.array(kw["dh"], dtype=float)
+    dhc = 0.5 * (dh[:-1] + dh[1:])
+    idh0 = np.zeros(nl); idh1 = np.zeros(nl)
+    idh1[:-1] = 1. / (dhc * dh[:-1]); idh0[1:] = 1. / (dhc * dh[1:])
+    s = np.array([(fr / kw["Rom"]) ** 2 * np.ones((N, N)) for fr in kw["Fr"]])
+    # sig_filt = min(afilt*Rd, Lfmax) with Rd = 1, restricted; low-pass mask per level, then 1 - mask
+    sf = {depth: np.full((N, N), min(afilt * 1., kw.get("Lfmax", m.p.Lfmax)))}
+    for l in range(depth - 1, -1, -1):
+        sf[l] = restrict(sf[l + 1][None])[0]
+    sl = {}
+    for l in range(depth, -1, -1):
+        n = 1 << l
+        Dl = L0 / n
+        low = np.where(sf[l] > 2 * Dl, 0., np.where(sf[l] > Dl, 1 - (sf[l] - Dl) / Dl, 1.))
+        if l < depth:
+            c = sl[l + 1]
+            flag = c[0::2, 0::2] + c[1::2, 0::2] + c[0::2, 1::2] + c[1::2, 1::2]
+            low = np.where(flag > 0, 1., low)
+        sl[l] = low
+    for l in sl:
+        sl[l] = 1 - sl[l]
+        assert np.abs(sl[l] - m.siglev(l)).max() <= 1e-15, l
+    psi, st, _ = numpy_solve(psi0, q0, s, dh, L0)                      # invertq, warm start
+    lev = {depth: psi}
+    for l in range(depth - 1, -1, -1):
+        lev[l] = restrict(lev[l + 1])
+    w = {0: lev[0].copy()}
+    for l in range(1, depth + 1):
+        w[l] = lev[l] - prolong(lev[l - 1])
+    for l in w:
+        w[l] = w[l] * sl[l][None]
+    rec = w[0]
+    for l in range(1, depth + 1):
+        rec = prolong(rec) + w[l]
+    D = L0 / N
+    q1 = np.array([lap(pad(rec[l], -1), D) for l in range(nl)]) + stretch(rec, list(s), idh0, idh1)
+    assert np.abs(m.get(O.PSI) - rec).max() <= 1e-10 * np.abs(psi0).max()
+    assert np.abs(m.get(O.Q) - q1).max() <= 1e-9 * np.abs(q0).max()
+    assert np.abs(m.get(O.QOF) - (q0 - q1) / dtflt).max() <= 1e-8 * np.abs(q0).max() / dtflt
+    assert 0 < np.abs(q1).max() < np.abs(q0).max()
